@@ -1,0 +1,129 @@
+/* oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY; see oracle.h for scope and the
+ * "parity unpinned" statement).  Plain C11 + OpenMP, compiled with -ffp-contract=off.
+ */
+#include "oracle.h"
+#include "tableaus_gen.h"
+#include <math.h>
+#include <omp.h>
+#include <string.h>
+#include <stddef.h>
+
+/* ---------------------------------------------------------------- fastpow
+ * Restates the approximate power upstream's PI controller uses (SURVEY.md 7.3 "fastpower",
+ * [UPSTREAM-RECALLED] FastPower.jl): compute in Float32, log2 by exponent extraction plus a
+ * rational correction on the mantissa, then 2^x.  Here both halves are spelled out in
+ * IEEE-exact primitive operations so that the CUDA kernels reproduce them bit for bit.
+ *   log2(x) ~= e + t*(a*t + b)/(t + c),  t = mantissa-1 in [0,1)
+ *   2^y     =  2^rint(y) * P6(y - rint(y)),  P6 = degree-6 Taylor of exp(f ln 2), |f|<=1/2
+ */
+static inline float fastlog2f(float x) {
+    uint32_t ix;
+    memcpy(&ix, &x, 4);
+    const int e = (int)(ix >> 23) - 127;
+    const uint32_t im = (ix & 0x007fffffu) | 0x3f800000u;
+    float m;
+    memcpy(&m, &im, 4);
+    const float t = m - 1.0f;
+    const float num = t * fmaf(0.338953f, t, 2.198599f);
+    return (float)e + num / (t + 1.523692f);
+}
+static inline float fastexp2f(float y) {
+    y = fminf(fmaxf(y, -125.0f), 125.0f);
+    const float fi = rintf(y);
+    const float f = y - fi;
+    float p = 1.5403530e-4f;
+    p = fmaf(p, f, 1.3333558e-3f);
+    p = fmaf(p, f, 9.6181291e-3f);
+    p = fmaf(p, f, 5.5504109e-2f);
+    p = fmaf(p, f, 2.4022651e-1f);
+    p = fmaf(p, f, 6.9314718e-1f);
+    p = fmaf(p, f, 1.0f);
+    uint32_t ip;
+    memcpy(&ip, &p, 4);
+    ip += (uint32_t)((int32_t)fi << 23);
+    memcpy(&p, &ip, 4);
+    return p;
+}
+float orc_fastpow(float x, float y) {
+    if (!(x > 0.0f)) return 0.0f;
+    return fastexp2f(y * fastlog2f(x));
+}
+
+/* ---------------------------------------------------------------- Philox4x32-10 (B.9) */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+/* counter = (traj_lo, traj_hi, step, block), key = (seed_lo, seed_hi) -- SURVEY 8(d) cfg 4.
+ * f32: four u32 -> two Box-Muller pairs -> 4 normals; uniforms ((x>>8)+0.5)*2^-24 in (0,1).
+ * f64: two 53-bit uniforms ((x>>11)+0.5)*2^-53 -> one pair -> 2 normals. */
+#define TWO_PI 6.283185307179586476925
+void orc_normals_f32(uint64_t seed, uint64_t traj, uint32_t step, uint32_t block, float z[4]) {
+    const uint32_t ctr[4] = {(uint32_t)traj, (uint32_t)(traj >> 32), step, block};
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t r[4];
+    orc_philox4x32_10(ctr, key, r);
+    for (int h = 0; h < 2; h++) {
+        const float u1 = ((float)(r[2 * h] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+        const float u2 = ((float)(r[2 * h + 1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+        const float rad = sqrtf(-2.0f * logf(u1));
+        const float ang = (float)TWO_PI * u2;
+        z[2 * h] = rad * cosf(ang);
+        z[2 * h + 1] = rad * sinf(ang);
+    }
+}
+void orc_normals_f64(uint64_t seed, uint64_t traj, uint32_t step, uint32_t block, double z[2]) {
+    const uint32_t ctr[4] = {(uint32_t)traj, (uint32_t)(traj >> 32), step, block};
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t r[4];
+    orc_philox4x32_10(ctr, key, r);
+    const uint64_t a = ((uint64_t)r[0] << 32) | r[1], b = ((uint64_t)r[2] << 32) | r[3];
+    const double u1 = ((double)(a >> 11) + 0.5) * 1.1102230246251565404e-16;
+    const double u2 = ((double)(b >> 11) + 0.5) * 1.1102230246251565404e-16;
+    const double rad = sqrt(-2.0 * log(u1));
+    const double ang = TWO_PI * u2;
+    z[0] = rad * cos(ang);
+    z[1] = rad * sin(ang);
+}
+int orc_max_threads(void) { return omp_get_max_threads(); }
+
+/* ---------------------------------------------------------------- f64 instantiation */
+#define REAL double
+#define SUF(x) x##_f64
+#define FMA fma
+#define FABS fabs
+#define FMAX fmax
+#define FMIN fmin
+#define SQRT sqrt
+#define REAL_EPS 2.220446049250313e-16
+#define NORMALS_PER_CALL 2
+#include "oracle_impl.inc"
+#undef REAL
+#undef SUF
+#undef FMA
+#undef FABS
+#undef FMAX
+#undef FMIN
+#undef SQRT
+#undef REAL_EPS
+#undef NORMALS_PER_CALL
+
+/* ---------------------------------------------------------------- f32 instantiation */
+#define REAL float
+#define SUF(x) x##_f32
+#define FMA fmaf
+#define FABS fabsf
+#define FMAX fmaxf
+#define FMIN fminf
+#define SQRT sqrtf
+#define REAL_EPS 1.1920928955078125e-7f
+#define NORMALS_PER_CALL 4
+#include "oracle_impl.inc"

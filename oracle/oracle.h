@@ -1,0 +1,80 @@
+/* oracle.h -- CPU ORACLE for the B200 ensemble ODE/SDE hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library.  The product (libb200ens.so) never links or calls it.
+ *
+ * PARITY UNPINNED: the reference (/root/reference, DifferentialEquations.jl v8.0.3) is a
+ * 32-line re-export metapackage (src/DifferentialEquations.jl:8-9); the arithmetic lives
+ * in un-vendored OrdinaryDiffEq 7 / SciMLBase 3 (Project.toml:7,10,13,18) and Julia is not
+ * installed here.  This file restates the upstream algorithm as specified in SURVEY.md
+ * Appendix A (integrator loop, PI controller, norm, saveat, callbacks, SDE steps) with the
+ * coefficient tables of Appendix B.  It is anchored on what the reference's own tests pin
+ * (test/core.jl:15,18,34,93-95: Success retcodes, first saved value == u0, 11 saveat
+ * points) and on independent truths (closed forms, order conditions, scipy/mpmath
+ * solutions under tests/golden/).
+ */
+#ifndef B2_ORACLE_H
+#define B2_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_NMAX 32
+#define ORC_PMAX 64
+
+enum { ORC_TSIT5 = 1, ORC_VERN7 = 2, ORC_ROSENBROCK23 = 3, ORC_RODAS5 = 4, ORC_RODAS5P = 5,
+       ORC_EM = 6, ORC_SOSRA = 7, ORC_RODAS4 = 8 };
+enum { ORC_RC_DEFAULT = 0, ORC_RC_SUCCESS = 1, ORC_RC_TERMINATED = 2, ORC_RC_MAXITERS = 3,
+       ORC_RC_DTLESSTHANMIN = 4, ORC_RC_UNSTABLE = 5, ORC_RC_DTNAN = 6, ORC_RC_FAILURE = 7 };
+
+typedef struct {
+    int32_t naccept, nreject, nf, nevents;
+} orc_stats;
+
+/* model functions; the void* members are cast to the f32 or f64 signature:
+ *   rhs   (T* du, const T* u, const T* p, T t)
+ *   jac   (T* J /+ row-major n x n +/, const T* u, const T* p, T t)
+ *   tgrad (T* dT, const T* u, const T* p, T t)             optional (NULL = autonomous)
+ *   noise (T* g, const T* u, const T* p, T t)              diagonal noise
+ *   cond  T (const T* u, const T* p, T t)
+ *   affect(T* u, const T* p, T t)
+ */
+typedef struct {
+    int32_t alg, n_state, n_param, adaptive;
+    double t0, t1, dt, abstol, reltol;
+    double dtmin, dtmax, qmin, qmax, gamma, beta1, beta2, qoldinit; /* <0 or NaN => default */
+    int64_t maxiters;
+    int32_t n_save;
+    int32_t noise_injected;   /* 1: dW given [N][nsteps][nvec][n]; 0: Philox4x32-10 */
+    uint64_t seed;
+    int32_t has_event, event_terminate, interp_points;
+    int32_t save_tstops;      /* 1: saveat points are tstops (steps clipped, no interpolation) */
+    void *rhs, *jac, *tgrad, *noise, *cond, *affect;
+} orc_opts;
+
+/* u0 [N][n], p [N][m], saveat [n_save], out_u [N][n_save][n], retcode [N], stats [N] or NULL.
+ * nthreads: OpenMP threads (<=0: all).  Returns 0 or a negative error. */
+int orc_solve_f64(const orc_opts* o, int64_t N, const double* u0, const double* p, const double* saveat,
+                  const double* dW, double* out_u, int32_t* retcode, orc_stats* stats, int nthreads);
+int orc_solve_f32(const orc_opts* o, int64_t N, const float* u0, const float* p, const float* saveat,
+                  const float* dW, float* out_u, int32_t* retcode, orc_stats* stats, int nthreads);
+
+/* built-in hand-written models (oracle/models.c): "lorenz", "robertson", "linear",
+ * "gbm", "lorenz_additive", "net16".  which: "rhs","jac","noise","cond","affect". */
+void* orc_model_fn(const char* model, const char* which, int is_f64);
+
+/* deterministic pow used by the PI controller (restates upstream's approximate FastPower) */
+float orc_fastpow(float x, float y);
+/* Philox4x32-10 */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* normals exactly as the kernels draw them: counter=(traj_lo,traj_hi,step,block) */
+void orc_normals_f32(uint64_t seed, uint64_t traj, uint32_t step, uint32_t block, float z[4]);
+void orc_normals_f64(uint64_t seed, uint64_t traj, uint32_t step, uint32_t block, double z[2]);
+int orc_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,139 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs; never from the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liboracle_b200ens.so")
+
+ALG = {"Tsit5": 1, "Vern7": 2, "Rosenbrock23": 3, "Rodas5": 4, "Rodas5P": 5, "EM": 6, "SOSRA": 7, "Rodas4": 8}
+RC_SUCCESS, RC_TERMINATED, RC_MAXITERS, RC_DTLESSTHANMIN, RC_UNSTABLE, RC_DTNAN = 1, 2, 3, 4, 5, 6
+
+
+class Stats(C.Structure):
+    _fields_ = [("naccept", C.c_int32), ("nreject", C.c_int32), ("nf", C.c_int32), ("nevents", C.c_int32)]
+
+
+class Opts(C.Structure):
+    _fields_ = [
+        ("alg", C.c_int32), ("n_state", C.c_int32), ("n_param", C.c_int32), ("adaptive", C.c_int32),
+        ("t0", C.c_double), ("t1", C.c_double), ("dt", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
+        ("dtmin", C.c_double), ("dtmax", C.c_double), ("qmin", C.c_double), ("qmax", C.c_double),
+        ("gamma", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("qoldinit", C.c_double),
+        ("maxiters", C.c_int64), ("n_save", C.c_int32), ("noise_injected", C.c_int32), ("seed", C.c_uint64),
+        ("has_event", C.c_int32), ("event_terminate", C.c_int32), ("interp_points", C.c_int32),
+        ("save_tstops", C.c_int32),
+        ("rhs", C.c_void_p), ("jac", C.c_void_p), ("tgrad", C.c_void_p), ("noise", C.c_void_p),
+        ("cond", C.c_void_p), ("affect", C.c_void_p),
+    ]
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB) or any(
+        os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(LIB)
+        for f in ("oracle.c", "oracle_impl.inc", "models.c", "oracle.h", "tableaus_gen.h")
+    ):
+        subprocess.check_call(["make", "-C", HERE, "-s"])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+        _lib.orc_model_fn.restype = C.c_void_p
+        _lib.orc_model_fn.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        _lib.orc_fastpow.restype = C.c_float
+        _lib.orc_fastpow.argtypes = [C.c_float, C.c_float]
+        for name in ("orc_solve_f64", "orc_solve_f32"):
+            getattr(_lib, name).restype = C.c_int
+    return _lib
+
+
+def model_fn(model, which, f64):
+    return lib().orc_model_fn(model.encode(), which.encode(), 1 if f64 else 0)
+
+
+def compile_c_model(src, tag, workdir):
+    """Compile emitted C model source (double + float variants) with the oracle's flags."""
+    os.makedirs(workdir, exist_ok=True)
+    cpath = os.path.join(workdir, f"model_{tag}.c")
+    so = os.path.join(workdir, f"model_{tag}.so")
+    open(cpath, "w").write(src)
+    subprocess.check_call(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, cpath, "-lm"])
+    return C.CDLL(so)
+
+
+def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adaptive=True, dtype=np.float64,
+          maxiters=100000, dW=None, seed=0, event=False, terminate=False, interp_points=10, nthreads=0,
+          fns=None, want_stats=True, save_tstops=None, **ctl):
+    """Run the oracle.  model: built-in name, or fns = dict(rhs=ptr, jac=ptr, ...)."""
+    L = lib()
+    f64 = np.dtype(dtype) == np.float64
+    u0 = np.ascontiguousarray(u0, dtype=dtype)
+    p = np.ascontiguousarray(p, dtype=dtype)
+    N, n = u0.shape
+    m = p.shape[1]
+    saveat = np.ascontiguousarray(saveat, dtype=dtype)
+    o = Opts()
+    o.alg = ALG[alg]
+    o.n_state, o.n_param, o.adaptive = n, m, int(adaptive)
+    o.t0, o.t1, o.dt, o.abstol, o.reltol = tspan[0], tspan[1], dt, abstol, reltol
+    for k in ("dtmin", "dtmax", "qmin", "qmax", "gamma", "beta1", "beta2", "qoldinit"):
+        setattr(o, k, ctl.get(k, -1.0))
+    o.maxiters = maxiters
+    o.n_save = len(saveat)
+    o.noise_injected = 0 if dW is None else 1
+    o.seed = seed
+    o.has_event, o.event_terminate, o.interp_points = int(event), int(terminate), interp_points
+    if save_tstops is None:
+        save_tstops = alg in ("Rodas4", "Rodas5", "Rodas5P")
+    o.save_tstops = int(save_tstops)
+    get = (lambda w: (fns or {}).get(w)) if fns is not None else (lambda w: model_fn(model, w, f64))
+    o.rhs, o.jac, o.tgrad, o.noise = get("rhs"), get("jac"), get("tgrad") if fns else None, get("noise")
+    o.cond, o.affect = (get("cond"), get("affect")) if event else (None, None)
+    out = np.empty((N, len(saveat), n), dtype=dtype)
+    rc = np.zeros(N, dtype=np.int32)
+    stats = np.zeros((N, 4), dtype=np.int32) if want_stats else None
+    if dW is not None:
+        dW = np.ascontiguousarray(dW, dtype=dtype)
+    fn = L.orc_solve_f64 if f64 else L.orc_solve_f32
+    vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    err = fn(C.byref(o), C.c_int64(N), vp(u0), vp(p), vp(saveat), vp(dW), vp(out), vp(rc), vp(stats),
+             C.c_int(nthreads))
+    if err != 0:
+        raise RuntimeError(f"oracle error {err}")
+    return out, rc, stats
+
+
+def fastpow(x, y):
+    return float(lib().orc_fastpow(C.c_float(x), C.c_float(y)))
+
+
+def philox(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().orc_philox4x32_10(c, k, o)
+    return list(o)
+
+
+def normals(seed, traj, step, block, f64):
+    L = lib()
+    if f64:
+        z = (C.c_double * 2)()
+        L.orc_normals_f64(C.c_uint64(seed), C.c_uint64(traj), C.c_uint32(step), C.c_uint32(block), z)
+    else:
+        z = (C.c_float * 4)()
+        L.orc_normals_f32(C.c_uint64(seed), C.c_uint64(traj), C.c_uint32(step), C.c_uint32(block), z)
+    return np.array(list(z))

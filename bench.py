@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 ensemble path (BASELINE.json metric).
+
+metric : trajectories/sec, Lorenz parameter-sweep EnsembleProblem, Tsit5 adaptive
+         (abstol 1e-6, reltol 1e-3, dt0 0.1), saveat 0:1:10, 1M trajectories per GPU
+         (BASELINE.json configs[1]; random DiffEqGPU-style parameter sweep).
+step   : one complete ensemble solve of the resident batch (one kernel launch).
+value  : whole-job trajectories/s with u0/p/saveat already resident in HBM (CUDA events on
+         the launching stream, L2 flushed between steps, max over ranks).
+e2e    : the same solve through the public API / C ABI with HOST (pinned) buffers:
+         H2D of u0,p + kernel + D2H of saveat outputs, retcodes and stats inside the timed region.
+roofline: FP32 (or FP64) FMA-issue roofline -- 266 algorithmic flops per attempted Tsit5 step
+         (68n + 6F + 14, n=3, F=8) x attempted steps / kernel time, against the
+         FFMA/DFMA peak measured live by csrc/fma_peak.cu on the same GPU; plus the HBM view.
+cpu_baseline / --impl reference: the CPU oracle (restated EnsembleThreads path, OpenMP over
+         trajectories, all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_STEP = 266.0          # Tsit5 attempted step on Lorenz, SURVEY.md 8(d)
+SAVEAT = np.arange(0.0, 10.5, 1.0)
+TSPAN = (0.0, 10.0)
+ABSTOL, RELTOL, DT0 = 1e-6, 1e-3, 0.1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--trajectories", type=int, default=1_000_000, help="trajectories per GPU")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--sweep", default="random", choices=["random", "ordered"])
+    ap.add_argument("--refill", type=int, default=0)
+    ap.add_argument("--stage", type=int, default=-1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"lorenz_tsit5_adaptive_{a.dtype}_{a.trajectories}traj_per_gpu_{a.sweep}_sweep_saveat0:1:10"
+            f"_abstol1e-6_reltol1e-3")
+
+
+# ------------------------------------------------------------------ CPU oracle timing (baseline / reference arm)
+def oracle_throughput(dtype, sweep, n_target, seconds, seed=0):
+    """Time the CPU oracle on a bounded sample (first n trajectories of the same seeded workload)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    from b200ens import workloads as W
+
+    oracle_py.build()
+    cores = int(oracle_py.lib().orc_max_threads())
+    u0, p = W.lorenz_params(n_target, sweep, seed, dtype)
+    probe = min(n_target, 20000)
+    t = time.perf_counter()
+    oracle_py.solve("lorenz", "Tsit5", u0[:probe], p[:probe], TSPAN, SAVEAT, DT0, abstol=ABSTOL, reltol=RELTOL, dtype=dtype)
+    rate = probe / (time.perf_counter() - t)
+    n = int(max(probe, min(n_target, rate * seconds)))
+    t = time.perf_counter()
+    _, rc, st = oracle_py.solve("lorenz", "Tsit5", u0[:n], p[:n], TSPAN, SAVEAT, DT0, abstol=ABSTOL, reltol=RELTOL, dtype=dtype)
+    el = time.perf_counter() - t
+    steps = int(st[:, 0].sum() + st[:, 1].sum())
+    return {"value": n / el, "unit": "trajectories/s", "cores": cores, "kind": "port",
+            "sample": f"first {n} trajectories of the workload, CPU oracle (C, OpenMP dynamic, -O2, {cores} threads), "
+                      f"{el:.2f} s, {steps / el:.3g} attempted steps/s",
+            "seconds": el, "n": n}
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    dtype = np.float32 if a.dtype == "f32" else np.float64
+    vals = []
+    base = None
+    for i in range(a.warmup + a.steps):
+        r = oracle_throughput(dtype, a.sweep, a.trajectories, max(1.0, a.cpu_seconds / max(1, a.steps)))
+        if i >= a.warmup:
+            vals.append(r)
+        base = r
+    v = float(np.mean([r["value"] for r in vals]))
+    ms = float(np.mean([r["seconds"] for r in vals])) * 1e3
+    line = {
+        "impl": "reference", "metric": "trajectories/sec (Lorenz Tsit5, 1M traj)", "value": v, "unit": "trajectories/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": workload_name(a), "note": "restated CPU baseline (oracle port of the EnsembleThreads path), not Julia"},
+        "cpu_baseline": {"value": v, "unit": "trajectories/s", "cores": base["cores"], "kind": "port", "sample": base["sample"]},
+        "e2e": {"value": v, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ clocks sampling
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [x for x in sm if x >= 0.5 * max(sm)]
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def fma_peak(device, f64):
+    lib = ctypes.CDLL(os.path.join(ROOT, "differentialequations.jl_b200", "csrc", "libb200peak.so"))
+    lib.b200_fma_peak_tflops.restype = ctypes.c_double
+    lib.b200_fma_peak_tflops.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    return float(lib.b200_fma_peak_tflops(device, int(f64), 4096 if not f64 else 2048))
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import b200ens
+    from b200ens import _lib, workloads as W
+
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    f64 = a.dtype == "f64"
+    npdt = np.float64 if f64 else np.float32
+    tdt = torch.float64 if f64 else torch.float32
+    N = a.trajectories
+    n_save = len(SAVEAT)
+
+    # weak scaling: every rank owns N trajectories of the seeded sweep (rank r = shard r of a world*N ensemble)
+    u0_h, p_h = W.lorenz_params(N, a.sweep, seed=rank, dtype=npdt)
+    model = b200ens.build_model(W.lorenz_problem(npdt, TSPAN), b200ens.Tsit5())
+    o = _lib.default_opts()
+    o.adaptive, o.t0, o.t1, o.dt, o.abstol, o.reltol = 1, TSPAN[0], TSPAN[1], DT0, ABSTOL, RELTOL
+    o.refill_threshold, o.stage_outputs = a.refill, a.stage
+    o.device_mask = 1 << dev
+    o.traj_offset = rank * N
+
+    # ---- device-resident leg (value)
+    d_u0 = torch.from_numpy(u0_h).cuda()
+    d_p = torch.from_numpy(p_h).cuda()
+    d_save = torch.from_numpy(SAVEAT.astype(npdt)).cuda()
+    d_out = torch.empty((N, n_save, 3), dtype=tdt, device="cuda")
+    d_rc = torch.zeros(N, dtype=torch.int32, device="cuda")
+    d_st = torch.zeros((N, 4), dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        return model.solve_device(o, dev, stream.cuda_stream, N, d_u0.data_ptr(), d_p.data_ptr(), d_save.data_ptr(),
+                                  n_save, d_out.data_ptr(), d_rc.data_ptr(), d_st.data_ptr(), timed=False)
+
+    for _ in range(a.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    peak_tf = fma_peak(dev, f64)  # measured FMA roofline denominator (also warms the clocks)
+    sampler = ClockSampler(dev)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    for s, e in evs:
+        flush.zero_()          # L2 flush between timed steps (256 MiB > 126 MB L2), outside the events
+        s.record(stream)
+        step_device()
+        e.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    kernel_ms = [s.elapsed_time(e) for s, e in evs]
+    total_ms = float(sum(kernel_ms))
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / a.steps
+    value = world * N / (ms_per_step * 1e-3)
+
+    st = d_st.cpu().numpy()
+    rc = d_rc.cpu().numpy()
+    attempted = int(st[:, 0].sum() + st[:, 1].sum())
+    ok = bool((rc == 1).all())
+    my_ms = float(np.mean(kernel_ms))
+    achieved_tf = FLOPS_PER_STEP * attempted / (my_ms * 1e-3) / 1e12
+    es = 8 if f64 else 4
+    alg_bytes = N * ((3 + 3 + n_save * 3) * es + 4 + 16)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(a.dtype)
+    except Exception:
+        pass
+    roofline = {"bound": "fma_fp64" if f64 else "fma_fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": traffic,
+                "peak_source": "measured live by csrc/fma_peak.cu (FFMA/DFMA register-operand chains); nominal "
+                               + ("37.2" if f64 else "74.4") + " TFLOP/s",
+                "flops_per_step": FLOPS_PER_STEP, "attempted_steps_per_launch": attempted,
+                "steps_per_s": attempted / (my_ms * 1e-3), "kernel_ms": my_ms}
+    roofline_hbm = {"bound": "hbm", "achieved": alg_bytes / (my_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": alg_bytes / (my_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"}
+
+    # ---- end-to-end leg through the public C-ABI call with pinned HOST buffers
+    u0_pin = _lib.pinned_empty(u0_h.shape, npdt)
+    p_pin = _lib.pinned_empty(p_h.shape, npdt)
+    out_pin = _lib.pinned_empty((N, n_save, 3), npdt)
+    rc_pin = _lib.pinned_empty((N,), np.int32)
+    st_pin = _lib.pinned_empty((N, 4), np.int32)
+    u0_pin[:] = u0_h
+    p_pin[:] = p_h
+    e2e_launches = 0
+    for _ in range(2):
+        model.solve(o, u0_pin, p_pin, SAVEAT, out=out_pin, rc=rc_pin, stats=st_pin)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        _, rc2, _, tm = model.solve(o, u0_pin, p_pin, SAVEAT, out=out_pin, rc=rc_pin, stats=st_pin)
+        e2e_launches += tm.launches
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * N * a.steps / e2e_s
+    same = bool(np.array_equal(out_pin[:1000], d_out[:1000].cpu().numpy(), equal_nan=True))
+    h2d = int(u0_h.nbytes + p_h.nbytes + SAVEAT.astype(npdt).nbytes)
+    d2h = int(out_pin.nbytes + 4 * N + 16 * N)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = oracle_throughput(npdt, a.sweep, N, a.cpu_seconds)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "trajectories/sec (Lorenz Tsit5, 1M traj)", "value": value, "unit": "trajectories/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(a), "trajectories_per_gpu": N, "l2": "flushed between timed steps (256 MiB memset)",
+                       "parallelism": f"trajectory ranges sharded over {world} GPU(s), no collective",
+                       "refill_threshold": a.refill, "stage_outputs": a.stage, "all_success": ok,
+                       "regs": model.info()["regs"]},
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "trajectories/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s / a.steps * 1e3, "matches_device_leg": same},
+            "gpu_launches": a.steps + e2e_launches, "clocks": clocks,
+            "trajectory_steps_per_s": world * attempted / (ms_per_step * 1e-3),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

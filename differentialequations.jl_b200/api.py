@@ -1,0 +1,402 @@
+"""Host-side mirror of the reference's problem / ensemble / solve interface for EnsembleB200.
+
+Names follow /root/reference/test/qa/qa.jl (ODEProblem :86, SDEProblem :103, EnsembleProblem
+:50, EnsembleSolution :52, ContinuousCallback :26, ReturnCode :213, remake :183, solve :192,
+Tsit5 :119, Vern7 :126, Rosenbrock23 :98, Rodas5P :97).  `EnsembleB200` is the new sibling of
+EnsembleThreads (:56): same `solve(eprob, alg, ensemblealg; trajectories, saveat, dt, abstol,
+reltol, callback, maxiters)` call, but every trajectory is integrated on the GPUs through
+libb200ens.so.  Semantics the reference's tests pin (test/core.jl): retcode Success (:15),
+first saved value == u0 (:18,:34), saveat=0.1 on (0,1) gives 11 points (:93-95),
+ContinuousCallback(condition(u,t,integrator), affect!(integrator)) (:69-72), remake (:84).
+"""
+import enum
+import time
+
+import numpy as np
+
+from . import _lib, codegen
+from .codegen import terminate_b  # noqa: F401  (re-export: Julia's terminate!)
+
+
+class ReturnCode(enum.IntEnum):
+    Default = 0
+    Success = 1
+    Terminated = 2
+    MaxIters = 3
+    DtLessThanMin = 4
+    Unstable = 5
+    DtNaN = 6
+    Failure = 7
+
+
+# ---------------------------------------------------------------- algorithms
+class _Alg:
+    name = ""
+    adaptive_default = True
+    is_sde = False
+
+    def __repr__(self):
+        return f"{self.name}()"
+
+
+class Tsit5(_Alg):
+    name = "Tsit5"
+
+
+class Vern7(_Alg):
+    name = "Vern7"
+
+
+class Rosenbrock23(_Alg):
+    name = "Rosenbrock23"
+
+
+class Rodas4(_Alg):
+    name = "Rodas4"
+
+
+class Rodas5(_Alg):
+    name = "Rodas5"
+
+
+class Rodas5P(_Alg):
+    name = "Rodas5P"
+
+
+class EM(_Alg):
+    name = "EM"
+    adaptive_default = False
+    is_sde = True
+
+
+class SOSRA(_Alg):
+    name = "SOSRA"
+    adaptive_default = False
+    is_sde = True
+
+
+# ---------------------------------------------------------------- problems
+class ODEProblem:
+    """ODEProblem(f, u0, tspan, p): f(u,p,t) -> du  or in-place f(du,u,p,t) (test/core.jl:22-30)."""
+
+    is_sde = False
+
+    def __init__(self, f, u0, tspan, p=None, g=None):
+        self.f = f
+        self.g = g
+        self.scalar = np.ndim(u0) == 0
+        self.u0 = np.atleast_1d(np.asarray(u0))
+        if self.u0.dtype not in (np.float32, np.float64):
+            self.u0 = self.u0.astype(np.float64)
+        self.tspan = (float(tspan[0]), float(tspan[1]))
+        self.p = np.zeros(0, self.u0.dtype) if p is None else np.atleast_1d(np.asarray(p, dtype=self.u0.dtype))
+
+    def _replace(self, **kw):
+        new = object.__new__(type(self))
+        new.__dict__.update(self.__dict__)
+        if "u0" in kw:
+            u0 = np.atleast_1d(np.asarray(kw["u0"], dtype=self.u0.dtype if np.asarray(kw["u0"]).dtype.kind != "f" else None))
+            if u0.dtype not in (np.float32, np.float64):
+                u0 = u0.astype(np.float64)
+            new.u0 = u0
+        if "p" in kw:
+            new.p = np.atleast_1d(np.asarray(kw["p"], dtype=new.u0.dtype))
+        if "tspan" in kw:
+            new.tspan = (float(kw["tspan"][0]), float(kw["tspan"][1]))
+        bad = set(kw) - {"u0", "p", "tspan"}
+        if bad:
+            raise TypeError(f"remake: unsupported fields {sorted(bad)}")
+        return new
+
+
+class SDEProblem(ODEProblem):
+    """SDEProblem(f, g, u0, tspan, p) with diagonal noise g(u,p,t) (qa.jl:103)."""
+
+    is_sde = True
+
+    def __init__(self, f, g, u0, tspan, p=None):
+        super().__init__(f, u0, tspan, p, g=g)
+
+
+def remake(prob, **kw):
+    """remake(prob; u0, p, tspan) (qa.jl:183, test/core.jl:84)."""
+    return prob._replace(**kw)
+
+
+class ContinuousCallback:
+    """ContinuousCallback(condition, affect!) with condition(u,t,integrator) and affect!(integrator)
+    (test/core.jl:69-72).  Both must be symbolically traceable (they are emitted as CUDA C)."""
+
+    def __init__(self, condition, affect, interp_points=10, save_positions=(False, False)):
+        self.condition = condition
+        self.affect = affect
+        self.interp_points = interp_points
+        if tuple(save_positions) != (False, False):
+            raise NotImplementedError("EnsembleB200 needs save_positions=(false,false) (saveat output is fixed-size)")
+
+
+class EnsembleProblem:
+    """EnsembleProblem(prob; prob_func, output_func, reduction) (qa.jl:50).
+
+    prob_func(prob, i, repeat) -> problem for trajectory i (1-based like Julia); it may only
+    change u0 and p.  Extension (SURVEY 7.3 'host-side prob_func'): `u0s` / `ps` matrices
+    [N, n] can be given directly, skipping N host calls of prob_func."""
+
+    def __init__(self, prob, prob_func=None, output_func=None, reduction=None, u0s=None, ps=None, safetycopy=False):
+        self.prob = prob
+        self.prob_func = prob_func
+        self.output_func = output_func
+        self.reduction = reduction
+        self.u0s = u0s
+        self.ps = ps
+
+
+class EnsembleB200:
+    """The ensemble algorithm: sibling of EnsembleThreads / EnsembleGPUKernel.
+
+    devices: iterable of CUDA device ids (None = all visible); refill_threshold: idle lanes of a
+    warp before it fetches new trajectories (0 = auto); stage_outputs: -1 auto / 0 / 1."""
+
+    def __init__(self, devices=None, refill_threshold=0, stage_outputs=-1, fast_math=False):
+        self.devices = devices
+        self.refill_threshold = refill_threshold
+        self.stage_outputs = stage_outputs
+        self.fast_math = fast_math
+
+
+# ---------------------------------------------------------------- solutions
+class ODESolution:
+    def __init__(self, t, u, retcode, stats, scalar=False):
+        self.t = t
+        self.u = u[:, 0] if scalar else u
+        self.retcode = ReturnCode(int(retcode))
+        self.stats = None if stats is None else dict(zip(("naccept", "nreject", "nf", "nevents"), map(int, stats)))
+
+    def __getitem__(self, i):
+        return self.u[i]
+
+    def __len__(self):
+        return len(self.t)
+
+
+class EnsembleSolution:
+    """EnsembleSolution (qa.jl:52): sol.u[i] / sol[i] is trajectory i's ODESolution.  The raw
+    gathered arrays stay available as u_array [N, n_save, n_state], retcodes [N], stats [N,4]."""
+
+    def __init__(self, t, u_array, retcodes, stats, elapsed, timing, scalar=False):
+        self.t = t
+        self.u_array = u_array
+        self.retcodes = retcodes
+        self.stats = stats
+        self.elapsedTime = elapsed
+        self.timing = timing
+        self.converged = bool(np.all(retcodes == ReturnCode.Success))
+        self._scalar = scalar
+
+    def __len__(self):
+        return self.u_array.shape[0]
+
+    def __getitem__(self, i):
+        return ODESolution(self.t, self.u_array[i], self.retcodes[i], None if self.stats is None else self.stats[i],
+                           self._scalar)
+
+    @property
+    def u(self):
+        return _LazySeq(self)
+
+
+class _LazySeq:
+    def __init__(self, es):
+        self._es = es
+
+    def __len__(self):
+        return len(self._es)
+
+    def __getitem__(self, i):
+        return self._es[i]
+
+    def __iter__(self):
+        return (self._es[i] for i in range(len(self._es)))
+
+
+# ---------------------------------------------------------------- model building (codegen + NVRTC)
+_model_cache = {}
+
+
+def build_model(prob, alg, callback=None, fast_math=False):
+    """Trace prob.f (and g / callback), emit CUDA C, JIT it for sm_100a.  Cached per function objects."""
+    n, m = prob.u0.shape[0], prob.p.shape[0]
+    dtype = prob.u0.dtype
+    key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math)
+    hit = _model_cache.get(key)
+    if hit is not None and hit[1] is prob.f:
+        return hit[0]
+    exprs, usyms, _, tsym = codegen.trace_vector_fn(prob.f, n, m)
+    srcs = {"rhs_src": codegen.emit_rhs(exprs)}
+    if alg.name in ("Rosenbrock23", "Rodas4", "Rodas5", "Rodas5P"):
+        srcs["jac_src"] = codegen.emit_jac(exprs, usyms)
+        srcs["tgrad_src"] = codegen.emit_tgrad(exprs, tsym)
+    if alg.is_sde:
+        if not prob.is_sde:
+            raise TypeError(f"{alg.name} needs an SDEProblem")
+        gex, _, _, _ = codegen.trace_vector_fn(prob.g, n, m)
+        if alg.name == "SOSRA" and any(e.has(*usyms) for e in gex):
+            raise ValueError("SOSRA is for additive noise only: g(u,p,t) must not depend on u (SURVEY A.9)")
+        srcs["noise_src"] = codegen.emit_noise(gex)
+    terminate = False
+    if callback is not None:
+        srcs["condition_src"], srcs["affect_src"], terminate = codegen.emit_callback(callback, n, m)
+    model = _lib.Model(n, m, dtype, alg.name, name=getattr(prob.f, "__name__", "model"), fast_math=fast_math, **srcs)
+    model.sources = srcs
+    model.event_terminate = terminate
+    _model_cache[key] = (model, prob.f)
+    return model
+
+
+def _saveat_array(saveat, tspan, dtype):
+    t0, t1 = tspan
+    if saveat is None:
+        return np.array([t0, t1], dtype=dtype)
+    if np.ndim(saveat) == 0:
+        step = float(saveat)
+        k = int(np.floor((t1 - t0) / step * (1 + 1e-12) + 1e-9))
+        ts = t0 + step * np.arange(k + 1)
+        ts[np.abs(ts - t1) < 1e-12 * max(1.0, abs(t1))] = t1
+        if ts[-1] < t1:
+            ts = np.append(ts, t1)
+        return ts.astype(dtype)
+    ts = np.asarray(saveat, dtype=np.float64)
+    if ts.size and (np.any(np.diff(ts) <= 0) or ts[0] < t0 or ts[-1] > t1):
+        raise ValueError("saveat must be strictly increasing and inside tspan")
+    return ts.astype(dtype)
+
+
+def _pack(eprob, N, dtype):
+    """Run prob_func on the host (as EnsembleThreads / EnsembleGPUKernel do) -> u0 [N,n], p [N,m]."""
+    prob = eprob.prob
+    n, m = prob.u0.shape[0], prob.p.shape[0]
+    if eprob.u0s is not None or eprob.ps is not None:
+        u0 = np.broadcast_to(prob.u0, (N, n)) if eprob.u0s is None else np.asarray(eprob.u0s).reshape(N, n)
+        p = np.broadcast_to(prob.p, (N, m)) if eprob.ps is None else np.asarray(eprob.ps).reshape(N, m)
+        return u0, p
+    u0 = np.empty((N, n), dtype=dtype)
+    p = np.empty((N, m), dtype=dtype)
+    if eprob.prob_func is None:
+        u0[:] = prob.u0
+        p[:] = prob.p
+        return u0, p
+    for i in range(N):
+        pi = eprob.prob_func(prob, i + 1, 1)
+        if pi.f is not prob.f or pi.tspan != prob.tspan:
+            raise ValueError("EnsembleB200: prob_func may only change u0 and p (one compiled kernel per ensemble)")
+        u0[i] = pi.u0
+        p[i] = pi.p
+    return u0, p
+
+
+def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, abstol=None, reltol=None,
+          adaptive=None, callback=None, maxiters=None, save_everystep=False, dense=False, seed=0, dW=None,
+          save_tstops=None, **kwargs):
+    """solve(eprob, alg, EnsembleB200(); trajectories, saveat, dt, abstol, reltol, ...) -> EnsembleSolution.
+    A plain ODEProblem/SDEProblem is solved as a one-trajectory ensemble and returns its ODESolution."""
+    if kwargs:
+        raise TypeError(f"solve: unsupported keyword arguments {sorted(kwargs)}")
+    if save_everystep or dense:
+        raise NotImplementedError("EnsembleB200 saves at `saveat` points only (fixed-size output); "
+                                  "save_everystep/dense=true are not supported")
+    single = not isinstance(prob, EnsembleProblem)
+    eprob = EnsembleProblem(prob) if single else prob
+    if single:
+        trajectories = 1
+    if ensemblealg is None:
+        ensemblealg = EnsembleB200()
+    if not isinstance(ensemblealg, EnsembleB200):
+        raise TypeError("this back-end only implements EnsembleB200()")
+    if trajectories is None:
+        raise TypeError("solve(::EnsembleProblem, ...) needs `trajectories`")
+    base = eprob.prob
+    N = int(trajectories)
+    dtype = base.u0.dtype
+    if adaptive is None:
+        adaptive = alg.adaptive_default
+    if alg.is_sde and adaptive:
+        raise NotImplementedError("adaptive SDE stepping (RSwM) is not implemented; use a fixed dt")
+    if dt is None:
+        if not adaptive:
+            raise ValueError("fixed-step solves need dt")
+        dt = _initial_dt(base, alg, abstol, reltol)
+    model = build_model(base, alg, callback, ensemblealg.fast_math)
+    ts = _saveat_array(saveat, base.tspan, dtype)
+    t_pack = time.perf_counter()
+    u0, p = _pack(eprob, N, dtype)
+    t_pack = time.perf_counter() - t_pack
+
+    o = _lib.default_opts()
+    o.adaptive = int(bool(adaptive))
+    o.t0, o.t1, o.dt = base.tspan[0], base.tspan[1], float(dt)
+    if abstol is not None:
+        o.abstol = float(abstol)
+    if reltol is not None:
+        o.reltol = float(reltol)
+    if maxiters is not None:
+        o.maxiters = int(maxiters)
+    o.seed = int(seed)
+    o.noise_injected = 0 if dW is None else 1
+    if callback is not None:
+        o.event_terminate = int(model.event_terminate)
+        o.interp_points = int(callback.interp_points)
+    if save_tstops is not None:
+        o.save_tstops = int(save_tstops)
+    if ensemblealg.devices is not None:
+        mask = 0
+        for g in ensemblealg.devices:
+            mask |= 1 << int(g)
+        o.device_mask = mask
+    o.refill_threshold = int(ensemblealg.refill_threshold)
+    o.stage_outputs = int(ensemblealg.stage_outputs)
+
+    t_solve = time.perf_counter()
+    out, rc, stats, tm = model.solve(o, u0, p, ts, dW=dW)
+    elapsed = time.perf_counter() - t_solve
+    timing = tm.asdict()
+    timing["prob_func_s"] = t_pack
+    sol = EnsembleSolution(ts, out, rc, stats, elapsed, timing, scalar=base.scalar)
+    if single:
+        return sol[0]
+    if eprob.output_func is not None:
+        outs = []
+        for i in range(N):
+            val, rerun = eprob.output_func(sol[i], i + 1)
+            if rerun:
+                raise NotImplementedError("output_func requested rerun; not supported by EnsembleB200")
+            outs.append(val)
+        if eprob.reduction is not None:
+            outs, _ = eprob.reduction([], outs, range(1, N + 1))
+        sol.outputs = outs
+    return sol
+
+
+def _initial_dt(prob, alg, abstol, reltol):
+    """Hairer-Norsett-Wanner initial step evaluated ONCE on the base problem on the host and used
+    for every trajectory.  (Upstream evaluates it per trajectory; the north-star signature passes dt.)"""
+    import sympy as sp
+
+    n, m = prob.u0.shape[0], prob.p.shape[0]
+    exprs, usyms, psyms, tsym = codegen.trace_vector_fn(prob.f, n, m)
+    fn = sp.lambdify([usyms, psyms, tsym], exprs, "math")
+    order = {"Tsit5": 5, "Vern7": 7, "Rosenbrock23": 2, "Rodas4": 4}.get(alg.name, 5)
+    abstol = 1e-6 if abstol is None else abstol
+    reltol = 1e-3 if reltol is None else reltol
+    u0 = prob.u0.astype(np.float64)
+    pp = list(prob.p.astype(np.float64)) + [0.0]
+    t0, t1 = prob.tspan
+    f0 = np.array(fn(list(u0), pp, t0), dtype=np.float64)
+    sk = abstol + np.abs(u0) * reltol
+    nrm = lambda x: float(np.sqrt(np.mean(x * x)))
+    d0, d1 = nrm(u0 / sk), nrm(f0 / sk)
+    dt0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+    f1 = np.array(fn(list(u0 + dt0 * f0), pp, t0 + dt0), dtype=np.float64)
+    d2 = nrm((f1 - f0) / sk) / dt0
+    dmax = max(d1, d2)
+    dt1 = max(1e-6, 1e-3 * dt0) if dmax <= 1e-15 else 10.0 ** (-(2 + np.log10(dmax)) / order)
+    return min(100 * dt0, dt1, t1 - t0)

@@ -1,0 +1,218 @@
+"""RHS / Jacobian / noise / callback code generation: symbolic form -> CUDA C.
+
+Stand-in for the Symbolics/ModelingToolkit front-end the north star names (SURVEY.md 2.2
+E7; README hyperlink /root/reference/README.md:54): the problem's functions are traced
+with sympy symbols (as Symbolics traces a Julia `f`), the analytic Jacobian is derived
+symbolically, and each function is emitted as a `__device__` CUDA-C function with the
+fixed names include/b200ens.h documents (b2_rhs, b2_jac, b2_tgrad, b2_noise,
+b2_condition, b2_affect).  The same text compiles as host C++ (tests build it with g++ for
+the CPU oracle) given `#define __device__` -- nothing in it is CUDA-specific.
+
+Numerical contract: literals are emitted as `(real)(<17 digits>)`, integer powers up to 4
+are expanded to products, nothing is contracted into FMAs (the kernels are compiled with
+--fmad=false), so the expression tree is the same on the GPU and in the oracle.
+"""
+import inspect
+
+import sympy as sp
+from sympy.printing.c import C99CodePrinter
+
+
+class _RealPrinter(C99CodePrinter):
+    """C printer that keeps all arithmetic in `real` (float or double)."""
+
+    def _print_Float(self, expr):
+        return "(real)(%.17g)" % float(expr)
+
+    def _print_Integer(self, expr):
+        return "(real)(%d)" % int(expr)
+
+    def _print_Rational(self, expr):
+        return "((real)(%d) / (real)(%d))" % (expr.p, expr.q)
+
+    def _print_Pow(self, expr):
+        b, e = expr.base, expr.exp
+        if e.is_Integer and 2 <= int(e) <= 4:
+            bs = self.parenthesize(b, 50)  # PRECEDENCE["Mul"]
+            return "(" + " * ".join([bs] * int(e)) + ")"
+        if e == -1:
+            return "((real)(1) / %s)" % self.parenthesize(b, 100)
+        if e.is_Integer and -4 <= int(e) <= -2:
+            bs = self.parenthesize(b, 50)
+            return "((real)(1) / (" + " * ".join([bs] * (-int(e))) + "))"
+        if e == sp.Rational(1, 2):
+            return "sqrt(%s)" % self._print(b)
+        return "pow(%s, %s)" % (self._print(b), self._print(e))
+
+    def _print_Symbol(self, expr):
+        return expr.name
+
+
+_printer = _RealPrinter({"math_macros": {}})
+
+
+def _c(expr):
+    return _printer.doprint(sp.sympify(expr))
+
+
+class _Vec:
+    """Indexable vector of symbols standing for a device array (u[i], p[i], du[i])."""
+
+    def __init__(self, name, n):
+        self.syms = [sp.Symbol(f"{name}[{i}]", real=True) for i in range(n)]
+        self.vals = list(self.syms)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return self.vals[i]
+        return self.vals[i]
+
+    def __setitem__(self, i, v):
+        self.vals[i] = sp.sympify(v)
+
+    def __len__(self):
+        return len(self.vals)
+
+    def __iter__(self):
+        return iter(self.vals)
+
+
+def _nparams(fn):
+    try:
+        return len(inspect.signature(fn).parameters)
+    except (TypeError, ValueError):
+        return None
+
+
+def trace_vector_fn(fn, n_state, n_param):
+    """Trace f(u,p,t) -> sequence  or  f!(du,u,p,t) (in place) into sympy expressions."""
+    u, p, t = _Vec("u", n_state), _Vec("p", max(n_param, 1)), sp.Symbol("t", real=True)
+    if _nparams(fn) == 4:
+        du = _Vec("du", n_state)
+        du.vals = [sp.Integer(0)] * n_state
+        fn(du, u, p, t)
+        out = list(du.vals)
+    else:
+        out = fn(u, p, t)
+        if not hasattr(out, "__len__"):
+            out = [out]
+        out = [sp.sympify(x) for x in out]
+    if len(out) != n_state:
+        raise ValueError(f"function returned {len(out)} components for n_state={n_state}")
+    return out, u.syms, p.syms, t
+
+
+def _emit_body(assign_targets, exprs, cse=True):
+    lines = []
+    if cse:
+        repl, red = sp.cse(list(exprs), symbols=sp.numbered_symbols("x"), order="none")
+    else:
+        repl, red = [], list(exprs)
+    for s, e in repl:
+        lines.append(f"    const real {s} = {_c(e)};")
+    for tgt, e in zip(assign_targets, red):
+        lines.append(f"    {tgt} = {_c(e)};")
+    return "\n".join(lines)
+
+
+_SIG = "__device__ __forceinline__ void {name}(real* __restrict__ {out}, const real* __restrict__ u, const real* __restrict__ p, const real t)"
+
+
+def emit_rhs(exprs):
+    n = len(exprs)
+    body = _emit_body([f"du[{i}]" for i in range(n)], exprs)
+    return _SIG.format(name="b2_rhs", out="du") + " {\n    (void)p; (void)t;\n" + body + "\n}\n"
+
+
+def emit_jac(exprs, usyms):
+    n = len(exprs)
+    J = sp.Matrix(exprs).jacobian(sp.Matrix(usyms))
+    entries = [J[i, j] for i in range(n) for j in range(n)]
+    body = _emit_body([f"J[{k}]" for k in range(n * n)], entries)
+    return _SIG.format(name="b2_jac", out="J") + " {\n    (void)p; (void)t;\n" + body + "\n}\n"
+
+
+def emit_tgrad(exprs, t):
+    d = [sp.diff(e, t) for e in exprs]
+    if all(x == 0 for x in d):
+        return None
+    body = _emit_body([f"dT[{i}]" for i in range(len(d))], d)
+    return _SIG.format(name="b2_tgrad", out="dT") + " {\n    (void)p; (void)t;\n" + body + "\n}\n"
+
+
+def emit_noise(exprs):
+    body = _emit_body([f"g[{i}]" for i in range(len(exprs))], exprs)
+    return _SIG.format(name="b2_noise", out="g") + " {\n    (void)u; (void)p; (void)t;\n" + body + "\n}\n"
+
+
+class _TraceIntegrator:
+    """What `condition(u,t,integrator)` / `affect!(integrator)` see while being traced."""
+
+    def __init__(self, n_state, n_param):
+        self.u = _Vec("u", n_state)
+        self.p = _Vec("p", max(n_param, 1)).syms
+        self.t = sp.Symbol("t", real=True)
+        self.terminated = False
+
+
+def terminate_b(integrator):
+    """Julia's terminate!(integrator)."""
+    integrator.terminated = True
+
+
+def emit_callback(cb, n_state, n_param):
+    """ContinuousCallback(condition, affect!) -> (condition_src, affect_src, terminate)."""
+    integ = _TraceIntegrator(n_state, n_param)
+    try:
+        g = cb.condition(integ.u, integ.t, integ)
+    except Exception as e:  # not expressible symbolically -> reject (no CPU fallback), SURVEY 7.3
+        raise NotImplementedError(
+            "ContinuousCallback condition is not symbolically traceable; EnsembleB200 only accepts "
+            "callbacks that can be emitted as CUDA C") from e
+    cond_src = ("__device__ __forceinline__ real b2_condition(const real* __restrict__ u, const real* __restrict__ p, "
+                "const real t) {\n    (void)u; (void)p; (void)t;\n    return " + _c(g) + ";\n}\n")
+    integ2 = _TraceIntegrator(n_state, n_param)
+    try:
+        cb.affect(integ2)
+    except Exception as e:
+        raise NotImplementedError("ContinuousCallback affect! is not symbolically traceable") from e
+    lines = []
+    changed = [(i, v) for i, (s, v) in enumerate(zip(integ2.u.syms, integ2.u.vals)) if v != s]
+    # evaluate all right-hand sides before assigning (affect! sees the pre-event state)
+    for i, v in changed:
+        lines.append(f"    const real n{i} = {_c(v)};")
+    for i, _ in changed:
+        lines.append(f"    u[{i}] = n{i};")
+    aff_src = ("__device__ __forceinline__ void b2_affect(real* __restrict__ u, const real* __restrict__ p, "
+               "const real t) {\n    (void)u; (void)p; (void)t;\n" + "\n".join(lines) + "\n}\n")
+    return cond_src, aff_src, bool(integ2.terminated)
+
+
+HOST_PRELUDE = """// host build of emitted model code (tests: compiled with g++ for the CPU oracle)
+#include <cmath>
+using std::sqrt; using std::pow; using std::sin; using std::cos; using std::exp; using std::log; using std::fabs;
+#define __device__
+#define __forceinline__ inline
+"""
+
+
+def host_wrapper_source(sources, names=("b2_rhs", "b2_jac", "b2_tgrad", "b2_noise", "b2_condition", "b2_affect")):
+    """C++ translation unit exposing the emitted functions for float and double with C linkage
+    (oracle side of the parity tests)."""
+    parts = [HOST_PRELUDE]
+    for suf, ty in (("f32", "float"), ("f64", "double")):
+        parts.append(f"namespace ns_{suf} {{\ntypedef {ty} real;\n" + "\n".join(s for s in sources if s) + "\n}\n")
+    parts.append('extern "C" {\n')
+    present = "\n".join(s for s in sources if s)
+    for suf, ty in (("f32", "float"), ("f64", "double")):
+        for nm in names:
+            if nm + "(" not in present:
+                continue
+            if nm == "b2_condition":
+                parts.append(f"{ty} {nm}_{suf}(const {ty}* u, const {ty}* p, {ty} t) {{ return ns_{suf}::{nm}(u, p, t); }}\n")
+            elif nm == "b2_affect":
+                parts.append(f"void {nm}_{suf}({ty}* u, const {ty}* p, {ty} t) {{ ns_{suf}::{nm}(u, p, t); }}\n")
+            else:
+                parts.append(f"void {nm}_{suf}({ty}* o, const {ty}* u, const {ty}* p, {ty} t) {{ ns_{suf}::{nm}(o, u, p, t); }}\n")
+    parts.append("}\n")
+    return "".join(parts)

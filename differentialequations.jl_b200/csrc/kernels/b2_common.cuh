@@ -1,0 +1,151 @@
+// b2_common.cuh -- shared device code of the B200 ensemble kernels (sm_100a, NVRTC-compiled).
+//
+// One trajectory per thread, state in registers.  The generated prelude defines
+//   B2_F64 (0/1), B2_NSTATE, B2_NPARAM, B2_ALG, B2_HAS_JAC/TGRAD/NOISE/EVENT
+// and the model's device functions b2_rhs / b2_jac / ... before including this file.
+//
+// Arithmetic contract (mirrors, but does not share code with, oracle/oracle_impl.inc):
+// every multiply-add that is meant to fuse is an explicit b2_fma(); NVRTC runs with
+// --fmad=false so nothing else contracts.  Linear combinations accumulate left to right:
+//   s = c1*x1; s = fma(c2,x2,s); ...   stage argument U = fma(dt, s, uprev).
+#pragma once
+
+#if B2_F64
+typedef double real;
+#define B2_EPS 2.220446049250313e-16
+#else
+typedef float real;
+#define B2_EPS 1.1920928955078125e-7f
+#endif
+
+#define B2_N B2_NSTATE
+#define B2_NPA (B2_NPARAM > 0 ? B2_NPARAM : 1)
+#define B2_FULL 0xffffffffu
+
+// retcodes (include/b200ens.h enum b200ens_retcode); 0 doubles as "still running"
+#define B2_RC_SUCCESS 1
+#define B2_RC_TERMINATED 2
+#define B2_RC_MAXITERS 3
+#define B2_RC_DTLESSTHANMIN 4
+#define B2_RC_UNSTABLE 5
+#define B2_RC_DTNAN 6
+
+struct B2Stats {
+    int naccept, nreject, nf, nevents;
+};
+
+// Kernel argument block; one layout for f32 and f64 (scalars travel as double).
+struct B2Args {
+    const void* u0;       // [N][n_state]
+    const void* p;        // [N][n_param]
+    const void* saveat;   // [n_save]
+    const void* dW;       // injected increments or null
+    void* out_u;          // [N][n_save][n_state]
+    int* retcode;         // [N]
+    B2Stats* stats;       // [N] or null
+    unsigned long long* work_counter;
+    long long N;
+    long long maxiters;
+    long long nsteps_noise;
+    unsigned long long seed;
+    unsigned long long traj_offset;
+    double t0, t1, dt, abstol, reltol, dtmin, dtmax, qmin, qmax, gamma, beta1, beta2, qoldinit;
+    int n_save, adaptive, refill_threshold, stage_stride;
+    int noise_injected, event_terminate, interp_points, save_tstops;
+};
+
+__device__ __forceinline__ float b2_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double b2_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float b2_abs(float a) { return fabsf(a); }
+__device__ __forceinline__ double b2_abs(double a) { return fabs(a); }
+__device__ __forceinline__ float b2_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double b2_max(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float b2_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double b2_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float b2_sqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double b2_sqrt(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ bool b2_isnan(real a) { return a != a; }
+
+// ---- deterministic float power for the PI controller (same primitive sequence as the
+// oracle's orc_fastpow; restates upstream's approximate FastPower)
+__device__ __forceinline__ float b2_fastlog2(float x) {
+    const unsigned ix = __float_as_uint(x);
+    const int e = (int)(ix >> 23) - 127;
+    const float m = __uint_as_float((ix & 0x007fffffu) | 0x3f800000u);
+    const float t = __fsub_rn(m, 1.0f);
+    const float num = __fmul_rn(t, __fmaf_rn(0.338953f, t, 2.198599f));
+    return __fadd_rn((float)e, __fdiv_rn(num, __fadd_rn(t, 1.523692f)));
+}
+__device__ __forceinline__ float b2_fastexp2(float y) {
+    y = fminf(fmaxf(y, -125.0f), 125.0f);
+    const float fi = rintf(y);
+    const float f = __fsub_rn(y, fi);
+    float p = 1.5403530e-4f;
+    p = __fmaf_rn(p, f, 1.3333558e-3f);
+    p = __fmaf_rn(p, f, 9.6181291e-3f);
+    p = __fmaf_rn(p, f, 5.5504109e-2f);
+    p = __fmaf_rn(p, f, 2.4022651e-1f);
+    p = __fmaf_rn(p, f, 6.9314718e-1f);
+    p = __fmaf_rn(p, f, 1.0f);
+    return __uint_as_float(__float_as_uint(p) + (unsigned)((int)fi << 23));
+}
+__device__ __forceinline__ float b2_fastpow(float x, float y) {
+    if (!(x > 0.0f)) return 0.0f;
+    return b2_fastexp2(__fmul_rn(y, b2_fastlog2(x)));
+}
+
+// ---- per-lane output sink: shared-memory staging (flushed coalesced by the whole warp
+// when the lane retires) or direct global stores for outputs too large to stage.
+struct B2Sink {
+    real* stage;       // this lane's staging row (null in direct mode)
+    real* gout;        // out_u as real*
+    long long base;    // idx * n_save * B2_N
+    __device__ __forceinline__ void put(int si, const real (&v)[B2_N]) const {
+        if (stage) {
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) stage[si * B2_N + i] = v[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) gout[base + (long long)si * B2_N + i] = v[i];
+        }
+    }
+    __device__ __forceinline__ void fill(int si, int n_save, real v) const {
+        for (; si < n_save; si++) {
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) {
+                if (stage) stage[si * B2_N + i] = v;
+                else gout[base + (long long)si * B2_N + i] = v;
+            }
+        }
+    }
+};
+
+// Warp-cooperative flush of the staged outputs of every lane in `dirty_mask`: all 32 lanes
+// copy one retired lane's row at a time -> coalesced 128-byte global stores.
+__device__ __forceinline__ void b2_flush(unsigned dirty_mask, const real* warp_stage, int stride, real* gout,
+                                         long long idx, int out_per_traj, unsigned lane) {
+    __syncwarp();
+    while (dirty_mask) {
+        const int L = __ffs(dirty_mask) - 1;
+        dirty_mask &= dirty_mask - 1;
+        const long long iL = __shfl_sync(B2_FULL, idx, L);
+        const real* src = warp_stage + (size_t)L * stride;
+        real* dst = gout + iL * (long long)out_per_traj;
+        for (int j = lane; j < out_per_traj; j += 32) dst[j] = src[j];
+    }
+    __syncwarp();
+}
+
+// Warp-aggregated work fetch: one atomicAdd per warp hands consecutive trajectory indices
+// to the idle lanes (in lane order).  Returns this lane's index or -1.
+__device__ __forceinline__ long long b2_fetch(unsigned idle_mask, unsigned long long* counter, long long N,
+                                              unsigned lane, bool& exhausted) {
+    const int cnt = __popc(idle_mask);
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, (unsigned long long)cnt);
+    base = __shfl_sync(B2_FULL, base, 0);
+    if ((long long)base + cnt >= N) exhausted = true;
+    if (!((idle_mask >> lane) & 1u)) return -1;
+    const long long my = (long long)base + __popc(idle_mask & ((1u << lane) - 1u));
+    return my < N ? my : -1;
+}

@@ -1,0 +1,30 @@
+// b2_entry.cuh -- the one __global__ entry point of a compiled model: picks the stepper for
+// B2_ALG (include/b200ens.h enum b200ens_alg) and runs the persistent ensemble driver.
+#pragma once
+#include "b2_common.cuh"
+
+#if B2_ALG == 1 || B2_ALG == 2
+#include "b2_erk.cuh"
+#include "b2_ode_driver.cuh"
+#elif B2_ALG == 3 || B2_ALG == 4 || B2_ALG == 5 || B2_ALG == 8
+#include "b2_rosenbrock.cuh"
+#include "b2_ode_driver.cuh"
+#elif B2_ALG == 6 || B2_ALG == 7
+#include "b2_sde.cuh"
+#else
+#error "unknown B2_ALG"
+#endif
+
+extern "C" __global__ void __launch_bounds__(B2_BLOCK) b2_ensemble_kernel(const __grid_constant__ B2Args a) {
+#if B2_ALG == 1
+    b2_ode_driver<B2Tsit5>(a);
+#elif B2_ALG == 2
+    b2_ode_driver<B2Vern7>(a);
+#elif B2_ALG == 3
+    b2_ode_driver<B2Ros23>(a);
+#elif B2_ALG == 4 || B2_ALG == 5 || B2_ALG == 8
+    b2_ode_driver<B2Rodas>(a);
+#else
+    b2_sde_driver<B2_ALG>(a);
+#endif
+}

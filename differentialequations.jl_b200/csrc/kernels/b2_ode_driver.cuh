@@ -1,0 +1,277 @@
+// b2_ode_driver.cuh -- the persistent one-trajectory-per-thread ODE ensemble kernel body.
+//
+// Replaces, for the whole ensemble at once, the per-trajectory integrator loop that
+// EnsembleThreads runs on the CPU (SciMLBase.__solve/solve_batch/batch_func ->
+// OrdinaryDiffEq.solve!: loopheader!/perform_step!/loopfooter!/savevalues!/handle_callbacks!;
+// call sites /root/reference/test/core.jl:14,32,47,72,93; semantics SURVEY.md A.1-A.8).
+//
+// Structure: every warp is persistent.  Each outer iteration a lane performs ONE step
+// attempt of its trajectory.  Lanes whose trajectory finished are parked; when at least
+// `refill_threshold` lanes of a warp are parked (warp vote), the warp flushes the parked
+// lanes' staged saveat outputs with coalesced stores and refills them from a global atomic
+// work counter, so SIMT lanes stay busy although step counts differ 10x between
+// trajectories (0.54 warp efficiency without refill).
+#pragma once
+#include "b2_common.cuh"
+
+template <class Alg>
+__device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
+    extern __shared__ __align__(16) unsigned char b2_smem[];
+    const unsigned lane = threadIdx.x & 31u;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int stride = a.stage_stride;
+    real* const warp_stage = reinterpret_cast<real*>(b2_smem) + (size_t)warp_in_block * 32 * stride;
+    real* const gout = reinterpret_cast<real*>(a.out_u);
+    const real* const gu0 = reinterpret_cast<const real*>(a.u0);
+    const real* const gp = reinterpret_cast<const real*>(a.p);
+    const real* const gsave = reinterpret_cast<const real*>(a.saveat);
+    const int n_save = a.n_save;
+    const int out_per_traj = n_save * B2_N;
+
+    const real t0 = (real)a.t0, t1 = (real)a.t1, dt_user = (real)a.dt;
+    const real abstol = (real)a.abstol, reltol = (real)a.reltol;
+    const real qmax = (real)a.qmax, qmin = (real)a.qmin, gam = (real)a.gamma;
+    const real inv_qmax = (real)1 / qmax, inv_qmin = (real)1 / qmin;
+    const real qoldinit = (real)a.qoldinit, dtmax = (real)a.dtmax, dtmin = (real)a.dtmin;
+    const float beta1 = (float)a.beta1, beta2 = (float)a.beta2;
+    const bool adaptive = a.adaptive != 0;
+    const bool save_tstops = a.save_tstops != 0;
+
+    Alg alg;
+    real u[B2_N], p[B2_NPA];
+    real t = t0, dt = dt_user, qold = qoldinit;
+    long long idx = -1, iter = 0;
+    int si = 0, naccept = 0, nreject = 0, nf = 0, nevents = 0;
+    bool active = false, dirty = false, exhausted = false;
+#if B2_HAS_EVENT
+    bool just_fired = false;
+    const int ip = a.interp_points;
+#endif
+    B2Sink sink;
+    sink.stage = stride ? warp_stage + (size_t)lane * stride : nullptr;
+    sink.gout = gout;
+    sink.base = 0;
+
+    for (;;) {
+        // ---------------- retire / refill (warp-uniform control flow)
+        const unsigned idle = __ballot_sync(B2_FULL, !active);
+        if (idle) {
+            const bool all_idle = idle == B2_FULL;
+            if (exhausted ? all_idle : (__popc(idle) >= a.refill_threshold || all_idle)) {
+                if (stride) {
+                    const unsigned dmask = __ballot_sync(B2_FULL, dirty);
+                    b2_flush(dmask, warp_stage, stride, gout, idx, out_per_traj, lane);
+                    dirty = false;
+                }
+                if (!exhausted) {
+                    const long long my = b2_fetch(idle, a.work_counter, a.N, lane, exhausted);
+                    if (!active && my >= 0) {
+                        idx = my;
+                        sink.base = idx * (long long)out_per_traj;
+#pragma unroll
+                        for (int i = 0; i < B2_N; i++) u[i] = gu0[idx * B2_N + i];
+#pragma unroll
+                        for (int i = 0; i < B2_NPARAM; i++) p[i] = gp[idx * B2_NPARAM + i];
+                        t = t0;
+                        dt = dt_user;
+                        qold = qoldinit;
+                        iter = 0;
+                        si = 0;
+                        naccept = nreject = nevents = 0;
+                        // the first saved value is u0 itself (test/core.jl:34)
+                        while (si < n_save && __ldg(gsave + si) <= t0) {
+                            sink.put(si, u);
+                            si++;
+                        }
+                        alg.start(u, p, t);
+                        nf = 1;
+                        active = true;
+#if B2_HAS_EVENT
+                        just_fired = false;
+#endif
+                    }
+                }
+                if (__ballot_sync(B2_FULL, active) == 0u) break;
+            }
+        }
+        if (!active) continue;
+
+        // ---------------- one step attempt (loopheader!/check_error!)
+        int rc = 0;
+        iter++;
+        if (iter > a.maxiters) {
+            rc = B2_RC_MAXITERS;
+        } else {
+            if (!adaptive) dt = dt_user;
+            bool clipped = false;
+            real tstop = t1;
+            if (save_tstops && si < n_save) {
+                const real s = __ldg(gsave + si);
+                if (s < t1) tstop = s;
+            }
+            if (dt > tstop - t) {
+                dt = tstop - t;
+                clipped = true;
+            }
+            if (b2_isnan(dt)) {
+                rc = B2_RC_DTNAN;
+            } else if (adaptive && !clipped && dt <= b2_max(dtmin, (real)B2_EPS * b2_abs(t))) {
+                rc = B2_RC_DTLESSTHANMIN;
+            } else {
+                real un[B2_N], ut[B2_N];
+                alg.step(u, p, t, dt, un, ut, adaptive, nf);
+                bool accept = true;
+                real dtnew = dt;
+                if (adaptive) {
+                    // error norm (A.4) and PI controller (A.5)
+                    real acc = 0;
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) {
+                        const real sk = b2_fma(b2_max(b2_abs(u[i]), b2_abs(un[i])), reltol, abstol);
+                        const real r = ut[i] / sk;
+                        acc = b2_fma(r, r, acc);
+                    }
+                    const real EEst = b2_sqrt(acc / (real)B2_N);
+                    if (b2_isnan(EEst)) {
+                        rc = B2_RC_DTNAN;  // upstream: NaN EEst -> NaN dt -> ReturnCode.DtNaN
+                        accept = false;
+                    } else {
+                        real q, q11 = 0;
+                        if (EEst == (real)0) {
+                            q = inv_qmax;
+                        } else {
+                            q11 = (real)b2_fastpow((float)EEst, beta1);
+                            q = q11 / (real)b2_fastpow((float)qold, beta2);
+                            q = b2_max(inv_qmax, b2_min(inv_qmin, q / gam));
+                        }
+                        if (!(EEst <= (real)1)) {
+                            accept = false;
+                            nreject++;
+                            dt = dt / b2_min(inv_qmin, q11 / gam);
+                        } else {
+                            qold = b2_max(EEst, qoldinit);
+                            dtnew = dt / q;
+                        }
+                    }
+                } else {
+                    bool bad = false;
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) bad |= b2_isnan(un[i]);
+                    if (bad) {
+                        rc = B2_RC_UNSTABLE;
+                        accept = false;
+                    }
+                }
+                if (accept) {
+                    // ---------------- loopfooter!: advance, saveat (A.6), callbacks (A.8), FSAL
+                    naccept++;
+                    const real tprev = t;
+                    real tnew = t + dt;
+                    if (b2_abs(tnew - tstop) < (real)100 * (real)B2_EPS * b2_max(b2_abs(tnew), b2_abs(tstop))) tnew = tstop;
+                    alg.accepted(un, p, tnew, nf);
+                    bool fired = false;
+#if B2_HAS_EVENT
+                    real th_end = 1;
+                    {
+                        real w[B2_N];
+                        real gprev, lo = 0, hi = 0;
+                        alg.prepare_dense(u, p, tprev, dt, nf);
+                        if (just_fired) {
+                            alg.interp(u, un, (real)0.01, dt, w);
+                            gprev = b2_condition(w, p, b2_fma((real)0.01, dt, tprev));
+                            lo = (real)0.01;
+                        } else {
+                            gprev = b2_condition(u, p, tprev);
+                        }
+                        for (int mm = 1; mm <= ip && !fired; mm++) {
+                            const real th = (mm == ip) ? (real)1 : (real)mm / (real)ip;
+                            real g;
+                            if (mm == ip) {
+                                g = b2_condition(un, p, tnew);
+                            } else {
+                                alg.interp(u, un, th, dt, w);
+                                g = b2_condition(w, p, b2_fma(th, dt, tprev));
+                            }
+                            if ((gprev < 0 && g >= 0) || (gprev > 0 && g <= 0)) {
+                                fired = true;
+                                hi = th;
+                            } else {
+                                lo = th;
+                            }
+                        }
+                        if (fired) {  // bisection on theta; keep the LEFT side of the root
+                            for (int it = 0; it < 64; it++) {
+                                const real mid = (real)0.5 * (lo + hi);
+                                if (!(mid > lo && mid < hi)) break;
+                                alg.interp(u, un, mid, dt, w);
+                                const real g = b2_condition(w, p, b2_fma(mid, dt, tprev));
+                                if ((gprev < 0 && g >= 0) || (gprev > 0 && g <= 0)) hi = mid;
+                                else lo = mid;
+                            }
+                            th_end = lo;
+                            tnew = b2_fma(th_end, dt, tprev);
+                        }
+                    }
+#endif
+                    while (si < n_save) {
+                        const real tau = __ldg(gsave + si);
+                        if (!(tau <= tnew)) break;
+                        if (tau == tnew && !fired) {
+                            sink.put(si, un);
+                        } else {
+                            real w[B2_N];
+                            alg.prepare_dense(u, p, tprev, dt, nf);
+                            alg.interp(u, un, (tau - tprev) / dt, dt, w);
+                            sink.put(si, w);
+                        }
+                        si++;
+                    }
+                    t = tnew;
+#if B2_HAS_EVENT
+                    if (fired) {
+                        real w[B2_N];
+                        alg.interp(u, un, th_end, dt, w);
+                        b2_affect(w, p, t);
+#pragma unroll
+                        for (int i = 0; i < B2_N; i++) u[i] = w[i];
+                        nevents++;
+                        alg.start(u, p, t);
+                        nf++;
+                        just_fired = true;
+                        if (a.event_terminate) rc = B2_RC_TERMINATED;
+                    } else
+#endif
+                    {
+#pragma unroll
+                        for (int i = 0; i < B2_N; i++) u[i] = un[i];
+                        alg.advance();
+#if B2_HAS_EVENT
+                        just_fired = false;
+#endif
+                    }
+                    if (adaptive) dt = b2_min(dtmax, dtnew);
+                    if (rc == 0 && !(t < t1)) rc = B2_RC_SUCCESS;
+                }
+            }
+        }
+        if (rc != 0) {
+            // ---------------- retire this lane
+            if (rc == B2_RC_TERMINATED) {
+                for (; si < n_save; si++) sink.put(si, u);
+            } else if (rc != B2_RC_SUCCESS) {
+                sink.fill(si, n_save, (real)__int_as_float(0x7fc00000));
+            }
+            a.retcode[idx] = rc;
+            if (a.stats) {
+                B2Stats s;
+                s.naccept = naccept;
+                s.nreject = nreject;
+                s.nf = nf;
+                s.nevents = nevents;
+                a.stats[idx] = s;
+            }
+            active = false;
+            dirty = stride != 0;
+        }
+    }
+}

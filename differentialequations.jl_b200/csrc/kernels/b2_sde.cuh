@@ -1,0 +1,219 @@
+// b2_sde.cuh -- fixed-step SDE ensemble kernel: Euler-Maruyama (diagonal noise) and SOSRA
+// (additive noise, strong order 1.5) with counter-based Philox4x32-10 noise generated on the
+// device, or Brownian increments injected by the caller for pathwise parity.
+// Reference names: SDEProblem /root/reference/test/qa/qa.jl:103 (EM/SOSRA live in
+// StochasticDiffEq, outside the dep closure; step forms SURVEY.md A.9, table B.8, RNG B.9).
+#pragma once
+#include "b2_common.cuh"
+#include "tableaus_gen.cuh"
+
+#define B2_PHILOX_M0 0xD2511F53u
+#define B2_PHILOX_M1 0xCD9E8D57u
+#define B2_PHILOX_W0 0x9E3779B9u
+#define B2_PHILOX_W1 0xBB67AE85u
+
+__device__ __forceinline__ uint4 b2_philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(B2_PHILOX_M0, c.x), lo0 = B2_PHILOX_M0 * c.x;
+        const unsigned hi1 = __umulhi(B2_PHILOX_M1, c.z), lo1 = B2_PHILOX_M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += B2_PHILOX_W0;
+        k.y += B2_PHILOX_W1;
+    }
+    return c;
+}
+
+#define B2_TWO_PI 6.283185307179586476925
+#if B2_F64
+#define B2_NORMALS_PER_CALL 2
+// counter = (traj_lo, traj_hi, step, block), key = (seed_lo, seed_hi); two 53-bit uniforms -> one Box-Muller pair
+__device__ __forceinline__ void b2_normals(unsigned long long seed, unsigned long long traj, unsigned step,
+                                           unsigned block, real* z) {
+    const uint4 r = b2_philox4x32_10(make_uint4((unsigned)traj, (unsigned)(traj >> 32), step, block),
+                                     make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const unsigned long long a = ((unsigned long long)r.x << 32) | r.y, b = ((unsigned long long)r.z << 32) | r.w;
+    const double u1 = ((double)(a >> 11) + 0.5) * 1.1102230246251565404e-16;
+    const double u2 = ((double)(b >> 11) + 0.5) * 1.1102230246251565404e-16;
+    const double rad = sqrt(-2.0 * log(u1));
+    const double ang = B2_TWO_PI * u2;
+    z[0] = rad * cos(ang);
+    z[1] = rad * sin(ang);
+}
+#else
+#define B2_NORMALS_PER_CALL 4
+// four u32 -> two Box-Muller pairs; uniforms ((x>>8)+0.5)*2^-24 in (0,1)
+__device__ __forceinline__ void b2_normals(unsigned long long seed, unsigned long long traj, unsigned step,
+                                           unsigned block, real* z) {
+    const uint4 r = b2_philox4x32_10(make_uint4((unsigned)traj, (unsigned)(traj >> 32), step, block),
+                                     make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const float u1 = ((float)(w[2 * h] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+        const float u2 = ((float)(w[2 * h + 1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+        const float rad = sqrtf(-2.0f * logf(u1));
+        const float ang = (float)B2_TWO_PI * u2;
+        z[2 * h] = rad * cosf(ang);
+        z[2 * h + 1] = rad * sinf(ang);
+    }
+}
+#endif
+
+#define SO(x) ((real)(B2T_SOSRA_##x))
+#define B2_INV_SQRT3 0.57735026918962576451
+
+template <int ALG>
+__device__ __forceinline__ void b2_sde_driver(const B2Args& a) {
+    extern __shared__ __align__(16) unsigned char b2_smem[];
+    const unsigned lane = threadIdx.x & 31u;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int stride = a.stage_stride;
+    real* const warp_stage = reinterpret_cast<real*>(b2_smem) + (size_t)warp_in_block * 32 * stride;
+    real* const gout = reinterpret_cast<real*>(a.out_u);
+    const real* const gu0 = reinterpret_cast<const real*>(a.u0);
+    const real* const gp = reinterpret_cast<const real*>(a.p);
+    const real* const gsave = reinterpret_cast<const real*>(a.saveat);
+    const real* const gdW = reinterpret_cast<const real*>(a.dW);
+    const int n_save = a.n_save;
+    const int out_per_traj = n_save * B2_N;
+    constexpr int NVEC = (ALG == 7) ? 2 : 1;
+    const real t0 = (real)a.t0, t1 = (real)a.t1, dt_user = (real)a.dt;
+
+    B2Sink sink;
+    sink.stage = stride ? warp_stage + (size_t)lane * stride : nullptr;
+    sink.gout = gout;
+    bool exhausted = false;
+    while (!exhausted) {
+        // uniform work per path: hand out whole warps of consecutive paths
+        long long idx = b2_fetch(B2_FULL, a.work_counter, a.N, lane, exhausted);
+        const bool active = idx >= 0;
+        if (__ballot_sync(B2_FULL, active) == 0u) break;
+        if (active) {
+            real u[B2_N], p[B2_NPA];
+            sink.base = idx * (long long)out_per_traj;
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) u[i] = gu0[idx * B2_N + i];
+#pragma unroll
+            for (int i = 0; i < B2_NPARAM; i++) p[i] = gp[idx * B2_NPARAM + i];
+            real t = t0;
+            int si = 0, rc = 0;
+            long long step = 0;
+            while (si < n_save && __ldg(gsave + si) <= t0) {
+                sink.put(si, u);
+                si++;
+            }
+            const unsigned long long traj = a.traj_offset + (unsigned long long)idx;
+            while (t < t1) {
+                if (step >= a.maxiters) {
+                    rc = B2_RC_MAXITERS;
+                    break;
+                }
+                real dt = dt_user;
+                if (dt > t1 - t) dt = t1 - t;
+                real up[B2_N], dW[B2_N], dZ[B2_N];
+#pragma unroll
+                for (int i = 0; i < B2_N; i++) up[i] = u[i];
+                if (a.noise_injected) {
+                    const real* src = gdW + ((size_t)idx * a.nsteps_noise + (size_t)step) * (NVEC * B2_N);
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) {
+                        dW[i] = src[i];
+                        dZ[i] = NVEC > 1 ? src[B2_N + i] : (real)0;
+                    }
+                } else {
+                    constexpr int NEED = NVEC * B2_N;
+                    constexpr int NCALL = (NEED + B2_NORMALS_PER_CALL - 1) / B2_NORMALS_PER_CALL;
+                    real z[NCALL * B2_NORMALS_PER_CALL];
+                    const real sq = b2_sqrt(dt);
+#pragma unroll
+                    for (int b = 0; b < NCALL; b++)
+                        b2_normals(a.seed, traj, (unsigned)step, (unsigned)b, &z[b * B2_NORMALS_PER_CALL]);
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) {
+                        dW[i] = sq * z[i];
+                        dZ[i] = NVEC > 1 ? sq * z[(NVEC > 1 ? B2_N : 0) + i] : (real)0;
+                    }
+                }
+                real k1[B2_N], g1[B2_N];
+                if (ALG == 6) {  // Euler-Maruyama: u += f dt + g dW
+                    b2_rhs(k1, up, p, t);
+                    b2_noise(g1, up, p, t);
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) u[i] = b2_fma(g1[i], dW[i], b2_fma(dt, k1[i], up[i]));
+                } else {  // SOSRA
+                    real chi2[B2_N], g2[B2_N], g3[B2_N], k2[B2_N], k3[B2_N], H[B2_N];
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) chi2[i] = (real)0.5 * b2_fma(dZ[i], (real)B2_INV_SQRT3, dW[i]);
+                    b2_noise(g1, up, p, t + SO(c11) * dt);
+                    b2_noise(g2, up, p, t + SO(c12) * dt);
+                    b2_noise(g3, up, p, t + SO(c13) * dt);
+                    b2_rhs(k1, up, p, t);
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++)
+                        H[i] = b2_fma(chi2[i], SO(B021) * g1[i], b2_fma(dt, SO(A021) * k1[i], up[i]));
+                    b2_rhs(k2, H, p, t + SO(c02) * dt);
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) {
+                        const real aa = b2_fma(SO(A032), k2[i], SO(A031) * k1[i]);
+                        const real bb = b2_fma(SO(B032), g2[i], SO(B031) * g1[i]);
+                        H[i] = b2_fma(chi2[i], bb, b2_fma(dt, aa, up[i]));
+                    }
+                    b2_rhs(k3, H, p, t + SO(c03) * dt);
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) {
+                        real d = SO(alpha1) * k1[i];
+                        d = b2_fma(SO(alpha2), k2[i], d);
+                        d = b2_fma(SO(alpha3), k3[i], d);
+                        real e1 = SO(beta11) * g1[i];
+                        e1 = b2_fma(SO(beta12), g2[i], e1);
+                        e1 = b2_fma(SO(beta13), g3[i], e1);
+                        real e2 = SO(beta21) * g1[i];
+                        e2 = b2_fma(SO(beta22), g2[i], e2);
+                        e2 = b2_fma(SO(beta23), g3[i], e2);
+                        u[i] = b2_fma(chi2[i], e2, b2_fma(dW[i], e1, b2_fma(dt, d, up[i])));
+                    }
+                }
+                bool bad = false;
+#pragma unroll
+                for (int i = 0; i < B2_N; i++) bad |= b2_isnan(u[i]);
+                if (bad) {
+                    rc = B2_RC_UNSTABLE;
+                    break;
+                }
+                const real tprev = t;
+                real tnew = t + dt;
+                if (b2_abs(tnew - t1) < (real)100 * (real)B2_EPS * b2_max(b2_abs(tnew), b2_abs(t1))) tnew = t1;
+                while (si < n_save) {  // linear interpolation between grid points
+                    const real tau = __ldg(gsave + si);
+                    if (!(tau <= tnew)) break;
+                    if (tau == tnew) {
+                        sink.put(si, u);
+                    } else {
+                        const real th = (tau - tprev) / dt;
+                        real w[B2_N];
+#pragma unroll
+                        for (int i = 0; i < B2_N; i++) w[i] = b2_fma(th, u[i] - up[i], up[i]);
+                        sink.put(si, w);
+                    }
+                    si++;
+                }
+                t = tnew;
+                step++;
+            }
+            if (rc == 0) rc = B2_RC_SUCCESS;
+            else sink.fill(si, n_save, (real)__int_as_float(0x7fc00000));
+            a.retcode[idx] = rc;
+            if (a.stats) {
+                B2Stats s;
+                s.naccept = (int)step;
+                s.nreject = 0;
+                s.nf = 0;
+                s.nevents = 0;
+                a.stats[idx] = s;
+            }
+        }
+        if (stride) b2_flush(__ballot_sync(B2_FULL, active), warp_stage, stride, gout, idx, out_per_traj, lane);
+    }
+}
+#undef SO

@@ -1,0 +1,158 @@
+/* b200ens.h -- C ABI of libb200ens.so, the B200-native ensemble ODE/SDE back-end.
+ *
+ * This is the drop-in boundary for the hot path
+ *     solve(EnsembleProblem(prob; prob_func), alg, EnsembleB200();
+ *           trajectories=N, saveat, dt, abstol, reltol)
+ * of DifferentialEquations.jl.  The reference defines no FFI for this path (it is a
+ * 32-line re-export metapackage, /root/reference/src/DifferentialEquations.jl:8-9); what
+ * each entry point replaces is therefore cited by the reference-visible NAME it stands
+ * behind (the exported-name contract /root/reference/test/qa/qa.jl:3-217) and by the call
+ * sites in /root/reference/test/core.jl.  The Julia binding a maintainer would add is
+ * shown in INTEGRATION.md (julia/EnsembleB200.jl).
+ *
+ * Rules of the ABI: plain pointers and sizes, caller owns every buffer, no exceptions or
+ * longjmp cross it, no callbacks into the host language (model functions arrive as CUDA-C
+ * SOURCE, JIT-compiled with NVRTC for sm_100a).  There is NO CPU fallback: every solve
+ * entry fails with B200ENS_E_NODEVICE when no CUDA device is usable.
+ */
+#ifndef B200ENS_H
+#define B200ENS_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ENS_ABI_VERSION 1
+
+/* scalar type of u, p, t (Julia eltype(u0)) */
+enum b200ens_dtype { B200ENS_F32 = 0, B200ENS_F64 = 1 };
+
+/* algorithm ids <- OrdinaryDiffEq / StochasticDiffEq algorithm types
+ * (Tsit5 qa.jl:119, Vern7 qa.jl:126, Rosenbrock23 qa.jl:98, Rodas5P qa.jl:97;
+ *  Rodas5/Rodas4 live in OrdinaryDiffEqRosenbrock, EM/SOSRA in StochasticDiffEq) */
+enum b200ens_alg {
+    B200ENS_TSIT5 = 1, B200ENS_VERN7 = 2, B200ENS_ROSENBROCK23 = 3, B200ENS_RODAS5 = 4,
+    B200ENS_RODAS5P = 5, B200ENS_EM = 6, B200ENS_SOSRA = 7, B200ENS_RODAS4 = 8
+};
+
+/* per-trajectory return codes <- SciMLBase.ReturnCode (qa.jl:213); the Julia glue maps by name */
+enum b200ens_retcode {
+    B200ENS_RC_DEFAULT = 0, B200ENS_RC_SUCCESS = 1, B200ENS_RC_TERMINATED = 2, B200ENS_RC_MAXITERS = 3,
+    B200ENS_RC_DTLESSTHANMIN = 4, B200ENS_RC_UNSTABLE = 5, B200ENS_RC_DTNAN = 6, B200ENS_RC_FAILURE = 7
+};
+
+/* library error codes (negative returns) */
+enum b200ens_error {
+    B200ENS_OK = 0, B200ENS_E_INVALID = -1, B200ENS_E_COMPILE = -2, B200ENS_E_NODEVICE = -3,
+    B200ENS_E_CUDA = -4, B200ENS_E_NOMEM = -5, B200ENS_E_UNSUPPORTED = -6
+};
+
+/* model flags */
+#define B200ENS_MODEL_FAST_MATH 1u /* let NVRTC contract a*b+c in MODEL code (breaks bitwise oracle parity) */
+
+/* What a problem looks like to the library: ODEProblem / SDEProblem (qa.jl:86,103) with f,
+ * jac, tgrad, g and one ContinuousCallback (qa.jl:26; test/core.jl:69-72) given as CUDA-C
+ * source defining these device functions (`real` is float or double per dtype):
+ *   __device__ void b2_rhs      (real* du, const real* u, const real* p, real t);
+ *   __device__ void b2_jac      (real* J,  const real* u, const real* p, real t);   row-major n x n
+ *   __device__ void b2_tgrad    (real* dT, const real* u, const real* p, real t);   optional
+ *   __device__ void b2_noise    (real* g,  const real* u, const real* p, real t);   diagonal noise
+ *   __device__ real b2_condition(const real* u, const real* p, real t);
+ *   __device__ void b2_affect   (real* u,  const real* p, real t);
+ * NULL = absent. */
+typedef struct b200ens_model_desc {
+    uint32_t struct_size;   /* sizeof(b200ens_model_desc) */
+    int32_t n_state;        /* length(u0), 1..32 */
+    int32_t n_param;        /* length(p), 0..64 */
+    int32_t dtype;          /* enum b200ens_dtype */
+    int32_t alg;            /* enum b200ens_alg */
+    uint32_t flags;
+    const char* rhs_src;
+    const char* jac_src;
+    const char* tgrad_src;
+    const char* noise_src;
+    const char* condition_src;
+    const char* affect_src;
+    const char* name;       /* label for logs / cache, may be NULL */
+} b200ens_model_desc;
+
+/* solve keyword arguments (test/core.jl:14,54,72,93: reltol, abstol, dense/saveat, callback).
+ * Doubles set to NaN or <0 take the upstream default. */
+typedef struct b200ens_opts {
+    uint32_t struct_size;   /* sizeof(b200ens_opts) */
+    int32_t adaptive;       /* 1 adaptive (default for ODE algs), 0 fixed dt */
+    double t0, t1;          /* tspan */
+    double dt;              /* initial dt (adaptive) or the fixed dt */
+    double abstol, reltol;  /* defaults 1e-6 / 1e-3 */
+    double dtmin, dtmax;    /* defaults 0 (+ eps(t) floor) / t1-t0 */
+    double qmin, qmax, gamma, beta1, beta2, qoldinit; /* PI controller; defaults 1/5, 10, 9/10, 7/(10k), 2/(5k), 1e-4 */
+    int64_t maxiters;       /* <=0: 100000 */
+    uint64_t seed;          /* Philox key */
+    uint64_t traj_offset;   /* global index of trajectory 0 of this call (Philox counter base) */
+    int32_t noise_injected; /* 1: dW holds the Brownian increments; 0: Philox4x32-10 on device */
+    int32_t event_terminate;/* 1: the ContinuousCallback terminates the trajectory (terminate!) */
+    int32_t interp_points;  /* ContinuousCallback interp_points, <=0: 10 */
+    int32_t save_tstops;    /* -1 auto (on for Rodas*), 0 interpolate, 1 saveat points are tstops */
+    uint32_t device_mask;   /* bit g set: use CUDA device g; 0: all visible devices */
+    int32_t refill_threshold; /* lanes of a warp that must be idle before it fetches new trajectories; <=0 auto */
+    int32_t block_threads;  /* <=0 auto */
+    int32_t stage_outputs;  /* -1 auto, 0 direct global stores, 1 stage saveat outputs in shared memory */
+} b200ens_opts;
+
+typedef struct b200ens_stats {
+    int32_t naccept, nreject, nf, nevents;
+} b200ens_stats;
+
+typedef struct b200ens_timing {
+    double h2d_ms, kernel_ms, d2h_ms, total_ms; /* device-event times; max over devices */
+    int32_t n_devices, launches;
+    int32_t grid, block, smem_bytes, regs;      /* of the last launch on the first device */
+} b200ens_timing;
+
+typedef struct b200ens_model b200ens_model;
+
+int b200ens_abi_version(void);
+/* number of usable CUDA devices; <0 on CUDA initialisation failure */
+int b200ens_device_count(void);
+/* thread-local description of the last error */
+const char* b200ens_last_error(void);
+
+/* Fill o with defaults (everything "auto"). */
+void b200ens_opts_init(b200ens_opts* o);
+
+/* JIT-compile (model source x algorithm kernel x dtype) for sm_100a.  Needs no GPU.  The
+ * NVRTC/ptxas log (register count, spills) is copied into log (may be NULL). */
+int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log, size_t log_len);
+void b200ens_free(b200ens_model* m);
+/* cubin size, registers/thread, static smem, local (spill) bytes as parsed from the ptxas log; any may be NULL */
+int b200ens_model_info(const b200ens_model* m, int64_t* cubin_bytes, int32_t* regs, int32_t* smem, int32_t* lmem);
+
+/* The ensemble solve behind  solve(::EnsembleProblem, alg, ::EnsembleB200; trajectories=N, ...)
+ * (replaces SciMLBase.__solve / solve_batch / batch_func of EnsembleThreads, qa.jl:56,192).
+ * HOST buffers, trajectory-major:
+ *   u0 [N][n_state], p [N][n_param], saveat [n_save] (ascending, within [t0,t1]),
+ *   dW  NULL or [N][nsteps][nvec][n_state]  (nvec = 1 EM, 2 SOSRA: dW then dZ),
+ *   out_u [N][n_save][n_state], out_t [n_save] or NULL, retcode [N], stats [N] or NULL.
+ * Trajectory ranges are sharded over the devices in device_mask; blocking. */
+int b200ens_solve(b200ens_model* m, const b200ens_opts* o, int64_t N, const void* u0, const void* p,
+                  const void* saveat, int32_t n_save, const void* dW, void* out_u, void* out_t,
+                  int32_t* retcode, b200ens_stats* stats, b200ens_timing* timing);
+
+/* Same solve with every buffer already resident in the HBM of `device`, launched on
+ * `stream` (a cudaStream_t, NULL = default stream).  Blocks until the kernel has finished
+ * unless timing == NULL, in which case it only enqueues. */
+int b200ens_solve_device(b200ens_model* m, const b200ens_opts* o, int32_t device, void* stream, int64_t N,
+                         const void* d_u0, const void* d_p, const void* d_saveat, int32_t n_save,
+                         const void* d_dW, void* d_out_u, int32_t* d_retcode, b200ens_stats* d_stats,
+                         b200ens_timing* timing);
+
+/* pinned host memory for callers that want zero-staging transfers */
+void* b200ens_host_alloc(size_t bytes);
+void b200ens_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

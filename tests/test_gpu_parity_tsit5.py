@@ -1,0 +1,94 @@
+"""GPU parity: Tsit5 kernels vs the CPU oracle on identical inputs (BASELINE.json configs 1-2).
+
+Bars (BASELINE.json north_star): fixed-dt Float64 final states agree to 1e-12 relative;
+adaptive runs agree at saveat points within abstol + reltol*|u| with matching retcodes.
+Because kernel and oracle restate the same expression tree (explicit FMAs, deterministic
+fastpow) the observed differences are far below those bars; the step counts must match exactly.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SAVEAT = np.arange(0.0, 10.5, 1.0)
+
+
+def _solve_gpu(B, dtype, u0, p, saveat, dt, adaptive=True, abstol=1e-6, reltol=1e-3, tspan=(0.0, 10.0), **ens):
+    from b200ens import workloads as W
+
+    prob = W.lorenz_problem(dtype, tspan)
+    eprob = B.EnsembleProblem(prob, u0s=u0, ps=p)
+    return B.solve(eprob, B.Tsit5(), B.EnsembleB200(**ens), trajectories=u0.shape[0], saveat=saveat, dt=dt,
+                   abstol=abstol, reltol=reltol, adaptive=adaptive)
+
+
+@pytest.mark.parametrize("kind", ["ordered", "random"])
+def test_fixed_dt_f64_final_state_1e12(B, gpu_lib, oracle, kind):
+    from b200ens import workloads as W
+
+    N = 2000
+    u0, p = W.lorenz_params(N, kind, seed=0)
+    sol = _solve_gpu(B, np.float64, u0, p, [10.0], 1e-3, adaptive=False)
+    ref, rc, st = oracle.solve("lorenz", "Tsit5", u0, p, (0.0, 10.0), [10.0], 1e-3, adaptive=False, maxiters=10**6)
+    assert np.all(sol.retcodes == 1) and np.all(rc == 1)
+    assert np.array_equal(sol.stats[:, 0], st[:, 0])
+    rel = np.abs(sol.u_array - ref) / np.maximum(np.abs(ref), 1e-300)
+    assert rel.max() <= 1e-12, rel.max()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind", ["ordered", "random"])
+def test_adaptive_saveat_matches_oracle(B, gpu_lib, oracle, dtype, kind):
+    from b200ens import workloads as W
+
+    N = 10000
+    abstol, reltol = 1e-6, 1e-3
+    u0, p = W.lorenz_params(N, kind, seed=0, dtype=dtype)
+    sol = _solve_gpu(B, dtype, u0, p, SAVEAT, 0.1, abstol=abstol, reltol=reltol)
+    ref, rc, st = oracle.solve("lorenz", "Tsit5", u0, p, (0.0, 10.0), SAVEAT, 0.1, abstol=abstol, reltol=reltol,
+                               dtype=dtype)
+    assert sol.u_array.shape == (N, 11, 3)
+    assert np.array_equal(sol.retcodes, rc) and np.all(rc == 1)
+    assert np.array_equal(sol.u_array[:, 0, :], u0)            # first saved value is u0 itself (test/core.jl:34)
+    assert np.array_equal(sol.stats[:, :2], st[:, :2])          # identical accept/reject sequences
+    err = np.abs(sol.u_array.astype(np.float64) - ref.astype(np.float64))
+    tol = abstol + reltol * np.abs(ref.astype(np.float64))
+    assert np.all(err <= tol), float((err / tol).max())
+
+
+@pytest.mark.parametrize("refill,stage", [(1, 1), (8, 0), (32, 1), (32, 0)])
+def test_schedule_variants_identical(B, gpu_lib, refill, stage):
+    """Lane refill / output staging are scheduling choices: results must be bit-identical."""
+    from b200ens import workloads as W
+
+    N = 4099  # ragged: not a multiple of the warp or block size
+    u0, p = W.lorenz_params(N, "random", seed=5)
+    base = _solve_gpu(B, np.float64, u0, p, SAVEAT, 0.1)
+    var = _solve_gpu(B, np.float64, u0, p, SAVEAT, 0.1, refill_threshold=refill, stage_outputs=stage)
+    assert np.array_equal(base.u_array, var.u_array)
+    assert np.array_equal(base.retcodes, var.retcodes)
+    assert np.array_equal(base.stats, var.stats)
+
+
+def test_edge_cases(B, gpu_lib, oracle):
+    from b200ens import workloads as W
+
+    # one trajectory, tight tolerance (test/core.jl:14 uses 1e-8)
+    u0, p = W.lorenz_params(1, "ordered")
+    p[0] = [10.0, 28.0, 8.0 / 3.0]
+    sol = _solve_gpu(B, np.float64, u0, p, np.linspace(0, 1, 11), 0.01, abstol=1e-8, reltol=1e-8, tspan=(0.0, 1.0))
+    ref, rc, st = oracle.solve("lorenz", "Tsit5", u0, p, (0.0, 1.0), np.linspace(0, 1, 11), 0.01, abstol=1e-8, reltol=1e-8)
+    assert sol.retcodes[0] == 1 and len(sol[0].t) == 11
+    assert np.allclose(sol.u_array, ref, rtol=1e-12, atol=1e-13)
+    # maxiters exhaustion -> MaxIters retcode and NaN-filled tail, same as the oracle
+    u0, p = W.lorenz_params(64, "random", seed=2)
+    prob = W.lorenz_problem()
+    s2 = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), B.Tsit5(), B.EnsembleB200(), trajectories=64, saveat=SAVEAT,
+                 dt=0.1, maxiters=20)
+    ref2, rc2, _ = oracle.solve("lorenz", "Tsit5", u0, p, (0.0, 10.0), SAVEAT, 0.1, maxiters=20)
+    assert np.array_equal(s2.retcodes, rc2) and (rc2 == 3).any()
+    assert np.array_equal(np.isnan(s2.u_array), np.isnan(ref2))
+    # NaN parameters -> DtNaN
+    p[3] = np.nan
+    s3 = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), B.Tsit5(), B.EnsembleB200(), trajectories=64, saveat=SAVEAT, dt=0.1)
+    assert s3.retcodes[3] == 6 and s3.retcodes[2] == 1

@@ -16,6 +16,9 @@
 #define B2_HAS_NOISE 1
 #define B2_HAS_EVENT 0
 #define B2_BLOCK 128
+#ifndef B2_MINBLOCKS
+#define B2_MINBLOCKS 1
+#endif
 #include "b2_common.cuh"
 
 __device__ __forceinline__ void b2_rhs(real* __restrict__ du, const real* __restrict__ u, const real* __restrict__ p, const real t) {

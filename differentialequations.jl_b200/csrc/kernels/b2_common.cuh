@@ -52,7 +52,15 @@ struct B2Args {
     double t0, t1, dt, abstol, reltol, dtmin, dtmax, qmin, qmax, gamma, beta1, beta2, qoldinit;
     int n_save, adaptive, refill_threshold, stage_stride;
     int noise_injected, event_terminate, interp_points, save_tstops;
+    // the same scalars pre-converted to float by the host (f32 kernels read these: no F2F in the loop)
+    float f_t0, f_t1, f_dt, f_abstol, f_reltol, f_dtmin, f_dtmax, f_qmin, f_qmax, f_gamma, f_beta1, f_beta2, f_qoldinit;
 };
+
+#if B2_F64
+#define B2_ARG(a, name) ((a).name)
+#else
+#define B2_ARG(a, name) ((a).f_##name)
+#endif
 
 __device__ __forceinline__ float b2_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ double b2_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
@@ -66,15 +74,21 @@ __device__ __forceinline__ float b2_sqrt(float a) { return __fsqrt_rn(a); }
 __device__ __forceinline__ double b2_sqrt(double a) { return __dsqrt_rn(a); }
 __device__ __forceinline__ bool b2_isnan(real a) { return a != a; }
 
-// ---- deterministic float power for the PI controller (same primitive sequence as the
-// oracle's orc_fastpow; restates upstream's approximate FastPower)
+// ---- deterministic float log2 / exp2 for the PI controller (same primitive sequence as the
+// oracle's orc_fastlog2 / orc_fastexp2; restates upstream's approximate FastPower):
+//   log2(x) = e + t*P5(t), t = mantissa-1;   2^y = 2^rint(y) * Q6(y - rint(y))
 __device__ __forceinline__ float b2_fastlog2(float x) {
     const unsigned ix = __float_as_uint(x);
     const int e = (int)(ix >> 23) - 127;
     const float m = __uint_as_float((ix & 0x007fffffu) | 0x3f800000u);
     const float t = __fsub_rn(m, 1.0f);
-    const float num = __fmul_rn(t, __fmaf_rn(0.338953f, t, 2.198599f));
-    return __fadd_rn((float)e, __fdiv_rn(num, __fadd_rn(t, 1.523692f)));
+    float p = -0.02645725943148136f;
+    p = __fmaf_rn(p, t, 0.12345092743635178f);
+    p = __fmaf_rn(p, t, -0.27953752875328064f);
+    p = __fmaf_rn(p, t, 0.45827049016952515f);
+    p = __fmaf_rn(p, t, -0.7182818651199341f);
+    p = __fmaf_rn(p, t, 1.442553162574768f);
+    return __fmaf_rn(t, p, (float)e);
 }
 __device__ __forceinline__ float b2_fastexp2(float y) {
     y = fminf(fmaxf(y, -125.0f), 125.0f);
@@ -88,10 +102,6 @@ __device__ __forceinline__ float b2_fastexp2(float y) {
     p = __fmaf_rn(p, f, 6.9314718e-1f);
     p = __fmaf_rn(p, f, 1.0f);
     return __uint_as_float(__float_as_uint(p) + (unsigned)((int)fi << 23));
-}
-__device__ __forceinline__ float b2_fastpow(float x, float y) {
-    if (!(x > 0.0f)) return 0.0f;
-    return b2_fastexp2(__fmul_rn(y, b2_fastlog2(x)));
 }
 
 // ---- per-lane output sink: shared-memory staging (flushed coalesced by the whole warp

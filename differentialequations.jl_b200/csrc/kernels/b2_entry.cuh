@@ -15,7 +15,7 @@
 #error "unknown B2_ALG"
 #endif
 
-extern "C" __global__ void __launch_bounds__(B2_BLOCK) b2_ensemble_kernel(const __grid_constant__ B2Args a) {
+extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble_kernel(const __grid_constant__ B2Args a) {
 #if B2_ALG == 1
     b2_ode_driver<B2Tsit5>(a);
 #elif B2_ALG == 2

@@ -78,7 +78,7 @@ __device__ __forceinline__ void b2_sde_driver(const B2Args& a) {
     const int n_save = a.n_save;
     const int out_per_traj = n_save * B2_N;
     constexpr int NVEC = (ALG == 7) ? 2 : 1;
-    const real t0 = (real)a.t0, t1 = (real)a.t1, dt_user = (real)a.dt;
+    const real t0 = B2_ARG(a, t0), t1 = B2_ARG(a, t1), dt_user = B2_ARG(a, dt);
 
     B2Sink sink;
     sink.stage = stride ? warp_stage + (size_t)lane * stride : nullptr;

@@ -8,15 +8,18 @@
 #include <string.h>
 #include <stddef.h>
 
-/* ---------------------------------------------------------------- fastpow
- * Restates the approximate power upstream's PI controller uses (SURVEY.md 7.3 "fastpower",
- * [UPSTREAM-RECALLED] FastPower.jl): compute in Float32, log2 by exponent extraction plus a
- * rational correction on the mantissa, then 2^x.  Here both halves are spelled out in
- * IEEE-exact primitive operations so that the CUDA kernels reproduce them bit for bit.
- *   log2(x) ~= e + t*(a*t + b)/(t + c),  t = mantissa-1 in [0,1)
- *   2^y     =  2^rint(y) * P6(y - rint(y)),  P6 = degree-6 Taylor of exp(f ln 2), |f|<=1/2
+/* ---------------------------------------------------------------- fast log2 / exp2
+ * The PI controller needs EEst^beta1 / qold^beta2.  Upstream evaluates both powers with an
+ * approximate Float32 routine (SURVEY.md 7.3 "fastpower", [UPSTREAM-RECALLED] FastPower.jl);
+ * this restatement keeps that character -- Float32, ~2e-6 accurate -- but spells both halves
+ * out in IEEE-exact primitive operations (integer exponent extraction, FMA-Horner polynomials)
+ * so that the CUDA kernels reproduce them bit for bit:
+ *   log2(x) = e + t*P5(t),  t = mantissa-1 in [0,1)     (max abs error 2.2e-6)
+ *   2^y     = 2^rint(y) * Q6(y - rint(y)),  Q6 = degree-6 Taylor of exp(f ln 2), |f|<=1/2
+ * The controller works in the log domain (one log2 of EEst^2, one exp2 per step); see
+ * oracle_impl.inc for the exact expression tree.
  */
-static inline float fastlog2f(float x) {
+float orc_fastlog2(float x) {
     uint32_t ix;
     memcpy(&ix, &x, 4);
     const int e = (int)(ix >> 23) - 127;
@@ -24,10 +27,15 @@ static inline float fastlog2f(float x) {
     float m;
     memcpy(&m, &im, 4);
     const float t = m - 1.0f;
-    const float num = t * fmaf(0.338953f, t, 2.198599f);
-    return (float)e + num / (t + 1.523692f);
+    float p = -0.02645725943148136f;
+    p = fmaf(p, t, 0.12345092743635178f);
+    p = fmaf(p, t, -0.27953752875328064f);
+    p = fmaf(p, t, 0.45827049016952515f);
+    p = fmaf(p, t, -0.7182818651199341f);
+    p = fmaf(p, t, 1.442553162574768f);
+    return fmaf(t, p, (float)e);
 }
-static inline float fastexp2f(float y) {
+float orc_fastexp2(float y) {
     y = fminf(fmaxf(y, -125.0f), 125.0f);
     const float fi = rintf(y);
     const float f = y - fi;
@@ -46,7 +54,7 @@ static inline float fastexp2f(float y) {
 }
 float orc_fastpow(float x, float y) {
     if (!(x > 0.0f)) return 0.0f;
-    return fastexp2f(y * fastlog2f(x));
+    return orc_fastexp2(y * orc_fastlog2(x));
 }
 
 /* ---------------------------------------------------------------- Philox4x32-10 (B.9) */

@@ -67,6 +67,8 @@ void* orc_model_fn(const char* model, const char* which, int is_f64);
 
 /* deterministic pow used by the PI controller (restates upstream's approximate FastPower) */
 float orc_fastpow(float x, float y);
+float orc_fastlog2(float x);
+float orc_fastexp2(float y);
 /* Philox4x32-10 */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* normals exactly as the kernels draw them: counter=(traj_lo,traj_hi,step,block) */

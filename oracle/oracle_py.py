@@ -64,14 +64,33 @@ def model_fn(model, which, f64):
     return lib().orc_model_fn(model.encode(), which.encode(), 1 if f64 else 0)
 
 
-def compile_c_model(src, tag, workdir):
-    """Compile emitted C model source (double + float variants) with the oracle's flags."""
+def compile_host_model(src, tag, workdir):
+    """Compile emitted model code (C++ wrapper from codegen.host_wrapper_source) with the oracle's
+    floating-point flags (no contraction) so that the oracle runs the SAME expression tree as the GPU."""
+    import hashlib
+
     os.makedirs(workdir, exist_ok=True)
-    cpath = os.path.join(workdir, f"model_{tag}.c")
-    so = os.path.join(workdir, f"model_{tag}.so")
-    open(cpath, "w").write(src)
-    subprocess.check_call(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, cpath, "-lm"])
+    h = hashlib.sha1(src.encode()).hexdigest()[:12]
+    cpath = os.path.join(workdir, f"model_{tag}_{h}.cpp")
+    so = os.path.join(workdir, f"model_{tag}_{h}.so")
+    if not os.path.exists(so):
+        open(cpath, "w").write(src)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                               "-o", so, cpath, "-lm"])
     return C.CDLL(so)
+
+
+def fns_from_host_model(dll, f64):
+    """dict(rhs=ptr, jac=ptr, ...) for solve(fns=...) from a compile_host_model() library."""
+    suf = "f64" if f64 else "f32"
+    out = {}
+    for key, nm in (("rhs", "b2_rhs"), ("jac", "b2_jac"), ("tgrad", "b2_tgrad"), ("noise", "b2_noise"),
+                    ("cond", "b2_condition"), ("affect", "b2_affect")):
+        try:
+            out[key] = C.cast(getattr(dll, f"{nm}_{suf}"), C.c_void_p).value
+        except AttributeError:
+            out[key] = None
+    return out
 
 
 def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adaptive=True, dtype=np.float64,
@@ -100,7 +119,8 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
         save_tstops = alg in ("Rodas4", "Rodas5", "Rodas5P")
     o.save_tstops = int(save_tstops)
     get = (lambda w: (fns or {}).get(w)) if fns is not None else (lambda w: model_fn(model, w, f64))
-    o.rhs, o.jac, o.tgrad, o.noise = get("rhs"), get("jac"), get("tgrad") if fns else None, get("noise")
+    o.rhs, o.jac, o.noise = get("rhs"), get("jac"), get("noise")
+    o.tgrad = get("tgrad") if fns else None
     o.cond, o.affect = (get("cond"), get("affect")) if event else (None, None)
     out = np.empty((N, len(saveat), n), dtype=dtype)
     rc = np.zeros(N, dtype=np.int32)

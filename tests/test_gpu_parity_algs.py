@@ -1,0 +1,181 @@
+"""GPU parity for the remaining steppers (BASELINE.json configs 3-5): Vern7, Rosenbrock23,
+Rodas4/5/5P, EM, SOSRA, ContinuousCallback -- each against the CPU oracle on identical inputs.
+
+Two oracle flavours are used: the hand-written C models (oracle/models.c, independent of the
+sympy->CUDA-C emitter; compared at abstol + reltol*|u|) and the emitter's own source compiled
+for the host (same expression tree as the GPU; compared essentially bit-for-bit)."""
+import numpy as np
+import pytest
+
+from helpers import oracle_fns, within_tol
+
+pytestmark = pytest.mark.gpu
+
+
+def _ens(B, prob, u0, p):
+    return B.EnsembleProblem(prob, u0s=u0, ps=p)
+
+
+# ---------------------------------------------------------------- Vern7 (config 5's stepper) on Lorenz
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_vern7_lorenz_adaptive(B, gpu_lib, oracle, dtype):
+    from b200ens import workloads as W
+
+    N = 3000
+    tol = 1e-8 if dtype == np.float64 else 1e-5
+    saveat = np.arange(0.0, 10.5, 0.5)
+    u0, p = W.lorenz_params(N, "random", seed=7, dtype=dtype)
+    sol = B.solve(_ens(B, W.lorenz_problem(dtype), u0, p), B.Vern7(), B.EnsembleB200(), trajectories=N, saveat=saveat,
+                  dt=0.05, abstol=tol, reltol=tol)
+    ref, rc, st = oracle.solve("lorenz", "Vern7", u0, p, (0.0, 10.0), saveat, 0.05, abstol=tol, reltol=tol, dtype=dtype)
+    assert np.array_equal(sol.retcodes, rc) and np.all(rc == 1)
+    assert np.array_equal(sol.stats[:, :3], st[:, :3])
+    ok, worst = within_tol(sol.u_array, ref, tol, tol)
+    assert ok, worst
+
+
+def test_vern7_fixed_dt_f64(B, gpu_lib, oracle):
+    from b200ens import workloads as W
+
+    N = 512
+    u0, p = W.lorenz_params(N, "ordered")
+    sol = B.solve(_ens(B, W.lorenz_problem(), u0, p), B.Vern7(), B.EnsembleB200(), trajectories=N, saveat=[10.0],
+                  dt=2e-3, adaptive=False, maxiters=10**6)
+    ref, rc, st = oracle.solve("lorenz", "Vern7", u0, p, (0.0, 10.0), [10.0], 2e-3, adaptive=False, maxiters=10**6)
+    assert np.all(sol.retcodes == 1)
+    rel = np.abs(sol.u_array - ref) / np.maximum(np.abs(ref), 1e-300)
+    assert rel.max() <= 1e-12, rel.max()
+
+
+# ---------------------------------------------------------------- config 3: Robertson, Rosenbrock methods
+@pytest.mark.parametrize("alg", ["Rosenbrock23", "Rodas4", "Rodas5", "Rodas5P"])
+def test_robertson_rosenbrock(B, gpu_lib, oracle, alg):
+    from b200ens import workloads as W
+
+    N = 2000
+    abstol, reltol = 1e-8, 1e-6
+    u0, p = W.robertson_params(N)
+    prob = W.robertson_problem()
+    A = getattr(B, alg)()
+    sol = B.solve(_ens(B, prob, u0, p), A, B.EnsembleB200(), trajectories=N, saveat=W.ROBERTSON_SAVEAT, dt=1e-6,
+                  abstol=abstol, reltol=reltol)
+    assert np.all(sol.retcodes == 1)
+    # (a) same expression tree: emitted model compiled for the oracle -> identical step sequences
+    model = B.build_model(prob, A)
+    ref, rc, st = oracle.solve(None, alg, u0, p, (0.0, 1e5), W.ROBERTSON_SAVEAT, 1e-6, abstol=abstol, reltol=reltol,
+                               fns=oracle_fns(oracle, B, model))
+    assert np.array_equal(sol.retcodes, rc)
+    assert np.array_equal(sol.stats[:, :3], st[:, :3])
+    ok, worst = within_tol(sol.u_array, ref, 1e-14, 1e-9)
+    assert ok, worst
+    # (b) independent hand-written C model: agreement at the solver tolerance
+    ref2, rc2, _ = oracle.solve("robertson", alg, u0, p, (0.0, 1e5), W.ROBERTSON_SAVEAT, 1e-6, abstol=abstol, reltol=reltol)
+    assert np.array_equal(sol.retcodes, rc2)
+    ok, worst = within_tol(sol.u_array, ref2, abstol, reltol)
+    assert ok, worst
+    # Robertson invariant y1+y2+y3 = 1
+    assert np.abs(sol.u_array.sum(axis=2) - 1.0).max() < 1e-9
+
+
+# ---------------------------------------------------------------- config 4: SDEs with injected increments
+def _increments(N, nsteps, nvec, n, dt, dtype, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal((N, nsteps, nvec, n)) * np.sqrt(dt)).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_em_gbm_injected_pathwise(B, gpu_lib, oracle, dtype):
+    from b200ens import workloads as W
+
+    N, nsteps = 4096, 256
+    dt = 1.0 / nsteps
+    u0, p = W.gbm_params(N, dtype=dtype)
+    dW = _increments(N, nsteps, 1, 1, dt, dtype, 11)
+    saveat = np.linspace(0, 1, 5)
+    sol = B.solve(_ens(B, W.gbm_problem(dtype), u0, p), B.EM(), B.EnsembleB200(), trajectories=N, saveat=saveat, dt=dt, dW=dW)
+    ref, rc, _ = oracle.solve("gbm", "EM", u0, p, (0.0, 1.0), saveat, dt, dtype=dtype, dW=dW, adaptive=False)
+    assert np.all(sol.retcodes == 1) and np.all(rc == 1)
+    tol = 1e-10 if dtype == np.float64 else 1e-5
+    assert np.abs(sol.u_array.astype(np.float64) - ref.astype(np.float64)).max() <= tol * max(1.0, np.abs(ref).max())
+    if dtype == np.float64:  # EM converges to the closed form u0 exp((mu - s^2/2) t + s W_t): weak sanity bound
+        WT = dW[:, :, 0, 0].sum(axis=1)
+        exact = np.exp((p[:, 0] - 0.5 * p[:, 1] ** 2) + p[:, 1] * WT)
+        assert np.median(np.abs(sol.u_array[:, -1, 0] - exact) / exact) < 0.05
+
+
+@pytest.mark.parametrize("alg,nvec", [("EM", 1), ("SOSRA", 2)])
+def test_stochastic_lorenz_injected_pathwise(B, gpu_lib, oracle, alg, nvec):
+    from b200ens import workloads as W
+
+    N, nsteps = 1024, 512
+    dt = 2.0 / nsteps
+    u0, p = W.lorenz_additive_params(N)
+    dW = _increments(N, nsteps, nvec, 3, dt, np.float64, 13)
+    saveat = np.linspace(0, 2, 9)
+    prob = W.lorenz_additive_problem(tspan=(0.0, 2.0))
+    sol = B.solve(_ens(B, prob, u0, p), getattr(B, alg)(), B.EnsembleB200(), trajectories=N, saveat=saveat, dt=dt, dW=dW)
+    ref, rc, _ = oracle.solve("lorenz_additive", alg, u0, p, (0.0, 2.0), saveat, dt, dW=dW, adaptive=False)
+    assert np.all(sol.retcodes == 1) and np.all(rc == 1)
+    assert np.abs(sol.u_array - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_em_philox_device_noise_matches_oracle(B, gpu_lib, oracle, dtype):
+    """Device-side Philox4x32-10 + Box-Muller vs the oracle's generator (same counters/keys).  log/sin/cos
+    differ by ulps between CUDA and glibc, hence a tolerance instead of bit equality."""
+    from b200ens import workloads as W
+
+    N, nsteps = 2048, 64
+    dt = 1.0 / nsteps
+    u0, p = W.gbm_params(N, dtype=dtype)
+    sol = B.solve(_ens(B, W.gbm_problem(dtype), u0, p), B.EM(), B.EnsembleB200(), trajectories=N, saveat=[1.0], dt=dt, seed=1234)
+    ref, rc, _ = oracle.solve("gbm", "EM", u0, p, (0.0, 1.0), [1.0], dt, dtype=dtype, seed=1234, adaptive=False)
+    tol = 1e-9 if dtype == np.float64 else 2e-4
+    rel = np.abs(sol.u_array.astype(np.float64) - ref.astype(np.float64)) / np.abs(ref.astype(np.float64))
+    assert rel.max() < tol, rel.max()
+    # the sample mean of GBM is exp(mu t): 2048 paths -> a few percent
+    assert abs(np.mean(sol.u_array[:, 0, 0] / np.exp(p[:, 0].astype(np.float64))) - 1.0) < 0.1
+
+
+# ---------------------------------------------------------------- config 5: Vern7 + ContinuousCallback on the 16-species network
+def test_net16_vern7_callback(B, gpu_lib, oracle):
+    from b200ens import workloads as W
+
+    N = 1024
+    tol = 1e-8
+    saveat = np.linspace(0.0, 10.0, 101)
+    u0, p = W.net16_params(N)
+    prob = W.net16_problem()
+    cb = W.net16_callback()
+    sol = B.solve(_ens(B, prob, u0, p), B.Vern7(), B.EnsembleB200(), trajectories=N, saveat=saveat, dt=0.01,
+                  abstol=tol, reltol=tol, callback=cb)
+    assert np.all(sol.retcodes == 1)
+    assert sol.stats[:, 3].max() >= 1, "no event fired in the whole ensemble: test is vacuous"
+    model = B.build_model(prob, B.Vern7(), cb)
+    ref, rc, st = oracle.solve(None, "Vern7", u0, p, (0.0, 10.0), saveat, 0.01, abstol=tol, reltol=tol, event=True,
+                               fns=oracle_fns(oracle, B, model))
+    assert np.array_equal(sol.retcodes, rc)
+    assert np.array_equal(sol.stats, st)                       # same steps, RHS calls and event counts
+    ok, worst = within_tol(sol.u_array, ref, 1e-13, 1e-10)
+    assert ok, worst
+    # independent hand-written network in the oracle: agreement at the solver tolerance (events included)
+    ref2, rc2, st2 = oracle.solve("net16", "Vern7", u0, p, (0.0, 10.0), saveat, 0.01, abstol=tol, reltol=tol, event=True)
+    assert np.array_equal(st2[:, 3], sol.stats[:, 3])
+    ok, worst = within_tol(sol.u_array, ref2, 1e-6, 1e-6)
+    assert ok, worst
+
+
+def test_reference_callback_semantics(B, gpu_lib, oracle):
+    """test/core.jl:60-79: condition(u,t,integrator) = t - 0.5 with a no-op affect! -> Success; and terminate!."""
+    from b200ens import workloads as W
+
+    prob = B.ODEProblem(W.linear, 0.5, (0.0, 1.0), [1.01])
+    cb = B.ContinuousCallback(lambda u, t, integrator: t - 0.5, lambda integrator: None)
+    sol = B.solve(prob, B.Tsit5(), callback=cb, dt=0.05, saveat=0.1)
+    assert sol.retcode == B.ReturnCode.Success and len(sol.t) == 11
+    assert sol.stats["nevents"] == 1
+    assert abs(sol.u[-1] - 0.5 * np.exp(1.01)) < 1e-3
+    cbt = B.ContinuousCallback(lambda u, t, integrator: u[0] - 0.8, lambda integrator: B.terminate_b(integrator))
+    sol2 = B.solve(prob, B.Tsit5(), callback=cbt, dt=0.05, saveat=0.1, abstol=1e-10, reltol=1e-10)
+    assert sol2.retcode == B.ReturnCode.Terminated
+    assert abs(sol2.u[-1] - 0.8) < 1e-8       # state at the event, held for the remaining save slots

@@ -388,7 +388,7 @@ def _initial_dt(prob, alg, abstol, reltol):
     abstol = 1e-6 if abstol is None else abstol
     reltol = 1e-3 if reltol is None else reltol
     u0 = prob.u0.astype(np.float64)
-    pp = list(prob.p.astype(np.float64)) + [0.0]
+    pp = list(prob.p.astype(np.float64)) if m > 0 else [0.0]
     t0, t1 = prob.tspan
     f0 = np.array(fn(list(u0), pp, t0), dtype=np.float64)
     sk = abstol + np.abs(u0) * reltol

@@ -49,6 +49,7 @@ typedef struct {
     int32_t n_save;
     int32_t noise_injected;   /* 1: dW given [N][nsteps][nvec][n]; 0: Philox4x32-10 */
     uint64_t seed;
+    uint64_t traj_offset;     /* global index of trajectory 0 (Philox counter base) */
     int32_t has_event, event_terminate, interp_points;
     int32_t save_tstops;      /* 1: saveat points are tstops (steps clipped, no interpolation) */
     void *rhs, *jac, *tgrad, *noise, *cond, *affect;

@@ -26,7 +26,7 @@ class Opts(C.Structure):
         ("t0", C.c_double), ("t1", C.c_double), ("dt", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
         ("dtmin", C.c_double), ("dtmax", C.c_double), ("qmin", C.c_double), ("qmax", C.c_double),
         ("gamma", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("qoldinit", C.c_double),
-        ("maxiters", C.c_int64), ("n_save", C.c_int32), ("noise_injected", C.c_int32), ("seed", C.c_uint64),
+        ("maxiters", C.c_int64), ("n_save", C.c_int32), ("noise_injected", C.c_int32), ("seed", C.c_uint64), ("traj_offset", C.c_uint64),
         ("has_event", C.c_int32), ("event_terminate", C.c_int32), ("interp_points", C.c_int32),
         ("save_tstops", C.c_int32),
         ("rhs", C.c_void_p), ("jac", C.c_void_p), ("tgrad", C.c_void_p), ("noise", C.c_void_p),
@@ -95,7 +95,7 @@ def fns_from_host_model(dll, f64):
 
 def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adaptive=True, dtype=np.float64,
           maxiters=100000, dW=None, seed=0, event=False, terminate=False, interp_points=10, nthreads=0,
-          fns=None, want_stats=True, save_tstops=None, **ctl):
+          fns=None, want_stats=True, save_tstops=None, traj_offset=0, **ctl):
     """Run the oracle.  model: built-in name, or fns = dict(rhs=ptr, jac=ptr, ...)."""
     L = lib()
     f64 = np.dtype(dtype) == np.float64
@@ -114,6 +114,7 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
     o.n_save = len(saveat)
     o.noise_injected = 0 if dW is None else 1
     o.seed = seed
+    o.traj_offset = traj_offset
     o.has_event, o.event_terminate, o.interp_points = int(event), int(terminate), interp_points
     if save_tstops is None:
         save_tstops = alg in ("Rodas4", "Rodas5", "Rodas5P")

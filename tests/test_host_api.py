@@ -1,0 +1,101 @@
+"""Host-side mirror of the reference interface (names /root/reference/test/qa/qa.jl, usage test/core.jl):
+problem construction, remake, prob_func handling, saveat semantics, codegen, error behaviour."""
+import numpy as np
+import pytest
+
+
+def test_exported_names_mirror_the_reference(B):
+    for name in ("ODEProblem", "SDEProblem", "EnsembleProblem", "EnsembleSolution", "ContinuousCallback", "ReturnCode",
+                 "remake", "solve", "Tsit5", "Vern7", "Rosenbrock23", "Rodas5P", "EnsembleB200"):
+        assert hasattr(B, name), name
+    assert B.ReturnCode.Success == 1 and B.ReturnCode(3).name == "MaxIters"
+
+
+def test_saveat_semantics(B):
+    from b200ens.api import _saveat_array
+
+    ts = _saveat_array(0.1, (0.0, 1.0), np.float64)       # saveat=0.1 on (0,1) -> 11 points (test/core.jl:93-95)
+    assert len(ts) == 11 and ts[0] == 0.0 and ts[-1] == 1.0
+    ts = _saveat_array(0.3, (0.0, 1.0), np.float64)       # end point appended when not on the grid
+    assert np.allclose(ts, [0, 0.3, 0.6, 0.9, 1.0])
+    assert list(_saveat_array(None, (0.0, 2.0), np.float32)) == [0.0, 2.0]
+    with pytest.raises(ValueError):
+        _saveat_array([0.5, 0.4], (0.0, 1.0), np.float64)
+    with pytest.raises(ValueError):
+        _saveat_array([0.5, 1.4], (0.0, 1.0), np.float64)
+
+
+def test_remake_and_prob_func_packing(B):
+    from b200ens import workloads as W
+    from b200ens.api import _pack
+
+    prob = W.lorenz_problem()
+    p2 = B.remake(prob, u0=[2.0, 0.0, 0.0])                # test/core.jl:84
+    assert p2.u0[0] == 2.0 and prob.u0[0] == 1.0 and p2.f is prob.f
+    eprob = B.EnsembleProblem(prob, prob_func=lambda pr, i, repeat: B.remake(pr, p=[10.0, float(i), 8 / 3]))
+    u0, p = _pack(eprob, 5, np.float64)
+    assert u0.shape == (5, 3) and list(p[:, 1]) == [1.0, 2.0, 3.0, 4.0, 5.0]   # i is 1-based like Julia
+    bad = B.EnsembleProblem(prob, prob_func=lambda pr, i, repeat: B.ODEProblem(W.robertson, pr.u0, pr.tspan, pr.p))
+    with pytest.raises(ValueError):
+        _pack(bad, 2, np.float64)
+    with pytest.raises(TypeError):
+        B.remake(prob, f=None)
+
+
+def test_codegen_rhs_jacobian_tgrad(B):
+    import sympy as sp
+    from b200ens import codegen, workloads as W
+
+    ex, us, ps, t = codegen.trace_vector_fn(W.robertson, 3, 3)
+    jac = codegen.emit_jac(ex, us)
+    assert "J[6] = (real)(0);" in jac and "J[3] = p[0];" in jac      # d(du2)/du1 = k1, d(du3)/du1 = 0
+    assert codegen.emit_tgrad(ex, t) is None                           # autonomous
+    ex2, us2, _, t2 = codegen.trace_vector_fn(lambda u, p, t: [p[0] * u[0] + sp.sin(t)], 1, 1)
+    assert "cos(t)" in codegen.emit_tgrad(ex2, t2)
+    rhs = codegen.emit_rhs(ex2)
+    assert "__device__" in rhs and "b2_rhs" in rhs and "(real)" not in rhs.split("{")[0]
+    # literals stay in `real` precision
+    ex3, *_ = codegen.trace_vector_fn(lambda u, p, t: [1.5 * u[0] ** 2 / 3], 1, 0)
+    assert "(real)" in codegen.emit_rhs(ex3) and "pow(" not in codegen.emit_rhs(ex3)
+
+
+def test_callback_tracing_and_rejection(B):
+    from b200ens import codegen
+
+    cb = B.ContinuousCallback(lambda u, t, integ: u[0] - integ.p[1], lambda integ: integ.u.__setitem__(0, integ.u[0] + 1))
+    cond, aff, term = codegen.emit_callback(cb, 2, 2)
+    assert "return -p[1] + u[0];" in cond and "u[0] = n0;" in aff and term is False
+    cbt = B.ContinuousCallback(lambda u, t, integ: t - 0.5, lambda integ: B.terminate_b(integ))
+    assert codegen.emit_callback(cbt, 1, 1)[2] is True
+
+    def opaque(u, t, integ):
+        return 1.0 if float(u[0]) > 0 else -1.0             # not symbolically traceable
+
+    with pytest.raises(NotImplementedError):
+        codegen.emit_callback(B.ContinuousCallback(opaque, lambda integ: None), 1, 1)
+    with pytest.raises(NotImplementedError):
+        B.ContinuousCallback(lambda u, t, i: t, lambda i: None, save_positions=(True, True))
+
+
+def test_solve_argument_errors(B):
+    from b200ens import workloads as W
+
+    prob = W.lorenz_problem()
+    with pytest.raises(NotImplementedError):
+        B.solve(prob, B.Tsit5(), save_everystep=True, dt=0.1)
+    with pytest.raises(TypeError):
+        B.solve(B.EnsembleProblem(prob), B.Tsit5(), B.EnsembleB200(), dt=0.1)          # trajectories missing
+    with pytest.raises(TypeError):
+        B.solve(prob, B.EM(), dt=0.1)                                                    # EM needs an SDEProblem
+    with pytest.raises(ValueError):
+        B.solve(W.gbm_problem(), B.SOSRA(), dt=0.01)                                     # multiplicative noise
+    with pytest.raises(ValueError):
+        B.solve(prob, B.Tsit5(), adaptive=False)                                         # fixed step needs dt
+
+
+def test_initial_dt_heuristic_is_sane(B):
+    from b200ens import workloads as W
+    from b200ens.api import _initial_dt
+
+    dt = _initial_dt(W.lorenz_problem(), B.Tsit5(), None, None)
+    assert 1e-6 < dt < 0.5

@@ -1,0 +1,159 @@
+"""The CPU oracle pinned against independent truths (tests/golden/, tools/gen_golden.py) and against the
+semantics the reference's own tests assert (/root/reference/test/core.jl)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ODE_ALGS = ["Tsit5", "Vern7", "Rosenbrock23", "Rodas4", "Rodas5", "Rodas5P"]
+
+
+def _load(name):
+    return json.load(open(os.path.join(G, name)))
+
+
+def test_philox_known_answers(oracle):
+    for v in _load("philox_kat.json")["vectors"]:
+        out = oracle.philox([int(x, 16) for x in v["ctr"]], [int(x, 16) for x in v["key"]])
+        assert [f"{x:08x}" for x in out] == v["out"]
+
+
+def test_fastlog2_exp2_accuracy(oracle):
+    L = oracle.lib()
+    import ctypes as C
+    L.orc_fastlog2.restype = C.c_float
+    L.orc_fastexp2.restype = C.c_float
+    xs = np.concatenate([np.logspace(-30, 30, 2001), np.linspace(1, 2, 1001)]).astype(np.float32)
+    err = max(abs(L.orc_fastlog2(C.c_float(float(x))) - np.log2(float(x))) for x in xs)
+    assert err < 6e-6
+    ys = np.linspace(-100, 100, 4001).astype(np.float32)
+    rel = max(abs(L.orc_fastexp2(C.c_float(float(y))) / 2.0 ** float(y) - 1) for y in ys)
+    assert rel < 2e-6
+    assert abs(oracle.fastpow(0.37, 0.14) / 0.37 ** 0.14 - 1) < 1e-5
+
+
+@pytest.mark.parametrize("alg", ODE_ALGS)
+def test_linear_closed_form(oracle, alg):
+    g = _load("linear.json")
+    out, rc, st = oracle.solve("linear", alg, [g["u0"]], [g["p"]], (0.0, 1.0), g["t"], 0.05, abstol=1e-10, reltol=1e-10)
+    assert rc[0] == 1                                   # ReturnCode.Success (test/core.jl:15)
+    assert out[0, 0, 0] == 0.5                          # first saved value is u0 (test/core.jl:18)
+    tol = 2e-5 if alg == "Rosenbrock23" else 1e-8
+    assert np.abs(out[0] - np.array(g["u"])).max() < tol
+
+
+@pytest.mark.parametrize("alg", ODE_ALGS)
+def test_lorenz_vs_dop853(oracle, alg):
+    g = _load("lorenz_t1.json")
+    tol = 1e-7 if alg == "Rosenbrock23" else 1e-10
+    out, rc, st = oracle.solve("lorenz", alg, [g["u0"]], [g["p"]], (0.0, 1.0), g["t"], 0.01, abstol=tol, reltol=tol)
+    assert rc[0] == 1
+    assert np.array_equal(out[0, 0], np.array(g["u0"]))  # sol.u[1] == u0 exactly (test/core.jl:34)
+    assert out.shape[1] == 11                            # saveat=0.1 on (0,1) -> 11 points (test/core.jl:93-95)
+    bound = 2e-3 if alg == "Rosenbrock23" else 2e-7
+    assert np.abs(out[0] - np.array(g["u"])).max() < bound
+
+
+def test_lorenz_sweep_default_tolerances(oracle):
+    """BASELINE config 1 settings: the non-chaotic cases must sit within a small multiple of the tolerance."""
+    g = _load("lorenz_t10.json")
+    for k, case in enumerate(g["cases"][:2]):
+        out, rc, _ = oracle.solve("lorenz", "Tsit5", [g["u0"]], [case["p"]], (0.0, 10.0), g["t"], 0.1)
+        ref = np.array(case["u"])
+        assert rc[0] == 1
+        if k == 0:   # rho = 0.5: decays to the origin, global error stays at the local tolerance
+            assert np.all(np.abs(out[0] - ref) <= 20 * (1e-6 + 1e-3 * np.abs(ref)))
+        else:        # rho = 14: long spiral transient amplifies the reltol=1e-3 local errors
+            assert np.abs(out[0, -1] - ref[-1]).max() < 0.5
+        out, rc, _ = oracle.solve("lorenz", "Tsit5", [g["u0"]], [case["p"]], (0.0, 10.0), g["t"], 0.1, abstol=1e-10, reltol=1e-10)
+        assert np.abs(out[0] - ref).max() < 1e-6
+
+
+@pytest.mark.parametrize("alg", ["Rosenbrock23", "Rodas4", "Rodas5", "Rodas5P"])
+def test_robertson_vs_radau(oracle, alg):
+    g = _load("robertson.json")
+    out, rc, st = oracle.solve("robertson", alg, [g["u0"]], [g["p"]], (0.0, 1e5), g["t"], 1e-6, abstol=1e-10, reltol=1e-8)
+    ref = np.array(g["u"])
+    assert rc[0] == 1                                    # Success to t=1e5 (test/core.jl:47-48)
+    scale = 3000 if alg == "Rosenbrock23" else 50
+    assert np.all(np.abs(out[0] - ref) <= scale * (1e-10 + 1e-8 * np.abs(ref)))
+    assert abs(out[0, -1].sum() - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("alg,order", [("Tsit5", 5), ("Vern7", 7), ("Rosenbrock23", 2), ("Rodas4", 4), ("Rodas5", 5), ("Rodas5P", 5)])
+def test_convergence_order_fixed_dt(oracle, alg, order):
+    g = _load("lorenz_t1.json")
+    ref = np.array(g["u"])[-1]
+    dts = {7: [0.05, 0.025], 2: [0.002, 0.001]}.get(order, [0.02, 0.01])
+    errs = []
+    for dt in dts:
+        out, rc, _ = oracle.solve("lorenz", alg, [g["u0"]], [g["p"]], (0.0, 1.0), [1.0], dt, adaptive=False, maxiters=10**6)
+        errs.append(np.abs(out[0, 0] - ref).max())
+    observed = np.log2(errs[0] / errs[1])
+    assert observed > order - 0.6, (observed, errs)
+
+
+def test_interpolant_orders(oracle):
+    """Dense output between steps: Tsit5 order 4, Vern7 order 6 (derived), Rosenbrock23 order 2."""
+    g = _load("lorenz_t1.json")
+    from scipy.integrate import solve_ivp
+
+    def lor(t, u):
+        s, r, b = g["p"]
+        return [s * (u[1] - u[0]), u[0] * (r - u[2]) - u[1], u[0] * u[1] - b * u[2]]
+    tq = [0.037, 0.061, 0.083]
+    ref = solve_ivp(lor, (0, 0.1), g["u0"], method="DOP853", t_eval=tq, rtol=1e-13, atol=1e-13).y.T
+    for alg, want in (("Tsit5", 4), ("Vern7", 6), ("Rosenbrock23", 2)):
+        errs = []
+        for dt in (0.1, 0.05):
+            out, rc, _ = oracle.solve("lorenz", alg, [g["u0"]], [g["p"]], (0.0, 0.1), tq, dt, adaptive=False)
+            errs.append(np.abs(out[0] - ref).max())
+        assert np.log2(errs[0] / errs[1]) > want - 0.7, (alg, errs)
+
+
+def test_retcodes_and_failure_fill(oracle):
+    out, rc, st = oracle.solve("lorenz", "Tsit5", [[1, 0, 0]], [[10, 28, 8 / 3]], (0.0, 10.0), np.arange(0, 10.5, 1), 0.1, maxiters=10)
+    assert rc[0] == oracle.RC_MAXITERS and np.isnan(out[0, -1]).all() and not np.isnan(out[0, 0]).any()
+    out, rc, st = oracle.solve("lorenz", "Tsit5", [[1, 0, 0]], [[10, np.nan, 8 / 3]], (0.0, 1.0), [1.0], 0.1)
+    assert rc[0] == oracle.RC_DTNAN
+    out, rc, st = oracle.solve("linear", "Tsit5", [[1.0]], [[400.0]], (0.0, 10.0), [10.0], 0.5, adaptive=False)
+    assert rc[0] in (oracle.RC_UNSTABLE, oracle.RC_SUCCESS)
+
+
+def test_callback_reference_semantics(oracle):
+    """test/core.jl:69-72: condition = t - 0.5, affect! = nothing -> Success, exactly one event, left of the root."""
+    out, rc, st = oracle.solve("linear", "Tsit5", [[0.5]], [[1.01, 0.5]], (0.0, 1.0), np.linspace(0, 1, 11), 0.05, event=True)
+    assert rc[0] == 1 and st[0, 3] == 1
+    assert abs(out[0, -1, 0] - 0.5 * np.exp(1.01)) < 1e-5
+
+
+def test_sde_em_strong_convergence_and_sosra_order(oracle):
+    """EM on GBM against the closed form (strong order ~0.5..1 for this scalar problem); SOSRA vs EM on the additive
+    Lorenz: SOSRA with dt is closer to a fine-dt reference than EM with the same dt."""
+    rng = np.random.default_rng(0)
+    N, fine = 400, 1024
+    dWf = rng.standard_normal((N, fine, 1, 1)) / np.sqrt(fine)
+    u0 = np.ones((N, 1))
+    p = np.tile([1.01, 0.87], (N, 1))
+    exact = np.exp((1.01 - 0.5 * 0.87 ** 2) + 0.87 * dWf[:, :, 0, 0].sum(1))
+    errs = []
+    for coarse in (64, 256):
+        dW = dWf.reshape(N, coarse, fine // coarse, 1, 1).sum(2)
+        out, rc, _ = oracle.solve("gbm", "EM", u0, p, (0.0, 1.0), [1.0], 1.0 / coarse, dW=dW, adaptive=False)
+        errs.append(np.mean(np.abs(out[:, 0, 0] - exact)))
+    assert errs[1] < 0.7 * errs[0]
+    # additive-noise Lorenz: compare coarse solutions against a fine EM reference on the same Brownian path
+    N, fine = 64, 4096
+    u0 = np.tile([1.0, 0.0, 0.0], (N, 1))
+    p = np.tile([10.0, 28.0, 8 / 3, 1.0], (N, 1))
+    dWf = rng.standard_normal((N, fine, 1, 3)) * np.sqrt(0.5 / fine)
+    ref, _, _ = oracle.solve("lorenz_additive", "EM", u0, p, (0.0, 0.5), [0.5], 0.5 / fine, dW=dWf, adaptive=False)
+    coarse = 128
+    dWc = dWf.reshape(N, coarse, fine // coarse, 1, 3).sum(2)
+    em, _, _ = oracle.solve("lorenz_additive", "EM", u0, p, (0.0, 0.5), [0.5], 0.5 / coarse, dW=dWc, adaptive=False)
+    dZ = np.zeros_like(dWc)   # dZ = 0: SOSRA degenerates to its deterministic order-1.5+ drift treatment
+    so, _, _ = oracle.solve("lorenz_additive", "SOSRA", u0, p, (0.0, 0.5), [0.5], 0.5 / coarse,
+                            dW=np.concatenate([dWc, dZ], axis=2), adaptive=False)
+    assert np.mean(np.abs(so - ref)) < 0.5 * np.mean(np.abs(em - ref))

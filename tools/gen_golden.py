@@ -1,0 +1,62 @@
+"""Generate tests/golden/*.json -- independent truths the CPU oracle is pinned against.
+
+The reference's own tests assert no trajectory value, and Julia is not
+available, so these vectors come from INDEPENDENT solvers, not from the reference:
+  * lorenz / robertson: scipy DOP853 / Radau at rtol=atol~1e-13 on the problems of
+    /root/reference/test/core.jl:22-30 and :39-46
+  * linear: closed form 0.5*exp(1.01 t)   (test/core.jl:10-13)
+  * philox: Random123 known-answer vectors for Philox4x32-10
+Run:  python tools/gen_golden.py     (needs scipy; output is committed)
+"""
+import json
+import os
+
+import numpy as np
+from scipy.integrate import solve_ivp
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def lor(t, u, s, r, b):
+    return [s * (u[1] - u[0]), u[0] * (r - u[2]) - u[1], u[0] * u[1] - b * u[2]]
+
+
+def rob(t, u, k1, k2, k3):
+    return [-k1 * u[0] + k3 * u[1] * u[2], k1 * u[0] - k2 * u[1] ** 2 - k3 * u[1] * u[2], k2 * u[1] ** 2]
+
+
+def rob_jac(t, u, k1, k2, k3):
+    return [[-k1, k3 * u[2], k3 * u[1]], [k1, -2 * k2 * u[1] - k3 * u[2], -k3 * u[1]], [0, 2 * k2 * u[1], 0]]
+
+
+ts = np.linspace(0, 1, 11)
+sol = solve_ivp(lor, (0, 1), [1.0, 0.0, 0.0], method="DOP853", t_eval=ts, rtol=1e-13, atol=1e-13, args=(10.0, 28.0, 8.0 / 3.0))
+json.dump({"problem": "lorenz test/core.jl:22-30", "u0": [1.0, 0.0, 0.0], "p": [10.0, 28.0, 8.0 / 3.0], "t": ts.tolist(),
+           "u": sol.y.T.tolist(), "source": "scipy DOP853 rtol=atol=1e-13"}, open(os.path.join(OUT, "lorenz_t1.json"), "w"), indent=1)
+
+ts = np.arange(0, 10.5, 1.0)
+rows = []
+for rho in (0.5, 14.0, 28.0):
+    s = solve_ivp(lor, (0, 10), [1.0, 0.0, 0.0], method="DOP853", t_eval=ts, rtol=1e-13, atol=1e-13, args=(10.0, rho, 8.0 / 3.0))
+    rows.append({"p": [10.0, rho, 8.0 / 3.0], "u": s.y.T.tolist()})
+json.dump({"problem": "lorenz sweep, tspan (0,10) (BASELINE config 1)", "u0": [1.0, 0.0, 0.0], "t": ts.tolist(), "cases": rows,
+           "source": "scipy DOP853 rtol=atol=1e-13 (chaotic cases are only usable at early times)"},
+          open(os.path.join(OUT, "lorenz_t10.json"), "w"), indent=1)
+
+ts = 10.0 ** np.arange(-5, 6)
+s = solve_ivp(rob, (0, 1e5), [1.0, 0.0, 0.0], method="Radau", jac=rob_jac, t_eval=ts, rtol=1e-12, atol=1e-15, args=(0.04, 3e7, 1e4))
+json.dump({"problem": "robertson test/core.jl:39-46", "u0": [1.0, 0.0, 0.0], "p": [0.04, 3e7, 1e4], "t": ts.tolist(),
+           "u": s.y.T.tolist(), "source": "scipy Radau rtol=1e-12 atol=1e-15"}, open(os.path.join(OUT, "robertson.json"), "w"), indent=1)
+
+ts = np.linspace(0, 1, 11)
+json.dump({"problem": "u'=1.01u test/core.jl:10-13", "u0": [0.5], "p": [1.01], "t": ts.tolist(),
+           "u": (0.5 * np.exp(1.01 * ts)).reshape(-1, 1).tolist(), "source": "closed form"},
+          open(os.path.join(OUT, "linear.json"), "w"), indent=1)
+
+json.dump({"source": "Random123 kat_vectors, Philox4x32-10 (SURVEY.md B.9)", "vectors": [
+    {"ctr": ["00000000"] * 4, "key": ["00000000"] * 2, "out": ["6627e8d5", "e169c58d", "bc57ac4c", "9b00dbd8"]},
+    {"ctr": ["ffffffff"] * 4, "key": ["ffffffff"] * 2, "out": ["408f276d", "41c83b0e", "a20bc7c6", "6d5451fd"]},
+    {"ctr": ["243f6a88", "85a308d3", "13198a2e", "03707344"], "key": ["a4093822", "299f31d0"],
+     "out": ["d16cfe09", "94fdcceb", "5001e420", "24126ea1"]}]}, open(os.path.join(OUT, "philox_kat.json"), "w"), indent=1)
+print("golden vectors written to", OUT)

@@ -92,3 +92,33 @@ def test_edge_cases(B, gpu_lib, oracle):
     p[3] = np.nan
     s3 = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), B.Tsit5(), B.EnsembleB200(), trajectories=64, saveat=SAVEAT, dt=0.1)
     assert s3.retcodes[3] == 6 and s3.retcodes[2] == 1
+
+
+def test_multi_device_sharding_matches_single_device(B, gpu_lib):
+    """b200ens_solve shards contiguous trajectory ranges over the devices in device_mask (host gather, no
+    collective); results must be bit-identical to the single-device run.  Needs >= 2 GPUs."""
+    from b200ens import workloads as W
+
+    ndev = gpu_lib.lib().b200ens_device_count()
+    if ndev < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    N = 100003
+    u0, p = W.lorenz_params(N, "random", seed=3, dtype=np.float32)
+    one = _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1, devices=[0])
+    many = _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1, devices=list(range(ndev)))
+    assert many.timing["n_devices"] == ndev
+    assert np.array_equal(one.u_array, many.u_array) and np.array_equal(one.retcodes, many.retcodes)
+    assert np.array_equal(one.stats, many.stats)
+
+
+def test_chunked_pipeline_matches_single_launch(B, gpu_lib, monkeypatch):
+    """The host path streams trajectories in chunks over two streams; chunking must not change results."""
+    from b200ens import workloads as W
+
+    N = 50000
+    u0, p = W.lorenz_params(N, "random", seed=4)
+    base = _solve_gpu(B, np.float64, u0, p, SAVEAT, 0.1)
+    monkeypatch.setenv("B200ENS_CHUNK", "7001")
+    chunked = _solve_gpu(B, np.float64, u0, p, SAVEAT, 0.1)
+    assert chunked.timing["launches"] == 8
+    assert np.array_equal(base.u_array, chunked.u_array) and np.array_equal(base.stats, chunked.stats)

@@ -105,6 +105,9 @@ struct b200ens_model {
     std::string name, source, log;
     std::vector<char> cubin;
     int regs = -1, smem = -1, lmem = -1, spill = 0, min_blocks = 1;
+    int block = 128;        // threads per CTA the kernel was compiled for (B2_BLOCK)
+    int ksmem = 0;          // 1: ERK stage vectors in shared memory
+    int kvec_bytes = 0;     // shared-memory bytes per thread for them
     std::mutex mu;
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
@@ -141,16 +144,16 @@ void parse_ptxas_log(b200ens_model* m) {
     }
 }
 
-std::string build_source(const b200ens_model_desc* d, int min_blocks) {
+std::string build_source(const b200ens_model_desc* d, int min_blocks, int block, int ksmem) {
     char head[1024];
     snprintf(head, sizeof head,
              "// generated by libb200ens (model '%s')\n"
              "#define B2_F64 %d\n#define B2_NSTATE %d\n#define B2_NPARAM %d\n#define B2_ALG %d\n"
              "#define B2_HAS_JAC %d\n#define B2_HAS_TGRAD %d\n#define B2_HAS_NOISE %d\n#define B2_HAS_EVENT %d\n"
-             "#define B2_BLOCK %d\n#define B2_MINBLOCKS %d\n#include \"b2_common.cuh\"\n",
+             "#define B2_BLOCK %d\n#define B2_MINBLOCKS %d\n#define B2_KSMEM %d\n#include \"b2_common.cuh\"\n",
              d->name ? d->name : "", d->dtype == B200ENS_F64 ? 1 : 0, d->n_state, d->n_param, d->alg,
              d->jac_src ? 1 : 0, d->tgrad_src ? 1 : 0, d->noise_src ? 1 : 0,
-             (d->condition_src && d->affect_src) ? 1 : 0, kBlock, min_blocks);
+             (d->condition_src && d->affect_src) ? 1 : 0, block, min_blocks, ksmem);
     std::string s = head;
     for (const char* part : {d->rhs_src, d->jac_src, d->tgrad_src, d->noise_src, d->condition_src, d->affect_src})
         if (part) {
@@ -279,30 +282,34 @@ struct LaunchPlan {
 };
 
 int plan_launch(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, long long N, int n_save, LaunchPlan* lp) {
-    const int block = kBlock;
+    const int block = m->block;
     const size_t es = m->elem();
+    const size_t ksm = m->ksmem ? (size_t)m->kvec_bytes * block : 0;
     int stride = n_save * m->n_state;
     if (stride % 2 == 0) stride += 1;  // odd row stride: conflict-free staging rows
     size_t smem = (size_t)block * stride * es;
     int nb_direct = 0, nb_staged = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_direct, (const void*)m->kernel, block, 0));
+    if (ksm > 48 * 1024)
+        CU(cudaFuncSetAttribute((const void*)m->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_direct, (const void*)m->kernel, block, ksm));
     bool staged = false;
     // Measured on B200 (profiles/): for the saveat shapes of configs 1-4 direct global stores are ~3%
     // faster than shared-memory staging (L2 merges the 12-byte rows), so auto means direct.
-    if (o->stage_outputs > 0 && n_save > 0 && smem <= 200 * 1024) {
-        if (smem > 48 * 1024)
-            CU(cudaFuncSetAttribute((const void*)m->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_staged, (const void*)m->kernel, block, smem));
+    if (o->stage_outputs > 0 && n_save > 0 && smem + ksm <= 200 * 1024) {
+        if (smem + ksm > 48 * 1024)
+            CU(cudaFuncSetAttribute((const void*)m->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + ksm)));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_staged, (const void*)m->kernel, block, smem + ksm));
         // stage when it costs at most a quarter of the occupancy (or when forced)
         staged = nb_staged >= 1 && (o->stage_outputs > 0 || 4 * nb_staged >= 3 * nb_direct);
     }
     if (o->stage_outputs > 0 && !staged)
         return fail(B200ENS_E_UNSUPPORTED, "stage_outputs=1 but %zu bytes of shared memory per block do not fit", smem);
-    const int nb = staged ? nb_staged : nb_direct;
+    int nb = staged ? nb_staged : nb_direct;
+    if (const char* e = getenv("B200ENS_BLOCKS_PER_SM")) nb = std::max(1, std::min(nb, atoi(e)));  // experiments
     if (nb < 1) return fail(B200ENS_E_CUDA, "kernel cannot be resident (occupancy 0)");
     lp->block = block;
     lp->stride = staged ? stride : 0;
-    lp->smem = staged ? (int)smem : 0;
+    lp->smem = (int)((staged ? smem : 0) + ksm);
     const long long want = (N + block - 1) / block;
     lp->grid = (int)std::max<long long>(1, std::min<long long>((long long)nb * d->sms, want));
     int refill = o->refill_threshold;
@@ -566,12 +573,49 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     int mb = d->dtype == B200ENS_F64 ? 5 : 7;
     if (const char* e = getenv("B200ENS_MINBLOCKS")) mb = std::max(1, atoi(e));
     int rc = 0;
-    for (;; mb--) {
-        m->source = build_source(d, mb);
-        rc = nvrtc_compile(m.get());
-        if (rc) break;
-        parse_ptxas_log(m.get());
-        if (m->spill <= 96 || mb <= 1 || getenv("B200ENS_MINBLOCKS")) break;
+    const char* force_k = getenv("B200ENS_KSMEM");
+    const int nvec = d->alg == B200ENS_TSIT5 ? 7 : d->alg == B200ENS_VERN7 ? 14 : 0;
+    bool try_regs = !(force_k && atoi(force_k) == 1 && nvec);
+    if (try_regs) {
+        for (;; mb--) {
+            m->source = build_source(d, mb, kBlock, 0);
+            rc = nvrtc_compile(m.get());
+            if (rc) break;
+            parse_ptxas_log(m.get());
+            if (m->spill <= 96 || mb <= 1 || getenv("B200ENS_MINBLOCKS")) break;
+        }
+    }
+    // Large systems: the k-vectors do not fit the register file (config 5: n=16 f64 Vern7 spilled 4 KB per
+    // thread and was DRAM-bound on local-memory traffic).  Recompile with the stage vectors in shared memory,
+    // CTA size chosen so that two CTAs fit in the 227 KB of an SM.
+    if (!rc && nvec && ((try_regs && m->spill > 6000 && !(force_k && atoi(force_k) == 0)) || !try_regs)) {
+        const int per_thread = nvec * d->n_state * (d->dtype == B200ENS_F64 ? 8 : 4);
+        int block = std::min(128, (114688 / per_thread) / 32 * 32);
+        if (block >= 32) {
+            auto keep_src = m->source;
+            auto keep_cubin = m->cubin;
+            auto keep_log = m->log;
+            const int keep_spill = m->spill, keep_regs = m->regs, keep_lmem = m->lmem, keep_smem = m->smem;
+            m->source = build_source(d, 1, block, 1);
+            int rc2 = nvrtc_compile(m.get());
+            if (!rc2) parse_ptxas_log(m.get());
+            if (!rc2 && (!try_regs || m->spill < keep_spill)) {
+                m->ksmem = 1;
+                m->block = block;
+                m->kvec_bytes = per_thread;
+                mb = 1;
+            } else if (try_regs) {
+                m->source = keep_src;
+                m->cubin = keep_cubin;
+                m->log = keep_log;
+                m->spill = keep_spill;
+                m->regs = keep_regs;
+                m->lmem = keep_lmem;
+                m->smem = keep_smem;
+            } else {
+                rc = rc2;
+            }
+        }
     }
     m->min_blocks = mb;
     if (log && log_len) {

@@ -18,6 +18,9 @@ typedef float real;
 #define B2_EPS 1.1920928955078125e-7f
 #endif
 
+#ifndef B2_KSMEM
+#define B2_KSMEM 0   // 1: ERK stage vectors live in shared memory (large n_state), see b2_erk.cuh
+#endif
 #define B2_N B2_NSTATE
 #define B2_NPA (B2_NPARAM > 0 ? B2_NPARAM : 1)
 #define B2_FULL 0xffffffffu

@@ -7,78 +7,106 @@
 #include "b2_common.cuh"
 #include "tableaus_gen.cuh"
 
+// ---- stage-vector storage.  Small systems keep every k-vector in registers.  When n_state x stages
+// no longer fits the register file (ptxas spills: config 5, n=16 f64 Vern7 spilled 4 KB/thread and became
+// DRAM-bound on local-memory traffic, profiles/r1_net16_*), the model is recompiled with B2_KSMEM=1 and the
+// k-vectors live in shared memory as [vector][component][thread] (bank-conflict-free, no spills).
+#if B2_KSMEM
+#define B2_KSTRIDE B2_BLOCK
+#define B2_KDECL(name) real* name
+#define B2_KBIND(name, slot) name = kbase + (size_t)(slot) * B2_N * B2_BLOCK
+// RHS into a shared-memory vector: evaluate into registers, then store
+#define B2_RHS_TO(k, x, t_)                                  \
+    do {                                                     \
+        real f_[B2_N];                                       \
+        b2_rhs(f_, x, p, t_);                                \
+        _Pragma("unroll") for (int i_ = 0; i_ < B2_N; i_++) KV(k, i_) = f_[i_]; \
+    } while (0)
+#else
+#define B2_KSTRIDE 1
+#define B2_KDECL(name) real name[B2_N]
+#define B2_KBIND(name, slot)
+#define B2_RHS_TO(k, x, t_) b2_rhs(k, x, p, t_)
+#endif
+#define KV(name, i) name[(i) * B2_KSTRIDE]
+
 #define TS(x) ((real)(B2T_TSIT5_##x))
 
 struct B2Tsit5 {
     static constexpr int ORDER = 5;
-    real k1[B2_N], k2[B2_N], k3[B2_N], k4[B2_N], k5[B2_N], k6[B2_N], k7[B2_N];
+    static constexpr int NVEC = 7;   // k-vectors held per thread (shared-memory slots when B2_KSMEM)
+    B2_KDECL(k1); B2_KDECL(k2); B2_KDECL(k3); B2_KDECL(k4); B2_KDECL(k5); B2_KDECL(k6); B2_KDECL(k7);
+    __device__ __forceinline__ void bind(real* kbase) {
+        (void)kbase;
+        B2_KBIND(k1, 0); B2_KBIND(k2, 1); B2_KBIND(k3, 2); B2_KBIND(k4, 3); B2_KBIND(k5, 4); B2_KBIND(k6, 5); B2_KBIND(k7, 6);
+    }
 
     __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {
-        b2_rhs(k1, u, p, t);
+        B2_RHS_TO(k1, u, t);
     }
     // one step attempt from (up, t) with k1 = f(up, t); writes the proposal u and dt*error estimate
     __device__ __forceinline__ void step(const real (&up)[B2_N], const real (&p)[B2_NPA], real t, real dt,
                                          real (&u)[B2_N], real (&ut)[B2_N], bool adaptive, int& nf) {
         real tmp[B2_N];
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) tmp[i] = b2_fma(dt, TS(a21) * k1[i], up[i]);
-        b2_rhs(k2, tmp, p, t + TS(c2) * dt);
+        for (int i = 0; i < B2_N; i++) tmp[i] = b2_fma(dt, TS(a21) * KV(k1, i), up[i]);
+        B2_RHS_TO(k2, tmp, t + TS(c2) * dt);
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = TS(a31) * k1[i];
-            s = b2_fma(TS(a32), k2[i], s);
+            real s = TS(a31) * KV(k1, i);
+            s = b2_fma(TS(a32), KV(k2, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
         }
-        b2_rhs(k3, tmp, p, t + TS(c3) * dt);
+        B2_RHS_TO(k3, tmp, t + TS(c3) * dt);
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = TS(a41) * k1[i];
-            s = b2_fma(TS(a42), k2[i], s);
-            s = b2_fma(TS(a43), k3[i], s);
+            real s = TS(a41) * KV(k1, i);
+            s = b2_fma(TS(a42), KV(k2, i), s);
+            s = b2_fma(TS(a43), KV(k3, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
         }
-        b2_rhs(k4, tmp, p, t + TS(c4) * dt);
+        B2_RHS_TO(k4, tmp, t + TS(c4) * dt);
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = TS(a51) * k1[i];
-            s = b2_fma(TS(a52), k2[i], s);
-            s = b2_fma(TS(a53), k3[i], s);
-            s = b2_fma(TS(a54), k4[i], s);
+            real s = TS(a51) * KV(k1, i);
+            s = b2_fma(TS(a52), KV(k2, i), s);
+            s = b2_fma(TS(a53), KV(k3, i), s);
+            s = b2_fma(TS(a54), KV(k4, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
         }
-        b2_rhs(k5, tmp, p, t + TS(c5) * dt);
+        B2_RHS_TO(k5, tmp, t + TS(c5) * dt);
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = TS(a61) * k1[i];
-            s = b2_fma(TS(a62), k2[i], s);
-            s = b2_fma(TS(a63), k3[i], s);
-            s = b2_fma(TS(a64), k4[i], s);
-            s = b2_fma(TS(a65), k5[i], s);
+            real s = TS(a61) * KV(k1, i);
+            s = b2_fma(TS(a62), KV(k2, i), s);
+            s = b2_fma(TS(a63), KV(k3, i), s);
+            s = b2_fma(TS(a64), KV(k4, i), s);
+            s = b2_fma(TS(a65), KV(k5, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
         }
-        b2_rhs(k6, tmp, p, t + dt);
+        B2_RHS_TO(k6, tmp, t + dt);
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = TS(a71) * k1[i];
-            s = b2_fma(TS(a72), k2[i], s);
-            s = b2_fma(TS(a73), k3[i], s);
-            s = b2_fma(TS(a74), k4[i], s);
-            s = b2_fma(TS(a75), k5[i], s);
-            s = b2_fma(TS(a76), k6[i], s);
+            real s = TS(a71) * KV(k1, i);
+            s = b2_fma(TS(a72), KV(k2, i), s);
+            s = b2_fma(TS(a73), KV(k3, i), s);
+            s = b2_fma(TS(a74), KV(k4, i), s);
+            s = b2_fma(TS(a75), KV(k5, i), s);
+            s = b2_fma(TS(a76), KV(k6, i), s);
             u[i] = b2_fma(dt, s, up[i]);
         }
-        b2_rhs(k7, u, p, t + dt);
+        B2_RHS_TO(k7, u, t + dt);
         nf += 6;
         if (adaptive) {
 #pragma unroll
             for (int i = 0; i < B2_N; i++) {
-                real s = TS(btilde1) * k1[i];
-                s = b2_fma(TS(btilde2), k2[i], s);
-                s = b2_fma(TS(btilde3), k3[i], s);
-                s = b2_fma(TS(btilde4), k4[i], s);
-                s = b2_fma(TS(btilde5), k5[i], s);
-                s = b2_fma(TS(btilde6), k6[i], s);
-                s = b2_fma(TS(btilde7), k7[i], s);
+                real s = TS(btilde1) * KV(k1, i);
+                s = b2_fma(TS(btilde2), KV(k2, i), s);
+                s = b2_fma(TS(btilde3), KV(k3, i), s);
+                s = b2_fma(TS(btilde4), KV(k4, i), s);
+                s = b2_fma(TS(btilde5), KV(k5, i), s);
+                s = b2_fma(TS(btilde6), KV(k6, i), s);
+                s = b2_fma(TS(btilde7), KV(k7, i), s);
                 ut[i] = dt * s;
             }
         }
@@ -95,20 +123,26 @@ struct B2Tsit5 {
 #undef TSB
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = b1 * k1[i];
-            s = b2_fma(b2, k2[i], s);
-            s = b2_fma(b3, k3[i], s);
-            s = b2_fma(b4, k4[i], s);
-            s = b2_fma(b5, k5[i], s);
-            s = b2_fma(b6, k6[i], s);
-            s = b2_fma(b7, k7[i], s);
+            real s = b1 * KV(k1, i);
+            s = b2_fma(b2, KV(k2, i), s);
+            s = b2_fma(b3, KV(k3, i), s);
+            s = b2_fma(b4, KV(k4, i), s);
+            s = b2_fma(b5, KV(k5, i), s);
+            s = b2_fma(b6, KV(k6, i), s);
+            s = b2_fma(b7, KV(k7, i), s);
             out[i] = b2_fma(dt, s, up[i]);
         }
     }
     // FSAL: k7 = f(u_new) becomes the next step's k1
     __device__ __forceinline__ void advance() {
+#if B2_KSMEM
+        real* t_ = k1;
+        k1 = k7;
+        k7 = t_;
+#else
 #pragma unroll
         for (int i = 0; i < B2_N; i++) k1[i] = k7[i];
+#endif
     }
 };
 #undef TS
@@ -118,121 +152,128 @@ struct B2Tsit5 {
 
 struct B2Vern7 {
     static constexpr int ORDER = 7;
-    // k2 and k3 only feed stages 3/4, so they share scratch; k10 is the error-only stage.
-    real k1[B2_N], k4[B2_N], k5[B2_N], k6[B2_N], k7[B2_N], k8[B2_N], k9[B2_N], k11[B2_N];
-    real k12[B2_N], k13[B2_N], k14[B2_N], k15[B2_N], k16[B2_N];
+    // k2 (feeds stage 3 only) and k10 (error-only stage) are step-local register scratch.
+    static constexpr int NVEC = 14;
+    B2_KDECL(k1); B2_KDECL(k3); B2_KDECL(k4); B2_KDECL(k5); B2_KDECL(k6); B2_KDECL(k7); B2_KDECL(k8); B2_KDECL(k9);
+    B2_KDECL(k11); B2_KDECL(k12); B2_KDECL(k13); B2_KDECL(k14); B2_KDECL(k15); B2_KDECL(k16);
+    __device__ __forceinline__ void bind(real* kbase) {
+        (void)kbase;
+        B2_KBIND(k1, 0); B2_KBIND(k3, 1); B2_KBIND(k4, 2); B2_KBIND(k5, 3); B2_KBIND(k6, 4); B2_KBIND(k7, 5); B2_KBIND(k8, 6);
+        B2_KBIND(k9, 7); B2_KBIND(k11, 8); B2_KBIND(k12, 9); B2_KBIND(k13, 10); B2_KBIND(k14, 11); B2_KBIND(k15, 12);
+        B2_KBIND(k16, 13);
+    }
     bool have_extra;
 
     __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {
-        b2_rhs(k1, u, p, t);
+        B2_RHS_TO(k1, u, t);
         have_extra = false;
     }
     __device__ __forceinline__ void step(const real (&up)[B2_N], const real (&p)[B2_NPA], real t, real dt,
                                          real (&u)[B2_N], real (&ut)[B2_N], bool adaptive, int& nf) {
-        real tmp[B2_N], k2[B2_N], k3[B2_N];
+        real tmp[B2_N], q2[B2_N];
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) tmp[i] = b2_fma(dt, V7(a0201) * k1[i], up[i]);
-        b2_rhs(k2, tmp, p, t + V7(c2) * dt);
-#pragma unroll
-        for (int i = 0; i < B2_N; i++) {
-            real s = V7(a0301) * k1[i];
-            s = b2_fma(V7(a0302), k2[i], s);
-            tmp[i] = b2_fma(dt, s, up[i]);
-        }
-        b2_rhs(k3, tmp, p, t + V7(c3) * dt);
+        for (int i = 0; i < B2_N; i++) tmp[i] = b2_fma(dt, V7(a0201) * KV(k1, i), up[i]);
+        b2_rhs(q2, tmp, p, t + V7(c2) * dt);
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = V7(a0401) * k1[i];
-            s = b2_fma(V7(a0403), k3[i], s);
+            real s = V7(a0301) * KV(k1, i);
+            s = b2_fma(V7(a0302), q2[i], s);
             tmp[i] = b2_fma(dt, s, up[i]);
         }
-        b2_rhs(k4, tmp, p, t + V7(c4) * dt);
+        B2_RHS_TO(k3, tmp, t + V7(c3) * dt);
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = V7(a0501) * k1[i];
-            s = b2_fma(V7(a0503), k3[i], s);
-            s = b2_fma(V7(a0504), k4[i], s);
+            real s = V7(a0401) * KV(k1, i);
+            s = b2_fma(V7(a0403), KV(k3, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
         }
-        b2_rhs(k5, tmp, p, t + V7(c5) * dt);
+        B2_RHS_TO(k4, tmp, t + V7(c4) * dt);
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = V7(a0601) * k1[i];
-            s = b2_fma(V7(a0603), k3[i], s);
-            s = b2_fma(V7(a0604), k4[i], s);
-            s = b2_fma(V7(a0605), k5[i], s);
+            real s = V7(a0501) * KV(k1, i);
+            s = b2_fma(V7(a0503), KV(k3, i), s);
+            s = b2_fma(V7(a0504), KV(k4, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
         }
-        b2_rhs(k6, tmp, p, t + V7(c6) * dt);
+        B2_RHS_TO(k5, tmp, t + V7(c5) * dt);
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = V7(a0701) * k1[i];
-            s = b2_fma(V7(a0703), k3[i], s);
-            s = b2_fma(V7(a0704), k4[i], s);
-            s = b2_fma(V7(a0705), k5[i], s);
-            s = b2_fma(V7(a0706), k6[i], s);
+            real s = V7(a0601) * KV(k1, i);
+            s = b2_fma(V7(a0603), KV(k3, i), s);
+            s = b2_fma(V7(a0604), KV(k4, i), s);
+            s = b2_fma(V7(a0605), KV(k5, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
         }
-        b2_rhs(k7, tmp, p, t + V7(c7) * dt);
+        B2_RHS_TO(k6, tmp, t + V7(c6) * dt);
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = V7(a0801) * k1[i];
-            s = b2_fma(V7(a0803), k3[i], s);
-            s = b2_fma(V7(a0804), k4[i], s);
-            s = b2_fma(V7(a0805), k5[i], s);
-            s = b2_fma(V7(a0806), k6[i], s);
-            s = b2_fma(V7(a0807), k7[i], s);
+            real s = V7(a0701) * KV(k1, i);
+            s = b2_fma(V7(a0703), KV(k3, i), s);
+            s = b2_fma(V7(a0704), KV(k4, i), s);
+            s = b2_fma(V7(a0705), KV(k5, i), s);
+            s = b2_fma(V7(a0706), KV(k6, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
         }
-        b2_rhs(k8, tmp, p, t + V7(c8) * dt);
+        B2_RHS_TO(k7, tmp, t + V7(c7) * dt);
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = V7(a0901) * k1[i];
-            s = b2_fma(V7(a0903), k3[i], s);
-            s = b2_fma(V7(a0904), k4[i], s);
-            s = b2_fma(V7(a0905), k5[i], s);
-            s = b2_fma(V7(a0906), k6[i], s);
-            s = b2_fma(V7(a0907), k7[i], s);
-            s = b2_fma(V7(a0908), k8[i], s);
+            real s = V7(a0801) * KV(k1, i);
+            s = b2_fma(V7(a0803), KV(k3, i), s);
+            s = b2_fma(V7(a0804), KV(k4, i), s);
+            s = b2_fma(V7(a0805), KV(k5, i), s);
+            s = b2_fma(V7(a0806), KV(k6, i), s);
+            s = b2_fma(V7(a0807), KV(k7, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
         }
-        b2_rhs(k9, tmp, p, t + dt);
-        real k10[B2_N];
+        B2_RHS_TO(k8, tmp, t + V7(c8) * dt);
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) {
+            real s = V7(a0901) * KV(k1, i);
+            s = b2_fma(V7(a0903), KV(k3, i), s);
+            s = b2_fma(V7(a0904), KV(k4, i), s);
+            s = b2_fma(V7(a0905), KV(k5, i), s);
+            s = b2_fma(V7(a0906), KV(k6, i), s);
+            s = b2_fma(V7(a0907), KV(k7, i), s);
+            s = b2_fma(V7(a0908), KV(k8, i), s);
+            tmp[i] = b2_fma(dt, s, up[i]);
+        }
+        B2_RHS_TO(k9, tmp, t + dt);
+        real q10[B2_N];
         if (adaptive) {
 #pragma unroll
             for (int i = 0; i < B2_N; i++) {
-                real s = V7(a1001) * k1[i];
-                s = b2_fma(V7(a1003), k3[i], s);
-                s = b2_fma(V7(a1004), k4[i], s);
-                s = b2_fma(V7(a1005), k5[i], s);
-                s = b2_fma(V7(a1006), k6[i], s);
-                s = b2_fma(V7(a1007), k7[i], s);
+                real s = V7(a1001) * KV(k1, i);
+                s = b2_fma(V7(a1003), KV(k3, i), s);
+                s = b2_fma(V7(a1004), KV(k4, i), s);
+                s = b2_fma(V7(a1005), KV(k5, i), s);
+                s = b2_fma(V7(a1006), KV(k6, i), s);
+                s = b2_fma(V7(a1007), KV(k7, i), s);
                 tmp[i] = b2_fma(dt, s, up[i]);
             }
-            b2_rhs(k10, tmp, p, t + dt);
+            b2_rhs(q10, tmp, p, t + dt);
         }
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = V7(b1) * k1[i];
-            s = b2_fma(V7(b4), k4[i], s);
-            s = b2_fma(V7(b5), k5[i], s);
-            s = b2_fma(V7(b6), k6[i], s);
-            s = b2_fma(V7(b7), k7[i], s);
-            s = b2_fma(V7(b8), k8[i], s);
-            s = b2_fma(V7(b9), k9[i], s);
+            real s = V7(b1) * KV(k1, i);
+            s = b2_fma(V7(b4), KV(k4, i), s);
+            s = b2_fma(V7(b5), KV(k5, i), s);
+            s = b2_fma(V7(b6), KV(k6, i), s);
+            s = b2_fma(V7(b7), KV(k7, i), s);
+            s = b2_fma(V7(b8), KV(k8, i), s);
+            s = b2_fma(V7(b9), KV(k9, i), s);
             u[i] = b2_fma(dt, s, up[i]);
         }
         if (adaptive) {
 #pragma unroll
             for (int i = 0; i < B2_N; i++) {
-                real s = V7(btilde1) * k1[i];
-                s = b2_fma(V7(btilde4), k4[i], s);
-                s = b2_fma(V7(btilde5), k5[i], s);
-                s = b2_fma(V7(btilde6), k6[i], s);
-                s = b2_fma(V7(btilde7), k7[i], s);
-                s = b2_fma(V7(btilde8), k8[i], s);
-                s = b2_fma(V7(btilde9), k9[i], s);
-                s = b2_fma(V7(btilde10), k10[i], s);
+                real s = V7(btilde1) * KV(k1, i);
+                s = b2_fma(V7(btilde4), KV(k4, i), s);
+                s = b2_fma(V7(btilde5), KV(k5, i), s);
+                s = b2_fma(V7(btilde6), KV(k6, i), s);
+                s = b2_fma(V7(btilde7), KV(k7, i), s);
+                s = b2_fma(V7(btilde8), KV(k8, i), s);
+                s = b2_fma(V7(btilde9), KV(k9, i), s);
+                s = b2_fma(V7(btilde10), q10[i], s);
                 ut[i] = dt * s;
             }
         }
@@ -241,7 +282,7 @@ struct B2Vern7 {
     }
     // k11 = f(u_new): dense-output stage 11 and the next step's k1 (Vern7 is not FSAL in the step itself)
     __device__ __forceinline__ void accepted(const real (&u)[B2_N], const real (&p)[B2_NPA], real tnew, int& nf) {
-        b2_rhs(k11, u, p, tnew);
+        B2_RHS_TO(k11, u, tnew);
         nf += 1;
     }
     // lazy stages 12..16, only on steps that are interpolated (saveat / event search)
@@ -251,26 +292,26 @@ struct B2Vern7 {
         real tmp[B2_N];
 #define V7ROW(r, KLAST)                                                    \
     _Pragma("unroll") for (int i = 0; i < B2_N; i++) {                     \
-        real s = V7X(a##r##01) * k1[i];                                    \
-        s = b2_fma(V7X(a##r##04), k4[i], s);                               \
-        s = b2_fma(V7X(a##r##05), k5[i], s);                               \
-        s = b2_fma(V7X(a##r##06), k6[i], s);                               \
-        s = b2_fma(V7X(a##r##07), k7[i], s);                               \
-        s = b2_fma(V7X(a##r##08), k8[i], s);                               \
-        s = b2_fma(V7X(a##r##09), k9[i], s);                               \
-        s = b2_fma(V7X(a##r##11), k11[i], s);                              \
+        real s = V7X(a##r##01) * KV(k1, i);                                    \
+        s = b2_fma(V7X(a##r##04), KV(k4, i), s);                               \
+        s = b2_fma(V7X(a##r##05), KV(k5, i), s);                               \
+        s = b2_fma(V7X(a##r##06), KV(k6, i), s);                               \
+        s = b2_fma(V7X(a##r##07), KV(k7, i), s);                               \
+        s = b2_fma(V7X(a##r##08), KV(k8, i), s);                               \
+        s = b2_fma(V7X(a##r##09), KV(k9, i), s);                               \
+        s = b2_fma(V7X(a##r##11), KV(k11, i), s);                              \
         KLAST tmp[i] = b2_fma(dt, s, up[i]);                               \
     }
         V7ROW(12, )
-        b2_rhs(k12, tmp, p, t + V7X(c12) * dt);
-        V7ROW(13, s = b2_fma(V7X(a1312), k12[i], s);)
-        b2_rhs(k13, tmp, p, t + V7X(c13) * dt);
-        V7ROW(14, s = b2_fma(V7X(a1412), k12[i], s); s = b2_fma(V7X(a1413), k13[i], s);)
-        b2_rhs(k14, tmp, p, t + V7X(c14) * dt);
-        V7ROW(15, s = b2_fma(V7X(a1512), k12[i], s); s = b2_fma(V7X(a1513), k13[i], s);)
-        b2_rhs(k15, tmp, p, t + V7X(c15) * dt);
-        V7ROW(16, s = b2_fma(V7X(a1612), k12[i], s); s = b2_fma(V7X(a1613), k13[i], s);)
-        b2_rhs(k16, tmp, p, t + V7X(c16) * dt);
+        B2_RHS_TO(k12, tmp, t + V7X(c12) * dt);
+        V7ROW(13, s = b2_fma(V7X(a1312), KV(k12, i), s);)
+        B2_RHS_TO(k13, tmp, t + V7X(c13) * dt);
+        V7ROW(14, s = b2_fma(V7X(a1412), KV(k12, i), s); s = b2_fma(V7X(a1413), KV(k13, i), s);)
+        B2_RHS_TO(k14, tmp, t + V7X(c14) * dt);
+        V7ROW(15, s = b2_fma(V7X(a1512), KV(k12, i), s); s = b2_fma(V7X(a1513), KV(k13, i), s);)
+        B2_RHS_TO(k15, tmp, t + V7X(c15) * dt);
+        V7ROW(16, s = b2_fma(V7X(a1612), KV(k12, i), s); s = b2_fma(V7X(a1613), KV(k13, i), s);)
+        B2_RHS_TO(k16, tmp, t + V7X(c16) * dt);
 #undef V7ROW
         nf += 5;
         have_extra = true;
@@ -286,25 +327,31 @@ struct B2Vern7 {
 #undef V7B
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            real s = b01 * k1[i];
-            s = b2_fma(b04, k4[i], s);
-            s = b2_fma(b05, k5[i], s);
-            s = b2_fma(b06, k6[i], s);
-            s = b2_fma(b07, k7[i], s);
-            s = b2_fma(b08, k8[i], s);
-            s = b2_fma(b09, k9[i], s);
-            s = b2_fma(b11, k11[i], s);
-            s = b2_fma(b12, k12[i], s);
-            s = b2_fma(b13, k13[i], s);
-            s = b2_fma(b14, k14[i], s);
-            s = b2_fma(b15, k15[i], s);
-            s = b2_fma(b16, k16[i], s);
+            real s = b01 * KV(k1, i);
+            s = b2_fma(b04, KV(k4, i), s);
+            s = b2_fma(b05, KV(k5, i), s);
+            s = b2_fma(b06, KV(k6, i), s);
+            s = b2_fma(b07, KV(k7, i), s);
+            s = b2_fma(b08, KV(k8, i), s);
+            s = b2_fma(b09, KV(k9, i), s);
+            s = b2_fma(b11, KV(k11, i), s);
+            s = b2_fma(b12, KV(k12, i), s);
+            s = b2_fma(b13, KV(k13, i), s);
+            s = b2_fma(b14, KV(k14, i), s);
+            s = b2_fma(b15, KV(k15, i), s);
+            s = b2_fma(b16, KV(k16, i), s);
             out[i] = b2_fma(dt, s, up[i]);
         }
     }
     __device__ __forceinline__ void advance() {
+#if B2_KSMEM
+        real* t_ = k1;
+        k1 = k11;
+        k11 = t_;
+#else
 #pragma unroll
         for (int i = 0; i < B2_N; i++) k1[i] = k11[i];
+#endif
     }
 };
 #undef V7

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libb200ens.so")
 F32, F64 = 0, 1
 ALG_IDS = {"Tsit5": 1, "Vern7": 2, "Rosenbrock23": 3, "Rodas5": 4, "Rodas5P": 5, "EM": 6, "SOSRA": 7, "Rodas4": 8}
 MODEL_FAST_MATH = 1
+MODEL_PACKED_X2 = 2
 
 E_NODEVICE = -3
 
@@ -123,14 +124,14 @@ class Model:
     """A compiled (problem functions x algorithm x dtype) kernel: b200ens_model*."""
 
     def __init__(self, n_state, n_param, dtype, alg, rhs_src, jac_src=None, tgrad_src=None, noise_src=None,
-                 condition_src=None, affect_src=None, name="model", fast_math=False):
+                 condition_src=None, affect_src=None, name="model", fast_math=False, packed_x2=False):
         L = lib()
         d = ModelDesc()
         d.struct_size = C.sizeof(ModelDesc)
         d.n_state, d.n_param = n_state, n_param
         d.dtype = F64 if np.dtype(dtype) == np.float64 else F32
         d.alg = ALG_IDS[alg] if isinstance(alg, str) else int(alg)
-        d.flags = MODEL_FAST_MATH if fast_math else 0
+        d.flags = (MODEL_FAST_MATH if fast_math else 0) | (MODEL_PACKED_X2 if packed_x2 else 0)
         enc = lambda s: s.encode() if s is not None else None
         d.rhs_src, d.jac_src, d.tgrad_src = enc(rhs_src), enc(jac_src), enc(tgrad_src)
         d.noise_src, d.condition_src, d.affect_src = enc(noise_src), enc(condition_src), enc(affect_src)

@@ -157,11 +157,12 @@ class EnsembleB200:
     devices: iterable of CUDA device ids (None = all visible); refill_threshold: idle lanes of a
     warp before it fetches new trajectories (0 = auto); stage_outputs: -1 auto / 0 / 1."""
 
-    def __init__(self, devices=None, refill_threshold=0, stage_outputs=-1, fast_math=False):
+    def __init__(self, devices=None, refill_threshold=0, stage_outputs=-1, fast_math=False, packed_x2=False):
         self.devices = devices
         self.refill_threshold = refill_threshold
         self.stage_outputs = stage_outputs
         self.fast_math = fast_math
+        self.packed_x2 = packed_x2   # Float32 Tsit5: two trajectories per thread in packed FP32 (FFMA2)
 
 
 # ---------------------------------------------------------------- solutions
@@ -223,11 +224,11 @@ class _LazySeq:
 _model_cache = {}
 
 
-def build_model(prob, alg, callback=None, fast_math=False):
+def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False):
     """Trace prob.f (and g / callback), emit CUDA C, JIT it for sm_100a.  Cached per function objects."""
     n, m = prob.u0.shape[0], prob.p.shape[0]
     dtype = prob.u0.dtype
-    key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math)
+    key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math, packed_x2)
     hit = _model_cache.get(key)
     if hit is not None and hit[1] is prob.f:
         return hit[0]
@@ -246,7 +247,8 @@ def build_model(prob, alg, callback=None, fast_math=False):
     terminate = False
     if callback is not None:
         srcs["condition_src"], srcs["affect_src"], terminate = codegen.emit_callback(callback, n, m)
-    model = _lib.Model(n, m, dtype, alg.name, name=getattr(prob.f, "__name__", "model"), fast_math=fast_math, **srcs)
+    model = _lib.Model(n, m, dtype, alg.name, name=getattr(prob.f, "__name__", "model"), fast_math=fast_math,
+                       packed_x2=packed_x2, **srcs)
     model.sources = srcs
     model.event_terminate = terminate
     _model_cache[key] = (model, prob.f)
@@ -325,7 +327,7 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, 
         if not adaptive:
             raise ValueError("fixed-step solves need dt")
         dt = _initial_dt(base, alg, abstol, reltol)
-    model = build_model(base, alg, callback, ensemblealg.fast_math)
+    model = build_model(base, alg, callback, ensemblealg.fast_math, ensemblealg.packed_x2)
     ts = _saveat_array(saveat, base.tspan, dtype)
     t_pack = time.perf_counter()
     u0, p = _pack(eprob, N, dtype)

@@ -16,6 +16,9 @@
 #define B2_HAS_NOISE 1
 #define B2_HAS_EVENT 0
 #define B2_BLOCK 128
+#ifdef AOT_X2
+#define B2_X2 1
+#endif
 #ifndef B2_MINBLOCKS
 #define B2_MINBLOCKS 1
 #endif

@@ -108,9 +108,11 @@ struct b200ens_model {
     int block = 128;        // threads per CTA the kernel was compiled for (B2_BLOCK)
     int ksmem = 0;          // 1: ERK stage vectors in shared memory
     int kvec_bytes = 0;     // shared-memory bytes per thread for them
+    int x2 = 0;             // 1: two trajectories per thread, packed FP32 (FFMA2)
     std::mutex mu;
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
+    cudaKernel_t kernel_adaptive = nullptr;   // specialised entry (adaptive=1, save_tstops=0) when the module has one
     size_t elem() const { return dtype == B200ENS_F64 ? 8 : 4; }
 };
 
@@ -144,16 +146,16 @@ void parse_ptxas_log(b200ens_model* m) {
     }
 }
 
-std::string build_source(const b200ens_model_desc* d, int min_blocks, int block, int ksmem) {
+std::string build_source(const b200ens_model_desc* d, int min_blocks, int block, int ksmem, int x2 = 0) {
     char head[1024];
     snprintf(head, sizeof head,
              "// generated by libb200ens (model '%s')\n"
              "#define B2_F64 %d\n#define B2_NSTATE %d\n#define B2_NPARAM %d\n#define B2_ALG %d\n"
              "#define B2_HAS_JAC %d\n#define B2_HAS_TGRAD %d\n#define B2_HAS_NOISE %d\n#define B2_HAS_EVENT %d\n"
-             "#define B2_BLOCK %d\n#define B2_MINBLOCKS %d\n#define B2_KSMEM %d\n#include \"b2_common.cuh\"\n",
+             "#define B2_BLOCK %d\n#define B2_MINBLOCKS %d\n#define B2_KSMEM %d\n#define B2_X2 %d\n#include \"b2_common.cuh\"\n",
              d->name ? d->name : "", d->dtype == B200ENS_F64 ? 1 : 0, d->n_state, d->n_param, d->alg,
              d->jac_src ? 1 : 0, d->tgrad_src ? 1 : 0, d->noise_src ? 1 : 0,
-             (d->condition_src && d->affect_src) ? 1 : 0, block, min_blocks, ksmem);
+             (d->condition_src && d->affect_src) ? 1 : 0, block, min_blocks, ksmem, x2);
     std::string s = head;
     for (const char* part : {d->rhs_src, d->jac_src, d->tgrad_src, d->noise_src, d->condition_src, d->affect_src})
         if (part) {
@@ -217,6 +219,10 @@ int ensure_loaded(b200ens_model* m) {
     if (m->kernel) return 0;
     CU(cudaLibraryLoadData(&m->lib, m->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
     CU(cudaLibraryGetKernel(&m->kernel, m->lib, "b2_ensemble_kernel"));
+    if (cudaLibraryGetKernel(&m->kernel_adaptive, m->lib, "b2_ensemble_kernel_adaptive") != cudaSuccess) {
+        m->kernel_adaptive = nullptr;
+        (void)cudaGetLastError();
+    }
     return 0;
 }
 
@@ -295,14 +301,14 @@ int plan_launch(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, long long
     bool staged = false;
     // Measured on B200 (profiles/): for the saveat shapes of configs 1-4 direct global stores are ~3%
     // faster than shared-memory staging (L2 merges the 12-byte rows), so auto means direct.
-    if (o->stage_outputs > 0 && n_save > 0 && smem + ksm <= 200 * 1024) {
+    if (o->stage_outputs > 0 && n_save > 0 && !m->x2 && smem + ksm <= 200 * 1024) {
         if (smem + ksm > 48 * 1024)
             CU(cudaFuncSetAttribute((const void*)m->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + ksm)));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_staged, (const void*)m->kernel, block, smem + ksm));
         // stage when it costs at most a quarter of the occupancy (or when forced)
         staged = nb_staged >= 1 && (o->stage_outputs > 0 || 4 * nb_staged >= 3 * nb_direct);
     }
-    if (o->stage_outputs > 0 && !staged)
+    if (o->stage_outputs > 0 && !staged && !m->x2)
         return fail(B200ENS_E_UNSUPPORTED, "stage_outputs=1 but %zu bytes of shared memory per block do not fit", smem);
     int nb = staged ? nb_staged : nb_direct;
     if (const char* e = getenv("B200ENS_BLOCKS_PER_SM")) nb = std::max(1, std::min(nb, atoi(e)));  // experiments
@@ -310,11 +316,13 @@ int plan_launch(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, long long
     lp->block = block;
     lp->stride = staged ? stride : 0;
     lp->smem = (int)((staged ? smem : 0) + ksm);
-    const long long want = (N + block - 1) / block;
+    const long long per_block = (long long)block * (m->x2 ? 2 : 1);   // packed kernels hold two trajectories per thread
+    const long long want = (N + per_block - 1) / per_block;
     lp->grid = (int)std::max<long long>(1, std::min<long long>((long long)nb * d->sms, want));
     int refill = o->refill_threshold;
     if (refill <= 0) refill = (o->adaptive && !is_sde(m->alg)) ? 4 : 32;
-    lp->refill = std::min(refill, 32);
+    refill = std::min(refill, 32);
+    lp->refill = m->x2 ? 2 * refill : refill;   // packed kernels count idle slots out of 64 per warp
     return 0;
 }
 
@@ -373,7 +381,10 @@ int check_opts(const b200ens_model* m, const b200ens_opts* o, int n_save, const 
 
 int launch(b200ens_model* m, const LaunchPlan& lp, const B2Args& a, cudaStream_t stream) {
     void* params[] = {(void*)&a};
-    CU(cudaLaunchKernel((const void*)m->kernel, dim3(lp.grid), dim3(lp.block), params, lp.smem, stream));
+    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && !a.save_tstops) ? m->kernel_adaptive : m->kernel;
+    if (k != m->kernel && lp.smem > 48 * 1024)
+        CU(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, lp.smem));
+    CU(cudaLaunchKernel((const void*)k, dim3(lp.grid), dim3(lp.block), params, lp.smem, stream));
     return 0;
 }
 
@@ -484,7 +495,8 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
         a.refill_threshold = lp.refill;
         a.stage_stride = lp.stride;
         LaunchPlan l2 = lp;
-        l2.grid = (int)std::max<long long>(1, std::min<long long>(lp.grid, (cn + lp.block - 1) / lp.block));
+        const long long pb = (long long)lp.block * (m->x2 ? 2 : 1);
+        l2.grid = (int)std::max<long long>(1, std::min<long long>(lp.grid, (cn + pb - 1) / pb));
         CU(cudaEventRecord(s.ev[1], s.stream));
         if ((rc = launch(m, l2, a, s.stream))) return rc;
         CU(cudaEventRecord(s.ev[2], s.stream));
@@ -576,6 +588,28 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     const char* force_k = getenv("B200ENS_KSMEM");
     const int nvec = d->alg == B200ENS_TSIT5 ? 7 : d->alg == B200ENS_VERN7 ? 14 : 0;
     bool try_regs = !(force_k && atoi(force_k) == 1 && nvec);
+    // Packed FP32: two trajectories per thread (FFMA2/FADD2/FMUL2, Blackwell only) for the register-light
+    // Float32 explicit case without callbacks -- the headline Lorenz/Tsit5 configuration.
+    const char* force_x2 = getenv("B200ENS_X2");
+    const bool ask_x2 = (d->flags & B200ENS_MODEL_PACKED_X2) || (force_x2 && atoi(force_x2) == 1);
+    const bool want_x2 = ask_x2 && d->dtype == B200ENS_F32 && d->alg == B200ENS_TSIT5 && !d->condition_src && d->n_state <= 6;
+    if (want_x2) {
+        int mbx = 4;
+        if (const char* e = getenv("B200ENS_MINBLOCKS")) mbx = std::max(1, atoi(e));
+        for (;; mbx--) {
+            m->source = build_source(d, mbx, kBlock, 0, 1);
+            rc = nvrtc_compile(m.get());
+            if (rc) break;
+            parse_ptxas_log(m.get());
+            if (m->spill <= 96 || mbx <= 1 || getenv("B200ENS_MINBLOCKS")) break;
+        }
+        if (!rc && m->spill <= 96) {
+            m->x2 = 1;
+            mb = mbx;
+            try_regs = false;
+        }
+        rc = 0;
+    }
     if (try_regs) {
         for (;; mb--) {
             m->source = build_source(d, mb, kBlock, 0);
@@ -588,7 +622,7 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     // Large systems: the k-vectors do not fit the register file (config 5: n=16 f64 Vern7 spilled 4 KB per
     // thread and was DRAM-bound on local-memory traffic).  Recompile with the stage vectors in shared memory,
     // CTA size chosen so that two CTAs fit in the 227 KB of an SM.
-    if (!rc && nvec && ((try_regs && m->spill > 6000 && !(force_k && atoi(force_k) == 0)) || !try_regs)) {
+    if (!rc && nvec && !m->x2 && ((try_regs && m->spill > 6000 && !(force_k && atoi(force_k) == 0)) || !try_regs)) {
         const int per_thread = nvec * d->n_state * (d->dtype == B200ENS_F64 ? 8 : 4);
         int block = std::min(128, (114688 / per_thread) / 32 * 32);
         if (block >= 32) {

@@ -10,12 +10,57 @@
 //   s = c1*x1; s = fma(c2,x2,s); ...   stage argument U = fma(dt, s, uprev).
 #pragma once
 
+#ifndef B2_X2
+#define B2_X2 0   // 1: two trajectories per thread, packed FP32 (FFMA2/FADD2/FMUL2, sm_100+), see b2_ode_driver_x2.cuh
+#endif
+
+// sreal: the scalar storage type of u, p, t in global memory.  real: the type the steppers compute in
+// (== sreal, or the packed pair b2f2 in B2_X2 mode).
 #if B2_F64
-typedef double real;
+typedef double sreal;
 #define B2_EPS 2.220446049250313e-16
 #else
-typedef float real;
+typedef float sreal;
 #define B2_EPS 1.1920928955078125e-7f
+#endif
+
+#if B2_X2
+// Two independent trajectories in the two halves of a 64-bit register pair.  Every operation is the IEEE
+// round-to-nearest FP32 operation applied per half (FFMA2/FADD2/FMUL2 are exact per-lane equivalents of
+// FFMA/FADD/FMUL), so a packed run is bit-identical to two scalar runs.
+struct __align__(8) b2f2 {
+    float2 v;
+    __device__ __forceinline__ b2f2() {}
+    __device__ __forceinline__ b2f2(float a) { v.x = a; v.y = a; }
+    __device__ __forceinline__ b2f2(double a) { v.x = (float)a; v.y = (float)a; }
+    __device__ __forceinline__ b2f2(int a) { v.x = (float)a; v.y = (float)a; }
+    __device__ __forceinline__ b2f2(float a, float b) { v.x = a; v.y = b; }
+    __device__ __forceinline__ explicit b2f2(float2 a) : v(a) {}
+};
+typedef b2f2 real;
+__device__ __forceinline__ b2f2 operator+(b2f2 a, b2f2 b) { return b2f2(__fadd2_rn(a.v, b.v)); }
+// negation / subtraction as exact packed ops (x * -1 and fma(b, -1, a) round exactly like -x and a - b);
+// a scalar sign flip per half would cost two extra issue slots each
+__device__ __forceinline__ b2f2 operator-(b2f2 a) { return b2f2(__fmul2_rn(a.v, make_float2(-1.0f, -1.0f))); }
+__device__ __forceinline__ b2f2 operator-(b2f2 a, b2f2 b) { return b2f2(__ffma2_rn(b.v, make_float2(-1.0f, -1.0f), a.v)); }
+__device__ __forceinline__ b2f2 operator*(b2f2 a, b2f2 b) { return b2f2(__fmul2_rn(a.v, b.v)); }
+__device__ __forceinline__ b2f2 operator/(b2f2 a, b2f2 b) { return b2f2(__fdiv_rn(a.v.x, b.v.x), __fdiv_rn(a.v.y, b.v.y)); }
+__device__ __forceinline__ b2f2 b2_fma(b2f2 a, b2f2 b, b2f2 c) { return b2f2(__ffma2_rn(a.v, b.v, c.v)); }
+__device__ __forceinline__ b2f2 b2_abs(b2f2 a) { return b2f2(fabsf(a.v.x), fabsf(a.v.y)); }
+__device__ __forceinline__ b2f2 b2_max(b2f2 a, b2f2 b) { return b2f2(fmaxf(a.v.x, b.v.x), fmaxf(a.v.y, b.v.y)); }
+__device__ __forceinline__ b2f2 b2_min(b2f2 a, b2f2 b) { return b2f2(fminf(a.v.x, b.v.x), fminf(a.v.y, b.v.y)); }
+__device__ __forceinline__ b2f2 b2_sqrt(b2f2 a) { return b2f2(__fsqrt_rn(a.v.x), __fsqrt_rn(a.v.y)); }
+// math functions a traced model may use (codegen.py emits these names), applied per half
+#define B2_X2_FN1(name, fn) __device__ __forceinline__ b2f2 name(b2f2 a) { return b2f2(fn(a.v.x), fn(a.v.y)); }
+B2_X2_FN1(sqrt, __fsqrt_rn) B2_X2_FN1(exp, expf) B2_X2_FN1(log, logf) B2_X2_FN1(sin, sinf) B2_X2_FN1(cos, cosf)
+B2_X2_FN1(tan, tanf) B2_X2_FN1(tanh, tanhf) B2_X2_FN1(fabs, fabsf)
+__device__ __forceinline__ b2f2 pow(b2f2 a, b2f2 b) { return b2f2(powf(a.v.x, b.v.x), powf(a.v.y, b.v.y)); }
+// half selection (h is a compile-time constant after unrolling) and per-half blend
+__device__ __forceinline__ float b2_get(const b2f2& a, int h) { return h ? a.v.y : a.v.x; }
+__device__ __forceinline__ void b2_set(b2f2& a, int h, float s) { if (h) a.v.y = s; else a.v.x = s; }
+__device__ __forceinline__ b2f2 b2_blend(bool c0, bool c1, b2f2 a, b2f2 b) { return b2f2(c0 ? a.v.x : b.v.x, c1 ? a.v.y : b.v.y); }
+#else
+typedef sreal real;
 #endif
 
 #ifndef B2_KSMEM
@@ -75,7 +120,7 @@ __device__ __forceinline__ float b2_min(float a, float b) { return fminf(a, b); 
 __device__ __forceinline__ double b2_min(double a, double b) { return fmin(a, b); }
 __device__ __forceinline__ float b2_sqrt(float a) { return __fsqrt_rn(a); }
 __device__ __forceinline__ double b2_sqrt(double a) { return __dsqrt_rn(a); }
-__device__ __forceinline__ bool b2_isnan(real a) { return a != a; }
+__device__ __forceinline__ bool b2_isnan(sreal a) { return a != a; }
 
 // ---- deterministic float log2 / exp2 for the PI controller (same primitive sequence as the
 // oracle's orc_fastlog2 / orc_fastexp2; restates upstream's approximate FastPower):
@@ -110,10 +155,10 @@ __device__ __forceinline__ float b2_fastexp2(float y) {
 // ---- per-lane output sink: shared-memory staging (flushed coalesced by the whole warp
 // when the lane retires) or direct global stores for outputs too large to stage.
 struct B2Sink {
-    real* stage;       // this lane's staging row (null in direct mode)
-    real* gout;        // out_u as real*
+    sreal* stage;       // this lane's staging row (null in direct mode)
+    sreal* gout;       // out_u as real*
     long long base;    // idx * n_save * B2_N
-    __device__ __forceinline__ void put(int si, const real (&v)[B2_N]) const {
+    __device__ __forceinline__ void put(int si, const sreal (&v)[B2_N]) const {
         if (stage) {
 #pragma unroll
             for (int i = 0; i < B2_N; i++) stage[si * B2_N + i] = v[i];
@@ -122,7 +167,7 @@ struct B2Sink {
             for (int i = 0; i < B2_N; i++) gout[base + (long long)si * B2_N + i] = v[i];
         }
     }
-    __device__ __forceinline__ void fill(int si, int n_save, real v) const {
+    __device__ __forceinline__ void fill(int si, int n_save, sreal v) const {
         for (; si < n_save; si++) {
 #pragma unroll
             for (int i = 0; i < B2_N; i++) {
@@ -135,15 +180,15 @@ struct B2Sink {
 
 // Warp-cooperative flush of the staged outputs of every lane in `dirty_mask`: all 32 lanes
 // copy one retired lane's row at a time -> coalesced 128-byte global stores.
-__device__ __forceinline__ void b2_flush(unsigned dirty_mask, const real* warp_stage, int stride, real* gout,
+__device__ __forceinline__ void b2_flush(unsigned dirty_mask, const sreal* warp_stage, int stride, sreal* gout,
                                          long long idx, int out_per_traj, unsigned lane) {
     __syncwarp();
     while (dirty_mask) {
         const int L = __ffs(dirty_mask) - 1;
         dirty_mask &= dirty_mask - 1;
         const long long iL = __shfl_sync(B2_FULL, idx, L);
-        const real* src = warp_stage + (size_t)L * stride;
-        real* dst = gout + iL * (long long)out_per_traj;
+        const sreal* src = warp_stage + (size_t)L * stride;
+        sreal* dst = gout + iL * (long long)out_per_traj;
         for (int j = lane; j < out_per_traj; j += 32) dst[j] = src[j];
     }
     __syncwarp();

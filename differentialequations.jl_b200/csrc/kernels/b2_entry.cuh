@@ -5,7 +5,11 @@
 
 #if B2_ALG == 1 || B2_ALG == 2
 #include "b2_erk.cuh"
+#if B2_X2
+#include "b2_ode_driver_x2.cuh"
+#else
 #include "b2_ode_driver.cuh"
+#endif
 #elif B2_ALG == 3 || B2_ALG == 4 || B2_ALG == 5 || B2_ALG == 8
 #include "b2_rosenbrock.cuh"
 #include "b2_ode_driver.cuh"
@@ -15,8 +19,21 @@
 #error "unknown B2_ALG"
 #endif
 
-extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble_kernel(const __grid_constant__ B2Args a) {
+#if (B2_ALG == 1 || B2_ALG == 2) && !B2_X2
+// the common explicit case (adaptive, saveat interpolated) with both options folded at compile time
+extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble_kernel_adaptive(const __grid_constant__ B2Args a) {
 #if B2_ALG == 1
+    b2_ode_driver<B2Tsit5, 1, 0>(a);
+#else
+    b2_ode_driver<B2Vern7, 1, 0>(a);
+#endif
+}
+#endif
+
+extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble_kernel(const __grid_constant__ B2Args a) {
+#if B2_ALG == 1 && B2_X2
+    b2_ode_driver_x2<B2Tsit5>(a);
+#elif B2_ALG == 1
     b2_ode_driver<B2Tsit5>(a);
 #elif B2_ALG == 2
     b2_ode_driver<B2Vern7>(a);

@@ -44,6 +44,21 @@ struct B2Tsit5 {
     __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {
         B2_RHS_TO(k1, u, t);
     }
+#if B2_X2
+    static constexpr int NF_ATTEMPT = 6;
+    // packed mode: (re)start only the halves in (m0, m1); the other half keeps its k1
+    __device__ __forceinline__ void start_masked(const real (&u)[B2_N], const real (&p)[B2_NPA], real t, bool m0, bool m1) {
+        real f[B2_N];
+        b2_rhs(f, u, p, t);
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) k1[i] = b2_blend(m0, m1, f[i], k1[i]);
+    }
+    // FSAL hand-over only for the halves whose step was accepted
+    __device__ __forceinline__ void advance_masked(bool m0, bool m1) {
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) k1[i] = b2_blend(m0, m1, k7[i], k1[i]);
+    }
+#endif
     // one step attempt from (up, t) with k1 = f(up, t); writes the proposal u and dt*error estimate
     __device__ __forceinline__ void step(const real (&up)[B2_N], const real (&p)[B2_NPA], real t, real dt,
                                          real (&u)[B2_N], real (&ut)[B2_N], bool adaptive, int& nf) {

@@ -14,7 +14,9 @@
 #pragma once
 #include "b2_common.cuh"
 
-template <class Alg>
+// ADAPT / TSTOPS: 0 or 1 = compile-time specialisation of the two solve options that sit in the per-iteration
+// control path, -1 = read them from the argument block.
+template <class Alg, int ADAPT = -1, int TSTOPS = -1>
 __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     extern __shared__ __align__(16) unsigned char b2_smem[];
     const unsigned lane = threadIdx.x & 31u;
@@ -36,8 +38,8 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     const real qoldinit = B2_ARG(a, qoldinit), dtmax = B2_ARG(a, dtmax), dtmin = B2_ARG(a, dtmin);
     const float beta1 = a.f_beta1, beta2 = a.f_beta2;
     const float lqinit = b2_fastlog2((float)qoldinit);
-    const bool adaptive = a.adaptive != 0;
-    const bool save_tstops = a.save_tstops != 0;
+    const bool adaptive = ADAPT < 0 ? (a.adaptive != 0) : (ADAPT != 0);
+    const bool save_tstops = TSTOPS < 0 ? (a.save_tstops != 0) : (TSTOPS != 0);
 
     Alg alg;
 #if B2_KSMEM

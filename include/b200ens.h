@@ -51,6 +51,9 @@ enum b200ens_error {
 
 /* model flags */
 #define B200ENS_MODEL_FAST_MATH 1u /* let NVRTC contract a*b+c in MODEL code (breaks bitwise oracle parity) */
+#define B200ENS_MODEL_PACKED_X2 2u /* Float32 Tsit5 without callbacks: two trajectories per thread in packed FP32
+                                      (FFMA2/FADD2/FMUL2, sm_100+); bit-identical results; measured 5% SLOWER than the
+                                      scalar kernel on B200 (profiles/README.md), hence opt-in */
 
 /* What a problem looks like to the library: ODEProblem / SDEProblem (qa.jl:86,103) with f,
  * jac, tgrad, g and one ContinuousCallback (qa.jl:26; test/core.jl:69-72) given as CUDA-C

@@ -56,6 +56,23 @@ def test_adaptive_saveat_matches_oracle(B, gpu_lib, oracle, dtype, kind):
     assert np.all(err <= tol), float((err / tol).max())
 
 
+def test_packed_ffma2_kernel_bit_identical(B, gpu_lib, oracle):
+    """Two trajectories per thread in packed FP32 (FFMA2/FADD2/FMUL2): every packed op is the per-half IEEE op,
+    so the result must equal the scalar kernel's and the oracle's bit for bit."""
+    from b200ens import workloads as W
+
+    N = 20011
+    u0, p = W.lorenz_params(N, "random", seed=9, dtype=np.float32)
+    packed = _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1, packed_x2=True)
+    ref, rc, st = oracle.solve("lorenz", "Tsit5", u0, p, (0.0, 10.0), SAVEAT, 0.1, dtype=np.float32)
+    assert np.array_equal(packed.retcodes, rc)
+    assert np.array_equal(packed.stats[:, :3], st[:, :3])
+    assert np.array_equal(packed.u_array, ref)
+    fixed = _solve_gpu(B, np.float32, u0[:999], p[:999], [10.0], 0.01, adaptive=False, packed_x2=True)
+    ref2, _, _ = oracle.solve("lorenz", "Tsit5", u0[:999], p[:999], (0.0, 10.0), [10.0], 0.01, dtype=np.float32, adaptive=False)
+    assert np.array_equal(fixed.u_array, ref2)
+
+
 @pytest.mark.parametrize("refill,stage", [(1, 1), (8, 0), (32, 1), (32, 0)])
 def test_schedule_variants_identical(B, gpu_lib, refill, stage):
     """Lane refill / output staging are scheduling choices: results must be bit-identical."""

@@ -33,8 +33,9 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     const real t0 = B2_ARG(a, t0), t1 = B2_ARG(a, t1), dt_user = B2_ARG(a, dt);
     const real abstol = B2_ARG(a, abstol), reltol = B2_ARG(a, reltol);
     const real qmax = B2_ARG(a, qmax), qmin = B2_ARG(a, qmin), gam = B2_ARG(a, gamma);
-    const real inv_qmax = (real)1 / qmax, inv_qmin = (real)1 / qmin, inv_gam = (real)1 / gam;
-    const real inv_n = (real)1 / (real)B2_N;
+    const float inv_qmax = __fdiv_rn(1.0f, (float)qmax), inv_qmin = __fdiv_rn(1.0f, (float)qmin);
+    const float inv_gam = __fdiv_rn(1.0f, (float)gam);
+    const float inv_n = __fdiv_rn(1.0f, (float)B2_N);
     const real qoldinit = B2_ARG(a, qoldinit), dtmax = B2_ARG(a, dtmax), dtmin = B2_ARG(a, dtmin);
     const float beta1 = a.f_beta1, beta2 = a.f_beta2;
     const float lqinit = b2_fastlog2((float)qoldinit);
@@ -146,38 +147,38 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                     dts = dt;
                     dtnew = dt;
                     if (adaptive) {
-                        // error norm (A.4) and PI controller (A.5)
-                        real acc = 0;
+                        // error norm (A.4): scale in the working precision, ratio / square / sum in Float32 (EEst only
+                        // steers the step size; keeps Float64 kernels free of IEEE double divisions).  Accept iff
+                        // EEst^2 <= 1.  PI controller (A.5) in the log domain: l = log2(EEst), lq = log2(qold),
+                        // q = 2^(beta1*l - beta2*lq) / gamma -> one log2 + one exp2 per step.
+                        float acc = 0.0f;
 #pragma unroll
                         for (int i = 0; i < B2_N; i++) {
                             const real sk = b2_fma(b2_max(b2_abs(u[i]), b2_abs(un[i])), reltol, abstol);
-                            const real r = ut[i] / sk;
-                            acc = b2_fma(r, r, acc);
+                            const float r = __fdiv_rn((float)ut[i], (float)sk);
+                            acc = __fmaf_rn(r, r, acc);
                         }
-                        // accept iff EEst <= 1 <=> EEst^2 <= 1; q = EEst^beta1 / qold^beta2 / gamma in the
-                        // log domain: l = log2(EEst), lq = log2(qold) -> one log2 + one exp2 per step
-                        const real EE2 = acc * inv_n;
-                        if (b2_isnan(EE2)) {
+                        const float EE2 = __fmul_rn(acc, inv_n);
+                        if (EE2 != EE2) {
                             rc = B2_RC_DTNAN;  // upstream: NaN EEst -> NaN dt -> ReturnCode.DtNaN
                             accepted = false;
                         } else {
-                            real q;
-                            float l = lqinit;
-                            if (EE2 == (real)0) {
+                            float q, l = lqinit;
+                            if (EE2 == 0.0f) {
                                 q = inv_qmax;
                             } else {
-                                l = __fmul_rn(0.5f, b2_fastlog2((float)EE2));
-                                q = (real)b2_fastexp2(__fmaf_rn(-beta2, lq, __fmul_rn(beta1, l)));
-                                q = b2_max(inv_qmax, b2_min(inv_qmin, q * inv_gam));
+                                l = __fmul_rn(0.5f, b2_fastlog2(EE2));
+                                q = b2_fastexp2(__fmaf_rn(-beta2, lq, __fmul_rn(beta1, l)));
+                                q = fmaxf(inv_qmax, fminf(inv_qmin, __fmul_rn(q, inv_gam)));
                             }
-                            if (!(EE2 <= (real)1)) {
+                            if (!(EE2 <= 1.0f)) {
                                 accepted = false;
                                 nreject++;
-                                const real q11 = (real)b2_fastexp2(__fmul_rn(beta1, l));
-                                dt = dt / b2_min(inv_qmin, q11 * inv_gam);
+                                const float q11 = b2_fastexp2(__fmul_rn(beta1, l));
+                                dt = dt * (real)__fdiv_rn(1.0f, fminf(inv_qmin, __fmul_rn(q11, inv_gam)));
                             } else {
                                 lq = fmaxf(l, lqinit);
-                                dtnew = dt / q;
+                                dtnew = dt * (real)__fdiv_rn(1.0f, q);
                             }
                         }
                     } else {

@@ -199,11 +199,11 @@ __device__ __forceinline__ void b2_ode_driver_x2(const B2Args& a) {
                             if (!(ee <= 1.0f)) {
                                 nreject[h]++;
                                 const float q11 = b2_fastexp2(__fmul_rn(beta1, l));
-                                dt[h] = __fdiv_rn(dt[h], fminf(inv_qmin, __fmul_rn(q11, inv_gam)));
+                                dt[h] = __fmul_rn(dt[h], __fdiv_rn(1.0f, fminf(inv_qmin, __fmul_rn(q11, inv_gam))));
                             } else {
                                 accepted[h] = true;
                                 lq[h] = fmaxf(l, lqinit);
-                                dtnew[h] = __fdiv_rn(dt[h], q);
+                                dtnew[h] = __fmul_rn(dt[h], __fdiv_rn(1.0f, q));
                             }
                         }
                     }

@@ -28,6 +28,7 @@ class ModelDesc(C.Structure):
         ("alg", C.c_int32), ("flags", C.c_uint32),
         ("rhs_src", C.c_char_p), ("jac_src", C.c_char_p), ("tgrad_src", C.c_char_p), ("noise_src", C.c_char_p),
         ("condition_src", C.c_char_p), ("affect_src", C.c_char_p), ("name", C.c_char_p),
+        ("dcondition_src", C.c_char_p), ("daffect_src", C.c_char_p),
     ]
 
 
@@ -124,7 +125,8 @@ class Model:
     """A compiled (problem functions x algorithm x dtype) kernel: b200ens_model*."""
 
     def __init__(self, n_state, n_param, dtype, alg, rhs_src, jac_src=None, tgrad_src=None, noise_src=None,
-                 condition_src=None, affect_src=None, name="model", fast_math=False, packed_x2=False):
+                 condition_src=None, affect_src=None, name="model", fast_math=False, packed_x2=False,
+                 dcondition_src=None, daffect_src=None):
         L = lib()
         d = ModelDesc()
         d.struct_size = C.sizeof(ModelDesc)
@@ -136,13 +138,14 @@ class Model:
         d.rhs_src, d.jac_src, d.tgrad_src = enc(rhs_src), enc(jac_src), enc(tgrad_src)
         d.noise_src, d.condition_src, d.affect_src = enc(noise_src), enc(condition_src), enc(affect_src)
         d.name = enc(name)
+        d.dcondition_src, d.daffect_src = enc(dcondition_src), enc(daffect_src)
         self.handle = C.c_void_p()
         logbuf = C.create_string_buffer(1 << 16)
         code = L.b200ens_compile(C.byref(d), C.byref(self.handle), logbuf, len(logbuf))
         self.log = logbuf.value.decode(errors="replace")
         check(code)
         self.n_state, self.n_param, self.dtype, self.alg = n_state, n_param, np.dtype(dtype), alg
-        self.has_event = condition_src is not None
+        self.has_event = condition_src is not None or dcondition_src is not None
 
     def info(self):
         cb, regs, smem, lmem = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()

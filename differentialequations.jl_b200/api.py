@@ -135,6 +135,39 @@ class ContinuousCallback:
             raise NotImplementedError("EnsembleB200 needs save_positions=(false,false) (saveat output is fixed-size)")
 
 
+class DiscreteCallback:
+    """DiscreteCallback(condition, affect!) with condition(u,t,integrator)::Bool tested after every accepted step
+    (test/core.jl:76-77).  Both functions must be symbolically traceable."""
+
+    def __init__(self, condition, affect, save_positions=(False, False)):
+        self.condition = condition
+        self.affect = affect
+        if tuple(save_positions) != (False, False):
+            raise NotImplementedError("EnsembleB200 needs save_positions=(false,false) (saveat output is fixed-size)")
+
+
+class CallbackSet:
+    """CallbackSet(cb...) (qa.jl:24): at most one ContinuousCallback and one DiscreteCallback on this back-end."""
+
+    def __init__(self, *cbs):
+        self.continuous = [c for c in cbs if isinstance(c, ContinuousCallback)]
+        self.discrete = [c for c in cbs if isinstance(c, DiscreteCallback)]
+        if len(self.continuous) > 1 or len(self.discrete) > 1 or len(self.continuous) + len(self.discrete) != len(cbs):
+            raise NotImplementedError("EnsembleB200 supports one ContinuousCallback plus one DiscreteCallback")
+
+
+def _split_callbacks(callback):
+    if callback is None:
+        return None, None
+    if isinstance(callback, ContinuousCallback):
+        return callback, None
+    if isinstance(callback, DiscreteCallback):
+        return None, callback
+    if isinstance(callback, CallbackSet):
+        return (callback.continuous[0] if callback.continuous else None), (callback.discrete[0] if callback.discrete else None)
+    raise TypeError("callback must be a ContinuousCallback, DiscreteCallback or CallbackSet")
+
+
 class EnsembleProblem:
     """EnsembleProblem(prob; prob_func, output_func, reduction) (qa.jl:50).
 
@@ -244,9 +277,14 @@ def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False):
         if alg.name == "SOSRA" and any(e.has(*usyms) for e in gex):
             raise ValueError("SOSRA is for additive noise only: g(u,p,t) must not depend on u (SURVEY A.9)")
         srcs["noise_src"] = codegen.emit_noise(gex)
-    terminate = False
-    if callback is not None:
-        srcs["condition_src"], srcs["affect_src"], terminate = codegen.emit_callback(callback, n, m)
+    terminate = 0
+    ccb, dcb = _split_callbacks(callback)
+    if ccb is not None:
+        srcs["condition_src"], srcs["affect_src"], term = codegen.emit_callback(ccb, n, m)
+        terminate |= 1 if term else 0
+    if dcb is not None:
+        srcs["dcondition_src"], srcs["daffect_src"], term = codegen.emit_discrete_callback(dcb, n, m)
+        terminate |= 2 if term else 0
     model = _lib.Model(n, m, dtype, alg.name, name=getattr(prob.f, "__name__", "model"), fast_math=fast_math,
                        packed_x2=packed_x2, **srcs)
     model.sources = srcs
@@ -346,7 +384,9 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, 
     o.noise_injected = 0 if dW is None else 1
     if callback is not None:
         o.event_terminate = int(model.event_terminate)
-        o.interp_points = int(callback.interp_points)
+        ccb, _ = _split_callbacks(callback)
+        if ccb is not None:
+            o.interp_points = int(ccb.interp_points)
     if save_tstops is not None:
         o.save_tstops = int(save_tstops)
     if ensemblealg.devices is not None:

@@ -188,6 +188,33 @@ def emit_callback(cb, n_state, n_param):
     return cond_src, aff_src, bool(integ2.terminated)
 
 
+def emit_discrete_callback(cb, n_state, n_param):
+    """DiscreteCallback(condition, affect!) -> (dcondition_src, daffect_src, terminate).  condition(u,t,integrator)
+    must trace to a sympy relational / boolean (e.g. `t >= 0.5`, `(u[0] > 1) & (t < 3)`)."""
+    integ = _TraceIntegrator(n_state, n_param)
+    try:
+        g = cb.condition(integ.u, integ.t, integ)
+        g = sp.sympify(g)
+        if not (g.is_Relational or g.is_Boolean or g in (sp.true, sp.false)):
+            raise TypeError("condition must be a boolean expression")
+    except Exception as e:
+        raise NotImplementedError(
+            "DiscreteCallback condition is not symbolically traceable to a boolean expression; EnsembleB200 only "
+            "accepts callbacks that can be emitted as CUDA C") from e
+    cond_src = ("__device__ __forceinline__ bool b2_dcondition(const real* __restrict__ u, const real* __restrict__ p, "
+                "const real t) {\n    (void)u; (void)p; (void)t;\n    return " + _c(g) + ";\n}\n")
+    integ2 = _TraceIntegrator(n_state, n_param)
+    try:
+        cb.affect(integ2)
+    except Exception as e:
+        raise NotImplementedError("DiscreteCallback affect! is not symbolically traceable") from e
+    changed = [(i, v) for i, (s, v) in enumerate(zip(integ2.u.syms, integ2.u.vals)) if v != s]
+    lines = [f"    const real n{i} = {_c(v)};" for i, v in changed] + [f"    u[{i}] = n{i};" for i, _ in changed]
+    aff_src = ("__device__ __forceinline__ void b2_daffect(real* __restrict__ u, const real* __restrict__ p, "
+               "const real t) {\n    (void)u; (void)p; (void)t;\n" + "\n".join(lines) + "\n}\n")
+    return cond_src, aff_src, bool(integ2.terminated)
+
+
 HOST_PRELUDE = """// host build of emitted model code (tests: compiled with g++ for the CPU oracle)
 #include <cmath>
 using std::sqrt; using std::pow; using std::sin; using std::cos; using std::exp; using std::log; using std::fabs;
@@ -196,7 +223,8 @@ using std::sqrt; using std::pow; using std::sin; using std::cos; using std::exp;
 """
 
 
-def host_wrapper_source(sources, names=("b2_rhs", "b2_jac", "b2_tgrad", "b2_noise", "b2_condition", "b2_affect")):
+def host_wrapper_source(sources, names=("b2_rhs", "b2_jac", "b2_tgrad", "b2_noise", "b2_condition", "b2_affect",
+                                        "b2_dcondition", "b2_daffect")):
     """C++ translation unit exposing the emitted functions for float and double with C linkage
     (oracle side of the parity tests)."""
     parts = [HOST_PRELUDE]
@@ -210,7 +238,9 @@ def host_wrapper_source(sources, names=("b2_rhs", "b2_jac", "b2_tgrad", "b2_nois
                 continue
             if nm == "b2_condition":
                 parts.append(f"{ty} {nm}_{suf}(const {ty}* u, const {ty}* p, {ty} t) {{ return ns_{suf}::{nm}(u, p, t); }}\n")
-            elif nm == "b2_affect":
+            elif nm == "b2_dcondition":
+                parts.append(f"int {nm}_{suf}(const {ty}* u, const {ty}* p, {ty} t) {{ return ns_{suf}::{nm}(u, p, t) ? 1 : 0; }}\n")
+            elif nm in ("b2_affect", "b2_daffect"):
                 parts.append(f"void {nm}_{suf}({ty}* u, const {ty}* p, {ty} t) {{ ns_{suf}::{nm}(u, p, t); }}\n")
             else:
                 parts.append(f"void {nm}_{suf}({ty}* o, const {ty}* u, const {ty}* p, {ty} t) {{ ns_{suf}::{nm}(o, u, p, t); }}\n")

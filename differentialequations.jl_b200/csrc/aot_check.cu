@@ -15,6 +15,7 @@
 #define B2_HAS_TGRAD 0
 #define B2_HAS_NOISE 1
 #define B2_HAS_EVENT 0
+#define B2_HAS_DEVENT 0
 #define B2_BLOCK 128
 #ifdef AOT_X2
 #define B2_X2 1

@@ -151,13 +151,15 @@ std::string build_source(const b200ens_model_desc* d, int min_blocks, int block,
     snprintf(head, sizeof head,
              "// generated by libb200ens (model '%s')\n"
              "#define B2_F64 %d\n#define B2_NSTATE %d\n#define B2_NPARAM %d\n#define B2_ALG %d\n"
-             "#define B2_HAS_JAC %d\n#define B2_HAS_TGRAD %d\n#define B2_HAS_NOISE %d\n#define B2_HAS_EVENT %d\n"
+             "#define B2_HAS_JAC %d\n#define B2_HAS_TGRAD %d\n#define B2_HAS_NOISE %d\n#define B2_HAS_EVENT %d\n#define B2_HAS_DEVENT %d\n"
              "#define B2_BLOCK %d\n#define B2_MINBLOCKS %d\n#define B2_KSMEM %d\n#define B2_X2 %d\n#include \"b2_common.cuh\"\n",
              d->name ? d->name : "", d->dtype == B200ENS_F64 ? 1 : 0, d->n_state, d->n_param, d->alg,
              d->jac_src ? 1 : 0, d->tgrad_src ? 1 : 0, d->noise_src ? 1 : 0,
-             (d->condition_src && d->affect_src) ? 1 : 0, block, min_blocks, ksmem, x2);
+             (d->condition_src && d->affect_src) ? 1 : 0, (d->dcondition_src && d->daffect_src) ? 1 : 0, block, min_blocks,
+             ksmem, x2);
     std::string s = head;
-    for (const char* part : {d->rhs_src, d->jac_src, d->tgrad_src, d->noise_src, d->condition_src, d->affect_src})
+    for (const char* part : {d->rhs_src, d->jac_src, d->tgrad_src, d->noise_src, d->condition_src, d->affect_src,
+                             d->dcondition_src, d->daffect_src})
         if (part) {
             s += part;
             s += "\n";
@@ -569,7 +571,10 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     if (is_sde(d->alg) && !d->noise_src) return fail(B200ENS_E_INVALID, "SDE algorithms need noise_src");
     if ((d->condition_src != nullptr) != (d->affect_src != nullptr))
         return fail(B200ENS_E_INVALID, "condition_src and affect_src must be given together");
-    if (is_sde(d->alg) && d->condition_src) return fail(B200ENS_E_UNSUPPORTED, "callbacks on SDE algorithms are not supported");
+    if ((d->dcondition_src != nullptr) != (d->daffect_src != nullptr))
+        return fail(B200ENS_E_INVALID, "dcondition_src and daffect_src must be given together");
+    if (is_sde(d->alg) && (d->condition_src || d->dcondition_src))
+        return fail(B200ENS_E_UNSUPPORTED, "callbacks on SDE algorithms are not supported");
     auto m = std::make_unique<b200ens_model>();
     m->n_state = d->n_state;
     m->n_param = d->n_param;
@@ -592,7 +597,8 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     // Float32 explicit case without callbacks -- the headline Lorenz/Tsit5 configuration.
     const char* force_x2 = getenv("B200ENS_X2");
     const bool ask_x2 = (d->flags & B200ENS_MODEL_PACKED_X2) || (force_x2 && atoi(force_x2) == 1);
-    const bool want_x2 = ask_x2 && d->dtype == B200ENS_F32 && d->alg == B200ENS_TSIT5 && !d->condition_src && d->n_state <= 6;
+    const bool want_x2 = ask_x2 && d->dtype == B200ENS_F32 && d->alg == B200ENS_TSIT5 && !d->condition_src &&
+                         !d->dcondition_src && d->n_state <= 6;
     if (want_x2) {
         int mbx = 4;
         if (const char* e = getenv("B200ENS_MINBLOCKS")) mbx = std::max(1, atoi(e));

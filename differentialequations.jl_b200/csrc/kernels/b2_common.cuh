@@ -63,6 +63,9 @@ __device__ __forceinline__ b2f2 b2_blend(bool c0, bool c1, b2f2 a, b2f2 b) { ret
 typedef sreal real;
 #endif
 
+#ifndef B2_HAS_DEVENT
+#define B2_HAS_DEVENT 0
+#endif
 #ifndef B2_KSMEM
 #define B2_KSMEM 0   // 1: ERK stage vectors live in shared memory (large n_state), see b2_erk.cuh
 #endif

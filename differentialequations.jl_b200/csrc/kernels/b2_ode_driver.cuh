@@ -309,7 +309,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                 alg.start(u, p, t);
                 nf++;
                 just_fired = true;
-                if (a.event_terminate) rc = B2_RC_TERMINATED;
+                if (a.event_terminate & 1) rc = B2_RC_TERMINATED;
             } else
 #endif
             {
@@ -320,6 +320,17 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                 just_fired = false;
 #endif
             }
+#if B2_HAS_DEVENT
+            // DiscreteCallback (test/core.jl:76-77): condition(u,t,integrator)::Bool tested on every accepted
+            // state; affect! modifies u, so the FSAL derivative is re-evaluated
+            if (rc == 0 && b2_dcondition(u, p, t)) {
+                b2_daffect(u, p, t);
+                nevents++;
+                alg.start(u, p, t);
+                nf++;
+                if (a.event_terminate & 2) rc = B2_RC_TERMINATED;
+            }
+#endif
             if (adaptive) dt = b2_min(dtmax, dtnew);
             if (rc == 0 && !(t < t1)) rc = B2_RC_SUCCESS;
         }

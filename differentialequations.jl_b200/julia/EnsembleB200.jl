@@ -23,6 +23,7 @@ struct ModelDesc
     struct_size::UInt32; n_state::Int32; n_param::Int32; dtype::Int32; alg::Int32; flags::UInt32
     rhs_src::Cstring; jac_src::Cstring; tgrad_src::Cstring; noise_src::Cstring
     condition_src::Cstring; affect_src::Cstring; name::Cstring
+    dcondition_src::Cstring; daffect_src::Cstring
 end
 mutable struct Opts
     struct_size::UInt32; adaptive::Int32
@@ -81,7 +82,7 @@ function __solve(eprob::AbstractEnsembleProblem, alg, ens::EnsembleB200; traject
     GC.@preserve rhs jac noise begin
         d = ModelDesc(sizeof(ModelDesc), n, m, T == Float64 ? 1 : 0, ALG_IDS[nameof(typeof(alg))], 0,
                       pointer(rhs), jac === nothing ? C_NULL : pointer(jac), C_NULL,
-                      noise === nothing ? C_NULL : pointer(noise), C_NULL, C_NULL, C_NULL)
+                      noise === nothing ? C_NULL : pointer(noise), C_NULL, C_NULL, C_NULL, C_NULL, C_NULL)
         check(ccall((:b200ens_compile, LIB), Cint, (Ref{ModelDesc}, Ref{Ptr{Cvoid}}, Ptr{UInt8}, Csize_t), d, model, log, length(log)))
     end
     o = Opts(); ccall((:b200ens_opts_init, LIB), Cvoid, (Ref{Opts},), o)

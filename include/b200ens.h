@@ -62,9 +62,12 @@ enum b200ens_error {
  *   __device__ void b2_jac      (real* J,  const real* u, const real* p, real t);   row-major n x n
  *   __device__ void b2_tgrad    (real* dT, const real* u, const real* p, real t);   optional
  *   __device__ void b2_noise    (real* g,  const real* u, const real* p, real t);   diagonal noise
- *   __device__ real b2_condition(const real* u, const real* p, real t);
+ *   __device__ real b2_condition(const real* u, const real* p, real t);             ContinuousCallback
  *   __device__ void b2_affect   (real* u,  const real* p, real t);
- * NULL = absent. */
+ *   __device__ bool b2_dcondition(const real* u, const real* p, real t);            DiscreteCallback (qa.jl:36,
+ *   __device__ void b2_daffect  (real* u,  const real* p, real t);                   test/core.jl:76-77)
+ * NULL = absent.  One ContinuousCallback and one DiscreteCallback may be combined (CallbackSet, qa.jl:24):
+ * the continuous event is handled first, the discrete condition is then tested on the accepted state. */
 typedef struct b200ens_model_desc {
     uint32_t struct_size;   /* sizeof(b200ens_model_desc) */
     int32_t n_state;        /* length(u0), 1..32 */
@@ -79,6 +82,8 @@ typedef struct b200ens_model_desc {
     const char* condition_src;
     const char* affect_src;
     const char* name;       /* label for logs / cache, may be NULL */
+    const char* dcondition_src;
+    const char* daffect_src;
 } b200ens_model_desc;
 
 /* solve keyword arguments (test/core.jl:14,54,72,93: reltol, abstol, dense/saveat, callback).
@@ -95,7 +100,7 @@ typedef struct b200ens_opts {
     uint64_t seed;          /* Philox key */
     uint64_t traj_offset;   /* global index of trajectory 0 of this call (Philox counter base) */
     int32_t noise_injected; /* 1: dW holds the Brownian increments; 0: Philox4x32-10 on device */
-    int32_t event_terminate;/* 1: the ContinuousCallback terminates the trajectory (terminate!) */
+    int32_t event_terminate;/* bit 0: the ContinuousCallback terminates the trajectory (terminate!); bit 1: the DiscreteCallback does */
     int32_t interp_points;  /* ContinuousCallback interp_points, <=0: 10 */
     int32_t save_tstops;    /* -1 auto (on for Rodas*), 0 interpolate, 1 saveat points are tstops */
     uint32_t device_mask;   /* bit g set: use CUDA device g; 0: all visible devices */

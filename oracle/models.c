@@ -65,7 +65,10 @@
     static T net16_cond_##S(const T* u, const T* p, T t) { (void)t; return u[0] - p[4]; }                 \
     static void net16_affect_##S(T* u, const T* p, T t) { (void)t; u[0] += p[5]; }                        \
     static T tcross_cond_##S(const T* u, const T* p, T t) { (void)u; return t - p[1]; }                   \
-    static void noop_affect_##S(T* u, const T* p, T t) { (void)u; (void)p; (void)t; }
+    static void noop_affect_##S(T* u, const T* p, T t) { (void)u; (void)p; (void)t; }                      \
+    /* test/core.jl:76: DiscreteCallback((u,t,integrator) -> t >= 0.5, affect!) ; here affect! halves u */ \
+    static int tge_dcond_##S(const T* u, const T* p, T t) { (void)u; return t >= p[1]; }                  \
+    static void halve_affect_##S(T* u, const T* p, T t) { (void)p; (void)t; u[0] = u[0] * (T)0.5; }
 
 const double net16_w[15] = {1.3, 0.42, 6.1, 0.17, 2.9, 0.88, 4.4, 0.23, 7.7, 1.9, 0.35, 3.3, 0.61, 5.2, 1.1};
 const double net16_v[15] = {0.7, 2.4, 0.19, 3.8, 0.52, 1.6, 0.11, 8.3, 0.93, 0.27, 4.9, 0.44, 2.2, 0.15, 6.6};
@@ -88,6 +91,8 @@ void* orc_model_fn(const char* model, const char* which, int is_f64) {
         if (!strcmp(which, "jac")) return PICK(linear_jac);
         if (!strcmp(which, "cond")) return PICK(tcross_cond);
         if (!strcmp(which, "affect")) return PICK(noop_affect);
+        if (!strcmp(which, "dcond")) return PICK(tge_dcond);
+        if (!strcmp(which, "daffect")) return PICK(halve_affect);
     } else if (!strcmp(model, "gbm")) {
         if (!strcmp(which, "rhs")) return PICK(gbm_rhs);
         if (!strcmp(which, "noise")) return PICK(gbm_noise);

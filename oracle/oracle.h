@@ -53,6 +53,8 @@ typedef struct {
     int32_t has_event, event_terminate, interp_points;
     int32_t save_tstops;      /* 1: saveat points are tstops (steps clipped, no interpolation) */
     void *rhs, *jac, *tgrad, *noise, *cond, *affect;
+    void *dcond, *daffect;    /* DiscreteCallback: int dcond(u,p,t), daffect(u,p,t); NULL = none */
+    int32_t devent_terminate, pad_;
 } orc_opts;
 
 /* u0 [N][n], p [N][m], saveat [n_save], out_u [N][n_save][n], retcode [N], stats [N] or NULL.

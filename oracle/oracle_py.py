@@ -30,7 +30,8 @@ class Opts(C.Structure):
         ("has_event", C.c_int32), ("event_terminate", C.c_int32), ("interp_points", C.c_int32),
         ("save_tstops", C.c_int32),
         ("rhs", C.c_void_p), ("jac", C.c_void_p), ("tgrad", C.c_void_p), ("noise", C.c_void_p),
-        ("cond", C.c_void_p), ("affect", C.c_void_p),
+        ("cond", C.c_void_p), ("affect", C.c_void_p), ("dcond", C.c_void_p), ("daffect", C.c_void_p),
+        ("devent_terminate", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -85,7 +86,8 @@ def fns_from_host_model(dll, f64):
     suf = "f64" if f64 else "f32"
     out = {}
     for key, nm in (("rhs", "b2_rhs"), ("jac", "b2_jac"), ("tgrad", "b2_tgrad"), ("noise", "b2_noise"),
-                    ("cond", "b2_condition"), ("affect", "b2_affect")):
+                    ("cond", "b2_condition"), ("affect", "b2_affect"), ("dcond", "b2_dcondition"),
+                    ("daffect", "b2_daffect")):
         try:
             out[key] = C.cast(getattr(dll, f"{nm}_{suf}"), C.c_void_p).value
         except AttributeError:
@@ -95,7 +97,7 @@ def fns_from_host_model(dll, f64):
 
 def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adaptive=True, dtype=np.float64,
           maxiters=100000, dW=None, seed=0, event=False, terminate=False, interp_points=10, nthreads=0,
-          fns=None, want_stats=True, save_tstops=None, traj_offset=0, **ctl):
+          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, **ctl):
     """Run the oracle.  model: built-in name, or fns = dict(rhs=ptr, jac=ptr, ...)."""
     L = lib()
     f64 = np.dtype(dtype) == np.float64
@@ -123,6 +125,8 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
     o.rhs, o.jac, o.noise = get("rhs"), get("jac"), get("noise")
     o.tgrad = get("tgrad") if fns else None
     o.cond, o.affect = (get("cond"), get("affect")) if event else (None, None)
+    o.dcond, o.daffect = (get("dcond"), get("daffect")) if devent else (None, None)
+    o.devent_terminate = int(dterminate)
     out = np.empty((N, len(saveat), n), dtype=dtype)
     rc = np.zeros(N, dtype=np.int32)
     stats = np.zeros((N, 4), dtype=np.int32) if want_stats else None

@@ -11,7 +11,8 @@ def oracle_fns(oracle, B, model, f64=True):
     """Function pointers for the oracle built from the SAME emitted model source the GPU kernel was JIT-compiled
     from (g++ -ffp-contract=off), so both sides evaluate one expression tree."""
     src = B.codegen.host_wrapper_source([model.sources.get(k) for k in
-                                         ("rhs_src", "jac_src", "tgrad_src", "noise_src", "condition_src", "affect_src")])
+                                         ("rhs_src", "jac_src", "tgrad_src", "noise_src", "condition_src", "affect_src",
+                                          "dcondition_src", "daffect_src")])
     dll = oracle.compile_host_model(src, "m", _WORK)
     fns = oracle.fns_from_host_model(dll, f64)
     fns["_dll"] = dll

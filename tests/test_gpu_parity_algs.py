@@ -179,3 +179,32 @@ def test_reference_callback_semantics(B, gpu_lib, oracle):
     sol2 = B.solve(prob, B.Tsit5(), callback=cbt, dt=0.05, saveat=0.1, abstol=1e-10, reltol=1e-10)
     assert sol2.retcode == B.ReturnCode.Terminated
     assert abs(sol2.u[-1] - 0.8) < 1e-8       # state at the event, held for the remaining save slots
+
+
+def test_discrete_callback_and_callbackset(B, gpu_lib, oracle):
+    """test/core.jl:76-77: DiscreteCallback((u,t,integrator) -> t >= 0.5, affect!).  Here affect! halves u; the
+    oracle's hand-written model does the same.  Also a CallbackSet with a ContinuousCallback."""
+    from b200ens import workloads as W
+
+    N = 500
+    rng = np.random.default_rng(5)
+    u0 = 0.5 + rng.random((N, 1))
+    p = np.stack([1.01 * (0.5 + rng.random(N)), np.full(N, 0.5)], axis=1)
+    prob = B.ODEProblem(W.linear, u0[0], (0.0, 1.0), p[0])
+    dcb = B.DiscreteCallback(lambda u, t, integrator: t >= integrator.p[1],
+                             lambda integrator: integrator.u.__setitem__(0, integrator.u[0] * 0.5))
+    saveat = np.linspace(0, 1, 11)
+    sol = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), B.Tsit5(), B.EnsembleB200(), trajectories=N, saveat=saveat, dt=0.05,
+                  callback=dcb, abstol=1e-9, reltol=1e-9)
+    ref, rc, st = oracle.solve("linear", "Tsit5", u0, p, (0.0, 1.0), saveat, 0.05, devent=True, abstol=1e-9, reltol=1e-9)
+    assert np.all(sol.retcodes == 1) and np.array_equal(sol.retcodes, rc)
+    assert np.array_equal(sol.stats, st) and sol.stats[:, 3].min() >= 1
+    assert np.abs(sol.u_array - ref).max() <= 1e-14
+    # CallbackSet: the continuous crossing of t = 0.5 (no-op affect) plus the discrete halving
+    ccb = B.ContinuousCallback(lambda u, t, integrator: t - integrator.p[1], lambda integrator: None)
+    sol2 = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), B.Tsit5(), B.EnsembleB200(), trajectories=N, saveat=saveat, dt=0.05,
+                   callback=B.CallbackSet(ccb, dcb), abstol=1e-9, reltol=1e-9)
+    ref2, rc2, st2 = oracle.solve("linear", "Tsit5", u0, p, (0.0, 1.0), saveat, 0.05, event=True, devent=True,
+                                  abstol=1e-9, reltol=1e-9)
+    assert np.array_equal(sol2.retcodes, rc2) and np.array_equal(sol2.stats, st2)
+    assert np.abs(sol2.u_array - ref2).max() <= 1e-14

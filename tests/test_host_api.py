@@ -75,6 +75,14 @@ def test_callback_tracing_and_rejection(B):
         codegen.emit_callback(B.ContinuousCallback(opaque, lambda integ: None), 1, 1)
     with pytest.raises(NotImplementedError):
         B.ContinuousCallback(lambda u, t, i: t, lambda i: None, save_positions=(True, True))
+    # DiscreteCallback (test/core.jl:76-77) and CallbackSet
+    dcb = B.DiscreteCallback(lambda u, t, integ: t >= 0.5, lambda integ: integ.u.__setitem__(0, integ.u[0] * 2))
+    dc, da, dterm = codegen.emit_discrete_callback(dcb, 1, 1)
+    assert "bool b2_dcondition" in dc and ">=" in dc and "u[0] = n0;" in da and dterm is False
+    with pytest.raises(NotImplementedError):
+        codegen.emit_discrete_callback(B.DiscreteCallback(lambda u, t, integ: t - 0.5, lambda integ: None), 1, 1)
+    with pytest.raises(NotImplementedError):
+        B.CallbackSet(cb, cbt)
 
 
 def test_solve_argument_errors(B):

@@ -63,8 +63,8 @@ class Timing(C.Structure):
 
 EXPORTS = [
     "b200ens_abi_version", "b200ens_device_count", "b200ens_last_error", "b200ens_opts_init", "b200ens_compile",
-    "b200ens_free", "b200ens_model_info", "b200ens_solve", "b200ens_solve_device", "b200ens_host_alloc",
-    "b200ens_host_free",
+    "b200ens_free", "b200ens_model_info", "b200ens_solve", "b200ens_solve_device", "b200ens_solve_moments",
+    "b200ens_host_alloc", "b200ens_host_free",
 ]
 
 _lib = None
@@ -100,6 +100,10 @@ def lib():
                                        C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.POINTER(Timing)]
     L.b200ens_solve_device.restype = C.c_int
+    L.b200ens_solve_moments.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
+                                        C.c_void_p, C.POINTER(Timing)]
+    L.b200ens_solve_moments.restype = C.c_int
     L.b200ens_host_alloc.argtypes = [C.c_size_t]
     L.b200ens_host_alloc.restype = C.c_void_p
     L.b200ens_host_free.argtypes = [C.c_void_p]
@@ -182,6 +186,26 @@ class Model:
         check(lib().b200ens_solve(self.handle, C.byref(opts), N, vp(u0), vp(p), vp(saveat), n_save, vp(dW), vp(out),
                                   None, vp(rc), vp(stats), C.byref(tm)))
         return out, rc, stats, tm
+
+    # ---- ensemble moments without shipping trajectories to the host (b200ens_solve_moments)
+    def solve_moments(self, opts, u0, p, saveat, dW=None):
+        N = u0.shape[0]
+        dt = self.dtype
+        u0 = np.ascontiguousarray(u0, dtype=dt)
+        p = np.ascontiguousarray(p, dtype=dt).reshape(N, self.n_param)
+        saveat = np.ascontiguousarray(saveat, dtype=dt)
+        n_save = saveat.shape[0]
+        s = np.zeros((n_save, self.n_state))
+        q = np.zeros((n_save, self.n_state))
+        cnt = C.c_int64(0)
+        rc = np.zeros(N, dtype=np.int32)
+        if dW is not None:
+            dW = np.ascontiguousarray(dW, dtype=dt)
+        tm = Timing()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        check(lib().b200ens_solve_moments(self.handle, C.byref(opts), N, vp(u0), vp(p), vp(saveat), n_save, vp(dW),
+                                          vp(s), vp(q), C.byref(cnt), vp(rc), C.byref(tm)))
+        return s, q, cnt.value, rc, tm
 
     # ---- device-buffer solve (b200ens_solve_device); pointers are raw ints (e.g. torch .data_ptr())
     def solve_device(self, opts, device, stream, N, d_u0, d_p, d_saveat, n_save, d_out, d_rc, d_stats=None,

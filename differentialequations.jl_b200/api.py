@@ -239,6 +239,35 @@ class EnsembleSolution:
         return _LazySeq(self)
 
 
+class EnsembleSummary:
+    """EnsembleSummary (qa.jl:54): per-time-point mean `u` and sample variance `v` over the trajectories that finished
+    with Success, computed ON THE DEVICE (EnsembleAnalysis.timestep_meanvar, qa.jl:211) -- the trajectories never travel
+    to the host.  `sum`/`sumsq`/`num_monte` are kept so that partial summaries of several ranks can be merged."""
+
+    def __init__(self, t, s, q, count, retcodes, elapsed, timing):
+        self.t = t
+        self.sum, self.sumsq, self.num_monte = s, q, int(count)
+        self.retcodes = retcodes
+        self.elapsedTime = elapsed
+        self.timing = timing
+        self.converged = bool(np.all(retcodes == ReturnCode.Success))
+
+    @property
+    def u(self):
+        return self.sum / max(self.num_monte, 1)
+
+    @property
+    def v(self):
+        n = self.num_monte
+        return (self.sumsq - self.sum * self.sum / max(n, 1)) / max(n - 1, 1)
+
+    def merge(self, other):
+        """Combine with the summary of another shard (sums and counts add)."""
+        return EnsembleSummary(self.t, self.sum + other.sum, self.sumsq + other.sumsq, self.num_monte + other.num_monte,
+                               np.concatenate([self.retcodes, other.retcodes]), max(self.elapsedTime, other.elapsedTime),
+                               self.timing)
+
+
 class _LazySeq:
     def __init__(self, es):
         self._es = es
@@ -336,7 +365,7 @@ def _pack(eprob, N, dtype):
 
 def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, abstol=None, reltol=None,
           adaptive=None, callback=None, maxiters=None, save_everystep=False, dense=False, seed=0, dW=None,
-          save_tstops=None, **kwargs):
+          save_tstops=None, summary=False, **kwargs):
     """solve(eprob, alg, EnsembleB200(); trajectories, saveat, dt, abstol, reltol, ...) -> EnsembleSolution.
     A plain ODEProblem/SDEProblem is solved as a one-trajectory ensemble and returns its ODESolution."""
     if kwargs:
@@ -397,6 +426,12 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, 
     o.refill_threshold = int(ensemblealg.refill_threshold)
     o.stage_outputs = int(ensemblealg.stage_outputs)
 
+    if summary:  # EnsembleAnalysis.timestep_meanvar on the device: returns an EnsembleSummary
+        t_solve = time.perf_counter()
+        s_, q_, cnt, rc, tm = model.solve_moments(o, u0, p, ts, dW=dW)
+        timing = tm.asdict()
+        timing["prob_func_s"] = t_pack
+        return EnsembleSummary(ts, s_, q_, cnt, rc, time.perf_counter() - t_solve, timing)
     t_solve = time.perf_counter()
     out, rc, stats, tm = model.solve(o, u0, p, ts, dW=dW)
     elapsed = time.perf_counter() - t_solve

@@ -245,6 +245,8 @@ struct DeviceCtx {
     Slot slot[2];
     void* saveat = nullptr;
     size_t cap_save = 0;
+    void* acc = nullptr;      // ensemble-moments accumulators
+    size_t cap_acc = 0;
     unsigned long long* counters = nullptr;  // ring for solve_device
     std::atomic<unsigned> ring{0};
     bool init = false;
@@ -390,6 +392,57 @@ int launch(b200ens_model* m, const LaunchPlan& lp, const B2Args& a, cudaStream_t
     return 0;
 }
 
+// ---------------------------------------------------------------- on-device ensemble moments (b2_moments.cuh)
+struct MomentsKernel {
+    std::mutex mu;
+    std::vector<char> cubin;
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;
+};
+MomentsKernel g_moments[2];
+
+int moments_kernel(int f64, cudaKernel_t* out) {
+    MomentsKernel& mk = g_moments[f64 ? 1 : 0];
+    std::lock_guard<std::mutex> lk(mk.mu);
+    if (!mk.kernel) {
+        std::string src = std::string("#define B2M_F64 ") + (f64 ? "1" : "0") + "\n#include \"b2_moments.cuh\"\n";
+        nvrtcProgram prog;
+        const char* hdr_names[kNumHeaders];
+        const char* hdr_text[kNumHeaders];
+        for (int i = 0; i < kNumHeaders; i++) {
+            hdr_names[i] = kHeaders[i].name;
+            hdr_text[i] = kHeaders[i].text;
+        }
+        if (nvrtcCreateProgram(&prog, src.c_str(), "b200ens_moments.cu", kNumHeaders, hdr_text, hdr_names) != NVRTC_SUCCESS)
+            return fail(B200ENS_E_COMPILE, "nvrtcCreateProgram(moments) failed");
+        const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+        nvrtcResult r = nvrtcCompileProgram(prog, 3, opts);
+        if (r != NVRTC_SUCCESS) {
+            size_t n = 0;
+            nvrtcGetProgramLogSize(prog, &n);
+            std::string log(n, 0);
+            if (n) nvrtcGetProgramLog(prog, &log[0]);
+            nvrtcDestroyProgram(&prog);
+            return fail(B200ENS_E_COMPILE, "NVRTC (moments kernel): %.1000s", log.c_str());
+        }
+        size_t n = 0;
+        nvrtcGetCUBINSize(prog, &n);
+        mk.cubin.resize(n);
+        nvrtcGetCUBIN(prog, mk.cubin.data());
+        nvrtcDestroyProgram(&prog);
+        CU(cudaLibraryLoadData(&mk.lib, mk.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+        CU(cudaLibraryGetKernel(&mk.kernel, mk.lib, "b2_moments_kernel"));
+    }
+    *out = mk.kernel;
+    return 0;
+}
+
+struct Moments {       // per-shard request: accumulate instead of copying out_u back
+    double* sum = nullptr;       // host [row_len], this shard's partial result
+    double* sumsq = nullptr;
+    long long count = 0;
+};
+
 struct ShardResult {
     int code = 0;
     std::string err;
@@ -401,7 +454,7 @@ struct ShardResult {
 // Solve trajectories [lo, hi) of the caller's host buffers on one device.
 int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, long long hi, const char* u0,
                 const char* p, const void* saveat, int n_save, const char* dW, char* out_u, int32_t* retcode,
-                b200ens_stats* stats, ShardResult* res) {
+                b200ens_stats* stats, ShardResult* res, Moments* mom = nullptr) {
     DeviceCtx* d;
     int rc = device_ctx(dev, &d);
     if (rc) return rc;
@@ -439,6 +492,17 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
     rc = plan_launch(m, o, d, chunk, n_save, &lp);
     if (rc) return rc;
     res->lp = lp;
+    // moments mode: device accumulators [sum | sumsq | count] instead of the D2H copy of out_u
+    const int row_len = n_save * n;
+    cudaKernel_t mom_kernel = nullptr;
+    double* d_acc = nullptr;
+    if (mom) {
+        if ((rc = moments_kernel(m->dtype == B200ENS_F64, &mom_kernel))) return rc;
+        if ((rc = grow(&d->acc, &d->cap_acc, (2 * (size_t)row_len + 1) * sizeof(double)))) return rc;
+        d_acc = static_cast<double*>(d->acc);
+        CU(cudaMemsetAsync(d_acc, 0, (2 * (size_t)row_len + 1) * sizeof(double), d->slot[0].stream));
+        CU(cudaStreamSynchronize(d->slot[0].stream));  // both pipeline streams accumulate into it
+    }
 
     struct Pending {
         bool used = false;
@@ -502,7 +566,21 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
         CU(cudaEventRecord(s.ev[1], s.stream));
         if ((rc = launch(m, l2, a, s.stream))) return rc;
         CU(cudaEventRecord(s.ev[2], s.stream));
-        if (n_save) CU(cudaMemcpyAsync(out_u + (size_t)g0 * out_per_traj, s.out, (size_t)cn * out_per_traj, cudaMemcpyDeviceToHost, s.stream));
+        if (mom) {
+            long long nn = cn;
+            int rl = row_len;
+            const void* po = s.out;
+            const int* prc = s.rc;
+            double* ps = d_acc;
+            double* pq = d_acc + row_len;
+            unsigned long long* pc = reinterpret_cast<unsigned long long*>(d_acc + 2 * (size_t)row_len);
+            void* margs[] = {&po, &prc, &nn, &rl, &ps, &pq, &pc};
+            const int gx = (row_len + 127) / 128;
+            const int gy = (int)std::max<long long>(1, std::min<long long>(cn, (long long)d->sms * 16 / gx));
+            CU(cudaLaunchKernel((const void*)mom_kernel, dim3(gx, gy), dim3(128), margs, 0, s.stream));
+            res->launches++;
+        } else if (n_save)
+            CU(cudaMemcpyAsync(out_u + (size_t)g0 * out_per_traj, s.out, (size_t)cn * out_per_traj, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(retcode + g0, s.rc, (size_t)cn * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         if (stats) CU(cudaMemcpyAsync(stats + g0, s.stats, (size_t)cn * sizeof(b200ens_stats), cudaMemcpyDeviceToHost, s.stream));
         CU(cudaEventRecord(s.ev[3], s.stream));
@@ -513,6 +591,17 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
     }
     for (int k = 0; k < 2; k++)
         if (pend[k].used && (rc = collect(d->slot[k]))) return rc;
+    if (mom) {
+        std::vector<double> h(2 * (size_t)row_len + 1);
+        CU(cudaMemcpy(h.data(), d_acc, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < row_len; i++) {
+            mom->sum[i] = h[i];
+            mom->sumsq[i] = h[row_len + i];
+        }
+        unsigned long long c;
+        memcpy(&c, &h[2 * (size_t)row_len], sizeof c);
+        mom->count = (long long)c;
+    }
     CU(cudaGetLastError());
     res->total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     return 0;
@@ -682,14 +771,15 @@ int b200ens_model_info(const b200ens_model* m, int64_t* cubin_bytes, int32_t* re
     return 0;
 }
 
-int b200ens_solve(b200ens_model* m, const b200ens_opts* o, int64_t N, const void* u0, const void* p,
-                  const void* saveat, int32_t n_save, const void* dW, void* out_u, void* out_t, int32_t* retcode,
-                  b200ens_stats* stats, b200ens_timing* timing) {
+static int solve_host(b200ens_model* m, const b200ens_opts* o, int64_t N, const void* u0, const void* p,
+                      const void* saveat, int32_t n_save, const void* dW, void* out_u, void* out_t, int32_t* retcode,
+                      b200ens_stats* stats, b200ens_timing* timing, double* msum, double* msumsq, int64_t* mcount) {
+    const bool moments = msum != nullptr;
     int rc = check_opts(m, o, n_save, dW);
     if (rc) return rc;
     if (N < 0) return fail(B200ENS_E_INVALID, "N < 0");
     if (timing) memset(timing, 0, sizeof *timing);
-    if (!u0 || !retcode || (m->n_param && !p) || (n_save && (!saveat || !out_u)))
+    if (!u0 || !retcode || (m->n_param && !p) || (n_save && (!saveat || (!out_u && !moments))))
         return fail(B200ENS_E_INVALID, "null buffer");
     if (out_t && n_save) memcpy(out_t, saveat, (size_t)n_save * m->elem());
     if (N == 0) return 0;
@@ -702,10 +792,19 @@ int b200ens_solve(b200ens_model* m, const b200ens_opts* o, int64_t N, const void
     if ((long long)devs.size() > N) devs.resize((size_t)N);
     const int G = (int)devs.size();
     std::vector<ShardResult> res(G);
+    const size_t row_len = (size_t)n_save * m->n_state;
+    std::vector<Moments> moms(G);
+    std::vector<std::vector<double>> mbuf(G);
+    if (moments)
+        for (int g = 0; g < G; g++) {
+            mbuf[g].assign(2 * row_len, 0.0);
+            moms[g].sum = mbuf[g].data();
+            moms[g].sumsq = mbuf[g].data() + row_len;
+        }
     auto run = [&](int g) {
         const long long lo = N * g / G, hi = N * (g + 1) / G;  // contiguous trajectory ranges
         res[g].code = solve_shard(m, o, devs[g], lo, hi, (const char*)u0, (const char*)p, saveat, n_save,
-                                  (const char*)dW, (char*)out_u, retcode, stats, &res[g]);
+                                  (const char*)dW, (char*)out_u, retcode, stats, &res[g], moments ? &moms[g] : nullptr);
         if (res[g].code) res[g].err = g_err;
     };
     if (G == 1) {
@@ -720,6 +819,17 @@ int b200ens_solve(b200ens_model* m, const b200ens_opts* o, int64_t N, const void
             g_err = res[g].err;
             return res[g].code;
         }
+    if (moments) {  // host gather of the per-device partial sums (no collective needed inside one process)
+        for (size_t i = 0; i < row_len; i++) msum[i] = msumsq[i] = 0.0;
+        *mcount = 0;
+        for (int g = 0; g < G; g++) {
+            for (size_t i = 0; i < row_len; i++) {
+                msum[i] += moms[g].sum[i];
+                msumsq[i] += moms[g].sumsq[i];
+            }
+            *mcount += moms[g].count;
+        }
+    }
     if (timing) {
         for (int g = 0; g < G; g++) {
             timing->h2d_ms = std::max(timing->h2d_ms, res[g].h2d);
@@ -735,6 +845,23 @@ int b200ens_solve(b200ens_model* m, const b200ens_opts* o, int64_t N, const void
         timing->regs = m->regs;
     }
     return 0;
+}
+
+int b200ens_solve(b200ens_model* m, const b200ens_opts* o, int64_t N, const void* u0, const void* p,
+                  const void* saveat, int32_t n_save, const void* dW, void* out_u, void* out_t, int32_t* retcode,
+                  b200ens_stats* stats, b200ens_timing* timing) {
+    return solve_host(m, o, N, u0, p, saveat, n_save, dW, out_u, out_t, retcode, stats, timing, nullptr, nullptr, nullptr);
+}
+
+int b200ens_solve_moments(b200ens_model* m, const b200ens_opts* o, int64_t N, const void* u0, const void* p,
+                          const void* saveat, int32_t n_save, const void* dW, double* sum, double* sumsq,
+                          int64_t* count, int32_t* retcode, b200ens_timing* timing) {
+    if (!sum || !sumsq || !count) return fail(B200ENS_E_INVALID, "null moments buffer");
+    if (N == 0) {
+        *count = 0;
+        for (int i = 0; m && i < n_save * m->n_state; i++) sum[i] = sumsq[i] = 0.0;
+    }
+    return solve_host(m, o, N, u0, p, saveat, n_save, dW, nullptr, nullptr, retcode, nullptr, timing, sum, sumsq, count);
 }
 
 int b200ens_solve_device(b200ens_model* m, const b200ens_opts* o, int32_t device, void* stream, int64_t N,

@@ -32,3 +32,22 @@ def solve_sharded(local_solve, N, u0, p, rank, world, gather=True, group=None):
     assert parts[0][0] == 0 and parts[-1][1] == N and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
     cat = lambda k: np.concatenate([x[k] for x in parts], axis=0)
     return cat(2), cat(3), (cat(4) if parts[0][4] is not None else None)
+
+
+def allreduce_summary(summary, group=None):
+    """Merge per-rank EnsembleSummary partial sums across ranks: the ONE collective of this back-end (SURVEY 8(f)
+    item 2) -- a few hundred doubles, all-reduced with torch.distributed (NCCL over NVLink on GPUs, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return summary
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    buf = torch.from_numpy(np.concatenate([summary.sum.ravel(), summary.sumsq.ravel(), [float(summary.num_monte)]])).to(dev)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    h = buf.cpu().numpy()
+    k = summary.sum.size
+    summary.sum = h[:k].reshape(summary.sum.shape)
+    summary.sumsq = h[k:2 * k].reshape(summary.sumsq.shape)
+    summary.num_monte = int(round(h[2 * k]))
+    return summary

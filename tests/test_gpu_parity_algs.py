@@ -208,3 +208,21 @@ def test_discrete_callback_and_callbackset(B, gpu_lib, oracle):
                                   abstol=1e-9, reltol=1e-9)
     assert np.array_equal(sol2.retcodes, rc2) and np.array_equal(sol2.stats, st2)
     assert np.abs(sol2.u_array - ref2).max() <= 1e-14
+
+
+def test_device_ensemble_summary_matches_host_statistics(B, gpu_lib, oracle):
+    """EnsembleAnalysis.timestep_meanvar computed on the device (b200ens_solve_moments) vs numpy statistics of the
+    oracle's trajectories; failed trajectories are excluded from the moments and counted out."""
+    from b200ens import workloads as W
+
+    N = 30000
+    saveat = np.arange(0.0, 10.5, 1.0)
+    u0, p = W.lorenz_params(N, "random", seed=17)
+    p[5] = np.nan                                               # one trajectory fails (DtNaN)
+    eprob = B.EnsembleProblem(W.lorenz_problem(), u0s=u0, ps=p)
+    summ = B.solve(eprob, B.Tsit5(), B.EnsembleB200(), trajectories=N, saveat=saveat, dt=0.1, summary=True)
+    ref, rc, _ = oracle.solve("lorenz", "Tsit5", u0, p, (0.0, 10.0), saveat, 0.1)
+    ok = rc == 1
+    assert summ.num_monte == ok.sum() == N - 1 and np.array_equal(summ.retcodes, rc)
+    assert np.allclose(summ.u, ref[ok].mean(axis=0), rtol=1e-12, atol=1e-12)
+    assert np.allclose(summ.v, ref[ok].var(axis=0, ddof=1), rtol=1e-9, atol=1e-12)

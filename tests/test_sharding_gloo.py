@@ -27,8 +27,14 @@ def _worker(rank, world, port, N, q):
         return out, rc, st
 
     out, rc, st = sharding.solve_sharded(local, N, u0, p, rank, world)
+    # the one collective of the back-end: all-reduce of per-rank ensemble moments (gloo here, NCCL on GPUs)
+    lo, hi = sharding.shard_range(N, rank, world)
+    mine = out if world == 1 or rank != 0 else out[lo:hi]
+    part = b200ens.EnsembleSummary(np.array([0.5, 1.0]), mine.sum(axis=0), (mine * mine).sum(axis=0), mine.shape[0],
+                                   np.ones(mine.shape[0], dtype=np.int32), 0.0, {})
+    summ = sharding.allreduce_summary(part)
     if rank == 0:
-        q.put((out, rc, st))
+        q.put((out, rc, st, summ.u, summ.v, summ.num_monte))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -55,10 +61,11 @@ def test_world2_gloo_matches_single_process(oracle):
     procs = [ctx.Process(target=_worker, args=(r, world, port, N, q)) for r in range(world)]
     for pr in procs:
         pr.start()
-    out, rc, st = q.get(timeout=180)
+    out, rc, st, mean, var, cnt = q.get(timeout=180)
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
     u0, p = W.gbm_params(N)
     ref, rc1, _ = oracle.solve("gbm", "EM", u0, p, (0.0, 1.0), [0.5, 1.0], 1 / 32, seed=99, adaptive=False)
     assert out.shape == (N, 2, 1) and np.array_equal(out, ref) and np.array_equal(rc, rc1)
+    assert cnt == N and np.allclose(mean, ref.mean(axis=0), rtol=1e-12) and np.allclose(var, ref.var(axis=0, ddof=1), rtol=1e-9)

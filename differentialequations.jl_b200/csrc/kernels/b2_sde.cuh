@@ -27,10 +27,12 @@ __device__ __forceinline__ uint4 b2_philox4x32_10(uint4 c, uint2 k) {
 #define B2_TWO_PI 6.283185307179586476925
 #if B2_F64
 #define B2_NORMALS_PER_CALL 2
-// counter = (traj_lo, traj_hi, step, block), key = (seed_lo, seed_hi); two 53-bit uniforms -> one Box-Muller pair
-__device__ __forceinline__ void b2_normals(unsigned long long seed, unsigned long long traj, unsigned step,
-                                           unsigned block, real* z) {
-    const uint4 r = b2_philox4x32_10(make_uint4((unsigned)traj, (unsigned)(traj >> 32), step, block),
+// Each trajectory consumes one continuous stream of normals: normal q = element q % K of the Philox block with
+// counter = (traj_lo, traj_hi, b_lo, b_hi), b = q / K, key = (seed_lo, seed_hi); no generated normal is discarded.
+// f64: two 53-bit uniforms -> one Box-Muller pair (K = 2)
+__device__ __forceinline__ void b2_normals(unsigned long long seed, unsigned long long traj, unsigned long long block,
+                                           real* z) {
+    const uint4 r = b2_philox4x32_10(make_uint4((unsigned)traj, (unsigned)(traj >> 32), (unsigned)block, (unsigned)(block >> 32)),
                                      make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
     const unsigned long long a = ((unsigned long long)r.x << 32) | r.y, b = ((unsigned long long)r.z << 32) | r.w;
     const double u1 = ((double)(a >> 11) + 0.5) * 1.1102230246251565404e-16;
@@ -42,10 +44,10 @@ __device__ __forceinline__ void b2_normals(unsigned long long seed, unsigned lon
 }
 #else
 #define B2_NORMALS_PER_CALL 4
-// four u32 -> two Box-Muller pairs; uniforms ((x>>8)+0.5)*2^-24 in (0,1)
-__device__ __forceinline__ void b2_normals(unsigned long long seed, unsigned long long traj, unsigned step,
-                                           unsigned block, real* z) {
-    const uint4 r = b2_philox4x32_10(make_uint4((unsigned)traj, (unsigned)(traj >> 32), step, block),
+// f32: four u32 -> two Box-Muller pairs (K = 4); uniforms ((x>>8)+0.5)*2^-24 in (0,1)
+__device__ __forceinline__ void b2_normals(unsigned long long seed, unsigned long long traj, unsigned long long block,
+                                           real* z) {
+    const uint4 r = b2_philox4x32_10(make_uint4((unsigned)traj, (unsigned)(traj >> 32), (unsigned)block, (unsigned)(block >> 32)),
                                      make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
     const unsigned w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -104,6 +106,9 @@ __device__ __forceinline__ void b2_sde_driver(const B2Args& a) {
                 si++;
             }
             const unsigned long long traj = a.traj_offset + (unsigned long long)idx;
+            real zbuf[B2_NORMALS_PER_CALL];
+            int zavail = 0;
+            unsigned long long zblock = 0;
             while (t < t1) {
                 if (step >= a.maxiters) {
                     rc = B2_RC_MAXITERS;
@@ -122,13 +127,26 @@ __device__ __forceinline__ void b2_sde_driver(const B2Args& a) {
                         dZ[i] = NVEC > 1 ? src[B2_N + i] : (real)0;
                     }
                 } else {
+                    // take the next NEED normals of this trajectory's stream; the K-normal Philox block is cached in
+                    // zbuf and indexed with selects (all lanes of a warp are in lockstep, so the refill branch is uniform)
                     constexpr int NEED = NVEC * B2_N;
-                    constexpr int NCALL = (NEED + B2_NORMALS_PER_CALL - 1) / B2_NORMALS_PER_CALL;
-                    real z[NCALL * B2_NORMALS_PER_CALL];
+                    real z[NEED];
                     const real sq = b2_sqrt(dt);
 #pragma unroll
-                    for (int b = 0; b < NCALL; b++)
-                        b2_normals(a.seed, traj, (unsigned)step, (unsigned)b, &z[b * B2_NORMALS_PER_CALL]);
+                    for (int j = 0; j < NEED; j++) {
+                        if (zavail == 0) {
+                            b2_normals(a.seed, traj, zblock, zbuf);
+                            zblock++;
+                            zavail = B2_NORMALS_PER_CALL;
+                        }
+                        const int pos = B2_NORMALS_PER_CALL - zavail;
+#if B2_F64
+                        z[j] = pos == 0 ? zbuf[0] : zbuf[1];
+#else
+                        z[j] = pos == 0 ? zbuf[0] : pos == 1 ? zbuf[1] : pos == 2 ? zbuf[2] : zbuf[3];
+#endif
+                        zavail--;
+                    }
 #pragma unroll
                     for (int i = 0; i < B2_N; i++) {
                         dW[i] = sq * z[i];

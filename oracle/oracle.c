@@ -70,12 +70,15 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-/* counter = (traj_lo, traj_hi, step, block), key = (seed_lo, seed_hi) -- SURVEY 8(d) cfg 4.
+/* Every trajectory consumes ONE continuous stream of standard normals; normal number q of trajectory i is
+ * element q % K of the Philox block with counter = (i_lo, i_hi, b_lo, b_hi), b = q / K, key = (seed_lo, seed_hi),
+ * K = normals per Philox call (4 in f32, 2 in f64).  A step that needs m normals takes the next m of the
+ * stream, so no generated normal is thrown away (SURVEY 7.3 "Integer Philox competes with FMA").
  * f32: four u32 -> two Box-Muller pairs -> 4 normals; uniforms ((x>>8)+0.5)*2^-24 in (0,1).
  * f64: two 53-bit uniforms ((x>>11)+0.5)*2^-53 -> one pair -> 2 normals. */
 #define TWO_PI 6.283185307179586476925
-void orc_normals_f32(uint64_t seed, uint64_t traj, uint32_t step, uint32_t block, float z[4]) {
-    const uint32_t ctr[4] = {(uint32_t)traj, (uint32_t)(traj >> 32), step, block};
+void orc_normals_f32(uint64_t seed, uint64_t traj, uint64_t block, float z[4]) {
+    const uint32_t ctr[4] = {(uint32_t)traj, (uint32_t)(traj >> 32), (uint32_t)block, (uint32_t)(block >> 32)};
     const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t r[4];
     orc_philox4x32_10(ctr, key, r);
@@ -88,8 +91,8 @@ void orc_normals_f32(uint64_t seed, uint64_t traj, uint32_t step, uint32_t block
         z[2 * h + 1] = rad * sinf(ang);
     }
 }
-void orc_normals_f64(uint64_t seed, uint64_t traj, uint32_t step, uint32_t block, double z[2]) {
-    const uint32_t ctr[4] = {(uint32_t)traj, (uint32_t)(traj >> 32), step, block};
+void orc_normals_f64(uint64_t seed, uint64_t traj, uint64_t block, double z[2]) {
+    const uint32_t ctr[4] = {(uint32_t)traj, (uint32_t)(traj >> 32), (uint32_t)block, (uint32_t)(block >> 32)};
     const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t r[4];
     orc_philox4x32_10(ctr, key, r);

@@ -74,9 +74,9 @@ float orc_fastlog2(float x);
 float orc_fastexp2(float y);
 /* Philox4x32-10 */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-/* normals exactly as the kernels draw them: counter=(traj_lo,traj_hi,step,block) */
-void orc_normals_f32(uint64_t seed, uint64_t traj, uint32_t step, uint32_t block, float z[4]);
-void orc_normals_f64(uint64_t seed, uint64_t traj, uint32_t step, uint32_t block, double z[2]);
+/* normals exactly as the kernels draw them: Philox block `block` of trajectory `traj`'s normal stream */
+void orc_normals_f32(uint64_t seed, uint64_t traj, uint64_t block, float z[4]);
+void orc_normals_f64(uint64_t seed, uint64_t traj, uint64_t block, double z[2]);
 int orc_max_threads(void);
 
 #ifdef __cplusplus

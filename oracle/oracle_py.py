@@ -153,12 +153,12 @@ def philox(ctr, key):
     return list(o)
 
 
-def normals(seed, traj, step, block, f64):
+def normals(seed, traj, block, f64):
     L = lib()
     if f64:
         z = (C.c_double * 2)()
-        L.orc_normals_f64(C.c_uint64(seed), C.c_uint64(traj), C.c_uint32(step), C.c_uint32(block), z)
+        L.orc_normals_f64(C.c_uint64(seed), C.c_uint64(traj), C.c_uint64(block), z)
     else:
         z = (C.c_float * 4)()
-        L.orc_normals_f32(C.c_uint64(seed), C.c_uint64(traj), C.c_uint32(step), C.c_uint32(block), z)
+        L.orc_normals_f32(C.c_uint64(seed), C.c_uint64(traj), C.c_uint64(block), z)
     return np.array(list(z))

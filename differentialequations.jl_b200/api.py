@@ -190,12 +190,14 @@ class EnsembleB200:
     devices: iterable of CUDA device ids (None = all visible); refill_threshold: idle lanes of a
     warp before it fetches new trajectories (0 = auto); stage_outputs: -1 auto / 0 / 1."""
 
-    def __init__(self, devices=None, refill_threshold=0, stage_outputs=-1, fast_math=False, packed_x2=False):
+    def __init__(self, devices=None, refill_threshold=0, stage_outputs=-1, fast_math=False, packed_x2=False,
+                 stage_vectors_in_smem=False):
         self.devices = devices
         self.refill_threshold = refill_threshold
         self.stage_outputs = stage_outputs
         self.fast_math = fast_math
         self.packed_x2 = packed_x2   # Float32 Tsit5: two trajectories per thread in packed FP32 (FFMA2)
+        self.stage_vectors_in_smem = stage_vectors_in_smem   # ERK k-vectors in shared memory (large n_state)
 
 
 # ---------------------------------------------------------------- solutions
@@ -286,11 +288,11 @@ class _LazySeq:
 _model_cache = {}
 
 
-def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False):
+def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False, ksmem=False):
     """Trace prob.f (and g / callback), emit CUDA C, JIT it for sm_100a.  Cached per function objects."""
     n, m = prob.u0.shape[0], prob.p.shape[0]
     dtype = prob.u0.dtype
-    key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math, packed_x2)
+    key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math, packed_x2, ksmem)
     hit = _model_cache.get(key)
     if hit is not None and hit[1] is prob.f:
         return hit[0]
@@ -315,7 +317,7 @@ def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False):
         srcs["dcondition_src"], srcs["daffect_src"], term = codegen.emit_discrete_callback(dcb, n, m)
         terminate |= 2 if term else 0
     model = _lib.Model(n, m, dtype, alg.name, name=getattr(prob.f, "__name__", "model"), fast_math=fast_math,
-                       packed_x2=packed_x2, **srcs)
+                       packed_x2=packed_x2, ksmem=ksmem, **srcs)
     model.sources = srcs
     model.event_terminate = terminate
     _model_cache[key] = (model, prob.f)
@@ -393,8 +395,9 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, 
     if dt is None:
         if not adaptive:
             raise ValueError("fixed-step solves need dt")
-        dt = _initial_dt(base, alg, abstol, reltol)
-    model = build_model(base, alg, callback, ensemblealg.fast_math, ensemblealg.packed_x2)
+        dt = 0.0   # automatic per-trajectory initial step on the device
+    model = build_model(base, alg, callback, ensemblealg.fast_math, ensemblealg.packed_x2,
+                        ensemblealg.stage_vectors_in_smem)
     ts = _saveat_array(saveat, base.tspan, dtype)
     t_pack = time.perf_counter()
     u0, p = _pack(eprob, N, dtype)
@@ -451,29 +454,3 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, 
             outs, _ = eprob.reduction([], outs, range(1, N + 1))
         sol.outputs = outs
     return sol
-
-
-def _initial_dt(prob, alg, abstol, reltol):
-    """Hairer-Norsett-Wanner initial step evaluated ONCE on the base problem on the host and used
-    for every trajectory.  (Upstream evaluates it per trajectory; the north-star signature passes dt.)"""
-    import sympy as sp
-
-    n, m = prob.u0.shape[0], prob.p.shape[0]
-    exprs, usyms, psyms, tsym = codegen.trace_vector_fn(prob.f, n, m)
-    fn = sp.lambdify([usyms, psyms, tsym], exprs, "math")
-    order = {"Tsit5": 5, "Vern7": 7, "Rosenbrock23": 2, "Rodas4": 4}.get(alg.name, 5)
-    abstol = 1e-6 if abstol is None else abstol
-    reltol = 1e-3 if reltol is None else reltol
-    u0 = prob.u0.astype(np.float64)
-    pp = list(prob.p.astype(np.float64)) if m > 0 else [0.0]
-    t0, t1 = prob.tspan
-    f0 = np.array(fn(list(u0), pp, t0), dtype=np.float64)
-    sk = abstol + np.abs(u0) * reltol
-    nrm = lambda x: float(np.sqrt(np.mean(x * x)))
-    d0, d1 = nrm(u0 / sk), nrm(f0 / sk)
-    dt0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
-    f1 = np.array(fn(list(u0 + dt0 * f0), pp, t0 + dt0), dtype=np.float64)
-    d2 = nrm((f1 - f0) / sk) / dt0
-    dmax = max(d1, d2)
-    dt1 = max(1e-6, 1e-3 * dt0) if dmax <= 1e-15 else 10.0 ** (-(2 + np.log10(dmax)) / order)
-    return min(100 * dt0, dt1, t1 - t0)

@@ -355,7 +355,8 @@ int fill_args(const b200ens_model* m, const b200ens_opts* o, B2Args* a) {
     if (st < 0) st = (m->alg == B200ENS_RODAS4 || m->alg == B200ENS_RODAS5 || m->alg == B200ENS_RODAS5P) ? 1 : 0;
     a->save_tstops = st;
     if (!(o->t1 > o->t0)) return fail(B200ENS_E_INVALID, "tspan must satisfy t1 > t0 (forward integration only)");
-    if (!(o->dt > 0)) return fail(B200ENS_E_INVALID, "dt must be > 0 (initial dt for adaptive, step for fixed)");
+    if (!(o->dt > 0) && !(a->adaptive && o->dt == 0 && !m->x2))
+        return fail(B200ENS_E_INVALID, "dt must be > 0 (fixed step, SDE, packed kernel) or 0 = automatic initial step (adaptive)");
     a->f_t0 = (float)a->t0;
     a->f_t1 = (float)a->t1;
     a->f_dt = (float)a->dt;
@@ -681,7 +682,8 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     int rc = 0;
     const char* force_k = getenv("B200ENS_KSMEM");
     const int nvec = d->alg == B200ENS_TSIT5 ? 7 : d->alg == B200ENS_VERN7 ? 14 : 0;
-    bool try_regs = !(force_k && atoi(force_k) == 1 && nvec);
+    const bool flag_k = (d->flags & B200ENS_MODEL_KSMEM) != 0;
+    bool try_regs = !(((force_k && atoi(force_k) == 1) || flag_k) && nvec);
     // Packed FP32: two trajectories per thread (FFMA2/FADD2/FMUL2, Blackwell only) for the register-light
     // Float32 explicit case without callbacks -- the headline Lorenz/Tsit5 configuration.
     const char* force_x2 = getenv("B200ENS_X2");

@@ -44,6 +44,7 @@ struct B2Tsit5 {
     __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {
         B2_RHS_TO(k1, u, t);
     }
+    __device__ __forceinline__ real fsal0(int i) const { return KV(k1, i); }  // f(u, t) of the current state
 #if B2_X2
     static constexpr int NF_ATTEMPT = 6;
     // packed mode: (re)start only the halves in (m0, m1); the other half keeps its k1
@@ -183,6 +184,7 @@ struct B2Vern7 {
         B2_RHS_TO(k1, u, t);
         have_extra = false;
     }
+    __device__ __forceinline__ real fsal0(int i) const { return KV(k1, i); }
     __device__ __forceinline__ void step(const real (&up)[B2_N], const real (&p)[B2_NPA], real t, real dt,
                                          real (&u)[B2_N], real (&ut)[B2_N], bool adaptive, int& nf) {
         real tmp[B2_N], q2[B2_N];

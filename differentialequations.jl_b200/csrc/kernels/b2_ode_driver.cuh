@@ -97,6 +97,37 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                         }
                         alg.start(u, p, t);
                         nf = 1;
+                        if (adaptive && !(dt_user > (real)0)) {
+                            // automatic initial step (Hairer-Norsett-Wanner as in OrdinaryDiffEq's initdt)
+                            real a0 = 0, a1 = 0, a2 = 0, u1[B2_N], f1[B2_N];
+#pragma unroll
+                            for (int i = 0; i < B2_N; i++) {
+                                const real sk = b2_fma(b2_abs(u[i]), reltol, abstol);
+                                const real r0 = u[i] / sk, r1 = alg.fsal0(i) / sk;
+                                a0 = b2_fma(r0, r0, a0);
+                                a1 = b2_fma(r1, r1, a1);
+                            }
+                            const real d0 = b2_sqrt(a0 / (real)B2_N), d1 = b2_sqrt(a1 / (real)B2_N);
+                            real dt0 = (d0 < (real)1e-5 || d1 < (real)1e-5) ? (real)1e-6 : (real)0.01 * (d0 / d1);
+                            dt0 = b2_min(dt0, dtmax);
+#pragma unroll
+                            for (int i = 0; i < B2_N; i++) u1[i] = b2_fma(dt0, alg.fsal0(i), u[i]);
+                            b2_rhs(f1, u1, p, t0 + dt0);
+                            nf++;
+#pragma unroll
+                            for (int i = 0; i < B2_N; i++) {
+                                const real sk = b2_fma(b2_abs(u[i]), reltol, abstol);
+                                const real r2 = (f1[i] - alg.fsal0(i)) / sk;
+                                a2 = b2_fma(r2, r2, a2);
+                            }
+                            const real d2 = b2_sqrt(a2 / (real)B2_N) / dt0;
+                            const real dmx = b2_max(d1, d2);
+                            real dt1;
+                            if (dmx <= (real)1e-15) dt1 = b2_max((real)1e-6, dt0 * (real)1e-3);
+                            else dt1 = (real)b2_fastexp2(__fmul_rn(-__fadd_rn(6.6438562f, b2_fastlog2((float)dmx)),
+                                                                  __fdiv_rn(1.0f, (float)Alg::ORDER)));
+                            dt = b2_min(b2_min((real)100 * dt0, dt1), dtmax);
+                        }
                         active = true;
 #if B2_HAS_EVENT
                         just_fired = false;

@@ -86,6 +86,7 @@ struct B2Ros23 {
     __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {
         b2_rhs(f0, u, p, t);
     }
+    __device__ __forceinline__ real fsal0(int i) const { return f0[i]; }
     __device__ __forceinline__ void step(const real (&up)[B2_N], const real (&p)[B2_NPA], real t, real dt,
                                          real (&u)[B2_N], real (&ut)[B2_N], bool, int& nf) {
         B2LU lu;
@@ -206,6 +207,7 @@ struct B2Rodas {
     __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {
         b2_rhs(f0, u, p, t);
     }
+    __device__ __forceinline__ real fsal0(int i) const { return f0[i]; }
     __device__ __forceinline__ void step(const real (&up)[B2_N], const real (&p)[B2_NPA], real t, real dt,
                                          real (&u)[B2_N], real (&ut)[B2_N], bool, int& nf) {
         B2LU lu;

@@ -55,6 +55,8 @@ enum b200ens_error {
                                       (FFMA2/FADD2/FMUL2, sm_100+); bit-identical results; measured 5% SLOWER than the
                                       scalar kernel on B200 (profiles/README.md), hence opt-in */
 
+#define B200ENS_MODEL_KSMEM 4u     /* force the ERK stage vectors into shared memory (default: only when ptxas spills > 6 KB) */
+
 /* What a problem looks like to the library: ODEProblem / SDEProblem (qa.jl:86,103) with f,
  * jac, tgrad, g and one ContinuousCallback (qa.jl:26; test/core.jl:69-72) given as CUDA-C
  * source defining these device functions (`real` is float or double per dtype):
@@ -92,7 +94,7 @@ typedef struct b200ens_opts {
     uint32_t struct_size;   /* sizeof(b200ens_opts) */
     int32_t adaptive;       /* 1 adaptive (default for ODE algs), 0 fixed dt */
     double t0, t1;          /* tspan */
-    double dt;              /* initial dt (adaptive) or the fixed dt */
+    double dt;              /* initial dt (adaptive; 0 = automatic per-trajectory initial step) or the fixed dt */
     double abstol, reltol;  /* defaults 1e-6 / 1e-3 */
     double dtmin, dtmax;    /* defaults 0 (+ eps(t) floor) / t1-t0 */
     double qmin, qmax, gamma, beta1, beta2, qoldinit; /* PI controller; defaults 1/5, 10, 9/10, 7/(10k), 2/(5k), 1e-4 */

@@ -92,3 +92,20 @@ def test_device_resident_entry_matches_host_entry(B, gpu_lib):
     s.synchronize()
     assert np.array_equal(d_out.cpu().numpy(), out) and np.array_equal(d_rc.cpu().numpy(), rc)
     assert np.array_equal(d_st.cpu().numpy(), st)
+
+
+@pytest.mark.parametrize("alg", ["Tsit5", "Vern7", "Rodas5P"])
+def test_automatic_initial_dt_matches_oracle(B, gpu_lib, oracle, alg):
+    """No dt given (test/core.jl:14,32,47 call solve without dt): per-trajectory Hairer-Norsett-Wanner initial step
+    on the device, identical to the oracle's."""
+    from b200ens import workloads as W
+
+    N = 2000
+    u0, p = W.lorenz_params(N, "random", seed=12)
+    saveat = np.arange(0.0, 1.05, 0.1)
+    sol = B.solve(B.EnsembleProblem(W.lorenz_problem(tspan=(0.0, 1.0)), u0s=u0, ps=p), getattr(B, alg)(), B.EnsembleB200(),
+                  trajectories=N, saveat=saveat, abstol=1e-8, reltol=1e-8)
+    ref, rc, st = oracle.solve("lorenz", alg, u0, p, (0.0, 1.0), saveat, 0.0, abstol=1e-8, reltol=1e-8)
+    assert np.all(sol.retcodes == 1) and np.array_equal(sol.retcodes, rc)
+    assert np.array_equal(sol.stats[:, :3], st[:, :3])
+    assert np.abs(sol.u_array - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())

@@ -101,9 +101,11 @@ def test_solve_argument_errors(B):
         B.solve(prob, B.Tsit5(), adaptive=False)                                         # fixed step needs dt
 
 
-def test_initial_dt_heuristic_is_sane(B):
-    from b200ens import workloads as W
-    from b200ens.api import _initial_dt
-
-    dt = _initial_dt(W.lorenz_problem(), B.Tsit5(), None, None)
-    assert 1e-6 < dt < 0.5
+def test_automatic_initial_dt_in_the_oracle(oracle):
+    """solve(prob, Tsit5(), reltol=1e-8, abstol=1e-8) without dt (test/core.jl:14): the Hairer-Norsett-Wanner initial
+    step is computed per trajectory; result and step count must be close to a hand-picked dt run."""
+    g = [[0.5]], [[1.01]]
+    out, rc, st = oracle.solve("linear", "Tsit5", g[0], g[1], (0.0, 1.0), [1.0], 0.0, abstol=1e-8, reltol=1e-8)
+    assert rc[0] == 1 and abs(out[0, 0, 0] - 0.5 * np.exp(1.01)) < 1e-8
+    out2, rc2, st2 = oracle.solve("linear", "Tsit5", g[0], g[1], (0.0, 1.0), [1.0], 0.05, abstol=1e-8, reltol=1e-8)
+    assert abs(int(st[0, 0]) - int(st2[0, 0])) <= 3 and st[0, 2] == st[0, 0] * 6 + st[0, 1] * 6 + 2

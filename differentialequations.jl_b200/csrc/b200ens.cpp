@@ -716,10 +716,11 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
             if (m->spill <= 96 || mb <= 1 || getenv("B200ENS_MINBLOCKS")) break;
         }
     }
-    // Large systems: the k-vectors do not fit the register file (config 5: n=16 f64 Vern7 spilled 4 KB per
-    // thread and was DRAM-bound on local-memory traffic).  Recompile with the stage vectors in shared memory,
-    // CTA size chosen so that two CTAs fit in the 227 KB of an SM.
-    if (!rc && nvec && !m->x2 && ((try_regs && m->spill > 6000 && !(force_k && atoi(force_k) == 0)) || !try_regs)) {
+    // Large systems: the k-vectors do not fit the register file (config 5: n=16 f64 Vern7 spills 4 KB per thread).
+    // On request (B200ENS_MODEL_KSMEM / B200ENS_KSMEM=1) compile with the stage vectors in shared memory, CTA size
+    // chosen so that two CTAs fit in the 227 KB of an SM.  Opt-in: measured 0.8-1.35x of the register variant
+    // (profiles/README.md), no consistent win.
+    if (!rc && nvec && !m->x2 && (!try_regs)) {
         const int per_thread = nvec * d->n_state * (d->dtype == B200ENS_F64 ? 8 : 4);
         int block = std::min(128, (114688 / per_thread) / 32 * 32);
         if (block >= 32) {

@@ -237,12 +237,16 @@ struct Slot {  // one pipeline slot = one stream + device buffers for one chunk
     b200ens_stats* stats = nullptr;
     unsigned long long* counter = nullptr;
     size_t cap_u0 = 0, cap_p = 0, cap_out = 0, cap_dW = 0, cap_n = 0;
+    // pinned bounce buffers for callers whose arrays are pageable (e.g. plain Julia Arrays)
+    char *h_in = nullptr, *h_out = nullptr;
+    size_t cap_hin = 0, cap_hout = 0;
 };
+constexpr int kMaxSlots = 4;
 struct DeviceCtx {
     int dev = -1;
     int sms = 0;
     std::mutex mu;  // one host-buffer solve at a time per device
-    Slot slot[2];
+    Slot slot[kMaxSlots];
     void* saveat = nullptr;
     size_t cap_save = 0;
     void* acc = nullptr;      // ensemble-moments accumulators
@@ -284,6 +288,43 @@ int grow(void** ptr, size_t* cap, size_t need) {
     const size_t want = need + need / 8 + 256;
     CU(cudaMalloc(ptr, want));
     *cap = want;
+    return 0;
+}
+
+// ---------------------------------------------------------------- pageable host buffers
+bool is_pinned(const void* ptr) {
+    if (!ptr) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+void par_memcpy(void* dst, const void* src, size_t bytes) {
+    const size_t kMin = 2u << 20;
+    int nt = (int)std::min<size_t>(8, bytes / kMin);
+    if (nt <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = (bytes / nt + 63) & ~(size_t)63;
+    for (int i = 0; i < nt; i++) {
+        const size_t off = (size_t)i * per;
+        if (off >= bytes) break;
+        const size_t len = std::min(per, bytes - off);
+        th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+    }
+    for (auto& t : th) t.join();
+}
+int grow_host(char** ptr, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*ptr) CU(cudaFreeHost(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    CU(cudaHostAlloc((void**)ptr, need + need / 8 + 256, cudaHostAllocDefault));
+    *cap = need + need / 8 + 256;
     return 0;
 }
 
@@ -482,10 +523,12 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
     const size_t per_traj = (size_t)n * es + (size_t)np * es + out_per_traj + noise_per_traj + 4 + sizeof(b200ens_stats);
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    // two pipeline slots: at least 256k trajectories per launch (smaller launches lose to the drain tail of the
-    // persistent kernel, profiles/r1_e2e_probe.log), otherwise half the shard per slot
-    long long chunk = std::min<long long>(total, std::max<long long>(1 << 18, (total + 1) / 2));
-    const long long mem_cap = (long long)((free_b / 4) / std::max<size_t>(1, per_traj));
+    // four pipeline slots (stream + buffers each), chunk = a quarter of the shard clamped to [128k, 1M] trajectories:
+    // everything is enqueued without host synchronisation, the D2H engine never idles after the first chunk
+    // (profiles/r1_e2e_probe.log: 3.6 ms vs 4.3 ms with two half-shard chunks for 1M Float32 trajectories).  Smaller
+    // launches lose to the drain tail of the persistent kernel.
+    long long chunk = std::min<long long>(total, std::max<long long>(1 << 17, std::min<long long>(1 << 20, (total + 3) / 4)));
+    const long long mem_cap = (long long)((free_b / 8) / std::max<size_t>(1, per_traj));
     chunk = std::max<long long>(1, std::min(chunk, mem_cap));
     if (const char* e = getenv("B200ENS_CHUNK")) chunk = std::max<long long>(1, atoll(e));
 
@@ -505,13 +548,29 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
         CU(cudaStreamSynchronize(d->slot[0].stream));  // both pipeline streams accumulate into it
     }
 
+    // Callers with pageable arrays (plain Julia Arrays, numpy): stage through pinned bounce buffers with a parallel
+    // host memcpy (cudaMemcpyAsync straight from pageable memory measured 10x slower, profiles/r1_e2e_probe.log).
+    const bool stage_in = !(is_pinned(u0) && is_pinned(p) && is_pinned(dW));
+    const bool stage_out = !(is_pinned(mom ? nullptr : out_u) && is_pinned(retcode) && is_pinned(stats));
     struct Pending {
         bool used = false;
-    } pend[2];
+        long long g0 = 0, cn = 0;
+    } pend[kMaxSlots];
+    int nslots = kMaxSlots;
+    if (const char* e = getenv("B200ENS_SLOTS")) nslots = std::max(1, std::min(kMaxSlots, atoi(e)));
     long long done = 0;
     int it = 0;
-    auto collect = [&](Slot& s) -> int {
+    const size_t out_b = (mom || !n_save) ? 0 : out_per_traj;   // bytes per trajectory in the staged output block
+    auto collect = [&](Slot& s, const Pending& pd) -> int {
         CU(cudaEventSynchronize(s.ev[3]));
+        if (stage_out) {
+            const char* h = s.h_out;
+            if (out_b) par_memcpy(out_u + (size_t)pd.g0 * out_per_traj, h, (size_t)pd.cn * out_b);
+            h += (size_t)pd.cn * out_b;
+            memcpy(retcode + pd.g0, h, (size_t)pd.cn * sizeof(int));
+            h += (size_t)pd.cn * sizeof(int);
+            if (stats) par_memcpy(stats + pd.g0, h, (size_t)pd.cn * sizeof(b200ens_stats));
+        }
         float a_ = 0, b_ = 0, c_ = 0;
         CU(cudaEventElapsedTime(&a_, s.ev[0], s.ev[1]));
         CU(cudaEventElapsedTime(&b_, s.ev[1], s.ev[2]));
@@ -524,9 +583,9 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
     while (done < total) {
         const long long cn = std::min(chunk, total - done);
         const long long g0 = lo + done;  // global index of the chunk's first trajectory
-        Slot& s = d->slot[it & 1];
-        if (pend[it & 1].used) {
-            rc = collect(s);
+        Slot& s = d->slot[it % nslots];
+        if (pend[it % nslots].used) {
+            rc = collect(s, pend[it % nslots]);
             if (rc) return rc;
         }
         if ((rc = grow(&s.u0, &s.cap_u0, (size_t)cn * n * es))) return rc;
@@ -542,10 +601,24 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
             CU(cudaMalloc(&s.stats, (size_t)cn * sizeof(b200ens_stats)));
             s.cap_n = (size_t)cn;
         }
+        const char *src_u0 = u0 + (size_t)g0 * n * es, *src_p = np ? p + (size_t)g0 * np * es : nullptr;
+        const char* src_dW = dW ? dW + (size_t)g0 * noise_per_traj : nullptr;
+        if (stage_in) {
+            const size_t bu = (size_t)cn * n * es, bp = (size_t)cn * np * es, bw = dW ? (size_t)cn * noise_per_traj : 0;
+            if ((rc = grow_host(&s.h_in, &s.cap_hin, bu + bp + bw))) return rc;
+            par_memcpy(s.h_in, src_u0, bu);
+            if (bp) par_memcpy(s.h_in + bu, src_p, bp);
+            if (bw) par_memcpy(s.h_in + bu + bp, src_dW, bw);
+            src_u0 = s.h_in;
+            src_p = s.h_in + bu;
+            src_dW = dW ? s.h_in + bu + bp : nullptr;
+        }
+        if (stage_out && (rc = grow_host(&s.h_out, &s.cap_hout, (size_t)cn * (out_b + sizeof(int) + (stats ? sizeof(b200ens_stats) : 0)))))
+            return rc;
         CU(cudaEventRecord(s.ev[0], s.stream));
-        CU(cudaMemcpyAsync(s.u0, u0 + (size_t)g0 * n * es, (size_t)cn * n * es, cudaMemcpyHostToDevice, s.stream));
-        if (np) CU(cudaMemcpyAsync(s.p, p + (size_t)g0 * np * es, (size_t)cn * np * es, cudaMemcpyHostToDevice, s.stream));
-        if (dW) CU(cudaMemcpyAsync(s.dW, dW + (size_t)g0 * noise_per_traj, (size_t)cn * noise_per_traj, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.u0, src_u0, (size_t)cn * n * es, cudaMemcpyHostToDevice, s.stream));
+        if (np) CU(cudaMemcpyAsync(s.p, src_p, (size_t)cn * np * es, cudaMemcpyHostToDevice, s.stream));
+        if (dW) CU(cudaMemcpyAsync(s.dW, src_dW, (size_t)cn * noise_per_traj, cudaMemcpyHostToDevice, s.stream));
         CU(cudaMemsetAsync(s.counter, 0, sizeof(unsigned long long), s.stream));
         B2Args a = base;
         a.u0 = s.u0;
@@ -580,18 +653,25 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
             const int gy = (int)std::max<long long>(1, std::min<long long>(cn, (long long)d->sms * 16 / gx));
             CU(cudaLaunchKernel((const void*)mom_kernel, dim3(gx, gy), dim3(128), margs, 0, s.stream));
             res->launches++;
-        } else if (n_save)
-            CU(cudaMemcpyAsync(out_u + (size_t)g0 * out_per_traj, s.out, (size_t)cn * out_per_traj, cudaMemcpyDeviceToHost, s.stream));
-        CU(cudaMemcpyAsync(retcode + g0, s.rc, (size_t)cn * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-        if (stats) CU(cudaMemcpyAsync(stats + g0, s.stats, (size_t)cn * sizeof(b200ens_stats), cudaMemcpyDeviceToHost, s.stream));
+        }
+        {
+            char* dst_out = stage_out ? s.h_out : (out_u ? out_u + (size_t)g0 * out_per_traj : nullptr);
+            char* dst_rc = stage_out ? s.h_out + (size_t)cn * out_b : (char*)(retcode + g0);
+            char* dst_st = stage_out ? dst_rc + (size_t)cn * sizeof(int) : (char*)(stats ? stats + g0 : nullptr);
+            if (out_b) CU(cudaMemcpyAsync(dst_out, s.out, (size_t)cn * out_per_traj, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(dst_rc, s.rc, (size_t)cn * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            if (stats) CU(cudaMemcpyAsync(dst_st, s.stats, (size_t)cn * sizeof(b200ens_stats), cudaMemcpyDeviceToHost, s.stream));
+        }
         CU(cudaEventRecord(s.ev[3], s.stream));
-        pend[it & 1].used = true;
+        pend[it % nslots].used = true;
+        pend[it % nslots].g0 = g0;
+        pend[it % nslots].cn = cn;
         res->launches++;
         done += cn;
         it++;
     }
-    for (int k = 0; k < 2; k++)
-        if (pend[k].used && (rc = collect(d->slot[k]))) return rc;
+    for (int k = 0; k < kMaxSlots; k++)
+        if (pend[k].used && (rc = collect(d->slot[k], pend[k]))) return rc;
     if (mom) {
         std::vector<double> h(2 * (size_t)row_len + 1);
         CU(cudaMemcpy(h.data(), d_acc, h.size() * sizeof(double), cudaMemcpyDeviceToHost));

@@ -109,3 +109,23 @@ def test_automatic_initial_dt_matches_oracle(B, gpu_lib, oracle, alg):
     assert np.all(sol.retcodes == 1) and np.array_equal(sol.retcodes, rc)
     assert np.array_equal(sol.stats[:, :3], st[:, :3])
     assert np.abs(sol.u_array - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+
+
+def test_pinned_and_pageable_host_buffers_agree(B, gpu_lib):
+    """b200ens_solve takes any host pointer: pinned arrays go straight to the copy engines, pageable ones are staged
+    through pinned bounce buffers with a parallel memcpy.  Both must give the same bytes."""
+    from b200ens import workloads as W
+
+    N = 300007
+    u0, p = W.lorenz_params(N, "random", seed=31, dtype=np.float32)
+    m = B.build_model(W.lorenz_problem(np.float32), B.Tsit5())
+    o = B._lib.default_opts()
+    o.t0, o.t1, o.dt = 0.0, 10.0, 0.1
+    saveat = np.arange(0, 10.5, 1.0)
+    out_a, rc_a, st_a, _ = m.solve(o, u0, p, saveat)                       # pageable numpy arrays
+    pin = lambda a: (lambda b: (b.__setitem__(slice(None), a), b)[1])(B.pinned_empty(a.shape, a.dtype))
+    out_p = B.pinned_empty((N, 11, 3), np.float32)
+    rc_p = B.pinned_empty((N,), np.int32)
+    st_p = B.pinned_empty((N, 4), np.int32)
+    m.solve(o, pin(u0), pin(p), saveat, out=out_p, rc=rc_p, stats=st_p)
+    assert np.array_equal(out_a, out_p) and np.array_equal(rc_a, rc_p) and np.array_equal(st_a, st_p)

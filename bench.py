@@ -155,6 +155,30 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def numa_bind(dev):
+    """Best effort: run this rank (and first-touch its pinned host buffers) on the NUMA node its GPU hangs off, so
+    that H2D/D2H traffic of the ranks does not cross the socket interconnect.  Returns a short description."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return f"{bdf}: no NUMA affinity reported"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{bdf}: node {node}, {len(allowed)} cpus"
+        return f"{bdf}: node {node} has no allowed cpus"
+    except Exception as e:  # noqa: BLE001
+        return f"unavailable ({type(e).__name__})"
+
+
 def fma_peak(device, f64):
     lib = ctypes.CDLL(os.path.join(ROOT, "differentialequations.jl_b200", "csrc", "libb200peak.so"))
     lib.b200_fma_peak_tflops.restype = ctypes.c_double
@@ -179,6 +203,7 @@ def main():
 
     dev = local_rank
     torch.cuda.set_device(dev)
+    numa = numa_bind(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     f64 = a.dtype == "f64"
@@ -306,7 +331,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": workload_name(a), "trajectories_per_gpu": N, "l2": "flushed between timed steps (256 MiB memset)",
                        "parallelism": f"trajectory ranges sharded over {world} GPU(s), no collective",
-                       "refill_threshold": a.refill, "stage_outputs": a.stage, "all_success": ok,
+                       "refill_threshold": a.refill, "stage_outputs": a.stage, "all_success": ok, "numa": numa,
                        "regs": model.info()["regs"]},
             "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "trajectories/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

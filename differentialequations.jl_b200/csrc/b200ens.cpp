@@ -427,7 +427,7 @@ int check_opts(const b200ens_model* m, const b200ens_opts* o, int n_save, const 
 
 int launch(b200ens_model* m, const LaunchPlan& lp, const B2Args& a, cudaStream_t stream) {
     void* params[] = {(void*)&a};
-    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && !a.save_tstops) ? m->kernel_adaptive : m->kernel;
+    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && !a.save_tstops && a.dt > 0) ? m->kernel_adaptive : m->kernel;
     if (k != m->kernel && lp.smem > 48 * 1024)
         CU(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, lp.smem));
     CU(cudaLaunchKernel((const void*)k, dim3(lp.grid), dim3(lp.block), params, lp.smem, stream));
@@ -797,10 +797,11 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
         }
     }
     // Large systems: the k-vectors do not fit the register file (config 5: n=16 f64 Vern7 spills 4 KB per thread).
-    // On request (B200ENS_MODEL_KSMEM / B200ENS_KSMEM=1) compile with the stage vectors in shared memory, CTA size
-    // chosen so that two CTAs fit in the 227 KB of an SM.  Opt-in: measured 0.8-1.35x of the register variant
-    // (profiles/README.md), no consistent win.
-    if (!rc && nvec && !m->x2 && (!try_regs)) {
+    // When the register variant spills more than 4 KB (or on request: B200ENS_MODEL_KSMEM / B200ENS_KSMEM=1) compile
+    // with the stage vectors in shared memory, CTA size chosen so that two CTAs fit in the 227 KB of an SM, and keep
+    // it if it spills less.  Measured on config 5 (profiles/README.md): 156 vs 204 ms (saveat 101), 234 vs 297 ms
+    // (saveat 1001) per 200k trajectories.
+    if (!rc && nvec && !m->x2 && (!try_regs || (m->spill > 4096 && !(force_k && atoi(force_k) == 0)))) {
         const int per_thread = nvec * d->n_state * (d->dtype == B200ENS_F64 ? 8 : 4);
         int block = std::min(128, (114688 / per_thread) / 32 * 32);
         if (block >= 32) {

@@ -15,8 +15,9 @@
 #include "b2_common.cuh"
 
 // ADAPT / TSTOPS: 0 or 1 = compile-time specialisation of the two solve options that sit in the per-iteration
-// control path, -1 = read them from the argument block.
-template <class Alg, int ADAPT = -1, int TSTOPS = -1>
+// control path, -1 = read them from the argument block.  AUTODT = 0 compiles the automatic-initial-step block out
+// (the specialised entry is only launched with a caller-supplied dt; keeps its register pressure down).
+template <class Alg, int ADAPT = -1, int TSTOPS = -1, int AUTODT = 1>
 __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     extern __shared__ __align__(16) unsigned char b2_smem[];
     const unsigned lane = threadIdx.x & 31u;
@@ -97,7 +98,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                         }
                         alg.start(u, p, t);
                         nf = 1;
-                        if (adaptive && !(dt_user > (real)0)) {
+                        if (AUTODT && adaptive && !(dt_user > (real)0)) {
                             // automatic initial step (Hairer-Norsett-Wanner as in OrdinaryDiffEq's initdt)
                             real a0 = 0, a1 = 0, a2 = 0, u1[B2_N], f1[B2_N];
 #pragma unroll

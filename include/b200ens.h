@@ -55,7 +55,7 @@ enum b200ens_error {
                                       (FFMA2/FADD2/FMUL2, sm_100+); bit-identical results; measured 5% SLOWER than the
                                       scalar kernel on B200 (profiles/README.md), hence opt-in */
 
-#define B200ENS_MODEL_KSMEM 4u     /* ERK stage vectors in shared memory instead of registers (large n_state; opt-in) */
+#define B200ENS_MODEL_KSMEM 4u     /* force ERK stage vectors into shared memory (default: automatic when the register variant spills > 4 KB) */
 
 /* What a problem looks like to the library: ODEProblem / SDEProblem (qa.jl:86,103) with f,
  * jac, tgrad, g and one ContinuousCallback (qa.jl:26; test/core.jl:69-72) given as CUDA-C

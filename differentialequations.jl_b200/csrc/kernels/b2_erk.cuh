@@ -29,6 +29,13 @@
 #define B2_RHS_TO(k, x, t_) b2_rhs(k, x, p, t_)
 #endif
 #define KV(name, i) name[(i) * B2_KSTRIDE]
+// In shared-memory mode ptxas otherwise hoists the loads of all components of a stage to the top of the unrolled
+// loop (hundreds of live registers -> spills); a compiler-level memory barrier per component keeps live ranges short.
+#if B2_KSMEM
+#define B2_KBAR asm volatile("" ::: "memory")
+#else
+#define B2_KBAR
+#endif
 
 #define TS(x) ((real)(B2T_TSIT5_##x))
 
@@ -72,6 +79,7 @@ struct B2Tsit5 {
             real s = TS(a31) * KV(k1, i);
             s = b2_fma(TS(a32), KV(k2, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
         B2_RHS_TO(k3, tmp, t + TS(c3) * dt);
 #pragma unroll
@@ -80,6 +88,7 @@ struct B2Tsit5 {
             s = b2_fma(TS(a42), KV(k2, i), s);
             s = b2_fma(TS(a43), KV(k3, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
         B2_RHS_TO(k4, tmp, t + TS(c4) * dt);
 #pragma unroll
@@ -89,6 +98,7 @@ struct B2Tsit5 {
             s = b2_fma(TS(a53), KV(k3, i), s);
             s = b2_fma(TS(a54), KV(k4, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
         B2_RHS_TO(k5, tmp, t + TS(c5) * dt);
 #pragma unroll
@@ -99,6 +109,7 @@ struct B2Tsit5 {
             s = b2_fma(TS(a64), KV(k4, i), s);
             s = b2_fma(TS(a65), KV(k5, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
         B2_RHS_TO(k6, tmp, t + dt);
 #pragma unroll
@@ -110,6 +121,7 @@ struct B2Tsit5 {
             s = b2_fma(TS(a75), KV(k5, i), s);
             s = b2_fma(TS(a76), KV(k6, i), s);
             u[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
         B2_RHS_TO(k7, u, t + dt);
         nf += 6;
@@ -124,6 +136,7 @@ struct B2Tsit5 {
                 s = b2_fma(TS(btilde6), KV(k6, i), s);
                 s = b2_fma(TS(btilde7), KV(k7, i), s);
                 ut[i] = dt * s;
+                B2_KBAR;
             }
         }
     }
@@ -147,6 +160,7 @@ struct B2Tsit5 {
             s = b2_fma(b6, KV(k6, i), s);
             s = b2_fma(b7, KV(k7, i), s);
             out[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
     }
     // FSAL: k7 = f(u_new) becomes the next step's k1
@@ -196,6 +210,7 @@ struct B2Vern7 {
             real s = V7(a0301) * KV(k1, i);
             s = b2_fma(V7(a0302), q2[i], s);
             tmp[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
         B2_RHS_TO(k3, tmp, t + V7(c3) * dt);
 #pragma unroll
@@ -203,6 +218,7 @@ struct B2Vern7 {
             real s = V7(a0401) * KV(k1, i);
             s = b2_fma(V7(a0403), KV(k3, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
         B2_RHS_TO(k4, tmp, t + V7(c4) * dt);
 #pragma unroll
@@ -211,6 +227,7 @@ struct B2Vern7 {
             s = b2_fma(V7(a0503), KV(k3, i), s);
             s = b2_fma(V7(a0504), KV(k4, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
         B2_RHS_TO(k5, tmp, t + V7(c5) * dt);
 #pragma unroll
@@ -220,6 +237,7 @@ struct B2Vern7 {
             s = b2_fma(V7(a0604), KV(k4, i), s);
             s = b2_fma(V7(a0605), KV(k5, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
         B2_RHS_TO(k6, tmp, t + V7(c6) * dt);
 #pragma unroll
@@ -230,6 +248,7 @@ struct B2Vern7 {
             s = b2_fma(V7(a0705), KV(k5, i), s);
             s = b2_fma(V7(a0706), KV(k6, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
         B2_RHS_TO(k7, tmp, t + V7(c7) * dt);
 #pragma unroll
@@ -241,6 +260,7 @@ struct B2Vern7 {
             s = b2_fma(V7(a0806), KV(k6, i), s);
             s = b2_fma(V7(a0807), KV(k7, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
         B2_RHS_TO(k8, tmp, t + V7(c8) * dt);
 #pragma unroll
@@ -253,6 +273,7 @@ struct B2Vern7 {
             s = b2_fma(V7(a0907), KV(k7, i), s);
             s = b2_fma(V7(a0908), KV(k8, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
         B2_RHS_TO(k9, tmp, t + dt);
         real q10[B2_N];
@@ -266,6 +287,7 @@ struct B2Vern7 {
                 s = b2_fma(V7(a1006), KV(k6, i), s);
                 s = b2_fma(V7(a1007), KV(k7, i), s);
                 tmp[i] = b2_fma(dt, s, up[i]);
+                B2_KBAR;
             }
             b2_rhs(q10, tmp, p, t + dt);
         }
@@ -279,6 +301,7 @@ struct B2Vern7 {
             s = b2_fma(V7(b8), KV(k8, i), s);
             s = b2_fma(V7(b9), KV(k9, i), s);
             u[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
         if (adaptive) {
 #pragma unroll
@@ -292,6 +315,7 @@ struct B2Vern7 {
                 s = b2_fma(V7(btilde9), KV(k9, i), s);
                 s = b2_fma(V7(btilde10), q10[i], s);
                 ut[i] = dt * s;
+                B2_KBAR;
             }
         }
         nf += adaptive ? 9 : 8;
@@ -318,6 +342,7 @@ struct B2Vern7 {
         s = b2_fma(V7X(a##r##09), KV(k9, i), s);                               \
         s = b2_fma(V7X(a##r##11), KV(k11, i), s);                              \
         KLAST tmp[i] = b2_fma(dt, s, up[i]);                               \
+        B2_KBAR;                                                           \
     }
         V7ROW(12, )
         B2_RHS_TO(k12, tmp, t + V7X(c12) * dt);
@@ -358,6 +383,7 @@ struct B2Vern7 {
             s = b2_fma(b15, KV(k15, i), s);
             s = b2_fma(b16, KV(k16, i), s);
             out[i] = b2_fma(dt, s, up[i]);
+            B2_KBAR;
         }
     }
     __device__ __forceinline__ void advance() {

@@ -169,7 +169,14 @@ def emit_callback(cb, n_state, n_param):
         raise NotImplementedError(
             "ContinuousCallback condition is not symbolically traceable; EnsembleB200 only accepts "
             "callbacks that can be emitted as CUDA C") from e
-    cond_src = ("__device__ __forceinline__ real b2_condition(const real* __restrict__ u, const real* __restrict__ p, "
+    # which components of u the condition reads: the event search builds its interpolation polynomial only for these
+    gs = sp.sympify(g)
+    mask = 0
+    for i, sym in enumerate(integ.u.syms):
+        if gs.has(sym):
+            mask |= 1 << i
+    cond_src = (f"#undef B2_COND_MASK\n#define B2_COND_MASK 0x{mask:x}u\n"
+                "__device__ __forceinline__ real b2_condition(const real* __restrict__ u, const real* __restrict__ p, "
                 "const real t) {\n    (void)u; (void)p; (void)t;\n    return " + _c(g) + ";\n}\n")
     integ2 = _TraceIntegrator(n_state, n_param)
     try:

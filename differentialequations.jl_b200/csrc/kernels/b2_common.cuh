@@ -63,6 +63,9 @@ __device__ __forceinline__ b2f2 b2_blend(bool c0, bool c1, b2f2 a, b2f2 b) { ret
 typedef sreal real;
 #endif
 
+#ifndef B2_COND_MASK
+#define B2_COND_MASK 0xffffffffu   // components of u the ContinuousCallback condition reads (bit i = u[i])
+#endif
 #ifndef B2_HAS_DEVENT
 #define B2_HAS_DEVENT 0
 #endif

@@ -163,6 +163,25 @@ struct B2Tsit5 {
             B2_KBAR;
         }
     }
+    // Coefficient form of the interpolant for ONE component (used by the event search, which evaluates the dense
+    // output many times per step): u_i(t + th*dt) = up_i + dt * th*(C1 + th*(C2 + th*(C3 + th*C4))), C_j = sum_s r_sj k_s[i]
+    static constexpr int DEG = 4;
+    __device__ __forceinline__ void poly_coeffs(int i, real (&c)[DEG]) const {
+        c[0] = TS(r11) * KV(k1, i);
+#define TSC(j)                                          \
+    {                                                   \
+        real s = TS(r1##j) * KV(k1, i);                 \
+        s = b2_fma(TS(r2##j), KV(k2, i), s);            \
+        s = b2_fma(TS(r3##j), KV(k3, i), s);            \
+        s = b2_fma(TS(r4##j), KV(k4, i), s);            \
+        s = b2_fma(TS(r5##j), KV(k5, i), s);            \
+        s = b2_fma(TS(r6##j), KV(k6, i), s);            \
+        s = b2_fma(TS(r7##j), KV(k7, i), s);            \
+        c[j - 1] = s;                                   \
+    }
+        TSC(2) TSC(3) TSC(4)
+#undef TSC
+    }
     // FSAL: k7 = f(u_new) becomes the next step's k1
     __device__ __forceinline__ void advance() {
 #if B2_KSMEM
@@ -385,6 +404,29 @@ struct B2Vern7 {
             out[i] = b2_fma(dt, s, up[i]);
             B2_KBAR;
         }
+    }
+    // coefficient form of the order-6 interpolant for ONE component (event search): C_j = sum_s R_s,j k_s[i]
+    static constexpr int DEG = 6;
+    __device__ __forceinline__ void poly_coeffs(int i, real (&c)[DEG]) const {
+#define V7C(j)                                           \
+    {                                                    \
+        real s = V7(R01_##j) * KV(k1, i);                \
+        s = b2_fma(V7(R04_##j), KV(k4, i), s);           \
+        s = b2_fma(V7(R05_##j), KV(k5, i), s);           \
+        s = b2_fma(V7(R06_##j), KV(k6, i), s);           \
+        s = b2_fma(V7(R07_##j), KV(k7, i), s);           \
+        s = b2_fma(V7(R08_##j), KV(k8, i), s);           \
+        s = b2_fma(V7(R09_##j), KV(k9, i), s);           \
+        s = b2_fma(V7(R11_##j), KV(k11, i), s);          \
+        s = b2_fma(V7(R12_##j), KV(k12, i), s);          \
+        s = b2_fma(V7(R13_##j), KV(k13, i), s);          \
+        s = b2_fma(V7(R14_##j), KV(k14, i), s);          \
+        s = b2_fma(V7(R15_##j), KV(k15, i), s);          \
+        s = b2_fma(V7(R16_##j), KV(k16, i), s);          \
+        c[j - 1] = s;                                    \
+    }
+        V7C(1) V7C(2) V7C(3) V7C(4) V7C(5) V7C(6)
+#undef V7C
     }
     __device__ __forceinline__ void advance() {
 #if B2_KSMEM

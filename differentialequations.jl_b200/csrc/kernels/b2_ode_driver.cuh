@@ -191,28 +191,28 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                             acc = __fmaf_rn(r, r, acc);
                         }
                         const float EE2 = __fmul_rn(acc, inv_n);
-                        if (EE2 != EE2) {
-                            rc = B2_RC_DTNAN;  // upstream: NaN EEst -> NaN dt -> ReturnCode.DtNaN
-                            accepted = false;
-                        } else {
-                            float q, l = lqinit;
-                            if (EE2 == 0.0f) {
-                                q = inv_qmax;
-                            } else {
-                                l = __fmul_rn(0.5f, b2_fastlog2(EE2));
-                                q = b2_fastexp2(__fmaf_rn(-beta2, lq, __fmul_rn(beta1, l)));
-                                q = fmaxf(inv_qmax, fminf(inv_qmin, __fmul_rn(q, inv_gam)));
-                            }
-                            if (!(EE2 <= 1.0f)) {
-                                accepted = false;
-                                nreject++;
-                                const float q11 = b2_fastexp2(__fmul_rn(beta1, l));
-                                dt = dt * (real)__fdiv_rn(1.0f, fminf(inv_qmin, __fmul_rn(q11, inv_gam)));
-                            } else {
-                                lq = fmaxf(l, lqinit);
-                                dtnew = dt * (real)__fdiv_rn(1.0f, q);
-                            }
-                        }
+                        // Branch-free accept/reject: rejections are rare per lane (3 %) but some lane of the warp
+                        // rejects in 37 % of the iterations, so a separate reject path costs every warp ~36 extra
+                        // instructions at 2/32 lane efficiency (profiles/).  Both cases are dt * (1/q) with
+                        //   accept: q = clamp(2^(beta1*l - beta2*lq) / gamma, 1/qmax, 1/qmin)
+                        //   reject: q = min(2^(beta1*l) / gamma, 1/qmin)
+                        // so only the exponent argument and the lower clamp are selected.  Same values as before.
+                        const bool isn = EE2 != EE2;   // upstream: NaN EEst -> NaN dt -> ReturnCode.DtNaN
+                        const bool ok = EE2 <= 1.0f;
+                        const bool zero = EE2 == 0.0f;
+                        const float l = __fmul_rn(0.5f, b2_fastlog2(EE2));
+                        const float bl = __fmul_rn(beta1, l);
+                        float q = b2_fastexp2(ok ? __fmaf_rn(-beta2, lq, bl) : bl);
+                        q = fminf(inv_qmin, __fmul_rn(q, inv_gam));
+                        q = ok ? fmaxf(inv_qmax, q) : q;
+                        q = zero ? inv_qmax : q;
+                        const real dtq = dt * (real)__fdiv_rn(1.0f, q);
+                        accepted = ok;
+                        if (isn) rc = B2_RC_DTNAN;
+                        nreject += (!ok && !isn) ? 1 : 0;
+                        lq = ok ? fmaxf(zero ? lqinit : l, lqinit) : lq;
+                        dtnew = ok ? dtq : dtnew;
+                        dt = (!ok && !isn) ? dtq : dt;
                     } else {
                         bool bad = false;
 #pragma unroll
@@ -234,9 +234,37 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                         real w[B2_N];
                         real gprev, lo = 0, hi = 0, glo, ghi = 0;
                         alg.prepare_dense(u, p, tprev, dts, nf);
+                        // The event search evaluates the dense output 10-25 times per step.  For the ERK steppers it
+                        // uses the coefficient form of the interpolant, built once per step and only for the
+                        // components the condition reads (B2_COND_MASK, from the symbolic condition): Horner in theta
+                        // instead of re-weighting all stage vectors at every probe.
+                        constexpr int PD = Alg::DEG > 0 ? Alg::DEG : 1;
+                        real cc[B2_N][PD];
+                        if (Alg::DEG > 0) {
+#pragma unroll
+                            for (int i = 0; i < B2_N; i++)
+                                if ((B2_COND_MASK >> i) & 1u) alg.poly_coeffs(i, cc[i]);
+                        }
+                        auto cond_at = [&](real th) -> real {
+                            if (Alg::DEG > 0) {
+#pragma unroll
+                                for (int i = 0; i < B2_N; i++) {
+                                    if ((B2_COND_MASK >> i) & 1u) {
+                                        real pv = cc[i][PD - 1];
+#pragma unroll
+                                        for (int j = PD - 2; j >= 0; j--) pv = b2_fma(th, pv, cc[i][j]);
+                                        w[i] = b2_fma(dts, th * pv, u[i]);
+                                    } else {
+                                        w[i] = u[i];  // not read by the condition
+                                    }
+                                }
+                            } else {
+                                alg.interp(u, un, th, dts, w);
+                            }
+                            return b2_condition(w, p, b2_fma(th, dts, tprev));
+                        };
                         if (just_fired) {
-                            alg.interp(u, un, (real)0.01, dts, w);
-                            gprev = b2_condition(w, p, b2_fma((real)0.01, dts, tprev));
+                            gprev = cond_at((real)0.01);
                             lo = (real)0.01;
                         } else {
                             gprev = b2_condition(u, p, tprev);
@@ -244,13 +272,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                         glo = gprev;
                         for (int mm = 1; mm <= ip && !fired; mm++) {
                             const real th = (mm == ip) ? (real)1 : (real)mm / (real)ip;
-                            real g;
-                            if (mm == ip) {
-                                g = b2_condition(un, p, tnew);
-                            } else {
-                                alg.interp(u, un, th, dts, w);
-                                g = b2_condition(w, p, b2_fma(th, dts, tprev));
-                            }
+                            const real g = (mm == ip) ? b2_condition(un, p, tnew) : cond_at(th);
                             if ((gprev < 0 && g >= 0) || (gprev > 0 && g <= 0)) {
                                 fired = true;
                                 hi = th;
@@ -283,8 +305,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                                 real x = (b2_abs(xt - xh) <= r) ? xt : xh - sg * r;
                                 if (!(x > lo && x < hi)) x = xh;
                                 if (!(x > lo && x < hi)) break;
-                                alg.interp(u, un, x, dts, w);
-                                const real g = b2_condition(w, p, b2_fma(x, dts, tprev));
+                                const real g = cond_at(x);
                                 if ((gprev < 0 && g >= 0) || (gprev > 0 && g <= 0)) {
                                     hi = x;
                                     ghi = g;

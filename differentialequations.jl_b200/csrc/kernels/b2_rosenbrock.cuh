@@ -81,6 +81,8 @@ struct B2LU {
 struct B2Ros23 {
     static constexpr int ORDER = 2;
     __device__ __forceinline__ void bind(real*) {}
+    static constexpr int DEG = 0;  // no coefficient form: the event search uses interp() directly
+    __device__ __forceinline__ void poly_coeffs(int, real (&)[1]) const {}
     real f0[B2_N], k1[B2_N], k2[B2_N], f2[B2_N];
 
     __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {
@@ -202,6 +204,8 @@ __constant__ real B2_RODAS_d[6] = {RT(d1), RT(d2), RT(d3), RT(d4), 0, 0};
 struct B2Rodas {
     static constexpr int ORDER = (B2_RODAS_S == 8) ? 5 : 4;
     __device__ __forceinline__ void bind(real*) {}
+    static constexpr int DEG = 0;  // no coefficient form: the event search uses interp() directly
+    __device__ __forceinline__ void poly_coeffs(int, real (&)[1]) const {}
     real f0[B2_N], fnew[B2_N];
 
     __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {

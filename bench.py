@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--sweep", default="random", choices=["random", "ordered"])
     ap.add_argument("--refill", type=int, default=0)
     ap.add_argument("--stage", type=int, default=-1)
+    ap.add_argument("--work-order", type=int, default=-1, help="-1 auto, 0 caller's order, 1 expected-work order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -217,7 +218,7 @@ def main():
     model = b200ens.build_model(W.lorenz_problem(npdt, TSPAN), b200ens.Tsit5())
     o = _lib.default_opts()
     o.adaptive, o.t0, o.t1, o.dt, o.abstol, o.reltol = 1, TSPAN[0], TSPAN[1], DT0, ABSTOL, RELTOL
-    o.refill_threshold, o.stage_outputs = a.refill, a.stage
+    o.refill_threshold, o.stage_outputs, o.work_order = a.refill, a.stage, a.work_order
     o.device_mask = 1 << dev
     o.traj_offset = rank * N
 
@@ -240,6 +241,10 @@ def main():
     for _ in range(a.warmup):
         step_device()
     torch.cuda.synchronize()
+    # kernels per device-resident step: 1 ensemble kernel (+ 2 of the expected-work ordering pre-pass when it is on)
+    launches_per_step = int(model.solve_device(o, dev, stream.cuda_stream, N, d_u0.data_ptr(), d_p.data_ptr(),
+                                               d_save.data_ptr(), n_save, d_out.data_ptr(), d_rc.data_ptr(),
+                                               d_st.data_ptr(), timed=True).launches)
     peak_tf = fma_peak(dev, f64)  # measured FMA roofline denominator (also warms the clocks)
     if world > 1:
         dist.barrier()
@@ -331,12 +336,13 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": workload_name(a), "trajectories_per_gpu": N, "l2": "flushed between timed steps (256 MiB memset)",
                        "parallelism": f"trajectory ranges sharded over {world} GPU(s), no collective",
-                       "refill_threshold": a.refill, "stage_outputs": a.stage, "all_success": ok, "numa": numa,
+                       "refill_threshold": a.refill, "stage_outputs": a.stage, "work_order": a.work_order,
+                       "kernels_per_step": launches_per_step, "all_success": ok, "numa": numa,
                        "regs": model.info()["regs"]},
             "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "trajectories/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / a.steps * 1e3, "matches_device_leg": same},
-            "gpu_launches": a.steps + e2e_launches, "clocks": clocks,
+            "gpu_launches": a.steps * launches_per_step + e2e_launches, "clocks": clocks,
             "trajectory_steps_per_s": world * attempted / (ms_per_step * 1e-3),
         }
         print(json.dumps(line), flush=True)

@@ -44,6 +44,7 @@ class Opts(C.Structure):
         ("noise_injected", C.c_int32), ("event_terminate", C.c_int32), ("interp_points", C.c_int32),
         ("save_tstops", C.c_int32), ("device_mask", C.c_uint32), ("refill_threshold", C.c_int32),
         ("block_threads", C.c_int32), ("stage_outputs", C.c_int32),
+        ("work_order", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -63,7 +64,7 @@ class Timing(C.Structure):
 
 
 EXPORTS = [
-    "b200ens_abi_version", "b200ens_device_count", "b200ens_last_error", "b200ens_opts_init", "b200ens_compile",
+    "b200ens_abi_version", "b200ens_device_count", "b200ens_last_error", "b200ens_nvrtc_info", "b200ens_opts_init", "b200ens_compile",
     "b200ens_free", "b200ens_model_info", "b200ens_solve", "b200ens_solve_device", "b200ens_solve_moments",
     "b200ens_host_alloc", "b200ens_host_free",
 ]
@@ -82,6 +83,7 @@ def lib():
             "(python __graft_entry__.py build).  The B200 ensemble path has no fallback.")
     L = C.CDLL(LIB_PATH)
     L.b200ens_abi_version.restype = C.c_int
+    L.b200ens_nvrtc_info.restype = C.c_char_p
     L.b200ens_device_count.restype = C.c_int
     L.b200ens_last_error.restype = C.c_char_p
     L.b200ens_opts_init.argtypes = [C.POINTER(Opts)]
@@ -109,7 +111,7 @@ def lib():
     L.b200ens_host_alloc.restype = C.c_void_p
     L.b200ens_host_free.argtypes = [C.c_void_p]
     L.b200ens_host_free.restype = None
-    if L.b200ens_abi_version() != 1:
+    if L.b200ens_abi_version() != 2:
         raise ImportError("libb200ens ABI version mismatch")
     _lib = L
     return L

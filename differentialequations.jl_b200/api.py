@@ -188,13 +188,15 @@ class EnsembleB200:
     """The ensemble algorithm: sibling of EnsembleThreads / EnsembleGPUKernel.
 
     devices: iterable of CUDA device ids (None = all visible); refill_threshold: idle lanes of a
-    warp before it fetches new trajectories (0 = auto); stage_outputs: -1 auto / 0 / 1."""
+    warp before it fetches new trajectories (0 = auto); stage_outputs: -1 auto / 0 / 1; work_order: -1 auto / 0
+    caller's order / 1 integrate in descending expected-work order (scheduling only, identical results)."""
 
     def __init__(self, devices=None, refill_threshold=0, stage_outputs=-1, fast_math=False, packed_x2=False,
-                 stage_vectors_in_smem=False):
+                 stage_vectors_in_smem=False, work_order=-1):
         self.devices = devices
         self.refill_threshold = refill_threshold
         self.stage_outputs = stage_outputs
+        self.work_order = work_order
         self.fast_math = fast_math
         self.packed_x2 = packed_x2   # Float32 Tsit5: two trajectories per thread in packed FP32 (FFMA2)
         self.stage_vectors_in_smem = stage_vectors_in_smem   # ERK k-vectors in shared memory (large n_state)
@@ -428,6 +430,7 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, 
         o.device_mask = mask
     o.refill_threshold = int(ensemblealg.refill_threshold)
     o.stage_outputs = int(ensemblealg.stage_outputs)
+    o.work_order = int(ensemblealg.work_order)
 
     if summary:  # EnsembleAnalysis.timestep_meanvar on the device: returns an EnsembleSummary
         t_solve = time.perf_counter()

@@ -108,6 +108,8 @@ struct B2Args {
     int noise_injected, event_terminate, interp_points, save_tstops;
     // the same scalars pre-converted to float by the host (f32 kernels read these: no F2F in the loop)
     float f_t0, f_t1, f_dt, f_abstol, f_reltol, f_dtmin, f_dtmax, f_qmin, f_qmax, f_gamma, f_beta1, f_beta2, f_qoldinit;
+    int pad0_;
+    const unsigned* perm;  // queue position -> trajectory index (expected-work order, b2_work.cuh) or null = identity
 };
 
 #if B2_F64

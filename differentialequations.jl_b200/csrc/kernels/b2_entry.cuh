@@ -19,13 +19,17 @@
 #error "unknown B2_ALG"
 #endif
 
+#if !(B2_ALG == 6 || B2_ALG == 7) && !B2_X2
+#include "b2_work.cuh"   // expected-work ordering of the trajectory queue (adaptive ODE steppers)
+#endif
+
 #if (B2_ALG == 1 || B2_ALG == 2) && !B2_X2
 // the common explicit case (adaptive, saveat interpolated, caller-supplied dt) folded at compile time
 extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble_kernel_adaptive(const __grid_constant__ B2Args a) {
 #if B2_ALG == 1
-    b2_ode_driver<B2Tsit5, 1, 0, 0>(a);
+    b2_ode_driver<B2Tsit5, 1, 0, 0, 0>(a);
 #else
-    b2_ode_driver<B2Vern7, 1, 0, 0>(a);
+    b2_ode_driver<B2Vern7, 1, 0, 0, 0>(a);
 #endif
 }
 #endif

@@ -17,12 +17,13 @@
 // ADAPT / TSTOPS: 0 or 1 = compile-time specialisation of the two solve options that sit in the per-iteration
 // control path, -1 = read them from the argument block.  AUTODT = 0 compiles the automatic-initial-step block out
 // (the specialised entry is only launched with a caller-supplied dt; keeps its register pressure down).
-template <class Alg, int ADAPT = -1, int TSTOPS = -1, int AUTODT = 1>
+template <class Alg, int ADAPT = -1, int TSTOPS = -1, int AUTODT = 1, int STAGED = -1>
 __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     extern __shared__ __align__(16) unsigned char b2_smem[];
     const unsigned lane = threadIdx.x & 31u;
     const int warp_in_block = threadIdx.x >> 5;
-    const int stride = a.stage_stride;
+    // STAGED = 0: output staging compiled out (direct global stores, the default and the faster mode, profiles/)
+    const int stride = STAGED == 0 ? 0 : a.stage_stride;
     real* const warp_stage = reinterpret_cast<real*>(b2_smem) + (size_t)warp_in_block * 32 * stride;
     real* const gout = reinterpret_cast<real*>(a.out_u);
     const real* const gu0 = reinterpret_cast<const real*>(a.u0);
@@ -55,6 +56,8 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     float lq = lqinit;
     long long idx = -1, iter = 0;
     int si = 0, naccept = 0, nreject = 0, nf = 0, nevents = 0;
+    // next save time of this lane (cached: the saveat check runs twice per iteration); +inf when none is left
+    real tau_next = (real)__int_as_float(0x7f800000);
     bool active = false, dirty = false, exhausted = false;
 #if B2_HAS_EVENT
     bool just_fired = false;
@@ -79,7 +82,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                 if (!exhausted) {
                     const long long my = b2_fetch(idle, a.work_counter, a.N, lane, exhausted);
                     if (!active && my >= 0) {
-                        idx = my;
+                        idx = a.perm ? (long long)__ldg(a.perm + my) : my;
                         sink.base = idx * (long long)out_per_traj;
 #pragma unroll
                         for (int i = 0; i < B2_N; i++) u[i] = gu0[idx * B2_N + i];
@@ -96,6 +99,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                             sink.put(si, u);
                             si++;
                         }
+                        tau_next = si < n_save ? __ldg(gsave + si) : (real)__int_as_float(0x7f800000);
                         alg.start(u, p, t);
                         nf = 1;
                         if (AUTODT && adaptive && !(dt_user > (real)0)) {
@@ -154,10 +158,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
         if (active) {
             iter++;
             if (!adaptive) dt = dt_user;
-            if (save_tstops && si < n_save) {
-                const real s = __ldg(gsave + si);
-                if (s < t1) tstop = s;
-            }
+            if (save_tstops && tau_next < t1) tstop = tau_next;
             const bool clipped = dt > tstop - t;
             if (clipped) dt = tstop - t;
             const bool toosmall = dt <= b2_max(dtmin, (real)B2_EPS * b2_abs(t));
@@ -330,12 +331,8 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
         // Instead the whole warp evaluates the interpolant whenever ANY lane needs a save, each
         // lane with its own theta, and only the lanes that need it store.
         for (;;) {
-            real tau = 0;
-            bool need = false;
-            if (accepted && si < n_save) {
-                tau = __ldg(gsave + si);
-                need = tau <= tnew;
-            }
+            const real tau = tau_next;
+            const bool need = accepted && tau <= tnew;
             if (!__any_sync(B2_FULL, need)) break;
             const bool at_end = tau == tnew && !fired;  // the step lands exactly on the save point: store u_new
             if (need && !at_end) alg.prepare_dense(u, p, tprev, dts, nf);
@@ -345,6 +342,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                 if (at_end) sink.put(si, un);
                 else sink.put(si, w);
                 si++;
+                tau_next = si < n_save ? __ldg(gsave + si) : (real)__int_as_float(0x7f800000);
             }
         }
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200ENS_ABI_VERSION 1
+#define B200ENS_ABI_VERSION 2
 
 /* scalar type of u, p, t (Julia eltype(u0)) */
 enum b200ens_dtype { B200ENS_F32 = 0, B200ENS_F64 = 1 };
@@ -109,6 +109,10 @@ typedef struct b200ens_opts {
     int32_t refill_threshold; /* lanes of a warp that must be idle before it fetches new trajectories; <=0 auto */
     int32_t block_threads;  /* <=0 auto */
     int32_t stage_outputs;  /* -1 auto, 0 direct global stores, 1 stage saveat outputs in shared memory */
+    int32_t work_order;     /* -1 auto (on for adaptive ODE solves of >= 32768 trajectories per device chunk), 0 caller's
+                               order, 1 integrate trajectories in descending expected-work order (device-side counting
+                               sort on the initial-step proxy; scheduling only, results are bit-identical) */
+    int32_t reserved0;
 } b200ens_opts;
 
 typedef struct b200ens_stats {
@@ -128,6 +132,10 @@ int b200ens_abi_version(void);
 int b200ens_device_count(void);
 /* thread-local description of the last error */
 const char* b200ens_last_error(void);
+
+/* "<major>.<minor> <path>" of the NVRTC the library JIT-compiles with (dlopen'ed explicitly: $B200ENS_NVRTC, then the
+ * CUDA toolkit's libnvrtc.so.12, then the default loader path); "" when none could be loaded. */
+const char* b200ens_nvrtc_info(void);
 
 /* Fill o with defaults (everything "auto"). */
 void b200ens_opts_init(b200ens_opts* o);

@@ -1,0 +1,73 @@
+"""GPU: the expected-work ordering of the trajectory queue (kernels/b2_work.cuh, b200ens_opts.work_order) is a
+SCHEDULING decision only: saved values, retcodes and step statistics are bit-identical with the caller's order,
+for every adaptive stepper family, and the oracle parity of the ordered run holds like the unordered one's."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SAVEAT = np.arange(0.0, 10.5, 1.0)
+
+
+def _lorenz(B, dtype, N, order, alg=None):
+    from b200ens import workloads as W
+
+    u0, p = W.lorenz_params(N, "random", seed=3, dtype=dtype)
+    eprob = B.EnsembleProblem(W.lorenz_problem(dtype), u0s=u0, ps=p)
+    sol = B.solve(eprob, alg or B.Tsit5(), B.EnsembleB200(work_order=order), trajectories=N, saveat=SAVEAT, dt=0.1,
+                  abstol=1e-6, reltol=1e-3)
+    return u0, p, sol
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("N", [1, 33, 4097, 70001])
+def test_tsit5_bit_identical_with_and_without_ordering(B, gpu_lib, dtype, N):
+    _, _, a = _lorenz(B, dtype, N, 0)
+    _, _, b = _lorenz(B, dtype, N, 1)
+    assert np.array_equal(a.retcodes, b.retcodes) and np.all(a.retcodes == 1)
+    assert np.array_equal(a.stats, b.stats)
+    assert np.array_equal(a.u_array, b.u_array)
+
+
+def test_ordered_run_matches_oracle(B, gpu_lib, oracle):
+    N = 40000   # above the auto threshold (32768): the default path of large ensembles
+    u0, p, sol = _lorenz(B, np.float64, N, -1)
+    ref, rc, st = oracle.solve("lorenz", "Tsit5", u0, p, (0.0, 10.0), SAVEAT, 0.1, abstol=1e-6, reltol=1e-3)
+    assert np.array_equal(sol.retcodes, rc)
+    assert np.array_equal(sol.stats[:, :2], st[:, :2])
+    err = np.abs(sol.u_array - ref)
+    assert np.all(err <= 1e-6 + 1e-3 * np.abs(ref))
+
+
+def test_vern7_and_rosenbrock_families(B, gpu_lib):
+    from b200ens import workloads as W
+
+    _, _, a = _lorenz(B, np.float64, 5000, 0, B.Vern7())
+    _, _, b = _lorenz(B, np.float64, 5000, 1, B.Vern7())
+    assert np.array_equal(a.u_array, b.u_array) and np.array_equal(a.stats, b.stats)
+    N = 3000
+    u0, p = W.robertson_params(N)
+    sols = []
+    for order in (0, 1):
+        eprob = B.EnsembleProblem(W.robertson_problem(), u0s=u0, ps=p)
+        sols.append(B.solve(eprob, B.Rodas5P(), B.EnsembleB200(work_order=order), trajectories=N,
+                            saveat=W.ROBERTSON_SAVEAT, dt=1e-6, abstol=1e-8, reltol=1e-6))
+    assert np.all(sols[0].retcodes == 1)
+    assert np.array_equal(sols[0].u_array, sols[1].u_array) and np.array_equal(sols[0].stats, sols[1].stats)
+
+
+def test_nan_and_failing_trajectories_keep_their_slots(B, gpu_lib):
+    """Trajectories whose proxy is NaN/inf sort first; their outputs must still land at their own index."""
+    from b200ens import workloads as W
+
+    N = 2048
+    u0, p = W.lorenz_params(N, "random", seed=5, dtype=np.float64)
+    u0[7, 0] = np.nan
+    p[100, 1] = np.inf
+    outs = []
+    for order in (0, 1):
+        eprob = B.EnsembleProblem(W.lorenz_problem(np.float64), u0s=u0, ps=p)
+        outs.append(B.solve(eprob, B.Tsit5(), B.EnsembleB200(work_order=order), trajectories=N, saveat=SAVEAT, dt=0.1))
+    assert np.array_equal(outs[0].retcodes, outs[1].retcodes)
+    assert outs[1].retcodes[7] != 1 and outs[1].retcodes[100] != 1
+    assert np.array_equal(outs[0].u_array, outs[1].u_array, equal_nan=True)

@@ -155,7 +155,9 @@ NvrtcApi* nvrtc_api() {
         cand.push_back("libnvrtc.so.12");
         cand.push_back("libnvrtc.so");
         for (const auto& c : cand) {
-            void* h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+            // DEEPBIND: the library must resolve its own internal symbols, not those of another NVRTC already in the
+            // global scope (torch preloads its bundled 12.8 with RTLD_GLOBAL)
+            void* h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL | RTLD_DEEPBIND);
             if (!h) continue;
             NvrtcApi a;
             a.handle = h;
@@ -191,28 +193,92 @@ NvrtcApi* nvrtc_api() {
 std::mutex g_cache_mu;
 std::map<std::string, std::shared_ptr<std::pair<std::vector<char>, std::string>>> g_cache;
 
+// Registers / stack frame / spills of the ensemble entry points (max over the generic and the specialised entry; the
+// work-ordering helper kernels of the same module are ignored).  Authoritative source: the cubin itself (.nv.info
+// EIATTR_REGCOUNT / EIATTR_FRAME_SIZE).  The ptxas -v log only refines the spill figure: NVRTC 12.9 answers repeated
+// compilations of the same source from an on-disk cache with an EMPTY log (measured: every process after the first),
+// so nothing here may depend on the log being present.
+bool cubin_resources(const std::vector<char>& cubin, int* regs, int* frame) {
+    const unsigned char* d = (const unsigned char*)cubin.data();
+    const size_t n = cubin.size();
+    if (n < 0x40 || memcmp(d, "\177ELF", 4) != 0 || d[4] != 2) return false;
+    auto rd = [&](size_t off, int bytes) -> unsigned long long {
+        unsigned long long v = 0;
+        if (off + bytes > n) return 0;
+        memcpy(&v, d + off, bytes);
+        return v;
+    };
+    const size_t shoff = rd(0x28, 8);
+    const int shentsize = (int)rd(0x3A, 2), shnum = (int)rd(0x3C, 2), shstrndx = (int)rd(0x3E, 2);
+    if (!shoff || shentsize < 64 || shstrndx >= shnum) return false;
+    auto sh = [&](int i, int field_off, int bytes) { return rd(shoff + (size_t)i * shentsize + field_off, bytes); };
+    const size_t shstr = sh(shstrndx, 0x18, 8);
+    int i_info = -1, i_sym = -1;
+    for (int i = 0; i < shnum; i++) {
+        const char* nm = (const char*)d + shstr + sh(i, 0, 4);
+        if ((size_t)(nm - (const char*)d) >= n) continue;
+        if (!strcmp(nm, ".nv.info")) i_info = i;
+        if (sh(i, 4, 4) == 2) i_sym = i;   // SHT_SYMTAB
+    }
+    if (i_info < 0 || i_sym < 0) return false;
+    const size_t symoff = sh(i_sym, 0x18, 8), stroff = sh((int)sh(i_sym, 0x28, 4), 0x18, 8);
+    auto is_ens = [&](unsigned symidx) {
+        const size_t name_off = stroff + rd(symoff + (size_t)symidx * 24, 4);
+        return name_off < n && !strncmp((const char*)d + name_off, "b2_ensemble_kernel", strlen("b2_ensemble_kernel"));
+    };
+    size_t p = sh(i_info, 0x18, 8);
+    const size_t end = p + sh(i_info, 0x20, 8);
+    int r = -1, f = 0;
+    while (p + 4 <= end && end <= n) {
+        const int fmt = d[p], attr = d[p + 1], size = (int)rd(p + 2, 2);
+        p += 4;
+        if (fmt != 4) continue;   // NVAL/BVAL/HVAL carry their value in the size field
+        if (size >= 8 && (attr == 0x2f || attr == 0x11) && is_ens((unsigned)rd(p, 4))) {
+            const int v = (int)rd(p + 4, 4);
+            if (attr == 0x2f) r = std::max(r, v);   // EIATTR_REGCOUNT
+            else f = std::max(f, v);                // EIATTR_FRAME_SIZE
+        }
+        p += size;
+    }
+    *regs = r;
+    *frame = f;
+    return r >= 0;
+}
+
 void parse_ptxas_log(b200ens_model* m) {
+    m->regs = -1;
+    m->smem = m->lmem = 0;
+    m->spill = -1;
+    if (getenv("B200ENS_IGNORE_PTXAS_LOG")) m->log.clear();   // tests: behave as if NVRTC served the compile from its cache
     const char* s = m->log.c_str();
-    const char* q;
-    if ((q = strstr(s, "Used ")) != nullptr) m->regs = atoi(q + 5);
-    m->smem = 0;
-    if ((q = strstr(s, " bytes smem")) != nullptr) {
+    const char* pos = s;
+    auto num_before = [&](const char* blk, const char* end, const char* tag) {
+        const char* q = strstr(blk, tag);
+        if (!q || q >= end) return -1;
         const char* b = q;
-        while (b > s && (isdigit((unsigned char)b[-1]))) b--;
-        m->smem = atoi(b);
+        while (b > blk && isdigit((unsigned char)b[-1])) b--;
+        return atoi(b);
+    };
+    while ((pos = strstr(pos, "Compiling entry function '")) != nullptr) {
+        const char* name = pos + strlen("Compiling entry function '");
+        const char* next = strstr(name, "Compiling entry function '");
+        const char* end = next ? next : s + m->log.size();
+        if (!strncmp(name, "b2_ensemble_kernel", strlen("b2_ensemble_kernel"))) {
+            const char* q = strstr(name, "Used ");
+            if (q && q < end) m->regs = std::max(m->regs, atoi(q + 5));
+            m->smem = std::max(m->smem, num_before(name, end, " bytes smem"));
+            m->lmem = std::max(m->lmem, num_before(name, end, " bytes stack frame"));
+            m->spill = std::max(m->spill, num_before(name, end, " bytes spill stores"));
+        }
+        pos = name;
     }
-    m->lmem = 0;
-    if ((q = strstr(s, " bytes stack frame")) != nullptr) {
-        const char* b = q;
-        while (b > s && (isdigit((unsigned char)b[-1]))) b--;
-        m->lmem = atoi(b);
+    int regs = -1, frame = 0;
+    if (cubin_resources(m->cubin, &regs, &frame)) {
+        m->regs = regs;
+        m->lmem = frame;
     }
-    m->spill = 0;
-    if ((q = strstr(s, " bytes spill stores")) != nullptr) {
-        const char* b = q;
-        while (b > s && (isdigit((unsigned char)b[-1]))) b--;
-        m->spill = atoi(b);
-    }
+    // no log (compile served from NVRTC's cache): a stack frame of F bytes corresponds to ~2F bytes of spill stores
+    if (m->spill < 0) m->spill = 2 * m->lmem;
 }
 
 std::string build_source(const b200ens_model_desc* d, int min_blocks, int block, int ksmem, int x2 = 0) {

@@ -109,3 +109,25 @@ def test_automatic_initial_dt_in_the_oracle(oracle):
     assert rc[0] == 1 and abs(out[0, 0, 0] - 0.5 * np.exp(1.01)) < 1e-8
     out2, rc2, st2 = oracle.solve("linear", "Tsit5", g[0], g[1], (0.0, 1.0), [1.0], 0.05, abstol=1e-8, reltol=1e-8)
     assert abs(int(st[0, 0]) - int(st2[0, 0])) <= 3 and st[0, 2] == st[0, 0] * 6 + st[0, 1] * 6 + 2
+
+
+def test_kernel_resources_do_not_depend_on_the_ptxas_log():
+    """NVRTC 12.9 serves repeated compilations from an on-disk cache with an EMPTY log (measured on the GPU box: every
+    process after the first): registers / stack frame and the occupancy + shared-memory-stage decisions must come out
+    the same from the cubin alone (csrc/b200ens.cpp cubin_resources)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, json, numpy as np; sys.path.insert(0, %r); import b200ens as B; from b200ens import workloads as W\n"
+        "r = [B.build_model(W.lorenz_problem(np.float32), B.Tsit5()).info(), B.build_model(W.lorenz_problem(np.float64), B.Tsit5()).info(),\n"
+        "     B.build_model(W.robertson_problem(), B.Rodas5P()).info()]\n"
+        "print(json.dumps(r))\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for extra in ({}, {"B200ENS_IGNORE_PTXAS_LOG": "1"}):
+        env = dict(os.environ, **extra)
+        outs.append(json.loads(subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().splitlines()[-1]))
+    assert outs[0] == outs[1]
+    assert all(o["regs"] > 0 and o["lmem"] == 0 for o in outs[0])

@@ -15,6 +15,8 @@ tdt = torch.float32 if dt == "f32" else torch.float64
 SAVEAT = np.arange(0.0, 10.5, 1.0)
 u0, p = W.lorenz_params(N, sweep, 0, npdt)
 model = b200ens.build_model(W.lorenz_problem(npdt), b200ens.Tsit5())
+if os.environ.get('SWEEP_DIAG'):
+    print('DIAG', _lib.lib().b200ens_nvrtc_info(), model.info(), repr(str(model.log)[:300]), flush=True)
 d_u0, d_p = torch.from_numpy(u0).cuda(), torch.from_numpy(p).cuda()
 d_save = torch.from_numpy(SAVEAT.astype(npdt)).cuda()
 d_out = torch.empty((N, 11, 3), dtype=tdt, device="cuda")

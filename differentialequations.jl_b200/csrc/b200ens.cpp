@@ -388,6 +388,7 @@ constexpr int kMaxSlots = 4;
 struct DeviceCtx {
     int dev = -1;
     int sms = 0;
+    size_t mem_total = 0;
     std::mutex mu;  // one host-buffer solve at a time per device
     Slot slot[kMaxSlots];
     void* saveat = nullptr;
@@ -411,6 +412,10 @@ int device_ctx(int dev, DeviceCtx** out) {
         CU(cudaSetDevice(dev));
         d.dev = dev;
         CU(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+        {
+            size_t fr = 0;
+            CU(cudaMemGetInfo(&fr, &d.mem_total));
+        }
         {   // keep stream-ordered scratch (work ordering in b200ens_solve_device) cached in the default pool
             cudaMemPool_t pool;
             if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
@@ -705,6 +710,17 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
     rc = grow(&d->saveat, &d->cap_save, std::max<size_t>(es, (size_t)n_save * es));
     if (rc) return rc;
     const auto wall0 = std::chrono::steady_clock::now();
+    // B200ENS_TRACE=1: host-side timeline of the pipeline (ms since entry) on stderr -- where the wall time of an
+    // end-to-end solve goes beyond the PCIe floor
+    static const bool trace = getenv("B200ENS_TRACE") != nullptr;
+    std::string trace_txt;
+    auto mark = [&](const char* what, long long v = -1) {
+        if (!trace) return;
+        char b[96];
+        snprintf(b, sizeof b, " %s%s%s@%.3f", what, v >= 0 ? ":" : "", v >= 0 ? std::to_string(v).c_str() : "",
+                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+        trace_txt += b;
+    };
     if (n_save) CU(cudaMemcpyAsync(d->saveat, saveat, (size_t)n_save * es, cudaMemcpyHostToDevice, d->slot[0].stream));
     CU(cudaStreamSynchronize(d->slot[0].stream));
 
@@ -712,15 +728,45 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
     const long long total = hi - lo;
     const size_t per_traj = (size_t)n * es + (size_t)np * es + out_per_traj + noise_per_traj + 4 + sizeof(b200ens_stats);
     size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    // four pipeline slots (stream + buffers each), chunk = a quarter of the shard clamped to [128k, 1M] trajectories:
-    // everything is enqueued without host synchronisation, the D2H engine never idles after the first chunk
-    // (profiles/r1_e2e_probe.log: 3.6 ms vs 4.3 ms with two half-shard chunks for 1M Float32 trajectories).  Smaller
-    // launches lose to the drain tail of the persistent kernel.
-    long long chunk = std::min<long long>(total, std::max<long long>(1 << 17, std::min<long long>(1 << 20, (total + 3) / 4)));
+    mark("saveat");
+    // cudaMemGetInfo costs ~0.09 ms (a tenth of the kernel time of 1M Lorenz trajectories): only ask when four slots of
+    // the largest chunk could come anywhere near the device memory (total size cached at device init)
+    if (4 * per_traj * (size_t)std::min<long long>(total, 1 << 20) > d->mem_total / 8) {
+        CU(cudaMemGetInfo(&free_b, &total_b));
+    } else {
+        free_b = total_b = d->mem_total;
+    }
+    mark("meminfo");
+    // Four pipeline slots (stream + buffers each); everything is enqueued without host synchronisation.  The run is
+    // D2H-bound (1M Float32 Lorenz trajectories: 152 MB back = 2.7 ms of PCIe against 1.0 ms of kernel), so the
+    // schedule starts SMALL and grows: 1/16 of the shard first (the D2H engine has work after ~0.3 ms instead of
+    // ~0.6 ms with equal quarters), then 3/16, then the rest in equal large chunks (large copies reach 53-56 GB/s;
+    // per-chunk host overhead is ~30 us of API calls; B200ENS_TRACE=1 prints the timeline).
+    long long chunk = std::min<long long>(total, 1 << 20);
     const long long mem_cap = (long long)((free_b / 8) / std::max<size_t>(1, per_traj));
     chunk = std::max<long long>(1, std::min(chunk, mem_cap));
-    if (const char* e = getenv("B200ENS_CHUNK")) chunk = std::max<long long>(1, atoll(e));
+    std::vector<long long> sched;
+    if (const char* e = getenv("B200ENS_CHUNK")) {   // fixed size (tests, experiments)
+        chunk = std::max<long long>(1, atoll(e));
+        for (long long r = total; r > 0; r -= chunk) sched.push_back(std::min(chunk, r));
+    } else {
+        const long long first = std::min<long long>(chunk, std::max<long long>(1 << 15, (total + 15) / 16));
+        long long r = total;
+        if (r > 4 * first) {
+            sched.push_back(first);
+            r -= first;
+            const long long second = std::min<long long>(chunk, 3 * first);
+            sched.push_back(second);
+            r -= second;
+        }
+        const long long k = std::max<long long>(r > 2 * first ? 2 : 1, (r + chunk - 1) / chunk);
+        for (long long i = 0; i < k; i++) {
+            const long long c = (r + (k - i) - 1) / (k - i);
+            sched.push_back(c);
+            r -= c;
+        }
+        chunk = *std::max_element(sched.begin(), sched.end());
+    }
 
     LaunchPlan lp;
     rc = plan_launch(m, o, d, chunk, n_save, &lp);
@@ -771,7 +817,7 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
         return 0;
     };
     while (done < total) {
-        const long long cn = std::min(chunk, total - done);
+        const long long cn = std::min<long long>(sched[std::min<size_t>(it, sched.size() - 1)], total - done);
         const long long g0 = lo + done;  // global index of the chunk's first trajectory
         Slot& s = d->slot[it % nslots];
         if (pend[it % nslots].used) {
@@ -859,6 +905,7 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
             if (stats) CU(cudaMemcpyAsync(dst_st, s.stats, (size_t)cn * sizeof(b200ens_stats), cudaMemcpyDeviceToHost, s.stream));
         }
         CU(cudaEventRecord(s.ev[3], s.stream));
+        mark("enq", cn);
         pend[it % nslots].used = true;
         pend[it % nslots].g0 = g0;
         pend[it % nslots].cn = cn;
@@ -866,8 +913,11 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
         done += cn;
         it++;
     }
-    for (int k = 0; k < kMaxSlots; k++)
+    for (int k = 0; k < kMaxSlots; k++) {
         if (pend[k].used && (rc = collect(d->slot[k], pend[k]))) return rc;
+        mark("collect", k);
+    }
+    if (trace) fprintf(stderr, "[b200ens trace dev %d]%s\n", dev, trace_txt.c_str());
     if (mom) {
         std::vector<double> h(2 * (size_t)row_len + 1);
         CU(cudaMemcpy(h.data(), d_acc, h.size() * sizeof(double), cudaMemcpyDeviceToHost));

@@ -13,6 +13,8 @@ ALG_IDS = {"Tsit5": 1, "Vern7": 2, "Rosenbrock23": 3, "Rodas5": 4, "Rodas5P": 5,
 MODEL_FAST_MATH = 1
 MODEL_PACKED_X2 = 2
 MODEL_KSMEM = 4
+MODEL_SPLIT = 8
+MODEL_NOSPLIT = 16
 
 E_NODEVICE = -3
 
@@ -133,7 +135,7 @@ class Model:
 
     def __init__(self, n_state, n_param, dtype, alg, rhs_src, jac_src=None, tgrad_src=None, noise_src=None,
                  condition_src=None, affect_src=None, name="model", fast_math=False, packed_x2=False,
-                 dcondition_src=None, daffect_src=None, ksmem=False):
+                 dcondition_src=None, daffect_src=None, ksmem=False, split=None):
         L = lib()
         d = ModelDesc()
         d.struct_size = C.sizeof(ModelDesc)
@@ -141,7 +143,8 @@ class Model:
         d.dtype = F64 if np.dtype(dtype) == np.float64 else F32
         d.alg = ALG_IDS[alg] if isinstance(alg, str) else int(alg)
         d.flags = ((MODEL_FAST_MATH if fast_math else 0) | (MODEL_PACKED_X2 if packed_x2 else 0)
-                   | (MODEL_KSMEM if ksmem else 0))
+                   | (MODEL_KSMEM if ksmem else 0) | (MODEL_SPLIT if split is True else 0)
+                   | (MODEL_NOSPLIT if split is False else 0))
         enc = lambda s: s.encode() if s is not None else None
         d.rhs_src, d.jac_src, d.tgrad_src = enc(rhs_src), enc(jac_src), enc(tgrad_src)
         d.noise_src, d.condition_src, d.affect_src = enc(noise_src), enc(condition_src), enc(affect_src)

@@ -192,7 +192,7 @@ class EnsembleB200:
     caller's order / 1 integrate in descending expected-work order (scheduling only, identical results)."""
 
     def __init__(self, devices=None, refill_threshold=0, stage_outputs=-1, fast_math=False, packed_x2=False,
-                 stage_vectors_in_smem=False, work_order=-1):
+                 stage_vectors_in_smem=False, work_order=-1, split=None):
         self.devices = devices
         self.refill_threshold = refill_threshold
         self.stage_outputs = stage_outputs
@@ -200,6 +200,7 @@ class EnsembleB200:
         self.fast_math = fast_math
         self.packed_x2 = packed_x2   # Float32 Tsit5: two trajectories per thread in packed FP32 (FFMA2)
         self.stage_vectors_in_smem = stage_vectors_in_smem   # ERK k-vectors in shared memory (large n_state)
+        self.split = split   # None auto / True / False: components of one trajectory split over the 4 warps of a CTA
 
 
 # ---------------------------------------------------------------- solutions
@@ -290,11 +291,11 @@ class _LazySeq:
 _model_cache = {}
 
 
-def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False, ksmem=False):
+def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False, ksmem=False, split=None):
     """Trace prob.f (and g / callback), emit CUDA C, JIT it for sm_100a.  Cached per function objects."""
     n, m = prob.u0.shape[0], prob.p.shape[0]
     dtype = prob.u0.dtype
-    key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math, packed_x2, ksmem)
+    key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math, packed_x2, ksmem, split)
     hit = _model_cache.get(key)
     if hit is not None and hit[1] is prob.f:
         return hit[0]
@@ -319,7 +320,7 @@ def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False, ksme
         srcs["dcondition_src"], srcs["daffect_src"], term = codegen.emit_discrete_callback(dcb, n, m)
         terminate |= 2 if term else 0
     model = _lib.Model(n, m, dtype, alg.name, name=getattr(prob.f, "__name__", "model"), fast_math=fast_math,
-                       packed_x2=packed_x2, ksmem=ksmem, **srcs)
+                       packed_x2=packed_x2, ksmem=ksmem, split=split, **srcs)
     model.sources = srcs
     model.event_terminate = terminate
     _model_cache[key] = (model, prob.f)
@@ -399,7 +400,7 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, 
             raise ValueError("fixed-step solves need dt")
         dt = 0.0   # automatic per-trajectory initial step on the device
     model = build_model(base, alg, callback, ensemblealg.fast_math, ensemblealg.packed_x2,
-                        ensemblealg.stage_vectors_in_smem)
+                        ensemblealg.stage_vectors_in_smem, ensemblealg.split)
     ts = _saveat_array(saveat, base.tspan, dtype)
     t_pack = time.perf_counter()
     u0, p = _pack(eprob, N, dtype)

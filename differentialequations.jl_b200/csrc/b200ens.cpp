@@ -110,6 +110,7 @@ struct b200ens_model {
     int regs = -1, smem = -1, lmem = -1, spill = 0, min_blocks = 1;
     int block = 128;        // threads per CTA the kernel was compiled for (B2_BLOCK)
     int ksmem = 0;          // 1: ERK stage vectors in shared memory
+    int split = 0;          // 1: one trajectory per lane of a 4-warp CTA, components split over the warps (b2_split.cuh)
     int kvec_bytes = 0;     // shared-memory bytes per thread for them
     int x2 = 0;             // 1: two trajectories per thread, packed FP32 (FFMA2)
     std::mutex mu;
@@ -281,17 +282,17 @@ void parse_ptxas_log(b200ens_model* m) {
     if (m->spill < 0) m->spill = 2 * m->lmem;
 }
 
-std::string build_source(const b200ens_model_desc* d, int min_blocks, int block, int ksmem, int x2 = 0) {
+std::string build_source(const b200ens_model_desc* d, int min_blocks, int block, int ksmem, int x2 = 0, int split = 0) {
     char head[1024];
     snprintf(head, sizeof head,
              "// generated by libb200ens (model '%s')\n"
              "#define B2_F64 %d\n#define B2_NSTATE %d\n#define B2_NPARAM %d\n#define B2_ALG %d\n"
              "#define B2_HAS_JAC %d\n#define B2_HAS_TGRAD %d\n#define B2_HAS_NOISE %d\n#define B2_HAS_EVENT %d\n#define B2_HAS_DEVENT %d\n"
-             "#define B2_BLOCK %d\n#define B2_MINBLOCKS %d\n#define B2_KSMEM %d\n#define B2_X2 %d\n#include \"b2_common.cuh\"\n",
+             "#define B2_BLOCK %d\n#define B2_MINBLOCKS %d\n#define B2_KSMEM %d\n#define B2_X2 %d\n#define B2_SPLIT %d\n#include \"b2_common.cuh\"\n",
              d->name ? d->name : "", d->dtype == B200ENS_F64 ? 1 : 0, d->n_state, d->n_param, d->alg,
              d->jac_src ? 1 : 0, d->tgrad_src ? 1 : 0, d->noise_src ? 1 : 0,
              (d->condition_src && d->affect_src) ? 1 : 0, (d->dcondition_src && d->daffect_src) ? 1 : 0, block, min_blocks,
-             ksmem, x2);
+             ksmem, x2, split);
     std::string s = head;
     for (const char* part : {d->rhs_src, d->jac_src, d->tgrad_src, d->noise_src, d->condition_src, d->affect_src,
                              d->dcondition_src, d->daffect_src})
@@ -502,14 +503,14 @@ int plan_launch(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, long long
     bool staged = false;
     // Measured on B200 (profiles/): for the saveat shapes of configs 1-4 direct global stores are ~3%
     // faster than shared-memory staging (L2 merges the 12-byte rows), so auto means direct.
-    if (o->stage_outputs > 0 && n_save > 0 && !m->x2 && smem + ksm <= 200 * 1024) {
+    if (o->stage_outputs > 0 && n_save > 0 && !m->x2 && !m->split && smem + ksm <= 200 * 1024) {
         if (smem + ksm > 48 * 1024)
             CU(cudaFuncSetAttribute((const void*)m->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + ksm)));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_staged, (const void*)m->kernel, block, smem + ksm));
         // stage when it costs at most a quarter of the occupancy (or when forced)
         staged = nb_staged >= 1 && (o->stage_outputs > 0 || 4 * nb_staged >= 3 * nb_direct);
     }
-    if (o->stage_outputs > 0 && !staged && !m->x2)
+    if (o->stage_outputs > 0 && !staged && !m->x2 && !m->split)
         return fail(B200ENS_E_UNSUPPORTED, "stage_outputs=1 but %zu bytes of shared memory per block do not fit", smem);
     int nb = staged ? nb_staged : nb_direct;
     if (const char* e = getenv("B200ENS_BLOCKS_PER_SM")) nb = std::max(1, std::min(nb, atoi(e)));  // experiments
@@ -517,7 +518,8 @@ int plan_launch(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, long long
     lp->block = block;
     lp->stride = staged ? stride : 0;
     lp->smem = (int)((staged ? smem : 0) + ksm);
-    const long long per_block = (long long)block * (m->x2 ? 2 : 1);   // packed kernels hold two trajectories per thread
+    // packed kernels hold two trajectories per thread; split kernels one trajectory per LANE of a 4-warp CTA
+    const long long per_block = m->split ? 32 : (long long)block * (m->x2 ? 2 : 1);
     const long long want = (N + per_block - 1) / per_block;
     lp->grid = (int)std::max<long long>(1, std::min<long long>((long long)nb * d->sms, want));
     int refill = o->refill_threshold;
@@ -870,7 +872,7 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
         a.refill_threshold = lp.refill;
         a.stage_stride = lp.stride;
         LaunchPlan l2 = lp;
-        const long long pb = (long long)lp.block * (m->x2 ? 2 : 1);
+        const long long pb = m->split ? 32 : (long long)lp.block * (m->x2 ? 2 : 1);
         l2.grid = (int)std::max<long long>(1, std::min<long long>(lp.grid, (cn + pb - 1) / pb));
         CU(cudaEventRecord(s.ev[1], s.stream));
         if (want_work_order(m, o, a, cn)) {
@@ -1053,7 +1055,50 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     // with the stage vectors in shared memory, CTA size chosen so that two CTAs fit in the 227 KB of an SM, and keep
     // it if it spills less.  Measured on config 5 (profiles/README.md): 156 vs 204 ms (saveat 101), 234 vs 297 ms
     // (saveat 1001) per 200k trajectories.
-    if (!rc && nvec && !m->x2 && (!try_regs || (m->spill > 4096 && !(force_k && atoi(force_k) == 0)))) {
+    // Large systems with a ContinuousCallback: SPLIT the trajectory over the four warps of a CTA (kernels/b2_split.cuh):
+    // a thread holds a quarter of every state / stage vector.  Measured on the 16-species network, Float64, 200k
+    // trajectories (profiles/README.md): Vern7 + event 81.7 ms split (4 CTAs/SM, 128 registers, 1.4 KB of spills) vs
+    // 102.6 ms one-thread with shared-memory stage vectors; WITHOUT the event search the one-thread kernels win
+    // (Vern7 7.8 vs 11.5 ms, Tsit5 4.0 vs 4.8 ms), so the automatic choice is limited to models with a
+    // ContinuousCallback whose one-thread variant spills more than 4 KB.  B200ENS_MODEL_SPLIT / B200ENS_SPLIT=1 force it.
+    // Unlike the one-thread kernels the split kernel prefers occupancy over a spill-free build (four warps meet at a
+    // barrier ~25 times per step): start at 4 CTAs/SM and accept up to 2 KB of spill stores.
+    {
+        const char* force_s = getenv("B200ENS_SPLIT");
+        const bool off = (d->flags & B200ENS_MODEL_NOSPLIT) || (force_s && atoi(force_s) == 0);
+        const bool on = (d->flags & B200ENS_MODEL_SPLIT) || (force_s && atoi(force_s) == 1);
+        const bool eligible = nvec && !m->x2 && !d->dcondition_src && d->n_state >= 4 && !flag_k && !(force_k && atoi(force_k) == 1);
+        if (!rc && eligible && !off && (on || (try_regs && d->condition_src && d->affect_src && m->spill > 4096))) {
+            auto keep_src = m->source;
+            auto keep_cubin = m->cubin;
+            auto keep_log = m->log;
+            const int keep_spill = m->spill, keep_regs = m->regs, keep_lmem = m->lmem, keep_smem = m->smem;
+            int mbs = 4, rc2 = 0;
+            if (const char* e = getenv("B200ENS_MINBLOCKS")) mbs = std::max(1, atoi(e));
+            for (;; mbs--) {
+                m->source = build_source(d, mbs, 128, 0, 0, 1);
+                rc2 = nvrtc_compile(m.get());
+                if (rc2) break;
+                parse_ptxas_log(m.get());
+                if (m->spill <= 2048 || mbs <= 1 || getenv("B200ENS_MINBLOCKS")) break;
+            }
+            if (!rc2 && (on || m->spill < keep_spill)) {
+                m->split = 1;
+                m->block = 128;
+                mb = mbs;
+                try_regs = true;   // settled: skip the shared-memory variant
+            } else {
+                m->source = keep_src;
+                m->cubin = keep_cubin;
+                m->log = keep_log;
+                m->spill = keep_spill;
+                m->regs = keep_regs;
+                m->lmem = keep_lmem;
+                m->smem = keep_smem;
+            }
+        }
+    }
+    if (!rc && nvec && !m->x2 && !m->split && (!try_regs || (m->spill > 4096 && !(force_k && atoi(force_k) == 0)))) {
         const int per_thread = nvec * d->n_state * (d->dtype == B200ENS_F64 ? 8 : 4);
         int block = std::min(128, (114688 / per_thread) / 32 * 32);
         if (block >= 32) {

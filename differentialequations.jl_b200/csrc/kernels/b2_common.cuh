@@ -160,6 +160,28 @@ __device__ __forceinline__ float b2_fastexp2(float y) {
     return __uint_as_float(__float_as_uint(p) + (unsigned)((int)fi << 23));
 }
 
+// ---- ITP root-find helper: pw = eps * 2^(k+1), eps = 2*B2_EPS, k = number of halvings of wd until wd <= 2*eps
+// (the oracle computes it with that loop; ~50 iterations in Float64).  All quantities are powers of two, so the
+// closed form from the exponent bits is exact: with wd = m * 2^e, m in [1,2): k = e - tau + (m > 1), 2*eps = 2^tau.
+__device__ __forceinline__ float b2_itp_pw(float wd) {
+    const int tau = -21;   // 2*eps = 2 * 2 * 2^-23
+    int k = 0;
+    if (wd > 4.76837158203125e-07f) {   // 2^-21
+        const unsigned b = __float_as_uint(wd);
+        k = (int)(b >> 23) - 127 - tau + ((b & 0x007fffffu) ? 1 : 0);
+    }
+    return __uint_as_float((unsigned)(tau + k + 127) << 23);
+}
+__device__ __forceinline__ double b2_itp_pw(double wd) {
+    const int tau = -50;   // 2*eps = 2 * 2 * 2^-52
+    int k = 0;
+    if (wd > 8.8817841970012523e-16) {   // 2^-50
+        const unsigned long long b = (unsigned long long)__double_as_longlong(wd);
+        k = (int)(b >> 52) - 1023 - tau + ((b & 0x000fffffffffffffull) ? 1 : 0);
+    }
+    return __longlong_as_double((long long)(tau + k + 1023) << 52);
+}
+
 // ---- per-lane output sink: shared-memory staging (flushed coalesced by the whole warp
 // when the lane retires) or direct global stores for outputs too large to stage.
 struct B2Sink {

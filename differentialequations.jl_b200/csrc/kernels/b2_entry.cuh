@@ -3,9 +3,17 @@
 #pragma once
 #include "b2_common.cuh"
 
+#ifndef B2_SPLIT
+#define B2_SPLIT 0   // 1: one trajectory per lane of a 4-warp CTA, components split over the warps (large systems)
+#endif
 #if B2_ALG == 1 || B2_ALG == 2
+#if B2_SPLIT
+#include "b2_split.cuh"
+#endif
 #include "b2_erk.cuh"
-#if B2_X2
+#if B2_SPLIT
+#include "b2_ode_driver_split.cuh"
+#elif B2_X2
 #include "b2_ode_driver_x2.cuh"
 #else
 #include "b2_ode_driver.cuh"
@@ -23,7 +31,7 @@
 #include "b2_work.cuh"   // expected-work ordering of the trajectory queue (adaptive ODE steppers)
 #endif
 
-#if (B2_ALG == 1 || B2_ALG == 2) && !B2_X2
+#if (B2_ALG == 1 || B2_ALG == 2) && !B2_X2 && !B2_SPLIT
 // the common explicit case (adaptive, saveat interpolated, caller-supplied dt) folded at compile time
 extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble_kernel_adaptive(const __grid_constant__ B2Args a) {
 #if B2_ALG == 1
@@ -35,7 +43,11 @@ extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble
 #endif
 
 extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble_kernel(const __grid_constant__ B2Args a) {
-#if B2_ALG == 1 && B2_X2
+#if B2_ALG == 1 && B2_SPLIT
+    b2_ode_driver_split<B2Tsit5>(a);
+#elif B2_ALG == 2 && B2_SPLIT
+    b2_ode_driver_split<B2Vern7>(a);
+#elif B2_ALG == 1 && B2_X2
     b2_ode_driver_x2<B2Tsit5>(a);
 #elif B2_ALG == 1
     b2_ode_driver<B2Tsit5>(a);

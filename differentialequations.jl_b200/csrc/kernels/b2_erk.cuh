@@ -11,6 +11,18 @@
 // no longer fits the register file (ptxas spills: config 5, n=16 f64 Vern7 spilled 4 KB/thread and became
 // DRAM-bound on local-memory traffic, profiles/r1_net16_*), the model is recompiled with B2_KSMEM=1 and the
 // k-vectors live in shared memory as [vector][component][thread] (bank-conflict-free, no spills).
+// B2_NV: components of the state a THREAD holds.  One trajectory per thread: all of them.  Split mode (B2_SPLIT,
+// b2_ode_driver_split.cuh): the four warps of a CTA share 32 trajectories, warp g owns components [g*NL, (g+1)*NL),
+// and every RHS evaluation goes through b2_split_rhs (publish the stage argument in shared memory, barrier, evaluate
+// only the owned outputs).
+#if B2_SPLIT
+#define B2_NV B2_NL
+#define B2_RHS_REG(out, x, t_) b2_split_rhs(*this, out, x, p, t_)
+#else
+#define B2_NV B2_N
+#define B2_RHS_REG(out, x, t_) b2_rhs(out, x, p, t_)
+#endif
+
 #if B2_KSMEM
 #define B2_KSTRIDE B2_BLOCK
 #define B2_KDECL(name) real* name
@@ -24,9 +36,9 @@
     } while (0)
 #else
 #define B2_KSTRIDE 1
-#define B2_KDECL(name) real name[B2_N]
+#define B2_KDECL(name) real name[B2_NV]
 #define B2_KBIND(name, slot)
-#define B2_RHS_TO(k, x, t_) b2_rhs(k, x, p, t_)
+#define B2_RHS_TO(k, x, t_) B2_RHS_REG(k, x, t_)
 #endif
 #define KV(name, i) name[(i) * B2_KSTRIDE]
 // In shared-memory mode ptxas otherwise hoists the loads of all components of a stage to the top of the unrolled
@@ -48,34 +60,43 @@ struct B2Tsit5 {
         B2_KBIND(k1, 0); B2_KBIND(k2, 1); B2_KBIND(k3, 2); B2_KBIND(k4, 3); B2_KBIND(k5, 4); B2_KBIND(k6, 5); B2_KBIND(k7, 6);
     }
 
-    __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {
+    __device__ __forceinline__ void start(const real (&u)[B2_NV], const real (&p)[B2_NPA], real t) {
         B2_RHS_TO(k1, u, t);
     }
     __device__ __forceinline__ real fsal0(int i) const { return KV(k1, i); }  // f(u, t) of the current state
+#if B2_SPLIT
+    B2Xchg xc;   // shared-memory exchange context of the 4-warp group (b2_split.cuh)
+    __device__ __forceinline__ void reset_dense() {}
+    __device__ __forceinline__ void rhs(real (&f)[B2_NV], const real (&x)[B2_NV], const real (&p)[B2_NPA], real t) { B2_RHS_REG(f, x, t); }
+    __device__ __forceinline__ void set_k1(const real (&f)[B2_NV]) {
+#pragma unroll
+        for (int i = 0; i < B2_NV; i++) k1[i] = f[i];
+    }
+#endif
 #if B2_X2
     static constexpr int NF_ATTEMPT = 6;
     // packed mode: (re)start only the halves in (m0, m1); the other half keeps its k1
-    __device__ __forceinline__ void start_masked(const real (&u)[B2_N], const real (&p)[B2_NPA], real t, bool m0, bool m1) {
-        real f[B2_N];
+    __device__ __forceinline__ void start_masked(const real (&u)[B2_NV], const real (&p)[B2_NPA], real t, bool m0, bool m1) {
+        real f[B2_NV];
         b2_rhs(f, u, p, t);
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) k1[i] = b2_blend(m0, m1, f[i], k1[i]);
+        for (int i = 0; i < B2_NV; i++) k1[i] = b2_blend(m0, m1, f[i], k1[i]);
     }
     // FSAL hand-over only for the halves whose step was accepted
     __device__ __forceinline__ void advance_masked(bool m0, bool m1) {
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) k1[i] = b2_blend(m0, m1, k7[i], k1[i]);
+        for (int i = 0; i < B2_NV; i++) k1[i] = b2_blend(m0, m1, k7[i], k1[i]);
     }
 #endif
     // one step attempt from (up, t) with k1 = f(up, t); writes the proposal u and dt*error estimate
-    __device__ __forceinline__ void step(const real (&up)[B2_N], const real (&p)[B2_NPA], real t, real dt,
-                                         real (&u)[B2_N], real (&ut)[B2_N], bool adaptive, int& nf) {
-        real tmp[B2_N];
+    __device__ __forceinline__ void step(const real (&up)[B2_NV], const real (&p)[B2_NPA], real t, real dt,
+                                         real (&u)[B2_NV], real (&ut)[B2_NV], bool adaptive, int& nf) {
+        real tmp[B2_NV];
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) tmp[i] = b2_fma(dt, TS(a21) * KV(k1, i), up[i]);
+        for (int i = 0; i < B2_NV; i++) tmp[i] = b2_fma(dt, TS(a21) * KV(k1, i), up[i]);
         B2_RHS_TO(k2, tmp, t + TS(c2) * dt);
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = TS(a31) * KV(k1, i);
             s = b2_fma(TS(a32), KV(k2, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
@@ -83,7 +104,7 @@ struct B2Tsit5 {
         }
         B2_RHS_TO(k3, tmp, t + TS(c3) * dt);
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = TS(a41) * KV(k1, i);
             s = b2_fma(TS(a42), KV(k2, i), s);
             s = b2_fma(TS(a43), KV(k3, i), s);
@@ -92,7 +113,7 @@ struct B2Tsit5 {
         }
         B2_RHS_TO(k4, tmp, t + TS(c4) * dt);
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = TS(a51) * KV(k1, i);
             s = b2_fma(TS(a52), KV(k2, i), s);
             s = b2_fma(TS(a53), KV(k3, i), s);
@@ -102,7 +123,7 @@ struct B2Tsit5 {
         }
         B2_RHS_TO(k5, tmp, t + TS(c5) * dt);
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = TS(a61) * KV(k1, i);
             s = b2_fma(TS(a62), KV(k2, i), s);
             s = b2_fma(TS(a63), KV(k3, i), s);
@@ -113,7 +134,7 @@ struct B2Tsit5 {
         }
         B2_RHS_TO(k6, tmp, t + dt);
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = TS(a71) * KV(k1, i);
             s = b2_fma(TS(a72), KV(k2, i), s);
             s = b2_fma(TS(a73), KV(k3, i), s);
@@ -127,7 +148,7 @@ struct B2Tsit5 {
         nf += 6;
         if (adaptive) {
 #pragma unroll
-            for (int i = 0; i < B2_N; i++) {
+            for (int i = 0; i < B2_NV; i++) {
                 real s = TS(btilde1) * KV(k1, i);
                 s = b2_fma(TS(btilde2), KV(k2, i), s);
                 s = b2_fma(TS(btilde3), KV(k3, i), s);
@@ -141,17 +162,17 @@ struct B2Tsit5 {
         }
     }
     // called once per accepted step before interpolation / FSAL hand-over (no-op here)
-    __device__ __forceinline__ void accepted(const real (&)[B2_N], const real (&)[B2_NPA], real, int&) {}
-    __device__ __forceinline__ void prepare_dense(const real (&)[B2_N], const real (&)[B2_NPA], real, real, int&) {}
+    __device__ __forceinline__ void accepted(const real (&)[B2_NV], const real (&)[B2_NPA], real, int&) {}
+    __device__ __forceinline__ void prepare_dense(const real (&)[B2_NV], const real (&)[B2_NPA], real, real, int&) {}
     // u(t + th*dt) = up + dt * sum_i b_i(th) k_i
-    __device__ __forceinline__ void interp(const real (&up)[B2_N], const real (&)[B2_N], real th, real dt,
-                                           real (&out)[B2_N]) const {
+    __device__ __forceinline__ void interp(const real (&up)[B2_NV], const real (&)[B2_NV], real th, real dt,
+                                           real (&out)[B2_NV]) const {
 #define TSB(i, r1) (th * b2_fma(th, b2_fma(th, b2_fma(th, TS(r##i##4), TS(r##i##3)), TS(r##i##2)), (real)(r1)))
         const real b1 = TSB(1, B2T_TSIT5_r11), b2 = TSB(2, 0.0), b3 = TSB(3, 0.0), b4 = TSB(4, 0.0),
                    b5 = TSB(5, 0.0), b6 = TSB(6, 0.0), b7 = TSB(7, 0.0);
 #undef TSB
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = b1 * KV(k1, i);
             s = b2_fma(b2, KV(k2, i), s);
             s = b2_fma(b3, KV(k3, i), s);
@@ -190,7 +211,7 @@ struct B2Tsit5 {
         k7 = t_;
 #else
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) k1[i] = k7[i];
+        for (int i = 0; i < B2_NV; i++) k1[i] = k7[i];
 #endif
     }
 };
@@ -213,19 +234,28 @@ struct B2Vern7 {
     }
     bool have_extra;
 
-    __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {
+    __device__ __forceinline__ void start(const real (&u)[B2_NV], const real (&p)[B2_NPA], real t) {
         B2_RHS_TO(k1, u, t);
         have_extra = false;
     }
     __device__ __forceinline__ real fsal0(int i) const { return KV(k1, i); }
-    __device__ __forceinline__ void step(const real (&up)[B2_N], const real (&p)[B2_NPA], real t, real dt,
-                                         real (&u)[B2_N], real (&ut)[B2_N], bool adaptive, int& nf) {
-        real tmp[B2_N], q2[B2_N];
+#if B2_SPLIT
+    B2Xchg xc;
+    __device__ __forceinline__ void reset_dense() { have_extra = false; }
+    __device__ __forceinline__ void rhs(real (&f)[B2_NV], const real (&x)[B2_NV], const real (&p)[B2_NPA], real t) { B2_RHS_REG(f, x, t); }
+    __device__ __forceinline__ void set_k1(const real (&f)[B2_NV]) {
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) tmp[i] = b2_fma(dt, V7(a0201) * KV(k1, i), up[i]);
-        b2_rhs(q2, tmp, p, t + V7(c2) * dt);
+        for (int i = 0; i < B2_NV; i++) k1[i] = f[i];
+    }
+#endif
+    __device__ __forceinline__ void step(const real (&up)[B2_NV], const real (&p)[B2_NPA], real t, real dt,
+                                         real (&u)[B2_NV], real (&ut)[B2_NV], bool adaptive, int& nf) {
+        real tmp[B2_NV], q2[B2_NV];
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) tmp[i] = b2_fma(dt, V7(a0201) * KV(k1, i), up[i]);
+        B2_RHS_REG(q2, tmp, t + V7(c2) * dt);
+#pragma unroll
+        for (int i = 0; i < B2_NV; i++) {
             real s = V7(a0301) * KV(k1, i);
             s = b2_fma(V7(a0302), q2[i], s);
             tmp[i] = b2_fma(dt, s, up[i]);
@@ -233,7 +263,7 @@ struct B2Vern7 {
         }
         B2_RHS_TO(k3, tmp, t + V7(c3) * dt);
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = V7(a0401) * KV(k1, i);
             s = b2_fma(V7(a0403), KV(k3, i), s);
             tmp[i] = b2_fma(dt, s, up[i]);
@@ -241,7 +271,7 @@ struct B2Vern7 {
         }
         B2_RHS_TO(k4, tmp, t + V7(c4) * dt);
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = V7(a0501) * KV(k1, i);
             s = b2_fma(V7(a0503), KV(k3, i), s);
             s = b2_fma(V7(a0504), KV(k4, i), s);
@@ -250,7 +280,7 @@ struct B2Vern7 {
         }
         B2_RHS_TO(k5, tmp, t + V7(c5) * dt);
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = V7(a0601) * KV(k1, i);
             s = b2_fma(V7(a0603), KV(k3, i), s);
             s = b2_fma(V7(a0604), KV(k4, i), s);
@@ -260,7 +290,7 @@ struct B2Vern7 {
         }
         B2_RHS_TO(k6, tmp, t + V7(c6) * dt);
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = V7(a0701) * KV(k1, i);
             s = b2_fma(V7(a0703), KV(k3, i), s);
             s = b2_fma(V7(a0704), KV(k4, i), s);
@@ -271,7 +301,7 @@ struct B2Vern7 {
         }
         B2_RHS_TO(k7, tmp, t + V7(c7) * dt);
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = V7(a0801) * KV(k1, i);
             s = b2_fma(V7(a0803), KV(k3, i), s);
             s = b2_fma(V7(a0804), KV(k4, i), s);
@@ -283,7 +313,7 @@ struct B2Vern7 {
         }
         B2_RHS_TO(k8, tmp, t + V7(c8) * dt);
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = V7(a0901) * KV(k1, i);
             s = b2_fma(V7(a0903), KV(k3, i), s);
             s = b2_fma(V7(a0904), KV(k4, i), s);
@@ -295,10 +325,10 @@ struct B2Vern7 {
             B2_KBAR;
         }
         B2_RHS_TO(k9, tmp, t + dt);
-        real q10[B2_N];
+        real q10[B2_NV];
         if (adaptive) {
 #pragma unroll
-            for (int i = 0; i < B2_N; i++) {
+            for (int i = 0; i < B2_NV; i++) {
                 real s = V7(a1001) * KV(k1, i);
                 s = b2_fma(V7(a1003), KV(k3, i), s);
                 s = b2_fma(V7(a1004), KV(k4, i), s);
@@ -308,10 +338,10 @@ struct B2Vern7 {
                 tmp[i] = b2_fma(dt, s, up[i]);
                 B2_KBAR;
             }
-            b2_rhs(q10, tmp, p, t + dt);
+            B2_RHS_REG(q10, tmp, t + dt);
         }
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = V7(b1) * KV(k1, i);
             s = b2_fma(V7(b4), KV(k4, i), s);
             s = b2_fma(V7(b5), KV(k5, i), s);
@@ -324,7 +354,7 @@ struct B2Vern7 {
         }
         if (adaptive) {
 #pragma unroll
-            for (int i = 0; i < B2_N; i++) {
+            for (int i = 0; i < B2_NV; i++) {
                 real s = V7(btilde1) * KV(k1, i);
                 s = b2_fma(V7(btilde4), KV(k4, i), s);
                 s = b2_fma(V7(btilde5), KV(k5, i), s);
@@ -341,17 +371,17 @@ struct B2Vern7 {
         have_extra = false;
     }
     // k11 = f(u_new): dense-output stage 11 and the next step's k1 (Vern7 is not FSAL in the step itself)
-    __device__ __forceinline__ void accepted(const real (&u)[B2_N], const real (&p)[B2_NPA], real tnew, int& nf) {
+    __device__ __forceinline__ void accepted(const real (&u)[B2_NV], const real (&p)[B2_NPA], real tnew, int& nf) {
         B2_RHS_TO(k11, u, tnew);
         nf += 1;
     }
     // lazy stages 12..16, only on steps that are interpolated (saveat / event search)
-    __device__ __forceinline__ void prepare_dense(const real (&up)[B2_N], const real (&p)[B2_NPA], real t, real dt,
+    __device__ __forceinline__ void prepare_dense(const real (&up)[B2_NV], const real (&p)[B2_NPA], real t, real dt,
                                                   int& nf) {
         if (have_extra) return;
-        real tmp[B2_N];
+        real tmp[B2_NV];
 #define V7ROW(r, KLAST)                                                    \
-    _Pragma("unroll") for (int i = 0; i < B2_N; i++) {                     \
+    _Pragma("unroll") for (int i = 0; i < B2_NV; i++) {                     \
         real s = V7X(a##r##01) * KV(k1, i);                                    \
         s = b2_fma(V7X(a##r##04), KV(k4, i), s);                               \
         s = b2_fma(V7X(a##r##05), KV(k5, i), s);                               \
@@ -377,8 +407,8 @@ struct B2Vern7 {
         nf += 5;
         have_extra = true;
     }
-    __device__ __forceinline__ void interp(const real (&up)[B2_N], const real (&)[B2_N], real th, real dt,
-                                           real (&out)[B2_N]) const {
+    __device__ __forceinline__ void interp(const real (&up)[B2_NV], const real (&)[B2_NV], real th, real dt,
+                                           real (&out)[B2_NV]) const {
 #define V7B(ss)                                                                                                   \
     (th * b2_fma(th, b2_fma(th, b2_fma(th, b2_fma(th, b2_fma(th, V7(R##ss##_6), V7(R##ss##_5)), V7(R##ss##_4)), \
                                        V7(R##ss##_3)), V7(R##ss##_2)), V7(R##ss##_1)))
@@ -387,7 +417,7 @@ struct B2Vern7 {
                    b16 = V7B(16);
 #undef V7B
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
+        for (int i = 0; i < B2_NV; i++) {
             real s = b01 * KV(k1, i);
             s = b2_fma(b04, KV(k4, i), s);
             s = b2_fma(b05, KV(k5, i), s);
@@ -435,7 +465,7 @@ struct B2Vern7 {
         k11 = t_;
 #else
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) k1[i] = k11[i];
+        for (int i = 0; i < B2_NV; i++) k1[i] = k11[i];
 #endif
     }
 };

@@ -289,12 +289,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                             // issued instructions of config 5, profiles/r1_net16_*).  Keeps the LEFT end.
                             const real eps = (real)2 * (real)B2_EPS;
                             const real k1 = (real)0.2 / (hi - lo);
-                            real pw = eps, wd = hi - lo;
-                            while (wd > (real)2 * eps) {
-                                wd *= (real)0.5;
-                                pw *= (real)2;
-                            }
-                            pw *= (real)2;
+                            real pw = b2_itp_pw(hi - lo);   // eps * 2^(halvings + 1), closed form
                             for (int it = 0; it < 100 && hi - lo > (real)2 * eps; it++) {
                                 const real xh = (real)0.5 * (lo + hi);
                                 const real r = pw - (real)0.5 * (hi - lo);

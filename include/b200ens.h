@@ -56,6 +56,10 @@ enum b200ens_error {
                                       scalar kernel on B200 (profiles/README.md), hence opt-in */
 
 #define B200ENS_MODEL_KSMEM 4u     /* force ERK stage vectors into shared memory (default: automatic when the register variant spills > 4 KB) */
+#define B200ENS_MODEL_SPLIT 8u     /* force the split kernel (one trajectory per lane of a 4-warp CTA, components split over the
+                                      warps; Tsit5 / Vern7 without DiscreteCallback; default: automatic when the one-thread
+                                      variant spills > 4 KB) */
+#define B200ENS_MODEL_NOSPLIT 16u  /* never use the split kernel */
 
 /* What a problem looks like to the library: ODEProblem / SDEProblem (qa.jl:86,103) with f,
  * jac, tgrad, g and one ContinuousCallback (qa.jl:26; test/core.jl:69-72) given as CUDA-C

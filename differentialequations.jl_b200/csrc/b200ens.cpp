@@ -1055,25 +1055,26 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     // with the stage vectors in shared memory, CTA size chosen so that two CTAs fit in the 227 KB of an SM, and keep
     // it if it spills less.  Measured on config 5 (profiles/README.md): 156 vs 204 ms (saveat 101), 234 vs 297 ms
     // (saveat 1001) per 200k trajectories.
-    // Large systems with a ContinuousCallback: SPLIT the trajectory over the four warps of a CTA (kernels/b2_split.cuh):
-    // a thread holds a quarter of every state / stage vector.  Measured on the 16-species network, Float64, 200k
-    // trajectories (profiles/README.md): Vern7 + event 81.7 ms split (4 CTAs/SM, 128 registers, 1.4 KB of spills) vs
-    // 102.6 ms one-thread with shared-memory stage vectors; WITHOUT the event search the one-thread kernels win
-    // (Vern7 7.8 vs 11.5 ms, Tsit5 4.0 vs 4.8 ms), so the automatic choice is limited to models with a
-    // ContinuousCallback whose one-thread variant spills more than 4 KB.  B200ENS_MODEL_SPLIT / B200ENS_SPLIT=1 force it.
+    // Large systems: SPLIT the trajectory over the four warps of a CTA (kernels/b2_split.cuh): a thread holds a quarter
+    // of every state / stage vector, and the generated RHS exists once per warp role out of line, which keeps the loop
+    // body inside the instruction cache.  Measured on the 16-species network, Float64, 200k trajectories
+    // (profiles/README.md): Vern7 + event 42 ms split vs 103 ms one-thread (shared-memory stage vectors);
+    // Vern7 without event 6.4 vs 7.8 ms; Tsit5 without event 4.4 vs 3.9 ms (its 7 stage vectors nearly fit one thread).
+    // Tried when the one-thread variant spills more than 1 KB (Vern7; its loop body is then several hundred KB of SASS)
+    // or 4 KB (Tsit5), kept when it spills less; B200ENS_MODEL_SPLIT / B200ENS_SPLIT=1 force it.
     // Unlike the one-thread kernels the split kernel prefers occupancy over a spill-free build (four warps meet at a
-    // barrier ~25 times per step): start at 4 CTAs/SM and accept up to 2 KB of spill stores.
+    // barrier ~25 times per step): start at 3 CTAs/SM and accept up to 2 KB of spill stores.
     {
         const char* force_s = getenv("B200ENS_SPLIT");
         const bool off = (d->flags & B200ENS_MODEL_NOSPLIT) || (force_s && atoi(force_s) == 0);
         const bool on = (d->flags & B200ENS_MODEL_SPLIT) || (force_s && atoi(force_s) == 1);
         const bool eligible = nvec && !m->x2 && !d->dcondition_src && d->n_state >= 4 && !flag_k && !(force_k && atoi(force_k) == 1);
-        if (!rc && eligible && !off && (on || (try_regs && d->condition_src && d->affect_src && m->spill > 4096))) {
+        if (!rc && eligible && !off && (on || (try_regs && m->spill > (d->alg == B200ENS_VERN7 ? 1024 : 4096)))) {
             auto keep_src = m->source;
             auto keep_cubin = m->cubin;
             auto keep_log = m->log;
             const int keep_spill = m->spill, keep_regs = m->regs, keep_lmem = m->lmem, keep_smem = m->smem;
-            int mbs = 4, rc2 = 0;
+            int mbs = 3, rc2 = 0;
             if (const char* e = getenv("B200ENS_MINBLOCKS")) mbs = std::max(1, atoi(e));
             for (;; mbs--) {
                 m->source = build_source(d, mbs, 128, 0, 0, 1);

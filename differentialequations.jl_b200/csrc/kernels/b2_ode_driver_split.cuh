@@ -35,6 +35,7 @@ template <class Alg>
 __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     __shared__ __align__(16) real s_xchg[2 * B2_NP * 32];
     __shared__ long long s_my[32];
+    __shared__ __align__(16) real s_par[B2_NPA * 32];   // the trajectories' parameters, read by the out-of-line RHS
     __shared__ int s_flag[4];
     const unsigned lane = threadIdx.x & 31u;
     const int g = threadIdx.x >> 5;
@@ -65,6 +66,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     alg.xc.lane = (int)lane;
     alg.xc.phase = 0;
     alg.xc.g = g;
+    alg.xc.pcol = s_par + lane;
     real u[B2_NL], p[B2_NPA];
 #pragma unroll
     for (int j = 0; j < B2_NL; j++) u[j] = 0;
@@ -111,6 +113,10 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                         for (int j = 0; j < B2_NL; j++) u[j] = (c0 + j < B2_N) ? gu0[idx * B2_N + c0 + j] : (real)0;
 #pragma unroll
                         for (int i = 0; i < B2_NPARAM; i++) p[i] = gp[idx * B2_NPARAM + i];
+                        if (g == 0) {
+#pragma unroll
+                            for (int i = 0; i < B2_NPARAM; i++) s_par[i * 32 + lane] = p[i];
+                        }
                         t = t0;
                         dt = dt_user;
                         lq = lqinit;

@@ -25,6 +25,7 @@ struct B2Xchg {
     int lane;       // trajectory slot = lane index (column of the exchange area)
     int phase;      // which half the next exchange uses
     int g;          // warp role (0..3), warp-uniform
+    const real* pcol; // this lane's column of the parameter mirror in shared memory: real [B2_NPA][32]
 };
 __host__ __device__ constexpr int b2_popc_c(unsigned x) {
     int c = 0;
@@ -48,25 +49,46 @@ __device__ __forceinline__ const T* b2_split_publish(B2Xchg& xc, const T (&x)[B2
     return b;
 }
 
+// The owned block of f(X, p, t) for warp role G: the generated b2_rhs is inlined once per role and the outputs other
+// roles own are dead code.  ONE out-of-line copy per kernel (not one per call site): a Vern7 step with its event search
+// evaluates the RHS at 18 places, and with the four role bodies inlined everywhere the loop body was 172 KB of SASS --
+// ncu showed the kernel stalled on instruction fetch (no_instruction: 9 of 13 stalled warps per issue).  Arguments
+// travel through shared memory (the stage argument just published, the trajectory's parameters), the result in
+// registers.
+struct B2Blk {
+    real v[B2_NL];
+};
 #define B2_SPLIT_CASE(G)                                                                   \
     case G: {                                                                              \
         real X_[B2_N], F_[B2_N];                                                           \
-        _Pragma("unroll") for (int i = 0; i < B2_N; i++) X_[i] = b[i * 32];                \
-        b2_rhs(F_, X_, p, t);                                                              \
+        _Pragma("unroll") for (int i = 0; i < B2_N; i++) X_[i] = xb[i * 32];               \
+        b2_rhs(F_, X_, P_, t);                                                             \
         _Pragma("unroll") for (int j = 0; j < B2_NL; j++)                                  \
-            out[j] = (G * B2_NL + j < B2_N) ? F_[(G * B2_NL + j < B2_N) ? G * B2_NL + j : 0] : (real)0; \
+            r.v[j] = (G * B2_NL + j < B2_N) ? F_[(G * B2_NL + j < B2_N) ? G * B2_NL + j : 0] : (real)0; \
     } break;
 
-// out = the owned block of f(x_full, p, t)
-template <class Alg>
-__device__ __forceinline__ void b2_split_rhs(Alg& alg, real (&out)[B2_NL], const real (&x)[B2_NL], const real (&p)[B2_NPA],
-                                             real t) {
-    const real* b = b2_split_publish(alg.xc, x);
-    switch (alg.xc.g) {
+__device__ __noinline__ B2Blk b2_split_rhs_role(int g, const real* xb, const real* pb, real t) {
+    B2Blk r;
+    real P_[B2_NPA];
+#pragma unroll
+    for (int i = 0; i < B2_NPARAM; i++) P_[i] = pb[i * 32];
+    switch (g) {
         B2_SPLIT_CASE(0)
         B2_SPLIT_CASE(1)
         B2_SPLIT_CASE(2)
         default:
         B2_SPLIT_CASE(3)
     }
+    return r;
+}
+
+// out = the owned block of f(x_full, p, t)
+template <class Alg>
+__device__ __forceinline__ void b2_split_rhs(Alg& alg, real (&out)[B2_NL], const real (&x)[B2_NL], const real (&p)[B2_NPA],
+                                             real t) {
+    (void)p;   // the out-of-line role body reads the parameters from shared memory (alg.xc.pcol)
+    const real* b = b2_split_publish(alg.xc, x);
+    const B2Blk r = b2_split_rhs_role(alg.xc.g, b, alg.xc.pcol, t);
+#pragma unroll
+    for (int j = 0; j < B2_NL; j++) out[j] = r.v[j];
 }

@@ -358,14 +358,13 @@ int ensure_loaded(b200ens_model* m) {
     if (m->kernel) return 0;
     CU(cudaLibraryLoadData(&m->lib, m->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
     CU(cudaLibraryGetKernel(&m->kernel, m->lib, "b2_ensemble_kernel"));
-    if (cudaLibraryGetKernel(&m->kernel_adaptive, m->lib, "b2_ensemble_kernel_adaptive") != cudaSuccess) {
-        m->kernel_adaptive = nullptr;
-        (void)cudaGetLastError();
-    }
-    if (cudaLibraryGetKernel(&m->k_work_keys, m->lib, "b2_work_keys") != cudaSuccess ||
-        cudaLibraryGetKernel(&m->k_work_scatter, m->lib, "b2_work_scatter") != cudaSuccess) {
-        m->k_work_keys = m->k_work_scatter = nullptr;   // SDE / packed modules have no ordering kernels
-        (void)cudaGetLastError();
+    // optional entry points are looked up only in modules that define them (kernels/b2_entry.cuh): no failing API
+    // calls on the normal path (they show up as errors under compute-sanitizer)
+    const bool erk = m->alg == B200ENS_TSIT5 || m->alg == B200ENS_VERN7;
+    if (erk && !m->x2 && !m->split) CU(cudaLibraryGetKernel(&m->kernel_adaptive, m->lib, "b2_ensemble_kernel_adaptive"));
+    if (!is_sde(m->alg) && !m->x2) {
+        CU(cudaLibraryGetKernel(&m->k_work_keys, m->lib, "b2_work_keys"));
+        CU(cudaLibraryGetKernel(&m->k_work_scatter, m->lib, "b2_work_scatter"));
     }
     return 0;
 }

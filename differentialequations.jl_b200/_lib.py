@@ -223,6 +223,13 @@ class Model:
         return tm
 
 
+def copy_opts(o):
+    """A by-value copy of a b200ens_opts struct."""
+    c = Opts()
+    C.memmove(C.byref(c), C.byref(o), C.sizeof(Opts))
+    return c
+
+
 def pinned_empty(shape, dtype):
     """numpy array backed by cudaHostAlloc memory (zero-staging H2D/D2H)."""
     dtype = np.dtype(dtype)

@@ -205,11 +205,30 @@ class EnsembleB200:
 
 # ---------------------------------------------------------------- solutions
 class ODESolution:
-    def __init__(self, t, u, retcode, stats, scalar=False):
+    def __init__(self, t, u, retcode, stats, scalar=False, dense=None):
         self.t = t
         self.u = u[:, 0] if scalar else u
         self.retcode = ReturnCode(int(retcode))
         self.stats = None if stats is None else dict(zip(("naccept", "nreject", "nf", "nevents"), map(int, stats)))
+        self._scalar = scalar
+        self._dense = dense
+
+    def __call__(self, t):
+        """sol(t): the continuous (dense-output) solution, as solve(...; dense=true) gives upstream
+        (test/core.jl:51-58).  Evaluated by the SAME interpolant the saveat path uses (Tsit5: free 4th-order, Vern7:
+        order 6, Rosenbrock23: its own, Rodas: cubic Hermite): saveat points do not influence the step sequence, so
+        re-running this one trajectory on the device with saveat = t returns exactly the value the dense output of the
+        original run has at t -- no per-step storage of stage vectors."""
+        if self._dense is None:
+            raise ValueError("this solution was computed without dense=True")
+        tt = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        order = np.argsort(tt, kind="stable")
+        vals = self._dense(tt[order])
+        out = np.empty_like(vals)
+        out[order] = vals
+        if self._scalar:
+            out = out[:, 0]
+        return out[0] if np.ndim(t) == 0 else out
 
     def __getitem__(self, i):
         return self.u[i]
@@ -222,7 +241,7 @@ class EnsembleSolution:
     """EnsembleSolution (qa.jl:52): sol.u[i] / sol[i] is trajectory i's ODESolution.  The raw
     gathered arrays stay available as u_array [N, n_save, n_state], retcodes [N], stats [N,4]."""
 
-    def __init__(self, t, u_array, retcodes, stats, elapsed, timing, scalar=False):
+    def __init__(self, t, u_array, retcodes, stats, elapsed, timing, scalar=False, dense=None):
         self.t = t
         self.u_array = u_array
         self.retcodes = retcodes
@@ -231,13 +250,15 @@ class EnsembleSolution:
         self.timing = timing
         self.converged = bool(np.all(retcodes == ReturnCode.Success))
         self._scalar = scalar
+        self._dense = dense   # dense(i, times) -> [len(times), n_state] of trajectory i, or None
 
     def __len__(self):
         return self.u_array.shape[0]
 
     def __getitem__(self, i):
+        dense = None if self._dense is None else (lambda tt, _i=int(i): self._dense(_i, tt))
         return ODESolution(self.t, self.u_array[i], self.retcodes[i], None if self.stats is None else self.stats[i],
-                           self._scalar)
+                           self._scalar, dense)
 
     @property
     def u(self):
@@ -375,9 +396,13 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, 
     A plain ODEProblem/SDEProblem is solved as a one-trajectory ensemble and returns its ODESolution."""
     if kwargs:
         raise TypeError(f"solve: unsupported keyword arguments {sorted(kwargs)}")
-    if save_everystep or dense:
-        raise NotImplementedError("EnsembleB200 saves at `saveat` points only (fixed-size output); "
-                                  "save_everystep/dense=true are not supported")
+    if save_everystep:
+        raise NotImplementedError("EnsembleB200 saves at `saveat` points only (fixed-size output); save_everystep=true "
+                                  "is not supported -- use dense=True and evaluate sol(t), or pass saveat")
+    if dense and save_tstops:
+        raise ValueError("dense=True needs interpolated saves (save_tstops=False): tstops would change the step sequence")
+    if dense and dW is not None:
+        raise NotImplementedError("dense=True with injected noise increments")
     single = not isinstance(prob, EnsembleProblem)
     eprob = EnsembleProblem(prob) if single else prob
     if single:
@@ -424,6 +449,8 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, 
             o.interp_points = int(ccb.interp_points)
     if save_tstops is not None:
         o.save_tstops = int(save_tstops)
+    if dense:
+        o.save_tstops = 0   # every save point (now and in sol(t)) goes through the interpolant
     if ensemblealg.devices is not None:
         mask = 0
         for g in ensemblealg.devices:
@@ -444,7 +471,18 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, 
     elapsed = time.perf_counter() - t_solve
     timing = tm.asdict()
     timing["prob_func_s"] = t_pack
-    sol = EnsembleSolution(ts, out, rc, stats, elapsed, timing, scalar=base.scalar)
+    dense_fn = None
+    if dense:
+        def dense_fn(i, tt, _o=o, _u0=u0, _p=p, _off=int(o.traj_offset)):
+            tt = np.asarray(tt, dtype=np.float64)
+            if tt.size and (tt.min() < base.tspan[0] or tt.max() > base.tspan[1]):
+                raise ValueError("sol(t): t outside tspan")
+            o2 = _lib.copy_opts(_o)
+            o2.traj_offset = _off + i            # same Philox stream as in the ensemble run (SDE paths)
+            o2.work_order = 0
+            out1, rc1, _, _ = model.solve(o2, _u0[i:i + 1], _p[i:i + 1], tt.astype(dtype))
+            return out1[0].astype(np.float64) if dtype != np.float64 else out1[0]
+    sol = EnsembleSolution(ts, out, rc, stats, elapsed, timing, scalar=base.scalar, dense=dense_fn)
     if single:
         return sol[0]
     if eprob.output_func is not None:

@@ -246,3 +246,31 @@ def test_shared_memory_stage_vectors_bit_identical(B, gpu_lib, alg):
         assert b.timing["smem_bytes"] > 0   # (the default may pick either storage, depending on ptxas spills)
         assert np.array_equal(a.u_array, b.u_array) and np.array_equal(a.stats, b.stats)
         assert np.all(a.retcodes == 1)
+
+
+def test_reference_dense_solution_interpolation(B, gpu_lib, oracle):
+    """test/core.jl:51-58: sol = solve(prob, Tsit5(), dense = true); sol(0.5) isa Number and > 0.5.
+    sol(t) must be the value of the run's own dense output: identical to saving at t in the first place."""
+    from b200ens import workloads as W
+
+    prob = B.ODEProblem(lambda u, p, t: [1.01 * u[0]], 0.5, (0.0, 1.0))
+    sol = B.solve(prob, B.Tsit5(), dense=True)
+    assert sol.retcode == B.ReturnCode.Success
+    v = sol(0.5)
+    assert np.ndim(v) == 0 and v > 0.5
+    assert abs(v - 0.5 * np.exp(1.01 * 0.5)) < 1e-5
+    tt = np.array([0.9, 0.1, 0.5, 0.0, 1.0])
+    ref = B.solve(prob, B.Tsit5(), saveat=np.sort(tt))
+    assert np.array_equal(np.sort(sol(tt)), np.asarray(ref.u))     # exponential growth: sorted by time == sorted by value
+    with pytest.raises(ValueError):
+        B.solve(prob, B.Tsit5())(0.5)
+    # ensemble: every trajectory has its own dense output; Vern7 and an event in the step sequence
+    N = 64
+    u0, p = W.net16_params(N)
+    eprob = B.EnsembleProblem(W.net16_problem(), u0s=u0, ps=p)
+    kw = dict(trajectories=N, dt=0.01, abstol=1e-8, reltol=1e-8, callback=W.net16_callback())
+    es = B.solve(eprob, B.Vern7(), B.EnsembleB200(), dense=True, **kw)
+    times = np.array([0.37, 3.3, 9.99])
+    direct = B.solve(eprob, B.Vern7(), B.EnsembleB200(), saveat=times, **kw)
+    for i in (0, 17, 63):
+        assert np.array_equal(es[i](times), direct.u_array[i])

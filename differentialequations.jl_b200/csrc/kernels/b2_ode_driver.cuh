@@ -191,6 +191,21 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                             const float r = __fdiv_rn((float)ut[i], (float)sk);
                             acc = __fmaf_rn(r, r, acc);
                         }
+#if B2_F64
+                        // The Float32 ratio overflows to inf/inf = NaN when a wildly unstable attempt produces |u| beyond
+                        // the Float32 range although the Float64 ratio is an ordinary number (Robertson, Rodas5P, first
+                        // step of the automatic dt: |u_new| ~ 1e185, EEst ~ 1e3 -> must be REJECTED, not DtNaN).  Rare
+                        // slow path: form the ratios in the working precision.  Genuine NaNs stay NaN.
+                        if (acc != acc) {
+                            acc = 0.0f;
+#pragma unroll
+                            for (int i = 0; i < B2_N; i++) {
+                                const real sk = b2_fma(b2_max(b2_abs(u[i]), b2_abs(un[i])), reltol, abstol);
+                                const float r = (float)(ut[i] / sk);
+                                acc = __fmaf_rn(r, r, acc);
+                            }
+                        }
+#endif
                         const float EE2 = __fmul_rn(acc, inv_n);
                         // Branch-free accept/reject: rejections are rare per lane (3 %) but some lane of the warp
                         // rejects in 37 % of the iterations, so a separate reject path costs every warp ~36 extra

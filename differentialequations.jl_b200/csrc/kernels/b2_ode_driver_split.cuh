@@ -240,6 +240,26 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                 const float ri = rb[i * 32];
                 acc = __fmaf_rn(ri, ri, acc);
             }
+#if B2_F64
+            // Float32 overflow of a finite Float64 ratio (see b2_ode_driver.cuh).  The slow path contains an exchange, so
+            // the whole CTA takes it when any lane needs it (every warp holds the same acc per lane).
+            if (__syncthreads_or(acc != acc)) {
+                float r2[B2_NL];
+#pragma unroll
+                for (int j = 0; j < B2_NL; j++) {
+                    const real sk = b2_fma(b2_max(b2_abs(u[j]), b2_abs(un[j])), reltol, abstol);
+                    r2[j] = (float)(ut[j] / sk);
+                }
+                const float* rb2 = b2_split_publish(alg.xc, r2);
+                float acc2 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < B2_N; i++) {
+                    const float ri = rb2[i * 32];
+                    acc2 = __fmaf_rn(ri, ri, acc2);
+                }
+                if (acc != acc) acc = acc2;
+            }
+#endif
             const float EE2 = __fmul_rn(acc, inv_n);
             const bool isn = EE2 != EE2;
             const bool ok = EE2 <= 1.0f;

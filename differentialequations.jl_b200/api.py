@@ -175,11 +175,13 @@ class EnsembleProblem:
     change u0 and p.  Extension (SURVEY 7.3 'host-side prob_func'): `u0s` / `ps` matrices
     [N, n] can be given directly, skipping N host calls of prob_func."""
 
-    def __init__(self, prob, prob_func=None, output_func=None, reduction=None, u0s=None, ps=None, safetycopy=False):
+    def __init__(self, prob, prob_func=None, output_func=None, reduction=None, u_init=None, u0s=None, ps=None,
+                 safetycopy=False):
         self.prob = prob
         self.prob_func = prob_func
-        self.output_func = output_func
-        self.reduction = reduction
+        self.output_func = output_func     # (sol, i) -> (out, rerun)
+        self.reduction = reduction         # (u, batch_data, I) -> (u, converged)
+        self.u_init = u_init               # initial value of the reduction (upstream default: empty vector)
         self.u0s = u0s
         self.ps = ps
 
@@ -366,13 +368,14 @@ def _saveat_array(saveat, tspan, dtype):
     return ts.astype(dtype)
 
 
-def _pack(eprob, N, dtype):
-    """Run prob_func on the host (as EnsembleThreads / EnsembleGPUKernel do) -> u0 [N,n], p [N,m]."""
+def _pack(eprob, N, dtype, lo=0, repeat=1):
+    """Run prob_func on the host (as EnsembleThreads / EnsembleGPUKernel do) for trajectories lo+1 .. lo+N (1-based
+    like Julia) -> u0 [N,n], p [N,m]."""
     prob = eprob.prob
     n, m = prob.u0.shape[0], prob.p.shape[0]
     if eprob.u0s is not None or eprob.ps is not None:
-        u0 = np.broadcast_to(prob.u0, (N, n)) if eprob.u0s is None else np.asarray(eprob.u0s).reshape(N, n)
-        p = np.broadcast_to(prob.p, (N, m)) if eprob.ps is None else np.asarray(eprob.ps).reshape(N, m)
+        u0 = np.broadcast_to(prob.u0, (N, n)) if eprob.u0s is None else np.asarray(eprob.u0s).reshape(-1, n)[lo:lo + N]
+        p = np.broadcast_to(prob.p, (N, m)) if eprob.ps is None else np.asarray(eprob.ps).reshape(-1, m)[lo:lo + N]
         return u0, p
     u0 = np.empty((N, n), dtype=dtype)
     p = np.empty((N, m), dtype=dtype)
@@ -381,7 +384,7 @@ def _pack(eprob, N, dtype):
         p[:] = prob.p
         return u0, p
     for i in range(N):
-        pi = eprob.prob_func(prob, i + 1, 1)
+        pi = eprob.prob_func(prob, lo + i + 1, repeat)
         if pi.f is not prob.f or pi.tspan != prob.tspan:
             raise ValueError("EnsembleB200: prob_func may only change u0 and p (one compiled kernel per ensemble)")
         u0[i] = pi.u0
@@ -389,11 +392,70 @@ def _pack(eprob, N, dtype):
     return u0, p
 
 
-def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, abstol=None, reltol=None,
-          adaptive=None, callback=None, maxiters=None, save_everystep=False, dense=False, seed=0, dW=None,
-          save_tstops=None, summary=False, **kwargs):
-    """solve(eprob, alg, EnsembleB200(); trajectories, saveat, dt, abstol, reltol, ...) -> EnsembleSolution.
-    A plain ODEProblem/SDEProblem is solved as a one-trajectory ensemble and returns its ODESolution."""
+class ReducedEnsembleSolution:
+    """EnsembleSolution of a run with output_func / reduction / batch_size: `u` is what the reduction built
+    (upstream: EnsembleSolution(u, elapsedTime, converged)), `converged` the flag the last reduction call returned."""
+
+    def __init__(self, u, elapsed, converged, batches):
+        self.u = u
+        self.elapsedTime = elapsed
+        self.converged = converged
+        self.batches = batches     # number of batches actually solved (early exit when the reduction converged)
+
+    def __len__(self):
+        return len(self.u)
+
+    def __getitem__(self, i):
+        return self.u[i]
+
+
+def solve(prob, alg, ensemblealg=None, trajectories=None, batch_size=None, **kw):
+    """solve(eprob, alg, EnsembleB200(); trajectories, batch_size=trajectories, saveat, dt, abstol, reltol, ...).
+
+    Mirrors SciMLBase.__solve(::AbstractEnsembleProblem, alg, ensemblealg; trajectories, batch_size) (qa.jl:56,192;
+    SURVEY 3.3): the trajectories are solved in batches of `batch_size`; every solution goes through
+    `output_func(sol, i) -> (out, rerun)` (rerun: the trajectory is solved again with prob_func(prob, i, repeat + 1)),
+    every batch through `u, converged = reduction(u, batch_data, I)` starting from `u_init`, and the loop stops early
+    when the reduction reports convergence.  Without output_func / reduction / batch_size the whole ensemble is ONE
+    device solve and the raw EnsembleSolution (arrays) is returned.  A plain ODEProblem/SDEProblem is solved as a
+    one-trajectory ensemble and returns its ODESolution."""
+    eprob = prob if isinstance(prob, EnsembleProblem) else None
+    if eprob is None or (eprob.output_func is None and eprob.reduction is None and batch_size is None) or kw.get("summary"):
+        return _solve_once(prob, alg, ensemblealg, trajectories, **kw)
+    if trajectories is None:
+        raise TypeError("solve(::EnsembleProblem, ...) needs `trajectories`")
+    N = int(trajectories)
+    bs = N if batch_size is None else max(1, int(batch_size))
+    output_func = eprob.output_func or (lambda sol, i: (sol, False))
+    reduction = eprob.reduction or (lambda u, data, I: (u + list(data), False))
+    u = [] if eprob.u_init is None else eprob.u_init
+    t_all = time.perf_counter()
+    converged, batches = False, 0
+    for lo in range(0, N, bs):
+        n_b = min(bs, N - lo)
+        bsol = _solve_once(eprob, alg, ensemblealg, n_b, _lo=lo, **kw)
+        data = []
+        for j in range(n_b):
+            out, rerun = output_func(bsol[j], lo + j + 1)
+            repeat = 1
+            while rerun:
+                repeat += 1
+                if repeat > 100:
+                    raise RuntimeError("output_func keeps asking for a rerun (100 repeats)")
+                one = _solve_once(eprob, alg, ensemblealg, 1, _lo=lo + j, _repeat=repeat, **kw)
+                out, rerun = output_func(one[0], lo + j + 1)
+            data.append(out)
+        u, converged = reduction(u, data, range(lo + 1, lo + n_b + 1))
+        batches += 1
+        if converged:
+            break
+    return ReducedEnsembleSolution(u, time.perf_counter() - t_all, bool(converged), batches)
+
+
+def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, abstol=None, reltol=None,
+                adaptive=None, callback=None, maxiters=None, save_everystep=False, dense=False, seed=0, dW=None,
+                save_tstops=None, summary=False, _lo=0, _repeat=1, **kwargs):
+    """One device solve of trajectories _lo+1 .. _lo+trajectories of the ensemble."""
     if kwargs:
         raise TypeError(f"solve: unsupported keyword arguments {sorted(kwargs)}")
     if save_everystep:
@@ -428,7 +490,7 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, 
                         ensemblealg.stage_vectors_in_smem, ensemblealg.split)
     ts = _saveat_array(saveat, base.tspan, dtype)
     t_pack = time.perf_counter()
-    u0, p = _pack(eprob, N, dtype)
+    u0, p = _pack(eprob, N, dtype, _lo, _repeat)
     t_pack = time.perf_counter() - t_pack
 
     o = _lib.default_opts()
@@ -441,6 +503,7 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, 
     if maxiters is not None:
         o.maxiters = int(maxiters)
     o.seed = int(seed)
+    o.traj_offset = int(_lo)    # global trajectory index of this batch's first trajectory (Philox counter base)
     o.noise_injected = 0 if dW is None else 1
     if callback is not None:
         o.event_terminate = int(model.event_terminate)
@@ -485,14 +548,4 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, 
     sol = EnsembleSolution(ts, out, rc, stats, elapsed, timing, scalar=base.scalar, dense=dense_fn)
     if single:
         return sol[0]
-    if eprob.output_func is not None:
-        outs = []
-        for i in range(N):
-            val, rerun = eprob.output_func(sol[i], i + 1)
-            if rerun:
-                raise NotImplementedError("output_func requested rerun; not supported by EnsembleB200")
-            outs.append(val)
-        if eprob.reduction is not None:
-            outs, _ = eprob.reduction([], outs, range(1, N + 1))
-        sol.outputs = outs
     return sol

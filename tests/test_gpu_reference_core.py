@@ -86,3 +86,53 @@ def test_saveat(B, gpu_lib):                              # core.jl:90-96
     sol = B.solve(prob, B.Tsit5(), saveat=0.1)
     assert sol.retcode == B.ReturnCode.Success
     assert len(sol.t) == 11
+
+
+def test_ensemble_batches_output_func_reduction(B, gpu_lib):
+    """EnsembleProblem(prob; prob_func, output_func, reduction, u_init) + solve(...; trajectories, batch_size)
+    (qa.jl:50,56): batches, global 1-based indices, rerun with repeat+1, early exit on convergence."""
+    from b200ens import workloads as W
+
+    base = W.lorenz_problem(np.float64, (0.0, 1.0))
+    calls = []
+
+    def prob_func(prob, i, repeat):
+        calls.append((i, repeat))
+        return B.remake(prob, p=[10.0, 20.0 + i * 0.01 + (5.0 if repeat > 1 else 0.0), 8 / 3])
+
+    def output_func(sol, i):
+        rerun = (i == 3) and (i, 2) not in calls          # ask once for a rerun of trajectory 3
+        return (float(sol.u[-1][0]), i), rerun
+
+    seen = []
+
+    def reduction(u, data, I):
+        seen.append((list(I)[0], list(I)[-1], len(data)))
+        u = u + [d[0] for d in data]
+        return u, len(u) >= 200                            # converged after two batches of 100
+
+    eprob = B.EnsembleProblem(base, prob_func=prob_func, output_func=output_func, reduction=reduction, u_init=[])
+    sol = B.solve(eprob, B.Tsit5(), B.EnsembleB200(), trajectories=250, batch_size=100, saveat=[1.0], dt=0.01)
+    assert sol.converged and sol.batches == 2 and len(sol.u) == 200
+    assert seen == [(1, 100, 100), (101, 200, 100)]
+    assert (3, 2) in calls and max(i for i, _ in calls) == 200          # batch 3 never ran, trajectory 3 was rerun
+    # values: same as one plain solve of the same parameters (trajectory 3 with its rerun parameters)
+    ps = np.array([[10.0, 20.0 + i * 0.01 + (5.0 if i == 3 else 0.0), 8 / 3] for i in range(1, 201)])
+    ref = B.solve(B.EnsembleProblem(base, ps=ps), B.Tsit5(), B.EnsembleB200(), trajectories=200, saveat=[1.0], dt=0.01)
+    assert np.array_equal(np.array(sol.u), ref.u_array[:, -1, 0])
+    # default output_func / reduction with batch_size: a list of per-trajectory solutions
+    sol2 = B.solve(B.EnsembleProblem(base, ps=ps), B.Tsit5(), B.EnsembleB200(), trajectories=200, batch_size=64, saveat=[1.0], dt=0.01)
+    assert len(sol2.u) == 200 and not sol2.converged and sol2.batches == 4
+    assert np.array_equal(np.array([s.u[-1] for s in sol2.u]), ref.u_array[:, -1, :])
+
+
+def test_sde_batches_share_the_global_noise_streams(B, gpu_lib):
+    """Philox counters are keyed by the GLOBAL trajectory index: solving in batches gives the same paths."""
+    from b200ens import workloads as W
+
+    N = 300
+    u0, p = W.gbm_params(N)
+    eprob = B.EnsembleProblem(W.gbm_problem(), u0s=u0, ps=p)
+    one = B.solve(eprob, B.EM(), B.EnsembleB200(), trajectories=N, saveat=[1.0], dt=1 / 64, seed=11)
+    parts = B.solve(eprob, B.EM(), B.EnsembleB200(), trajectories=N, batch_size=128, saveat=[1.0], dt=1 / 64, seed=11)
+    assert np.array_equal(np.array([s.u[-1] for s in parts.u]).reshape(N), one.u_array[:, -1, 0])

@@ -17,14 +17,15 @@ include/b200ens.h; this module only traces the model functions to CUDA C (codege
 packs the per-trajectory u0/p matrices and wraps the outputs.  No CPU fallback exists.
 """
 from . import _lib, codegen
+from . import analysis as EnsembleAnalysis
 from ._lib import B200EnsError, Model, pinned_empty
 from .api import (EM, SOSRA, CallbackSet, ContinuousCallback, DiscreteCallback, EnsembleB200, EnsembleProblem, EnsembleSolution,
                   EnsembleSummary, ODEProblem,
                   ODESolution, ReturnCode, Rodas4, Rodas5, Rodas5P, Rosenbrock23, SDEProblem, Tsit5, Vern7,
-                  build_model, remake, solve, terminate_b)
+                  ReducedEnsembleSolution, build_model, remake, solve, terminate_b)
 
 __all__ = [
     "ODEProblem", "SDEProblem", "EnsembleProblem", "EnsembleB200", "EnsembleSolution", "EnsembleSummary", "ODESolution", "ReturnCode",
     "ContinuousCallback", "DiscreteCallback", "CallbackSet", "remake", "solve", "terminate_b", "Tsit5", "Vern7", "Rosenbrock23", "Rodas4", "Rodas5",
-    "Rodas5P", "EM", "SOSRA", "build_model", "Model", "B200EnsError", "pinned_empty",
+    "Rodas5P", "EM", "SOSRA", "build_model", "Model", "B200EnsError", "pinned_empty", "EnsembleAnalysis", "ReducedEnsembleSolution",
 ]

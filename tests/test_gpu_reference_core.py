@@ -136,3 +136,22 @@ def test_sde_batches_share_the_global_noise_streams(B, gpu_lib):
     one = B.solve(eprob, B.EM(), B.EnsembleB200(), trajectories=N, saveat=[1.0], dt=1 / 64, seed=11)
     parts = B.solve(eprob, B.EM(), B.EnsembleB200(), trajectories=N, batch_size=128, saveat=[1.0], dt=1 / 64, seed=11)
     assert np.array_equal(np.array([s.u[-1] for s in parts.u]).reshape(N), one.u_array[:, -1, 0])
+
+
+def test_ensemble_analysis_on_a_device_run(B, gpu_lib):
+    """EnsembleAnalysis over a real ensemble; timestep_meanvar agrees with the on-device summary
+    (b200ens_solve_moments); timepoint_* off the save grid go through the trajectories' dense output."""
+    from b200ens import EnsembleAnalysis as EA
+    from b200ens import workloads as W
+
+    N = 2000
+    u0, p = W.lorenz_params(N, "random", seed=2)
+    eprob = B.EnsembleProblem(W.lorenz_problem(np.float64, (0.0, 2.0)), u0s=u0, ps=p)
+    kw = dict(trajectories=N, saveat=0.5, dt=0.05)
+    sim = B.solve(eprob, B.Tsit5(), B.EnsembleB200(), dense=True, **kw)
+    summ = B.solve(eprob, B.Tsit5(), B.EnsembleB200(), summary=True, **kw)
+    m, v = EA.timeseries_steps_meanvar(sim)
+    assert np.allclose(m, summ.u, rtol=1e-12, atol=1e-12) and np.allclose(v, summ.v, rtol=1e-9, atol=1e-12)
+    direct = B.solve(eprob, B.Tsit5(), B.EnsembleB200(), trajectories=N, saveat=[0.73], dt=0.05)
+    sub = B.EnsembleSolution(sim.t, sim.u_array[:50], sim.retcodes[:50], None, 0.0, {}, dense=sim._dense)
+    assert np.array_equal(EA.timepoint_mean(sub, 0.73), direct.u_array[:50, 0].mean(axis=0))

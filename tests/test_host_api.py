@@ -131,3 +131,35 @@ def test_kernel_resources_do_not_depend_on_the_ptxas_log():
         outs.append(json.loads(subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().splitlines()[-1]))
     assert outs[0] == outs[1]
     assert all(o["regs"] > 0 and o["lmem"] == 0 for o in outs[0])
+
+
+def test_ensemble_analysis_functions():
+    """EnsembleAnalysis (qa.jl:211) on a synthetic EnsembleSolution: names and conventions of the upstream module
+    (1-based timestep index, sample variance)."""
+    import b200ens as B
+    from b200ens import EnsembleAnalysis as EA
+
+    rng = np.random.default_rng(0)
+    N, ns, n = 500, 4, 3
+    arr = rng.normal(size=(N, ns, n))
+    t = np.array([0.0, 0.5, 1.0, 2.0])
+    sim = B.EnsembleSolution(t, arr, np.ones(N, dtype=np.int32), None, 0.0, {})
+    assert np.allclose(EA.timestep_mean(sim, 2), arr[:, 1].mean(0))
+    m, v = EA.timestep_meanvar(sim, 4)
+    assert np.allclose(m, arr[:, 3].mean(0)) and np.allclose(v, arr[:, 3].var(0, ddof=1))
+    assert np.allclose(EA.timestep_median(sim, 1), np.median(arr[:, 0], 0))
+    assert np.allclose(EA.timestep_quantile(sim, 0.9, 3), np.quantile(arr[:, 2], 0.9, axis=0))
+    ma, mb, cov = EA.timestep_meancov(sim, 1, 2)
+    assert np.allclose(cov, [np.cov(arr[:, 0, k], arr[:, 1, k])[0, 1] for k in range(n)])
+    _, _, cor = EA.timestep_meancor(sim, 1, 2)
+    assert np.allclose(cor, [np.corrcoef(arr[:, 0, k], arr[:, 1, k])[0, 1] for k in range(n)])
+    assert EA.timeseries_steps_mean(sim).shape == (ns, n)
+    mm, vv = EA.timeseries_steps_meanvar(sim)
+    assert np.allclose(vv, arr.var(0, ddof=1))
+    assert np.allclose(EA.timepoint_mean(sim, 0.5), arr[:, 1].mean(0))          # a save point
+    assert len(list(EA.get_timestep(sim, 1))) == N and len(EA.componentwise_vectors_timestep(sim, 1)) == n
+    with pytest.raises(ValueError):
+        EA.timepoint_mean(sim, 0.7)                                             # neither a save point nor dense
+    with pytest.raises(IndexError):
+        EA.timestep_mean(sim, 5)
+    assert np.allclose(EA.timeseries_point_mean(sim, [0.0, 2.0]), arr[:, [0, 3]].mean(0))

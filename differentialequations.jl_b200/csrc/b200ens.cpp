@@ -584,7 +584,9 @@ int check_opts(const b200ens_model* m, const b200ens_opts* o, int n_save, const 
 
 int launch(b200ens_model* m, const LaunchPlan& lp, const B2Args& a, cudaStream_t stream) {
     void* params[] = {(void*)&a};
-    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && !a.save_tstops && a.dt > 0 && a.stage_stride == 0) ? m->kernel_adaptive : m->kernel;
+    // the specialised entry keeps 32-bit output offsets in its Float32 save queue: fall back to the generic entry beyond 2^32 elements
+    const bool off32_ok = m->dtype == B200ENS_F64 || (unsigned long long)a.N * (unsigned long long)a.n_save * m->n_state < (1ull << 32);
+    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && !a.save_tstops && a.dt > 0 && a.stage_stride == 0 && off32_ok) ? m->kernel_adaptive : m->kernel;
     if (k != m->kernel && lp.smem > 48 * 1024)
         CU(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, lp.smem));
     CU(cudaLaunchKernel((const void*)k, dim3(lp.grid), dim3(lp.block), params, lp.smem, stream));

@@ -61,9 +61,15 @@ def test_packed_ffma2_kernel_bit_identical(B, gpu_lib, oracle):
     so the result must equal the scalar kernel's and the oracle's bit for bit."""
     from b200ens import workloads as W
 
+    nv = gpu_lib.lib().b200ens_nvrtc_info().decode()
+    if not nv.startswith("12.8 "):
+        # the library only honours PACKED_X2 under the ptxas it is bit-exact with (12.8); under 12.9 identical PTX gives
+        # ~1e-6 relative differences, so the request falls through to the scalar kernel and this test would be vacuous
+        pytest.skip(f"packed FP32x2 kernel is gated to NVRTC 12.8 (loaded: {nv})")
     N = 20011
     u0, p = W.lorenz_params(N, "random", seed=9, dtype=np.float32)
     packed = _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1, packed_x2=True)
+    assert packed.timing["regs"] > 100, "the packed kernel did not run"
     ref, rc, st = oracle.solve("lorenz", "Tsit5", u0, p, (0.0, 10.0), SAVEAT, 0.1, dtype=np.float32)
     assert np.array_equal(packed.retcodes, rc)
     assert np.array_equal(packed.stats[:, :3], st[:, :3])

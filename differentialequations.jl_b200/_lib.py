@@ -47,6 +47,7 @@ class Opts(C.Structure):
         ("save_tstops", C.c_int32), ("device_mask", C.c_uint32), ("refill_threshold", C.c_int32),
         ("block_threads", C.c_int32), ("stage_outputs", C.c_int32),
         ("work_order", C.c_int32), ("reserved0", C.c_int32),
+        ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double)),
     ]
 
 
@@ -113,7 +114,7 @@ def lib():
     L.b200ens_host_alloc.restype = C.c_void_p
     L.b200ens_host_free.argtypes = [C.c_void_p]
     L.b200ens_host_free.restype = None
-    if L.b200ens_abi_version() != 2:
+    if L.b200ens_abi_version() != 3:
         raise ImportError("libb200ens ABI version mismatch")
     _lib = L
     return L
@@ -227,6 +228,7 @@ def copy_opts(o):
     """A by-value copy of a b200ens_opts struct."""
     c = Opts()
     C.memmove(C.byref(c), C.byref(o), C.sizeof(Opts))
+    c._tol_keep = getattr(o, "_tol_keep", None)   # keep per-component tolerance arrays alive with the copy
     return c
 
 

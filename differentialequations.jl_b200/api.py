@@ -496,10 +496,20 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
     o = _lib.default_opts()
     o.adaptive = int(bool(adaptive))
     o.t0, o.t1, o.dt = base.tspan[0], base.tspan[1], float(dt)
-    if abstol is not None:
-        o.abstol = float(abstol)
-    if reltol is not None:
-        o.reltol = float(reltol)
+    # abstol / reltol: scalars, or one value per state component (solve(prob, Rodas5P(); abstol = [1e-8, 1e-14, 1e-6]))
+    tol_keep = []
+    for name, val in (("abstol", abstol), ("reltol", reltol)):
+        if val is None:
+            continue
+        if np.ndim(val) == 0:
+            setattr(o, name, float(val))
+        else:
+            vec = np.ascontiguousarray(val, dtype=np.float64)
+            if vec.shape != (base.u0.shape[0],):
+                raise ValueError(f"{name} must be a scalar or have one entry per state component")
+            tol_keep.append(vec)
+            setattr(o, name + "_vec", vec.ctypes.data_as(_lib.C.POINTER(_lib.C.c_double)))
+    o._tol_keep = tol_keep   # the arrays must outlive every solve that uses these options (dense re-solves too)
     if maxiters is not None:
         o.maxiters = int(maxiters)
     o.seed = int(seed)

@@ -78,6 +78,8 @@ struct B2Args {
     float f_t0, f_t1, f_dt, f_abstol, f_reltol, f_dtmin, f_dtmax, f_qmin, f_qmax, f_gamma, f_beta1, f_beta2, f_qoldinit;
     int pad0_;
     const unsigned* perm;
+    double tol_a[32], tol_r[32];
+    float f_tol_a[32], f_tol_r[32];
 };
 
 bool is_sde(int alg) { return alg == B200ENS_EM || alg == B200ENS_SOSRA; }
@@ -568,6 +570,15 @@ int fill_args(const b200ens_model* m, const b200ens_opts* o, B2Args* a) {
     a->f_beta1 = (float)a->beta1;
     a->f_beta2 = (float)a->beta2;
     a->f_qoldinit = (float)a->qoldinit;
+    for (int i = 0; i < 32; i++) {
+        const int c = i < m->n_state ? i : m->n_state - 1;
+        const double ta = o->abstol_vec ? o->abstol_vec[c] : a->abstol, tr = o->reltol_vec ? o->reltol_vec[c] : a->reltol;
+        if (!(ta >= 0) || !(tr >= 0) || !(ta + tr > 0)) return fail(B200ENS_E_INVALID, "tolerances must be >= 0 and not both 0 (component %d)", c);
+        a->tol_a[i] = ta;
+        a->tol_r[i] = tr;
+        a->f_tol_a[i] = (float)ta;
+        a->f_tol_r[i] = (float)tr;
+    }
     a->nsteps_noise = is_sde(m->alg) ? (long long)std::ceil((o->t1 - o->t0) / o->dt - 1e-9) : 0;
     return 0;
 }

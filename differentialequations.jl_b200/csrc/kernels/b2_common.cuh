@@ -110,12 +110,20 @@ struct B2Args {
     float f_t0, f_t1, f_dt, f_abstol, f_reltol, f_dtmin, f_dtmax, f_qmin, f_qmax, f_gamma, f_beta1, f_beta2, f_qoldinit;
     int pad0_;
     const unsigned* perm;  // queue position -> trajectory index (expected-work order, b2_work.cuh) or null = identity
+    // per-component tolerances (solve(...; abstol = [..], reltol = [..]); scalars are broadcast by the host).  Read with
+    // compile-time indices from the constant bank: no registers, FMA constant operands.
+    double tol_a[32], tol_r[32];
+    float f_tol_a[32], f_tol_r[32];
 };
 
 #if B2_F64
 #define B2_ARG(a, name) ((a).name)
+#define B2_ATOL(a, i) ((a).tol_a[i])
+#define B2_RTOL(a, i) ((a).tol_r[i])
 #else
 #define B2_ARG(a, name) ((a).f_##name)
+#define B2_ATOL(a, i) ((a).f_tol_a[i])
+#define B2_RTOL(a, i) ((a).f_tol_r[i])
 #endif
 
 __device__ __forceinline__ float b2_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }

@@ -84,7 +84,6 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     const int out_per_traj = n_save * B2_N;
 
     const real t0 = B2_ARG(a, t0), t1 = B2_ARG(a, t1), dt_user = B2_ARG(a, dt);
-    const real abstol = B2_ARG(a, abstol), reltol = B2_ARG(a, reltol);
     const real qmax = B2_ARG(a, qmax), qmin = B2_ARG(a, qmin), gam = B2_ARG(a, gamma);
     const float inv_qmax = __fdiv_rn(1.0f, (float)qmax), inv_qmin = __fdiv_rn(1.0f, (float)qmin);
     const float inv_gam = __fdiv_rn(1.0f, (float)gam);
@@ -171,7 +170,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                             real a0 = 0, a1 = 0, a2 = 0, u1[B2_N], f1[B2_N];
 #pragma unroll
                             for (int i = 0; i < B2_N; i++) {
-                                const real sk = b2_fma(b2_abs(u[i]), reltol, abstol);
+                                const real sk = b2_fma(b2_abs(u[i]), B2_RTOL(a, i), B2_ATOL(a, i));
                                 const real r0 = u[i] / sk, r1 = alg.fsal0(i) / sk;
                                 a0 = b2_fma(r0, r0, a0);
                                 a1 = b2_fma(r1, r1, a1);
@@ -185,7 +184,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                             nf++;
 #pragma unroll
                             for (int i = 0; i < B2_N; i++) {
-                                const real sk = b2_fma(b2_abs(u[i]), reltol, abstol);
+                                const real sk = b2_fma(b2_abs(u[i]), B2_RTOL(a, i), B2_ATOL(a, i));
                                 const real r2 = (f1[i] - alg.fsal0(i)) / sk;
                                 a2 = b2_fma(r2, r2, a2);
                             }
@@ -255,7 +254,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                         float acc = 0.0f;
 #pragma unroll
                         for (int i = 0; i < B2_N; i++) {
-                            const real sk = b2_fma(b2_max(b2_abs(u[i]), b2_abs(un[i])), reltol, abstol);
+                            const real sk = b2_fma(b2_max(b2_abs(u[i]), b2_abs(un[i])), B2_RTOL(a, i), B2_ATOL(a, i));
                             const float r = __fdiv_rn((float)ut[i], (float)sk);
                             acc = __fmaf_rn(r, r, acc);
                         }
@@ -268,7 +267,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                             acc = 0.0f;
 #pragma unroll
                             for (int i = 0; i < B2_N; i++) {
-                                const real sk = b2_fma(b2_max(b2_abs(u[i]), b2_abs(un[i])), reltol, abstol);
+                                const real sk = b2_fma(b2_max(b2_abs(u[i]), b2_abs(un[i])), B2_RTOL(a, i), B2_ATOL(a, i));
                                 const float r = (float)(ut[i] / sk);
                                 acc = __fmaf_rn(r, r, acc);
                             }

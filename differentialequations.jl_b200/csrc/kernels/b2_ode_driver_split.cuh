@@ -48,7 +48,6 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     const long long out_per_traj = (long long)n_save * B2_N;
 
     const real t0 = B2_ARG(a, t0), t1 = B2_ARG(a, t1), dt_user = B2_ARG(a, dt);
-    const real abstol = B2_ARG(a, abstol), reltol = B2_ARG(a, reltol);
     const real qmax = B2_ARG(a, qmax), qmin = B2_ARG(a, qmin), gam = B2_ARG(a, gamma);
     const float inv_qmax = __fdiv_rn(1.0f, (float)qmax), inv_qmin = __fdiv_rn(1.0f, (float)qmin);
     const float inv_gam = __fdiv_rn(1.0f, (float)gam);
@@ -59,6 +58,13 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     const bool adaptive = a.adaptive != 0;
     const bool save_tstops = a.save_tstops != 0;
     const real INF = (real)__int_as_float(0x7f800000);
+    real atol[B2_NL], rtol[B2_NL];   // tolerances of the owned components (padded components: any positive value)
+#pragma unroll
+    for (int j = 0; j < B2_NL; j++) {
+        const int c = c0 + j < B2_N ? c0 + j : B2_N - 1;
+        atol[j] = B2_ATOL(a, c);
+        rtol[j] = B2_RTOL(a, c);
+    }
 
     Alg alg;
     alg.bind(nullptr);
@@ -150,7 +156,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                         real r0[B2_NL], r1[B2_NL], r2[B2_NL], u1[B2_NL], f1[B2_NL];
 #pragma unroll
                         for (int j = 0; j < B2_NL; j++) {
-                            const real sk = b2_fma(b2_abs(u[j]), reltol, abstol);
+                            const real sk = b2_fma(b2_abs(u[j]), rtol[j], atol[j]);
                             r0[j] = u[j] / sk;
                             r1[j] = f0[j] / sk;
                         }
@@ -171,7 +177,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                         alg.rhs(f1, u1, p, t0 + dt0);
 #pragma unroll
                         for (int j = 0; j < B2_NL; j++) {
-                            const real sk = b2_fma(b2_abs(u[j]), reltol, abstol);
+                            const real sk = b2_fma(b2_abs(u[j]), rtol[j], atol[j]);
                             r2[j] = (f1[j] - f0[j]) / sk;
                         }
                         {
@@ -230,7 +236,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
             float r[B2_NL];
 #pragma unroll
             for (int j = 0; j < B2_NL; j++) {
-                const real sk = b2_fma(b2_max(b2_abs(u[j]), b2_abs(un[j])), reltol, abstol);
+                const real sk = b2_fma(b2_max(b2_abs(u[j]), b2_abs(un[j])), rtol[j], atol[j]);
                 r[j] = __fdiv_rn((float)ut[j], (float)sk);
             }
             const float* rb = b2_split_publish(alg.xc, r);
@@ -247,7 +253,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                 float r2[B2_NL];
 #pragma unroll
                 for (int j = 0; j < B2_NL; j++) {
-                    const real sk = b2_fma(b2_max(b2_abs(u[j]), b2_abs(un[j])), reltol, abstol);
+                    const real sk = b2_fma(b2_max(b2_abs(u[j]), b2_abs(un[j])), rtol[j], atol[j]);
                     r2[j] = (float)(ut[j] / sk);
                 }
                 const float* rb2 = b2_split_publish(alg.xc, r2);

@@ -59,7 +59,6 @@ __device__ __forceinline__ void b2_ode_driver_x2(const B2Args& a) {
     const long long out_per_traj = (long long)n_save * B2_N;
 
     const float t0 = a.f_t0, t1 = a.f_t1, dt_user = a.f_dt;
-    const real abstol = real(a.f_abstol), reltol = real(a.f_reltol);
     const float qmax = a.f_qmax, qmin = a.f_qmin, gam = a.f_gamma;
     const float inv_qmax = 1.0f / qmax, inv_qmin = 1.0f / qmin, inv_gam = 1.0f / gam;
     const real inv_n = real(1.0f / (float)B2_N);
@@ -172,7 +171,7 @@ __device__ __forceinline__ void b2_ode_driver_x2(const B2Args& a) {
                 real acc = real(0.0f);
 #pragma unroll
                 for (int i = 0; i < B2_N; i++) {
-                    const real sk = b2_fma(b2_max(b2_abs(u[i]), b2_abs(un[i])), reltol, abstol);
+                    const real sk = b2_fma(b2_max(b2_abs(u[i]), b2_abs(un[i])), real(a.f_tol_r[i]), real(a.f_tol_a[i]));
                     const real r = ut[i] / sk;
                     acc = b2_fma(r, r, acc);
                 }

@@ -40,7 +40,7 @@ extern "C" __global__ void __launch_bounds__(256) b2_work_keys(const __grid_cons
     __syncthreads();
     const sreal* const gu0 = reinterpret_cast<const sreal*>(a.u0);
     const sreal* const gp = reinterpret_cast<const sreal*>(a.p);
-    const sreal t0 = B2_ARG(a, t0), abstol = B2_ARG(a, abstol), reltol = B2_ARG(a, reltol);
+    const sreal t0 = B2_ARG(a, t0);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += (long long)gridDim.x * blockDim.x) {
         sreal u[B2_N], p[B2_NPA], f0[B2_N], f1[B2_N], u1[B2_N];
 #pragma unroll
@@ -52,7 +52,7 @@ extern "C" __global__ void __launch_bounds__(256) b2_work_keys(const __grid_cons
         float isk[B2_N];
 #pragma unroll
         for (int j = 0; j < B2_N; j++) {
-            isk[j] = __fdividef(1.0f, (float)b2_fma(b2_abs(u[j]), reltol, abstol));
+            isk[j] = __fdividef(1.0f, (float)b2_fma(b2_abs(u[j]), (sreal)B2_RTOL(a, j), (sreal)B2_ATOL(a, j)));
             const float r0 = (float)u[j] * isk[j], r1 = (float)f0[j] * isk[j];
             a0 = fmaf(r0, r0, a0);
             a1 = fmaf(r1, r1, a1);

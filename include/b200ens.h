@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200ENS_ABI_VERSION 2
+#define B200ENS_ABI_VERSION 3
 
 /* scalar type of u, p, t (Julia eltype(u0)) */
 enum b200ens_dtype { B200ENS_F32 = 0, B200ENS_F64 = 1 };
@@ -117,6 +117,8 @@ typedef struct b200ens_opts {
                                order, 1 integrate trajectories in descending expected-work order (device-side counting
                                sort on the initial-step proxy; scheduling only, results are bit-identical) */
     int32_t reserved0;
+    const double* abstol_vec; /* NULL, or n_state per-component absolute tolerances (solve(...; abstol = [...])); overrides abstol */
+    const double* reltol_vec; /* NULL, or n_state per-component relative tolerances; overrides reltol */
 } b200ens_opts;
 
 typedef struct b200ens_stats {

@@ -55,6 +55,7 @@ typedef struct {
     void *rhs, *jac, *tgrad, *noise, *cond, *affect;
     void *dcond, *daffect;    /* DiscreteCallback: int dcond(u,p,t), daffect(u,p,t); NULL = none */
     int32_t devent_terminate, pad_;
+    const double *abstol_vec, *reltol_vec;   /* NULL, or n_state per-component tolerances (override abstol / reltol) */
 } orc_opts;
 
 /* u0 [N][n], p [N][m], saveat [n_save], out_u [N][n_save][n], retcode [N], stats [N] or NULL.

@@ -32,6 +32,7 @@ class Opts(C.Structure):
         ("rhs", C.c_void_p), ("jac", C.c_void_p), ("tgrad", C.c_void_p), ("noise", C.c_void_p),
         ("cond", C.c_void_p), ("affect", C.c_void_p), ("dcond", C.c_void_p), ("daffect", C.c_void_p),
         ("devent_terminate", C.c_int32), ("pad_", C.c_int32),
+        ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double)),
     ]
 
 
@@ -109,6 +110,13 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
     o = Opts()
     o.alg = ALG[alg]
     o.n_state, o.n_param, o.adaptive = n, m, int(adaptive)
+    keep = []   # per-component tolerances: arrays must outlive the call
+    if np.ndim(abstol) > 0:
+        av = np.ascontiguousarray(abstol, dtype=np.float64); assert av.shape == (n,)
+        keep.append(av); o.abstol_vec = av.ctypes.data_as(C.POINTER(C.c_double)); abstol = float(av[0])
+    if np.ndim(reltol) > 0:
+        rv = np.ascontiguousarray(reltol, dtype=np.float64); assert rv.shape == (n,)
+        keep.append(rv); o.reltol_vec = rv.ctypes.data_as(C.POINTER(C.c_double)); reltol = float(rv[0])
     o.t0, o.t1, o.dt, o.abstol, o.reltol = tspan[0], tspan[1], dt, abstol, reltol
     for k in ("dtmin", "dtmax", "qmin", "qmax", "gamma", "beta1", "beta2", "qoldinit"):
         setattr(o, k, ctl.get(k, -1.0))

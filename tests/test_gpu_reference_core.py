@@ -155,3 +155,43 @@ def test_ensemble_analysis_on_a_device_run(B, gpu_lib):
     direct = B.solve(eprob, B.Tsit5(), B.EnsembleB200(), trajectories=N, saveat=[0.73], dt=0.05)
     sub = B.EnsembleSolution(sim.t, sim.u_array[:50], sim.retcodes[:50], None, 0.0, {}, dense=sim._dense)
     assert np.array_equal(EA.timepoint_mean(sub, 0.73), direct.u_array[:50, 0].mean(axis=0))
+
+
+def test_per_component_tolerances(B, gpu_lib, oracle):
+    """solve(prob, Rodas5P(); reltol = 1e-8, abstol = [1e-8, 1e-14, 1e-6]) -- the standard Robertson call of the
+    DifferentialEquations.jl documentation: per-component tolerances, bit-identical step sequence to the oracle."""
+    from b200ens import workloads as W
+    from helpers import oracle_fns
+
+    N = 200
+    u0, p = W.robertson_params(N)
+    atol = np.array([1e-8, 1e-14, 1e-6])
+    eprob = B.EnsembleProblem(W.robertson_problem(), u0s=u0, ps=p)
+    for alg in ("Rodas5P", "Rosenbrock23"):
+        sol = B.solve(eprob, getattr(B, alg)(), B.EnsembleB200(), trajectories=N, saveat=W.ROBERTSON_SAVEAT, dt=1e-6,
+                      reltol=1e-8, abstol=atol)
+        # the oracle runs the SAME emitted model source (one expression tree on both sides -> identical step sequences)
+        model = B.build_model(W.robertson_problem(), getattr(B, alg)())
+        ref, rc, st = oracle.solve(None, alg, u0, p, (0.0, 1e5), W.ROBERTSON_SAVEAT, 1e-6, abstol=atol, reltol=1e-8,
+                                   fns=oracle_fns(oracle, B, model))
+        assert np.all(sol.retcodes == 1) and np.array_equal(sol.retcodes, rc)
+        assert np.array_equal(sol.stats[:, :3], st[:, :3])
+        assert np.allclose(sol.u_array, ref, rtol=1e-12, atol=1e-300)
+        scal = B.solve(eprob, getattr(B, alg)(), B.EnsembleB200(), trajectories=N, saveat=W.ROBERTSON_SAVEAT, dt=1e-6,
+                       reltol=1e-8, abstol=1e-8)
+        assert not np.array_equal(scal.stats, sol.stats)            # the tight tolerance on y2 costs steps
+    # a vector of equal entries is the scalar case, bit for bit; Tsit5 Float32 and the split kernel take vectors too
+    u0l, pl = W.lorenz_params(1000, "random", seed=4, dtype=np.float32)
+    el = B.EnsembleProblem(W.lorenz_problem(np.float32), u0s=u0l, ps=pl)
+    kw = dict(trajectories=1000, saveat=1.0, dt=0.1)
+    a = B.solve(el, B.Tsit5(), B.EnsembleB200(), abstol=1e-6, reltol=1e-3, **kw)
+    b = B.solve(el, B.Tsit5(), B.EnsembleB200(), abstol=[1e-6] * 3, reltol=[1e-3] * 3, **kw)
+    assert np.array_equal(a.u_array, b.u_array) and np.array_equal(a.stats, b.stats)
+    u0n, pn = W.net16_params(100)
+    en = B.EnsembleProblem(W.net16_problem(), u0s=u0n, ps=pn)
+    av = np.geomspace(1e-10, 1e-6, 16)
+    outs = [B.solve(en, B.Vern7(), B.EnsembleB200(split=sp), trajectories=100, saveat=1.0, dt=0.01, abstol=av, reltol=1e-7,
+                    callback=W.net16_callback()) for sp in (False, True)]
+    assert np.array_equal(outs[0].u_array, outs[1].u_array) and np.array_equal(outs[0].stats, outs[1].stats)
+    with pytest.raises(ValueError):
+        B.solve(el, B.Tsit5(), B.EnsembleB200(), abstol=[1e-6, 1e-6], **kw)

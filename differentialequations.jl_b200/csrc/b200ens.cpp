@@ -363,7 +363,8 @@ int ensure_loaded(b200ens_model* m) {
     // optional entry points are looked up only in modules that define them (kernels/b2_entry.cuh): no failing API
     // calls on the normal path (they show up as errors under compute-sanitizer)
     const bool erk = m->alg == B200ENS_TSIT5 || m->alg == B200ENS_VERN7;
-    if (erk && !m->x2 && !m->split) CU(cudaLibraryGetKernel(&m->kernel_adaptive, m->lib, "b2_ensemble_kernel_adaptive"));
+    if ((erk && !m->x2 && !m->split) || is_rosenbrock(m->alg))
+        CU(cudaLibraryGetKernel(&m->kernel_adaptive, m->lib, "b2_ensemble_kernel_adaptive"));
     if (!is_sde(m->alg) && !m->x2) {
         CU(cudaLibraryGetKernel(&m->k_work_keys, m->lib, "b2_work_keys"));
         CU(cudaLibraryGetKernel(&m->k_work_scatter, m->lib, "b2_work_scatter"));
@@ -597,7 +598,8 @@ int launch(b200ens_model* m, const LaunchPlan& lp, const B2Args& a, cudaStream_t
     void* params[] = {(void*)&a};
     // the specialised entry keeps 32-bit output offsets in its Float32 save queue: fall back to the generic entry beyond 2^32 elements
     const bool off32_ok = m->dtype == B200ENS_F64 || (unsigned long long)a.N * (unsigned long long)a.n_save * m->n_state < (1ull << 32);
-    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && !a.save_tstops && a.dt > 0 && a.stage_stride == 0 && off32_ok) ? m->kernel_adaptive : m->kernel;
+    const bool tstops_ok = !a.save_tstops || is_rosenbrock(m->alg);   // the Rosenbrock entry keeps save_tstops a run-time flag
+    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && tstops_ok && a.dt > 0 && a.stage_stride == 0 && off32_ok) ? m->kernel_adaptive : m->kernel;
     if (k != m->kernel && lp.smem > 48 * 1024)
         CU(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, lp.smem));
     CU(cudaLaunchKernel((const void*)k, dim3(lp.grid), dim3(lp.block), params, lp.smem, stream));

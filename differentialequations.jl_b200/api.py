@@ -135,6 +135,22 @@ class ContinuousCallback:
             raise NotImplementedError("EnsembleB200 needs save_positions=(false,false) (saveat output is fixed-size)")
 
 
+class VectorContinuousCallback:
+    """VectorContinuousCallback(condition, affect!, len) (qa.jl:124): condition(out, u, t, integrator) fills `len`
+    event functions, the earliest root among those that change sign fires and affect!(integrator, idx) receives its
+    1-based index.  Both must be symbolically traceable."""
+
+    def __init__(self, condition, affect, len, interp_points=10, save_positions=(False, False)):
+        self.condition = condition
+        self.affect = affect
+        self.len = int(len)
+        self.interp_points = interp_points
+        if not 1 <= self.len <= 16:
+            raise ValueError("VectorContinuousCallback: len must be in 1..16")
+        if tuple(save_positions) != (False, False):
+            raise NotImplementedError("EnsembleB200 needs save_positions=(false,false) (saveat output is fixed-size)")
+
+
 class DiscreteCallback:
     """DiscreteCallback(condition, affect!) with condition(u,t,integrator)::Bool tested after every accepted step
     (test/core.jl:76-77).  Both functions must be symbolically traceable."""
@@ -150,7 +166,7 @@ class CallbackSet:
     """CallbackSet(cb...) (qa.jl:24): at most one ContinuousCallback and one DiscreteCallback on this back-end."""
 
     def __init__(self, *cbs):
-        self.continuous = [c for c in cbs if isinstance(c, ContinuousCallback)]
+        self.continuous = [c for c in cbs if isinstance(c, (ContinuousCallback, VectorContinuousCallback))]
         self.discrete = [c for c in cbs if isinstance(c, DiscreteCallback)]
         if len(self.continuous) > 1 or len(self.discrete) > 1 or len(self.continuous) + len(self.discrete) != len(cbs):
             raise NotImplementedError("EnsembleB200 supports one ContinuousCallback plus one DiscreteCallback")
@@ -159,7 +175,7 @@ class CallbackSet:
 def _split_callbacks(callback):
     if callback is None:
         return None, None
-    if isinstance(callback, ContinuousCallback):
+    if isinstance(callback, (ContinuousCallback, VectorContinuousCallback)):
         return callback, None
     if isinstance(callback, DiscreteCallback):
         return None, callback
@@ -337,7 +353,8 @@ def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False, ksme
     terminate = 0
     ccb, dcb = _split_callbacks(callback)
     if ccb is not None:
-        srcs["condition_src"], srcs["affect_src"], term = codegen.emit_callback(ccb, n, m)
+        emit = codegen.emit_vector_callback if isinstance(ccb, VectorContinuousCallback) else codegen.emit_callback
+        srcs["condition_src"], srcs["affect_src"], term = emit(ccb, n, m)
         terminate |= 1 if term else 0
     if dcb is not None:
         srcs["dcondition_src"], srcs["daffect_src"], term = codegen.emit_discrete_callback(dcb, n, m)

@@ -195,6 +195,47 @@ def emit_callback(cb, n_state, n_param):
     return cond_src, aff_src, bool(integ2.terminated)
 
 
+def emit_vector_callback(cb, n_state, n_param):
+    """VectorContinuousCallback(condition!, affect!, len) -> (vcondition_src, vaffect_src, terminate).
+    condition(out, u, t, integrator) fills out[0..len); affect(integrator, idx) is traced once per 1-based idx."""
+    nc = cb.len
+    integ = _TraceIntegrator(n_state, n_param)
+    out = _Vec("g", nc)
+    try:
+        cb.condition(out, integ.u, integ.t, integ)
+    except Exception as e:
+        raise NotImplementedError("VectorContinuousCallback condition is not symbolically traceable; EnsembleB200 "
+                                  "only accepts callbacks that can be emitted as CUDA C") from e
+    gs = [sp.sympify(v) for v in out.vals]
+    if any(v == sym for v, sym in zip(gs, out.syms)):
+        raise ValueError("VectorContinuousCallback: condition! must assign every out[i]")
+    mask = 0
+    for i, sym in enumerate(integ.u.syms):
+        if any(g.has(sym) for g in gs):
+            mask |= 1 << i
+    body = _emit_body([f"g[{k}]" for k in range(nc)], gs)
+    cond_src = (f"#undef B2_COND_MASK\n#define B2_COND_MASK 0x{mask:x}u\n#define B2_NCOND {nc}\n"
+                "__device__ __forceinline__ void b2_vcondition(real* __restrict__ g, const real* __restrict__ u, "
+                "const real* __restrict__ p, const real t) {\n    (void)u; (void)p; (void)t;\n" + body + "\n}\n")
+    cases, terminated = [], []
+    for k in range(nc):
+        it = _TraceIntegrator(n_state, n_param)
+        try:
+            cb.affect(it, k + 1)
+        except Exception as e:
+            raise NotImplementedError("VectorContinuousCallback affect! is not symbolically traceable") from e
+        changed = [(i, v) for i, (sy, v) in enumerate(zip(it.u.syms, it.u.vals)) if v != sy]
+        lines = [f"        const real n{i} = {_c(v)};" for i, v in changed] + [f"        u[{i}] = n{i};" for i, _ in changed]
+        cases.append(f"    case {k}: {{\n" + "\n".join(lines) + "\n    }} break;".replace("}}", "}"))
+        terminated.append(bool(it.terminated))
+    if any(terminated) and not all(terminated):
+        raise NotImplementedError("VectorContinuousCallback: terminate! must be called for every event index or none")
+    aff_src = ("__device__ __forceinline__ void b2_vaffect(real* __restrict__ u, const real* __restrict__ p, const real t, "
+               "const int idx) {\n    (void)u; (void)p; (void)t;\n    switch (idx) {\n" + "\n".join(cases) +
+               "\n    default: break;\n    }\n}\n")
+    return cond_src, aff_src, all(terminated)
+
+
 def emit_discrete_callback(cb, n_state, n_param):
     """DiscreteCallback(condition, affect!) -> (dcondition_src, daffect_src, terminate).  condition(u,t,integrator)
     must trace to a sympy relational / boolean (e.g. `t >= 0.5`, `(u[0] > 1) & (t < 3)`)."""
@@ -231,7 +272,7 @@ using std::sqrt; using std::pow; using std::sin; using std::cos; using std::exp;
 
 
 def host_wrapper_source(sources, names=("b2_rhs", "b2_jac", "b2_tgrad", "b2_noise", "b2_condition", "b2_affect",
-                                        "b2_dcondition", "b2_daffect")):
+                                        "b2_dcondition", "b2_daffect", "b2_vcondition", "b2_vaffect")):
     """C++ translation unit exposing the emitted functions for float and double with C linkage
     (oracle side of the parity tests)."""
     parts = [HOST_PRELUDE]
@@ -247,6 +288,8 @@ def host_wrapper_source(sources, names=("b2_rhs", "b2_jac", "b2_tgrad", "b2_nois
                 parts.append(f"{ty} {nm}_{suf}(const {ty}* u, const {ty}* p, {ty} t) {{ return ns_{suf}::{nm}(u, p, t); }}\n")
             elif nm == "b2_dcondition":
                 parts.append(f"int {nm}_{suf}(const {ty}* u, const {ty}* p, {ty} t) {{ return ns_{suf}::{nm}(u, p, t) ? 1 : 0; }}\n")
+            elif nm == "b2_vaffect":
+                parts.append(f"void {nm}_{suf}({ty}* u, const {ty}* p, {ty} t, int idx) {{ ns_{suf}::{nm}(u, p, t, idx); }}\n")
             elif nm in ("b2_affect", "b2_daffect"):
                 parts.append(f"void {nm}_{suf}({ty}* u, const {ty}* p, {ty} t) {{ ns_{suf}::{nm}(u, p, t); }}\n")
             else:

@@ -1082,7 +1082,8 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
         const char* force_s = getenv("B200ENS_SPLIT");
         const bool off = (d->flags & B200ENS_MODEL_NOSPLIT) || (force_s && atoi(force_s) == 0);
         const bool on = (d->flags & B200ENS_MODEL_SPLIT) || (force_s && atoi(force_s) == 1);
-        const bool eligible = nvec && !m->x2 && !d->dcondition_src && d->n_state >= 4 && !flag_k && !(force_k && atoi(force_k) == 1);
+        const bool vector_cb = d->condition_src && strstr(d->condition_src, "B2_NCOND") != nullptr;   // one-thread kernels only
+        const bool eligible = nvec && !m->x2 && !d->dcondition_src && !vector_cb && d->n_state >= 4 && !flag_k && !(force_k && atoi(force_k) == 1);
         if (!rc && eligible && !off && (on || (try_regs && m->spill > (d->alg == B200ENS_VERN7 ? 1024 : 4096)))) {
             auto keep_src = m->source;
             auto keep_cubin = m->cubin;

@@ -111,6 +111,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     bool active = false, dirty = false, exhausted = false;
 #if B2_HAS_EVENT
     bool just_fired = false;
+    int ev_last = 0;   // VectorContinuousCallback: index of the function that fired the last event
     const int ip = a.interp_points;
 #endif
     B2Sink sink;
@@ -219,6 +220,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
         real un[B2_N], ut[B2_N];
 #if B2_HAS_EVENT
         real th_end = 1;
+        int ev_idx = 0;   // which event function fired (VectorContinuousCallback)
 #endif
         bool do_step = false;
         real tstop = t1;
@@ -328,7 +330,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                             for (int i = 0; i < B2_N; i++)
                                 if ((B2_COND_MASK >> i) & 1u) alg.poly_coeffs(i, cc[i]);
                         }
-                        auto cond_at = [&](real th) -> real {
+                        auto fill_w = [&](real th) {
                             if (Alg::DEG > 0) {
 #pragma unroll
                                 for (int i = 0; i < B2_N; i++) {
@@ -344,6 +346,105 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                             } else {
                                 alg.interp(u, un, th, dts, w);
                             }
+                        };
+#ifdef B2_NCOND
+                        // ---- VectorContinuousCallback (qa.jl:124): B2_NCOND event functions; the first sub-interval in
+                        // which ANY of them changes sign is searched, each changed function gets its own ITP root-find
+                        // on that bracket, the earliest root fires and its index goes to affect!(integrator, idx).
+                        real gp_[B2_NCOND], gl_[B2_NCOND], gh_[B2_NCOND], gv_[B2_NCOND], lo_[B2_NCOND];
+                        unsigned chg = 0;
+                        b2_vcondition(gp_, u, p, tprev);
+#pragma unroll
+                        for (int k = 0; k < B2_NCOND; k++) lo_[k] = 0;
+                        if (just_fired) {
+                            // only the function that fired the previous event takes its "previous sign" just after
+                            // the step start (it sits on its root); the others keep their sign at the step start, so a
+                            // crossing right after the event (a corner) is not lost
+                            fill_w((real)0.01);
+                            b2_vcondition(gv_, w, p, b2_fma((real)0.01, dts, tprev));
+#pragma unroll
+                            for (int k = 0; k < B2_NCOND; k++)
+                                if (k == ev_last) {
+                                    gp_[k] = gv_[k];
+                                    lo_[k] = (real)0.01;
+                                }
+                        }
+#pragma unroll
+                        for (int k = 0; k < B2_NCOND; k++) gl_[k] = gp_[k];
+                        for (int mm = 1; mm <= ip && !fired; mm++) {
+                            const real th = (mm == ip) ? (real)1 : (real)mm / (real)ip;
+                            if (mm == ip) {
+                                b2_vcondition(gv_, un, p, tnew);
+                            } else {
+                                fill_w(th);
+                                b2_vcondition(gv_, w, p, b2_fma(th, dts, tprev));
+                            }
+                            chg = 0;
+#pragma unroll
+                            for (int k = 0; k < B2_NCOND; k++)
+                                if ((gp_[k] < 0 && gv_[k] >= 0) || (gp_[k] > 0 && gv_[k] <= 0)) chg |= 1u << k;
+                            if (chg) {
+                                fired = true;
+                                hi = th;
+#pragma unroll
+                                for (int k = 0; k < B2_NCOND; k++) gh_[k] = gv_[k];
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < B2_NCOND; k++) {
+                                    gl_[k] = gv_[k];
+                                    lo_[k] = th;
+                                }
+                            }
+                        }
+                        if (fired) {
+                            real best = (real)2;
+                            int bidx = 0;
+#pragma unroll
+                            for (int k = 0; k < B2_NCOND; k++) {
+                                if ((chg >> k) & 1u) {
+                                    real lo_k = lo_[k], hi_k = hi, glo_k = gl_[k], ghi_k = gh_[k];
+                                    const real gprev_k = gp_[k];
+                                    const real eps = (real)2 * (real)B2_EPS;
+                                    const real k1 = (real)0.2 / (hi_k - lo_k);
+                                    real pw = b2_itp_pw(hi_k - lo_k);
+                                    for (int it = 0; it < 100 && hi_k - lo_k > (real)2 * eps; it++) {
+                                        const real xh = (real)0.5 * (lo_k + hi_k);
+                                        const real r = pw - (real)0.5 * (hi_k - lo_k);
+                                        pw *= (real)0.5;
+                                        const real delta = k1 * (hi_k - lo_k) * (hi_k - lo_k);
+                                        const real xf = (ghi_k * lo_k - glo_k * hi_k) / (ghi_k - glo_k);
+                                        const real sg = (xh - xf) >= 0 ? (real)1 : (real)-1;
+                                        const real xt = (delta <= b2_abs(xh - xf)) ? xf + sg * delta : xh;
+                                        real x = (b2_abs(xt - xh) <= r) ? xt : xh - sg * r;
+                                        if (!(x > lo_k && x < hi_k)) x = xh;
+                                        if (!(x > lo_k && x < hi_k)) break;
+                                        real gx_[B2_NCOND];
+                                        fill_w(x);
+                                        b2_vcondition(gx_, w, p, b2_fma(x, dts, tprev));
+                                        const real g = gx_[k];
+                                        if ((gprev_k < 0 && g >= 0) || (gprev_k > 0 && g <= 0)) {
+                                            hi_k = x;
+                                            ghi_k = g;
+                                        } else {
+                                            lo_k = x;
+                                            glo_k = g;
+                                        }
+                                    }
+                                    if (lo_k < best) {   // earliest event wins; the lower index on ties
+                                        best = lo_k;
+                                        bidx = k;
+                                    }
+                                }
+                            }
+                            th_end = best;
+                            ev_idx = bidx;
+                            ev_last = bidx;
+                            tnew = b2_fma(th_end, dts, tprev);
+                        }
+                        (void)gprev; (void)glo; (void)ghi; (void)lo;
+#else
+                        auto cond_at = [&](real th) -> real {
+                            fill_w(th);
                             return b2_condition(w, p, b2_fma(th, dts, tprev));
                         };
                         if (just_fired) {
@@ -395,6 +496,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                             th_end = lo;
                             tnew = b2_fma(th_end, dts, tprev);
                         }
+#endif   // B2_NCOND
 #endif
                     }
                 }
@@ -458,7 +560,12 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
             if (fired) {
                 real w[B2_N];
                 alg.interp(u, un, th_end, dts, w);
+#ifdef B2_NCOND
+                b2_vaffect(w, p, t, ev_idx);
+#else
+                (void)ev_idx;
                 b2_affect(w, p, t);
+#endif
 #pragma unroll
                 for (int i = 0; i < B2_N; i++) u[i] = w[i];
                 nevents++;

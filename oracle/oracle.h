@@ -56,6 +56,8 @@ typedef struct {
     void *dcond, *daffect;    /* DiscreteCallback: int dcond(u,p,t), daffect(u,p,t); NULL = none */
     int32_t devent_terminate, pad_;
     const double *abstol_vec, *reltol_vec;   /* NULL, or n_state per-component tolerances (override abstol / reltol) */
+    void *vcond, *vaffect;    /* VectorContinuousCallback: vcond(g,u,p,t) fills ncond values, vaffect(u,p,t,idx); has_event=1 */
+    int32_t ncond, pad2_;
 } orc_opts;
 
 /* u0 [N][n], p [N][m], saveat [n_save], out_u [N][n_save][n], retcode [N], stats [N] or NULL.

@@ -33,6 +33,7 @@ class Opts(C.Structure):
         ("cond", C.c_void_p), ("affect", C.c_void_p), ("dcond", C.c_void_p), ("daffect", C.c_void_p),
         ("devent_terminate", C.c_int32), ("pad_", C.c_int32),
         ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double)),
+        ("vcond", C.c_void_p), ("vaffect", C.c_void_p), ("ncond", C.c_int32), ("pad2_", C.c_int32),
     ]
 
 
@@ -88,7 +89,7 @@ def fns_from_host_model(dll, f64):
     out = {}
     for key, nm in (("rhs", "b2_rhs"), ("jac", "b2_jac"), ("tgrad", "b2_tgrad"), ("noise", "b2_noise"),
                     ("cond", "b2_condition"), ("affect", "b2_affect"), ("dcond", "b2_dcondition"),
-                    ("daffect", "b2_daffect")):
+                    ("daffect", "b2_daffect"), ("vcond", "b2_vcondition"), ("vaffect", "b2_vaffect")):
         try:
             out[key] = C.cast(getattr(dll, f"{nm}_{suf}"), C.c_void_p).value
         except AttributeError:
@@ -98,7 +99,7 @@ def fns_from_host_model(dll, f64):
 
 def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adaptive=True, dtype=np.float64,
           maxiters=100000, dW=None, seed=0, event=False, terminate=False, interp_points=10, nthreads=0,
-          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, **ctl):
+          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, ncond=0, **ctl):
     """Run the oracle.  model: built-in name, or fns = dict(rhs=ptr, jac=ptr, ...)."""
     L = lib()
     f64 = np.dtype(dtype) == np.float64
@@ -132,7 +133,9 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
     get = (lambda w: (fns or {}).get(w)) if fns is not None else (lambda w: model_fn(model, w, f64))
     o.rhs, o.jac, o.noise = get("rhs"), get("jac"), get("noise")
     o.tgrad = get("tgrad") if fns else None
-    o.cond, o.affect = (get("cond"), get("affect")) if event else (None, None)
+    o.cond, o.affect = (get("cond"), get("affect")) if event and not ncond else (None, None)
+    if ncond:   # VectorContinuousCallback
+        o.vcond, o.vaffect, o.ncond = get("vcond"), get("vaffect"), int(ncond)
     o.dcond, o.daffect = (get("dcond"), get("daffect")) if devent else (None, None)
     o.devent_terminate = int(dterminate)
     out = np.empty((N, len(saveat), n), dtype=dtype)

@@ -274,3 +274,54 @@ def test_reference_dense_solution_interpolation(B, gpu_lib, oracle):
     direct = B.solve(eprob, B.Vern7(), B.EnsembleB200(), saveat=times, **kw)
     for i in (0, 17, 63):
         assert np.array_equal(es[i](times), direct.u_array[i])
+
+
+def test_vector_continuous_callback(B, gpu_lib, oracle):
+    """VectorContinuousCallback(condition!, affect!, len) (qa.jl:124): a ball in a box (gravity and linear drag in y,
+    so that the steps stay shorter than an excursion through a wall) -- four walls, the earliest
+    crossing fires and affect!(integrator, idx) reflects the matching velocity.  Bit-identical to the oracle (which runs
+    the same emitted sources); the elastic x-motion is checked against the closed-form triangle wave."""
+    def box(du, u, p, t):
+        du[0] = u[1]
+        du[1] = 0 * u[0]
+        du[2] = u[3]
+        du[3] = -p[1] - 0.3 * u[3]
+
+    def condition(out, u, t, integrator):
+        out[0] = u[0]
+        out[1] = integrator.p[0] - u[0]
+        out[2] = u[2]
+        out[3] = integrator.p[0] - u[2]
+
+    def affect(integrator, idx):
+        if idx <= 2:
+            integrator.u[1] = -integrator.u[1]
+        else:
+            integrator.u[3] = -integrator.u[3]          # elastic: no Zeno accumulation of bounces on the floor
+
+    N = 300
+    rng = np.random.default_rng(8)
+    u0 = np.stack([0.2 + 0.6 * rng.random(N), 0.5 + 2.0 * rng.random(N), 0.2 + 0.6 * rng.random(N), rng.normal(size=N)], axis=1)
+    p = np.stack([np.ones(N), 5.0 + 5.0 * rng.random(N)], axis=1)
+    prob = B.ODEProblem(box, u0[0], (0.0, 4.0), p[0])
+    cb = B.VectorContinuousCallback(condition, affect, 4, interp_points=20)
+    saveat = np.linspace(0.0, 4.0, 41)
+    for alg in ("Tsit5", "Vern7", "Rodas5P"):
+        A = getattr(B, alg)()
+        sol = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), A, B.EnsembleB200(), trajectories=N, saveat=saveat, dt=0.01,
+                      abstol=1e-9, reltol=1e-9, callback=cb)
+        assert np.all(sol.retcodes == 1)
+        model = B.build_model(prob, A, cb)
+        ref, rc, st = oracle.solve(None, alg, u0, p, (0.0, 4.0), saveat, 0.01, abstol=1e-9, reltol=1e-9, event=True, ncond=4,
+                                   interp_points=20, fns=oracle_fns(oracle, B, model))
+        assert np.array_equal(sol.retcodes, rc)
+        assert np.array_equal(sol.stats, st)
+        ok, worst = within_tol(sol.u_array, ref, 1e-13, 1e-10)
+        assert ok, worst
+        # elastic walls in x: position = triangle wave of the free flight
+        free = u0[:, None, 0] + u0[:, None, 1] * saveat[None, :]
+        tri = np.abs(((free + 1.0) % 2.0) - 1.0)
+        assert np.max(np.abs(sol.u_array[:, :, 0] - tri)) < 1e-7
+        nx = np.floor(u0[:, 0] + u0[:, 1] * 4.0).astype(int)           # wall hits in x up to t = 4
+        assert np.all(sol.stats[:, 3] >= nx)                            # plus the bounces in y
+        assert np.all((sol.u_array[:, :, 2] > -1e-9) & (sol.u_array[:, :, 2] < 1 + 1e-9))

@@ -163,3 +163,34 @@ def test_ensemble_analysis_functions():
     with pytest.raises(IndexError):
         EA.timestep_mean(sim, 5)
     assert np.allclose(EA.timeseries_point_mean(sim, [0.0, 2.0]), arr[:, [0, 3]].mean(0))
+
+
+def test_vector_continuous_callback_codegen():
+    """VectorContinuousCallback (qa.jl:124) -> b2_vcondition / b2_vaffect CUDA C; untraceable or incomplete callbacks are
+    rejected (no CPU fallback)."""
+    import b200ens as B
+    from b200ens import codegen
+
+    def condition(out, u, t, integrator):
+        out[0] = u[0] - integrator.p[0]
+        out[1] = t - 0.5
+
+    def affect(integrator, idx):
+        if idx == 1:
+            integrator.u[0] = -integrator.u[0]
+        else:
+            B.terminate_b(integrator)
+
+    cb = B.VectorContinuousCallback(condition, affect, 2)
+    with pytest.raises(NotImplementedError):                     # terminate! for one index only
+        codegen.emit_vector_callback(cb, 2, 1)
+    cb2 = B.VectorContinuousCallback(condition, lambda integrator, idx: integrator.u.__setitem__(idx - 1, 0.0), 2)
+    c, a, term = codegen.emit_vector_callback(cb2, 2, 1)
+    assert "#define B2_NCOND 2" in c and "#define B2_COND_MASK 0x1u" in c and "b2_vcondition" in c
+    assert "case 0:" in a and "case 1:" in a and "u[1] =" in a and not term
+    with pytest.raises(ValueError):                              # out[1] never assigned
+        codegen.emit_vector_callback(B.VectorContinuousCallback(lambda out, u, t, i: out.__setitem__(0, u[0]), affect, 2), 2, 1)
+    with pytest.raises(ValueError):
+        B.VectorContinuousCallback(condition, affect, 0)
+    src = codegen.host_wrapper_source([codegen.emit_rhs([-codegen.sp.Symbol("u[0]", real=True)] * 2), c, a])
+    assert "b2_vaffect_f64" in src and "b2_vcondition_f32" in src

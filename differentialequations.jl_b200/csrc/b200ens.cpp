@@ -363,7 +363,7 @@ int ensure_loaded(b200ens_model* m) {
     // optional entry points are looked up only in modules that define them (kernels/b2_entry.cuh): no failing API
     // calls on the normal path (they show up as errors under compute-sanitizer)
     const bool erk = m->alg == B200ENS_TSIT5 || m->alg == B200ENS_VERN7;
-    if ((erk && !m->x2 && !m->split) || is_rosenbrock(m->alg))
+    if ((erk && !m->x2) || is_rosenbrock(m->alg))
         CU(cudaLibraryGetKernel(&m->kernel_adaptive, m->lib, "b2_ensemble_kernel_adaptive"));
     if (!is_sde(m->alg) && !m->x2) {
         CU(cudaLibraryGetKernel(&m->k_work_keys, m->lib, "b2_work_keys"));

@@ -49,6 +49,17 @@ extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble
 }
 #endif
 
+#if (B2_ALG == 1 || B2_ALG == 2) && B2_SPLIT
+// split kernels: the same compile-time folding (adaptive, interpolated saveat, caller-supplied dt)
+extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble_kernel_adaptive(const __grid_constant__ B2Args a) {
+#if B2_ALG == 1
+    b2_ode_driver_split<B2Tsit5, 1, 0, 0>(a);
+#else
+    b2_ode_driver_split<B2Vern7, 1, 0, 0>(a);
+#endif
+}
+#endif
+
 #if B2_ALG == 3 || B2_ALG == 4 || B2_ALG == 5 || B2_ALG == 8
 // Rosenbrock methods: adaptive, caller-supplied dt, direct stores folded at compile time; saveat-as-tstops stays a
 // run-time flag (it is the default for the Rodas family, off for Rosenbrock23)

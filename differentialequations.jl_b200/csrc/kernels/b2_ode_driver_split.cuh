@@ -31,7 +31,8 @@
 #define B2_EV_M 1
 #endif
 
-template <class Alg>
+// ADAPT / TSTOPS / AUTODT: compile-time specialisation as in b2_ode_driver.cuh (-1 / 1 = decided at run time)
+template <class Alg, int ADAPT = -1, int TSTOPS = -1, int AUTODT = 1>
 __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     __shared__ __align__(16) real s_xchg[2 * B2_NP * 32];
     __shared__ long long s_my[32];
@@ -55,8 +56,8 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     const real qoldinit = B2_ARG(a, qoldinit), dtmax = B2_ARG(a, dtmax), dtmin = B2_ARG(a, dtmin);
     const float beta1 = a.f_beta1, beta2 = a.f_beta2;
     const float lqinit = b2_fastlog2((float)qoldinit);
-    const bool adaptive = a.adaptive != 0;
-    const bool save_tstops = a.save_tstops != 0;
+    const bool adaptive = ADAPT < 0 ? (a.adaptive != 0) : (ADAPT != 0);
+    const bool save_tstops = TSTOPS < 0 ? (a.save_tstops != 0) : (TSTOPS != 0);
     const real INF = (real)__int_as_float(0x7f800000);
     real atol[B2_NL], rtol[B2_NL];   // tolerances of the owned components (padded components: any positive value)
 #pragma unroll
@@ -150,7 +151,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                         just_fired = false;
 #endif
                     }
-                    if (adaptive && !(dt_user > (real)0)) {
+                    if (AUTODT && adaptive && !(dt_user > (real)0)) {
                         // automatic initial step (same formula and summation order as b2_ode_driver.cuh);
                         // whole CTA, committed by the fresh lanes
                         real r0[B2_NL], r1[B2_NL], r2[B2_NL], u1[B2_NL], f1[B2_NL];

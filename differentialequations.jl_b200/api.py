@@ -81,15 +81,20 @@ class ODEProblem:
 
     is_sde = False
 
-    def __init__(self, f, u0, tspan, p=None, g=None):
+    def __init__(self, f, u0, tspan, p=None, g=None, mass_matrix=None):
         self.f = f
         self.g = g
+        # ODEFunction(f; mass_matrix = M): M u' = f(u,p,t) with a constant, possibly singular M (index-1 DAE); supported by
+        # the Rodas family (the Robertson DAE example of the DifferentialEquations.jl documentation)
+        self.mass_matrix = None if mass_matrix is None else np.asarray(mass_matrix, dtype=np.float64)
         self.scalar = np.ndim(u0) == 0
         self.u0 = np.atleast_1d(np.asarray(u0))
         if self.u0.dtype not in (np.float32, np.float64):
             self.u0 = self.u0.astype(np.float64)
         self.tspan = (float(tspan[0]), float(tspan[1]))
         self.p = np.zeros(0, self.u0.dtype) if p is None else np.atleast_1d(np.asarray(p, dtype=self.u0.dtype))
+        if self.mass_matrix is not None and self.mass_matrix.shape != (self.u0.shape[0],) * 2:
+            raise ValueError("mass_matrix must be n_state x n_state")
 
     def _replace(self, **kw):
         new = object.__new__(type(self))
@@ -334,12 +339,21 @@ def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False, ksme
     """Trace prob.f (and g / callback), emit CUDA C, JIT it for sm_100a.  Cached per function objects."""
     n, m = prob.u0.shape[0], prob.p.shape[0]
     dtype = prob.u0.dtype
-    key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math, packed_x2, ksmem, split)
+    mm = getattr(prob, "mass_matrix", None)
+    key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math, packed_x2, ksmem, split,
+           None if mm is None else mm.tobytes())
     hit = _model_cache.get(key)
     if hit is not None and hit[1] is prob.f:
         return hit[0]
     exprs, usyms, _, tsym = codegen.trace_vector_fn(prob.f, n, m)
     srcs = {"rhs_src": codegen.emit_rhs(exprs)}
+    if mm is not None:
+        if alg.name not in ("Rodas4", "Rodas5", "Rodas5P"):
+            raise NotImplementedError(f"mass_matrix is supported by Rodas4 / Rodas5 / Rodas5P, not by {alg.name}")
+        if callback is not None:
+            raise NotImplementedError("callbacks on mass-matrix problems (their interpolant needs u', which M u' = f does "
+                                      "not give for algebraic components)")
+        srcs["rhs_src"] = codegen.emit_mass(mm) + srcs["rhs_src"]
     if alg.name in ("Rosenbrock23", "Rodas4", "Rodas5", "Rodas5P"):
         srcs["jac_src"] = codegen.emit_jac(exprs, usyms)
         srcs["tgrad_src"] = codegen.emit_tgrad(exprs, tsym)
@@ -480,6 +494,8 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
                                   "is not supported -- use dense=True and evaluate sol(t), or pass saveat")
     if dense and save_tstops:
         raise ValueError("dense=True needs interpolated saves (save_tstops=False): tstops would change the step sequence")
+    if getattr(prob.prob if isinstance(prob, EnsembleProblem) else prob, "mass_matrix", None) is not None and (dense or save_tstops is False or save_tstops == 0 and save_tstops is not None):
+        raise NotImplementedError("mass-matrix problems save at tstops only (no dense output / interpolated saveat)")
     if dense and dW is not None:
         raise NotImplementedError("dense=True with injected noise increments")
     single = not isinstance(prob, EnsembleProblem)

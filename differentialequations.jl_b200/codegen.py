@@ -14,6 +14,7 @@ are expanded to products, nothing is contracted into FMAs (the kernels are compi
 """
 import inspect
 
+import numpy as np
 import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
@@ -138,6 +139,14 @@ def emit_tgrad(exprs, t):
         return None
     body = _emit_body([f"dT[{i}]" for i in range(len(d))], d)
     return _SIG.format(name="b2_tgrad", out="dT") + " {\n    (void)p; (void)t;\n" + body + "\n}\n"
+
+
+def emit_mass(M):
+    """Constant mass matrix as a compile-time table: after unrolling the zero entries vanish from the kernel."""
+    M = np.asarray(M, dtype=np.float64)
+    vals = ", ".join(repr(float(v)) for v in M.reshape(-1))
+    return ("#undef B2_HAS_MASS\n#define B2_HAS_MASS 1\n"
+            f"static constexpr double B2_MASS_[{M.size}] = {{{vals}}};\n")
 
 
 def emit_noise(exprs):

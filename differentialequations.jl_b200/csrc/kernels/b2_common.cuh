@@ -69,6 +69,9 @@ typedef sreal real;
 #ifndef B2_HAS_DEVENT
 #define B2_HAS_DEVENT 0
 #endif
+#ifndef B2_HAS_MASS
+#define B2_HAS_MASS 0   // 1: the model source defines the constant mass matrix B2_MASS_[n*n] (Rodas family: M u' = f)
+#endif
 #ifndef B2_KSMEM
 #define B2_KSMEM 0   // 1: ERK stage vectors live in shared memory (large n_state), see b2_erk.cuh
 #endif

@@ -223,7 +223,12 @@ struct B2Rodas {
 #pragma unroll
         for (int i = 0; i < B2_N; i++)
 #pragma unroll
+#if B2_HAS_MASS
+            // M u' = f (constant mass matrix, possibly singular: index-1 DAE): W = M/(gamma dt) - J
+            for (int j = 0; j < B2_N; j++) lu.A[i][j] = (real)B2_MASS_[i * B2_N + j] * dtgi - J[i * B2_N + j];
+#else
             for (int j = 0; j < B2_N; j++) lu.A[i][j] = (i == j ? dtgi : (real)0) - J[i * B2_N + j];
+#endif
         lu.factor();
 #if B2_HAS_TGRAD
         real dT[B2_N];
@@ -253,13 +258,37 @@ struct B2Rodas {
                 b2_rhs(fU, U, p, t + B2_RODAS_c[st] * dt);
                 nf += 1;
             }
+#if B2_HAS_MASS
+            real cacc[B2_N];   // sum_j C[st][j] k_j, multiplied by M below (non-zero entries of a row in index order)
+            if (st > 0) {
+#pragma unroll
+                for (int i = 0; i < B2_N; i++) {
+                    real acc = B2_RODAS_C[st][0] * k[0][i];
+#pragma unroll
+                    for (int j = 1; j < st; j++) acc = b2_fma(B2_RODAS_C[st][j], k[j][i], acc);
+                    cacc[i] = acc;
+                }
+            }
+#endif
 #pragma unroll
             for (int i = 0; i < B2_N; i++) {
                 real r = fU[i];
                 if (st > 0) {
+#if B2_HAS_MASS
+                    real acc = 0;
+                    bool first = true;
+#pragma unroll
+                    for (int j = 0; j < B2_N; j++) {
+                        if (B2_MASS_[i * B2_N + j] != 0.0) {
+                            acc = first ? (real)B2_MASS_[i * B2_N + j] * cacc[j] : b2_fma((real)B2_MASS_[i * B2_N + j], cacc[j], acc);
+                            first = false;
+                        }
+                    }
+#else
                     real acc = B2_RODAS_C[st][0] * k[0][i];
 #pragma unroll
                     for (int j = 1; j < st; j++) acc = b2_fma(B2_RODAS_C[st][j], k[j][i], acc);
+#endif
                     r = b2_fma(acc, dtinv, r);
                 }
 #if B2_HAS_TGRAD

@@ -58,6 +58,7 @@ typedef struct {
     const double *abstol_vec, *reltol_vec;   /* NULL, or n_state per-component tolerances (override abstol / reltol) */
     void *vcond, *vaffect;    /* VectorContinuousCallback: vcond(g,u,p,t) fills ncond values, vaffect(u,p,t,idx); has_event=1 */
     int32_t ncond, pad2_;
+    const double* mass;       /* NULL, or constant mass matrix [n_state][n_state] (M u' = f; Rodas4/5/5P only) */
 } orc_opts;
 
 /* u0 [N][n], p [N][m], saveat [n_save], out_u [N][n_save][n], retcode [N], stats [N] or NULL.

@@ -34,6 +34,7 @@ class Opts(C.Structure):
         ("devent_terminate", C.c_int32), ("pad_", C.c_int32),
         ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double)),
         ("vcond", C.c_void_p), ("vaffect", C.c_void_p), ("ncond", C.c_int32), ("pad2_", C.c_int32),
+        ("mass", C.POINTER(C.c_double)),
     ]
 
 
@@ -99,7 +100,7 @@ def fns_from_host_model(dll, f64):
 
 def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adaptive=True, dtype=np.float64,
           maxiters=100000, dW=None, seed=0, event=False, terminate=False, interp_points=10, nthreads=0,
-          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, ncond=0, **ctl):
+          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, ncond=0, mass_matrix=None, **ctl):
     """Run the oracle.  model: built-in name, or fns = dict(rhs=ptr, jac=ptr, ...)."""
     L = lib()
     f64 = np.dtype(dtype) == np.float64
@@ -111,7 +112,10 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
     o = Opts()
     o.alg = ALG[alg]
     o.n_state, o.n_param, o.adaptive = n, m, int(adaptive)
-    keep = []   # per-component tolerances: arrays must outlive the call
+    keep = []   # per-component tolerances / mass matrix: arrays must outlive the call
+    if mass_matrix is not None:
+        mm = np.ascontiguousarray(mass_matrix, dtype=np.float64); assert mm.shape == (n, n)
+        keep.append(mm); o.mass = mm.ctypes.data_as(C.POINTER(C.c_double))
     if np.ndim(abstol) > 0:
         av = np.ascontiguousarray(abstol, dtype=np.float64); assert av.shape == (n,)
         keep.append(av); o.abstol_vec = av.ctypes.data_as(C.POINTER(C.c_double)); abstol = float(av[0])

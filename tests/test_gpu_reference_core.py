@@ -195,3 +195,41 @@ def test_per_component_tolerances(B, gpu_lib, oracle):
     assert np.array_equal(outs[0].u_array, outs[1].u_array) and np.array_equal(outs[0].stats, outs[1].stats)
     with pytest.raises(ValueError):
         B.solve(el, B.Tsit5(), B.EnsembleB200(), abstol=[1e-6, 1e-6], **kw)
+
+
+def test_mass_matrix_dae_rodas(B, gpu_lib, oracle):
+    """ODEFunction(f; mass_matrix = M) with a singular M: the Robertson problem as an index-1 DAE (third equation
+    y1 + y2 + y3 = 1), the standard Rodas5P DAE example of the DifferentialEquations.jl documentation."""
+    from b200ens import workloads as W
+    from helpers import oracle_fns
+
+    def rober_dae(du, u, p, t):
+        du[0] = -p[0] * u[0] + p[2] * u[1] * u[2]
+        du[1] = p[0] * u[0] - p[1] * u[1] ** 2 - p[2] * u[1] * u[2]
+        du[2] = u[0] + u[1] + u[2] - 1.0
+
+    M = np.diag([1.0, 1.0, 0.0])
+    prob = B.ODEProblem(rober_dae, [1.0, 0.0, 0.0], (0.0, 1e5), (0.04, 3e7, 1e4), mass_matrix=M)
+    sol = B.solve(prob, B.Rodas5P(), reltol=1e-8, abstol=1e-8)            # the documentation's call
+    assert sol.retcode == B.ReturnCode.Success
+    assert abs(np.sum(sol.u[-1]) - 1.0) < 1e-12
+    assert abs(sol.u[-1][0] - 0.017865) < 1e-5
+    N = 400
+    u0, p = W.robertson_params(N)
+    eprob = B.EnsembleProblem(prob, u0s=u0, ps=p)
+    ode = B.solve(B.EnsembleProblem(W.robertson_problem(), u0s=u0, ps=p), B.Rodas5P(), B.EnsembleB200(), trajectories=N,
+                  saveat=W.ROBERTSON_SAVEAT, dt=1e-6, abstol=1e-10, reltol=1e-8)
+    for alg in ("Rodas5P", "Rodas5", "Rodas4"):
+        A = getattr(B, alg)()
+        dae = B.solve(eprob, A, B.EnsembleB200(), trajectories=N, saveat=W.ROBERTSON_SAVEAT, dt=1e-6, abstol=1e-10, reltol=1e-8)
+        assert np.all(dae.retcodes == 1)
+        assert np.max(np.abs(dae.u_array.sum(axis=2) - 1.0)) < 1e-13          # the algebraic constraint holds exactly
+        assert np.max(np.abs(dae.u_array - ode.u_array) / (1e-9 + np.abs(ode.u_array))) < 1e-4
+        ref, rc, st = oracle.solve(None, alg, u0, p, (0.0, 1e5), W.ROBERTSON_SAVEAT, 1e-6, abstol=1e-10, reltol=1e-8,
+                                   fns=oracle_fns(oracle, B, B.build_model(prob, A)), mass_matrix=M)
+        assert np.array_equal(dae.retcodes, rc) and np.array_equal(dae.stats[:, :3], st[:, :3])
+        assert np.allclose(dae.u_array, ref, rtol=1e-12, atol=1e-300)
+    with pytest.raises(NotImplementedError):
+        B.solve(prob, B.Tsit5())
+    with pytest.raises(NotImplementedError):
+        B.solve(prob, B.Rodas5P(), dense=True)

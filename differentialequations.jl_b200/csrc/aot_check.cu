@@ -20,6 +20,9 @@
 #ifdef AOT_X2
 #define B2_X2 1
 #endif
+#ifdef AOT_SPLIT
+#define B2_SPLIT 1   // one trajectory per lane of a 4-warp CTA (kernels/b2_split.cuh); n = 3 -> one component per warp, one padded
+#endif
 #ifndef B2_MINBLOCKS
 #define B2_MINBLOCKS 1
 #endif

@@ -157,3 +157,107 @@ def test_sde_em_strong_convergence_and_sosra_order(oracle):
     so, _, _ = oracle.solve("lorenz_additive", "SOSRA", u0, p, (0.0, 0.5), [0.5], 0.5 / coarse,
                             dW=np.concatenate([dWc, dZ], axis=2), adaptive=False)
     assert np.mean(np.abs(so - ref)) < 0.5 * np.mean(np.abs(em - ref))
+
+
+# ---------------------------------------------------------------- features added in session 2 (oracle side, CPU)
+def _host_fns(oracle, srcs, f64=True):
+    """Compile emitted model sources for the host and hand their entry points to the oracle."""
+    import tempfile
+
+    import b200ens as B
+
+    src = B.codegen.host_wrapper_source(srcs)
+    dll = oracle.compile_host_model(src, "golden", os.path.join(tempfile.gettempdir(), "b200ens_test_models"))
+    fns = oracle.fns_from_host_model(dll, f64)
+    fns["_dll"] = dll
+    return fns
+
+
+@pytest.mark.parametrize("alg", ["Rodas4", "Rodas5", "Rodas5P"])
+def test_robertson_dae_mass_matrix_vs_radau(oracle, alg):
+    """M u' = f with M = diag(1,1,0) (third equation: y1 + y2 + y3 = 1): same solution as the ODE form (scipy Radau
+    golden vector), the algebraic constraint holds to rounding."""
+    import b200ens as B
+    from b200ens import codegen
+
+    def rober_dae(du, u, p, t):
+        du[0] = -p[0] * u[0] + p[2] * u[1] * u[2]
+        du[1] = p[0] * u[0] - p[1] * u[1] ** 2 - p[2] * u[1] * u[2]
+        du[2] = u[0] + u[1] + u[2] - 1.0
+
+    g = _load("robertson.json")
+    exprs, usyms, _, tsym = codegen.trace_vector_fn(rober_dae, 3, 3)
+    fns = _host_fns(oracle, [codegen.emit_rhs(exprs), codegen.emit_jac(exprs, usyms), codegen.emit_tgrad(exprs, tsym)])
+    M = np.diag([1.0, 1.0, 0.0])
+    out, rc, st = oracle.solve(None, alg, [g["u0"]], [g["p"]], (0.0, 1e5), g["t"], 1e-6, abstol=1e-10, reltol=1e-8, fns=fns,
+                               mass_matrix=M)
+    ref = np.array(g["u"])
+    assert rc[0] == 1
+    assert np.all(np.abs(out[0] - ref) <= 100 * (1e-10 + 1e-8 * np.abs(ref)))
+    assert np.max(np.abs(out[0].sum(axis=1) - 1.0)) < 1e-14
+    # M = I through the mass-matrix code path is the plain ODE solve, bit for bit
+    def rober(du, u, p, t):
+        du[0] = -p[0] * u[0] + p[2] * u[1] * u[2]
+        du[1] = p[0] * u[0] - p[1] * u[1] ** 2 - p[2] * u[1] * u[2]
+        du[2] = p[1] * u[1] ** 2
+
+    ex2, us2, _, ts2 = codegen.trace_vector_fn(rober, 3, 3)
+    f2 = _host_fns(oracle, [codegen.emit_rhs(ex2), codegen.emit_jac(ex2, us2), codegen.emit_tgrad(ex2, ts2)])
+    a, _, sa = oracle.solve(None, alg, [g["u0"]], [g["p"]], (0.0, 1e5), g["t"], 1e-6, abstol=1e-10, reltol=1e-8, fns=f2)
+    b, _, sb = oracle.solve(None, alg, [g["u0"]], [g["p"]], (0.0, 1e5), g["t"], 1e-6, abstol=1e-10, reltol=1e-8, fns=f2,
+                            mass_matrix=np.eye(3))
+    assert np.array_equal(a, b) and np.array_equal(sa, sb)
+
+
+def test_vector_continuous_callback_ball_in_a_box(oracle):
+    """VectorContinuousCallback in the oracle: elastic walls at x = 0, 1 -> the saved x is the triangle wave of the
+    free flight; the index passed to affect! decides which velocity flips."""
+    import b200ens as B
+    from b200ens import codegen
+
+    def box(du, u, p, t):
+        du[0] = u[1]
+        du[1] = 0 * u[0]
+        du[2] = u[3]
+        du[3] = -p[1] - 0.3 * u[3]
+
+    def condition(out, u, t, integrator):
+        out[0] = u[0]
+        out[1] = integrator.p[0] - u[0]
+        out[2] = u[2]
+        out[3] = integrator.p[0] - u[2]
+
+    def affect(integrator, idx):
+        if idx <= 2:
+            integrator.u[1] = -integrator.u[1]
+        else:
+            integrator.u[3] = -integrator.u[3]
+
+    cb = B.VectorContinuousCallback(condition, affect, 4, interp_points=20)
+    exprs, _, _, _ = codegen.trace_vector_fn(box, 4, 2)
+    csrc, asrc, _ = codegen.emit_vector_callback(cb, 4, 2)
+    fns = _host_fns(oracle, [codegen.emit_rhs(exprs), csrc, asrc])
+    rng = np.random.default_rng(8)
+    N = 64
+    u0 = np.stack([0.2 + 0.6 * rng.random(N), 0.5 + 2.0 * rng.random(N), 0.2 + 0.6 * rng.random(N), rng.normal(size=N)], axis=1)
+    p = np.stack([np.ones(N), 5.0 + 5.0 * rng.random(N)], axis=1)
+    saveat = np.linspace(0.0, 4.0, 41)
+    out, rc, st = oracle.solve(None, "Tsit5", u0, p, (0.0, 4.0), saveat, 0.01, abstol=1e-9, reltol=1e-9, event=True, ncond=4,
+                               interp_points=20, fns=fns)
+    assert np.all(rc == 1)
+    free = u0[:, None, 0] + u0[:, None, 1] * saveat[None, :]
+    assert np.max(np.abs(out[:, :, 0] - np.abs(((free + 1.0) % 2.0) - 1.0))) < 1e-7
+    assert np.all((out[:, :, 2] > -1e-9) & (out[:, :, 2] < 1 + 1e-9))
+    assert np.all(st[:, 3] >= np.floor(u0[:, 0] + u0[:, 1] * 4.0))
+
+
+def test_per_component_tolerances_oracle(oracle):
+    g = _load("robertson.json")
+    kw = dict(reltol=1e-8)
+    a, _, sa = oracle.solve("robertson", "Rodas5P", [g["u0"]], [g["p"]], (0.0, 1e5), g["t"], 1e-6, abstol=1e-8, **kw)
+    b, _, sb = oracle.solve("robertson", "Rodas5P", [g["u0"]], [g["p"]], (0.0, 1e5), g["t"], 1e-6, abstol=np.full(3, 1e-8), **kw)
+    c, _, sc = oracle.solve("robertson", "Rodas5P", [g["u0"]], [g["p"]], (0.0, 1e5), g["t"], 1e-6, abstol=np.array([1e-8, 1e-14, 1e-6]), **kw)
+    assert np.array_equal(a, b) and np.array_equal(sa, sb)           # a constant vector is the scalar case
+    assert sc[0, 0] > sa[0, 0]                                       # the tight tolerance on y2 costs steps
+    ref = np.array(g["u"])
+    assert np.all(np.abs(c[0] - ref) <= 100 * (np.array([1e-8, 1e-14, 1e-6]) + 1e-8 * np.abs(ref)))

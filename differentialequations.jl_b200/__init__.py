@@ -19,7 +19,7 @@ packs the per-trajectory u0/p matrices and wraps the outputs.  No CPU fallback e
 from . import _lib, codegen
 from . import analysis as EnsembleAnalysis
 from ._lib import B200EnsError, Model, pinned_empty
-from .api import (EM, SOSRA, CallbackSet, ContinuousCallback, DiscreteCallback, EnsembleB200, EnsembleProblem, EnsembleSolution,
+from .api import (EM, SOSRA, SRIW1, CallbackSet, ContinuousCallback, DiscreteCallback, EnsembleB200, EnsembleProblem, EnsembleSolution,
                   EnsembleSummary, ODEProblem,
                   ODESolution, ReturnCode, Rodas4, Rodas5, Rodas5P, Rosenbrock23, SDEProblem, Tsit5, VectorContinuousCallback, Vern7,
                   ReducedEnsembleSolution, build_model, remake, solve, terminate_b)
@@ -27,5 +27,5 @@ from .api import (EM, SOSRA, CallbackSet, ContinuousCallback, DiscreteCallback, 
 __all__ = [
     "ODEProblem", "SDEProblem", "EnsembleProblem", "EnsembleB200", "EnsembleSolution", "EnsembleSummary", "ODESolution", "ReturnCode",
     "ContinuousCallback", "VectorContinuousCallback", "DiscreteCallback", "CallbackSet", "remake", "solve", "terminate_b", "Tsit5", "Vern7", "Rosenbrock23", "Rodas4", "Rodas5",
-    "Rodas5P", "EM", "SOSRA", "build_model", "Model", "B200EnsError", "pinned_empty", "EnsembleAnalysis", "ReducedEnsembleSolution",
+    "Rodas5P", "EM", "SOSRA", "SRIW1", "build_model", "Model", "B200EnsError", "pinned_empty", "EnsembleAnalysis", "ReducedEnsembleSolution",
 ]

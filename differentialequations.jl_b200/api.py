@@ -75,6 +75,13 @@ class SOSRA(_Alg):
     is_sde = True
 
 
+class SRIW1(_Alg):
+    """Roessler's SRI W1 (StochasticDiffEq `SRIW1`): strong order 1.5 for diagonal noise, fixed dt."""
+    name = "SRIW1"
+    adaptive_default = False
+    is_sde = True
+
+
 # ---------------------------------------------------------------- problems
 class ODEProblem:
     """ODEProblem(f, u0, tspan, p): f(u,p,t) -> du  or in-place f(du,u,p,t) (test/core.jl:22-30)."""

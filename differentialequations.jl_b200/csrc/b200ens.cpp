@@ -82,7 +82,7 @@ struct B2Args {
     float f_tol_a[32], f_tol_r[32];
 };
 
-bool is_sde(int alg) { return alg == B200ENS_EM || alg == B200ENS_SOSRA; }
+bool is_sde(int alg) { return alg == B200ENS_EM || alg == B200ENS_SOSRA || alg == B200ENS_SRIW1; }
 bool is_rosenbrock(int alg) {
     return alg == B200ENS_ROSENBROCK23 || alg == B200ENS_RODAS4 || alg == B200ENS_RODAS5 || alg == B200ENS_RODAS5P;
 }
@@ -720,7 +720,7 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
     B2Args base{};
     rc = fill_args(m, o, &base);
     if (rc) return rc;
-    const size_t noise_per_traj = dW ? (size_t)base.nsteps_noise * (m->alg == B200ENS_SOSRA ? 2 : 1) * n * es : 0;
+    const size_t noise_per_traj = dW ? (size_t)base.nsteps_noise * ((m->alg == B200ENS_SOSRA || m->alg == B200ENS_SRIW1) ? 2 : 1) * n * es : 0;
     const size_t out_per_traj = (size_t)n_save * n * es;
 
     rc = grow(&d->saveat, &d->cap_save, std::max<size_t>(es, (size_t)n_save * es));
@@ -997,7 +997,7 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     if (d->n_state < 1 || d->n_state > 32) return fail(B200ENS_E_INVALID, "n_state must be in 1..32");
     if (d->n_param < 0 || d->n_param > 64) return fail(B200ENS_E_INVALID, "n_param must be in 0..64");
     if (d->dtype != B200ENS_F32 && d->dtype != B200ENS_F64) return fail(B200ENS_E_INVALID, "bad dtype");
-    if (d->alg < B200ENS_TSIT5 || d->alg > B200ENS_RODAS4) return fail(B200ENS_E_INVALID, "bad alg id %d", d->alg);
+    if (d->alg < B200ENS_TSIT5 || d->alg > B200ENS_SRIW1) return fail(B200ENS_E_INVALID, "bad alg id %d", d->alg);
     if (!d->rhs_src) return fail(B200ENS_E_INVALID, "rhs_src is required");
     if (is_rosenbrock(d->alg) && !d->jac_src)
         return fail(B200ENS_E_UNSUPPORTED, "Rosenbrock methods need the analytic Jacobian (jac_src); there is no AD/finite-difference fallback");

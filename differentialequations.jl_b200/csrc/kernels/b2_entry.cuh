@@ -21,13 +21,13 @@
 #elif B2_ALG == 3 || B2_ALG == 4 || B2_ALG == 5 || B2_ALG == 8
 #include "b2_rosenbrock.cuh"
 #include "b2_ode_driver.cuh"
-#elif B2_ALG == 6 || B2_ALG == 7
+#elif B2_ALG == 6 || B2_ALG == 7 || B2_ALG == 9
 #include "b2_sde.cuh"
 #else
 #error "unknown B2_ALG"
 #endif
 
-#if !(B2_ALG == 6 || B2_ALG == 7) && !B2_X2
+#if !(B2_ALG == 6 || B2_ALG == 7 || B2_ALG == 9) && !B2_X2
 #include "b2_work.cuh"   // expected-work ordering of the trajectory queue (adaptive ODE steppers)
 #endif
 

@@ -1,5 +1,5 @@
-// b2_sde.cuh -- fixed-step SDE ensemble kernel: Euler-Maruyama (diagonal noise) and SOSRA
-// (additive noise, strong order 1.5) with counter-based Philox4x32-10 noise generated on the
+// b2_sde.cuh -- fixed-step SDE ensemble kernel: Euler-Maruyama (diagonal noise), SRIW1 (diagonal noise, strong
+// order 1.5) and SOSRA (additive noise, strong order 1.5) with counter-based Philox4x32-10 noise generated on the
 // device, or Brownian increments injected by the caller for pathwise parity.
 // Reference names: SDEProblem /root/reference/test/qa/qa.jl:103 (EM/SOSRA live in
 // StochasticDiffEq, outside the dep closure; step forms SURVEY.md A.9, table B.8, RNG B.9).
@@ -79,7 +79,7 @@ __device__ __forceinline__ void b2_sde_driver(const B2Args& a) {
     const real* const gdW = reinterpret_cast<const real*>(a.dW);
     const int n_save = a.n_save;
     const int out_per_traj = n_save * B2_N;
-    constexpr int NVEC = (ALG == 7) ? 2 : 1;
+    constexpr int NVEC = (ALG == 7 || ALG == 9) ? 2 : 1;
     const real t0 = B2_ARG(a, t0), t1 = B2_ARG(a, t1), dt_user = B2_ARG(a, dt);
 
     B2Sink sink;
@@ -159,6 +159,50 @@ __device__ __forceinline__ void b2_sde_driver(const B2Args& a) {
                     b2_noise(g1, up, p, t);
 #pragma unroll
                     for (int i = 0; i < B2_N; i++) u[i] = b2_fma(g1[i], dW[i], b2_fma(dt, k1[i], up[i]));
+                } else if (ALG == 9) {
+                    // SRIW1 (Roessler SRI W1): strong order 1.5 for diagonal noise; same expression tree as the oracle
+                    real chi2[B2_N], i11[B2_N], i111[B2_N], k2[B2_N], g2[B2_N], g3[B2_N], g4[B2_N], H[B2_N];
+                    const real sq = b2_sqrt(dt);
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) {
+                        chi2[i] = (real)0.5 * b2_fma(dZ[i], (real)B2_INV_SQRT3, dW[i]);
+                        i11[i] = (real)0.5 * b2_fma(dW[i], dW[i], -dt) / sq;
+                        i111[i] = dW[i] * b2_fma(dW[i], dW[i], (real)-3 * dt) / ((real)6 * dt);
+                    }
+                    b2_rhs(k1, up, p, t);
+                    b2_noise(g1, up, p, t);
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) H[i] = b2_fma(chi2[i], (real)1.5 * g1[i], b2_fma(dt, (real)0.75 * k1[i], up[i]));
+                    b2_rhs(k2, H, p, t + (real)0.75 * dt);
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) H[i] = b2_fma(sq, (real)0.5 * g1[i], b2_fma(dt, (real)0.25 * k1[i], up[i]));
+                    b2_noise(g2, H, p, t + (real)0.25 * dt);
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) H[i] = b2_fma(sq, -g1[i], b2_fma(dt, k1[i], up[i]));
+                    b2_noise(g3, H, p, t + dt);
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) {
+                        const real bb = b2_fma((real)0.5, g3[i], b2_fma((real)3, g2[i], (real)-5 * g1[i]));
+                        H[i] = b2_fma(sq, bb, b2_fma(dt, (real)0.25 * k1[i], up[i]));
+                    }
+                    b2_noise(g4, H, p, t + (real)0.25 * dt);
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) {
+                        const real d = b2_fma((real)(2.0 / 3.0), k2[i], (real)(1.0 / 3.0) * k1[i]);
+                        real c1 = -dW[i];
+                        c1 = b2_fma((real)-1, i11[i], c1);
+                        c1 = b2_fma((real)2, chi2[i], c1);
+                        c1 = b2_fma((real)-2, i111[i], c1);
+                        real c2 = (real)(4.0 / 3.0) * dW[i];
+                        c2 = b2_fma((real)(4.0 / 3.0), i11[i], c2);
+                        c2 = b2_fma((real)(-4.0 / 3.0), chi2[i], c2);
+                        c2 = b2_fma((real)(5.0 / 3.0), i111[i], c2);
+                        real c3 = (real)(2.0 / 3.0) * dW[i];
+                        c3 = b2_fma((real)(-1.0 / 3.0), i11[i], c3);
+                        c3 = b2_fma((real)(-2.0 / 3.0), chi2[i], c3);
+                        c3 = b2_fma((real)(-2.0 / 3.0), i111[i], c3);
+                        u[i] = b2_fma(i111[i], g4[i], b2_fma(c3, g3[i], b2_fma(c2, g2[i], b2_fma(c1, g1[i], b2_fma(dt, d, up[i])))));
+                    }
                 } else {  // SOSRA
                     real chi2[B2_N], g2[B2_N], g3[B2_N], k2[B2_N], k3[B2_N], H[B2_N];
 #pragma unroll

@@ -34,7 +34,8 @@ enum b200ens_dtype { B200ENS_F32 = 0, B200ENS_F64 = 1 };
  *  Rodas5/Rodas4 live in OrdinaryDiffEqRosenbrock, EM/SOSRA in StochasticDiffEq) */
 enum b200ens_alg {
     B200ENS_TSIT5 = 1, B200ENS_VERN7 = 2, B200ENS_ROSENBROCK23 = 3, B200ENS_RODAS5 = 4,
-    B200ENS_RODAS5P = 5, B200ENS_EM = 6, B200ENS_SOSRA = 7, B200ENS_RODAS4 = 8
+    B200ENS_RODAS5P = 5, B200ENS_EM = 6, B200ENS_SOSRA = 7, B200ENS_RODAS4 = 8,
+    B200ENS_SRIW1 = 9   /* Roessler SRI W1: strong order 1.5 for diagonal noise (fixed dt; dW and dZ per step) */
 };
 
 /* per-trajectory return codes <- SciMLBase.ReturnCode (qa.jl:213); the Julia glue maps by name */

@@ -325,3 +325,34 @@ def test_vector_continuous_callback(B, gpu_lib, oracle):
         nx = np.floor(u0[:, 0] + u0[:, 1] * 4.0).astype(int)           # wall hits in x up to t = 4
         assert np.all(sol.stats[:, 3] >= nx)                            # plus the bounces in y
         assert np.all((sol.u_array[:, :, 2] > -1e-9) & (sol.u_array[:, :, 2] < 1 + 1e-9))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_sriw1_gbm_injected_pathwise_and_strong_accuracy(B, gpu_lib, oracle, dtype):
+    """SRIW1 (strong order 1.5, diagonal noise): pathwise agreement with the oracle on injected (dW, dZ) to 1e-10, and
+    far closer to the closed form of geometric Brownian motion than Euler-Maruyama on the same Brownian paths."""
+    from b200ens import workloads as W
+
+    N, nsteps = 4096, 64
+    dt = 1.0 / nsteps
+    u0, p = W.gbm_params(N, dtype=dtype)
+    dW = _increments(N, nsteps, 2, 1, dt, dtype, 17)
+    saveat = np.linspace(0, 1, 5)
+    sol = B.solve(_ens(B, W.gbm_problem(dtype), u0, p), B.SRIW1(), B.EnsembleB200(), trajectories=N, saveat=saveat, dt=dt, dW=dW)
+    ref, rc, _ = oracle.solve("gbm", "SRIW1", u0, p, (0.0, 1.0), saveat, dt, dtype=dtype, dW=dW, adaptive=False)
+    assert np.all(sol.retcodes == 1) and np.all(rc == 1)
+    tol = 1e-10 if dtype == np.float64 else 1e-5
+    assert np.abs(sol.u_array.astype(np.float64) - ref.astype(np.float64)).max() <= tol * max(1.0, np.abs(ref).max())
+    if dtype == np.float64:
+        WT = dW[:, :, 0, 0].sum(axis=1)
+        exact = np.exp((p[:, 0] - 0.5 * p[:, 1] ** 2) + p[:, 1] * WT)
+        em = B.solve(_ens(B, W.gbm_problem(dtype), u0, p), B.EM(), B.EnsembleB200(), trajectories=N, saveat=[1.0], dt=dt,
+                     dW=np.ascontiguousarray(dW[:, :, :1, :]))
+        e_sri = np.mean(np.abs(sol.u_array[:, -1, 0] - exact))
+        e_em = np.mean(np.abs(em.u_array[:, -1, 0] - exact))
+        assert e_sri < e_em / 10, (e_sri, e_em)
+    # device Philox noise: same streams as the oracle
+    sol2 = B.solve(_ens(B, W.gbm_problem(dtype), u0, p), B.SRIW1(), B.EnsembleB200(), trajectories=N, saveat=[1.0], dt=dt, seed=99)
+    ref2, _, _ = oracle.solve("gbm", "SRIW1", u0, p, (0.0, 1.0), [1.0], dt, dtype=dtype, seed=99, adaptive=False)
+    rel = np.abs(sol2.u_array.astype(np.float64) - ref2.astype(np.float64)) / np.abs(ref2.astype(np.float64))
+    assert rel.max() < (1e-8 if dtype == np.float64 else 5e-4), rel.max()

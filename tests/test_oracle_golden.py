@@ -261,3 +261,37 @@ def test_per_component_tolerances_oracle(oracle):
     assert sc[0, 0] > sa[0, 0]                                       # the tight tolerance on y2 costs steps
     ref = np.array(g["u"])
     assert np.all(np.abs(c[0] - ref) <= 100 * (np.array([1e-8, 1e-14, 1e-6]) + 1e-8 * np.abs(ref)))
+
+
+def test_sriw1_strong_order_on_gbm(oracle):
+    """SRIW1 coefficients (recalled, Roessler 2010 SRI W1): observed STRONG order ~1.5 on geometric Brownian motion
+    against the pathwise closed form, with (dW, dZ) of the coarse grids built consistently from one fine Brownian path;
+    Euler-Maruyama on the same paths shows ~0.5."""
+    rng = np.random.default_rng(1)
+    P, nf = 3000, 256
+    hf = 1.0 / nf
+    mu, sg = 1.01, 0.87
+    dWf = rng.normal(size=(P, nf)) * np.sqrt(hf)
+    dZf = rng.normal(size=(P, nf)) * np.sqrt(hf)
+    exact = np.exp((mu - sg * sg / 2) + sg * dWf.sum(1))
+    u0 = np.ones((P, 1))
+    p = np.tile([mu, sg], (P, 1))
+    hs, e_sri, e_em = [], [], []
+    for m in (32, 16, 8, 4):
+        n, h = nf // m, m * hf
+        Wc = dWf.reshape(P, n, m)
+        dW = Wc.sum(2)
+        I10f = hf * (dWf + dZf / np.sqrt(3)) / 2                       # int_0^h W ds of every fine step
+        I10c = (I10f.reshape(P, n, m) + hf * (np.cumsum(Wc, axis=2) - Wc)).sum(2)
+        dZ = np.sqrt(3) * (2 * I10c / h - dW)
+        out, rc, _ = oracle.solve("gbm", "SRIW1", u0, p, (0.0, 1.0), [1.0], h, adaptive=False, dW=np.stack([dW, dZ], axis=2).reshape(P, n, 2, 1))
+        out2, _, _ = oracle.solve("gbm", "EM", u0, p, (0.0, 1.0), [1.0], h, adaptive=False, dW=dW.reshape(P, n, 1, 1))
+        assert np.all(rc == 1)
+        hs.append(h)
+        e_sri.append(np.mean(np.abs(out[:, 0, 0] - exact)))
+        e_em.append(np.mean(np.abs(out2[:, 0, 0] - exact)))
+    o_sri = np.polyfit(np.log(hs), np.log(e_sri), 1)[0]
+    o_em = np.polyfit(np.log(hs), np.log(e_em), 1)[0]
+    assert 1.25 < o_sri < 1.75, (o_sri, e_sri)
+    assert 0.3 < o_em < 0.7, o_em
+    assert e_sri[-1] < e_em[-1] / 20

@@ -46,7 +46,7 @@ class Opts(C.Structure):
         ("noise_injected", C.c_int32), ("event_terminate", C.c_int32), ("interp_points", C.c_int32),
         ("save_tstops", C.c_int32), ("device_mask", C.c_uint32), ("refill_threshold", C.c_int32),
         ("block_threads", C.c_int32), ("stage_outputs", C.c_int32),
-        ("work_order", C.c_int32), ("reserved0", C.c_int32),
+        ("work_order", C.c_int32), ("save_everystep", C.c_int32),
         ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double)),
     ]
 
@@ -114,7 +114,7 @@ def lib():
     L.b200ens_host_alloc.restype = C.c_void_p
     L.b200ens_host_free.argtypes = [C.c_void_p]
     L.b200ens_host_free.restype = None
-    if L.b200ens_abi_version() != 3:
+    if L.b200ens_abi_version() != 4:
         raise ImportError("libb200ens ABI version mismatch")
     _lib = L
     return L
@@ -194,6 +194,24 @@ class Model:
         check(lib().b200ens_solve(self.handle, C.byref(opts), N, vp(u0), vp(p), vp(saveat), n_save, vp(dW), vp(out),
                                   None, vp(rc), vp(stats), C.byref(tm)))
         return out, rc, stats, tm
+
+    # ---- every accepted step (opts.save_everystep = 1): capacity slots per trajectory, per-trajectory step times
+    def solve_everystep(self, opts, u0, p, capacity):
+        N = u0.shape[0]
+        dt = self.dtype
+        u0 = np.ascontiguousarray(u0, dtype=dt)
+        p = np.ascontiguousarray(p, dtype=dt).reshape(N, self.n_param)
+        out = np.empty((N, capacity, self.n_state), dtype=dt)
+        times = np.empty((N, capacity), dtype=dt)
+        rc = np.zeros(N, dtype=np.int32)
+        stats = np.zeros((N, 4), dtype=np.int32)
+        tm = Timing()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        o = copy_opts(opts)
+        o.save_everystep = 1
+        check(lib().b200ens_solve(self.handle, C.byref(o), N, vp(u0), vp(p), None, int(capacity), None, vp(out), vp(times),
+                                  vp(rc), vp(stats), C.byref(tm)))
+        return out, times, rc, stats, tm
 
     # ---- ensemble moments without shipping trajectories to the host (b200ens_solve_moments)
     def solve_moments(self, opts, u0, p, saveat, dW=None):

@@ -287,6 +287,9 @@ class EnsembleSolution:
 
     def __getitem__(self, i):
         dense = None if self._dense is None else (lambda tt, _i=int(i): self._dense(_i, tt))
+        if np.ndim(self.t) == 2:   # save_everystep: per-trajectory times [N, capacity], valid entries = naccept + 1
+            k = int(self.stats[i, 0]) + 1
+            return ODESolution(self.t[i, :k], self.u_array[i, :k], self.retcodes[i], self.stats[i], self._scalar, dense)
         return ODESolution(self.t, self.u_array[i], self.retcodes[i], None if self.stats is None else self.stats[i],
                            self._scalar, dense)
 
@@ -491,14 +494,18 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, batch_size=None, **kw)
 
 
 def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, abstol=None, reltol=None,
-                adaptive=None, callback=None, maxiters=None, save_everystep=False, dense=False, seed=0, dW=None,
+                adaptive=None, callback=None, maxiters=None, save_everystep=None, dense=False, seed=0, dW=None,
                 save_tstops=None, summary=False, _lo=0, _repeat=1, **kwargs):
     """One device solve of trajectories _lo+1 .. _lo+trajectories of the ensemble."""
     if kwargs:
         raise TypeError(f"solve: unsupported keyword arguments {sorted(kwargs)}")
-    if save_everystep:
-        raise NotImplementedError("EnsembleB200 saves at `saveat` points only (fixed-size output); save_everystep=true "
-                                  "is not supported -- use dense=True and evaluate sol(t), or pass saveat")
+    # save_everystep: upstream's default when no saveat is given.  Here: the default for a single problem without saveat
+    # (sol.t / sol.u hold every accepted step, like upstream); ensembles keep the fixed-size saveat output unless asked.
+    is_single = not isinstance(prob, EnsembleProblem)
+    if save_everystep is None:
+        save_everystep = bool(is_single and saveat is None and not alg.is_sde and not summary)
+    if save_everystep and (alg.is_sde or summary or dW is not None):
+        raise NotImplementedError("save_everystep with SDE steppers / summary: pass the time grid as saveat instead")
     if dense and save_tstops:
         raise ValueError("dense=True needs interpolated saves (save_tstops=False): tstops would change the step sequence")
     if getattr(prob.prob if isinstance(prob, EnsembleProblem) else prob, "mass_matrix", None) is not None and (dense or save_tstops is False or save_tstops == 0 and save_tstops is not None):
@@ -526,8 +533,8 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
         if not adaptive:
             raise ValueError("fixed-step solves need dt")
         dt = 0.0   # automatic per-trajectory initial step on the device
-    model = build_model(base, alg, callback, ensemblealg.fast_math, ensemblealg.packed_x2,
-                        ensemblealg.stage_vectors_in_smem, ensemblealg.split)
+    model = build_model(base, alg, callback, ensemblealg.fast_math, ensemblealg.packed_x2 and not save_everystep,
+                        ensemblealg.stage_vectors_in_smem, False if save_everystep else ensemblealg.split)
     ts = _saveat_array(saveat, base.tspan, dtype)
     t_pack = time.perf_counter()
     u0, p = _pack(eprob, N, dtype, _lo, _repeat)
@@ -580,7 +587,19 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
         timing["prob_func_s"] = t_pack
         return EnsembleSummary(ts, s_, q_, cnt, rc, time.perf_counter() - t_solve, timing)
     t_solve = time.perf_counter()
-    out, rc, stats, tm = model.solve(o, u0, p, ts, dW=dW)
+    if save_everystep:
+        # every accepted step: fixed capacity per trajectory, doubled until the longest trajectory fits
+        cap = 256
+        while True:
+            out, ts, rc, stats, tm = model.solve_everystep(o, u0, p, cap)
+            need = int(stats[:, 0].max()) + 1
+            if need <= cap:
+                break
+            cap = 1 << int(np.ceil(np.log2(need)))
+        if saveat is not None:
+            raise ValueError("save_everystep=True and saveat are mutually exclusive on this back-end")
+    else:
+        out, rc, stats, tm = model.solve(o, u0, p, ts, dW=dW)
     elapsed = time.perf_counter() - t_solve
     timing = tm.asdict()
     timing["prob_func_s"] = t_pack

@@ -80,6 +80,8 @@ struct B2Args {
     const unsigned* perm;
     double tol_a[32], tol_r[32];
     float f_tol_a[32], f_tol_r[32];
+    void* every_t;
+    int save_every, pad1_;
 };
 
 bool is_sde(int alg) { return alg == B200ENS_EM || alg == B200ENS_SOSRA || alg == B200ENS_SRIW1; }
@@ -382,6 +384,8 @@ struct Slot {  // one pipeline slot = one stream + device buffers for one chunk
     unsigned long long* counter = nullptr;
     void* work = nullptr;   // expected-work ordering scratch (counter | histogram | cursors | perm | keys)
     size_t cap_work = 0;
+    void* every_t = nullptr;   // save_everystep: step times [chunk][capacity]
+    size_t cap_every = 0;
     size_t cap_u0 = 0, cap_p = 0, cap_out = 0, cap_dW = 0, cap_n = 0;
     // pinned bounce buffers for callers whose arrays are pageable (e.g. plain Julia Arrays)
     char *h_in = nullptr, *h_out = nullptr;
@@ -590,6 +594,13 @@ int check_opts(const b200ens_model* m, const b200ens_opts* o, int n_save, const 
         return fail(B200ENS_E_INVALID, "b200ens_opts.struct_size %u != %zu (ABI mismatch)", o->struct_size,
                     sizeof(b200ens_opts));
     if (n_save < 0) return fail(B200ENS_E_INVALID, "n_save < 0");
+    if (o->save_everystep) {
+        if (is_sde(m->alg) || m->x2 || m->split)
+            return fail(B200ENS_E_UNSUPPORTED, "save_everystep needs an ODE stepper and the one-thread kernel (compile with "
+                                               "B200ENS_MODEL_NOSPLIT for large systems; SDE: use a saveat grid)");
+        if (n_save < 2) return fail(B200ENS_E_INVALID, "save_everystep: n_save is the capacity per trajectory and must be >= 2");
+        if (o->stage_outputs > 0) return fail(B200ENS_E_UNSUPPORTED, "save_everystep with stage_outputs=1");
+    }
     if (o->noise_injected && !dW) return fail(B200ENS_E_INVALID, "noise_injected=1 but dW is NULL");
     return 0;
 }
@@ -599,7 +610,7 @@ int launch(b200ens_model* m, const LaunchPlan& lp, const B2Args& a, cudaStream_t
     // the specialised entry keeps 32-bit output offsets in its Float32 save queue: fall back to the generic entry beyond 2^32 elements
     const bool off32_ok = m->dtype == B200ENS_F64 || (unsigned long long)a.N * (unsigned long long)a.n_save * m->n_state < (1ull << 32);
     const bool tstops_ok = !a.save_tstops || is_rosenbrock(m->alg);   // the Rosenbrock entry keeps save_tstops a run-time flag
-    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && tstops_ok && a.dt > 0 && a.stage_stride == 0 && off32_ok) ? m->kernel_adaptive : m->kernel;
+    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && tstops_ok && a.dt > 0 && a.stage_stride == 0 && off32_ok && !a.save_every) ? m->kernel_adaptive : m->kernel;
     if (k != m->kernel && lp.smem > 48 * 1024)
         CU(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, lp.smem));
     CU(cudaLaunchKernel((const void*)k, dim3(lp.grid), dim3(lp.block), params, lp.smem, stream));
@@ -707,7 +718,7 @@ struct ShardResult {
 // Solve trajectories [lo, hi) of the caller's host buffers on one device.
 int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, long long hi, const char* u0,
                 const char* p, const void* saveat, int n_save, const char* dW, char* out_u, int32_t* retcode,
-                b200ens_stats* stats, ShardResult* res, Moments* mom = nullptr) {
+                b200ens_stats* stats, ShardResult* res, Moments* mom = nullptr, char* out_t_every = nullptr) {
     DeviceCtx* d;
     int rc = device_ctx(dev, &d);
     if (rc) return rc;
@@ -737,7 +748,8 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
         trace_txt += b;
     };
-    if (n_save) CU(cudaMemcpyAsync(d->saveat, saveat, (size_t)n_save * es, cudaMemcpyHostToDevice, d->slot[0].stream));
+    const bool every = o->save_everystep != 0;   // n_save = capacity, no saveat grid
+    if (n_save && !every) CU(cudaMemcpyAsync(d->saveat, saveat, (size_t)n_save * es, cudaMemcpyHostToDevice, d->slot[0].stream));
     CU(cudaStreamSynchronize(d->slot[0].stream));
 
     // chunk size: keep both pipeline slots under ~1/4 of the device memory and at least a few waves
@@ -844,6 +856,7 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
         if ((rc = grow(&s.p, &s.cap_p, std::max<size_t>(es, (size_t)cn * np * es)))) return rc;
         if ((rc = grow(&s.out, &s.cap_out, std::max<size_t>(es, (size_t)cn * out_per_traj)))) return rc;
         if (dW && (rc = grow(&s.dW, &s.cap_dW, (size_t)cn * noise_per_traj))) return rc;
+        if (every && (rc = grow(&s.every_t, &s.cap_every, (size_t)cn * n_save * es))) return rc;
         if ((size_t)cn > s.cap_n) {
             if (s.rc) CU(cudaFree(s.rc));
             if (s.stats) CU(cudaFree(s.stats));
@@ -874,7 +887,9 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
         B2Args a = base;
         a.u0 = s.u0;
         a.p = s.p;
-        a.saveat = d->saveat;
+        a.saveat = every ? nullptr : d->saveat;
+        a.every_t = every ? s.every_t : nullptr;
+        a.save_every = every ? 1 : 0;
         a.dW = dW ? s.dW : nullptr;
         a.out_u = s.out;
         a.retcode = s.rc;
@@ -919,6 +934,8 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
             if (out_b) CU(cudaMemcpyAsync(dst_out, s.out, (size_t)cn * out_per_traj, cudaMemcpyDeviceToHost, s.stream));
             CU(cudaMemcpyAsync(dst_rc, s.rc, (size_t)cn * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
             if (stats) CU(cudaMemcpyAsync(dst_st, s.stats, (size_t)cn * sizeof(b200ens_stats), cudaMemcpyDeviceToHost, s.stream));
+            if (every)   // step times straight into the caller's [N][capacity] array
+                CU(cudaMemcpyAsync(out_t_every + (size_t)g0 * n_save * es, s.every_t, (size_t)cn * n_save * es, cudaMemcpyDeviceToHost, s.stream));
         }
         CU(cudaEventRecord(s.ev[3], s.stream));
         mark("enq", cn);
@@ -1176,9 +1193,11 @@ static int solve_host(b200ens_model* m, const b200ens_opts* o, int64_t N, const 
     if (rc) return rc;
     if (N < 0) return fail(B200ENS_E_INVALID, "N < 0");
     if (timing) memset(timing, 0, sizeof *timing);
-    if (!u0 || !retcode || (m->n_param && !p) || (n_save && (!saveat || (!out_u && !moments))))
+    const bool every = o->save_everystep != 0;
+    if (every && (moments || !out_t)) return fail(B200ENS_E_INVALID, "save_everystep needs out_t [N][n_save] (and no moments mode)");
+    if (!u0 || !retcode || (m->n_param && !p) || (n_save && ((!saveat && !every) || (!out_u && !moments))))
         return fail(B200ENS_E_INVALID, "null buffer");
-    if (out_t && n_save) memcpy(out_t, saveat, (size_t)n_save * m->elem());
+    if (out_t && n_save && !every) memcpy(out_t, saveat, (size_t)n_save * m->elem());
     if (N == 0) return 0;
     const int ndev = b200ens_device_count();
     if (ndev <= 0) return fail(B200ENS_E_NODEVICE, "no CUDA device available (libb200ens has no CPU fallback)");
@@ -1201,7 +1220,8 @@ static int solve_host(b200ens_model* m, const b200ens_opts* o, int64_t N, const 
     auto run = [&](int g) {
         const long long lo = N * g / G, hi = N * (g + 1) / G;  // contiguous trajectory ranges
         res[g].code = solve_shard(m, o, devs[g], lo, hi, (const char*)u0, (const char*)p, saveat, n_save,
-                                  (const char*)dW, (char*)out_u, retcode, stats, &res[g], moments ? &moms[g] : nullptr);
+                                  (const char*)dW, (char*)out_u, retcode, stats, &res[g], moments ? &moms[g] : nullptr,
+                                  every ? (char*)out_t : nullptr);
         if (res[g].code) res[g].err = g_err;
     };
     if (G == 1) {
@@ -1267,6 +1287,7 @@ int b200ens_solve_device(b200ens_model* m, const b200ens_opts* o, int32_t device
     int rc = check_opts(m, o, n_save, d_dW);
     if (rc) return rc;
     if (timing) memset(timing, 0, sizeof *timing);
+    if (o->save_everystep) return fail(B200ENS_E_UNSUPPORTED, "save_everystep is served by b200ens_solve (host buffers) only");
     if (N <= 0) return N == 0 ? 0 : fail(B200ENS_E_INVALID, "N < 0");
     if (!d_u0 || !d_retcode || (m->n_param && !d_p) || (n_save && (!d_saveat || !d_out_u)))
         return fail(B200ENS_E_INVALID, "null buffer");

@@ -117,6 +117,10 @@ struct B2Args {
     // compile-time indices from the constant bank: no registers, FMA constant operands.
     double tol_a[32], tol_r[32];
     float f_tol_a[32], f_tol_r[32];
+    // save_everystep: out_u is [N][n_save = capacity][n_state], every_t [N][capacity] receives the step times; slot 0 is
+    // (t0, u0), slot k the state after the k-th accepted step; slots past the capacity are dropped (stats.naccept tells)
+    void* every_t;
+    int save_every, pad1_;
 };
 
 #if B2_F64

@@ -91,6 +91,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     const real qoldinit = B2_ARG(a, qoldinit), dtmax = B2_ARG(a, dtmax), dtmin = B2_ARG(a, dtmin);
     const float beta1 = a.f_beta1, beta2 = a.f_beta2;
     const float lqinit = b2_fastlog2((float)qoldinit);
+    constexpr bool EVERY = ADAPT < 0;   // save_everystep exists in the generic entry only (specialised entries: saveat)
     const bool adaptive = ADAPT < 0 ? (a.adaptive != 0) : (ADAPT != 0);
     const bool save_tstops = TSTOPS < 0 ? (a.save_tstops != 0) : (TSTOPS != 0);
 
@@ -159,11 +160,21 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                         si = 0;
                         naccept = nreject = nevents = 0;
                         // the first saved value is u0 itself (test/core.jl:34)
-                        while (si < n_save && __ldg(gsave + si) <= t0) {
-                            sink.put(si, u);
-                            si++;
+                        if (EVERY && a.save_every) {
+                            // save_everystep: slot 0 = (t0, u0); `si` counts the slots written, no saveat grid
+                            if (n_save > 0) {
+                                sink.put(0, u);
+                                reinterpret_cast<real*>(a.every_t)[idx * (long long)n_save] = t0;
+                            }
+                            si = 1;
+                            tau_next = (real)__int_as_float(0x7f800000);
+                        } else {
+                            while (si < n_save && __ldg(gsave + si) <= t0) {
+                                sink.put(si, u);
+                                si++;
+                            }
+                            tau_next = si < n_save ? __ldg(gsave + si) : (real)__int_as_float(0x7f800000);
                         }
-                        tau_next = si < n_save ? __ldg(gsave + si) : (real)__int_as_float(0x7f800000);
                         alg.start(u, p, t);
                         nf = 1;
                         if (AUTODT && adaptive && !(dt_user > (real)0)) {
@@ -596,11 +607,21 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
 #endif
             if (adaptive) dt = b2_min(dtmax, dtnew);
             if (rc == 0 && !(t < t1)) rc = B2_RC_SUCCESS;
+            if (EVERY && a.save_every) {   // the state after this accepted step (after callbacks), with its time
+                if (si < n_save) {
+                    sink.put(si, u);
+                    reinterpret_cast<real*>(a.every_t)[idx * (long long)n_save + si] = t;
+                }
+                si++;
+            }
         }
 
         // ---------------- phase 4: retire finished / failed lanes
         if (rc != 0) {
-            if (rc == B2_RC_TERMINATED) {
+            if (EVERY && a.save_every) {   // unused slots: NaN in both arrays
+                for (int k = si; k < n_save; k++) reinterpret_cast<real*>(a.every_t)[idx * (long long)n_save + k] = (real)__int_as_float(0x7fc00000);
+                sink.fill(si < n_save ? si : n_save, n_save, (real)__int_as_float(0x7fc00000));
+            } else if (rc == B2_RC_TERMINATED) {
                 for (; si < n_save; si++) sink.put(si, u);
             } else if (rc != B2_RC_SUCCESS) {
                 sink.fill(si, n_save, (real)__int_as_float(0x7fc00000));

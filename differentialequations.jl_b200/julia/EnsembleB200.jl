@@ -32,7 +32,7 @@ mutable struct Opts
     maxiters::Int64; seed::UInt64; traj_offset::UInt64
     noise_injected::Int32; event_terminate::Int32; interp_points::Int32; save_tstops::Int32
     device_mask::UInt32; refill_threshold::Int32; block_threads::Int32; stage_outputs::Int32
-    work_order::Int32; reserved0::Int32
+    work_order::Int32; save_everystep::Int32
     abstol_vec::Ptr{Float64}; reltol_vec::Ptr{Float64}
     Opts() = new()
 end

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200ENS_ABI_VERSION 3
+#define B200ENS_ABI_VERSION 4
 
 /* scalar type of u, p, t (Julia eltype(u0)) */
 enum b200ens_dtype { B200ENS_F32 = 0, B200ENS_F64 = 1 };
@@ -117,7 +117,12 @@ typedef struct b200ens_opts {
     int32_t work_order;     /* -1 auto (on for adaptive ODE solves of >= 32768 trajectories per device chunk), 0 caller's
                                order, 1 integrate trajectories in descending expected-work order (device-side counting
                                sort on the initial-step proxy; scheduling only, results are bit-identical) */
-    int32_t reserved0;
+    int32_t save_everystep; /* 1: save every accepted step instead of the saveat grid (upstream default without saveat):
+                               n_save is then the CAPACITY per trajectory, saveat is ignored (may be NULL), out_u is
+                               [N][n_save][n_state] and out_t (required) is [N][n_save] of the state type: slot 0 = (t0, u0),
+                               slot k = after the k-th accepted step, unused slots NaN; a trajectory with more than
+                               n_save - 1 accepted steps keeps integrating, the surplus is dropped (stats.naccept tells).
+                               ODE steppers, one-thread kernels; b200ens_solve only */
     const double* abstol_vec; /* NULL, or n_state per-component absolute tolerances (solve(...; abstol = [...])); overrides abstol */
     const double* reltol_vec; /* NULL, or n_state per-component relative tolerances; overrides reltol */
 } b200ens_opts;

@@ -59,6 +59,8 @@ typedef struct {
     void *vcond, *vaffect;    /* VectorContinuousCallback: vcond(g,u,p,t) fills ncond values, vaffect(u,p,t,idx); has_event=1 */
     int32_t ncond, pad2_;
     const double* mass;       /* NULL, or constant mass matrix [n_state][n_state] (M u' = f; Rodas4/5/5P only) */
+    void* every_t;            /* save_everystep: step times [N][n_save] of the state type; n_save = capacity, saveat ignored */
+    int32_t save_everystep, pad3_;
 } orc_opts;
 
 /* u0 [N][n], p [N][m], saveat [n_save], out_u [N][n_save][n], retcode [N], stats [N] or NULL.

@@ -35,6 +35,7 @@ class Opts(C.Structure):
         ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double)),
         ("vcond", C.c_void_p), ("vaffect", C.c_void_p), ("ncond", C.c_int32), ("pad2_", C.c_int32),
         ("mass", C.POINTER(C.c_double)),
+        ("every_t", C.c_void_p), ("save_everystep", C.c_int32), ("pad3_", C.c_int32),
     ]
 
 
@@ -100,7 +101,7 @@ def fns_from_host_model(dll, f64):
 
 def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adaptive=True, dtype=np.float64,
           maxiters=100000, dW=None, seed=0, event=False, terminate=False, interp_points=10, nthreads=0,
-          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, ncond=0, mass_matrix=None, **ctl):
+          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, ncond=0, mass_matrix=None, save_everystep=0, **ctl):
     """Run the oracle.  model: built-in name, or fns = dict(rhs=ptr, jac=ptr, ...)."""
     L = lib()
     f64 = np.dtype(dtype) == np.float64
@@ -149,10 +150,17 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
         dW = np.ascontiguousarray(dW, dtype=dtype)
     fn = L.orc_solve_f64 if f64 else L.orc_solve_f32
     vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    times = None
+    if save_everystep:   # n_save = len(saveat) is the capacity; the saveat values themselves are ignored
+        times = np.empty((N, len(saveat)), dtype=dtype)
+        o.every_t = times.ctypes.data_as(C.c_void_p)
+        o.save_everystep = 1
     err = fn(C.byref(o), C.c_int64(N), vp(u0), vp(p), vp(saveat), vp(dW), vp(out), vp(rc), vp(stats),
              C.c_int(nthreads))
     if err != 0:
         raise RuntimeError(f"oracle error {err}")
+    if save_everystep:
+        return out, rc, stats, times
     return out, rc, stats
 
 

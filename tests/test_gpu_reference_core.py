@@ -233,3 +233,43 @@ def test_mass_matrix_dae_rodas(B, gpu_lib, oracle):
         B.solve(prob, B.Tsit5())
     with pytest.raises(NotImplementedError):
         B.solve(prob, B.Rodas5P(), dense=True)
+
+
+def test_save_everystep_default_for_single_solves(B, gpu_lib, oracle):
+    """Without saveat upstream saves every accepted step (save_everystep = true): sol.t / sol.u of a single solve hold
+    the whole step sequence (test/core.jl:14-18 only pins length > 0 and sol.u[1] == u0).  Bit-identical to the oracle's
+    step sequence; the capacity grows until the longest trajectory fits; ensembles opt in."""
+    from b200ens import workloads as W
+    from helpers import oracle_fns
+
+    prob = W.lorenz_problem(np.float64, (0.0, 10.0))
+    sol = B.solve(prob, B.Tsit5(), dt=0.1)                       # no saveat -> every step
+    n = sol.stats["naccept"] + 1
+    assert len(sol.t) == n and len(sol.u) == n and n > 50
+    assert sol.t[0] == 0.0 and sol.t[-1] == 10.0 and np.all(np.diff(sol.t) > 0)
+    assert np.array_equal(sol.u[0], prob.u0)
+    model = B.build_model(prob, B.Tsit5(), split=False)
+    out, rc, st, tt = oracle.solve(None, "Tsit5", prob.u0[None, :], prob.p[None, :], (0.0, 10.0), np.zeros(256), 0.1,
+                                   fns=oracle_fns(oracle, B, model), save_everystep=1)
+    assert st[0, 0] + 1 == n
+    assert np.array_equal(sol.t, tt[0, :n]) and np.array_equal(sol.u, out[0, :n])
+    # with saveat the grid wins; the end state is the same either way
+    grid = B.solve(prob, B.Tsit5(), dt=0.1, saveat=[0.0, 10.0])
+    assert np.array_equal(grid.u[-1], sol.u[-1])
+    # ensemble, opt-in: ragged lengths, capacity doubling (tight tolerance -> > 256 steps), callbacks included
+    N = 100
+    u0, p = W.lorenz_params(N, "random", seed=6)
+    es = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), B.Vern7(), B.EnsembleB200(), trajectories=N, dt=0.01, abstol=1e-12,
+                 reltol=1e-12, save_everystep=True)
+    assert es.u_array.shape[1] >= int(es.stats[:, 0].max()) + 1 > 256
+    for i in (0, 50, 99):
+        s = es[i]
+        assert len(s.t) == es.stats[i, 0] + 1 and s.t[-1] == 10.0 and not np.isnan(s.u).any()
+    ref = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), B.Vern7(), B.EnsembleB200(), trajectories=N, dt=0.01, abstol=1e-12,
+                  reltol=1e-12, saveat=[10.0])
+    assert np.array_equal(np.stack([es[i].u[-1] for i in range(N)]), ref.u_array[:, 0])
+    cbt = B.ContinuousCallback(lambda u, t, integrator: u[2] - 20.0, lambda integrator: B.terminate_b(integrator))
+    term = B.solve(prob, B.Tsit5(), dt=0.1, callback=cbt)
+    assert term.retcode == B.ReturnCode.Terminated and abs(term.u[-1][2] - 20.0) < 1e-6 and term.t[-1] < 10.0
+    rob = B.solve(W.robertson_problem(), B.Rodas5P())            # the stiff example keeps its step list too
+    assert rob.retcode == B.ReturnCode.Success and len(rob.t) == rob.stats["naccept"] + 1 and rob.t[-1] == 1e5

@@ -90,7 +90,7 @@ def test_solve_argument_errors(B):
 
     prob = W.lorenz_problem()
     with pytest.raises(NotImplementedError):
-        B.solve(prob, B.Tsit5(), save_everystep=True, dt=0.1)
+        B.solve(W.gbm_problem(), B.EM(), save_everystep=True, dt=0.1)                   # SDE: pass the grid as saveat
     with pytest.raises(TypeError):
         B.solve(B.EnsembleProblem(prob), B.Tsit5(), B.EnsembleB200(), dt=0.1)          # trajectories missing
     with pytest.raises(TypeError):

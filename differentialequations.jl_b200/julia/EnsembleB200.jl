@@ -61,6 +61,11 @@ function model_sources(prob, alg)
     us, ps = collect(u), collect(p)
     du = SciMLBase.isinplace(prob) ? (d = similar(us, Num); prob.f(d, us, ps, t); d) : prob.f(us, ps, t)
     rhs = cuda_source("b2_rhs", "du", du)
+    M = prob.f.mass_matrix                              # ODEFunction(f; mass_matrix = M): constant table in the RHS source
+    if !(M isa SciMLBase.LinearAlgebra.UniformScaling)
+        rhs = "#undef B2_HAS_MASS\n#define B2_HAS_MASS 1\nstatic constexpr double B2_MASS_[$(n*n)] = {" *
+              join(string.(Float64.(vec(permutedims(Matrix(M))))), ", ") * "};\n" * rhs
+    end
     jac = nameof(typeof(alg)) in (:Rosenbrock23, :Rodas4, :Rodas5, :Rodas5P) ?
           cuda_source("b2_jac", "J", vec(permutedims(Symbolics.jacobian(du, us)))) : nothing
     noise = prob isa SDEProblem ? cuda_source("b2_noise", "g", prob.g(us, ps, t)) : nothing
@@ -88,12 +93,17 @@ function __solve(eprob::AbstractEnsembleProblem, alg, ens::EnsembleB200; traject
         check(ccall((:b200ens_compile, LIB), Cint, (Ref{ModelDesc}, Ref{Ptr{Cvoid}}, Ptr{UInt8}, Csize_t), d, model, log, length(log)))
     end
     o = Opts(); ccall((:b200ens_opts_init, LIB), Cvoid, (Ref{Opts},), o)
-    o.adaptive = adaptive; o.t0, o.t1 = prob.tspan; o.dt = dt; o.abstol = abstol; o.reltol = reltol
+    o.adaptive = adaptive; o.t0, o.t1 = prob.tspan; o.dt = dt
+    # scalar tolerances, or one per state component (solve(prob, Rodas5P(); abstol = [1e-8, 1e-14, 1e-6]))
+    atolv = abstol isa AbstractVector ? collect(Float64, abstol) : Float64[]
+    rtolv = reltol isa AbstractVector ? collect(Float64, reltol) : Float64[]
+    o.abstol = isempty(atolv) ? abstol : atolv[1]; o.reltol = isempty(rtolv) ? reltol : rtolv[1]
+    o.abstol_vec = isempty(atolv) ? C_NULL : pointer(atolv); o.reltol_vec = isempty(rtolv) ? C_NULL : pointer(rtolv)
     o.maxiters = maxiters; o.seed = seed; o.refill_threshold = ens.refill_threshold
     o.device_mask = isempty(ens.devices) ? 0 : reduce(|, UInt32(1) .<< ens.devices)
     out = Array{T, 3}(undef, n, length(ts), N)          # column-major == [N][n_save][n_state] of the ABI
     rc = Vector{Int32}(undef, N); st = Vector{Stats}(undef, N); tm = Timing()
-    elapsed = @elapsed check(ccall((:b200ens_solve, LIB), Cint,
+    elapsed = GC.@preserve atolv rtolv @elapsed check(ccall((:b200ens_solve, LIB), Cint,
         (Ptr{Cvoid}, Ref{Opts}, Int64, Ptr{T}, Ptr{T}, Ptr{T}, Int32, Ptr{T}, Ptr{T}, Ptr{T}, Ptr{Int32}, Ptr{Stats}, Ref{Timing}),
         model[], o, N, U0, P, ts, length(ts), C_NULL, out, C_NULL, rc, st, tm))
     ccall((:b200ens_free, LIB), Cvoid, (Ptr{Cvoid},), model[])

@@ -35,14 +35,7 @@
 // the common explicit case (adaptive, saveat interpolated, caller-supplied dt) folded at compile time
 extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble_kernel_adaptive(const __grid_constant__ B2Args a) {
 #if B2_ALG == 1
-// Shared-memory save queue (b2_ode_driver.cuh, SAVEQ): OFF.  Measured on B200 (profiles/README.md): bit-identical
-// results and ~8 % fewer issued instructions on paper, but the Float32 kernel sits exactly at the 72-register budget
-// of 7 CTAs/SM and the queue state pushes it over: 186 B of spills inside the main loop, 1.59 ms instead of 0.955 ms at
-// 7 CTAs/SM, 1.15 ms at 5 CTAs/SM (96 registers).  Kept for a later round (needs ~4 registers freed elsewhere first).
-#ifndef B2_SAVEQ
-#define B2_SAVEQ 0
-#endif
-    b2_ode_driver<B2Tsit5, 1, 0, 0, 0, B2_SAVEQ>(a);
+    b2_ode_driver<B2Tsit5, 1, 0, 0, 0>(a);
 #else
     b2_ode_driver<B2Vern7, 1, 0, 0, 0>(a);
 #endif

@@ -184,35 +184,6 @@ struct B2Tsit5 {
             B2_KBAR;
         }
     }
-#if !B2_KSMEM && !B2_X2 && !B2_SPLIT
-    // Save queue (b2_ode_driver.cuh, SAVEQ): everything interp() needs from this step, as SNAPW words of a queue entry
-    // (word w of entry e lives at q[w * qstride + e]), and the same interpolation from such an entry.
-    static constexpr int SNAPW = 7 * B2_NV;
-    __device__ __forceinline__ void snap_store(real* q, int qstride) const {
-#pragma unroll
-        for (int i = 0; i < B2_NV; i++) {
-            q[(0 * B2_NV + i) * qstride] = k1[i];
-            q[(1 * B2_NV + i) * qstride] = k2[i];
-            q[(2 * B2_NV + i) * qstride] = k3[i];
-            q[(3 * B2_NV + i) * qstride] = k4[i];
-            q[(4 * B2_NV + i) * qstride] = k5[i];
-            q[(5 * B2_NV + i) * qstride] = k6[i];
-            q[(6 * B2_NV + i) * qstride] = k7[i];
-        }
-    }
-    __device__ __forceinline__ void snap_load(const real* q, int qstride) {
-#pragma unroll
-        for (int i = 0; i < B2_NV; i++) {
-            k1[i] = q[(0 * B2_NV + i) * qstride];
-            k2[i] = q[(1 * B2_NV + i) * qstride];
-            k3[i] = q[(2 * B2_NV + i) * qstride];
-            k4[i] = q[(3 * B2_NV + i) * qstride];
-            k5[i] = q[(4 * B2_NV + i) * qstride];
-            k6[i] = q[(5 * B2_NV + i) * qstride];
-            k7[i] = q[(6 * B2_NV + i) * qstride];
-        }
-    }
-#endif
     // Coefficient form of the interpolant for ONE component (used by the event search, which evaluates the dense
     // output many times per step): u_i(t + th*dt) = up_i + dt * th*(C1 + th*(C2 + th*(C3 + th*C4))), C_j = sum_s r_sj k_s[i]
     static constexpr int DEG = 4;

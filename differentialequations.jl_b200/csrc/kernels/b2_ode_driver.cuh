@@ -14,61 +14,10 @@
 #pragma once
 #include "b2_common.cuh"
 
-#ifndef B2_QCAP
-#define B2_QCAP (B2_F64 ? 48 : 64)   // entries per warp; needs >= 32 + (drain threshold - 1) with partial pre-drains
-#endif
-// Save-queue entry codec.  Entry words (SoA over entries, stride B2_QCAP): SNAPW stage values, B2_N u_prev, dt,
-// tau - t_prev, output offset (element index into out_u; stored as the bit pattern of an integer of the word size).
-template <class Alg, int ON>
-struct B2_SaveQ {
-    static constexpr int WORDS = 1;
-    __device__ static __forceinline__ void put(real*, const Alg&, const real (&)[B2_N], real, real, long long) {}
-    __device__ static __forceinline__ void run(const real*, real*) {}
-};
-template <class Alg>
-struct B2_SaveQ<Alg, 1> {
-    static constexpr int WORDS = Alg::SNAPW + B2_N + 3;
-    __device__ static __forceinline__ void put(real* q, const Alg& alg, const real (&up)[B2_N], real dts, real dtau, long long off) {
-        alg.snap_store(q, B2_QCAP);
-#pragma unroll
-        for (int i = 0; i < B2_N; i++) q[(Alg::SNAPW + i) * B2_QCAP] = up[i];
-        q[(Alg::SNAPW + B2_N) * B2_QCAP] = dts;
-        q[(Alg::SNAPW + B2_N + 1) * B2_QCAP] = dtau;
-#if B2_F64
-        q[(Alg::SNAPW + B2_N + 2) * B2_QCAP] = __longlong_as_double(off);
-#else
-        q[(Alg::SNAPW + B2_N + 2) * B2_QCAP] = __uint_as_float((unsigned)off);
-#endif
-    }
-    __device__ static __noinline__ void run(const real* q, real* gout) {
-        Alg tmp;
-        tmp.snap_load(q, B2_QCAP);
-        real up[B2_N], w[B2_N];
-#pragma unroll
-        for (int i = 0; i < B2_N; i++) up[i] = q[(Alg::SNAPW + i) * B2_QCAP];
-        const real dts = q[(Alg::SNAPW + B2_N) * B2_QCAP];
-        const real dtau = q[(Alg::SNAPW + B2_N + 1) * B2_QCAP];
-#if B2_F64
-        const long long off = __double_as_longlong(q[(Alg::SNAPW + B2_N + 2) * B2_QCAP]);
-#else
-        const long long off = (long long)__float_as_uint(q[(Alg::SNAPW + B2_N + 2) * B2_QCAP]);
-#endif
-        tmp.interp(up, up, dtau / dts, dts, w);
-#pragma unroll
-        for (int i = 0; i < B2_N; i++) gout[off + i] = w[i];
-    }
-};
-
 // ADAPT / TSTOPS: 0 or 1 = compile-time specialisation of the two solve options that sit in the per-iteration
 // control path, -1 = read them from the argument block.  AUTODT = 0 compiles the automatic-initial-step block out
 // (the specialised entry is only launched with a caller-supplied dt; keeps its register pressure down).
-// SAVEQ = 1 (Tsit5 without callbacks, specialised entry): saveat interpolations go through a per-warp SHARED-MEMORY
-// QUEUE.  Lanes cross their save points on different iterations: the warp-convergent saveat block ran in 91 % of the
-// iterations with 5 of 32 lanes doing useful work (ncu: 18 % of all issue slots).  With the queue a lane that crosses a
-// save point only stores what the interpolation needs (its 7 stage vectors, u_prev, dt, tau - t_prev, the output
-// offset) into the next free entry; whenever 32 entries are pending the whole warp interpolates 32 of them at full
-// lane efficiency and stores the results.  Same interpolation arithmetic, so the saved values are bit-identical.
-template <class Alg, int ADAPT = -1, int TSTOPS = -1, int AUTODT = 1, int STAGED = -1, int SAVEQ = 0>
+template <class Alg, int ADAPT = -1, int TSTOPS = -1, int AUTODT = 1, int STAGED = -1>
 __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     extern __shared__ __align__(16) unsigned char b2_smem[];
     const unsigned lane = threadIdx.x & 31u;
@@ -119,19 +68,6 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     sink.stage = stride ? warp_stage + (size_t)lane * stride : nullptr;
     sink.gout = gout;
     sink.base = 0;
-    // ---- save queue (SAVEQ): word w of entry e at warp_q[w * B2_QCAP + e]
-    constexpr int QW = B2_SaveQ<Alg, SAVEQ>::WORDS;
-    __shared__ real s_saveq[SAVEQ ? (B2_BLOCK / 32) * QW * B2_QCAP : 1];
-    real* const warp_q = s_saveq + (SAVEQ ? warp_in_block * QW * B2_QCAP : 0);
-    int q_head = 0, q_count = 0;   // warp-uniform
-    auto q_drain = [&](int n) {    // interpolate the n (<= 32) oldest entries, one per lane
-        const int tail = q_head - q_count + (q_head - q_count < 0 ? B2_QCAP : 0);
-        int e = tail + (int)lane;
-        e -= e >= B2_QCAP ? B2_QCAP : 0;
-        if ((int)lane < n) B2_SaveQ<Alg, SAVEQ>::run(warp_q + e, gout);
-        q_count -= n;
-        __syncwarp();
-    };
 
     for (;;) {
         // ---------------- phase 0: retire / refill (warp-uniform control flow)
@@ -214,11 +150,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
 #endif
                     }
                 }
-                if (__ballot_sync(B2_FULL, active) == 0u) {
-                    if (SAVEQ)
-                        while (q_count > 0) q_drain(q_count < 32 ? q_count : 32);
-                    break;
-                }
+                if (__ballot_sync(B2_FULL, active) == 0u) break;
             }
         }
 
@@ -520,34 +452,6 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
         // (measured with ncu: 60% of all issue slots, 17.7 active threads per instruction).
         // Instead the whole warp evaluates the interpolant whenever ANY lane needs a save, each
         // lane with its own theta, and only the lanes that need it store.
-        if (SAVEQ) {
-            for (;;) {
-                const real tau = tau_next;
-                const bool need = accepted && tau <= tnew;
-                const unsigned mneed = __ballot_sync(B2_FULL, need);
-                if (!mneed) break;
-                const bool at_end = need && tau == tnew;     // the step lands exactly on the save point: store u_new
-                if (at_end) sink.put(si, un);
-                const bool enq = need && !at_end;
-                const unsigned menq = __ballot_sync(B2_FULL, enq);
-                const int ne = __popc(menq);
-                if (ne) {
-                    while (q_count + ne > B2_QCAP) q_drain(q_count < 32 ? q_count : 32);
-                    int e = q_head + __popc(menq & ((1u << lane) - 1u));
-                    e -= e >= B2_QCAP ? B2_QCAP : 0;
-                    if (enq) B2_SaveQ<Alg, SAVEQ>::put(warp_q + e, alg, u, dts, tau - tprev, sink.base + (long long)si * B2_N);
-                    q_head += ne;
-                    q_head -= q_head >= B2_QCAP ? B2_QCAP : 0;
-                    q_count += ne;
-                    __syncwarp();
-                }
-                if (need) {
-                    si++;
-                    tau_next = si < n_save ? __ldg(gsave + si) : (real)__int_as_float(0x7f800000);
-                }
-                if (q_count >= 32) q_drain(32);
-            }
-        } else
         for (;;) {
             const real tau = tau_next;
             const bool need = accepted && tau <= tnew;

@@ -145,3 +145,25 @@ def test_chunked_pipeline_matches_single_launch(B, gpu_lib, monkeypatch):
     chunked = _solve_gpu(B, np.float64, u0, p, SAVEAT, 0.1)
     assert chunked.timing["launches"] == 8
     assert np.array_equal(base.u_array, chunked.u_array) and np.array_equal(base.stats, chunked.stats)
+
+
+def test_packed_kernel_with_the_nvrtc_it_is_validated_for(gpu_lib):
+    """The packed FP32x2 kernel is only honoured under NVRTC 12.8 (see test_packed_ffma2_kernel_bit_identical).  The
+    image's toolkit NVRTC is 12.9, PyTorch bundles 12.8: run the packed parity test in a subprocess with
+    B200ENS_NVRTC pointing at that one, so the packed path stays tested."""
+    import glob
+    import os
+    import subprocess
+    import sys
+    import sysconfig
+
+    cands = glob.glob(os.path.join(sysconfig.get_paths()["purelib"], "nvidia", "cuda_nvrtc", "lib", "libnvrtc.so.12*"))
+    if not cands:
+        pytest.skip("no NVRTC 12.8 in site-packages")
+    env = dict(os.environ, B200ENS_NVRTC=sorted(cands)[0])
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-k",
+                        "test_packed_ffma2_kernel_bit_identical", "-rs"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    if "1 skipped" in r.stdout:
+        pytest.skip("that NVRTC is not 12.8 either: " + r.stdout[-300:])
+    assert "1 passed" in r.stdout, r.stdout[-2000:]

@@ -66,15 +66,17 @@ def oracle_throughput(dtype, sweep, n_target, seconds, seed=0):
     from b200ens import workloads as W
 
     oracle_py.build()
-    cores = int(oracle_py.lib().orc_max_threads())
+    # all host cores this process may use -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers,
+    # which would silently cripple the reference arm at N > 1
+    cores = max(int(oracle_py.lib().orc_max_threads()), len(os.sched_getaffinity(0)))
     u0, p = W.lorenz_params(n_target, sweep, seed, dtype)
     probe = min(n_target, 20000)
     t = time.perf_counter()
-    oracle_py.solve("lorenz", "Tsit5", u0[:probe], p[:probe], TSPAN, SAVEAT, DT0, abstol=ABSTOL, reltol=RELTOL, dtype=dtype)
+    oracle_py.solve("lorenz", "Tsit5", u0[:probe], p[:probe], TSPAN, SAVEAT, DT0, abstol=ABSTOL, reltol=RELTOL, dtype=dtype, nthreads=cores)
     rate = probe / (time.perf_counter() - t)
     n = int(max(probe, min(n_target, rate * seconds)))
     t = time.perf_counter()
-    _, rc, st = oracle_py.solve("lorenz", "Tsit5", u0[:n], p[:n], TSPAN, SAVEAT, DT0, abstol=ABSTOL, reltol=RELTOL, dtype=dtype)
+    _, rc, st = oracle_py.solve("lorenz", "Tsit5", u0[:n], p[:n], TSPAN, SAVEAT, DT0, abstol=ABSTOL, reltol=RELTOL, dtype=dtype, nthreads=cores)
     el = time.perf_counter() - t
     steps = int(st[:, 0].sum() + st[:, 1].sum())
     return {"value": n / el, "unit": "trajectories/s", "cores": cores, "kind": "port",

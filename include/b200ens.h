@@ -53,13 +53,14 @@ enum b200ens_error {
 /* model flags */
 #define B200ENS_MODEL_FAST_MATH 1u /* let NVRTC contract a*b+c in MODEL code (breaks bitwise oracle parity) */
 #define B200ENS_MODEL_PACKED_X2 2u /* Float32 Tsit5 without callbacks: two trajectories per thread in packed FP32
-                                      (FFMA2/FADD2/FMUL2, sm_100+); bit-identical results; measured 5% SLOWER than the
-                                      scalar kernel on B200 (profiles/README.md), hence opt-in */
+                                      (FFMA2/FADD2/FMUL2, sm_100+); bit-identical results under NVRTC 12.8 only (with any
+                                      other NVRTC the request falls through to the scalar kernel); measured 5% SLOWER
+                                      than the scalar kernel on B200 (profiles/README.md), hence opt-in */
 
 #define B200ENS_MODEL_KSMEM 4u     /* force ERK stage vectors into shared memory (default: automatic when the register variant spills > 4 KB) */
 #define B200ENS_MODEL_SPLIT 8u     /* force the split kernel (one trajectory per lane of a 4-warp CTA, components split over the
-                                      warps; Tsit5 / Vern7 without DiscreteCallback; default: automatic when the one-thread
-                                      variant spills > 4 KB) */
+                                      warps; Tsit5 / Vern7 with at most a scalar ContinuousCallback; default: automatic when
+                                      the one-thread variant spills > 1 KB (Vern7) / 4 KB (Tsit5)) */
 #define B200ENS_MODEL_NOSPLIT 16u  /* never use the split kernel */
 
 /* What a problem looks like to the library: ODEProblem / SDEProblem (qa.jl:86,103) with f,
@@ -71,6 +72,11 @@ enum b200ens_error {
  *   __device__ void b2_noise    (real* g,  const real* u, const real* p, real t);   diagonal noise
  *   __device__ real b2_condition(const real* u, const real* p, real t);             ContinuousCallback
  *   __device__ void b2_affect   (real* u,  const real* p, real t);
+ *   VectorContinuousCallback (qa.jl:124): condition_src carries `#define B2_NCOND <len>` and defines
+ *   __device__ void b2_vcondition(real* g, const real* u, const real* p, real t);   affect_src defines
+ *   __device__ void b2_vaffect  (real* u,  const real* p, real t, int idx);         idx = 0-based event index
+ *   constant mass matrix (M u' = f, Rodas4/5/5P): rhs_src carries `#define B2_HAS_MASS 1` and
+ *   `static constexpr double B2_MASS_[n*n]` (row-major)
  *   __device__ bool b2_dcondition(const real* u, const real* p, real t);            DiscreteCallback (qa.jl:36,
  *   __device__ void b2_daffect  (real* u,  const real* p, real t);                   test/core.jl:76-77)
  * NULL = absent.  One ContinuousCallback and one DiscreteCallback may be combined (CallbackSet, qa.jl:24):

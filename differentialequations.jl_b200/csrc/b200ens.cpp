@@ -778,7 +778,9 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
         chunk = std::max<long long>(1, atoll(e));
         for (long long r = total; r > 0; r -= chunk) sched.push_back(std::min(chunk, r));
     } else {
-        const long long first = std::min<long long>(chunk, std::max<long long>(1 << 15, (total + 15) / 16));
+        long long frac = 16;
+        if (const char* e = getenv("B200ENS_FIRST_FRAC")) frac = std::max(2, atoi(e));   // experiments
+        const long long first = std::min<long long>(chunk, std::max<long long>(1 << 14, (total + frac - 1) / frac));
         long long r = total;
         if (r > 4 * first) {
             sched.push_back(first);

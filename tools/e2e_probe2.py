@@ -15,9 +15,11 @@ u0p = _lib.pinned_empty(u0.shape, dt); u0p[:] = u0
 pp = _lib.pinned_empty(p.shape, dt); pp[:] = p
 outp = _lib.pinned_empty((N, 11, 3), dt)
 rcp = _lib.pinned_empty((N,), np.int32); stp = _lib.pinned_empty((N, 4), np.int32)
-for slots in (4,):
+for frac in (16, 24, 32, 48):
+  os.environ['B200ENS_FIRST_FRAC'] = str(frac)
+  for slots in (4,):
     os.environ["B200ENS_SLOTS"] = str(slots)
-    for chunk in (0, 250000):
+    for chunk in (0,):
         if chunk:
             os.environ["B200ENS_CHUNK"] = str(chunk)
         else:
@@ -25,4 +27,4 @@ for slots in (4,):
         best = 1e9
         for i in range(6):
             t = time.perf_counter(); _, _, _, tm = model.solve(o, u0p, pp, SAVEAT, out=outp, rc=rcp, stats=stp); best = min(best, (time.perf_counter() - t) * 1e3)
-        print(json.dumps({"slots": slots, "chunk": chunk, "wall_ms": round(best, 3), "h2d": round(tm.h2d_ms, 3), "kern": round(tm.kernel_ms, 3), "d2h": round(tm.d2h_ms, 3), "launches": tm.launches}), flush=True)
+        print(json.dumps({"frac": frac, "slots": slots, "chunk": chunk, "wall_ms": round(best, 3), "h2d": round(tm.h2d_ms, 3), "kern": round(tm.kernel_ms, 3), "d2h": round(tm.d2h_ms, 3), "launches": tm.launches}), flush=True)

@@ -80,7 +80,7 @@ def oracle_throughput(dtype, sweep, n_target, seconds, seed=0):
     el = time.perf_counter() - t
     steps = int(st[:, 0].sum() + st[:, 1].sum())
     return {"value": n / el, "unit": "trajectories/s", "cores": cores, "kind": "port",
-            "sample": f"first {n} trajectories of the workload, CPU oracle (C, OpenMP dynamic, -O2, {cores} threads), "
+            "sample": f"first {n} trajectories of the workload, CPU oracle (C, OpenMP dynamic, -O2 -mfma -mavx2, {cores} threads), "
                       f"{el:.2f} s, {steps / el:.3g} attempted steps/s",
             "seconds": el, "n": n}
 

@@ -175,13 +175,30 @@ class DiscreteCallback:
 
 
 class CallbackSet:
-    """CallbackSet(cb...) (qa.jl:24): at most one ContinuousCallback and one DiscreteCallback on this back-end."""
+    """CallbackSet(cb...) (qa.jl:24): any number of ContinuousCallbacks plus at most one DiscreteCallback.  Several
+    ContinuousCallbacks are one VectorContinuousCallback to the kernel (same upstream semantics: the earliest root among
+    the conditions that change sign fires, and only its affect! runs)."""
 
     def __init__(self, *cbs):
-        self.continuous = [c for c in cbs if isinstance(c, (ContinuousCallback, VectorContinuousCallback))]
+        cont = [c for c in cbs if isinstance(c, (ContinuousCallback, VectorContinuousCallback))]
         self.discrete = [c for c in cbs if isinstance(c, DiscreteCallback)]
-        if len(self.continuous) > 1 or len(self.discrete) > 1 or len(self.continuous) + len(self.discrete) != len(cbs):
-            raise NotImplementedError("EnsembleB200 supports one ContinuousCallback plus one DiscreteCallback")
+        if len(self.discrete) > 1 or len(cont) + len(self.discrete) != len(cbs):
+            raise NotImplementedError("EnsembleB200 supports ContinuousCallbacks plus at most one DiscreteCallback")
+        if len(cont) > 1:
+            if any(isinstance(c, VectorContinuousCallback) for c in cont):
+                raise NotImplementedError("a VectorContinuousCallback cannot be combined with further continuous callbacks")
+            scalars = list(cont)
+
+            def condition(out, u, t, integrator, _cbs=scalars):
+                for k, c in enumerate(_cbs):
+                    out[k] = c.condition(u, t, integrator)
+
+            def affect(integrator, idx, _cbs=scalars):
+                _cbs[idx - 1].affect(integrator)
+
+            cont = [VectorContinuousCallback(condition, affect, len(scalars),
+                                             interp_points=max(c.interp_points for c in scalars))]
+        self.continuous = cont
 
 
 def _split_callbacks(callback):

@@ -237,12 +237,12 @@ def emit_vector_callback(cb, n_state, n_param):
         lines = [f"        const real n{i} = {_c(v)};" for i, v in changed] + [f"        u[{i}] = n{i};" for i, _ in changed]
         cases.append(f"    case {k}: {{\n" + "\n".join(lines) + "\n    }} break;".replace("}}", "}"))
         terminated.append(bool(it.terminated))
-    if any(terminated) and not all(terminated):
-        raise NotImplementedError("VectorContinuousCallback: terminate! must be called for every event index or none")
-    aff_src = ("__device__ __forceinline__ void b2_vaffect(real* __restrict__ u, const real* __restrict__ p, const real t, "
+    tmask = sum(1 << k for k, tm in enumerate(terminated) if tm)   # which event indices call terminate!(integrator)
+    aff_src = (f"#define B2_VTERM_MASK 0x{tmask:x}u\n"
+               "__device__ __forceinline__ void b2_vaffect(real* __restrict__ u, const real* __restrict__ p, const real t, "
                "const int idx) {\n    (void)u; (void)p; (void)t;\n    switch (idx) {\n" + "\n".join(cases) +
                "\n    default: break;\n    }\n}\n")
-    return cond_src, aff_src, all(terminated)
+    return cond_src, aff_src, False   # termination is per event index (B2_VTERM_MASK), not the global flag
 
 
 def emit_discrete_callback(cb, n_state, n_param):

@@ -477,6 +477,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                 alg.interp(u, un, th_end, dts, w);
 #ifdef B2_NCOND
                 b2_vaffect(w, p, t, ev_idx);
+                if ((B2_VTERM_MASK >> ev_idx) & 1u) rc = B2_RC_TERMINATED;   // this index's affect! called terminate!
 #else
                 (void)ev_idx;
                 b2_affect(w, p, t);

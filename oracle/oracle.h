@@ -57,7 +57,8 @@ typedef struct {
     int32_t devent_terminate, pad_;
     const double *abstol_vec, *reltol_vec;   /* NULL, or n_state per-component tolerances (override abstol / reltol) */
     void *vcond, *vaffect;    /* VectorContinuousCallback: vcond(g,u,p,t) fills ncond values, vaffect(u,p,t,idx); has_event=1 */
-    int32_t ncond, pad2_;
+    int32_t ncond;
+    uint32_t vterm_mask;      /* bit k: event index k terminates the trajectory */
     const double* mass;       /* NULL, or constant mass matrix [n_state][n_state] (M u' = f; Rodas4/5/5P only) */
     void* every_t;            /* save_everystep: step times [N][n_save] of the state type; n_save = capacity, saveat ignored */
     int32_t save_everystep, pad3_;

@@ -33,7 +33,7 @@ class Opts(C.Structure):
         ("cond", C.c_void_p), ("affect", C.c_void_p), ("dcond", C.c_void_p), ("daffect", C.c_void_p),
         ("devent_terminate", C.c_int32), ("pad_", C.c_int32),
         ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double)),
-        ("vcond", C.c_void_p), ("vaffect", C.c_void_p), ("ncond", C.c_int32), ("pad2_", C.c_int32),
+        ("vcond", C.c_void_p), ("vaffect", C.c_void_p), ("ncond", C.c_int32), ("vterm_mask", C.c_uint32),
         ("mass", C.POINTER(C.c_double)),
         ("every_t", C.c_void_p), ("save_everystep", C.c_int32), ("pad3_", C.c_int32),
     ]
@@ -115,7 +115,7 @@ def fns_from_host_model(dll, f64):
 
 def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adaptive=True, dtype=np.float64,
           maxiters=100000, dW=None, seed=0, event=False, terminate=False, interp_points=10, nthreads=0,
-          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, ncond=0, mass_matrix=None, save_everystep=0, **ctl):
+          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, ncond=0, vterm_mask=0, mass_matrix=None, save_everystep=0, **ctl):
     """Run the oracle.  model: built-in name, or fns = dict(rhs=ptr, jac=ptr, ...)."""
     L = lib()
     f64 = np.dtype(dtype) == np.float64
@@ -154,7 +154,7 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
     o.tgrad = get("tgrad") if fns else None
     o.cond, o.affect = (get("cond"), get("affect")) if event and not ncond else (None, None)
     if ncond:   # VectorContinuousCallback
-        o.vcond, o.vaffect, o.ncond = get("vcond"), get("vaffect"), int(ncond)
+        o.vcond, o.vaffect, o.ncond, o.vterm_mask = get("vcond"), get("vaffect"), int(ncond), int(vterm_mask)
     o.dcond, o.daffect = (get("dcond"), get("daffect")) if devent else (None, None)
     o.devent_terminate = int(dterminate)
     out = np.empty((N, len(saveat), n), dtype=dtype)

@@ -356,3 +356,28 @@ def test_sriw1_gbm_injected_pathwise_and_strong_accuracy(B, gpu_lib, oracle, dty
     ref2, _, _ = oracle.solve("gbm", "SRIW1", u0, p, (0.0, 1.0), [1.0], dt, dtype=dtype, seed=99, adaptive=False)
     rel = np.abs(sol2.u_array.astype(np.float64) - ref2.astype(np.float64)) / np.abs(ref2.astype(np.float64))
     assert rel.max() < (1e-8 if dtype == np.float64 else 5e-4), rel.max()
+
+
+def test_callbackset_of_continuous_callbacks_and_per_index_terminate(B, gpu_lib, oracle):
+    """CallbackSet(cb1, cb2) with two ContinuousCallbacks = one vector callback in the kernel; terminate! in one of the
+    affects ends only the trajectories whose FIRST event is that one.  Bit-identical to the oracle."""
+    from b200ens import workloads as W
+
+    N = 400
+    u0, p = W.lorenz_params(N, "random", seed=12)
+    prob = W.lorenz_problem(np.float64, (0.0, 5.0))
+    flip = B.ContinuousCallback(lambda u, t, integrator: u[0] + 2.0, lambda integrator: integrator.u.__setitem__(1, -integrator.u[1]))
+    stop = B.ContinuousCallback(lambda u, t, integrator: u[2] - 25.0, lambda integrator: B.terminate_b(integrator))
+    cs = B.CallbackSet(flip, stop)
+    saveat = np.linspace(0.0, 5.0, 11)
+    sol = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), B.Tsit5(), B.EnsembleB200(), trajectories=N, saveat=saveat, dt=0.05,
+                  abstol=1e-9, reltol=1e-9, callback=cs)
+    model = B.build_model(prob, B.Tsit5(), cs)
+    ref, rc, st = oracle.solve(None, "Tsit5", u0, p, (0.0, 5.0), saveat, 0.05, abstol=1e-9, reltol=1e-9, event=True, ncond=2,
+                               vterm_mask=0b10, fns=oracle_fns(oracle, B, model))
+    assert np.array_equal(sol.retcodes, rc) and np.array_equal(sol.stats, st)
+    ok, worst = within_tol(sol.u_array, ref, 1e-13, 1e-10)
+    assert ok, worst
+    term = sol.retcodes == 2
+    assert term.any() and (sol.retcodes == 1).any()
+    assert np.max(np.abs(sol.u_array[term, -1, 2] - 25.0)) < 1e-6        # held at the terminating event

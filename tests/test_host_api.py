@@ -81,8 +81,13 @@ def test_callback_tracing_and_rejection(B):
     assert "bool b2_dcondition" in dc and ">=" in dc and "u[0] = n0;" in da and dterm is False
     with pytest.raises(NotImplementedError):
         codegen.emit_discrete_callback(B.DiscreteCallback(lambda u, t, integ: t - 0.5, lambda integ: None), 1, 1)
+    # several ContinuousCallbacks in a CallbackSet are one VectorContinuousCallback to the kernel; terminate! is per index
+    cs = B.CallbackSet(cb, cbt, dcb)
+    assert isinstance(cs.continuous[0], B.VectorContinuousCallback) and cs.continuous[0].len == 2 and len(cs.discrete) == 1
+    vc, va, vterm = codegen.emit_vector_callback(cs.continuous[0], 2, 2)
+    assert "#define B2_NCOND 2" in vc and "#define B2_VTERM_MASK 0x2u" in va and vterm is False
     with pytest.raises(NotImplementedError):
-        B.CallbackSet(cb, cbt)
+        B.CallbackSet(dcb, dcb)
 
 
 def test_solve_argument_errors(B):
@@ -182,8 +187,8 @@ def test_vector_continuous_callback_codegen():
             B.terminate_b(integrator)
 
     cb = B.VectorContinuousCallback(condition, affect, 2)
-    with pytest.raises(NotImplementedError):                     # terminate! for one index only
-        codegen.emit_vector_callback(cb, 2, 1)
+    _, a0, _ = codegen.emit_vector_callback(cb, 2, 1)            # terminate! for index 2 only -> per-index mask
+    assert "#define B2_VTERM_MASK 0x2u" in a0
     cb2 = B.VectorContinuousCallback(condition, lambda integrator, idx: integrator.u.__setitem__(idx - 1, 0.0), 2)
     c, a, term = codegen.emit_vector_callback(cb2, 2, 1)
     assert "#define B2_NCOND 2" in c and "#define B2_COND_MASK 0x1u" in c and "b2_vcondition" in c

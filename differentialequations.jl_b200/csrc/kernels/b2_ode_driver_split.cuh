@@ -9,9 +9,9 @@
 //   * anything that contains a barrier (RHS evaluations inside the stepper, the error-norm gather, the event-data
 //     gather) is executed by all 128 threads unconditionally; per-lane predicates only select what is COMMITTED;
 //   * warp 0 alone talks to the work queue and writes retcodes / stats.
-// Supported: Tsit5 / Vern7, adaptive or fixed dt, saveat through the dense output or as tstops, ContinuousCallback,
-// expected-work ordering.  Not here (the host falls back to the one-thread kernel): DiscreteCallback, automatic
-// initial dt, output staging.
+// Supported: Tsit5 / Vern7, adaptive or fixed dt, automatic initial dt, saveat through the dense output or as tstops,
+// scalar ContinuousCallback, expected-work ordering, per-component tolerances.  Not here (the host keeps the
+// one-thread kernel for these): DiscreteCallback, VectorContinuousCallback, save_everystep, output staging.
 #pragma once
 #include "b2_common.cuh"
 #include "b2_split.cuh"

@@ -295,3 +295,21 @@ def test_sriw1_strong_order_on_gbm(oracle):
     assert 1.25 < o_sri < 1.75, (o_sri, e_sri)
     assert 0.3 < o_em < 0.7, o_em
     assert e_sri[-1] < e_em[-1] / 20
+
+
+def test_save_everystep_oracle_semantics(oracle):
+    """Every-step output of the oracle (the checker of the GPU's save_everystep path): slot 0 = (t0, u0), one slot per
+    accepted step, strictly increasing times ending at t1, NaN padding; surplus steps beyond the capacity are dropped
+    but still counted; the last saved state equals the saveat solve's end state."""
+    g = _load("lorenz_t1.json")
+    u0, p = [g["u0"]], [g["p"]]
+    out, rc, st, tt = oracle.solve("lorenz", "Tsit5", u0, p, (0.0, 1.0), np.zeros(64), 0.0, save_everystep=1)
+    n = st[0, 0] + 1
+    assert rc[0] == 1 and 10 < n < 64
+    assert tt[0, 0] == 0.0 and tt[0, n - 1] == 1.0 and np.all(np.diff(tt[0, :n]) > 0)
+    assert np.array_equal(out[0, 0], np.array(g["u0"])) and np.isnan(tt[0, n:]).all() and np.isnan(out[0, n:]).all()
+    end, _, st2 = oracle.solve("lorenz", "Tsit5", u0, p, (0.0, 1.0), [1.0], 0.0)
+    assert np.array_equal(end[0, 0], out[0, n - 1]) and np.array_equal(st2[0, :3], st[0, :3])
+    small, rc3, st3, tt3 = oracle.solve("lorenz", "Tsit5", u0, p, (0.0, 1.0), np.zeros(8), 0.0, save_everystep=1)
+    assert rc3[0] == 1 and st3[0, 0] == st[0, 0]                  # same step sequence, only 8 slots kept
+    assert np.array_equal(small[0], out[0, :8]) and np.array_equal(tt3[0], tt[0, :8])

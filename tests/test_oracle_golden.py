@@ -313,3 +313,19 @@ def test_save_everystep_oracle_semantics(oracle):
     small, rc3, st3, tt3 = oracle.solve("lorenz", "Tsit5", u0, p, (0.0, 1.0), np.zeros(8), 0.0, save_everystep=1)
     assert rc3[0] == 1 and st3[0, 0] == st[0, 0]                  # same step sequence, only 8 slots kept
     assert np.array_equal(small[0], out[0, :8]) and np.array_equal(tt3[0], tt[0, :8])
+
+
+@pytest.mark.parametrize("alg", ["Vern7", "Tsit5"])
+def test_net16_bolus_events_vs_independent_event_integrator(oracle, alg):
+    """BASELINE config 5 against an INDEPENDENT truth: scipy DOP853 with terminal events, the bolus applied by hand and
+    the integration restarted (tools/gen_golden.py).  Same number of events, same states at the save points."""
+    g = _load("net16_event.json")
+    u0 = np.zeros((1, 16))
+    u0[0, 0] = 1.0
+    for case in g["cases"]:
+        out, rc, st = oracle.solve("net16", alg, u0, [case["p"]], (0.0, 10.0), g["t"], 0.01, abstol=1e-11, reltol=1e-11,
+                                   event=True)
+        ref = np.array(case["u"])
+        assert rc[0] == 1
+        assert st[0, 3] == len(case["event_times"])              # events fire on exactly the same crossings
+        assert np.max(np.abs(out[0] - ref)) < 2e-8, np.max(np.abs(out[0] - ref))

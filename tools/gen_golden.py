@@ -6,6 +6,8 @@ available, so these vectors come from INDEPENDENT solvers, not from the referenc
     /root/reference/test/core.jl:22-30 and :39-46
   * linear: closed form 0.5*exp(1.01 t)   (test/core.jl:10-13)
   * philox: Random123 known-answer vectors for Philox4x32-10
+  * net16_event: the 16-species network with its bolus ContinuousCallback (config 5), scipy DOP853 + terminal events +
+    manual affect + restart
 Run:  python tools/gen_golden.py     (needs scipy; output is committed)
 """
 import json
@@ -60,3 +62,58 @@ json.dump({"source": "Random123 kat_vectors, Philox4x32-10 (SURVEY.md B.9)", "ve
     {"ctr": ["243f6a88", "85a308d3", "13198a2e", "03707344"], "key": ["a4093822", "299f31d0"],
      "out": ["d16cfe09", "94fdcceb", "5001e420", "24126ea1"]}]}, open(os.path.join(OUT, "philox_kat.json"), "w"), indent=1)
 print("golden vectors written to", OUT)
+
+# ---- config 5: 16-species network with the bolus ContinuousCallback, by an INDEPENDENT event integrator:
+# scipy DOP853 with a terminal event on X0 - theta (both directions, like ContinuousCallback's default affect_neg! =
+# affect!), the bolus applied by hand, integration restarted at the event time.
+NET16_W = [1.3, 0.42, 6.1, 0.17, 2.9, 0.88, 4.4, 0.23, 7.7, 1.9, 0.35, 3.3, 0.61, 5.2, 1.1]
+NET16_V = [0.7, 2.4, 0.19, 3.8, 0.52, 1.6, 0.11, 8.3, 0.93, 0.27, 4.9, 0.44, 2.2, 0.15, 6.6]
+NET16_Z = [0.9, 0.31, 2.7, 0.14, 1.8, 0.66, 3.9, 0.21, 5.5, 0.48, 1.2, 0.12, 2.1, 0.77]
+
+
+def net16(t, u, p):
+    du = np.zeros(16)
+    for i in range(15):
+        fl = p[0] * NET16_W[i] * u[i] - p[1] * NET16_V[i] * u[i + 1]
+        du[i] -= fl
+        du[i + 1] += fl
+    for i in range(14):
+        r = p[2] * NET16_Z[i] * u[i] * u[i + 1]
+        du[i] -= r
+        du[i + 1] -= r
+        du[i + 2] += r
+    du[0] -= p[3] * u[0]
+    return du
+
+
+def net16_with_events(p, ts, t1=10.0):
+    ev = lambda t, u, p: u[0] - p[4]
+    ev.terminal = True
+    u = np.zeros(16)
+    u[0] = 1.0
+    t, times, rows, k = 0.0, [], [], 0
+    while True:
+        grid = [x for x in ts[k:] if x > t or (x == t and k == 0)]
+        s = solve_ivp(net16, (t, t1), u, method="DOP853", rtol=1e-12, atol=1e-14, args=(p,), events=ev, dense_output=True)
+        t_end = s.t_events[0][0] if s.status == 1 else t1
+        while k < len(ts) and ts[k] <= t_end:      # save points up to (and including) the event time: pre-affect state
+            rows.append(s.sol(ts[k]).tolist())
+            k += 1
+        if s.status != 1:
+            break
+        times.append(float(t_end))
+        u = s.y_events[0][0].copy()
+        u[0] += p[5]
+        t = t_end
+    return times, rows
+
+
+ts = np.linspace(0.0, 10.0, 11)
+cases = []
+for p in ([1.0, 0.5, 0.8, 0.3, 0.25, 0.5], [2.2, 0.5, 0.4, 0.3, 0.25, 0.5], [0.45, 0.5, 1.9, 0.3, 0.25, 0.5]):
+    times, rows = net16_with_events(p, ts)
+    cases.append({"p": p, "event_times": times, "u": rows})
+json.dump({"problem": "16-species network + bolus ContinuousCallback (BASELINE config 5; oracle/models.c net16)", "t": ts.tolist(),
+           "cases": cases, "source": "scipy DOP853 rtol=1e-12 atol=1e-14, terminal events + manual affect + restart"},
+          open(os.path.join(OUT, "net16_event.json"), "w"), indent=1)
+print("net16 event golden written:", [len(c["event_times"]) for c in cases], "events")

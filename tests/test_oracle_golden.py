@@ -329,3 +329,28 @@ def test_net16_bolus_events_vs_independent_event_integrator(oracle, alg):
         assert rc[0] == 1
         assert st[0, 3] == len(case["event_times"])              # events fire on exactly the same crossings
         assert np.max(np.abs(out[0] - ref)) < 2e-8, np.max(np.abs(out[0] - ref))
+
+
+@pytest.mark.parametrize("alg,bound", [("Rodas5P", 1e-4), ("Rodas5", 1e-4), ("Rodas4", 1e-5), ("Rosenbrock23", 5e-2)])
+def test_van_der_pol_vs_radau(oracle, alg, bound):
+    """A second stiff pin for the Rosenbrock family: van der Pol with mu = 100 against scipy Radau (golden vector).
+    The model goes through the same sympy -> C emitter as the GPU path (RHS, analytic Jacobian)."""
+    from b200ens import codegen
+
+    def vdp(du, u, p, t):
+        du[0] = u[1]
+        du[1] = p[0] * ((1 - u[0] ** 2) * u[1] - u[0])
+
+    g = _load("vdp_mu100.json")
+    exprs, usyms, _, tsym = codegen.trace_vector_fn(vdp, 2, 1)
+    fns = _host_fns(oracle, [codegen.emit_rhs(exprs), codegen.emit_jac(exprs, usyms), codegen.emit_tgrad(exprs, tsym)])
+    out, rc, st = oracle.solve(None, alg, [g["u0"]], [g["p"]], (0.0, 50.0), g["t"], 1e-4, abstol=1e-9, reltol=1e-9, fns=fns,
+                               maxiters=10**7)
+    ref = np.array(g["u"])
+    assert rc[0] == 1
+    # the relaxation oscillation amplifies local errors ~1e3-fold (phase error at the fast transitions); the order-2
+    # Rosenbrock23 converges like tol^(2/3).  Bounds = 5x the measured errors at this tolerance.
+    assert np.max(np.abs(out[0] - ref)) < bound, np.max(np.abs(out[0] - ref))
+    tight, _, _ = oracle.solve(None, alg, [g["u0"]], [g["p"]], (0.0, 50.0), g["t"], 1e-4, abstol=1e-11, reltol=1e-11, fns=fns,
+                               maxiters=10**8)
+    assert np.max(np.abs(tight[0] - ref)) < 0.2 * np.max(np.abs(out[0] - ref))      # and it converges with the tolerance

@@ -6,6 +6,7 @@ available, so these vectors come from INDEPENDENT solvers, not from the referenc
     /root/reference/test/core.jl:22-30 and :39-46
   * linear: closed form 0.5*exp(1.01 t)   (test/core.jl:10-13)
   * philox: Random123 known-answer vectors for Philox4x32-10
+  * vdp_mu100: van der Pol mu = 100 (second stiff pin), scipy Radau
   * net16_event: the 16-species network with its bolus ContinuousCallback (config 5), scipy DOP853 + terminal events +
     manual affect + restart
 Run:  python tools/gen_golden.py     (needs scipy; output is committed)
@@ -117,3 +118,13 @@ json.dump({"problem": "16-species network + bolus ContinuousCallback (BASELINE c
            "cases": cases, "source": "scipy DOP853 rtol=1e-12 atol=1e-14, terminal events + manual affect + restart"},
           open(os.path.join(OUT, "net16_event.json"), "w"), indent=1)
 print("net16 event golden written:", [len(c["event_times"]) for c in cases], "events")
+
+# ---- a second stiff pin for the Rosenbrock family: van der Pol, mu = 100, t in (0, 50), scipy Radau
+def vdp(t, u, mu):
+    return [u[1], mu * ((1 - u[0] ** 2) * u[1] - u[0])]
+
+
+ts = np.linspace(0.0, 50.0, 11)
+s = solve_ivp(vdp, (0, 50), [2.0, 0.0], method="Radau", t_eval=ts, rtol=1e-12, atol=1e-14, args=(100.0,))
+json.dump({"problem": "van der Pol mu=100", "u0": [2.0, 0.0], "p": [100.0], "t": ts.tolist(), "u": s.y.T.tolist(),
+           "source": "scipy Radau rtol=1e-12 atol=1e-14"}, open(os.path.join(OUT, "vdp_mu100.json"), "w"), indent=1)

@@ -12,6 +12,8 @@ def _arr(sim):
     a = getattr(sim, "u_array", None)
     if a is None:
         raise TypeError("EnsembleAnalysis needs an EnsembleSolution with gathered arrays (no output_func/reduction)")
+    if np.ndim(sim.t) != 1:
+        raise TypeError("EnsembleAnalysis needs a common time grid: solve the ensemble with saveat (not save_everystep)")
     return a.astype(np.float64, copy=False)
 
 

@@ -1077,6 +1077,40 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
         }
         rc = 0;
     }
+    // Vern7 on a system whose 14 stage vectors need more than ~300 registers cannot fit one thread: compile the split
+    // kernel first and skip the (slow to compile, several hundred KB) one-thread variants when it builds within its spill
+    // budget.  Same choice as the general rule below makes for these models, at half the compile time.
+    bool split_tried = false;
+    auto try_split = [&](int keep_spill, bool have_keep, bool forced) -> bool {
+        int mbs = 3, rc2 = 0;
+        if (const char* e = getenv("B200ENS_MINBLOCKS")) mbs = std::max(1, atoi(e));
+        for (;; mbs--) {
+            m->source = build_source(d, mbs, 128, 0, 0, 1);
+            rc2 = nvrtc_compile(m.get());
+            if (rc2) break;
+            parse_ptxas_log(m.get());
+            if (m->spill <= 2048 || mbs <= 1 || getenv("B200ENS_MINBLOCKS")) break;
+        }
+        split_tried = true;
+        if (!rc2 && (forced || (have_keep ? m->spill < keep_spill : m->spill <= 2048))) {
+            m->split = 1;
+            m->block = 128;
+            mb = mbs;
+            return true;
+        }
+        return false;
+    };
+    const char* force_s = getenv("B200ENS_SPLIT");
+    const bool split_off = (d->flags & B200ENS_MODEL_NOSPLIT) || (force_s && atoi(force_s) == 0);
+    const bool split_on = (d->flags & B200ENS_MODEL_SPLIT) || (force_s && atoi(force_s) == 1);
+    const bool vector_cb = d->condition_src && strstr(d->condition_src, "B2_NCOND") != nullptr;   // one-thread kernels only
+    const bool split_eligible = nvec && !m->x2 && !d->dcondition_src && !vector_cb && d->n_state >= 4 && !flag_k &&
+                                !(force_k && atoi(force_k) == 1);
+    const bool surely_spills = d->alg == B200ENS_VERN7 && nvec * d->n_state * (d->dtype == B200ENS_F64 ? 2 : 1) > 300;
+    if (try_regs && split_eligible && !split_off && (split_on || surely_spills) && try_split(0, false, split_on)) {
+        try_regs = false;   // settled
+        rc = 0;
+    }
     if (try_regs) {
         for (;; mb--) {
             m->source = build_source(d, mb, kBlock, 0);
@@ -1100,40 +1134,20 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     // or 4 KB (Tsit5), kept when it spills less; B200ENS_MODEL_SPLIT / B200ENS_SPLIT=1 force it.
     // Unlike the one-thread kernels the split kernel prefers occupancy over a spill-free build (four warps meet at a
     // barrier ~25 times per step): start at 3 CTAs/SM and accept up to 2 KB of spill stores.
-    {
-        const char* force_s = getenv("B200ENS_SPLIT");
-        const bool off = (d->flags & B200ENS_MODEL_NOSPLIT) || (force_s && atoi(force_s) == 0);
-        const bool on = (d->flags & B200ENS_MODEL_SPLIT) || (force_s && atoi(force_s) == 1);
-        const bool vector_cb = d->condition_src && strstr(d->condition_src, "B2_NCOND") != nullptr;   // one-thread kernels only
-        const bool eligible = nvec && !m->x2 && !d->dcondition_src && !vector_cb && d->n_state >= 4 && !flag_k && !(force_k && atoi(force_k) == 1);
-        if (!rc && eligible && !off && (on || (try_regs && m->spill > (d->alg == B200ENS_VERN7 ? 1024 : 4096)))) {
-            auto keep_src = m->source;
-            auto keep_cubin = m->cubin;
-            auto keep_log = m->log;
-            const int keep_spill = m->spill, keep_regs = m->regs, keep_lmem = m->lmem, keep_smem = m->smem;
-            int mbs = 3, rc2 = 0;
-            if (const char* e = getenv("B200ENS_MINBLOCKS")) mbs = std::max(1, atoi(e));
-            for (;; mbs--) {
-                m->source = build_source(d, mbs, 128, 0, 0, 1);
-                rc2 = nvrtc_compile(m.get());
-                if (rc2) break;
-                parse_ptxas_log(m.get());
-                if (m->spill <= 2048 || mbs <= 1 || getenv("B200ENS_MINBLOCKS")) break;
-            }
-            if (!rc2 && (on || m->spill < keep_spill)) {
-                m->split = 1;
-                m->block = 128;
-                mb = mbs;
-                try_regs = true;   // settled: skip the shared-memory variant
-            } else {
-                m->source = keep_src;
-                m->cubin = keep_cubin;
-                m->log = keep_log;
-                m->spill = keep_spill;
-                m->regs = keep_regs;
-                m->lmem = keep_lmem;
-                m->smem = keep_smem;
-            }
+    if (!rc && !m->split && !split_tried && split_eligible && !split_off &&
+        (split_on || (try_regs && m->spill > (d->alg == B200ENS_VERN7 ? 1024 : 4096)))) {
+        auto keep_src = m->source;
+        auto keep_cubin = m->cubin;
+        auto keep_log = m->log;
+        const int keep_spill = m->spill, keep_regs = m->regs, keep_lmem = m->lmem, keep_smem = m->smem;
+        if (!try_split(keep_spill, true, split_on)) {
+            m->source = keep_src;
+            m->cubin = keep_cubin;
+            m->log = keep_log;
+            m->spill = keep_spill;
+            m->regs = keep_regs;
+            m->lmem = keep_lmem;
+            m->smem = keep_smem;
         }
     }
     if (!rc && nvec && !m->x2 && !m->split && (!try_regs || (m->spill > 4096 && !(force_k && atoi(force_k) == 0)))) {

@@ -1077,7 +1077,7 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
         }
         rc = 0;
     }
-    // Vern7 on a system whose 14 stage vectors need more than ~300 registers cannot fit one thread: compile the split
+    // Vern7 on a system whose 14 stage vectors need more than ~200 registers cannot fit one thread: compile the split
     // kernel first and skip the (slow to compile, several hundred KB) one-thread variants when it builds within its spill
     // budget.  Same choice as the general rule below makes for these models, at half the compile time.
     bool split_tried = false;
@@ -1106,7 +1106,7 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     const bool vector_cb = d->condition_src && strstr(d->condition_src, "B2_NCOND") != nullptr;   // one-thread kernels only
     const bool split_eligible = nvec && !m->x2 && !d->dcondition_src && !vector_cb && d->n_state >= 4 && !flag_k &&
                                 !(force_k && atoi(force_k) == 1);
-    const bool surely_spills = d->alg == B200ENS_VERN7 && nvec * d->n_state * (d->dtype == B200ENS_F64 ? 2 : 1) > 300;
+    const bool surely_spills = d->alg == B200ENS_VERN7 && nvec * d->n_state * (d->dtype == B200ENS_F64 ? 2 : 1) > 200;   // + ~55 registers for everything else > 255
     if (try_regs && split_eligible && !split_off && (split_on || surely_spills) && try_split(0, false, split_on)) {
         try_regs = false;   // settled
         rc = 0;

@@ -1216,6 +1216,16 @@ static int solve_host(b200ens_model* m, const b200ens_opts* o, int64_t N, const 
     if (every && (moments || !out_t)) return fail(B200ENS_E_INVALID, "save_everystep needs out_t [N][n_save] (and no moments mode)");
     if (!u0 || !retcode || (m->n_param && !p) || (n_save && ((!saveat && !every) || (!out_u && !moments))))
         return fail(B200ENS_E_INVALID, "null buffer");
+    if (n_save && !every) {
+        // the header's contract (ascending, inside tspan): a point outside would silently stay unwritten.  Bounds are
+        // compared in the state type, which is what the kernel sees (tspan (0, 0.1) in Float32 ends at 0.1f > 0.1).
+        const bool f64 = m->dtype == B200ENS_F64;
+        auto at = [&](int i) { return f64 ? ((const double*)saveat)[i] : (double)((const float*)saveat)[i]; };
+        const double lo = f64 ? o->t0 : (double)(float)o->t0, hi = f64 ? o->t1 : (double)(float)o->t1;
+        for (int i = 0; i < n_save; i++)
+            if (!(at(i) >= lo && at(i) <= hi) || (i && !(at(i) >= at(i - 1))))
+                return fail(B200ENS_E_INVALID, "saveat[%d] = %g: the grid must be ascending and inside tspan [%g, %g]", i, at(i), lo, hi);
+    }
     if (out_t && n_save && !every) memcpy(out_t, saveat, (size_t)n_save * m->elem());
     if (N == 0) return 0;
     const int ndev = b200ens_device_count();

@@ -79,6 +79,21 @@ def test_no_cpu_fallback_without_device(B):
     assert e.value.code == B._lib.E_NODEVICE and "no CPU fallback" in str(e.value)
 
 
+def test_saveat_grid_is_validated_before_any_device_work(B):
+    """include/b200ens.h: saveat is ascending and inside tspan -- checked on the host, so it also fails without a GPU."""
+    from b200ens import workloads as W
+
+    for dtype in (np.float64, np.float32):
+        m = B.build_model(W.lorenz_problem(dtype), B.Tsit5())
+        o = B._lib.default_opts()
+        o.t0, o.t1, o.dt = 0.0, 10.0, 0.1
+        u0, p = W.lorenz_params(4, "random", seed=1, dtype=dtype)
+        for bad in ([0.0, 5.0, 4.0], [0.0, 10.5], [-1.0, 2.0], [1.0, float("nan")]):
+            with pytest.raises(B.B200EnsError) as e:
+                m.solve(o, u0, p, bad)
+            assert e.value.code == -1 and "saveat" in str(e.value), bad
+
+
 def test_product_never_touches_the_oracle():
     """oracle/ is test infrastructure: nothing under the package or include/ may reference it."""
     pkg = os.path.join(ROOT, "differentialequations.jl_b200")

@@ -168,7 +168,8 @@ int b200ens_model_info(const b200ens_model* m, int64_t* cubin_bytes, int32_t* re
 /* The ensemble solve behind  solve(::EnsembleProblem, alg, ::EnsembleB200; trajectories=N, ...)
  * (replaces SciMLBase.__solve / solve_batch / batch_func of EnsembleThreads, qa.jl:56,192).
  * HOST buffers, trajectory-major:
- *   u0 [N][n_state], p [N][n_param], saveat [n_save] (ascending, within [t0,t1]),
+ *   u0 [N][n_state], p [N][n_param], saveat [n_save] (ascending, within [t0,t1]; checked on the host,
+ *   B200ENS_E_INVALID otherwise -- b200ens_solve_device trusts its device-resident grid),
  *   dW  NULL or [N][nsteps][nvec][n_state]  (nvec = 1 EM, 2 SOSRA: dW then dZ),
  *   out_u [N][n_save][n_state], out_t [n_save] or NULL, retcode [N], stats [N] or NULL.
  * Trajectory ranges are sharded over the devices in device_mask; blocking. */

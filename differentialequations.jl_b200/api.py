@@ -320,6 +320,14 @@ class EnsembleSummary:
     with Success, computed ON THE DEVICE (EnsembleAnalysis.timestep_meanvar, qa.jl:211) -- the trajectories never travel
     to the host.  `sum`/`sumsq`/`num_monte` are kept so that partial summaries of several ranks can be merged."""
 
+    def __new__(cls, *args, **kw):
+        # upstream's constructor EnsembleSummary(sim, t = sim.t; quantiles = [0.05, 0.95]) on gathered trajectories
+        if args and isinstance(args[0], EnsembleSolution):
+            from .analysis import HostEnsembleSummary
+
+            return HostEnsembleSummary(*args, **kw)
+        return super().__new__(cls)
+
     def __init__(self, t, s, q, count, retcodes, elapsed, timing):
         self.t = t
         self.sum, self.sumsq, self.num_monte = s, q, int(count)

@@ -168,6 +168,41 @@ def test_ensemble_analysis_functions():
     with pytest.raises(IndexError):
         EA.timestep_mean(sim, 5)
     assert np.allclose(EA.timeseries_point_mean(sim, [0.0, 2.0]), arr[:, [0, 3]].mean(0))
+    # covariance / correlation between times, matrices over all save points, weighted variants
+    _, _, c = EA.timepoint_meancov(sim, 0.5, 2.0)
+    assert np.allclose(c, [np.cov(arr[:, 1, k], arr[:, 3, k])[0, 1] for k in range(n)])
+    _, _, r = EA.timepoint_meancor(sim, 0.0, 1.0)
+    assert np.allclose(r, [np.corrcoef(arr[:, 0, k], arr[:, 2, k])[0, 1] for k in range(n)])
+    M = EA.timeseries_steps_meancov(sim)
+    assert len(M) == ns and len(M[0]) == ns and np.allclose(M[2][2][2], arr[:, 2].var(0, ddof=1))
+    R = EA.timeseries_steps_meancor(sim)
+    assert np.allclose(R[1][1][2], 1.0) and np.allclose(R[0][3][2], np.asarray(R[3][0][2]))
+    P = EA.timeseries_point_meancov(sim, [0.0, 0.5], [1.0])
+    assert len(P) == 2 and len(P[0]) == 1 and np.allclose(P[1][0][2], M[1][2][2])
+    assert np.allclose(EA.timeseries_point_meancor(sim, [0.5], [0.5])[0][0][2], 1.0)
+    w = rng.random(N) + 0.1
+    ma, mb, cw = EA.timestep_weighted_meancov(sim, w, 1, 2)
+    assert np.allclose(ma, np.average(arr[:, 0], axis=0, weights=w))
+    ref = [np.cov(arr[:, 0, k], arr[:, 1, k], aweights=w)[0, 1] for k in range(n)]       # numpy aweights == 'reliability'
+    assert np.allclose(cw, ref)
+    fw = rng.integers(1, 4, N).astype(float)
+    _, _, cf = EA.timepoint_weighted_meancov(sim, fw, 0.0, 0.5, weight_type="frequency")
+    assert np.allclose(cf, [np.cov(arr[:, 0, k], arr[:, 1, k], fweights=fw.astype(int))[0, 1] for k in range(n)])
+    ones = EA.timeseries_steps_weighted_meancov(sim, np.ones(N))
+    assert np.allclose(ones[0][1][2], M[0][1][2])                                         # unit weights == plain covariance
+    assert np.allclose(EA.timeseries_point_weighted_meancov(sim, np.ones(N), [0.0], [0.5])[0][0][2], M[0][1][2])
+    with pytest.raises(ValueError):
+        EA.timestep_weighted_meancov(sim, np.ones(N - 1), 1, 2)
+    assert len(EA.componentwise_vectors_timepoint(sim, 1.0)) == n
+    assert np.allclose(EA.timeseries_point_median(sim, [0.5]), np.median(arr[:, 1], 0)[None])
+    assert np.allclose(EA.timeseries_point_quantile(sim, 0.25, [0.5, 2.0]), np.quantile(arr[:, [1, 3]], 0.25, axis=0))
+    # EnsembleSummary(sim) / EnsembleSummary(sim, ts; quantiles) (qa.jl:54) from gathered trajectories
+    es = B.EnsembleSummary(sim)
+    assert np.allclose(es.u, arr.mean(0)) and np.allclose(es.v, arr.var(0, ddof=1)) and es.num_monte == N
+    assert np.allclose(es.qlow, np.quantile(arr, 0.05, axis=0)) and np.allclose(es.qhigh, np.quantile(arr, 0.95, axis=0))
+    es2 = B.EnsembleSummary(sim, [0.5, 2.0], quantiles=(0.25, 0.75))
+    assert es2.u.shape == (2, n) and np.allclose(es2.med, np.median(arr[:, [1, 3]], axis=0))
+    assert np.allclose(es2.qhigh, np.quantile(arr[:, [1, 3]], 0.75, axis=0))
 
 
 def test_vector_continuous_callback_codegen():

@@ -83,12 +83,48 @@ class SRIW1(_Alg):
 
 
 # ---------------------------------------------------------------- problems
+class ODEFunction:
+    """ODEFunction(f; mass_matrix, jac, tgrad) (qa.jl: exported by the reference): the wrapper upstream uses to attach a
+    constant mass matrix (M u' = f, index-1 DAE) or an analytic Jacobian to f.  The device Jacobian and time gradient are
+    always derived symbolically from the traced f; a given `jac` is checked against that derivation when the model is
+    built (codegen.check_user_jacobian), `tgrad` is accepted for signature compatibility."""
+
+    def __init__(self, f, mass_matrix=None, jac=None, tgrad=None):
+        if isinstance(f, ODEFunction):
+            mass_matrix = f.mass_matrix if mass_matrix is None else mass_matrix
+            jac = f.jac if jac is None else jac
+            f = f.f
+        self.f, self.mass_matrix, self.jac, self.tgrad = f, mass_matrix, jac, tgrad
+
+    def __call__(self, *args):
+        return self.f(*args)
+
+
+class SDEFunction(ODEFunction):
+    """SDEFunction(f, g): drift and diagonal diffusion (qa.jl: exported by the reference)."""
+
+    def __init__(self, f, g):
+        super().__init__(f)
+        self.g = g
+
+
+def successful_retcode(x):
+    """successful_retcode(sol) / successful_retcode(retcode) (qa.jl: exported by the reference): Success or Terminated."""
+    rc = getattr(x, "retcode", x)
+    return int(rc) in (int(ReturnCode.Success), int(ReturnCode.Terminated))
+
+
 class ODEProblem:
     """ODEProblem(f, u0, tspan, p): f(u,p,t) -> du  or in-place f(du,u,p,t) (test/core.jl:22-30)."""
 
     is_sde = False
 
     def __init__(self, f, u0, tspan, p=None, g=None, mass_matrix=None):
+        self.jac = None
+        if isinstance(f, ODEFunction):   # ODEProblem(ODEFunction(f; mass_matrix = M, jac = J), u0, tspan, p)
+            mass_matrix = f.mass_matrix if mass_matrix is None else mass_matrix
+            self.jac = f.jac
+            f = f.f
         self.f = f
         self.g = g
         # ODEFunction(f; mass_matrix = M): M u' = f(u,p,t) with a constant, possibly singular M (index-1 DAE); supported by
@@ -126,7 +162,10 @@ class SDEProblem(ODEProblem):
 
     is_sde = True
 
-    def __init__(self, f, g, u0, tspan, p=None):
+    def __init__(self, f, g=None, u0=None, tspan=None, p=None):
+        if isinstance(f, SDEFunction):   # SDEProblem(SDEFunction(f, g), u0, tspan, p)
+            u0, tspan, p = g, u0, tspan
+            f, g = f.f, f.g
         super().__init__(f, u0, tspan, p, g=g)
 
 
@@ -390,6 +429,8 @@ def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False, ksme
                                       "not give for algebraic components)")
         srcs["rhs_src"] = codegen.emit_mass(mm) + srcs["rhs_src"]
     if alg.name in ("Rosenbrock23", "Rodas4", "Rodas5", "Rodas5P"):
+        if getattr(prob, "jac", None) is not None:
+            codegen.check_user_jacobian(prob.jac, exprs, usyms, n, m)
         srcs["jac_src"] = codegen.emit_jac(exprs, usyms)
         srcs["tgrad_src"] = codegen.emit_tgrad(exprs, tsym)
     if alg.is_sde:

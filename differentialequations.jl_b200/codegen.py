@@ -103,6 +103,25 @@ def trace_vector_fn(fn, n_state, n_param):
     return out, u.syms, p.syms, t
 
 
+def check_user_jacobian(jac, exprs, usyms, n_state, n_param):
+    """ODEFunction(f; jac = ...): the device Jacobian is always derived from the traced f (exact, and the expression tree
+    the oracle shares); a user-supplied jac(u,p,t) -> matrix or jac!(J,u,p,t) is traced too and must agree with it
+    symbolically -- a wrong analytic Jacobian is an error here instead of a silently slower Rosenbrock solve."""
+    u, p, t = _Vec("u", n_state), _Vec("p", max(n_param, 1)), sp.Symbol("t", real=True)
+    if _nparams(jac) == 4:
+        J = sp.zeros(n_state, n_state).as_mutable()
+        jac(J, u, p, t)
+    else:
+        J = sp.Matrix(jac(u, p, t))
+    if J.shape != (n_state, n_state):
+        raise ValueError(f"jac returned a {J.shape} matrix for n_state={n_state}")
+    ref = sp.Matrix(exprs).jacobian(sp.Matrix(usyms))
+    for i in range(n_state):
+        for j in range(n_state):
+            if sp.simplify(sp.sympify(J[i, j]) - ref[i, j]) != 0:
+                raise ValueError(f"jac[{i},{j}] = {J[i, j]} disagrees with d f[{i}] / d u[{j}] = {ref[i, j]}")
+
+
 def _emit_body(assign_targets, exprs, cse=True):
     lines = []
     if cse:

@@ -234,3 +234,37 @@ def test_vector_continuous_callback_codegen():
         B.VectorContinuousCallback(condition, affect, 0)
     src = codegen.host_wrapper_source([codegen.emit_rhs([-codegen.sp.Symbol("u[0]", real=True)] * 2), c, a])
     assert "b2_vaffect_f64" in src and "b2_vcondition_f32" in src
+
+
+def test_odefunction_sdefunction_and_successful_retcode(B):
+    """ODEFunction(f; mass_matrix, jac) / SDEFunction(f, g) / successful_retcode (exported by the reference, qa.jl):
+    the wrappers unwrap into the same problems, and a user Jacobian is checked against the symbolic one."""
+    def rober(u, p, t):
+        return [-p[0] * u[0] + p[2] * u[1] * u[2], p[0] * u[0] - p[2] * u[1] * u[2] - p[1] * u[1] ** 2, u[0] + u[1] + u[2] - 1.0]
+
+    def jac(J, u, p, t):
+        J[0, 0], J[0, 1], J[0, 2] = -p[0], p[2] * u[2], p[2] * u[1]
+        J[1, 0], J[1, 1], J[1, 2] = p[0], -p[2] * u[2] - 2 * p[1] * u[1], -p[2] * u[1]
+        J[2, 0], J[2, 1], J[2, 2] = 1, 1, 1
+
+    M = np.diag([1.0, 1.0, 0.0])
+    prob = B.ODEProblem(B.ODEFunction(rober, mass_matrix=M, jac=jac), [1.0, 0.0, 0.0], (0.0, 1e5), [0.04, 3e7, 1e4])
+    assert prob.f is rober and np.array_equal(prob.mass_matrix, M) and prob.jac is jac
+    m = B.build_model(prob, B.Rodas5P())                       # JIT only: the checked Jacobian passes
+    assert "B2_HAS_MASS 1" in m.sources["rhs_src"] and "b2_jac" in m.sources["jac_src"]
+    assert B.remake(prob, p=[0.05, 3e7, 1e4]).jac is jac
+
+    def bad_jac(u, p, t):
+        return [[-p[0], p[2] * u[2], p[2] * u[1]], [p[0], -p[2] * u[2] - p[1] * u[1], -p[2] * u[1]], [1, 1, 1]]
+
+    with pytest.raises(ValueError, match=r"jac\[1,1\]"):
+        B.build_model(B.ODEProblem(B.ODEFunction(rober, jac=bad_jac), [1.0, 0.0, 0.0], (0.0, 1.0), [0.04, 3e7, 1e4]), B.Rodas5())
+
+    f, g = (lambda u, p, t: [p[0] * u[0]]), (lambda u, p, t: [p[1] * u[0]])
+    sp_ = B.SDEProblem(B.SDEFunction(f, g), [1.0], (0.0, 1.0), [1.01, 0.87])
+    assert sp_.f is f and sp_.g is g and sp_.tspan == (0.0, 1.0) and sp_.p.tolist() == [1.01, 0.87] and sp_.is_sde
+
+    assert B.successful_retcode(B.ReturnCode.Success) and B.successful_retcode(B.ReturnCode.Terminated)
+    assert not B.successful_retcode(B.ReturnCode.MaxIters) and not B.successful_retcode(B.ReturnCode.DtNaN)
+    sol = B.ODESolution(np.array([0.0]), np.zeros((1, 1)), 1, None)
+    assert B.successful_retcode(sol)

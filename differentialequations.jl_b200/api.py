@@ -270,6 +270,40 @@ class EnsembleProblem:
         self.ps = ps
 
 
+class EnsembleContext(int):
+    """EnsembleContext (qa.jl:48, SciMLBase 3): what prob_func(prob, ctx) / output_func(sol, ctx) receive per trajectory.
+    It IS the 1-based trajectory index (an int, so SciMLBase 2 style callbacks that expect `i` keep working) and carries
+    `sim_id`, `repeat` and `rng`: a generator seeded by (solve seed, sim_id), i.e. reproducible for any batch size, rank
+    layout or rerun order (get_rng(ctx), qa.jl:152)."""
+
+    def __new__(cls, sim_id, repeat=1, seed=0):
+        self = super().__new__(cls, int(sim_id))
+        self.sim_id, self.repeat, self._seed, self._rng = int(sim_id), int(repeat), int(seed), None
+        return self
+
+    @property
+    def rng(self):
+        if self._rng is None:
+            self._rng = np.random.default_rng([self._seed, self.sim_id, self.repeat])
+        return self._rng
+
+
+def has_rng(ctx):
+    return isinstance(ctx, EnsembleContext)
+
+
+def get_rng(ctx):
+    return ctx.rng
+
+
+def _call_prob_func(prob_func, prob, i, repeat, seed):
+    """prob_func(prob, i, repeat) (SciMLBase 2, test usage) or prob_func(prob, ctx) (SciMLBase 3): probed by arity, like
+    `applicable` in the Julia glue."""
+    if codegen._nparams(prob_func) == 2:
+        return prob_func(prob, EnsembleContext(i, repeat, seed))
+    return prob_func(prob, i, repeat)
+
+
 class EnsembleB200:
     """The ensemble algorithm: sibling of EnsembleThreads / EnsembleGPUKernel.
 
@@ -475,7 +509,7 @@ def _saveat_array(saveat, tspan, dtype):
     return ts.astype(dtype)
 
 
-def _pack(eprob, N, dtype, lo=0, repeat=1):
+def _pack(eprob, N, dtype, lo=0, repeat=1, seed=0):
     """Run prob_func on the host (as EnsembleThreads / EnsembleGPUKernel do) for trajectories lo+1 .. lo+N (1-based
     like Julia) -> u0 [N,n], p [N,m]."""
     prob = eprob.prob
@@ -491,7 +525,7 @@ def _pack(eprob, N, dtype, lo=0, repeat=1):
         p[:] = prob.p
         return u0, p
     for i in range(N):
-        pi = eprob.prob_func(prob, lo + i + 1, repeat)
+        pi = _call_prob_func(eprob.prob_func, prob, lo + i + 1, repeat, seed)
         if pi.f is not prob.f or pi.tspan != prob.tspan:
             raise ValueError("EnsembleB200: prob_func may only change u0 and p (one compiled kernel per ensemble)")
         u0[i] = pi.u0
@@ -543,14 +577,15 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, batch_size=None, **kw)
         bsol = _solve_once(eprob, alg, ensemblealg, n_b, _lo=lo, **kw)
         data = []
         for j in range(n_b):
-            out, rerun = output_func(bsol[j], lo + j + 1)
+            seed = int(kw.get("seed") or 0)
+            out, rerun = output_func(bsol[j], EnsembleContext(lo + j + 1, 1, seed))
             repeat = 1
             while rerun:
                 repeat += 1
                 if repeat > 100:
                     raise RuntimeError("output_func keeps asking for a rerun (100 repeats)")
                 one = _solve_once(eprob, alg, ensemblealg, 1, _lo=lo + j, _repeat=repeat, **kw)
-                out, rerun = output_func(one[0], lo + j + 1)
+                out, rerun = output_func(one[0], EnsembleContext(lo + j + 1, repeat, seed))
             data.append(out)
         u, converged = reduction(u, data, range(lo + 1, lo + n_b + 1))
         batches += 1
@@ -603,7 +638,7 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
                         ensemblealg.stage_vectors_in_smem, False if save_everystep else ensemblealg.split)
     ts = _saveat_array(saveat, base.tspan, dtype)
     t_pack = time.perf_counter()
-    u0, p = _pack(eprob, N, dtype, _lo, _repeat)
+    u0, p = _pack(eprob, N, dtype, _lo, _repeat, int(seed or 0))
     t_pack = time.perf_counter() - t_pack
 
     o = _lib.default_opts()

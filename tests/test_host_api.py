@@ -40,6 +40,15 @@ def test_remake_and_prob_func_packing(B):
         _pack(bad, 2, np.float64)
     with pytest.raises(TypeError):
         B.remake(prob, f=None)
+    # SciMLBase 3 style prob_func(prob, ctx) (qa.jl:48,152): ctx is the 1-based index and carries a per-trajectory rng
+    # that depends on (seed, sim_id) only -> the same parameters whatever the batch layout
+    e3 = B.EnsembleProblem(prob, prob_func=lambda pr, ctx: B.remake(pr, p=[10.0, 28.0 * B.get_rng(ctx).random(), ctx.sim_id]))
+    _, pa = _pack(e3, 6, np.float64, seed=7)
+    _, pb = _pack(e3, 3, np.float64, lo=3, seed=7)
+    assert list(pa[:, 2]) == [1, 2, 3, 4, 5, 6] and np.array_equal(pa[3:], pb) and len(set(pa[:, 1])) == 6
+    assert not np.array_equal(_pack(e3, 6, np.float64, seed=8)[1][:, 1], pa[:, 1])
+    ctx = B.EnsembleContext(4, 2, 7)
+    assert ctx == 4 and ctx + 1 == 5 and ctx.repeat == 2 and B.has_rng(ctx) and not B.has_rng(4)
 
 
 def test_codegen_rhs_jacobian_tgrad(B):

@@ -61,7 +61,9 @@ typedef struct {
     uint32_t vterm_mask;      /* bit k: event index k terminates the trajectory */
     const double* mass;       /* NULL, or constant mass matrix [n_state][n_state] (M u' = f; Rodas4/5/5P only) */
     void* every_t;            /* save_everystep: step times [N][n_save] of the state type; n_save = capacity, saveat ignored */
-    int32_t save_everystep, pad3_;
+                              /* sde_adaptive: NULL, or receives W(t_end) of the accepted Brownian path, [N][n_state] */
+    int32_t save_everystep;
+    int32_t sde_adaptive;     /* 1: adaptive SRIW1 / SOSRA with rejection sampling with memory (RSwM1); `adaptive` stays unused for SDE algs */
 } orc_opts;
 
 /* u0 [N][n], p [N][m], saveat [n_save], out_u [N][n_save][n], retcode [N], stats [N] or NULL.

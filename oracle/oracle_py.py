@@ -35,7 +35,7 @@ class Opts(C.Structure):
         ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double)),
         ("vcond", C.c_void_p), ("vaffect", C.c_void_p), ("ncond", C.c_int32), ("vterm_mask", C.c_uint32),
         ("mass", C.POINTER(C.c_double)),
-        ("every_t", C.c_void_p), ("save_everystep", C.c_int32), ("pad3_", C.c_int32),
+        ("every_t", C.c_void_p), ("save_everystep", C.c_int32), ("sde_adaptive", C.c_int32),
     ]
 
 
@@ -115,7 +115,7 @@ def fns_from_host_model(dll, f64):
 
 def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adaptive=True, dtype=np.float64,
           maxiters=100000, dW=None, seed=0, event=False, terminate=False, interp_points=10, nthreads=0,
-          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, ncond=0, vterm_mask=0, mass_matrix=None, save_everystep=0, **ctl):
+          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, ncond=0, vterm_mask=0, mass_matrix=None, save_everystep=0, sde_adaptive=False, **ctl):
     """Run the oracle.  model: built-in name, or fns = dict(rhs=ptr, jac=ptr, ...)."""
     L = lib()
     f64 = np.dtype(dtype) == np.float64
@@ -149,6 +149,7 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
     if save_tstops is None:
         save_tstops = alg in ("Rodas4", "Rodas5", "Rodas5P")
     o.save_tstops = int(save_tstops)
+    o.sde_adaptive = int(bool(sde_adaptive))
     get = (lambda w: (fns or {}).get(w)) if fns is not None else (lambda w: model_fn(model, w, f64))
     o.rhs, o.jac, o.noise = get("rhs"), get("jac"), get("noise")
     o.tgrad = get("tgrad") if fns else None
@@ -169,11 +170,14 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
         times = np.empty((N, len(saveat)), dtype=dtype)
         o.every_t = times.ctypes.data_as(C.c_void_p)
         o.save_everystep = 1
+    if sde_adaptive:     # also return W(t_end) of every accepted path: (out, rc, stats, W)
+        times = np.empty((N, n), dtype=dtype)
+        o.every_t = times.ctypes.data_as(C.c_void_p)
     err = fn(C.byref(o), C.c_int64(N), vp(u0), vp(p), vp(saveat), vp(dW), vp(out), vp(rc), vp(stats),
              C.c_int(nthreads))
     if err != 0:
         raise RuntimeError(f"oracle error {err}")
-    if save_everystep:
+    if save_everystep or sde_adaptive:
         return out, rc, stats, times
     return out, rc, stats
 

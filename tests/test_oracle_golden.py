@@ -354,3 +354,64 @@ def test_van_der_pol_vs_radau(oracle, alg, bound):
     tight, _, _ = oracle.solve(None, alg, [g["u0"]], [g["p"]], (0.0, 50.0), g["t"], 1e-4, abstol=1e-11, reltol=1e-11, fns=fns,
                                maxiters=10**8)
     assert np.max(np.abs(tight[0] - ref)) < 0.2 * np.max(np.abs(out[0] - ref))      # and it converges with the tolerance
+
+
+def test_adaptive_sde_rswm_pathwise_and_law(oracle):
+    """Adaptive SRIW1 with rejection sampling with memory (oracle restatement for SURVEY 8f item 3, device path: next
+    round).  On geometric Brownian motion the accepted Brownian path's W(1) gives the pathwise closed form
+    X(1) = exp((mu - sigma^2/2) + sigma W(1)): the strong error must fall with the tolerance (order 3/2: ~30x per 10x
+    more steps), and W(1) must stay N(0,1) although ~6 rejections per path cut and re-use increments (Brownian bridge)."""
+    from scipy import stats as S
+
+    N, mu, sg = 6000, 1.01, 0.87
+    p, u0 = np.tile([mu, sg], (N, 1)), np.ones((N, 1))
+    errs, steps = [], []
+    for tol in (1e-2, 1e-3, 1e-4):
+        out, rc, st, W = oracle.solve("gbm", "SRIW1", u0, p, (0.0, 1.0), [0.0, 0.5, 1.0], 0.5, abstol=tol, reltol=tol,
+                                      sde_adaptive=True, seed=3)
+        assert np.all(rc == 1) and np.all(out[:, 0, 0] == 1.0)
+        exact = np.exp((mu - sg * sg / 2) + sg * W[:, 0])
+        errs.append(np.mean(np.abs(out[:, 2, 0] - exact) / exact))
+        steps.append(st[:, 0].mean())
+        assert st[:, 1].mean() > 2.0                                   # the big first step is rejected several times
+        assert S.kstest(W[:, 0], "norm").pvalue > 1e-3
+        assert abs(W.var() - 1.0) < 5 * np.sqrt(2.0 / N) and abs(W.mean()) < 5 / np.sqrt(N)
+    assert errs[0] > 8 * errs[1] > 64 * errs[2] and errs[2] < 2e-4, errs
+    assert steps[0] < steps[1] < steps[2]
+    # reproducible (Philox stream per trajectory, any thread count), and trajectory i does not depend on its neighbours
+    a = oracle.solve("gbm", "SRIW1", u0[:64], p[:64], (0.0, 1.0), [1.0], 0.5, abstol=1e-3, reltol=1e-3, sde_adaptive=True, seed=3, nthreads=1)
+    b = oracle.solve("gbm", "SRIW1", u0[:64], p[:64], (0.0, 1.0), [1.0], 0.5, abstol=1e-3, reltol=1e-3, sde_adaptive=True, seed=3, nthreads=4)
+    c = oracle.solve("gbm", "SRIW1", u0[32:64], p[32:64], (0.0, 1.0), [1.0], 0.5, abstol=1e-3, reltol=1e-3, sde_adaptive=True, seed=3, traj_offset=32)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3]) and np.array_equal(a[0][32:], c[0])
+    # Float32 runs the same algorithm
+    out32, rc32, st32, W32 = oracle.solve("gbm", "SRIW1", u0[:2000], p[:2000], (0.0, 1.0), [1.0], 0.5, abstol=1e-2, reltol=1e-2,
+                                          sde_adaptive=True, seed=3, dtype=np.float32)
+    ex32 = np.exp((mu - sg * sg / 2) + sg * W32[:, 0].astype(np.float64))
+    assert np.all(rc32 == 1) and np.mean(np.abs(out32[:, 0, 0] - ex32) / ex32) < 3 * errs[0]
+
+
+def test_adaptive_sosra_additive_noise(oracle):
+    """Adaptive SOSRA (additive noise) on the stochastic Lorenz system of config 4: tighter tolerances take more steps, the
+    Brownian path stays N(0, t) per component under rejections, and with zero noise the method reduces to a convergent
+    ODE integrator."""
+    from scipy import stats as S
+
+    N = 3000
+    p = np.tile([10.0, 28.0, 8 / 3, 3.0], (N, 1))
+    u0 = np.tile([1.0, 0.0, 0.0], (N, 1))
+    steps = []
+    for tol in (1e-1, 1e-2):
+        out, rc, st, W = oracle.solve("lorenz_additive", "SOSRA", u0, p, (0.0, 2.0), [2.0], 0.25, abstol=tol, reltol=tol,
+                                      sde_adaptive=True, seed=11)
+        assert np.all(rc == 1) and np.all(np.isfinite(out))
+        steps.append(st[:, 0].mean())
+        assert st[:, 1].mean() > 0.5
+        for k in range(3):
+            assert S.kstest(W[:, k] / np.sqrt(2.0), "norm").pvalue > 1e-3
+    assert steps[1] > 2 * steps[0]
+    # zero noise: the stepper reduces to a convergent ODE integrator (u' = 1.01 u, closed form)
+    out, rc, st, W = oracle.solve("gbm", "SOSRA", np.ones((1, 1)), np.array([[1.01, 0.0]]), (0.0, 1.0), [1.0], 0.1,
+                                  abstol=1e-3, reltol=1e-3, sde_adaptive=True)
+    assert rc[0] == 1 and abs(out[0, 0, 0] - np.exp(1.01)) < 1e-6 * np.exp(1.01), (out, st)
+    with pytest.raises(RuntimeError):                                 # EM has no embedded error estimate
+        oracle.solve("gbm", "EM", np.ones((1, 1)), np.array([[1.0, 0.5]]), (0.0, 1.0), [1.0], 0.1, sde_adaptive=True)

@@ -15,6 +15,7 @@ MODEL_PACKED_X2 = 2
 MODEL_KSMEM = 4
 MODEL_SPLIT = 8
 MODEL_NOSPLIT = 16
+MODEL_SDE_ADAPTIVE = 32
 
 E_NODEVICE = -3
 
@@ -136,7 +137,7 @@ class Model:
 
     def __init__(self, n_state, n_param, dtype, alg, rhs_src, jac_src=None, tgrad_src=None, noise_src=None,
                  condition_src=None, affect_src=None, name="model", fast_math=False, packed_x2=False,
-                 dcondition_src=None, daffect_src=None, ksmem=False, split=None):
+                 dcondition_src=None, daffect_src=None, ksmem=False, split=None, sde_adaptive=False):
         L = lib()
         d = ModelDesc()
         d.struct_size = C.sizeof(ModelDesc)
@@ -145,7 +146,7 @@ class Model:
         d.alg = ALG_IDS[alg] if isinstance(alg, str) else int(alg)
         d.flags = ((MODEL_FAST_MATH if fast_math else 0) | (MODEL_PACKED_X2 if packed_x2 else 0)
                    | (MODEL_KSMEM if ksmem else 0) | (MODEL_SPLIT if split is True else 0)
-                   | (MODEL_NOSPLIT if split is False else 0))
+                   | (MODEL_NOSPLIT if split is False else 0) | (MODEL_SDE_ADAPTIVE if sde_adaptive else 0))
         enc = lambda s: s.encode() if s is not None else None
         d.rhs_src, d.jac_src, d.tgrad_src = enc(rhs_src), enc(jac_src), enc(tgrad_src)
         d.noise_src, d.condition_src, d.affect_src = enc(noise_src), enc(condition_src), enc(affect_src)

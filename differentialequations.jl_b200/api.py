@@ -10,6 +10,7 @@ first saved value == u0 (:18,:34), saveat=0.1 on (0,1) gives 11 points (:93-95),
 ContinuousCallback(condition(u,t,integrator), affect!(integrator)) (:69-72), remake (:84).
 """
 import enum
+import os
 import time
 
 import numpy as np
@@ -443,13 +444,13 @@ class _LazySeq:
 _model_cache = {}
 
 
-def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False, ksmem=False, split=None):
+def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False, ksmem=False, split=None, sde_adaptive=False):
     """Trace prob.f (and g / callback), emit CUDA C, JIT it for sm_100a.  Cached per function objects."""
     n, m = prob.u0.shape[0], prob.p.shape[0]
     dtype = prob.u0.dtype
     mm = getattr(prob, "mass_matrix", None)
     key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math, packed_x2, ksmem, split,
-           None if mm is None else mm.tobytes())
+           None if mm is None else mm.tobytes(), sde_adaptive)
     hit = _model_cache.get(key)
     if hit is not None and hit[1] is prob.f:
         return hit[0]
@@ -484,7 +485,7 @@ def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False, ksme
         srcs["dcondition_src"], srcs["daffect_src"], term = codegen.emit_discrete_callback(dcb, n, m)
         terminate |= 2 if term else 0
     model = _lib.Model(n, m, dtype, alg.name, name=getattr(prob.f, "__name__", "model"), fast_math=fast_math,
-                       packed_x2=packed_x2, ksmem=ksmem, split=split, **srcs)
+                       packed_x2=packed_x2, ksmem=ksmem, split=split, sde_adaptive=sde_adaptive, **srcs)
     model.sources = srcs
     model.event_terminate = terminate
     _model_cache[key] = (model, prob.f)
@@ -628,14 +629,26 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
     dtype = base.u0.dtype
     if adaptive is None:
         adaptive = alg.adaptive_default
-    if alg.is_sde and adaptive:
-        raise NotImplementedError("adaptive SDE stepping (RSwM) is not implemented; use a fixed dt")
+    sde_adaptive = bool(alg.is_sde and adaptive)
+    if sde_adaptive:
+        # The adaptive SRIW1 / SOSRA kernel (rejection sampling with memory) is restated in the oracle and cross-compiled,
+        # but has not been validated on a GPU yet: opt in explicitly until it has.
+        if os.environ.get("B200ENS_EXPERIMENTAL_SDE_ADAPTIVE") != "1":
+            raise NotImplementedError("adaptive SDE stepping (RSwM) is experimental: pass adaptive=False and a fixed dt, or "
+                                      "set B200ENS_EXPERIMENTAL_SDE_ADAPTIVE=1")
+        if alg.name not in ("SRIW1", "SOSRA"):
+            raise NotImplementedError(f"{alg.name} has no embedded error estimate: adaptive stepping needs SRIW1 or SOSRA")
+        if dt is None or dW is not None:
+            raise ValueError("adaptive SDE stepping needs an initial dt and generates its own noise (no dW)")
+        abstol = 1e-2 if abstol is None else abstol      # StochasticDiffEq's defaults
+        reltol = 1e-2 if reltol is None else reltol
     if dt is None:
         if not adaptive:
             raise ValueError("fixed-step solves need dt")
         dt = 0.0   # automatic per-trajectory initial step on the device
     model = build_model(base, alg, callback, ensemblealg.fast_math, ensemblealg.packed_x2 and not save_everystep,
-                        ensemblealg.stage_vectors_in_smem, False if save_everystep else ensemblealg.split)
+                        ensemblealg.stage_vectors_in_smem, False if save_everystep else ensemblealg.split,
+                        sde_adaptive=sde_adaptive)
     ts = _saveat_array(saveat, base.tspan, dtype)
     t_pack = time.perf_counter()
     u0, p = _pack(eprob, N, dtype, _lo, _repeat, int(seed or 0))

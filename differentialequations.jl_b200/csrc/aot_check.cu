@@ -23,6 +23,9 @@
 #ifdef AOT_SPLIT
 #define B2_SPLIT 1   // one trajectory per lane of a 4-warp CTA (kernels/b2_split.cuh); n = 3 -> one component per warp, one padded
 #endif
+#ifdef AOT_SDE_ADAPT
+#define B2_SDE_ADAPT 1   // adaptive SRIW1 / SOSRA (kernels/b2_sde_adaptive.cuh)
+#endif
 #ifndef B2_MINBLOCKS
 #define B2_MINBLOCKS 1
 #endif

@@ -304,6 +304,7 @@ std::string build_source(const b200ens_model_desc* d, int min_blocks, int block,
             s += part;
             s += "\n";
         }
+    if (d->flags & B200ENS_MODEL_SDE_ADAPTIVE) s += "#define B2_SDE_ADAPT 1\n";
     s += "#include \"b2_entry.cuh\"\n";
     return s;
 }
@@ -547,10 +548,11 @@ int fill_args(const b200ens_model* m, const b200ens_opts* o, B2Args* a) {
     a->dtmin = dflt(o->dtmin, 0.0);
     a->dtmax = dflt(o->dtmax, o->t1 - o->t0);
     a->qmin = dflt(o->qmin, 0.2);
-    a->qmax = dflt(o->qmax, 10.0);
+    const bool sde_adapt = (m->flags & B200ENS_MODEL_SDE_ADAPTIVE) != 0;   // strong order 3/2, StochasticDiffEq's qmax
+    a->qmax = dflt(o->qmax, sde_adapt ? 1.125 : 10.0);
     a->gamma = dflt(o->gamma, 0.9);
-    a->beta1 = dflt(o->beta1, 7.0 / (10.0 * order));
-    a->beta2 = dflt(o->beta2, 2.0 / (5.0 * order));
+    a->beta1 = dflt(o->beta1, sde_adapt ? 7.0 / 15.0 : 7.0 / (10.0 * order));
+    a->beta2 = dflt(o->beta2, sde_adapt ? 4.0 / 15.0 : 2.0 / (5.0 * order));
     a->qoldinit = dflt(o->qoldinit, 1e-4);
     a->adaptive = is_sde(m->alg) ? 0 : (o->adaptive != 0);
     a->noise_injected = o->noise_injected;
@@ -602,6 +604,8 @@ int check_opts(const b200ens_model* m, const b200ens_opts* o, int n_save, const 
         if (o->stage_outputs > 0) return fail(B200ENS_E_UNSUPPORTED, "save_everystep with stage_outputs=1");
     }
     if (o->noise_injected && !dW) return fail(B200ENS_E_INVALID, "noise_injected=1 but dW is NULL");
+    if (o->noise_injected && (m->flags & B200ENS_MODEL_SDE_ADAPTIVE))
+        return fail(B200ENS_E_UNSUPPORTED, "adaptive SDE stepping draws its own noise (rejection sampling with memory): noise_injected=1 is not possible");
     return 0;
 }
 
@@ -1024,6 +1028,8 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     if (is_rosenbrock(d->alg) && !d->jac_src)
         return fail(B200ENS_E_UNSUPPORTED, "Rosenbrock methods need the analytic Jacobian (jac_src); there is no AD/finite-difference fallback");
     if (is_sde(d->alg) && !d->noise_src) return fail(B200ENS_E_INVALID, "SDE algorithms need noise_src");
+    if ((d->flags & B200ENS_MODEL_SDE_ADAPTIVE) && d->alg != B200ENS_SOSRA && d->alg != B200ENS_SRIW1)
+        return fail(B200ENS_E_UNSUPPORTED, "B200ENS_MODEL_SDE_ADAPTIVE needs a stepper with an embedded error estimate: SRIW1 or SOSRA");
     if ((d->condition_src != nullptr) != (d->affect_src != nullptr))
         return fail(B200ENS_E_INVALID, "condition_src and affect_src must be given together");
     if ((d->dcondition_src != nullptr) != (d->daffect_src != nullptr))

@@ -23,6 +23,9 @@
 #include "b2_ode_driver.cuh"
 #elif B2_ALG == 6 || B2_ALG == 7 || B2_ALG == 9
 #include "b2_sde.cuh"
+#ifdef B2_SDE_ADAPT
+#include "b2_sde_adaptive.cuh"   // adaptive SRIW1 / SOSRA with rejection sampling with memory (B200ENS_MODEL_SDE_ADAPTIVE)
+#endif
 #else
 #error "unknown B2_ALG"
 #endif
@@ -80,6 +83,8 @@ extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble
     b2_ode_driver<B2Ros23>(a);
 #elif B2_ALG == 4 || B2_ALG == 5 || B2_ALG == 8
     b2_ode_driver<B2Rodas>(a);
+#elif defined(B2_SDE_ADAPT)
+    b2_sde_adaptive_driver<B2_ALG>(a);
 #else
     b2_sde_driver<B2_ALG>(a);
 #endif

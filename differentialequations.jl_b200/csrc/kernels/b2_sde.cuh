@@ -65,6 +65,112 @@ __device__ __forceinline__ void b2_normals(unsigned long long seed, unsigned lon
 #define SO(x) ((real)(B2T_SOSRA_##x))
 #define B2_INV_SQRT3 0.57735026918962576451
 
+// one step of stepper ALG from (t, up) with the increments dW, dZ over dt -> u.  ERR: also form the two parts of the
+// embedded error estimate (adaptive driver, b2_sde_adaptive.cuh); the fixed-step driver compiles them out.
+template <int ALG, bool ERR>
+__device__ __forceinline__ void b2_sde_step(real* __restrict__ u, const real* __restrict__ up, const real* __restrict__ dW,
+                                            const real* __restrict__ dZ, const real* __restrict__ p, const real t, const real dt,
+                                            real* __restrict__ E1, real* __restrict__ E2) {
+    real k1[B2_N], g1[B2_N];
+    if (ALG == 6) {  // Euler-Maruyama: u += f dt + g dW
+        b2_rhs(k1, up, p, t);
+        b2_noise(g1, up, p, t);
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) u[i] = b2_fma(g1[i], dW[i], b2_fma(dt, k1[i], up[i]));
+    } else if (ALG == 9) {
+        // SRIW1 (Roessler SRI W1): strong order 1.5 for diagonal noise; same expression tree as the oracle
+        real chi2[B2_N], i11[B2_N], i111[B2_N], k2[B2_N], g2[B2_N], g3[B2_N], g4[B2_N], H[B2_N];
+        const real sq = b2_sqrt(dt);
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) {
+            chi2[i] = (real)0.5 * b2_fma(dZ[i], (real)B2_INV_SQRT3, dW[i]);
+            i11[i] = (real)0.5 * b2_fma(dW[i], dW[i], -dt) / sq;
+            i111[i] = dW[i] * b2_fma(dW[i], dW[i], (real)-3 * dt) / ((real)6 * dt);
+        }
+        b2_rhs(k1, up, p, t);
+        b2_noise(g1, up, p, t);
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) H[i] = b2_fma(chi2[i], (real)1.5 * g1[i], b2_fma(dt, (real)0.75 * k1[i], up[i]));
+        b2_rhs(k2, H, p, t + (real)0.75 * dt);
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) H[i] = b2_fma(sq, (real)0.5 * g1[i], b2_fma(dt, (real)0.25 * k1[i], up[i]));
+        b2_noise(g2, H, p, t + (real)0.25 * dt);
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) H[i] = b2_fma(sq, -g1[i], b2_fma(dt, k1[i], up[i]));
+        b2_noise(g3, H, p, t + dt);
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) {
+            const real bb = b2_fma((real)0.5, g3[i], b2_fma((real)3, g2[i], (real)-5 * g1[i]));
+            H[i] = b2_fma(sq, bb, b2_fma(dt, (real)0.25 * k1[i], up[i]));
+        }
+        b2_noise(g4, H, p, t + (real)0.25 * dt);
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) {
+            const real d = b2_fma((real)(2.0 / 3.0), k2[i], (real)(1.0 / 3.0) * k1[i]);
+            real c1 = -dW[i];
+            c1 = b2_fma((real)-1, i11[i], c1);
+            c1 = b2_fma((real)2, chi2[i], c1);
+            c1 = b2_fma((real)-2, i111[i], c1);
+            real c2 = (real)(4.0 / 3.0) * dW[i];
+            c2 = b2_fma((real)(4.0 / 3.0), i11[i], c2);
+            c2 = b2_fma((real)(-4.0 / 3.0), chi2[i], c2);
+            c2 = b2_fma((real)(5.0 / 3.0), i111[i], c2);
+            real c3 = (real)(2.0 / 3.0) * dW[i];
+            c3 = b2_fma((real)(-1.0 / 3.0), i11[i], c3);
+            c3 = b2_fma((real)(-2.0 / 3.0), chi2[i], c3);
+            c3 = b2_fma((real)(-2.0 / 3.0), i111[i], c3);
+            u[i] = b2_fma(i111[i], g4[i], b2_fma(c3, g3[i], b2_fma(c2, g2[i], b2_fma(c1, g1[i], b2_fma(dt, d, up[i])))));
+            if (ERR) {  // embedded estimate of the adaptive driver: E1 = h (f1 + f2), E2 = the chi2 and I111 terms of the update
+                real e2a = (real)2 * g1[i];
+                e2a = b2_fma((real)(-4.0 / 3.0), g2[i], e2a);
+                e2a = b2_fma((real)(-2.0 / 3.0), g3[i], e2a);
+                real e2b = (real)-2 * g1[i];
+                e2b = b2_fma((real)(5.0 / 3.0), g2[i], e2b);
+                e2b = b2_fma((real)(-2.0 / 3.0), g3[i], e2b);
+                e2b = e2b + g4[i];
+                E1[i] = dt * (k1[i] + k2[i]);
+                E2[i] = b2_fma(i111[i], e2b, chi2[i] * e2a);
+            }
+        }
+    } else {  // SOSRA
+        real chi2[B2_N], g2[B2_N], g3[B2_N], k2[B2_N], k3[B2_N], H[B2_N];
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) chi2[i] = (real)0.5 * b2_fma(dZ[i], (real)B2_INV_SQRT3, dW[i]);
+        b2_noise(g1, up, p, t + SO(c11) * dt);
+        b2_noise(g2, up, p, t + SO(c12) * dt);
+        b2_noise(g3, up, p, t + SO(c13) * dt);
+        b2_rhs(k1, up, p, t);
+#pragma unroll
+        for (int i = 0; i < B2_N; i++)
+            H[i] = b2_fma(chi2[i], SO(B021) * g1[i], b2_fma(dt, SO(A021) * k1[i], up[i]));
+        b2_rhs(k2, H, p, t + SO(c02) * dt);
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) {
+            const real aa = b2_fma(SO(A032), k2[i], SO(A031) * k1[i]);
+            const real bb = b2_fma(SO(B032), g2[i], SO(B031) * g1[i]);
+            H[i] = b2_fma(chi2[i], bb, b2_fma(dt, aa, up[i]));
+        }
+        b2_rhs(k3, H, p, t + SO(c03) * dt);
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) {
+            real d = SO(alpha1) * k1[i];
+            d = b2_fma(SO(alpha2), k2[i], d);
+            d = b2_fma(SO(alpha3), k3[i], d);
+            real e1 = SO(beta11) * g1[i];
+            e1 = b2_fma(SO(beta12), g2[i], e1);
+            e1 = b2_fma(SO(beta13), g3[i], e1);
+            real e2 = SO(beta21) * g1[i];
+            e2 = b2_fma(SO(beta22), g2[i], e2);
+            e2 = b2_fma(SO(beta23), g3[i], e2);
+            u[i] = b2_fma(chi2[i], e2, b2_fma(dW[i], e1, b2_fma(dt, d, up[i])));
+            if (ERR) {  // SRA estimate: E1 = h (f1 + f2 + f3), E2 = chi2 * sum beta2_i g_i
+                E1[i] = dt * ((k1[i] + k2[i]) + k3[i]);
+                E2[i] = chi2[i] * e2;
+            }
+        }
+    }
+}
+
 template <int ALG>
 __device__ __forceinline__ void b2_sde_driver(const B2Args& a) {
     extern __shared__ __align__(16) unsigned char b2_smem[];
@@ -153,89 +259,7 @@ __device__ __forceinline__ void b2_sde_driver(const B2Args& a) {
                         dZ[i] = NVEC > 1 ? sq * z[(NVEC > 1 ? B2_N : 0) + i] : (real)0;
                     }
                 }
-                real k1[B2_N], g1[B2_N];
-                if (ALG == 6) {  // Euler-Maruyama: u += f dt + g dW
-                    b2_rhs(k1, up, p, t);
-                    b2_noise(g1, up, p, t);
-#pragma unroll
-                    for (int i = 0; i < B2_N; i++) u[i] = b2_fma(g1[i], dW[i], b2_fma(dt, k1[i], up[i]));
-                } else if (ALG == 9) {
-                    // SRIW1 (Roessler SRI W1): strong order 1.5 for diagonal noise; same expression tree as the oracle
-                    real chi2[B2_N], i11[B2_N], i111[B2_N], k2[B2_N], g2[B2_N], g3[B2_N], g4[B2_N], H[B2_N];
-                    const real sq = b2_sqrt(dt);
-#pragma unroll
-                    for (int i = 0; i < B2_N; i++) {
-                        chi2[i] = (real)0.5 * b2_fma(dZ[i], (real)B2_INV_SQRT3, dW[i]);
-                        i11[i] = (real)0.5 * b2_fma(dW[i], dW[i], -dt) / sq;
-                        i111[i] = dW[i] * b2_fma(dW[i], dW[i], (real)-3 * dt) / ((real)6 * dt);
-                    }
-                    b2_rhs(k1, up, p, t);
-                    b2_noise(g1, up, p, t);
-#pragma unroll
-                    for (int i = 0; i < B2_N; i++) H[i] = b2_fma(chi2[i], (real)1.5 * g1[i], b2_fma(dt, (real)0.75 * k1[i], up[i]));
-                    b2_rhs(k2, H, p, t + (real)0.75 * dt);
-#pragma unroll
-                    for (int i = 0; i < B2_N; i++) H[i] = b2_fma(sq, (real)0.5 * g1[i], b2_fma(dt, (real)0.25 * k1[i], up[i]));
-                    b2_noise(g2, H, p, t + (real)0.25 * dt);
-#pragma unroll
-                    for (int i = 0; i < B2_N; i++) H[i] = b2_fma(sq, -g1[i], b2_fma(dt, k1[i], up[i]));
-                    b2_noise(g3, H, p, t + dt);
-#pragma unroll
-                    for (int i = 0; i < B2_N; i++) {
-                        const real bb = b2_fma((real)0.5, g3[i], b2_fma((real)3, g2[i], (real)-5 * g1[i]));
-                        H[i] = b2_fma(sq, bb, b2_fma(dt, (real)0.25 * k1[i], up[i]));
-                    }
-                    b2_noise(g4, H, p, t + (real)0.25 * dt);
-#pragma unroll
-                    for (int i = 0; i < B2_N; i++) {
-                        const real d = b2_fma((real)(2.0 / 3.0), k2[i], (real)(1.0 / 3.0) * k1[i]);
-                        real c1 = -dW[i];
-                        c1 = b2_fma((real)-1, i11[i], c1);
-                        c1 = b2_fma((real)2, chi2[i], c1);
-                        c1 = b2_fma((real)-2, i111[i], c1);
-                        real c2 = (real)(4.0 / 3.0) * dW[i];
-                        c2 = b2_fma((real)(4.0 / 3.0), i11[i], c2);
-                        c2 = b2_fma((real)(-4.0 / 3.0), chi2[i], c2);
-                        c2 = b2_fma((real)(5.0 / 3.0), i111[i], c2);
-                        real c3 = (real)(2.0 / 3.0) * dW[i];
-                        c3 = b2_fma((real)(-1.0 / 3.0), i11[i], c3);
-                        c3 = b2_fma((real)(-2.0 / 3.0), chi2[i], c3);
-                        c3 = b2_fma((real)(-2.0 / 3.0), i111[i], c3);
-                        u[i] = b2_fma(i111[i], g4[i], b2_fma(c3, g3[i], b2_fma(c2, g2[i], b2_fma(c1, g1[i], b2_fma(dt, d, up[i])))));
-                    }
-                } else {  // SOSRA
-                    real chi2[B2_N], g2[B2_N], g3[B2_N], k2[B2_N], k3[B2_N], H[B2_N];
-#pragma unroll
-                    for (int i = 0; i < B2_N; i++) chi2[i] = (real)0.5 * b2_fma(dZ[i], (real)B2_INV_SQRT3, dW[i]);
-                    b2_noise(g1, up, p, t + SO(c11) * dt);
-                    b2_noise(g2, up, p, t + SO(c12) * dt);
-                    b2_noise(g3, up, p, t + SO(c13) * dt);
-                    b2_rhs(k1, up, p, t);
-#pragma unroll
-                    for (int i = 0; i < B2_N; i++)
-                        H[i] = b2_fma(chi2[i], SO(B021) * g1[i], b2_fma(dt, SO(A021) * k1[i], up[i]));
-                    b2_rhs(k2, H, p, t + SO(c02) * dt);
-#pragma unroll
-                    for (int i = 0; i < B2_N; i++) {
-                        const real aa = b2_fma(SO(A032), k2[i], SO(A031) * k1[i]);
-                        const real bb = b2_fma(SO(B032), g2[i], SO(B031) * g1[i]);
-                        H[i] = b2_fma(chi2[i], bb, b2_fma(dt, aa, up[i]));
-                    }
-                    b2_rhs(k3, H, p, t + SO(c03) * dt);
-#pragma unroll
-                    for (int i = 0; i < B2_N; i++) {
-                        real d = SO(alpha1) * k1[i];
-                        d = b2_fma(SO(alpha2), k2[i], d);
-                        d = b2_fma(SO(alpha3), k3[i], d);
-                        real e1 = SO(beta11) * g1[i];
-                        e1 = b2_fma(SO(beta12), g2[i], e1);
-                        e1 = b2_fma(SO(beta13), g3[i], e1);
-                        real e2 = SO(beta21) * g1[i];
-                        e2 = b2_fma(SO(beta22), g2[i], e2);
-                        e2 = b2_fma(SO(beta23), g3[i], e2);
-                        u[i] = b2_fma(chi2[i], e2, b2_fma(dW[i], e1, b2_fma(dt, d, up[i])));
-                    }
-                }
+                b2_sde_step<ALG, false>(u, up, dW, dZ, p, t, dt, nullptr, nullptr);
                 bool bad = false;
 #pragma unroll
                 for (int i = 0; i < B2_N; i++) bad |= b2_isnan(u[i]);

@@ -1,0 +1,225 @@
+// b2_sde_adaptive.cuh -- ADAPTIVE SDE ensemble kernel (SRIW1, SOSRA): embedded error estimate, the PI controller of
+// the ODE path with the strong order 3/2, and rejection sampling with memory (RSwM1, Rackauckas & Nie 2017) so that a
+// rejected step keeps the part of the Brownian path it already sampled.  Compiled only into models built with
+// B200ENS_MODEL_SDE_ADAPTIVE (B2_SDE_ADAPT); same expression tree as oracle/oracle_impl.inc solve_sde_adaptive.
+// EXPERIMENTAL in round 1: written against the oracle, not yet run on a GPU (the host API keeps it behind
+// B200ENS_EXPERIMENTAL_SDE_ADAPTIVE=1).  Reference names: SDEProblem /root/reference/test/qa/qa.jl:103; the
+// adaptive loop lives in StochasticDiffEq, outside the dep closure.
+#pragma once
+#include "b2_sde.cuh"
+
+#ifndef B2_RSWM_DEPTH
+#define B2_RSWM_DEPTH 48   // remembered pieces per trajectory (one per consecutive rejection); overflow -> Failure
+#endif
+#define B2_RC_FAILURE_ 7
+
+template <int ALG>
+__device__ __forceinline__ void b2_sde_adaptive_driver(const B2Args& a) {
+    static_assert(ALG == 7 || ALG == 9, "adaptive SDE stepping needs an embedded estimate: SOSRA or SRIW1");
+    extern __shared__ __align__(16) unsigned char b2_smem[];
+    const unsigned lane = threadIdx.x & 31u;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int stride = a.stage_stride;
+    real* const warp_stage = reinterpret_cast<real*>(b2_smem) + (size_t)warp_in_block * 32 * stride;
+    real* const gout = reinterpret_cast<real*>(a.out_u);
+    const real* const gu0 = reinterpret_cast<const real*>(a.u0);
+    const real* const gp = reinterpret_cast<const real*>(a.p);
+    const real* const gsave = reinterpret_cast<const real*>(a.saveat);
+    const int n_save = a.n_save;
+    const int out_per_traj = n_save * B2_N;
+    const real t0 = B2_ARG(a, t0), t1 = B2_ARG(a, t1), dt_user = B2_ARG(a, dt);
+    const real dtmax = B2_ARG(a, dtmax), dtmin = B2_ARG(a, dtmin);
+    const real delta = ALG == 9 ? (real)(1.0 / 6.0) : (real)1;
+    const float beta1 = a.f_beta1, beta2 = a.f_beta2;
+    const float inv_qmax = 1.0f / a.f_qmax, inv_qmin = 1.0f / a.f_qmin, inv_gam = 1.0f / a.f_gamma;
+    const float lqinit = b2_fastlog2(a.f_qoldinit);
+
+    B2Sink sink;
+    sink.stage = stride ? warp_stage + (size_t)lane * stride : nullptr;
+    sink.gout = gout;
+    bool exhausted = false;
+    while (!exhausted) {
+        long long idx = b2_fetch(B2_FULL, a.work_counter, a.N, lane, exhausted);
+        const bool active = idx >= 0;
+        if (__ballot_sync(B2_FULL, active) == 0u) break;
+        if (active) {
+            real u[B2_N], p[B2_NPA];
+            sink.base = idx * (long long)out_per_traj;
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) u[i] = gu0[idx * B2_N + i];
+#pragma unroll
+            for (int i = 0; i < B2_NPARAM; i++) p[i] = gp[idx * B2_NPARAM + i];
+            real t = t0, dt = dt_user, h = (real)0;
+            float lq = lqinit;
+            int si = 0, rc = 0, sp = 0, naccept = 0, nreject = 0;
+            bool have = false;   // (h, dW, dZ) already hold the cut increments of a rejected step
+            long long iter = 0;
+            while (si < n_save && __ldg(gsave + si) <= t0) {
+                sink.put(si, u);
+                si++;
+            }
+            const unsigned long long traj = a.traj_offset + (unsigned long long)idx;
+            real zbuf[B2_NORMALS_PER_CALL];
+            int zavail = 0;
+            unsigned long long zblock = 0;
+            // the remembered pieces of the Brownian path beyond t (local memory: indexed dynamically)
+            real sk_len[B2_RSWM_DEPTH], sk_W[B2_RSWM_DEPTH][B2_N], sk_Z[B2_RSWM_DEPTH][B2_N];
+            real dW[B2_N], dZ[B2_N], z[2 * B2_N];
+            auto draw = [&]() {   // the next 2n normals of this trajectory's stream, in order
+#pragma unroll
+                for (int j = 0; j < 2 * B2_N; j++) {
+                    if (zavail == 0) {
+                        b2_normals(a.seed, traj, zblock, zbuf);
+                        zblock++;
+                        zavail = B2_NORMALS_PER_CALL;
+                    }
+                    const int pos = B2_NORMALS_PER_CALL - zavail;
+#if B2_F64
+                    z[j] = pos == 0 ? zbuf[0] : zbuf[1];
+#else
+                    z[j] = pos == 0 ? zbuf[0] : pos == 1 ? zbuf[1] : pos == 2 ? zbuf[2] : zbuf[3];
+#endif
+                    zavail--;
+                }
+            };
+            while (t < t1) {
+                iter++;
+                if (iter > a.maxiters) {
+                    rc = B2_RC_MAXITERS;
+                    break;
+                }
+                if (dt != dt) {
+                    rc = B2_RC_DTNAN;
+                    break;
+                }
+                if (!have) {
+                    h = b2_min(dt, dtmax);
+                    bool clipped = false;
+                    if (h > t1 - t) {
+                        h = t1 - t;
+                        clipped = true;
+                    }
+                    if (!clipped && h <= b2_max(dtmin, (real)B2_EPS * b2_abs(t))) {
+                        rc = B2_RC_DTLESSTHANMIN;
+                        break;
+                    }
+                    if (sp == 0) {   // nothing remembered beyond t: fresh increments
+                        draw();
+                        const real sq = b2_sqrt(h);
+#pragma unroll
+                        for (int i = 0; i < B2_N; i++) {
+                            dW[i] = sq * z[i];
+                            dZ[i] = sq * z[B2_N + i];
+                        }
+                    } else if (sk_len[sp - 1] <= h) {   // the remembered piece is the step
+                        sp--;
+                        h = sk_len[sp];
+#pragma unroll
+                        for (int i = 0; i < B2_N; i++) {
+                            dW[i] = sk_W[sp][i];
+                            dZ[i] = sk_Z[sp][i];
+                        }
+                    } else {   // the step ends inside the remembered piece: Brownian bridge at q = h / L
+                        const real L = sk_len[sp - 1], q = h / L, sd = b2_sqrt(((real)1 - q) * h);
+                        draw();
+#pragma unroll
+                        for (int i = 0; i < B2_N; i++) {
+                            dW[i] = b2_fma(sd, z[i], q * sk_W[sp - 1][i]);
+                            dZ[i] = b2_fma(sd, z[B2_N + i], q * sk_Z[sp - 1][i]);
+                            sk_W[sp - 1][i] -= dW[i];
+                            sk_Z[sp - 1][i] -= dZ[i];
+                        }
+                        sk_len[sp - 1] = L - h;
+                    }
+                }
+                have = false;
+                real up[B2_N], E1[B2_N], E2[B2_N];
+#pragma unroll
+                for (int i = 0; i < B2_N; i++) up[i] = u[i];
+                b2_sde_step<ALG, true>(u, up, dW, dZ, p, t, h, E1, E2);
+                float acc = 0.0f;
+#pragma unroll
+                for (int i = 0; i < B2_N; i++) {
+                    const real sk = b2_fma(b2_max(b2_abs(up[i]), b2_abs(u[i])), B2_RTOL(a, i), B2_ATOL(a, i));
+                    const float r = (float)(b2_fma(delta, E1[i], E2[i]) / sk);
+                    acc = fmaf(r, r, acc);
+                }
+                const float EE2 = acc * (1.0f / (float)B2_N);
+                if (EE2 != EE2) {
+                    rc = B2_RC_DTNAN;
+                    break;
+                }
+                float q, l = lqinit;
+                if (EE2 == 0.0f) {
+                    q = inv_qmax;
+                } else {
+                    l = 0.5f * b2_fastlog2(EE2);
+                    q = b2_fastexp2(fmaf(-beta2, lq, beta1 * l));
+                    q = fmaxf(inv_qmax, fminf(inv_qmin, q * inv_gam));
+                }
+                if (!(EE2 <= 1.0f)) {   // reject: keep the first part of the increments, remember the rest
+                    nreject++;
+                    const float q11 = b2_fastexp2(beta1 * l);
+                    const real qr = (real)__fdiv_rn(1.0f, fminf(inv_qmin, q11 * inv_gam));   // h' / h in [qmin, gamma]
+                    if (sp >= B2_RSWM_DEPTH) {
+                        rc = B2_RC_FAILURE_;
+                        break;
+                    }
+                    const real hn = qr * h, sd = b2_sqrt(((real)1 - qr) * hn);
+                    draw();
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) {
+                        const real w = b2_fma(sd, z[i], qr * dW[i]), zz = b2_fma(sd, z[B2_N + i], qr * dZ[i]);
+                        sk_W[sp][i] = dW[i] - w;
+                        sk_Z[sp][i] = dZ[i] - zz;
+                        dW[i] = w;
+                        dZ[i] = zz;
+                        u[i] = up[i];
+                    }
+                    sk_len[sp++] = h - hn;
+                    h = hn;
+                    dt = hn;
+                    have = true;
+                    if (hn <= b2_max(dtmin, (real)B2_EPS * b2_abs(t))) {
+                        rc = B2_RC_DTLESSTHANMIN;
+                        break;
+                    }
+                    continue;
+                }
+                lq = fmaxf(l, lqinit);
+                dt = h * (real)__fdiv_rn(1.0f, q);
+                naccept++;
+                const real tprev = t;
+                real tnew = t + h;
+                if (b2_abs(tnew - t1) < (real)100 * (real)B2_EPS * b2_max(b2_abs(tnew), b2_abs(t1))) tnew = t1;
+                while (si < n_save) {   // linear interpolation between accepted steps
+                    const real tau = __ldg(gsave + si);
+                    if (!(tau <= tnew)) break;
+                    if (tau == tnew) {
+                        sink.put(si, u);
+                    } else {
+                        const real th = (tau - tprev) / h;
+                        real w[B2_N];
+#pragma unroll
+                        for (int i = 0; i < B2_N; i++) w[i] = b2_fma(th, u[i] - up[i], up[i]);
+                        sink.put(si, w);
+                    }
+                    si++;
+                }
+                t = tnew;
+            }
+            if (rc == 0) rc = B2_RC_SUCCESS;
+            else sink.fill(si, n_save, (real)__int_as_float(0x7fc00000));
+            a.retcode[idx] = rc;
+            if (a.stats) {
+                B2Stats s;
+                s.naccept = naccept;
+                s.nreject = nreject;
+                s.nf = (naccept + nreject) * (ALG == 9 ? 2 : 3);
+                s.nevents = 0;
+                a.stats[idx] = s;
+            }
+        }
+        if (stride) b2_flush(__ballot_sync(B2_FULL, active), warp_stage, stride, gout, idx, out_per_traj, lane);
+    }
+}

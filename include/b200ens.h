@@ -62,6 +62,10 @@ enum b200ens_error {
                                       warps; Tsit5 / Vern7 with at most a scalar ContinuousCallback; default: automatic when
                                       the one-thread variant spills > 1 KB (Vern7) / 4 KB (Tsit5)) */
 #define B200ENS_MODEL_NOSPLIT 16u  /* never use the split kernel */
+#define B200ENS_MODEL_SDE_ADAPTIVE 32u /* SRIW1 / SOSRA only: compile the ADAPTIVE stepper (embedded error estimate, PI controller
+                                      with the strong order 3/2, qmax default 1.125, rejection sampling with memory RSwM1).
+                                      opts.dt is the initial step, abstol / reltol apply, dW injection is not possible.
+                                      EXPERIMENTAL: restated in the oracle and cross-compiled, not yet validated on a GPU */
 
 /* What a problem looks like to the library: ODEProblem / SDEProblem (qa.jl:86,103) with f,
  * jac, tgrad, g and one ContinuousCallback (qa.jl:26; test/core.jl:69-72) given as CUDA-C

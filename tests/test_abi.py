@@ -59,6 +59,24 @@ def test_every_stepper_jit_compiles_for_sm100a_without_a_gpu(B, alg, dtype):
     assert "sm_100a" in m.log
 
 
+@pytest.mark.parametrize("alg", ["SRIW1", "SOSRA"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_adaptive_sde_kernel_jit_compiles(B, alg, dtype):
+    """B200ENS_MODEL_SDE_ADAPTIVE (experimental, include/b200ens.h): the RSwM kernel compiles for sm_100a; its local-memory
+    frame is the stack of remembered Brownian increments, not register spills."""
+    from b200ens import workloads as W
+
+    m = B.build_model(W.lorenz_additive_problem(dtype), getattr(B, alg)(), sde_adaptive=True)
+    info = m.info()
+    n, es = 3, np.dtype(dtype).itemsize
+    assert 0 < info["regs"] <= 255 and info["lmem"] >= 48 * (1 + 2 * n) * es
+    with pytest.raises(B.B200EnsError) as e:
+        B.build_model(W.lorenz_additive_problem(dtype), B.EM(), sde_adaptive=True)
+    assert e.value.code == -6
+    with pytest.raises(NotImplementedError, match="experimental"):      # the public API keeps it behind an explicit opt-in
+        B.solve(W.lorenz_additive_problem(dtype), getattr(B, alg)(), adaptive=True, dt=0.1, saveat=1.0)
+
+
 def test_compile_errors_are_reported(B):
     with pytest.raises(B.B200EnsError) as e:
         B.Model(3, 3, np.float64, "Tsit5", "__device__ void b2_rhs(real* du, const real* u, const real* p, real t) { du[0] = nope; }")

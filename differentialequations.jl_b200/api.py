@@ -631,8 +631,8 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
         adaptive = alg.adaptive_default
     sde_adaptive = bool(alg.is_sde and adaptive)
     if sde_adaptive:
-        # The adaptive SRIW1 / SOSRA kernel (rejection sampling with memory) is restated in the oracle and cross-compiled,
-        # but has not been validated on a GPU yet: opt in explicitly until it has.
+        # The adaptive SRIW1 / SOSRA kernel (rejection sampling with memory): SRIW1 parity with the oracle was measured on
+        # a B200, the SOSRA case has not run there yet -- opt in explicitly until it has.
         if os.environ.get("B200ENS_EXPERIMENTAL_SDE_ADAPTIVE") != "1":
             raise NotImplementedError("adaptive SDE stepping (RSwM) is experimental: pass adaptive=False and a fixed dt, or "
                                       "set B200ENS_EXPERIMENTAL_SDE_ADAPTIVE=1")

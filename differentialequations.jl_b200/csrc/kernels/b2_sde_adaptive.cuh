@@ -2,8 +2,8 @@
 // the ODE path with the strong order 3/2, and rejection sampling with memory (RSwM1, Rackauckas & Nie 2017) so that a
 // rejected step keeps the part of the Brownian path it already sampled.  Compiled only into models built with
 // B200ENS_MODEL_SDE_ADAPTIVE (B2_SDE_ADAPT); same expression tree as oracle/oracle_impl.inc solve_sde_adaptive.
-// EXPERIMENTAL in round 1: written against the oracle, not yet run on a GPU (the host API keeps it behind
-// B200ENS_EXPERIMENTAL_SDE_ADAPTIVE=1).  Reference names: SDEProblem /root/reference/test/qa/qa.jl:103; the
+// EXPERIMENTAL in round 1: SRIW1 parity with the oracle was measured on a B200, the SOSRA case has not run yet (the
+// host API keeps it behind B200ENS_EXPERIMENTAL_SDE_ADAPTIVE=1).  Reference names: SDEProblem /root/reference/test/qa/qa.jl:103; the
 // adaptive loop lives in StochasticDiffEq, outside the dep closure.
 #pragma once
 #include "b2_sde.cuh"

@@ -65,7 +65,7 @@ enum b200ens_error {
 #define B200ENS_MODEL_SDE_ADAPTIVE 32u /* SRIW1 / SOSRA only: compile the ADAPTIVE stepper (embedded error estimate, PI controller
                                       with the strong order 3/2, qmax default 1.125, rejection sampling with memory RSwM1).
                                       opts.dt is the initial step, abstol / reltol apply, dW injection is not possible.
-                                      EXPERIMENTAL: restated in the oracle and cross-compiled, not yet validated on a GPU */
+                                      EXPERIMENTAL: SRIW1 parity with the oracle measured on a B200, SOSRA not yet run there */
 
 /* What a problem looks like to the library: ODEProblem / SDEProblem (qa.jl:86,103) with f,
  * jac, tgrad, g and one ContinuousCallback (qa.jl:26; test/core.jl:69-72) given as CUDA-C

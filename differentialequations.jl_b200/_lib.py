@@ -11,7 +11,6 @@ LIB_PATH = os.path.join(HERE, "csrc", "libb200ens.so")
 F32, F64 = 0, 1
 ALG_IDS = {"Tsit5": 1, "Vern7": 2, "Rosenbrock23": 3, "Rodas5": 4, "Rodas5P": 5, "EM": 6, "SOSRA": 7, "Rodas4": 8, "SRIW1": 9}
 MODEL_FAST_MATH = 1
-MODEL_PACKED_X2 = 2
 MODEL_KSMEM = 4
 MODEL_SPLIT = 8
 MODEL_NOSPLIT = 16
@@ -49,6 +48,7 @@ class Opts(C.Structure):
         ("block_threads", C.c_int32), ("stage_outputs", C.c_int32),
         ("work_order", C.c_int32), ("save_everystep", C.c_int32),
         ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double)),
+        ("noise_stream_len", C.c_int64),
     ]
 
 
@@ -115,7 +115,7 @@ def lib():
     L.b200ens_host_alloc.restype = C.c_void_p
     L.b200ens_host_free.argtypes = [C.c_void_p]
     L.b200ens_host_free.restype = None
-    if L.b200ens_abi_version() != 4:
+    if L.b200ens_abi_version() != 5:
         raise ImportError("libb200ens ABI version mismatch")
     _lib = L
     return L
@@ -136,7 +136,7 @@ class Model:
     """A compiled (problem functions x algorithm x dtype) kernel: b200ens_model*."""
 
     def __init__(self, n_state, n_param, dtype, alg, rhs_src, jac_src=None, tgrad_src=None, noise_src=None,
-                 condition_src=None, affect_src=None, name="model", fast_math=False, packed_x2=False,
+                 condition_src=None, affect_src=None, name="model", fast_math=False,
                  dcondition_src=None, daffect_src=None, ksmem=False, split=None, sde_adaptive=False):
         L = lib()
         d = ModelDesc()
@@ -144,7 +144,7 @@ class Model:
         d.n_state, d.n_param = n_state, n_param
         d.dtype = F64 if np.dtype(dtype) == np.float64 else F32
         d.alg = ALG_IDS[alg] if isinstance(alg, str) else int(alg)
-        d.flags = ((MODEL_FAST_MATH if fast_math else 0) | (MODEL_PACKED_X2 if packed_x2 else 0)
+        d.flags = ((MODEL_FAST_MATH if fast_math else 0)
                    | (MODEL_KSMEM if ksmem else 0) | (MODEL_SPLIT if split is True else 0)
                    | (MODEL_NOSPLIT if split is False else 0) | (MODEL_SDE_ADAPTIVE if sde_adaptive else 0))
         enc = lambda s: s.encode() if s is not None else None

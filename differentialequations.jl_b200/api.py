@@ -312,14 +312,13 @@ class EnsembleB200:
     warp before it fetches new trajectories (0 = auto); stage_outputs: -1 auto / 0 / 1; work_order: -1 auto / 0
     caller's order / 1 integrate in descending expected-work order (scheduling only, identical results)."""
 
-    def __init__(self, devices=None, refill_threshold=0, stage_outputs=-1, fast_math=False, packed_x2=False,
+    def __init__(self, devices=None, refill_threshold=0, stage_outputs=-1, fast_math=False,
                  stage_vectors_in_smem=False, work_order=-1, split=None):
         self.devices = devices
         self.refill_threshold = refill_threshold
         self.stage_outputs = stage_outputs
         self.work_order = work_order
         self.fast_math = fast_math
-        self.packed_x2 = packed_x2   # Float32 Tsit5: two trajectories per thread in packed FP32 (FFMA2)
         self.stage_vectors_in_smem = stage_vectors_in_smem   # ERK k-vectors in shared memory (large n_state)
         self.split = split   # None auto / True / False: components of one trajectory split over the 4 warps of a CTA
 
@@ -444,12 +443,12 @@ class _LazySeq:
 _model_cache = {}
 
 
-def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False, ksmem=False, split=None, sde_adaptive=False):
+def build_model(prob, alg, callback=None, fast_math=False, ksmem=False, split=None, sde_adaptive=False):
     """Trace prob.f (and g / callback), emit CUDA C, JIT it for sm_100a.  Cached per function objects."""
     n, m = prob.u0.shape[0], prob.p.shape[0]
     dtype = prob.u0.dtype
     mm = getattr(prob, "mass_matrix", None)
-    key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math, packed_x2, ksmem, split,
+    key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math, ksmem, split,
            None if mm is None else mm.tobytes(), sde_adaptive)
     hit = _model_cache.get(key)
     if hit is not None and hit[1] is prob.f:
@@ -485,7 +484,7 @@ def build_model(prob, alg, callback=None, fast_math=False, packed_x2=False, ksme
         srcs["dcondition_src"], srcs["daffect_src"], term = codegen.emit_discrete_callback(dcb, n, m)
         terminate |= 2 if term else 0
     model = _lib.Model(n, m, dtype, alg.name, name=getattr(prob.f, "__name__", "model"), fast_math=fast_math,
-                       packed_x2=packed_x2, ksmem=ksmem, split=split, sde_adaptive=sde_adaptive, **srcs)
+                       ksmem=ksmem, split=split, sde_adaptive=sde_adaptive, **srcs)
     model.sources = srcs
     model.event_terminate = terminate
     _model_cache[key] = (model, prob.f)
@@ -631,22 +630,19 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
         adaptive = alg.adaptive_default
     sde_adaptive = bool(alg.is_sde and adaptive)
     if sde_adaptive:
-        # The adaptive SRIW1 / SOSRA kernel (rejection sampling with memory): SRIW1 parity with the oracle was measured on
-        # a B200, the SOSRA case has not run there yet -- opt in explicitly until it has.
-        if os.environ.get("B200ENS_EXPERIMENTAL_SDE_ADAPTIVE") != "1":
-            raise NotImplementedError("adaptive SDE stepping (RSwM) is experimental: pass adaptive=False and a fixed dt, or "
-                                      "set B200ENS_EXPERIMENTAL_SDE_ADAPTIVE=1")
         if alg.name not in ("SRIW1", "SOSRA"):
             raise NotImplementedError(f"{alg.name} has no embedded error estimate: adaptive stepping needs SRIW1 or SOSRA")
-        if dt is None or dW is not None:
-            raise ValueError("adaptive SDE stepping needs an initial dt and generates its own noise (no dW)")
+        if dt is None:
+            raise ValueError("adaptive SDE stepping needs an initial dt")
+        # dW, when given, is the trajectory's stream of STANDARD NORMALS [N, len] (consumed in order by the rejection
+        # sampling with memory: 2n per fresh step, bridge draw or rejection) -- the pathwise-parity hook
         abstol = 1e-2 if abstol is None else abstol      # StochasticDiffEq's defaults
         reltol = 1e-2 if reltol is None else reltol
     if dt is None:
         if not adaptive:
             raise ValueError("fixed-step solves need dt")
         dt = 0.0   # automatic per-trajectory initial step on the device
-    model = build_model(base, alg, callback, ensemblealg.fast_math, ensemblealg.packed_x2 and not save_everystep,
+    model = build_model(base, alg, callback, ensemblealg.fast_math,
                         ensemblealg.stage_vectors_in_smem, False if save_everystep else ensemblealg.split,
                         sde_adaptive=sde_adaptive)
     ts = _saveat_array(saveat, base.tspan, dtype)
@@ -676,6 +672,9 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
     o.seed = int(seed)
     o.traj_offset = int(_lo)    # global trajectory index of this batch's first trajectory (Philox counter base)
     o.noise_injected = 0 if dW is None else 1
+    if sde_adaptive and dW is not None:
+        dW = np.ascontiguousarray(dW, dtype=dtype).reshape(N, -1)
+        o.noise_stream_len = int(dW.shape[1])
     if callback is not None:
         o.event_terminate = int(model.event_terminate)
         ccb, _ = _split_callbacks(callback)

@@ -17,9 +17,6 @@
 #define B2_HAS_EVENT 0
 #define B2_HAS_DEVENT 0
 #define B2_BLOCK 128
-#ifdef AOT_X2
-#define B2_X2 1
-#endif
 #ifdef AOT_SPLIT
 #define B2_SPLIT 1   // one trajectory per lane of a 4-warp CTA (kernels/b2_split.cuh); n = 3 -> one component per warp, one padded
 #endif

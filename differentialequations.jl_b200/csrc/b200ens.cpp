@@ -116,7 +116,6 @@ struct b200ens_model {
     int ksmem = 0;          // 1: ERK stage vectors in shared memory
     int split = 0;          // 1: one trajectory per lane of a 4-warp CTA, components split over the warps (b2_split.cuh)
     int kvec_bytes = 0;     // shared-memory bytes per thread for them
-    int x2 = 0;             // 1: two trajectories per thread, packed FP32 (FFMA2)
     std::mutex mu;
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
@@ -130,9 +129,7 @@ namespace {
 // ---------------------------------------------------------------- NVRTC, loaded explicitly
 // The JIT compiler is dlopen'ed by PATH instead of being bound at link time: a process that imported PyTorch first
 // already holds torch's bundled libnvrtc.so.12 (12.8 in this image), and link-time binding would silently pick that
-// one up instead of the CUDA toolkit's (12.9) -- different ptxas, different register allocation, and for the packed
-// FP32x2 kernel even different VALUES (measured: bit-identical to the oracle under 12.8, ~1e-6 relative off under
-// 12.9).  Search order: $B200ENS_NVRTC, the toolkit the library was built against, then the default loader path.
+// one up instead of the CUDA toolkit's (12.9) -- different ptxas, different register allocation.  Search order: $B200ENS_NVRTC, the toolkit the library was built against, then the default loader path.
 struct NvrtcApi {
     void* handle = nullptr;
     int major = 0, minor = 0;
@@ -286,18 +283,33 @@ void parse_ptxas_log(b200ens_model* m) {
     if (m->spill < 0) m->spill = 2 * m->lmem;
 }
 
-std::string build_source(const b200ens_model_desc* d, int min_blocks, int block, int ksmem, int x2 = 0, int split = 0) {
+std::string build_source(const b200ens_model_desc* d, int min_blocks, int block, int ksmem, int split = 0) {
     char head[1024];
     snprintf(head, sizeof head,
              "// generated by libb200ens (model '%s')\n"
              "#define B2_F64 %d\n#define B2_NSTATE %d\n#define B2_NPARAM %d\n#define B2_ALG %d\n"
              "#define B2_HAS_JAC %d\n#define B2_HAS_TGRAD %d\n#define B2_HAS_NOISE %d\n#define B2_HAS_EVENT %d\n#define B2_HAS_DEVENT %d\n"
-             "#define B2_BLOCK %d\n#define B2_MINBLOCKS %d\n#define B2_KSMEM %d\n#define B2_X2 %d\n#define B2_SPLIT %d\n#include \"b2_common.cuh\"\n",
+             "#define B2_BLOCK %d\n#define B2_MINBLOCKS %d\n#define B2_KSMEM %d\n#define B2_SPLIT %d\n#include \"b2_common.cuh\"\n",
              d->name ? d->name : "", d->dtype == B200ENS_F64 ? 1 : 0, d->n_state, d->n_param, d->alg,
              d->jac_src ? 1 : 0, d->tgrad_src ? 1 : 0, d->noise_src ? 1 : 0,
              (d->condition_src && d->affect_src) ? 1 : 0, (d->dcondition_src && d->daffect_src) ? 1 : 0, block, min_blocks,
-             ksmem, x2, split);
-    std::string s = head;
+             ksmem, split);
+    std::string s;
+    // B200ENS_DEFINES="NAME=VALUE,NAME2=VALUE2": extra #defines in front of everything (experiments and A/B tests of
+    // kernel variants, e.g. B2_PACK2=0); part of the source, hence of every cache key
+    if (const char* e = getenv("B200ENS_DEFINES")) {
+        std::string defs = e;
+        size_t pos = 0;
+        while (pos < defs.size()) {
+            size_t end = defs.find(',', pos);
+            if (end == std::string::npos) end = defs.size();
+            std::string item = defs.substr(pos, end - pos);
+            const size_t eq = item.find('=');
+            if (!item.empty()) s += "#define " + (eq == std::string::npos ? item : item.substr(0, eq) + " " + item.substr(eq + 1)) + "\n";
+            pos = end + 1;
+        }
+    }
+    s += head;
     for (const char* part : {d->rhs_src, d->jac_src, d->tgrad_src, d->noise_src, d->condition_src, d->affect_src,
                              d->dcondition_src, d->daffect_src})
         if (part) {
@@ -366,9 +378,9 @@ int ensure_loaded(b200ens_model* m) {
     // optional entry points are looked up only in modules that define them (kernels/b2_entry.cuh): no failing API
     // calls on the normal path (they show up as errors under compute-sanitizer)
     const bool erk = m->alg == B200ENS_TSIT5 || m->alg == B200ENS_VERN7;
-    if ((erk && !m->x2) || is_rosenbrock(m->alg))
+    if (erk || is_rosenbrock(m->alg))
         CU(cudaLibraryGetKernel(&m->kernel_adaptive, m->lib, "b2_ensemble_kernel_adaptive"));
-    if (!is_sde(m->alg) && !m->x2) {
+    if (!is_sde(m->alg)) {
         CU(cudaLibraryGetKernel(&m->k_work_keys, m->lib, "b2_work_keys"));
         CU(cudaLibraryGetKernel(&m->k_work_scatter, m->lib, "b2_work_scatter"));
     }
@@ -510,14 +522,14 @@ int plan_launch(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, long long
     bool staged = false;
     // Measured on B200 (profiles/): for the saveat shapes of configs 1-4 direct global stores are ~3%
     // faster than shared-memory staging (L2 merges the 12-byte rows), so auto means direct.
-    if (o->stage_outputs > 0 && n_save > 0 && !m->x2 && !m->split && smem + ksm <= 200 * 1024) {
+    if (o->stage_outputs > 0 && n_save > 0 && !m->split && smem + ksm <= 200 * 1024) {
         if (smem + ksm > 48 * 1024)
             CU(cudaFuncSetAttribute((const void*)m->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + ksm)));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_staged, (const void*)m->kernel, block, smem + ksm));
         // stage when it costs at most a quarter of the occupancy (or when forced)
         staged = nb_staged >= 1 && (o->stage_outputs > 0 || 4 * nb_staged >= 3 * nb_direct);
     }
-    if (o->stage_outputs > 0 && !staged && !m->x2 && !m->split)
+    if (o->stage_outputs > 0 && !staged && !m->split)
         return fail(B200ENS_E_UNSUPPORTED, "stage_outputs=1 but %zu bytes of shared memory per block do not fit", smem);
     int nb = staged ? nb_staged : nb_direct;
     if (const char* e = getenv("B200ENS_BLOCKS_PER_SM")) nb = std::max(1, std::min(nb, atoi(e)));  // experiments
@@ -525,14 +537,14 @@ int plan_launch(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, long long
     lp->block = block;
     lp->stride = staged ? stride : 0;
     lp->smem = (int)((staged ? smem : 0) + ksm);
-    // packed kernels hold two trajectories per thread; split kernels one trajectory per LANE of a 4-warp CTA
-    const long long per_block = m->split ? 32 : (long long)block * (m->x2 ? 2 : 1);
+    // split kernels: one trajectory per LANE of a 4-warp CTA
+    const long long per_block = m->split ? 32 : (long long)block;
     const long long want = (N + per_block - 1) / per_block;
     lp->grid = (int)std::max<long long>(1, std::min<long long>((long long)nb * d->sms, want));
     int refill = o->refill_threshold;
     if (refill <= 0) refill = (o->adaptive && !is_sde(m->alg)) ? 4 : 32;
     refill = std::min(refill, 32);
-    lp->refill = m->x2 ? 2 * refill : refill;   // packed kernels count idle slots out of 64 per warp
+    lp->refill = refill;
     return 0;
 }
 
@@ -562,8 +574,8 @@ int fill_args(const b200ens_model* m, const b200ens_opts* o, B2Args* a) {
     if (st < 0) st = (m->alg == B200ENS_RODAS4 || m->alg == B200ENS_RODAS5 || m->alg == B200ENS_RODAS5P) ? 1 : 0;
     a->save_tstops = st;
     if (!(o->t1 > o->t0)) return fail(B200ENS_E_INVALID, "tspan must satisfy t1 > t0 (forward integration only)");
-    if (!(o->dt > 0) && !(a->adaptive && o->dt == 0 && !m->x2))
-        return fail(B200ENS_E_INVALID, "dt must be > 0 (fixed step, SDE, packed kernel) or 0 = automatic initial step (adaptive)");
+    if (!(o->dt > 0) && !(a->adaptive && o->dt == 0))
+        return fail(B200ENS_E_INVALID, "dt must be > 0 (fixed step, SDE) or 0 = automatic initial step (adaptive)");
     a->f_t0 = (float)a->t0;
     a->f_t1 = (float)a->t1;
     a->f_dt = (float)a->dt;
@@ -587,6 +599,9 @@ int fill_args(const b200ens_model* m, const b200ens_opts* o, B2Args* a) {
         a->f_tol_r[i] = (float)tr;
     }
     a->nsteps_noise = is_sde(m->alg) ? (long long)std::ceil((o->t1 - o->t0) / o->dt - 1e-9) : 0;
+    if (is_sde(m->alg) && !sde_adapt && a->nsteps_noise >= (1ll << 31))
+        return fail(B200ENS_E_INVALID, "fixed-step SDE solve with %lld steps (the step index is 32-bit)", a->nsteps_noise);
+    if (sde_adapt) a->nsteps_noise = o->noise_injected ? o->noise_stream_len : 0;   // length of the injected stream of normals
     return 0;
 }
 
@@ -597,15 +612,15 @@ int check_opts(const b200ens_model* m, const b200ens_opts* o, int n_save, const 
                     sizeof(b200ens_opts));
     if (n_save < 0) return fail(B200ENS_E_INVALID, "n_save < 0");
     if (o->save_everystep) {
-        if (is_sde(m->alg) || m->x2 || m->split)
+        if (is_sde(m->alg) || m->split)
             return fail(B200ENS_E_UNSUPPORTED, "save_everystep needs an ODE stepper and the one-thread kernel (compile with "
                                                "B200ENS_MODEL_NOSPLIT for large systems; SDE: use a saveat grid)");
         if (n_save < 2) return fail(B200ENS_E_INVALID, "save_everystep: n_save is the capacity per trajectory and must be >= 2");
         if (o->stage_outputs > 0) return fail(B200ENS_E_UNSUPPORTED, "save_everystep with stage_outputs=1");
     }
     if (o->noise_injected && !dW) return fail(B200ENS_E_INVALID, "noise_injected=1 but dW is NULL");
-    if (o->noise_injected && (m->flags & B200ENS_MODEL_SDE_ADAPTIVE))
-        return fail(B200ENS_E_UNSUPPORTED, "adaptive SDE stepping draws its own noise (rejection sampling with memory): noise_injected=1 is not possible");
+    if (o->noise_injected && (m->flags & B200ENS_MODEL_SDE_ADAPTIVE) && o->noise_stream_len <= 0)
+        return fail(B200ENS_E_INVALID, "adaptive SDE stepping with noise_injected=1 needs opts.noise_stream_len > 0 (dW = [N][noise_stream_len] standard normals)");
     return 0;
 }
 
@@ -626,7 +641,7 @@ constexpr int kWorkBuckets = 1024, kWorkTile = 4;
 constexpr size_t kWorkHead = 16 + 2 * (size_t)kWorkBuckets * sizeof(unsigned);   // counter | histogram | cursors
 size_t work_scratch_bytes(long long N) { return kWorkHead + (size_t)N * (sizeof(unsigned) + sizeof(unsigned short)) + 16; }
 bool want_work_order(const b200ens_model* m, const b200ens_opts* o, const B2Args& a, long long N) {
-    if (!m->k_work_keys || !a.adaptive || m->x2 || N >= (1ll << 32)) return false;
+    if (!m->k_work_keys || !a.adaptive || N >= (1ll << 32)) return false;
     if (const char* e = getenv("B200ENS_WORK_ORDER")) return atoi(e) != 0;   // experiments
     return o->work_order > 0 || (o->work_order < 0 && N >= 32768);
 }
@@ -738,7 +753,9 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
     B2Args base{};
     rc = fill_args(m, o, &base);
     if (rc) return rc;
-    const size_t noise_per_traj = dW ? (size_t)base.nsteps_noise * ((m->alg == B200ENS_SOSRA || m->alg == B200ENS_SRIW1) ? 2 : 1) * n * es : 0;
+    const bool sde_adapt = (m->flags & B200ENS_MODEL_SDE_ADAPTIVE) != 0;   // dW = [N][noise_stream_len] standard normals
+    const size_t noise_per_traj = !dW ? 0 : sde_adapt ? (size_t)base.nsteps_noise * es
+                                  : (size_t)base.nsteps_noise * ((m->alg == B200ENS_SOSRA || m->alg == B200ENS_SRIW1) ? 2 : 1) * n * es;
     const size_t out_per_traj = (size_t)n_save * n * es;
 
     rc = grow(&d->saveat, &d->cap_save, std::max<size_t>(es, (size_t)n_save * es));
@@ -910,7 +927,7 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
         a.refill_threshold = lp.refill;
         a.stage_stride = lp.stride;
         LaunchPlan l2 = lp;
-        const long long pb = m->split ? 32 : (long long)lp.block * (m->x2 ? 2 : 1);
+        const long long pb = m->split ? 32 : (long long)lp.block;
         l2.grid = (int)std::max<long long>(1, std::min<long long>(lp.grid, (cn + pb - 1) / pb));
         CU(cudaEventRecord(s.ev[1], s.stream));
         if (want_work_order(m, o, a, cn)) {
@@ -1055,34 +1072,6 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     const int nvec = d->alg == B200ENS_TSIT5 ? 7 : d->alg == B200ENS_VERN7 ? 14 : 0;
     const bool flag_k = (d->flags & B200ENS_MODEL_KSMEM) != 0;
     bool try_regs = !(((force_k && atoi(force_k) == 1) || flag_k) && nvec);
-    // Packed FP32: two trajectories per thread (FFMA2/FADD2/FMUL2, Blackwell only) for the register-light
-    // Float32 explicit case without callbacks -- the headline Lorenz/Tsit5 configuration.
-    const char* force_x2 = getenv("B200ENS_X2");
-    const bool ask_x2 = (d->flags & B200ENS_MODEL_PACKED_X2) || (force_x2 && atoi(force_x2) == 1);
-    // The packed kernel is bit-identical to the scalar one only when ptxas keeps every packed op as written: validated
-    // with NVRTC 12.8; the 12.9 back-end produces ~1e-6 relative differences for the same PTX (profiles/README.md), so
-    // with any other NVRTC the request falls through to the scalar kernel (same results, and the faster one anyway).
-    const NvrtcApi* nvx = nvrtc_api();
-    const bool x2_validated = nvx && nvx->major == 12 && nvx->minor == 8;
-    const bool want_x2 = ask_x2 && x2_validated && d->dtype == B200ENS_F32 && d->alg == B200ENS_TSIT5 && !d->condition_src &&
-                         !d->dcondition_src && d->n_state <= 6;
-    if (want_x2) {
-        int mbx = 4;
-        if (const char* e = getenv("B200ENS_MINBLOCKS")) mbx = std::max(1, atoi(e));
-        for (;; mbx--) {
-            m->source = build_source(d, mbx, kBlock, 0, 1);
-            rc = nvrtc_compile(m.get());
-            if (rc) break;
-            parse_ptxas_log(m.get());
-            if (m->spill <= 96 || mbx <= 1 || getenv("B200ENS_MINBLOCKS")) break;
-        }
-        if (!rc && m->spill <= 96) {
-            m->x2 = 1;
-            mb = mbx;
-            try_regs = false;
-        }
-        rc = 0;
-    }
     // Vern7 on a system whose 14 stage vectors need more than ~200 registers cannot fit one thread: compile the split
     // kernel first and skip the (slow to compile, several hundred KB) one-thread variants when it builds within its spill
     // budget.  Same choice as the general rule below makes for these models, at half the compile time.
@@ -1091,7 +1080,7 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
         int mbs = 3, rc2 = 0;
         if (const char* e = getenv("B200ENS_MINBLOCKS")) mbs = std::max(1, atoi(e));
         for (;; mbs--) {
-            m->source = build_source(d, mbs, 128, 0, 0, 1);
+            m->source = build_source(d, mbs, 128, 0, 1);
             rc2 = nvrtc_compile(m.get());
             if (rc2) break;
             parse_ptxas_log(m.get());
@@ -1110,7 +1099,7 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     const bool split_off = (d->flags & B200ENS_MODEL_NOSPLIT) || (force_s && atoi(force_s) == 0);
     const bool split_on = (d->flags & B200ENS_MODEL_SPLIT) || (force_s && atoi(force_s) == 1);
     const bool vector_cb = d->condition_src && strstr(d->condition_src, "B2_NCOND") != nullptr;   // one-thread kernels only
-    const bool split_eligible = nvec && !m->x2 && !d->dcondition_src && !vector_cb && d->n_state >= 4 && !flag_k &&
+    const bool split_eligible = nvec && !d->dcondition_src && !vector_cb && d->n_state >= 4 && !flag_k &&
                                 !(force_k && atoi(force_k) == 1);
     const bool surely_spills = d->alg == B200ENS_VERN7 && nvec * d->n_state * (d->dtype == B200ENS_F64 ? 2 : 1) > 200;   // + ~55 registers for everything else > 255
     if (try_regs && split_eligible && !split_off && (split_on || surely_spills) && try_split(0, false, split_on)) {
@@ -1156,7 +1145,7 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
             m->smem = keep_smem;
         }
     }
-    if (!rc && nvec && !m->x2 && !m->split && (!try_regs || (m->spill > 4096 && !(force_k && atoi(force_k) == 0)))) {
+    if (!rc && nvec && !m->split && (!try_regs || (m->spill > 4096 && !(force_k && atoi(force_k) == 0)))) {
         const int per_thread = nvec * d->n_state * (d->dtype == B200ENS_F64 ? 8 : 4);
         int block = std::min(128, (114688 / per_thread) / 32 * 32);
         if (block >= 32) {

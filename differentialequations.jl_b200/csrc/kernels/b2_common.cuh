@@ -10,12 +10,7 @@
 //   s = c1*x1; s = fma(c2,x2,s); ...   stage argument U = fma(dt, s, uprev).
 #pragma once
 
-#ifndef B2_X2
-#define B2_X2 0   // 1: two trajectories per thread, packed FP32 (FFMA2/FADD2/FMUL2, sm_100+), see b2_ode_driver_x2.cuh
-#endif
-
-// sreal: the scalar storage type of u, p, t in global memory.  real: the type the steppers compute in
-// (== sreal, or the packed pair b2f2 in B2_X2 mode).
+// sreal: the scalar storage type of u, p, t in global memory; real: the type the steppers compute in (the same).
 #if B2_F64
 typedef double sreal;
 #define B2_EPS 2.220446049250313e-16
@@ -23,45 +18,7 @@ typedef double sreal;
 typedef float sreal;
 #define B2_EPS 1.1920928955078125e-7f
 #endif
-
-#if B2_X2
-// Two independent trajectories in the two halves of a 64-bit register pair.  Every operation is the IEEE
-// round-to-nearest FP32 operation applied per half (FFMA2/FADD2/FMUL2 are exact per-lane equivalents of
-// FFMA/FADD/FMUL), so a packed run is bit-identical to two scalar runs.
-struct __align__(8) b2f2 {
-    float2 v;
-    __device__ __forceinline__ b2f2() {}
-    __device__ __forceinline__ b2f2(float a) { v.x = a; v.y = a; }
-    __device__ __forceinline__ b2f2(double a) { v.x = (float)a; v.y = (float)a; }
-    __device__ __forceinline__ b2f2(int a) { v.x = (float)a; v.y = (float)a; }
-    __device__ __forceinline__ b2f2(float a, float b) { v.x = a; v.y = b; }
-    __device__ __forceinline__ explicit b2f2(float2 a) : v(a) {}
-};
-typedef b2f2 real;
-__device__ __forceinline__ b2f2 operator+(b2f2 a, b2f2 b) { return b2f2(__fadd2_rn(a.v, b.v)); }
-// negation / subtraction as exact packed ops (x * -1 and fma(b, -1, a) round exactly like -x and a - b);
-// a scalar sign flip per half would cost two extra issue slots each
-__device__ __forceinline__ b2f2 operator-(b2f2 a) { return b2f2(__fmul2_rn(a.v, make_float2(-1.0f, -1.0f))); }
-__device__ __forceinline__ b2f2 operator-(b2f2 a, b2f2 b) { return b2f2(__ffma2_rn(b.v, make_float2(-1.0f, -1.0f), a.v)); }
-__device__ __forceinline__ b2f2 operator*(b2f2 a, b2f2 b) { return b2f2(__fmul2_rn(a.v, b.v)); }
-__device__ __forceinline__ b2f2 operator/(b2f2 a, b2f2 b) { return b2f2(__fdiv_rn(a.v.x, b.v.x), __fdiv_rn(a.v.y, b.v.y)); }
-__device__ __forceinline__ b2f2 b2_fma(b2f2 a, b2f2 b, b2f2 c) { return b2f2(__ffma2_rn(a.v, b.v, c.v)); }
-__device__ __forceinline__ b2f2 b2_abs(b2f2 a) { return b2f2(fabsf(a.v.x), fabsf(a.v.y)); }
-__device__ __forceinline__ b2f2 b2_max(b2f2 a, b2f2 b) { return b2f2(fmaxf(a.v.x, b.v.x), fmaxf(a.v.y, b.v.y)); }
-__device__ __forceinline__ b2f2 b2_min(b2f2 a, b2f2 b) { return b2f2(fminf(a.v.x, b.v.x), fminf(a.v.y, b.v.y)); }
-__device__ __forceinline__ b2f2 b2_sqrt(b2f2 a) { return b2f2(__fsqrt_rn(a.v.x), __fsqrt_rn(a.v.y)); }
-// math functions a traced model may use (codegen.py emits these names), applied per half
-#define B2_X2_FN1(name, fn) __device__ __forceinline__ b2f2 name(b2f2 a) { return b2f2(fn(a.v.x), fn(a.v.y)); }
-B2_X2_FN1(sqrt, __fsqrt_rn) B2_X2_FN1(exp, expf) B2_X2_FN1(log, logf) B2_X2_FN1(sin, sinf) B2_X2_FN1(cos, cosf)
-B2_X2_FN1(tan, tanf) B2_X2_FN1(tanh, tanhf) B2_X2_FN1(fabs, fabsf)
-__device__ __forceinline__ b2f2 pow(b2f2 a, b2f2 b) { return b2f2(powf(a.v.x, b.v.x), powf(a.v.y, b.v.y)); }
-// half selection (h is a compile-time constant after unrolling) and per-half blend
-__device__ __forceinline__ float b2_get(const b2f2& a, int h) { return h ? a.v.y : a.v.x; }
-__device__ __forceinline__ void b2_set(b2f2& a, int h, float s) { if (h) a.v.y = s; else a.v.x = s; }
-__device__ __forceinline__ b2f2 b2_blend(bool c0, bool c1, b2f2 a, b2f2 b) { return b2f2(c0 ? a.v.x : b.v.x, c1 ? a.v.y : b.v.y); }
-#else
 typedef sreal real;
-#endif
 
 #ifndef B2_COND_MASK
 #define B2_COND_MASK 0xffffffffu   // components of u the ContinuousCallback condition reads (bit i = u[i])
@@ -145,6 +102,30 @@ __device__ __forceinline__ float b2_sqrt(float a) { return __fsqrt_rn(a); }
 __device__ __forceinline__ double b2_sqrt(double a) { return __dsqrt_rn(a); }
 __device__ __forceinline__ bool b2_isnan(sreal a) { return a != a; }
 
+// ---- packed component pairs (Float32, one trajectory per thread): Blackwell's FFMA2 / FMUL2 / FADD2 apply the IEEE
+// round-to-nearest FP32 operation to both halves of a 64-bit register pair and take a 32-bit immediate or a scalar
+// register broadcast as the other operand, so the linear combinations of two state COMPONENTS of one trajectory cost
+// one issue slot instead of two -- same bits, no extra registers (profiles/README.md, round 2).  B2_PACK2 = 1 turns the
+// chunked loops of b2_erk.cuh into pair loops (+ a scalar tail for odd n); everywhere else a chunk is one scalar.
+#ifndef B2_PACK2
+#define B2_PACK2 (!B2_F64 && !B2_KSMEM)
+#endif
+#if B2_PACK2
+struct b2p {
+    float2 v;
+};
+__device__ __forceinline__ b2p operator*(b2p a, b2p b) { b2p r; r.v = __fmul2_rn(a.v, b.v); return r; }
+__device__ __forceinline__ b2p b2_fma(b2p a, b2p b, b2p c) { b2p r; r.v = __ffma2_rn(a.v, b.v, c.v); return r; }
+template <class V> __device__ __forceinline__ V b2_bc(float x);
+template <> __device__ __forceinline__ float b2_bc<float>(float x) { return x; }
+template <> __device__ __forceinline__ b2p b2_bc<b2p>(float x) { b2p r; r.v = make_float2(x, x); return r; }
+template <class V> __device__ __forceinline__ V b2_ld(const float* a, int i);
+template <> __device__ __forceinline__ float b2_ld<float>(const float* a, int i) { return a[i]; }
+template <> __device__ __forceinline__ b2p b2_ld<b2p>(const float* a, int i) { b2p r; r.v = make_float2(a[i], a[i + 1]); return r; }
+__device__ __forceinline__ void b2_st(float* a, int i, float v) { a[i] = v; }
+__device__ __forceinline__ void b2_st(float* a, int i, b2p v) { a[i] = v.v.x; a[i + 1] = v.v.y; }
+#endif
+
 // ---- deterministic float log2 / exp2 for the PI controller (same primitive sequence as the
 // oracle's orc_fastlog2 / orc_fastexp2; restates upstream's approximate FastPower):
 //   log2(x) = e + t*P5(t), t = mantissa-1;   2^y = 2^rint(y) * Q6(y - rint(y))
@@ -173,6 +154,18 @@ __device__ __forceinline__ float b2_fastexp2(float y) {
     p = __fmaf_rn(p, f, 6.9314718e-1f);
     p = __fmaf_rn(p, f, 1.0f);
     return __uint_as_float(__float_as_uint(p) + (unsigned)((int)fi << 23));
+}
+
+// ---- deterministic Float32 reciprocal for the error norm: exponent-flip initial guess (relative error <= 5.1 %)
+// + two Newton steps x <- x + x*(1 - s*x) written as FMAs -> relative error <= 6.6e-6, seven issue slots, no MUFU, no
+// slow-path branch (an IEEE division is 13-15 slots with its FCHK / BSSY / BSYNC scaffolding, profiles/README.md).
+// Same primitive sequence as the oracle's orc_rcp_nr.  s = +0 -> +inf, s = +inf -> -inf (an overflowed proposal is
+// REJECTED through r = utilde * -inf, not accepted with a zero estimate), NaN -> NaN.
+__device__ __forceinline__ float b2_rcp_nr(float s) {
+    float x = __uint_as_float(0x7EF311C7u - __float_as_uint(s));
+    x = __fmaf_rn(x, __fmaf_rn(-s, x, 1.0f), x);
+    x = __fmaf_rn(x, __fmaf_rn(-s, x, 1.0f), x);
+    return x;
 }
 
 // ---- ITP root-find helper: pw = eps * 2^(k+1), eps = 2*B2_EPS, k = number of halvings of wd until wd <= 2*eps

@@ -13,8 +13,6 @@
 #include "b2_erk.cuh"
 #if B2_SPLIT
 #include "b2_ode_driver_split.cuh"
-#elif B2_X2
-#include "b2_ode_driver_x2.cuh"
 #else
 #include "b2_ode_driver.cuh"
 #endif
@@ -30,11 +28,11 @@
 #error "unknown B2_ALG"
 #endif
 
-#if !(B2_ALG == 6 || B2_ALG == 7 || B2_ALG == 9) && !B2_X2
+#if !(B2_ALG == 6 || B2_ALG == 7 || B2_ALG == 9)
 #include "b2_work.cuh"   // expected-work ordering of the trajectory queue (adaptive ODE steppers)
 #endif
 
-#if (B2_ALG == 1 || B2_ALG == 2) && !B2_X2 && !B2_SPLIT
+#if (B2_ALG == 1 || B2_ALG == 2) && !B2_SPLIT
 // the common explicit case (adaptive, saveat interpolated, caller-supplied dt) folded at compile time
 extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble_kernel_adaptive(const __grid_constant__ B2Args a) {
 #if B2_ALG == 1
@@ -73,8 +71,6 @@ extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble
     b2_ode_driver_split<B2Tsit5>(a);
 #elif B2_ALG == 2 && B2_SPLIT
     b2_ode_driver_split<B2Vern7>(a);
-#elif B2_ALG == 1 && B2_X2
-    b2_ode_driver_x2<B2Tsit5>(a);
 #elif B2_ALG == 1
     b2_ode_driver<B2Tsit5>(a);
 #elif B2_ALG == 2

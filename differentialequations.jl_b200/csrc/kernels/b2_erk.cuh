@@ -49,6 +49,24 @@
 #define B2_KBAR
 #endif
 
+// ---- chunked loops over the components a thread holds: a chunk is a component PAIR (FFMA2/FMUL2, B2_PACK2) with a
+// scalar tail for odd n, or one scalar everywhere else.  V = chunk type, i = first component of the chunk.
+#if B2_PACK2
+#define B2_CHUNKS(BODY)                                                                       \
+    _Pragma("unroll") for (int i = 0; i + 1 < B2_NV; i += 2) { typedef b2p V; BODY }           \
+    if (B2_NV & 1) { constexpr int i = B2_NV - 1; typedef float V; BODY }
+#define KL(name) b2_ld<V>(name, i)
+#define UL(name) b2_ld<V>(name, i)
+#define CB(x) b2_bc<V>(x)
+#define VST(name, val) b2_st(name, i, val)
+#else
+#define B2_CHUNKS(BODY) _Pragma("unroll") for (int i = 0; i < B2_NV; i++) { typedef real V; BODY B2_KBAR; }
+#define KL(name) KV(name, i)
+#define UL(name) name[i]
+#define CB(x) (x)
+#define VST(name, val) name[i] = (val)
+#endif
+
 #define TS(x) ((real)(B2T_TSIT5_##x))
 
 struct B2Tsit5 {
@@ -73,92 +91,52 @@ struct B2Tsit5 {
         for (int i = 0; i < B2_NV; i++) k1[i] = f[i];
     }
 #endif
-#if B2_X2
-    static constexpr int NF_ATTEMPT = 6;
-    // packed mode: (re)start only the halves in (m0, m1); the other half keeps its k1
-    __device__ __forceinline__ void start_masked(const real (&u)[B2_NV], const real (&p)[B2_NPA], real t, bool m0, bool m1) {
-        real f[B2_NV];
-        b2_rhs(f, u, p, t);
-#pragma unroll
-        for (int i = 0; i < B2_NV; i++) k1[i] = b2_blend(m0, m1, f[i], k1[i]);
-    }
-    // FSAL hand-over only for the halves whose step was accepted
-    __device__ __forceinline__ void advance_masked(bool m0, bool m1) {
-#pragma unroll
-        for (int i = 0; i < B2_NV; i++) k1[i] = b2_blend(m0, m1, k7[i], k1[i]);
-    }
-#endif
     // one step attempt from (up, t) with k1 = f(up, t); writes the proposal u and dt*error estimate
     __device__ __forceinline__ void step(const real (&up)[B2_NV], const real (&p)[B2_NPA], real t, real dt,
                                          real (&u)[B2_NV], real (&ut)[B2_NV], bool adaptive, int& nf) {
         real tmp[B2_NV];
-#pragma unroll
-        for (int i = 0; i < B2_NV; i++) tmp[i] = b2_fma(dt, TS(a21) * KV(k1, i), up[i]);
+        B2_CHUNKS(VST(tmp, b2_fma(CB(dt), CB(TS(a21)) * KL(k1), UL(up)));)
         B2_RHS_TO(k2, tmp, t + TS(c2) * dt);
-#pragma unroll
-        for (int i = 0; i < B2_NV; i++) {
-            real s = TS(a31) * KV(k1, i);
-            s = b2_fma(TS(a32), KV(k2, i), s);
-            tmp[i] = b2_fma(dt, s, up[i]);
-            B2_KBAR;
-        }
+        B2_CHUNKS(V s = CB(TS(a31)) * KL(k1);
+                  s = b2_fma(CB(TS(a32)), KL(k2), s);
+                  VST(tmp, b2_fma(CB(dt), s, UL(up)));)
         B2_RHS_TO(k3, tmp, t + TS(c3) * dt);
-#pragma unroll
-        for (int i = 0; i < B2_NV; i++) {
-            real s = TS(a41) * KV(k1, i);
-            s = b2_fma(TS(a42), KV(k2, i), s);
-            s = b2_fma(TS(a43), KV(k3, i), s);
-            tmp[i] = b2_fma(dt, s, up[i]);
-            B2_KBAR;
-        }
+        B2_CHUNKS(V s = CB(TS(a41)) * KL(k1);
+                  s = b2_fma(CB(TS(a42)), KL(k2), s);
+                  s = b2_fma(CB(TS(a43)), KL(k3), s);
+                  VST(tmp, b2_fma(CB(dt), s, UL(up)));)
         B2_RHS_TO(k4, tmp, t + TS(c4) * dt);
-#pragma unroll
-        for (int i = 0; i < B2_NV; i++) {
-            real s = TS(a51) * KV(k1, i);
-            s = b2_fma(TS(a52), KV(k2, i), s);
-            s = b2_fma(TS(a53), KV(k3, i), s);
-            s = b2_fma(TS(a54), KV(k4, i), s);
-            tmp[i] = b2_fma(dt, s, up[i]);
-            B2_KBAR;
-        }
+        B2_CHUNKS(V s = CB(TS(a51)) * KL(k1);
+                  s = b2_fma(CB(TS(a52)), KL(k2), s);
+                  s = b2_fma(CB(TS(a53)), KL(k3), s);
+                  s = b2_fma(CB(TS(a54)), KL(k4), s);
+                  VST(tmp, b2_fma(CB(dt), s, UL(up)));)
         B2_RHS_TO(k5, tmp, t + TS(c5) * dt);
-#pragma unroll
-        for (int i = 0; i < B2_NV; i++) {
-            real s = TS(a61) * KV(k1, i);
-            s = b2_fma(TS(a62), KV(k2, i), s);
-            s = b2_fma(TS(a63), KV(k3, i), s);
-            s = b2_fma(TS(a64), KV(k4, i), s);
-            s = b2_fma(TS(a65), KV(k5, i), s);
-            tmp[i] = b2_fma(dt, s, up[i]);
-            B2_KBAR;
-        }
+        B2_CHUNKS(V s = CB(TS(a61)) * KL(k1);
+                  s = b2_fma(CB(TS(a62)), KL(k2), s);
+                  s = b2_fma(CB(TS(a63)), KL(k3), s);
+                  s = b2_fma(CB(TS(a64)), KL(k4), s);
+                  s = b2_fma(CB(TS(a65)), KL(k5), s);
+                  VST(tmp, b2_fma(CB(dt), s, UL(up)));)
         B2_RHS_TO(k6, tmp, t + dt);
-#pragma unroll
-        for (int i = 0; i < B2_NV; i++) {
-            real s = TS(a71) * KV(k1, i);
-            s = b2_fma(TS(a72), KV(k2, i), s);
-            s = b2_fma(TS(a73), KV(k3, i), s);
-            s = b2_fma(TS(a74), KV(k4, i), s);
-            s = b2_fma(TS(a75), KV(k5, i), s);
-            s = b2_fma(TS(a76), KV(k6, i), s);
-            u[i] = b2_fma(dt, s, up[i]);
-            B2_KBAR;
-        }
+        B2_CHUNKS(V s = CB(TS(a71)) * KL(k1);
+                  s = b2_fma(CB(TS(a72)), KL(k2), s);
+                  s = b2_fma(CB(TS(a73)), KL(k3), s);
+                  s = b2_fma(CB(TS(a74)), KL(k4), s);
+                  s = b2_fma(CB(TS(a75)), KL(k5), s);
+                  s = b2_fma(CB(TS(a76)), KL(k6), s);
+                  VST(u, b2_fma(CB(dt), s, UL(up)));)
         B2_RHS_TO(k7, u, t + dt);
         nf += 6;
         if (adaptive) {
-#pragma unroll
-            for (int i = 0; i < B2_NV; i++) {
-                real s = TS(btilde1) * KV(k1, i);
-                s = b2_fma(TS(btilde2), KV(k2, i), s);
-                s = b2_fma(TS(btilde3), KV(k3, i), s);
-                s = b2_fma(TS(btilde4), KV(k4, i), s);
-                s = b2_fma(TS(btilde5), KV(k5, i), s);
-                s = b2_fma(TS(btilde6), KV(k6, i), s);
-                s = b2_fma(TS(btilde7), KV(k7, i), s);
-                ut[i] = dt * s;
-                B2_KBAR;
-            }
+            B2_CHUNKS(V s = CB(TS(btilde1)) * KL(k1);
+                      s = b2_fma(CB(TS(btilde2)), KL(k2), s);
+                      s = b2_fma(CB(TS(btilde3)), KL(k3), s);
+                      s = b2_fma(CB(TS(btilde4)), KL(k4), s);
+                      s = b2_fma(CB(TS(btilde5)), KL(k5), s);
+                      s = b2_fma(CB(TS(btilde6)), KL(k6), s);
+                      s = b2_fma(CB(TS(btilde7)), KL(k7), s);
+                      VST(ut, CB(dt) * s);)
         }
     }
     // called once per accepted step before interpolation / FSAL hand-over (no-op here)
@@ -171,18 +149,14 @@ struct B2Tsit5 {
         const real b1 = TSB(1, B2T_TSIT5_r11), b2 = TSB(2, 0.0), b3 = TSB(3, 0.0), b4 = TSB(4, 0.0),
                    b5 = TSB(5, 0.0), b6 = TSB(6, 0.0), b7 = TSB(7, 0.0);
 #undef TSB
-#pragma unroll
-        for (int i = 0; i < B2_NV; i++) {
-            real s = b1 * KV(k1, i);
-            s = b2_fma(b2, KV(k2, i), s);
-            s = b2_fma(b3, KV(k3, i), s);
-            s = b2_fma(b4, KV(k4, i), s);
-            s = b2_fma(b5, KV(k5, i), s);
-            s = b2_fma(b6, KV(k6, i), s);
-            s = b2_fma(b7, KV(k7, i), s);
-            out[i] = b2_fma(dt, s, up[i]);
-            B2_KBAR;
-        }
+        B2_CHUNKS(V s = CB(b1) * KL(k1);
+                  s = b2_fma(CB(b2), KL(k2), s);
+                  s = b2_fma(CB(b3), KL(k3), s);
+                  s = b2_fma(CB(b4), KL(k4), s);
+                  s = b2_fma(CB(b5), KL(k5), s);
+                  s = b2_fma(CB(b6), KL(k6), s);
+                  s = b2_fma(CB(b7), KL(k7), s);
+                  VST(out, b2_fma(CB(dt), s, UL(up)));)
     }
     // Coefficient form of the interpolant for ONE component (used by the event search, which evaluates the dense
     // output many times per step): u_i(t + th*dt) = up_i + dt * th*(C1 + th*(C2 + th*(C3 + th*C4))), C_j = sum_s r_sj k_s[i]

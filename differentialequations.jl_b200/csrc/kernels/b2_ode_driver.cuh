@@ -13,6 +13,7 @@
 // trajectories (0.54 warp efficiency without refill).
 #pragma once
 #include "b2_common.cuh"
+#include "b2_control.cuh"
 
 // ADAPT / TSTOPS: 0 or 1 = compile-time specialisation of the two solve options that sit in the per-iteration
 // control path, -1 = read them from the argument block.  AUTODT = 0 compiles the automatic-initial-step block out
@@ -33,13 +34,10 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     const int out_per_traj = n_save * B2_N;
 
     const real t0 = B2_ARG(a, t0), t1 = B2_ARG(a, t1), dt_user = B2_ARG(a, dt);
-    const real qmax = B2_ARG(a, qmax), qmin = B2_ARG(a, qmin), gam = B2_ARG(a, gamma);
-    const float inv_qmax = __fdiv_rn(1.0f, (float)qmax), inv_qmin = __fdiv_rn(1.0f, (float)qmin);
-    const float inv_gam = __fdiv_rn(1.0f, (float)gam);
+    const B2Ctl ctl = b2_ctl_init(a);   // the PI controller works in Float32 (b2_control.cuh)
+    const float lqinit = ctl.lqinit;
     const float inv_n = __fdiv_rn(1.0f, (float)B2_N);
-    const real qoldinit = B2_ARG(a, qoldinit), dtmax = B2_ARG(a, dtmax), dtmin = B2_ARG(a, dtmin);
-    const float beta1 = a.f_beta1, beta2 = a.f_beta2;
-    const float lqinit = b2_fastlog2((float)qoldinit);
+    const real dtmax = B2_ARG(a, dtmax), dtmin = B2_ARG(a, dtmin);
     constexpr bool EVERY = ADAPT < 0;   // save_everystep exists in the generic entry only (specialised entries: saveat)
     const bool adaptive = ADAPT < 0 ? (a.adaptive != 0) : (ADAPT != 0);
     const bool save_tstops = TSTOPS < 0 ? (a.save_tstops != 0) : (TSTOPS != 0);
@@ -194,13 +192,16 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                     if (adaptive) {
                         // error norm (A.4): scale in the working precision, ratio / square / sum in Float32 (EEst only
                         // steers the step size; keeps Float64 kernels free of IEEE double divisions).  Accept iff
-                        // EEst^2 <= 1.  PI controller (A.5) in the log domain: l = log2(EEst), lq = log2(qold),
-                        // q = 2^(beta1*l - beta2*lq) / gamma -> one log2 + one exp2 per step.
+                        // EEst^2 <= 1.  The division is the Newton reciprocal b2_rcp_nr (6.6e-6 accurate).
                         float acc = 0.0f;
 #pragma unroll
                         for (int i = 0; i < B2_N; i++) {
                             const real sk = b2_fma(b2_max(b2_abs(u[i]), b2_abs(un[i])), B2_RTOL(a, i), B2_ATOL(a, i));
+#ifdef B2_NORM_DIV   // experiments only (B200ENS_DEFINES): the IEEE division the Newton reciprocal replaced; NOT the oracle's bits
                             const float r = __fdiv_rn((float)ut[i], (float)sk);
+#else
+                            const float r = __fmul_rn((float)ut[i], b2_rcp_nr((float)sk));
+#endif
                             acc = __fmaf_rn(r, r, acc);
                         }
 #if B2_F64
@@ -219,26 +220,14 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                         }
 #endif
                         const float EE2 = __fmul_rn(acc, inv_n);
-                        // Branch-free accept/reject: rejections are rare per lane (3 %) but some lane of the warp
-                        // rejects in 37 % of the iterations, so a separate reject path costs every warp ~36 extra
-                        // instructions at 2/32 lane efficiency (profiles/).  Both cases are dt * (1/q) with
-                        //   accept: q = clamp(2^(beta1*l - beta2*lq) / gamma, 1/qmax, 1/qmin)
-                        //   reject: q = min(2^(beta1*l) / gamma, 1/qmin)
-                        // so only the exponent argument and the lower clamp are selected.  Same values as before.
-                        const bool isn = EE2 != EE2;   // upstream: NaN EEst -> NaN dt -> ReturnCode.DtNaN
-                        const bool ok = EE2 <= 1.0f;
-                        const bool zero = EE2 == 0.0f;
-                        const float l = __fmul_rn(0.5f, b2_fastlog2(EE2));
-                        const float bl = __fmul_rn(beta1, l);
-                        float q = b2_fastexp2(ok ? __fmaf_rn(-beta2, lq, bl) : bl);
-                        q = fminf(inv_qmin, __fmul_rn(q, inv_gam));
-                        q = ok ? fmaxf(inv_qmax, q) : q;
-                        q = zero ? inv_qmax : q;
-                        const real dtq = dt * (real)__fdiv_rn(1.0f, q);
+                        // PI controller (A.5), log domain, branch-free accept/reject (b2_control.cuh)
+                        const B2Decision d = b2_pi_controller(EE2, lq, ctl);
+                        const real dtq = dt * (real)d.qi;
+                        const bool ok = d.ok, isn = d.isn;
                         accepted = ok;
                         if (isn) rc = B2_RC_DTNAN;
                         nreject += (!ok && !isn) ? 1 : 0;
-                        lq = ok ? fmaxf(zero ? lqinit : l, lqinit) : lq;
+                        lq = ok ? b2_ctl_lq_next(d, ctl) : lq;
                         dtnew = ok ? dtq : dtnew;
                         dt = (!ok && !isn) ? dtq : dt;
                     } else {
@@ -260,7 +249,6 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                         // ---------------- ContinuousCallback (A.8): sign change over interp_points samples
                         // of the dense output, then bisection on theta keeping the LEFT side of the root
                         real w[B2_N];
-                        real gprev, lo = 0, hi = 0, glo, ghi = 0;
                         alg.prepare_dense(u, p, tprev, dts, nf);
                         // The event search evaluates the dense output 10-25 times per step.  For the ERK steppers it
                         // uses the coefficient form of the interpolant, built once per step and only for the
@@ -291,155 +279,26 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                             }
                         };
 #ifdef B2_NCOND
-                        // ---- VectorContinuousCallback (qa.jl:124): B2_NCOND event functions; the first sub-interval in
-                        // which ANY of them changes sign is searched, each changed function gets its own ITP root-find
-                        // on that bracket, the earliest root fires and its index goes to affect!(integrator, idx).
-                        real gp_[B2_NCOND], gl_[B2_NCOND], gh_[B2_NCOND], gv_[B2_NCOND], lo_[B2_NCOND];
-                        unsigned chg = 0;
-                        b2_vcondition(gp_, u, p, tprev);
-#pragma unroll
-                        for (int k = 0; k < B2_NCOND; k++) lo_[k] = 0;
-                        if (just_fired) {
-                            // only the function that fired the previous event takes its "previous sign" just after
-                            // the step start (it sits on its root); the others keep their sign at the step start, so a
-                            // crossing right after the event (a corner) is not lost
-                            fill_w((real)0.01);
-                            b2_vcondition(gv_, w, p, b2_fma((real)0.01, dts, tprev));
-#pragma unroll
-                            for (int k = 0; k < B2_NCOND; k++)
-                                if (k == ev_last) {
-                                    gp_[k] = gv_[k];
-                                    lo_[k] = (real)0.01;
-                                }
-                        }
-#pragma unroll
-                        for (int k = 0; k < B2_NCOND; k++) gl_[k] = gp_[k];
-                        for (int mm = 1; mm <= ip && !fired; mm++) {
-                            const real th = (mm == ip) ? (real)1 : (real)mm / (real)ip;
-                            if (mm == ip) {
-                                b2_vcondition(gv_, un, p, tnew);
-                            } else {
+                        // ---- VectorContinuousCallback (qa.jl:124), search shared with the split kernel (b2_control.cuh)
+                        fired = b2_vevent_search(
+                            ip, just_fired, ev_last, [&](real* g) { b2_vcondition(g, u, p, tprev); },
+                            [&](real th, real* g) {
                                 fill_w(th);
-                                b2_vcondition(gv_, w, p, b2_fma(th, dts, tprev));
-                            }
-                            chg = 0;
-#pragma unroll
-                            for (int k = 0; k < B2_NCOND; k++)
-                                if ((gp_[k] < 0 && gv_[k] >= 0) || (gp_[k] > 0 && gv_[k] <= 0)) chg |= 1u << k;
-                            if (chg) {
-                                fired = true;
-                                hi = th;
-#pragma unroll
-                                for (int k = 0; k < B2_NCOND; k++) gh_[k] = gv_[k];
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < B2_NCOND; k++) {
-                                    gl_[k] = gv_[k];
-                                    lo_[k] = th;
-                                }
-                            }
-                        }
-                        if (fired) {
-                            real best = (real)2;
-                            int bidx = 0;
-#pragma unroll
-                            for (int k = 0; k < B2_NCOND; k++) {
-                                if ((chg >> k) & 1u) {
-                                    real lo_k = lo_[k], hi_k = hi, glo_k = gl_[k], ghi_k = gh_[k];
-                                    const real gprev_k = gp_[k];
-                                    const real eps = (real)2 * (real)B2_EPS;
-                                    const real k1 = (real)0.2 / (hi_k - lo_k);
-                                    real pw = b2_itp_pw(hi_k - lo_k);
-                                    for (int it = 0; it < 100 && hi_k - lo_k > (real)2 * eps; it++) {
-                                        const real xh = (real)0.5 * (lo_k + hi_k);
-                                        const real r = pw - (real)0.5 * (hi_k - lo_k);
-                                        pw *= (real)0.5;
-                                        const real delta = k1 * (hi_k - lo_k) * (hi_k - lo_k);
-                                        const real xf = (ghi_k * lo_k - glo_k * hi_k) / (ghi_k - glo_k);
-                                        const real sg = (xh - xf) >= 0 ? (real)1 : (real)-1;
-                                        const real xt = (delta <= b2_abs(xh - xf)) ? xf + sg * delta : xh;
-                                        real x = (b2_abs(xt - xh) <= r) ? xt : xh - sg * r;
-                                        if (!(x > lo_k && x < hi_k)) x = xh;
-                                        if (!(x > lo_k && x < hi_k)) break;
-                                        real gx_[B2_NCOND];
-                                        fill_w(x);
-                                        b2_vcondition(gx_, w, p, b2_fma(x, dts, tprev));
-                                        const real g = gx_[k];
-                                        if ((gprev_k < 0 && g >= 0) || (gprev_k > 0 && g <= 0)) {
-                                            hi_k = x;
-                                            ghi_k = g;
-                                        } else {
-                                            lo_k = x;
-                                            glo_k = g;
-                                        }
-                                    }
-                                    if (lo_k < best) {   // earliest event wins; the lower index on ties
-                                        best = lo_k;
-                                        bidx = k;
-                                    }
-                                }
-                            }
-                            th_end = best;
-                            ev_idx = bidx;
-                            ev_last = bidx;
-                            tnew = b2_fma(th_end, dts, tprev);
-                        }
-                        (void)gprev; (void)glo; (void)ghi; (void)lo;
+                                b2_vcondition(g, w, p, b2_fma(th, dts, tprev));
+                            },
+                            [&](real* g) { b2_vcondition(g, un, p, tnew); }, th_end, ev_idx);
 #else
-                        auto cond_at = [&](real th) -> real {
-                            fill_w(th);
-                            return b2_condition(w, p, b2_fma(th, dts, tprev));
-                        };
-                        if (just_fired) {
-                            gprev = cond_at((real)0.01);
-                            lo = (real)0.01;
-                        } else {
-                            gprev = b2_condition(u, p, tprev);
-                        }
-                        glo = gprev;
-                        for (int mm = 1; mm <= ip && !fired; mm++) {
-                            const real th = (mm == ip) ? (real)1 : (real)mm / (real)ip;
-                            const real g = (mm == ip) ? b2_condition(un, p, tnew) : cond_at(th);
-                            if ((gprev < 0 && g >= 0) || (gprev > 0 && g <= 0)) {
-                                fired = true;
-                                hi = th;
-                                ghi = g;
-                            } else {
-                                lo = th;
-                                glo = g;
-                            }
-                        }
-                        if (fired) {
-                            // ITP bracketing root-find on theta (k1 = 0.2/(b-a), k2 = 2, n0 = 1): worst case
-                            // bisection+1 evaluations, typically ~8 (plain bisection to 1 ulp was 42% of all
-                            // issued instructions of config 5, profiles/r1_net16_*).  Keeps the LEFT end.
-                            const real eps = (real)2 * (real)B2_EPS;
-                            const real k1 = (real)0.2 / (hi - lo);
-                            real pw = b2_itp_pw(hi - lo);   // eps * 2^(halvings + 1), closed form
-                            for (int it = 0; it < 100 && hi - lo > (real)2 * eps; it++) {
-                                const real xh = (real)0.5 * (lo + hi);
-                                const real r = pw - (real)0.5 * (hi - lo);
-                                pw *= (real)0.5;
-                                const real delta = k1 * (hi - lo) * (hi - lo);
-                                const real xf = (ghi * lo - glo * hi) / (ghi - glo);
-                                const real sg = (xh - xf) >= 0 ? (real)1 : (real)-1;
-                                const real xt = (delta <= b2_abs(xh - xf)) ? xf + sg * delta : xh;
-                                real x = (b2_abs(xt - xh) <= r) ? xt : xh - sg * r;
-                                if (!(x > lo && x < hi)) x = xh;
-                                if (!(x > lo && x < hi)) break;
-                                const real g = cond_at(x);
-                                if ((gprev < 0 && g >= 0) || (gprev > 0 && g <= 0)) {
-                                    hi = x;
-                                    ghi = g;
-                                } else {
-                                    lo = x;
-                                    glo = g;
-                                }
-                            }
-                            th_end = lo;
-                            tnew = b2_fma(th_end, dts, tprev);
-                        }
+                        // ---- scalar ContinuousCallback: sign change over interp_points samples, ITP root-find keeping the
+                        // LEFT side of the root (b2_control.cuh)
+                        fired = b2_event_search(
+                            ip, just_fired, [&]() -> real { return b2_condition(u, p, tprev); },
+                            [&](real th) -> real {
+                                fill_w(th);
+                                return b2_condition(w, p, b2_fma(th, dts, tprev));
+                            },
+                            [&]() -> real { return b2_condition(un, p, tnew); }, th_end);
 #endif   // B2_NCOND
+                        if (fired) tnew = b2_fma(th_end, dts, tprev);
 #endif
                     }
                 }

@@ -14,6 +14,7 @@
 // one-thread kernel for these): DiscreteCallback, VectorContinuousCallback, save_everystep, output staging.
 #pragma once
 #include "b2_common.cuh"
+#include "b2_control.cuh"
 #include "b2_split.cuh"
 
 // owned block of a full-length register array, by warp role (compile-time indices in every case: no local memory)
@@ -49,13 +50,10 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     const long long out_per_traj = (long long)n_save * B2_N;
 
     const real t0 = B2_ARG(a, t0), t1 = B2_ARG(a, t1), dt_user = B2_ARG(a, dt);
-    const real qmax = B2_ARG(a, qmax), qmin = B2_ARG(a, qmin), gam = B2_ARG(a, gamma);
-    const float inv_qmax = __fdiv_rn(1.0f, (float)qmax), inv_qmin = __fdiv_rn(1.0f, (float)qmin);
-    const float inv_gam = __fdiv_rn(1.0f, (float)gam);
+    const B2Ctl ctl = b2_ctl_init(a);   // the PI controller works in Float32 (b2_control.cuh)
+    const float lqinit = ctl.lqinit;
     const float inv_n = __fdiv_rn(1.0f, (float)B2_N);
-    const real qoldinit = B2_ARG(a, qoldinit), dtmax = B2_ARG(a, dtmax), dtmin = B2_ARG(a, dtmin);
-    const float beta1 = a.f_beta1, beta2 = a.f_beta2;
-    const float lqinit = b2_fastlog2((float)qoldinit);
+    const real dtmax = B2_ARG(a, dtmax), dtmin = B2_ARG(a, dtmin);
     const bool adaptive = ADAPT < 0 ? (a.adaptive != 0) : (ADAPT != 0);
     const bool save_tstops = TSTOPS < 0 ? (a.save_tstops != 0) : (TSTOPS != 0);
     const real INF = (real)__int_as_float(0x7f800000);
@@ -93,7 +91,9 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
 #if B2_HAS_EVENT
     __shared__ __align__(16) real s_ev[B2_EV_M * (Alg::DEG + 2) * 32];
     __shared__ real s_evres[32];
+    __shared__ int s_evidx[32];
     bool just_fired = false;
+    int ev_last = 0;   // VectorContinuousCallback: index of the function that fired the last event
     const int ip = a.interp_points;
 #endif
 
@@ -210,6 +210,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
         real un[B2_NL], ut[B2_NL];
 #if B2_HAS_EVENT
         real th_end = 1;
+        int ev_idx = 0;   // which event function fired (VectorContinuousCallback)
 #endif
         bool do_step = false;
         real tstop = t1;
@@ -238,7 +239,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
 #pragma unroll
             for (int j = 0; j < B2_NL; j++) {
                 const real sk = b2_fma(b2_max(b2_abs(u[j]), b2_abs(un[j])), rtol[j], atol[j]);
-                r[j] = __fdiv_rn((float)ut[j], (float)sk);
+                r[j] = __fmul_rn((float)ut[j], b2_rcp_nr((float)sk));
             }
             const float* rb = b2_split_publish(alg.xc, r);
             float acc = 0.0f;
@@ -268,21 +269,14 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
             }
 #endif
             const float EE2 = __fmul_rn(acc, inv_n);
-            const bool isn = EE2 != EE2;
-            const bool ok = EE2 <= 1.0f;
-            const bool zero = EE2 == 0.0f;
-            const float l = __fmul_rn(0.5f, b2_fastlog2(EE2));
-            const float bl = __fmul_rn(beta1, l);
-            float q = b2_fastexp2(ok ? __fmaf_rn(-beta2, lq, bl) : bl);
-            q = fminf(inv_qmin, __fmul_rn(q, inv_gam));
-            q = ok ? fmaxf(inv_qmax, q) : q;
-            q = zero ? inv_qmax : q;
-            const real dtq = dt * (real)__fdiv_rn(1.0f, q);
+            const B2Decision d = b2_pi_controller(EE2, lq, ctl);   // shared with the one-thread driver
+            const real dtq = dt * (real)d.qi;
+            const bool ok = d.ok, isn = d.isn;
             if (do_step) {
                 accepted = ok;
                 if (isn) rc = B2_RC_DTNAN;
                 nreject += (!ok && !isn) ? 1 : 0;
-                lq = ok ? fmaxf(zero ? lqinit : l, lqinit) : lq;
+                lq = ok ? b2_ctl_lq_next(d, ctl) : lq;
                 dtnew = ok ? dtq : dtnew;
                 dt = (!ok && !isn) ? dtq : dt;
             }
@@ -371,6 +365,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                     }
                 }
             };
+#ifndef B2_NCOND
             auto cond_at = [&](real th) -> real {
                 real v[B2_EV_M];
 #pragma unroll
@@ -383,65 +378,53 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                 scatter(v);
                 return b2_condition(w, p, b2_fma(th, dts, tprev));
             };
+#endif
             // The search is sequential per lane and only ~1 lane in 10 fires on a given step: it would cost every warp the
             // full ~20 root-find iterations at 3/32 lane efficiency (ncu: 27 % of all issued instructions when
             // replicated).  Warp 0 searches alone and publishes theta of the event (or -1) for the other three.
             if (g == 0 && accepted) {
-                real gprev, lo = 0, hi = 0, glo, ghi = 0;
-                if (just_fired) {
-                    gprev = cond_at((real)0.01);
-                    lo = (real)0.01;
-                } else {
-                    scatter(eu);
-                    gprev = b2_condition(w, p, tprev);
-                }
-                glo = gprev;
-                for (int mm = 1; mm <= ip && !fired; mm++) {
-                    const real th = (mm == ip) ? (real)1 : (real)mm / (real)ip;
-                    real gv;
-                    if (mm == ip) {
+#ifdef B2_NCOND
+                // VectorContinuousCallback (qa.jl:124): the search of b2_control.cuh, shared with the one-thread driver
+                auto vcond_at = [&](real th, real* gv) {
+                    real v[B2_EV_M];
+#pragma unroll
+                    for (int m = 0; m < B2_EV_M; m++) {
+                        real pv = ecc[m][PD - 1];
+#pragma unroll
+                        for (int j = PD - 2; j >= 0; j--) pv = b2_fma(th, pv, ecc[m][j]);
+                        v[m] = b2_fma(dts, th * pv, eu[m]);
+                    }
+                    scatter(v);
+                    b2_vcondition(gv, w, p, b2_fma(th, dts, tprev));
+                };
+                fired = b2_vevent_search(
+                    ip, just_fired, ev_last,
+                    [&](real* gv) {
+                        scatter(eu);
+                        b2_vcondition(gv, w, p, tprev);
+                    },
+                    vcond_at,
+                    [&](real* gv) {
                         scatter(eun);
-                        gv = b2_condition(w, p, tnew);
-                    } else {
-                        gv = cond_at(th);
-                    }
-                    if ((gprev < 0 && gv >= 0) || (gprev > 0 && gv <= 0)) {
-                        fired = true;
-                        hi = th;
-                        ghi = gv;
-                    } else {
-                        lo = th;
-                        glo = gv;
-                    }
-                }
-                if (fired) {
-                    // ITP bracketing root-find on theta, LEFT end kept (same sequence as b2_ode_driver.cuh / the oracle)
-                    const real eps = (real)2 * (real)B2_EPS;
-                    const real k1 = (real)0.2 / (hi - lo);
-                    real pw = b2_itp_pw(hi - lo);   // eps * 2^(halvings + 1), closed form
-                    for (int it = 0; it < 100 && hi - lo > (real)2 * eps; it++) {
-                        const real xh = (real)0.5 * (lo + hi);
-                        const real rr = pw - (real)0.5 * (hi - lo);
-                        pw *= (real)0.5;
-                        const real delta = k1 * (hi - lo) * (hi - lo);
-                        const real xf = (ghi * lo - glo * hi) / (ghi - glo);
-                        const real sg = (xh - xf) >= 0 ? (real)1 : (real)-1;
-                        const real xt = (delta <= b2_abs(xh - xf)) ? xf + sg * delta : xh;
-                        real x = (b2_abs(xt - xh) <= rr) ? xt : xh - sg * rr;
-                        if (!(x > lo && x < hi)) x = xh;
-                        if (!(x > lo && x < hi)) break;
-                        const real gv = cond_at(x);
-                        if ((gprev < 0 && gv >= 0) || (gprev > 0 && gv <= 0)) {
-                            hi = x;
-                            ghi = gv;
-                        } else {
-                            lo = x;
-                            glo = gv;
-                        }
-                    }
-                    th_end = lo;
-                }
+                        b2_vcondition(gv, w, p, tnew);
+                    },
+                    th_end, ev_idx);
+#else
+                fired = b2_event_search(
+                    ip, just_fired,
+                    [&]() -> real {
+                        scatter(eu);
+                        return b2_condition(w, p, tprev);
+                    },
+                    cond_at,
+                    [&]() -> real {
+                        scatter(eun);
+                        return b2_condition(w, p, tnew);
+                    },
+                    th_end);
+#endif
             }
+            if (g == 0) s_evidx[lane] = ev_idx;
             if (g == 0) s_evres[lane] = fired ? th_end : (real)-1;
             __syncthreads();
             {
@@ -449,6 +432,8 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                 fired = accepted && th_pub >= (real)0;
                 if (fired) {
                     th_end = th_pub;
+                    ev_idx = s_evidx[lane];
+                    ev_last = ev_idx;
                     tnew = b2_fma(th_end, dts, tprev);
                 }
             }
@@ -492,7 +477,11 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
             real W[B2_N];
 #pragma unroll
             for (int i = 0; i < B2_N; i++) W[i] = fb[i * 32];
+#ifdef B2_NCOND
+            b2_vaffect(W, p, tnew, ev_idx);   // per lane: the index of the function that fired
+#else
             b2_affect(W, p, tnew);
+#endif
             real wn[B2_NL], fnew[B2_NL];
             B2_OWNED(wn, W, g)
             alg.rhs(fnew, wn, p, tnew);
@@ -504,6 +493,9 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                 nf++;
                 just_fired = true;
                 if (a.event_terminate & 1) rc = B2_RC_TERMINATED;
+#ifdef B2_NCOND
+                if ((B2_VTERM_MASK >> ev_idx) & 1u) rc = B2_RC_TERMINATED;   // this index's affect! called terminate!
+#endif
             }
         }
 #endif

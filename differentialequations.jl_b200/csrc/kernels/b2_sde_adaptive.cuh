@@ -7,6 +7,7 @@
 // adaptive loop lives in StochasticDiffEq, outside the dep closure.
 #pragma once
 #include "b2_sde.cuh"
+#include "b2_control.cuh"
 
 #ifndef B2_RSWM_DEPTH
 #define B2_RSWM_DEPTH 48   // remembered pieces per trajectory (one per consecutive rejection); overflow -> Failure
@@ -30,9 +31,8 @@ __device__ __forceinline__ void b2_sde_adaptive_driver(const B2Args& a) {
     const real t0 = B2_ARG(a, t0), t1 = B2_ARG(a, t1), dt_user = B2_ARG(a, dt);
     const real dtmax = B2_ARG(a, dtmax), dtmin = B2_ARG(a, dtmin);
     const real delta = ALG == 9 ? (real)(1.0 / 6.0) : (real)1;
-    const float beta1 = a.f_beta1, beta2 = a.f_beta2;
-    const float inv_qmax = 1.0f / a.f_qmax, inv_qmin = 1.0f / a.f_qmin, inv_gam = 1.0f / a.f_gamma;
-    const float lqinit = b2_fastlog2(a.f_qoldinit);
+    const B2Ctl ctl = b2_ctl_init(a);   // the PI controller of the ODE drivers (b2_control.cuh), strong order 3/2 exponents
+    const float lqinit = ctl.lqinit;
 
     B2Sink sink;
     sink.stage = stride ? warp_stage + (size_t)lane * stride : nullptr;
@@ -49,7 +49,7 @@ __device__ __forceinline__ void b2_sde_adaptive_driver(const B2Args& a) {
             for (int i = 0; i < B2_N; i++) u[i] = gu0[idx * B2_N + i];
 #pragma unroll
             for (int i = 0; i < B2_NPARAM; i++) p[i] = gp[idx * B2_NPARAM + i];
-            real t = t0, dt = dt_user, h = (real)0;
+            real t = t0, dt = dt_user, h = (real)0, hreq = (real)0;   // hreq: the step the controller asked for, before a remembered piece cut it
             float lq = lqinit;
             int si = 0, rc = 0, sp = 0, naccept = 0, nreject = 0;
             bool have = false;   // (h, dW, dZ) already hold the cut increments of a rejected step
@@ -65,9 +65,23 @@ __device__ __forceinline__ void b2_sde_adaptive_driver(const B2Args& a) {
             // the remembered pieces of the Brownian path beyond t (local memory: indexed dynamically)
             real sk_len[B2_RSWM_DEPTH], sk_W[B2_RSWM_DEPTH][B2_N], sk_Z[B2_RSWM_DEPTH][B2_N];
             real dW[B2_N], dZ[B2_N], z[2 * B2_N];
+            // noise_injected: the caller supplies the STANDARD NORMALS of every trajectory, [N][nsteps_noise], consumed in
+            // order in place of the Philox stream -- pathwise parity with the oracle including every accept / reject
+            const real* const zinj = a.noise_injected ? reinterpret_cast<const real*>(a.dW) + (size_t)idx * (size_t)a.nsteps_noise : nullptr;
+            long long zpos = 0;
+            bool starved = false;
             auto draw = [&]() {   // the next 2n normals of this trajectory's stream, in order
 #pragma unroll
                 for (int j = 0; j < 2 * B2_N; j++) {
+                    if (zinj) {
+                        if (zpos >= a.nsteps_noise) {
+                            starved = true;
+                            z[j] = (real)0;
+                        } else {
+                            z[j] = zinj[zpos++];
+                        }
+                        continue;
+                    }
                     if (zavail == 0) {
                         b2_normals(a.seed, traj, zblock, zbuf);
                         zblock++;
@@ -103,6 +117,7 @@ __device__ __forceinline__ void b2_sde_adaptive_driver(const B2Args& a) {
                         rc = B2_RC_DTLESSTHANMIN;
                         break;
                     }
+                    hreq = h;
                     if (sp == 0) {   // nothing remembered beyond t: fresh increments
                         draw();
                         const real sq = b2_sqrt(h);
@@ -133,6 +148,10 @@ __device__ __forceinline__ void b2_sde_adaptive_driver(const B2Args& a) {
                     }
                 }
                 have = false;
+                if (starved) {   // the injected stream of normals ran out
+                    rc = B2_RC_FAILURE_;
+                    break;
+                }
                 real up[B2_N], E1[B2_N], E2[B2_N];
 #pragma unroll
                 for (int i = 0; i < B2_N; i++) up[i] = u[i];
@@ -141,26 +160,18 @@ __device__ __forceinline__ void b2_sde_adaptive_driver(const B2Args& a) {
 #pragma unroll
                 for (int i = 0; i < B2_N; i++) {
                     const real sk = b2_fma(b2_max(b2_abs(up[i]), b2_abs(u[i])), B2_RTOL(a, i), B2_ATOL(a, i));
-                    const float r = (float)(b2_fma(delta, E1[i], E2[i]) / sk);
-                    acc = fmaf(r, r, acc);
+                    const float r = __fmul_rn((float)b2_fma(delta, E1[i], E2[i]), b2_rcp_nr((float)sk));
+                    acc = __fmaf_rn(r, r, acc);
                 }
-                const float EE2 = acc * (1.0f / (float)B2_N);
-                if (EE2 != EE2) {
+                const float EE2 = __fmul_rn(acc, __fdiv_rn(1.0f, (float)B2_N));
+                const B2Decision d = b2_pi_controller(EE2, lq, ctl);
+                if (d.isn) {
                     rc = B2_RC_DTNAN;
                     break;
                 }
-                float q, l = lqinit;
-                if (EE2 == 0.0f) {
-                    q = inv_qmax;
-                } else {
-                    l = 0.5f * b2_fastlog2(EE2);
-                    q = b2_fastexp2(fmaf(-beta2, lq, beta1 * l));
-                    q = fmaxf(inv_qmax, fminf(inv_qmin, q * inv_gam));
-                }
-                if (!(EE2 <= 1.0f)) {   // reject: keep the first part of the increments, remember the rest
+                if (!d.ok) {   // reject: keep the first part of the increments, remember the rest
                     nreject++;
-                    const float q11 = b2_fastexp2(beta1 * l);
-                    const real qr = (real)__fdiv_rn(1.0f, fminf(inv_qmin, q11 * inv_gam));   // h' / h in [qmin, gamma]
+                    const real qr = (real)d.qi;   // h' / h = max(qmin, gamma * EEst^-beta1), in [qmin, gamma]
                     if (sp >= B2_RSWM_DEPTH) {
                         rc = B2_RC_FAILURE_;
                         break;
@@ -179,15 +190,23 @@ __device__ __forceinline__ void b2_sde_adaptive_driver(const B2Args& a) {
                     sk_len[sp++] = h - hn;
                     h = hn;
                     dt = hn;
+                    hreq = hn;
                     have = true;
+                    if (starved) {
+                        rc = B2_RC_FAILURE_;
+                        break;
+                    }
                     if (hn <= b2_max(dtmin, (real)B2_EPS * b2_abs(t))) {
                         rc = B2_RC_DTLESSTHANMIN;
                         break;
                     }
                     continue;
                 }
-                lq = fmaxf(l, lqinit);
-                dt = h * (real)__fdiv_rn(1.0f, q);
+                lq = b2_ctl_lq_next(d, ctl);
+                dt = h * (real)d.qi;
+                // a step cut short to END ON a remembered time point does not shrink the proposal below what the controller
+                // had asked for (the leftover of a rejected step can be arbitrarily short; see the oracle)
+                if (h < hreq) dt = b2_max(dt, hreq);
                 naccept++;
                 const real tprev = t;
                 real tnew = t + h;

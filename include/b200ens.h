@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200ENS_ABI_VERSION 4
+#define B200ENS_ABI_VERSION 5
 
 /* scalar type of u, p, t (Julia eltype(u0)) */
 enum b200ens_dtype { B200ENS_F32 = 0, B200ENS_F64 = 1 };
@@ -52,11 +52,8 @@ enum b200ens_error {
 
 /* model flags */
 #define B200ENS_MODEL_FAST_MATH 1u /* let NVRTC contract a*b+c in MODEL code (breaks bitwise oracle parity) */
-#define B200ENS_MODEL_PACKED_X2 2u /* Float32 Tsit5 without callbacks: two trajectories per thread in packed FP32
-                                      (FFMA2/FADD2/FMUL2, sm_100+); bit-identical results under NVRTC 12.8 only (with any
-                                      other NVRTC the request falls through to the scalar kernel); measured 5% SLOWER
-                                      than the scalar kernel on B200 (profiles/README.md), hence opt-in */
-
+/* bit 2u: reserved (ABI <= 4: B200ENS_MODEL_PACKED_X2, the two-trajectories-per-thread kernel; removed -- the Float32
+   steppers now pack component PAIRS of one trajectory into FFMA2/FMUL2, which is faster and bit-identical) */
 #define B200ENS_MODEL_KSMEM 4u     /* force ERK stage vectors into shared memory (default: automatic when the register variant spills > 4 KB) */
 #define B200ENS_MODEL_SPLIT 8u     /* force the split kernel (one trajectory per lane of a 4-warp CTA, components split over the
                                       warps; Tsit5 / Vern7 with at most a scalar ContinuousCallback; default: automatic when
@@ -64,8 +61,8 @@ enum b200ens_error {
 #define B200ENS_MODEL_NOSPLIT 16u  /* never use the split kernel */
 #define B200ENS_MODEL_SDE_ADAPTIVE 32u /* SRIW1 / SOSRA only: compile the ADAPTIVE stepper (embedded error estimate, PI controller
                                       with the strong order 3/2, qmax default 1.125, rejection sampling with memory RSwM1).
-                                      opts.dt is the initial step, abstol / reltol apply, dW injection is not possible.
-                                      EXPERIMENTAL: SRIW1 parity with the oracle measured on a B200, SOSRA not yet run there */
+                                      opts.dt is the initial step, abstol / reltol apply; noise_injected = 1 injects the
+                                      stream of standard normals (opts.noise_stream_len) instead of Brownian increments */
 
 /* What a problem looks like to the library: ODEProblem / SDEProblem (qa.jl:86,103) with f,
  * jac, tgrad, g and one ContinuousCallback (qa.jl:26; test/core.jl:69-72) given as CUDA-C
@@ -135,6 +132,10 @@ typedef struct b200ens_opts {
                                ODE steppers, one-thread kernels; b200ens_solve only */
     const double* abstol_vec; /* NULL, or n_state per-component absolute tolerances (solve(...; abstol = [...])); overrides abstol */
     const double* reltol_vec; /* NULL, or n_state per-component relative tolerances; overrides reltol */
+    int64_t noise_stream_len; /* B200ENS_MODEL_SDE_ADAPTIVE with noise_injected = 1: dW holds STANDARD NORMALS,
+                                 [N][noise_stream_len] of the state type, which every trajectory consumes in order in place
+                                 of its Philox stream (2 n_state per fresh step, bridge draw or rejection); a trajectory that
+                                 runs out of them ends with B200ENS_RC_FAILURE.  Ignored otherwise */
 } b200ens_opts;
 
 typedef struct b200ens_stats {
@@ -174,7 +175,8 @@ int b200ens_model_info(const b200ens_model* m, int64_t* cubin_bytes, int32_t* re
  * HOST buffers, trajectory-major:
  *   u0 [N][n_state], p [N][n_param], saveat [n_save] (ascending, within [t0,t1]; checked on the host,
  *   B200ENS_E_INVALID otherwise -- b200ens_solve_device trusts its device-resident grid),
- *   dW  NULL or [N][nsteps][nvec][n_state]  (nvec = 1 EM, 2 SOSRA: dW then dZ),
+ *   dW  NULL or [N][nsteps][nvec][n_state]  (nvec = 1 EM, 2 SOSRA / SRIW1: dW then dZ; nsteps = ceil((t1-t0)/dt));
+ *       adaptive SDE models: [N][noise_stream_len] standard normals,
  *   out_u [N][n_save][n_state], out_t [n_save] or NULL, retcode [N], stats [N] or NULL.
  * Trajectory ranges are sharded over the devices in device_mask; blocking. */
 int b200ens_solve(b200ens_model* m, const b200ens_opts* o, int64_t N, const void* u0, const void* p,

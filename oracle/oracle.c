@@ -52,6 +52,42 @@ float orc_fastexp2(float y) {
     memcpy(&p, &ip, 4);
     return p;
 }
+/* Float32 reciprocal used by the error norm (restates b2_rcp_nr, kernels/b2_common.cuh): x0 = bits(0x7EF311C7 - bits(s))
+ * (relative error <= 5.1 %), two Newton steps x <- fma(x, fma(-s, x, 1), x) -> relative error <= 6.6e-6.  EEst only
+ * steers the step size; the spec'd arithmetic (IEEE division) is orc_opts.spec_arith. */
+float orc_rcp_nr(float s) {
+    uint32_t is;
+    memcpy(&is, &s, 4);
+    const uint32_t ix = 0x7EF311C7u - is;
+    float x;
+    memcpy(&x, &ix, 4);
+    x = fmaf(x, fmaf(-s, x, 1.0f), x);
+    x = fmaf(x, fmaf(-s, x, 1.0f), x);
+    return x;
+}
+
+/* PI controller in the log domain, Float32, division-free (restates b2_pi_controller, kernels/b2_control.cuh):
+ *   l = log2(EEst) = 0.5*log2(EEst^2), lq = log2(qold)
+ *   accept (EEst <= 1): dt_next  = dt * clamp(gamma * 2^(beta2*lq - beta1*l), qmin, qmax)   [= dt / q of A.5]
+ *   reject            : dt_retry = dt * max(gamma * 2^(-beta1*l), qmin)                      [= dt / min(1/qmin, q11/gamma)]
+ *   EEst == 0         : dt_next  = dt * qmax */
+typedef struct { float qmin, qmax, gam, beta1, beta2, lqinit; } orc_ctl;
+typedef struct { int ok, isn, zero; float l, qi; } orc_decision;
+static orc_decision orc_pi_controller(float EE2, float lq, const orc_ctl* c) {
+    orc_decision d;
+    d.isn = EE2 != EE2;
+    d.ok = EE2 <= 1.0f;
+    d.zero = EE2 == 0.0f;
+    d.l = 0.5f * orc_fastlog2(EE2);
+    const float nbl = -c->beta1 * d.l;
+    float qi = orc_fastexp2(d.ok ? fmaf(c->beta2, lq, nbl) : nbl);
+    qi = fmaxf(c->qmin, qi * c->gam);
+    qi = d.ok ? fminf(c->qmax, qi) : qi;
+    d.qi = d.zero ? c->qmax : qi;
+    return d;
+}
+static float orc_ctl_lq_next(const orc_decision* d, const orc_ctl* c) { return fmaxf(d->zero ? c->lqinit : d->l, c->lqinit); }
+
 float orc_fastpow(float x, float y) {
     if (!(x > 0.0f)) return 0.0f;
     return orc_fastexp2(y * orc_fastlog2(x));
@@ -114,6 +150,7 @@ int orc_max_threads(void) { return omp_get_max_threads(); }
 #define FMAX fmax
 #define FMIN fmin
 #define SQRT sqrt
+#define POW pow
 #define REAL_EPS 2.220446049250313e-16
 #define NORMALS_PER_CALL 2
 #include "oracle_impl.inc"
@@ -124,6 +161,7 @@ int orc_max_threads(void) { return omp_get_max_threads(); }
 #undef FMAX
 #undef FMIN
 #undef SQRT
+#undef POW
 #undef REAL_EPS
 #undef NORMALS_PER_CALL
 
@@ -135,6 +173,7 @@ int orc_max_threads(void) { return omp_get_max_threads(); }
 #define FMAX fmaxf
 #define FMIN fminf
 #define SQRT sqrtf
+#define POW powf
 #define REAL_EPS 1.1920928955078125e-7f
 #define NORMALS_PER_CALL 4
 #include "oracle_impl.inc"

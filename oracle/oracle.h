@@ -64,6 +64,14 @@ typedef struct {
                               /* sde_adaptive: NULL, or receives W(t_end) of the accepted Brownian path, [N][n_state] */
     int32_t save_everystep;
     int32_t sde_adaptive;     /* 1: adaptive SRIW1 / SOSRA with rejection sampling with memory (RSwM1); `adaptive` stays unused for SDE algs */
+    int64_t noise_stream_len; /* sde_adaptive && noise_injected: dW is [N][noise_stream_len] STANDARD NORMALS, consumed in order
+                                 instead of the trajectory's Philox stream (running out of them -> ORC_RC_FAILURE) */
+    int32_t spec_arith;       /* 1: step control to the letter of SURVEY.md A.4 / A.5 -- error norm in the working precision with
+                                 IEEE division and sqrt, EEst^beta1 / qold^beta2 with libm pow, dt / q -- instead of the kernels'
+                                 contract (Float32 norm with a Newton reciprocal, log-domain controller with polynomial
+                                 log2 / exp2).  ODE steppers only.  Exists to MEASURE what the contract changes
+                                 (tests/test_spec_arith.py); the kernels are compared bit for bit against spec_arith = 0 */
+    int32_t pad2_;
 } orc_opts;
 
 /* u0 [N][n], p [N][m], saveat [n_save], out_u [N][n_save][n], retcode [N], stats [N] or NULL.
@@ -81,6 +89,8 @@ void* orc_model_fn(const char* model, const char* which, int is_f64);
 float orc_fastpow(float x, float y);
 float orc_fastlog2(float x);
 float orc_fastexp2(float y);
+/* Float32 reciprocal of the error norm: exponent-flip guess + two Newton steps (relative error <= 6.6e-6) */
+float orc_rcp_nr(float s);
 /* Philox4x32-10 */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* normals exactly as the kernels draw them: Philox block `block` of trajectory `traj`'s normal stream */

@@ -19,7 +19,7 @@ def test_exports_every_declared_symbol(B):
     nm = subprocess.check_output(["nm", "-D", "--defined-only", B._lib.LIB_PATH], text=True)
     for sym in declared:
         assert hasattr(L, sym) and re.search(rf"\bT {sym}\b", nm), sym
-    assert L.b200ens_abi_version() == 4
+    assert L.b200ens_abi_version() == 5
 
 
 def test_struct_layouts_match_header(B, tmp_path):
@@ -62,7 +62,7 @@ def test_every_stepper_jit_compiles_for_sm100a_without_a_gpu(B, alg, dtype):
 @pytest.mark.parametrize("alg", ["SRIW1", "SOSRA"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_adaptive_sde_kernel_jit_compiles(B, alg, dtype):
-    """B200ENS_MODEL_SDE_ADAPTIVE (experimental, include/b200ens.h): the RSwM kernel compiles for sm_100a; its local-memory
+    """B200ENS_MODEL_SDE_ADAPTIVE (include/b200ens.h): the RSwM kernel compiles for sm_100a; its local-memory
     frame is the stack of remembered Brownian increments, not register spills."""
     from b200ens import workloads as W
 
@@ -73,8 +73,9 @@ def test_adaptive_sde_kernel_jit_compiles(B, alg, dtype):
     with pytest.raises(B.B200EnsError) as e:
         B.build_model(W.lorenz_additive_problem(dtype), B.EM(), sde_adaptive=True)
     assert e.value.code == -6
-    with pytest.raises(NotImplementedError, match="experimental"):      # the public API keeps it behind an explicit opt-in
+    with pytest.raises(B.B200EnsError) as e:      # shipped, un-gated: reaches the library, which has no CPU fallback
         B.solve(W.lorenz_additive_problem(dtype), getattr(B, alg)(), adaptive=True, dt=0.1, saveat=1.0)
+    assert e.value.code == -3
 
 
 def test_compile_errors_are_reported(B):

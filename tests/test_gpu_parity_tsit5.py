@@ -56,27 +56,46 @@ def test_adaptive_saveat_matches_oracle(B, gpu_lib, oracle, dtype, kind):
     assert np.all(err <= tol), float((err / tol).max())
 
 
-def test_packed_ffma2_kernel_bit_identical(B, gpu_lib, oracle):
-    """Two trajectories per thread in packed FP32 (FFMA2/FADD2/FMUL2): every packed op is the per-half IEEE op,
-    so the result must equal the scalar kernel's and the oracle's bit for bit."""
+def test_packed_component_pairs_bit_identical(B, gpu_lib, oracle, monkeypatch):
+    """Float32 steppers pack component PAIRS of one trajectory into FFMA2 / FMUL2 (B2_PACK2, b2_erk.cuh): every packed
+    op is the per-half IEEE op, so the result must equal the unpacked kernel's (B2_PACK2=0) and the oracle's bit for
+    bit -- for odd n (pair + scalar tail: Lorenz) and even n (the 16-species network, one-thread kernel)."""
     from b200ens import workloads as W
+    import b200ens.api as api
 
-    nv = gpu_lib.lib().b200ens_nvrtc_info().decode()
-    if not nv.startswith("12.8 "):
-        # the library only honours PACKED_X2 under the ptxas it is bit-exact with (12.8); under 12.9 identical PTX gives
-        # ~1e-6 relative differences, so the request falls through to the scalar kernel and this test would be vacuous
-        pytest.skip(f"packed FP32x2 kernel is gated to NVRTC 12.8 (loaded: {nv})")
     N = 20011
     u0, p = W.lorenz_params(N, "random", seed=9, dtype=np.float32)
-    packed = _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1, packed_x2=True)
-    assert packed.timing["regs"] > 100, "the packed kernel did not run"
+    packed = _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1)
     ref, rc, st = oracle.solve("lorenz", "Tsit5", u0, p, (0.0, 10.0), SAVEAT, 0.1, dtype=np.float32)
     assert np.array_equal(packed.retcodes, rc)
     assert np.array_equal(packed.stats[:, :3], st[:, :3])
     assert np.array_equal(packed.u_array, ref)
-    fixed = _solve_gpu(B, np.float32, u0[:999], p[:999], [10.0], 0.01, adaptive=False, packed_x2=True)
+    fixed = _solve_gpu(B, np.float32, u0[:999], p[:999], [10.0], 0.01, adaptive=False)
     ref2, _, _ = oracle.solve("lorenz", "Tsit5", u0[:999], p[:999], (0.0, 10.0), [10.0], 0.01, dtype=np.float32, adaptive=False)
     assert np.array_equal(fixed.u_array, ref2)
+
+    u16, p16 = (x.astype(np.float32) for x in W.net16_params(3001))
+    sv = np.linspace(0.0, 10.0, 11)
+    b16p = W.net16_problem()
+    prob16 = B.ODEProblem(W.net16, b16p.u0.astype(np.float32), b16p.tspan, b16p.p.astype(np.float32))
+
+    def net(split):
+        eprob = B.EnsembleProblem(prob16, u0s=u16, ps=p16)
+        return B.solve(eprob, B.Tsit5(), B.EnsembleB200(split=split), trajectories=u16.shape[0], saveat=sv, dt=0.01,
+                       abstol=1e-5, reltol=1e-4)
+
+    a16 = net(False)
+    monkeypatch.setenv("B200ENS_DEFINES", "B2_PACK2=0")   # experiments / tests: extra #defines for the JIT
+    api._model_cache.clear()
+    try:
+        unpacked = _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1)
+        b16 = net(False)
+    finally:
+        monkeypatch.delenv("B200ENS_DEFINES")
+        api._model_cache.clear()
+    assert np.array_equal(packed.u_array, unpacked.u_array) and np.array_equal(packed.stats, unpacked.stats)
+    assert np.array_equal(a16.u_array, b16.u_array) and np.array_equal(a16.stats, b16.stats)
+    assert np.all(a16.retcodes == 1)
 
 
 @pytest.mark.parametrize("refill,stage", [(1, 1), (8, 0), (32, 1), (32, 0)])
@@ -145,25 +164,3 @@ def test_chunked_pipeline_matches_single_launch(B, gpu_lib, monkeypatch):
     chunked = _solve_gpu(B, np.float64, u0, p, SAVEAT, 0.1)
     assert chunked.timing["launches"] == 8
     assert np.array_equal(base.u_array, chunked.u_array) and np.array_equal(base.stats, chunked.stats)
-
-
-def test_packed_kernel_with_the_nvrtc_it_is_validated_for(gpu_lib):
-    """The packed FP32x2 kernel is only honoured under NVRTC 12.8 (see test_packed_ffma2_kernel_bit_identical).  The
-    image's toolkit NVRTC is 12.9, PyTorch bundles 12.8: run the packed parity test in a subprocess with
-    B200ENS_NVRTC pointing at that one, so the packed path stays tested."""
-    import glob
-    import os
-    import subprocess
-    import sys
-    import sysconfig
-
-    cands = glob.glob(os.path.join(sysconfig.get_paths()["purelib"], "nvidia", "cuda_nvrtc", "lib", "libnvrtc.so.12*"))
-    if not cands:
-        pytest.skip("no NVRTC 12.8 in site-packages")
-    env = dict(os.environ, B200ENS_NVRTC=sorted(cands)[0])
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-k",
-                        "test_packed_ffma2_kernel_bit_identical", "-rs"], env=env, capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    if "1 skipped" in r.stdout:
-        pytest.skip("that NVRTC is not 12.8 either: " + r.stdout[-300:])
-    assert "1 passed" in r.stdout, r.stdout[-2000:]

@@ -47,6 +47,26 @@ json.dump({"problem": "lorenz sweep, tspan (0,10) (BASELINE config 1)", "u0": [1
            "source": "scipy DOP853 rtol=atol=1e-13 (chaotic cases are only usable at early times)"},
           open(os.path.join(OUT, "lorenz_t10.json"), "w"), indent=1)
 
+# ---- config 1 as a SWEEP: 12 points of the ordered rho-sweep and 12 seeded "random" parameter sets (r (.) (10, 28, 8/3)),
+# truth by DOP853 at 1e-13; `reliable` = number of leading save points at which a second DOP853 run at 1e-11 agrees to
+# 1e-7 relative (beyond that the chaotic cases are not a truth any more).  Used by tests/test_oracle_golden.py and
+# tests/test_spec_arith.py to put a real bound on the global error at the BASELINE tolerances.
+ts = np.arange(0.0, 10.5, 1.0)
+cases = [(10.0, 56.0 * k / 11, 8.0 / 3.0) for k in range(12)]
+rng = np.random.default_rng(123)
+for k in range(12):
+    r = rng.random(3)
+    cases.append((10.0 * r[0], 28.0 * r[1], 8.0 / 3.0 * r[2]))
+rows = []
+for (sg, rho, beta) in cases:
+    A = solve_ivp(lor, (0, 10), [1.0, 0.0, 0.0], method="DOP853", t_eval=ts, rtol=1e-13, atol=1e-13, args=(sg, rho, beta)).y.T
+    Bv = solve_ivp(lor, (0, 10), [1.0, 0.0, 0.0], method="DOP853", t_eval=ts, rtol=1e-11, atol=1e-11, args=(sg, rho, beta)).y.T
+    agree = np.abs(A - Bv).max(axis=1) <= 1e-7 * (1 + np.abs(A).max(axis=1))
+    rows.append({"p": [sg, rho, beta], "u": A.tolist(), "reliable": int(np.argmin(agree)) if not agree.all() else len(ts)})
+json.dump({"problem": "lorenz parameter sweep, tspan (0,10), u0 = [1,0,0] (BASELINE config 1)", "u0": [1.0, 0.0, 0.0], "t": ts.tolist(),
+           "cases": rows, "source": "scipy DOP853 rtol=atol=1e-13; `reliable` leading save points confirmed by a 1e-11 run"},
+          open(os.path.join(OUT, "lorenz_t10_sweep.json"), "w"), indent=1)
+
 ts = 10.0 ** np.arange(-5, 6)
 s = solve_ivp(rob, (0, 1e5), [1.0, 0.0, 0.0], method="Radau", jac=rob_jac, t_eval=ts, rtol=1e-12, atol=1e-15, args=(0.04, 3e7, 1e4))
 json.dump({"problem": "robertson test/core.jl:39-46", "u0": [1.0, 0.0, 0.0], "p": [0.04, 3e7, 1e4], "t": ts.tolist(),

@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-big", action="store_true", help="skip the informational 10M-trajectory run")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-configs", action="store_true", help="skip the block of the other BASELINE configs (3, 4, 5, Float64)")
     return ap.parse_args()
 
 
@@ -86,6 +87,125 @@ def oracle_throughput(dtype, sweep, n_target, seconds, seed=0):
             "sample": f"first {n} trajectories of the workload x {reps} repeats, CPU oracle (C, OpenMP dynamic, -O2 -mfma -mavx2, "
                       f"{cores} threads), {el:.2f} s per pass ({el * reps * cores:.0f} core-seconds), {steps / el:.3g} attempted steps/s",
             "seconds": el, "n": n}
+
+
+# ------------------------------------------------------------------ the other BASELINE.json configs (one JSON block)
+# Algorithmic flops per ATTEMPTED step (FMA = 2, add/mul/div/max = 1; RNG integer work not counted):
+#   Tsit5:  68 n + 6 F + 14                      Lorenz n = 3, F = 8                       -> 266
+#   Vern7: 118 n + 10 F + 14                     16-species network n = 16, F = 190        -> 3802
+#   Rosenbrock23 (n = 3, Robertson F = 13, J = 8):  W 9 + LU 18 + 3 solves x 18 + 3 F + ~60 of vector sums / norm -> 190
+#   Rodas5 / Rodas5P (s = 8):  J 8 + W 9 + LU 18 + 8 solves x 18 + 8 F + a-sums 96 + C-sums 147 + 42 + norm/controller 29 -> 600
+#   EM: 2n + 2n + F + G + n (dW = sqrt(dt) z)     GBM n = 1: 7;  stochastic Lorenz n = 3, F = 8, G = 0: 23
+#   SOSRA (3 drift stages, additive noise):  3 F + stage sums 2 x (4n + 2n) + update 12 n + chi2 3n + 6n (dW, dZ) -> 111 (n = 3)
+CFG_FLOPS = {"Tsit5": 266.0, "Vern7_net16": 3802.0, "Rosenbrock23": 190.0, "Rodas5": 600.0, "Rodas5P": 600.0,
+             "EM_gbm": 7.0, "EM_lorenz": 23.0, "SOSRA_lorenz": 111.0}
+
+
+def run_configs(dev, stream, peaks_tf, hbm_peak, cpu_seconds, cores):
+    """Device-resident runs of BASELINE.json configs 3, 4, 5 (+ the Float64 headline): kernel ms (best of `reps`, CUDA
+    events inside b200ens_solve_device), steps/s, the roofline that bounds each (FP32/FP64 FMA issue with the algorithmic
+    flops above, or HBM with the algorithmic bytes for the dense-saveat run) and a CPU-arm number from the oracle on a
+    bounded subset of the same seeded inputs.  Parity of every one of these launch shapes is in tests/."""
+    import torch
+
+    import b200ens as B
+    from b200ens import _lib, workloads as W
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+
+    out = {}
+
+    def run(name, prob, alg, u0, p, saveat, dt, flops, omodel, adaptive=True, abstol=1e-6, reltol=1e-3, callback=None, reps=3,
+            cpu_n=20000, bound=None, seed=0, maxiters=None):
+        npdt = prob.u0.dtype
+        f64 = npdt == np.float64
+        tdt = torch.float64 if f64 else torch.float32
+        N, n = u0.shape
+        t = time.perf_counter()
+        model = B.build_model(prob, alg, callback)
+        jit_s = time.perf_counter() - t
+        saveat = np.asarray(saveat, dtype=npdt)
+        d_u0 = torch.from_numpy(np.ascontiguousarray(u0, dtype=npdt)).cuda()
+        d_p = torch.from_numpy(np.ascontiguousarray(p, dtype=npdt)).cuda()
+        d_save = torch.from_numpy(saveat).cuda()
+        d_out = torch.empty((N, len(saveat), n), dtype=tdt, device="cuda")
+        d_rc = torch.zeros(N, dtype=torch.int32, device="cuda")
+        d_st = torch.zeros((N, 4), dtype=torch.int32, device="cuda")
+        o = _lib.default_opts()
+        o.adaptive, o.t0, o.t1, o.dt, o.abstol, o.reltol = int(adaptive), prob.tspan[0], prob.tspan[1], dt, abstol, reltol
+        o.seed = seed
+        if maxiters:
+            o.maxiters = maxiters
+        if callback is not None:
+            o.interp_points = 10
+        ms = []
+        for _ in range(reps):
+            tm = model.solve_device(o, dev, stream.cuda_stream, N, d_u0.data_ptr(), d_p.data_ptr(), d_save.data_ptr(), len(saveat),
+                                    d_out.data_ptr(), d_rc.data_ptr(), d_st.data_ptr())
+            ms.append(tm.kernel_ms)
+        st = d_st.cpu().numpy()
+        rc = d_rc.cpu().numpy()
+        best = min(ms[1:]) if len(ms) > 1 else ms[0]
+        steps = float(st[:, :2].sum())
+        es = np.dtype(npdt).itemsize
+        alg_bytes = N * ((n + p.shape[1] + len(saveat) * n) * es + 4 + 16)
+        tf = flops * steps / (best * 1e-3) / 1e12
+        peak = peaks_tf["f64" if f64 else "f32"]
+        gbs = alg_bytes / (best * 1e-3) / 1e9
+        if bound is None:
+            bound = "fma_fp64" if f64 else "fma_fp32"
+        roof = ({"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "algorithmic_bytes": alg_bytes}
+                if bound == "hbm" else
+                {"bound": bound, "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "flops_per_step": flops})
+        # CPU arm: the oracle on the first cpu_n trajectories of the same inputs, all host threads
+        cpu = None
+        if cpu_seconds > 0:
+            k = min(N, cpu_n)
+            kw = dict(abstol=abstol, reltol=reltol, adaptive=adaptive, dtype=npdt, nthreads=cores, seed=seed, want_stats=False)
+            if maxiters:
+                kw["maxiters"] = maxiters
+            if callback is not None:
+                kw["event"] = True
+            t = time.perf_counter()
+            oracle_py.solve(omodel, alg.name, u0[:k], p[:k], prob.tspan, saveat, dt, **kw)
+            el = time.perf_counter() - t
+            cpu = {"value": k / el, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": f"first {k} trajectories, {el:.2f} s"}
+        del d_out
+        torch.cuda.empty_cache()
+        out[name] = {"N": N, "dtype": np.dtype(npdt).name, "n_save": int(len(saveat)), "kernel_ms": round(best, 4),
+                     "traj_per_s": N / best * 1e3, "steps_per_s": steps / best * 1e3, "mean_steps": steps / N,
+                     "success_frac": float(np.isin(rc, (1, 2)).mean()), "events_mean": float(st[:, 3].mean()),
+                     "roofline": roof, "hbm_gbs_algorithmic": gbs, "regs": tm.regs, "launches": tm.launches, "jit_s": round(jit_s, 2),
+                     "cpu_baseline": cpu, "speedup_vs_cpu_port": (N / best * 1e3) / cpu["value"] if cpu else None}
+
+    SAVE11 = np.arange(0.0, 10.5, 1.0)
+    # configs[1] in Float64 (config 1 is a Float64 reference run)
+    u0, p = W.lorenz_params(1_000_000, "random", 0, np.float64)
+    run("cfg2_lorenz_tsit5_f64_1M", W.lorenz_problem(np.float64, TSPAN), B.Tsit5(), u0, p, SAVE11, DT0, CFG_FLOPS["Tsit5"], "lorenz", cpu_n=100000)
+    # config 3: Robertson, Rosenbrock23 / Rodas5 / Rodas5P with the analytic Jacobian, 1M trajectories
+    u0, p = W.robertson_params(1_000_000)
+    for alg in (B.Rosenbrock23(), B.Rodas5(), B.Rodas5P()):
+        run(f"cfg3_robertson_{alg.name}_f64_1M", W.robertson_problem(), alg, u0, p, W.ROBERTSON_SAVEAT, 1e-6, CFG_FLOPS[alg.name], "robertson",
+            abstol=1e-8, reltol=1e-6, cpu_n=50000)
+    # config 4: GBM (EM) and stochastic Lorenz (EM, SOSRA), 10M paths, Philox on the device
+    for dt_ in (np.float32, np.float64):
+        tag = np.dtype(dt_).name.replace("float", "f")
+        u0, p = W.gbm_params(10_000_000, dtype=dt_)
+        run(f"cfg4_gbm_EM_{tag}_10M", W.gbm_problem(dt_), B.EM(), u0, p, [1.0], 1 / 256, CFG_FLOPS["EM_gbm"], "gbm", adaptive=False, seed=7,
+            cpu_n=200000, reps=2)
+    u0, p = W.lorenz_additive_params(10_000_000, dtype=np.float32)
+    for alg, key in ((B.EM(), "EM_lorenz"), (B.SOSRA(), "SOSRA_lorenz")):
+        run(f"cfg4_stochastic_lorenz_{alg.name}_f32_10M", W.lorenz_additive_problem(np.float32), alg, u0, p, [10.0], 1 / 256, CFG_FLOPS[key],
+            "lorenz_additive", adaptive=False, seed=7, maxiters=10**6, cpu_n=20000, reps=2)
+    del u0, p
+    # config 5: 16-species network, Vern7 + ContinuousCallback, dense saveat
+    u0, p = W.net16_params(1_000_000)
+    run("cfg5_net16_vern7_event_f64_1M_saveat101", W.net16_problem(), B.Vern7(), u0, p, np.linspace(0, 10, 101), 0.01, CFG_FLOPS["Vern7_net16"],
+        "net16", abstol=1e-8, reltol=1e-8, callback=W.net16_callback(), reps=2, cpu_n=10000)
+    run("cfg5_net16_vern7_event_f64_500k_saveat1001", W.net16_problem(), B.Vern7(), u0[:500_000], p[:500_000], np.linspace(0, 10, 1001), 0.01,
+        CFG_FLOPS["Vern7_net16"], "net16", abstol=1e-8, reltol=1e-8, callback=W.net16_callback(), reps=2, cpu_n=10000, bound="hbm")
+    return out
 
 
 def run_reference(a, rank, world):
@@ -356,6 +476,17 @@ def main():
         cpu = oracle_throughput(npdt, a.sweep, N, a.cpu_seconds)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    configs = None
+    if rank == 0 and world == 1 and not a.no_configs:
+        t_cfg = time.perf_counter()
+        try:
+            peaks_tf = {"f32": peak_tf if not f64 else fma_peak(dev, False), "f64": peak_tf if f64 else fma_peak(dev, True)}
+            configs = run_configs(dev, stream, peaks_tf, hbm_peak, 0.0 if a.no_cpu_baseline else a.cpu_seconds,
+                                  cpu["cores"] if cpu else len(os.sched_getaffinity(0)))
+            configs["_seconds"] = round(time.perf_counter() - t_cfg, 1)
+        except Exception as e:  # noqa: BLE001 -- the headline line must still print
+            configs = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
     if rank == 0:
         line = {
             "metric": "trajectories/sec (Lorenz Tsit5, 1M traj)", "value": value, "unit": "trajectories/s",
@@ -371,6 +502,7 @@ def main():
                     "ms_per_step": e2e_s / a.steps * 1e3, "matches_device_leg": same},
             "gpu_launches": a.steps * launches_per_step + e2e_launches, "clocks": clocks,
             "trajectory_steps_per_s": world * attempted / (ms_per_step * 1e-3),
+            "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <nvrtc.h>
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -191,7 +193,7 @@ NvrtcApi* nvrtc_api() {
     NvrtcApi* var = nvrtc_api();                                                                                \
     if (!var) return fail(B200ENS_E_COMPILE, "NVRTC not found (set B200ENS_NVRTC to the path of libnvrtc.so.12)")
 
-// ---------------------------------------------------------------- compile cache (in-process)
+// ---------------------------------------------------------------- compile cache (in-process; the on-disk level follows)
 std::mutex g_cache_mu;
 std::map<std::string, std::shared_ptr<std::pair<std::vector<char>, std::string>>> g_cache;
 
@@ -321,6 +323,90 @@ std::string build_source(const b200ens_model_desc* d, int min_blocks, int block,
     return s;
 }
 
+// ---------------------------------------------------------------- compile cache (on disk)
+// A model is compiled once per (generated source, embedded kernel headers, flags, NVRTC version): the cubin and the
+// ptxas log are kept under $B200ENS_CACHE_DIR, else <directory of libb200ens.so>/cubin_cache (in-tree: it travels with
+// the library), else ~/.cache/b200ens.  Config 5's split Vern7 kernel takes 14.5 s to JIT (profiles/README.md); every
+// later process loads it in milliseconds.  B200ENS_CACHE=0 switches the disk cache off.  Entries are written to a
+// temporary file and renamed, so concurrent processes (one per GPU under torchrun) never see a partial cubin.
+uint64_t fnv1a(const void* data, size_t n, uint64_t h) {
+    const unsigned char* p = (const unsigned char*)data;
+    for (size_t i = 0; i < n; i++) {
+        h ^= p[i];
+        h *= 0x100000001b3ull;
+    }
+    return h;
+}
+const std::string& cache_dir() {
+    static std::string dir;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (const char* e = getenv("B200ENS_CACHE")) if (atoi(e) == 0) return;
+        std::vector<std::string> cand;
+        if (const char* e = getenv("B200ENS_CACHE_DIR")) cand.push_back(e);
+        Dl_info info;
+        if (dladdr((void*)&fnv1a, &info) && info.dli_fname) {
+            std::string so = info.dli_fname;
+            const size_t sl = so.rfind('/');
+            cand.push_back((sl == std::string::npos ? std::string(".") : so.substr(0, sl)) + "/cubin_cache");
+        }
+        if (const char* h = getenv("HOME")) cand.push_back(std::string(h) + "/.cache/b200ens");
+        for (const auto& c : cand) {
+            std::string cmd;
+            // mkdir -p by hand (two levels are enough for the candidates above)
+            for (size_t i = 1; i <= c.size(); i++)
+                if (i == c.size() || c[i] == '/') (void)::mkdir(c.substr(0, i).c_str(), 0755);
+            const std::string probe = c + "/.probe" + std::to_string((long long)getpid());
+            FILE* f = fopen(probe.c_str(), "wb");
+            if (!f) continue;
+            fclose(f);
+            remove(probe.c_str());
+            dir = c;
+            return;
+        }
+    });
+    return dir;
+}
+std::string cache_key(const b200ens_model* m, bool fast, const NvrtcApi* nv) {
+    static uint64_t hdr_a = 0, hdr_b = 0;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        hdr_a = 0xcbf29ce484222325ull;
+        hdr_b = 0x84222325cbf29ce4ull;
+        for (int i = 0; i < kNumHeaders; i++) {
+            hdr_a = fnv1a(kHeaders[i].text, strlen(kHeaders[i].text), fnv1a(kHeaders[i].name, strlen(kHeaders[i].name), hdr_a));
+            hdr_b = fnv1a(kHeaders[i].text, strlen(kHeaders[i].text), hdr_b * 31 + 7);
+        }
+    });
+    char tail[96];
+    snprintf(tail, sizeof tail, "|%s|nvrtc%d.%d|sm_100a|v1", fast ? "fmad" : "nofmad", nv ? nv->major : 0, nv ? nv->minor : 0);
+    uint64_t a = fnv1a(m->source.data(), m->source.size(), hdr_a), b = fnv1a(m->source.data(), m->source.size(), hdr_b);
+    a = fnv1a(tail, strlen(tail), a);
+    b = fnv1a(tail, strlen(tail), b);
+    char name[64];
+    snprintf(name, sizeof name, "%016llx%016llx", (unsigned long long)a, (unsigned long long)b);
+    return name;
+}
+bool read_file(const std::string& path, std::vector<char>* out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out->resize(n > 0 ? (size_t)n : 0);
+    const bool ok = n >= 0 && fread(out->data(), 1, out->size(), f) == out->size();
+    fclose(f);
+    return ok;
+}
+void write_file_atomic(const std::string& path, const void* data, size_t n) {
+    const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    const bool ok = fwrite(data, 1, n, f) == n;
+    fclose(f);
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+
 int nvrtc_compile(b200ens_model* m) {
     const bool fast = (m->flags & B200ENS_MODEL_FAST_MATH) != 0;
     const std::string key = std::string(fast ? "F" : "S") + m->source;
@@ -334,6 +420,19 @@ int nvrtc_compile(b200ens_model* m) {
         }
     }
     B2_NVRTC_OR_FAIL(nv);
+    const std::string& cdir = cache_dir();
+    const std::string cfile = cdir.empty() ? std::string() : cdir + "/" + cache_key(m, fast, nv);
+    if (!cfile.empty()) {
+        std::vector<char> cub, lg;
+        if (read_file(cfile + ".cubin", &cub) && cub.size() > 64 && memcmp(cub.data(), "\177ELF", 4) == 0) {
+            read_file(cfile + ".log", &lg);
+            m->cubin = cub;
+            m->log.assign(lg.begin(), lg.end());
+            std::lock_guard<std::mutex> lk(g_cache_mu);
+            g_cache[key] = std::make_shared<std::pair<std::vector<char>, std::string>>(m->cubin, m->log);
+            return 0;
+        }
+    }
     nvrtcProgram prog;
     const char* hdr_names[kNumHeaders];
     const char* hdr_text[kNumHeaders];
@@ -366,6 +465,10 @@ int nvrtc_compile(b200ens_model* m) {
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         g_cache[key] = std::make_shared<std::pair<std::vector<char>, std::string>>(m->cubin, m->log);
+    }
+    if (!cfile.empty()) {
+        write_file_atomic(cfile + ".log", m->log.data(), m->log.size());
+        write_file_atomic(cfile + ".cubin", m->cubin.data(), m->cubin.size());
     }
     return 0;
 }

@@ -168,6 +168,18 @@ __device__ __forceinline__ float b2_rcp_nr(float s) {
     return x;
 }
 
+// theta = (tau - tprev) / dt of a saveat point.  Float32: multiply by a three-step Newton reciprocal (relative error
+// <= 9e-8, under one ulp of theta; 8 issue slots against 13-15 for the IEEE division with its slow-path scaffolding --
+// the saveat block runs at ~5/32 lanes in 9 of 10 iterations, profiles/README.md).  Float64: IEEE division.
+__device__ __forceinline__ float b2_theta(float num, float dt) {
+    float x = __uint_as_float(0x7EF311C7u - __float_as_uint(dt));
+    x = __fmaf_rn(x, __fmaf_rn(-dt, x, 1.0f), x);
+    x = __fmaf_rn(x, __fmaf_rn(-dt, x, 1.0f), x);
+    x = __fmaf_rn(x, __fmaf_rn(-dt, x, 1.0f), x);
+    return __fmul_rn(num, x);
+}
+__device__ __forceinline__ double b2_theta(double num, double dt) { return num / dt; }
+
 // ---- ITP root-find helper: pw = eps * 2^(k+1), eps = 2*B2_EPS, k = number of halvings of wd until wd <= 2*eps
 // (the oracle computes it with that loop; ~50 iterations in Float64).  All quantities are powers of two, so the
 // closed form from the exponent bits is exact: with wd = m * 2^e, m in [1,2): k = e - tau + (m > 1), 2*eps = 2^tau.

@@ -318,7 +318,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
             const bool at_end = tau == tnew && !fired;  // the step lands exactly on the save point: store u_new
             if (need && !at_end) alg.prepare_dense(u, p, tprev, dts, nf);
             real w[B2_N];
-            alg.interp(u, un, (tau - tprev) / dts, dts, w);
+            alg.interp(u, un, b2_theta(tau - tprev, dts), dts, w);
             if (need) {
                 if (at_end) sink.put(si, un);
                 else sink.put(si, w);

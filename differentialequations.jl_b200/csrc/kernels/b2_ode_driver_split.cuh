@@ -456,7 +456,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                 lane_extra = true;
             }
             real w[B2_NL];
-            alg.interp(u, un, (tau - tprev) / dts, dts, w);
+            alg.interp(u, un, b2_theta(tau - tprev, dts), dts, w);
             if (need) {
 #pragma unroll
                 for (int j = 0; j < B2_NL; j++)

@@ -48,7 +48,7 @@ class Opts(C.Structure):
         ("block_threads", C.c_int32), ("stage_outputs", C.c_int32),
         ("work_order", C.c_int32), ("save_everystep", C.c_int32),
         ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double)),
-        ("noise_stream_len", C.c_int64),
+        ("noise_stream_len", C.c_int64), ("shard_blocks", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -61,6 +61,7 @@ class Timing(C.Structure):
         ("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
         ("n_devices", C.c_int32), ("launches", C.c_int32),
         ("grid", C.c_int32), ("block", C.c_int32), ("smem_bytes", C.c_int32), ("regs", C.c_int32),
+        ("kernel_ms_min", C.c_double),
     ]
 
     def asdict(self):

@@ -313,8 +313,9 @@ class EnsembleB200:
     caller's order / 1 integrate in descending expected-work order (scheduling only, identical results)."""
 
     def __init__(self, devices=None, refill_threshold=0, stage_outputs=-1, fast_math=False,
-                 stage_vectors_in_smem=False, work_order=-1, split=None):
+                 stage_vectors_in_smem=False, work_order=-1, split=None, shard_blocks=0):
         self.devices = devices
+        self.shard_blocks = shard_blocks   # multi-device dealing: 0 auto (8 blocks per device, boustrophedon), 1 contiguous ranges
         self.refill_threshold = refill_threshold
         self.stage_outputs = stage_outputs
         self.work_order = work_order
@@ -692,6 +693,7 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
     o.refill_threshold = int(ensemblealg.refill_threshold)
     o.stage_outputs = int(ensemblealg.stage_outputs)
     o.work_order = int(ensemblealg.work_order)
+    o.shard_blocks = int(ensemblealg.shard_blocks)
 
     if summary:  # EnsembleAnalysis.timestep_meanvar on the device: returns an EnsembleSummary
         t_solve = time.perf_counter()

@@ -840,8 +840,9 @@ struct ShardResult {
     LaunchPlan lp;
 };
 
-// Solve trajectories [lo, hi) of the caller's host buffers on one device.
-int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, long long hi, const char* u0,
+// Solve the trajectory ranges [lo, hi) in `ranges` (the blocks dealt to this device) of the caller's host buffers on one device.
+typedef std::vector<std::pair<long long, long long>> Ranges;
+int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& ranges, const char* u0,
                 const char* p, const void* saveat, int n_save, const char* dW, char* out_u, int32_t* retcode,
                 b200ens_stats* stats, ShardResult* res, Moments* mom = nullptr, char* out_t_every = nullptr) {
     DeviceCtx* d;
@@ -880,7 +881,9 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
     CU(cudaStreamSynchronize(d->slot[0].stream));
 
     // chunk size: keep both pipeline slots under ~1/4 of the device memory and at least a few waves
-    const long long total = hi - lo;
+    long long total = 0;
+    for (const auto& r : ranges) total += r.second - r.first;
+    const long long lo = ranges.empty() ? 0 : ranges[0].first;
     const size_t per_traj = (size_t)n * es + (size_t)np * es + out_per_traj + noise_per_traj + 4 + sizeof(b200ens_stats);
     size_t free_b = 0, total_b = 0;
     mark("saveat");
@@ -901,7 +904,15 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
     const long long mem_cap = (long long)((free_b / 8) / std::max<size_t>(1, per_traj));
     chunk = std::max<long long>(1, std::min(chunk, mem_cap));
     std::vector<long long> sched;
-    if (const char* e = getenv("B200ENS_CHUNK")) {   // fixed size (tests, experiments)
+    std::vector<std::pair<long long, long long>> work;   // (first trajectory, count) of every chunk, in launch order
+    if (ranges.size() > 1) {
+        // several blocks (multi-device dealing): one chunk per block, split further only when a block exceeds the cap
+        if (const char* e = getenv("B200ENS_CHUNK")) chunk = std::max<long long>(1, atoll(e));
+        for (const auto& r : ranges)
+            for (long long a0 = r.first; a0 < r.second; a0 += chunk) work.emplace_back(a0, std::min(chunk, r.second - a0));
+        chunk = 0;
+        for (const auto& w : work) chunk = std::max(chunk, w.second);
+    } else if (const char* e = getenv("B200ENS_CHUNK")) {   // fixed size (tests, experiments)
         chunk = std::max<long long>(1, atoll(e));
         for (long long r = total; r > 0; r -= chunk) sched.push_back(std::min(chunk, r));
     } else {
@@ -923,6 +934,14 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
             r -= c;
         }
         chunk = *std::max_element(sched.begin(), sched.end());
+    }
+    if (work.empty()) {
+        long long a0 = lo;
+        for (size_t i = 0; a0 < lo + total; i++) {
+            const long long cn = std::min<long long>(sched[std::min(i, sched.size() - 1)], lo + total - a0);
+            work.emplace_back(a0, cn);
+            a0 += cn;
+        }
     }
 
     LaunchPlan lp;
@@ -951,7 +970,6 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
     } pend[kMaxSlots];
     int nslots = kMaxSlots;
     if (const char* e = getenv("B200ENS_SLOTS")) nslots = std::max(1, std::min(kMaxSlots, atoi(e)));
-    long long done = 0;
     int it = 0;
     const size_t out_b = (mom || !n_save) ? 0 : out_per_traj;   // bytes per trajectory in the staged output block
     auto collect = [&](Slot& s, const Pending& pd) -> int {
@@ -973,9 +991,9 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
         res->d2h += c_;
         return 0;
     };
-    while (done < total) {
-        const long long cn = std::min<long long>(sched[std::min<size_t>(it, sched.size() - 1)], total - done);
-        const long long g0 = lo + done;  // global index of the chunk's first trajectory
+    for (const auto& wk : work) {
+        const long long cn = wk.second;
+        const long long g0 = wk.first;  // global index of the chunk's first trajectory
         Slot& s = d->slot[it % nslots];
         if (pend[it % nslots].used) {
             rc = collect(s, pend[it % nslots]);
@@ -1072,7 +1090,6 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, long long lo, 
         pend[it % nslots].g0 = g0;
         pend[it % nslots].cn = cn;
         res->launches++;
-        done += cn;
         it++;
     }
     for (int k = 0; k < kMaxSlots; k++) {
@@ -1332,6 +1349,12 @@ static int solve_host(b200ens_model* m, const b200ens_opts* o, int64_t N, const 
     for (int g = 0; g < ndev && g < 32; g++)
         if (o->device_mask == 0 || (o->device_mask >> g) & 1u) devs.push_back(g);
     if (devs.empty()) return fail(B200ENS_E_NODEVICE, "device_mask 0x%x selects no visible device", o->device_mask);
+    // tests: B200ENS_VIRTUAL_SHARDS=k deals the ensemble as if k devices were selected, all mapped onto the first one
+    // (the shards then run one after the other) -- exercises the multi-device dealing and gather on a one-GPU box
+    if (const char* e = getenv("B200ENS_VIRTUAL_SHARDS")) {
+        const int k = std::max(1, std::min(32, atoi(e)));
+        devs.assign((size_t)k, devs[0]);
+    }
     if ((long long)devs.size() > N) devs.resize((size_t)N);
     const int G = (int)devs.size();
     std::vector<ShardResult> res(G);
@@ -1344,9 +1367,27 @@ static int solve_host(b200ens_model* m, const b200ens_opts* o, int64_t N, const 
             moms[g].sum = mbuf[g].data();
             moms[g].sumsq = mbuf[g].data() + row_len;
         }
+    // Dealing the trajectories: the ensemble is cut into G*k contiguous blocks which go to the devices in
+    // boustrophedon order 0,1,..,G-1,G-1,..,1,0,0,1,..: along an ORDERED parameter sweep the work per trajectory varies
+    // ~10x (Lorenz rho-sweep), contiguous G-ths would leave the first GPU idle while the last one integrates the chaotic
+    // end; the back-and-forth deal cancels a linear trend exactly and leaves every device the same mix.  Every block is
+    // D2H-copied straight into its place in the caller's arrays -- the gather is still implicit, there is no collective
+    // -- and every trajectory is computed exactly as before (Philox streams are keyed by the global index).
+    int k_blocks = o->shard_blocks > 0 ? o->shard_blocks : 8;
+    if (G == 1) k_blocks = 1;
+    while (k_blocks > 1 && N / ((long long)G * k_blocks) < 4096) k_blocks /= 2;   // blocks stay large enough for 50+ GB/s copies
+    std::vector<Ranges> deal(G);
+    {
+        const long long nb = (long long)G * k_blocks;
+        for (long long b = 0; b < nb; b++) {
+            const long long lo = N * b / nb, hi = N * (b + 1) / nb;
+            const long long r = b % (2 * G);
+            const int g = (int)(r < G ? r : 2 * G - 1 - r);
+            if (hi > lo) deal[g].emplace_back(lo, hi);
+        }
+    }
     auto run = [&](int g) {
-        const long long lo = N * g / G, hi = N * (g + 1) / G;  // contiguous trajectory ranges
-        res[g].code = solve_shard(m, o, devs[g], lo, hi, (const char*)u0, (const char*)p, saveat, n_save,
+        res[g].code = solve_shard(m, o, devs[g], deal[g], (const char*)u0, (const char*)p, saveat, n_save,
                                   (const char*)dW, (char*)out_u, retcode, stats, &res[g], moments ? &moms[g] : nullptr,
                                   every ? (char*)out_t : nullptr);
         if (res[g].code) res[g].err = g_err;
@@ -1378,6 +1419,7 @@ static int solve_host(b200ens_model* m, const b200ens_opts* o, int64_t N, const 
         for (int g = 0; g < G; g++) {
             timing->h2d_ms = std::max(timing->h2d_ms, res[g].h2d);
             timing->kernel_ms = std::max(timing->kernel_ms, res[g].kern);
+            timing->kernel_ms_min = g == 0 ? res[g].kern : std::min(timing->kernel_ms_min, res[g].kern);
             timing->d2h_ms = std::max(timing->d2h_ms, res[g].d2h);
             timing->total_ms = std::max(timing->total_ms, res[g].total);
             timing->launches += res[g].launches;

@@ -53,7 +53,12 @@ __device__ __forceinline__ float b2_ctl_lq_next(const B2Decision& d, const B2Ctl
 // ---- ITP bracketing root-find on theta in (lo, hi) (kappa1 = 0.2/(b-a), kappa2 = 2, n0 = 1) down to a bracket of
 // 4 eps; keeps and returns the LEFT end (LeftRootFind: the condition has not changed sign yet at the event time).
 // cond_at(theta) evaluates the event function on the dense output; gprev is its sign reference at the step start.
-// Worst case bisection + 1 evaluations, typically ~8.  Same evaluation sequence as the oracle.
+// The truncation offset has a FLOOR of 1.5 eps: plain ITP reaches a bracket of ~1e-10 in ~7 evaluations and then
+// degenerates into bisection (its offset kappa1*w^2 falls below an ulp, the regula-falsi point lands ON the root and
+// only one side of the bracket moves): 17 evaluations on average, 25 for the slowest of four lanes.  With the floor the
+// probe sits 1.5 eps beside the estimated root, both sides close and the search ends after 9-10 evaluations -- the
+// root-find was 27 % of all instructions of config 5 at 3/32 lanes, on every CTA's critical path (profiles/README.md).
+// Still worst case bisection + 1 evaluations.  Same evaluation sequence as the oracle.
 template <class CondAt>
 __device__ __forceinline__ real b2_itp_left(real lo, real hi, real glo, real ghi, const real gprev, CondAt&& cond_at) {
     const real eps = (real)2 * (real)B2_EPS;
@@ -63,7 +68,7 @@ __device__ __forceinline__ real b2_itp_left(real lo, real hi, real glo, real ghi
         const real xh = (real)0.5 * (lo + hi);
         const real r = pw - (real)0.5 * (hi - lo);
         pw *= (real)0.5;
-        const real delta = k1 * (hi - lo) * (hi - lo);
+        const real delta = b2_max(k1 * (hi - lo) * (hi - lo), (real)0.75 * eps);
         const real xf = (ghi * lo - glo * hi) / (ghi - glo);
         const real sg = (xh - xf) >= 0 ? (real)1 : (real)-1;
         const real xt = (delta <= b2_abs(xh - xf)) ? xf + sg * delta : xh;

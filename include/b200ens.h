@@ -136,6 +136,12 @@ typedef struct b200ens_opts {
                                  [N][noise_stream_len] of the state type, which every trajectory consumes in order in place
                                  of its Philox stream (2 n_state per fresh step, bridge draw or rejection); a trajectory that
                                  runs out of them ends with B200ENS_RC_FAILURE.  Ignored otherwise */
+    int32_t shard_blocks;     /* b200ens_solve on G > 1 devices: how the trajectories are dealt.  0 auto (= 8), k >= 1: the
+                                 ensemble is cut into G*k contiguous blocks which go to the devices in boustrophedon order
+                                 0,1,..,G-1,G-1,..,1,0,0,1,.. -- every device gets the same mix of an ORDERED parameter sweep
+                                 (work varies ~10x along the Lorenz rho-sweep; a linear trend cancels exactly), results are
+                                 bit-identical to k = 1 (contiguous ranges [g N/G, (g+1) N/G)) */
+    int32_t reserved0;        /* must be 0 */
 } b200ens_opts;
 
 typedef struct b200ens_stats {
@@ -146,6 +152,8 @@ typedef struct b200ens_timing {
     double h2d_ms, kernel_ms, d2h_ms, total_ms; /* device-event times; max over devices */
     int32_t n_devices, launches;
     int32_t grid, block, smem_bytes, regs;      /* of the last launch on the first device */
+    double kernel_ms_min;                       /* min over devices of the summed kernel time (kernel_ms is the max): their
+                                                   ratio is the work balance of a multi-device solve */
 } b200ens_timing;
 
 typedef struct b200ens_model b200ens_model;

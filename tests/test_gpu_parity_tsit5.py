@@ -153,6 +153,46 @@ def test_multi_device_sharding_matches_single_device(B, gpu_lib):
     assert np.array_equal(one.stats, many.stats)
 
 
+@pytest.mark.parametrize("shards,blocks", [(2, 0), (3, 0), (8, 0), (4, 1), (5, 3)])
+def test_block_dealing_matches_single_device(B, gpu_lib, monkeypatch, shards, blocks):
+    """Multi-device dealing: G*k blocks dealt 0,1,..,G-1,G-1,..,0 so that every device gets the same mix of an
+    ordered sweep.  B200ENS_VIRTUAL_SHARDS maps G shards onto ONE device (they run one after the other), so the dealing,
+    the per-block pipeline and the implicit gather are exercised on a one-GPU box: results must be bit-identical to the
+    plain single-device solve, for ragged N, every block count, stats and retcodes included."""
+    from b200ens import workloads as W
+
+    N = 300007
+    u0, p = W.lorenz_params(N, "ordered", dtype=np.float32)
+    one = _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1, devices=[0])
+    monkeypatch.setenv("B200ENS_VIRTUAL_SHARDS", str(shards))
+    many = _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1, devices=[0], shard_blocks=blocks)
+    assert many.timing["n_devices"] == shards
+    assert np.array_equal(one.u_array, many.u_array) and np.array_equal(one.retcodes, many.retcodes)
+    assert np.array_equal(one.stats, many.stats)
+
+
+def test_block_dealing_balances_an_ordered_sweep(B, gpu_lib):
+    """On >= 2 real GPUs: the ordered rho-sweep (work per trajectory grows ~10x along it) with the boustrophedon deal keeps
+    the per-device kernel times within 5 % of each other; contiguous ranges (shard_blocks=1) do not."""
+    from b200ens import workloads as W
+
+    ndev = gpu_lib.lib().b200ens_device_count()
+    if ndev < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    N = 1_000_000
+    u0, p = W.lorenz_params(N, "ordered", dtype=np.float32)
+    devs = list(range(ndev))
+    _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1, devices=devs)   # warm-up: JIT, buffers
+    dealt = _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1, devices=devs)
+    contiguous = _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1, devices=devs, shard_blocks=1)
+    bal = dealt.timing["kernel_ms_min"] / dealt.timing["kernel_ms"]
+    bal1 = contiguous.timing["kernel_ms_min"] / contiguous.timing["kernel_ms"]
+    print(f"per-device kernel time min/max on {ndev} GPUs: dealt {bal:.3f} ({dealt.timing['kernel_ms']:.2f} ms), "
+          f"contiguous {bal1:.3f} ({contiguous.timing['kernel_ms']:.2f} ms)")
+    assert bal > 0.95 and bal1 < 0.9
+    assert np.array_equal(dealt.u_array, contiguous.u_array) and np.array_equal(dealt.stats, contiguous.stats)
+
+
 def test_chunked_pipeline_matches_single_launch(B, gpu_lib, monkeypatch):
     """The host path streams trajectories in chunks over two streams; chunking must not change results."""
     from b200ens import workloads as W

@@ -369,7 +369,7 @@ class EnsembleSolution:
         self.stats = stats
         self.elapsedTime = elapsed
         self.timing = timing
-        self.converged = bool(np.all(retcodes == ReturnCode.Success))
+        self.converged = bool(np.all((retcodes == ReturnCode.Success) | (retcodes == ReturnCode.Terminated)))
         self._scalar = scalar
         self._dense = dense   # dense(i, times) -> [len(times), n_state] of trajectory i, or None
 
@@ -408,14 +408,21 @@ class EnsembleSummary:
         self.retcodes = retcodes
         self.elapsedTime = elapsed
         self.timing = timing
-        self.converged = bool(np.all(retcodes == ReturnCode.Success))
+        self.converged = bool(np.all((retcodes == ReturnCode.Success) | (retcodes == ReturnCode.Terminated)))
+
+    def _need_members(self):
+        if self.num_monte == 0:
+            raise ValueError("EnsembleSummary: no trajectory finished with a successful retcode (Success / Terminated); "
+                             f"retcodes seen: {sorted(set(int(r) for r in np.unique(self.retcodes)))}")
 
     @property
     def u(self):
-        return self.sum / max(self.num_monte, 1)
+        self._need_members()
+        return self.sum / self.num_monte
 
     @property
     def v(self):
+        self._need_members()
         n = self.num_monte
         return (self.sumsq - self.sum * self.sum / max(n, 1)) / max(n - 1, 1)
 
@@ -450,9 +457,11 @@ def build_model(prob, alg, callback=None, fast_math=False, ksmem=False, split=No
     dtype = prob.u0.dtype
     mm = getattr(prob, "mass_matrix", None)
     key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math, ksmem, split,
-           None if mm is None else mm.tobytes(), sde_adaptive)
+           None if mm is None else mm.tobytes(), sde_adaptive, os.environ.get("B200ENS_DEFINES", ""))
     hit = _model_cache.get(key)
-    if hit is not None and hit[1] is prob.f:
+    # the entry keeps STRONG references to f, g and the callback, so none of their ids can be recycled for another object
+    # while it is cached; a hit still has to be the very same objects
+    if hit is not None and hit[1] is prob.f and hit[2] is prob.g and hit[3] is callback:
         return hit[0]
     exprs, usyms, _, tsym = codegen.trace_vector_fn(prob.f, n, m)
     srcs = {"rhs_src": codegen.emit_rhs(exprs)}
@@ -488,7 +497,7 @@ def build_model(prob, alg, callback=None, fast_math=False, ksmem=False, split=No
                        ksmem=ksmem, split=split, sde_adaptive=sde_adaptive, **srcs)
     model.sources = srcs
     model.event_terminate = terminate
-    _model_cache[key] = (model, prob.f)
+    _model_cache[key] = (model, prob.f, prob.g, callback)
     return model
 
 
@@ -670,7 +679,8 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
     o._tol_keep = tol_keep   # the arrays must outlive every solve that uses these options (dense re-solves too)
     if maxiters is not None:
         o.maxiters = int(maxiters)
-    o.seed = int(seed)
+    # an output_func rerun (repeat > 1) redraws the noise like upstream does: the Philox key depends on (seed, repeat)
+    o.seed = (int(seed) + (int(_repeat) - 1) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
     o.traj_offset = int(_lo)    # global trajectory index of this batch's first trajectory (Philox counter base)
     o.noise_injected = 0 if dW is None else 1
     if sde_adaptive and dW is not None:

@@ -177,10 +177,36 @@ class _TraceIntegrator:
     """What `condition(u,t,integrator)` / `affect!(integrator)` see while being traced."""
 
     def __init__(self, n_state, n_param):
+        object.__setattr__(self, "_frozen", False)
         self.u = _Vec("u", n_state)
-        self.p = _Vec("p", max(n_param, 1)).syms
+        # p and t are READ-ONLY while tracing: only changes to integrator.u can be emitted (the kernel's affect functions
+        # take p as const), so `integrator.p[i] = ...` (parameter switches, dosing) or `integrator.t = ...` raise instead
+        # of being dropped silently
+        self.p = _ReadOnlySeq(_Vec("p", max(n_param, 1)).syms, "integrator.p")
         self.t = sp.Symbol("t", real=True)
         self.terminated = False
+        object.__setattr__(self, "_frozen", True)
+
+    def __setattr__(self, name, value):
+        if getattr(self, "_frozen", False) and name not in ("terminated",):
+            if name == "u":
+                raise NotImplementedError("affect! must modify integrator.u in place (integrator.u[i] = ...), not rebind it")
+            raise NotImplementedError(f"affect! may only modify integrator.u (tried to set integrator.{name}): writes to p or t "
+                                      "cannot be emitted for the device and are not silently dropped")
+        object.__setattr__(self, name, value)
+
+
+class _ReadOnlySeq(tuple):
+    """integrator.p while tracing: indexable and iterable, assignment raises."""
+
+    def __new__(cls, items, what):
+        obj = super().__new__(cls, items)
+        obj._what = what
+        return obj
+
+    def __setitem__(self, i, v):
+        raise NotImplementedError(f"affect! may only modify integrator.u (tried to assign {self._what}[{i}]): parameter writes "
+                                  "cannot be emitted for the device and are not silently dropped")
 
 
 def terminate_b(integrator):

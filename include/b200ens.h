@@ -202,7 +202,7 @@ int b200ens_solve_device(b200ens_model* m, const b200ens_opts* o, int32_t device
 /* Ensemble summary statistics without shipping the trajectories to the host (SciMLBase.EnsembleAnalysis
  * timestep_mean / timestep_meanvar, qa.jl:211).  Same inputs as b200ens_solve; instead of
  * out_u the call returns, for every (save point, component), the sum and the sum of squares over the trajectories
- * that finished with B200ENS_RC_SUCCESS, and their number:
+ * that finished with B200ENS_RC_SUCCESS or B200ENS_RC_TERMINATED (SciMLBase.successful_retcode), and their number:
  *   sum [n_save][n_state], sumsq [n_save][n_state] (double), count (int64).  mean = sum/count,
  *   var = (sumsq - sum^2/count)/(count-1).  Partial results of several GPUs / ranks add up. */
 int b200ens_solve_moments(b200ens_model* m, const b200ens_opts* o, int64_t N, const void* u0, const void* p,

@@ -219,6 +219,8 @@ def emit_callback(cb, n_state, n_param):
     integ = _TraceIntegrator(n_state, n_param)
     try:
         g = cb.condition(integ.u, integ.t, integ)
+    except NotImplementedError:
+        raise   # a precise rejection (e.g. affect! writing integrator.p) is the message the user needs
     except Exception as e:  # not expressible symbolically -> reject (no CPU fallback), SURVEY 7.3
         raise NotImplementedError(
             "ContinuousCallback condition is not symbolically traceable; EnsembleB200 only accepts "
@@ -235,6 +237,8 @@ def emit_callback(cb, n_state, n_param):
     integ2 = _TraceIntegrator(n_state, n_param)
     try:
         cb.affect(integ2)
+    except NotImplementedError:
+        raise   # a precise rejection (e.g. affect! writing integrator.p) is the message the user needs
     except Exception as e:
         raise NotImplementedError("ContinuousCallback affect! is not symbolically traceable") from e
     lines = []
@@ -257,6 +261,8 @@ def emit_vector_callback(cb, n_state, n_param):
     out = _Vec("g", nc)
     try:
         cb.condition(out, integ.u, integ.t, integ)
+    except NotImplementedError:
+        raise   # a precise rejection (e.g. affect! writing integrator.p) is the message the user needs
     except Exception as e:
         raise NotImplementedError("VectorContinuousCallback condition is not symbolically traceable; EnsembleB200 "
                                   "only accepts callbacks that can be emitted as CUDA C") from e
@@ -276,6 +282,8 @@ def emit_vector_callback(cb, n_state, n_param):
         it = _TraceIntegrator(n_state, n_param)
         try:
             cb.affect(it, k + 1)
+        except NotImplementedError:
+            raise   # a precise rejection (e.g. affect! writing integrator.p) is the message the user needs
         except Exception as e:
             raise NotImplementedError("VectorContinuousCallback affect! is not symbolically traceable") from e
         changed = [(i, v) for i, (sy, v) in enumerate(zip(it.u.syms, it.u.vals)) if v != sy]
@@ -299,6 +307,8 @@ def emit_discrete_callback(cb, n_state, n_param):
         g = sp.sympify(g)
         if not (g.is_Relational or g.is_Boolean or g in (sp.true, sp.false)):
             raise TypeError("condition must be a boolean expression")
+    except NotImplementedError:
+        raise   # a precise rejection (e.g. affect! writing integrator.p) is the message the user needs
     except Exception as e:
         raise NotImplementedError(
             "DiscreteCallback condition is not symbolically traceable to a boolean expression; EnsembleB200 only "
@@ -308,6 +318,8 @@ def emit_discrete_callback(cb, n_state, n_param):
     integ2 = _TraceIntegrator(n_state, n_param)
     try:
         cb.affect(integ2)
+    except NotImplementedError:
+        raise   # a precise rejection (e.g. affect! writing integrator.p) is the message the user needs
     except Exception as e:
         raise NotImplementedError("DiscreteCallback affect! is not symbolically traceable") from e
     changed = [(i, v) for i, (s, v) in enumerate(zip(integ2.u.syms, integ2.u.vals)) if v != s]

@@ -645,7 +645,8 @@ int plan_launch(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, long long
     const long long want = (N + per_block - 1) / per_block;
     lp->grid = (int)std::max<long long>(1, std::min<long long>((long long)nb * d->sms, want));
     int refill = o->refill_threshold;
-    if (refill <= 0) refill = (o->adaptive && !is_sde(m->alg)) ? 4 : 32;
+    const bool lane_refill = (o->adaptive && !is_sde(m->alg)) || (m->flags & B200ENS_MODEL_SDE_ADAPTIVE);   // step counts vary per trajectory
+    if (refill <= 0) refill = lane_refill ? 4 : 32;
     refill = std::min(refill, 32);
     lp->refill = refill;
     return 0;
@@ -722,6 +723,8 @@ int check_opts(const b200ens_model* m, const b200ens_opts* o, int n_save, const 
         if (o->stage_outputs > 0) return fail(B200ENS_E_UNSUPPORTED, "save_everystep with stage_outputs=1");
     }
     if (o->noise_injected && !dW) return fail(B200ENS_E_INVALID, "noise_injected=1 but dW is NULL");
+    if ((m->flags & B200ENS_MODEL_SDE_ADAPTIVE) && o->stage_outputs > 0)
+        return fail(B200ENS_E_UNSUPPORTED, "adaptive SDE kernels store their outputs directly (stage_outputs=1 is not available)");
     if (o->noise_injected && (m->flags & B200ENS_MODEL_SDE_ADAPTIVE) && o->noise_stream_len <= 0)
         return fail(B200ENS_E_INVALID, "adaptive SDE stepping with noise_injected=1 needs opts.noise_stream_len > 0 (dW = [N][noise_stream_len] standard normals)");
     return 0;

@@ -277,3 +277,79 @@ def test_odefunction_sdefunction_and_successful_retcode(B):
     assert not B.successful_retcode(B.ReturnCode.MaxIters) and not B.successful_retcode(B.ReturnCode.DtNaN)
     sol = B.ODESolution(np.array([0.0]), np.zeros((1, 1)), 1, None)
     assert B.successful_retcode(sol)
+
+
+def test_affect_may_only_modify_u(B):
+    """an affect! that assigns integrator.p[i] or integrator.t used to trace without error and the assignment
+    was dropped.  Now it is rejected with a clear message (the kernel's affect functions take p as const)."""
+    from b200ens import codegen
+
+    def cond(u, t, integrator):
+        return u[0] - integrator.p[1]           # reading p is fine
+
+    def dose(integrator):
+        integrator.p[0] = 2.0                    # parameter switch: cannot be emitted
+
+    def warp(integrator):
+        integrator.t = 0.0
+
+    def fine(integrator):
+        integrator.u[0] = integrator.u[0] + integrator.p[1]
+
+    src = codegen.emit_callback(B.ContinuousCallback(cond, fine), 2, 2)
+    assert "p[1]" in src[0] and "u[0]" in src[1]
+    for bad in (dose, warp):
+        with pytest.raises(NotImplementedError, match="only modify integrator.u"):
+            codegen.emit_callback(B.ContinuousCallback(cond, bad), 2, 2)
+        with pytest.raises(NotImplementedError, match="only modify integrator.u"):
+            codegen.emit_discrete_callback(B.DiscreteCallback(lambda u, t, integrator: u[0] > 1, bad), 2, 2)
+
+
+def test_model_cache_is_keyed_on_the_callback_object(B):
+    """the model cache was keyed on id(callback) without keeping the callback alive, so a fresh callback
+    could inherit the id -- and the compiled kernel -- of a collected one.  The entry now holds strong references and
+    compares identities."""
+    import gc
+
+    import b200ens.api as api
+    from b200ens import workloads as W
+
+    prob = W.lorenz_problem(np.float64)
+    seen = set()
+    for k in range(4):
+        thr = 10.0 + k
+        cb = B.ContinuousCallback(lambda u, t, integ, thr=thr: u[0] - thr, lambda integ: None)
+        m = B.build_model(prob, B.Tsit5(), cb)
+        assert f"{thr}" in m.sources["condition_src"] or f"{int(thr)}" in m.sources["condition_src"]
+        seen.add(m.sources["condition_src"])
+        entry = [v for v in api._model_cache.values() if v[0] is m][0]
+        assert entry[3] is cb and entry[1] is prob.f
+        del cb, m
+        gc.collect()
+    assert len(seen) == 4
+
+
+def test_on_disk_cubin_cache(B, tmp_path):
+    """b200ens_compile keeps cubins on disk keyed by (source, kernel headers, flags, NVRTC version): a second PROCESS
+    loads instead of compiling.  (config 5's split kernel takes ~15 s to JIT.)"""
+    import os
+    import subprocess
+    import sys
+
+    code = ("import sys, time; sys.path.insert(0, %r); import numpy as np, b200ens as B; from b200ens import workloads as W;"
+            "t = time.time(); m = B.build_model(W.lorenz_problem(np.float64), B.Vern7()); print(time.time() - t, m.info()['regs'])"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, B200ENS_CACHE_DIR=str(tmp_path / "cc"))
+    first = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert first.returncode == 0, first.stderr[-2000:]
+    files = sorted(os.listdir(tmp_path / "cc"))
+    assert any(f.endswith(".cubin") for f in files) and any(f.endswith(".log") for f in files) and not any(".tmp" in f for f in files)
+    second = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert second.returncode == 0, second.stderr[-2000:]
+    t1, r1 = first.stdout.split()[:2]
+    t2, r2 = second.stdout.split()[:2]
+    assert r1 == r2 and sorted(os.listdir(tmp_path / "cc")) == files       # nothing new was compiled
+    assert float(t2) < 0.5, (t1, t2)                                      # loaded, not compiled
+    off = subprocess.run([sys.executable, "-c", code], env=dict(env, B200ENS_CACHE="0", B200ENS_CACHE_DIR=str(tmp_path / "none")),
+                         capture_output=True, text=True)
+    assert off.returncode == 0 and not os.path.exists(tmp_path / "none")

@@ -420,6 +420,11 @@ int nvrtc_compile(b200ens_model* m) {
         }
     }
     B2_NVRTC_OR_FAIL(nv);
+    if (const char* dd = getenv("B200ENS_DUMP_SRC")) {   // tools: write the generated translation unit for offline nvcc / cuobjdump
+        static std::atomic<int> seq{0};
+        const std::string path = std::string(dd) + "/b200ens_model_" + std::to_string(seq.fetch_add(1)) + ".cu";
+        write_file_atomic(path, m->source.data(), m->source.size());
+    }
     const std::string& cdir = cache_dir();
     const std::string cfile = cdir.empty() ? std::string() : cdir + "/" + cache_key(m, fast, nv);
     if (!cfile.empty()) {

@@ -67,7 +67,19 @@
 #define VST(name, val) name[i] = (val)
 #endif
 
+// Coefficients.  Float32: literals, which become 32-bit FFMA / FFMA2 immediates.  Float64: a 64-bit literal cannot be an
+// instruction operand -- ptxas materialises every one with two moves (UMOV / IMAD.MOV: 240 of the 1000 instructions of a
+// Float64 Tsit5 warp-iteration, profiles/README.md round 2), while a `__constant__ double` is a constant-bank operand of
+// the DFMA itself and costs nothing.  Same values, same bits.
+#if B2_F64
+#define B2_CDECL(n) __constant__ double b2c_##n = B2T_##n;
+B2T_FOREACH_TSIT5(B2_CDECL)
+B2T_FOREACH_VERN7(B2_CDECL)
+#undef B2_CDECL
+#define TS(x) (b2c_TSIT5_##x)
+#else
 #define TS(x) ((real)(B2T_TSIT5_##x))
+#endif
 
 struct B2Tsit5 {
     static constexpr int ORDER = 5;
@@ -195,8 +207,13 @@ struct B2Tsit5 {
 };
 #undef TS
 
+#if B2_F64
+#define V7(x) (b2c_VERN7_##x)
+#define V7X(x) (b2c_VERN7_EXTRA_##x)
+#else
 #define V7(x) ((real)(B2T_VERN7_##x))
 #define V7X(x) ((real)(B2T_VERN7_EXTRA_##x))
+#endif
 
 struct B2Vern7 {
     static constexpr int ORDER = 7;

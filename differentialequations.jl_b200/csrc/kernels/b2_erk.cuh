@@ -67,19 +67,11 @@
 #define VST(name, val) name[i] = (val)
 #endif
 
-// Coefficients.  Float32: literals, which become 32-bit FFMA / FFMA2 immediates.  Float64: a 64-bit literal cannot be an
-// instruction operand -- ptxas materialises every one with two moves (UMOV / IMAD.MOV: 240 of the 1000 instructions of a
-// Float64 Tsit5 warp-iteration, profiles/README.md round 2), while a `__constant__ double` is a constant-bank operand of
-// the DFMA itself and costs nothing.  Same values, same bits.
-#if B2_F64
-#define B2_CDECL(n) __constant__ double b2c_##n = B2T_##n;
-B2T_FOREACH_TSIT5(B2_CDECL)
-B2T_FOREACH_VERN7(B2_CDECL)
-#undef B2_CDECL
-#define TS(x) (b2c_TSIT5_##x)
-#else
+// Coefficients are literals: 32-bit FFMA / FFMA2 immediates in Float32; in Float64 ptxas materialises each with two
+// moves (UMOV / IMAD.MOV).  Declaring them `__constant__ double` instead (constant-bank loads, LDCU.128 per pair) was
+// measured in round 2: -5 % static instructions, but no faster (Tsit5 f64 1.443 -> 1.447 ms, Vern7 split 32.0 -> 33.3 ms
+// per 200k: more spills, constant-cache latency on the critical path), so the literals stay.
 #define TS(x) ((real)(B2T_TSIT5_##x))
-#endif
 
 struct B2Tsit5 {
     static constexpr int ORDER = 5;
@@ -207,13 +199,8 @@ struct B2Tsit5 {
 };
 #undef TS
 
-#if B2_F64
-#define V7(x) (b2c_VERN7_##x)
-#define V7X(x) (b2c_VERN7_EXTRA_##x)
-#else
 #define V7(x) ((real)(B2T_VERN7_##x))
 #define V7X(x) ((real)(B2T_VERN7_EXTRA_##x))
-#endif
 
 struct B2Vern7 {
     static constexpr int ORDER = 7;
@@ -224,8 +211,8 @@ struct B2Vern7 {
     __device__ __forceinline__ void bind(real* kbase) {
         (void)kbase;
         B2_KBIND(k1, 0); B2_KBIND(k3, 1); B2_KBIND(k4, 2); B2_KBIND(k5, 3); B2_KBIND(k6, 4); B2_KBIND(k7, 5); B2_KBIND(k8, 6);
-        B2_KBIND(k9, 7); B2_KBIND(k11, 8); B2_KBIND(k12, 9); B2_KBIND(k13, 10); B2_KBIND(k14, 11); B2_KBIND(k15, 12);
-        B2_KBIND(k16, 13);
+        B2_KBIND(k9, 7); B2_KBIND(k11, 8);
+        B2_KBIND(k12, 9); B2_KBIND(k13, 10); B2_KBIND(k14, 11); B2_KBIND(k15, 12); B2_KBIND(k16, 13);
     }
     bool have_extra;
 

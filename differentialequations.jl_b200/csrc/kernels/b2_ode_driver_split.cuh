@@ -57,13 +57,11 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     const bool adaptive = ADAPT < 0 ? (a.adaptive != 0) : (ADAPT != 0);
     const bool save_tstops = TSTOPS < 0 ? (a.save_tstops != 0) : (TSTOPS != 0);
     const real INF = (real)__int_as_float(0x7f800000);
-    real atol[B2_NL], rtol[B2_NL];   // tolerances of the owned components (padded components: any positive value)
-#pragma unroll
-    for (int j = 0; j < B2_NL; j++) {
-        const int c = c0 + j < B2_N ? c0 + j : B2_N - 1;
-        atol[j] = B2_ATOL(a, c);
-        rtol[j] = B2_RTOL(a, c);
-    }
+    // tolerances of the owned components: read from the kernel-argument constant bank with a warp-uniform index where
+    // they are used (not held in 4 * NL registers); padded components take the last real one
+#define B2_TOLIDX(j) ((c0 + (j) < B2_N) ? c0 + (j) : B2_N - 1)
+#define atol_(j) B2_ATOL(a, B2_TOLIDX(j))
+#define rtol_(j) B2_RTOL(a, B2_TOLIDX(j))
 
     Alg alg;
     alg.bind(nullptr);
@@ -72,11 +70,16 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     alg.xc.phase = 0;
     alg.xc.g = g;
     alg.xc.pcol = s_par + lane;
-    real u[B2_NL], p[B2_NPA];
+    real u[B2_NL], p[B2_NPA];   // p: placeholder for the stepper interface (the split RHS reads shared memory); never loaded
 #pragma unroll
     for (int j = 0; j < B2_NL; j++) u[j] = 0;
 #pragma unroll
     for (int j = 0; j < B2_NPA; j++) p[j] = 0;
+    // the parameters of this lane's trajectory, fetched from shared memory where a callback function needs them
+    auto load_params = [&](real (&pe)[B2_NPA]) {
+#pragma unroll
+        for (int i = 0; i < B2_NPA; i++) pe[i] = i < B2_NPARAM ? s_par[i * 32 + lane] : (real)0;
+    };
     {
         real z[B2_NL];
 #pragma unroll
@@ -119,11 +122,12 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                         obase = idx * out_per_traj;
 #pragma unroll
                         for (int j = 0; j < B2_NL; j++) u[j] = (c0 + j < B2_N) ? gu0[idx * B2_N + c0 + j] : (real)0;
-#pragma unroll
-                        for (int i = 0; i < B2_NPARAM; i++) p[i] = gp[idx * B2_NPARAM + i];
+                        // the trajectory's parameters live in shared memory only (read by the out-of-line RHS and, on demand,
+                        // by the callback functions): keeping a register copy would cost 2 * n_param registers for the
+                        // whole loop in a kernel that sits at its register budget
                         if (g == 0) {
 #pragma unroll
-                            for (int i = 0; i < B2_NPARAM; i++) s_par[i * 32 + lane] = p[i];
+                            for (int i = 0; i < B2_NPARAM; i++) s_par[i * 32 + lane] = gp[idx * B2_NPARAM + i];
                         }
                         t = t0;
                         dt = dt_user;
@@ -157,7 +161,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                         real r0[B2_NL], r1[B2_NL], r2[B2_NL], u1[B2_NL], f1[B2_NL];
 #pragma unroll
                         for (int j = 0; j < B2_NL; j++) {
-                            const real sk = b2_fma(b2_abs(u[j]), rtol[j], atol[j]);
+                            const real sk = b2_fma(b2_abs(u[j]), rtol_(j), atol_(j));
                             r0[j] = u[j] / sk;
                             r1[j] = f0[j] / sk;
                         }
@@ -178,7 +182,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                         alg.rhs(f1, u1, p, t0 + dt0);
 #pragma unroll
                         for (int j = 0; j < B2_NL; j++) {
-                            const real sk = b2_fma(b2_abs(u[j]), rtol[j], atol[j]);
+                            const real sk = b2_fma(b2_abs(u[j]), rtol_(j), atol_(j));
                             r2[j] = (f1[j] - f0[j]) / sk;
                         }
                         {
@@ -238,7 +242,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
             float r[B2_NL];
 #pragma unroll
             for (int j = 0; j < B2_NL; j++) {
-                const real sk = b2_fma(b2_max(b2_abs(u[j]), b2_abs(un[j])), rtol[j], atol[j]);
+                const real sk = b2_fma(b2_max(b2_abs(u[j]), b2_abs(un[j])), rtol_(j), atol_(j));
                 r[j] = __fmul_rn((float)ut[j], b2_rcp_nr((float)sk));
             }
             const float* rb = b2_split_publish(alg.xc, r);
@@ -255,7 +259,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                 float r2[B2_NL];
 #pragma unroll
                 for (int j = 0; j < B2_NL; j++) {
-                    const real sk = b2_fma(b2_max(b2_abs(u[j]), b2_abs(un[j])), rtol[j], atol[j]);
+                    const real sk = b2_fma(b2_max(b2_abs(u[j]), b2_abs(un[j])), rtol_(j), atol_(j));
                     r2[j] = (float)(ut[j] / sk);
                 }
                 const float* rb2 = b2_split_publish(alg.xc, r2);
@@ -353,7 +357,8 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
 #pragma unroll
                 for (int k = 0; k < PD; k++) ecc[m][k] = e[(2 + k) * 32];
             }
-            real w[B2_N];
+            real w[B2_N], pe[B2_NPA];
+            load_params(pe);
             auto scatter = [&](const real (&v)[B2_EV_M]) {
                 int m = 0;
 #pragma unroll
@@ -376,7 +381,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                     v[m] = b2_fma(dts, th * pv, eu[m]);
                 }
                 scatter(v);
-                return b2_condition(w, p, b2_fma(th, dts, tprev));
+                return b2_condition(w, pe, b2_fma(th, dts, tprev));
             };
 #endif
             // The search is sequential per lane and only ~1 lane in 10 fires on a given step: it would cost every warp the
@@ -395,18 +400,18 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                         v[m] = b2_fma(dts, th * pv, eu[m]);
                     }
                     scatter(v);
-                    b2_vcondition(gv, w, p, b2_fma(th, dts, tprev));
+                    b2_vcondition(gv, w, pe, b2_fma(th, dts, tprev));
                 };
                 fired = b2_vevent_search(
                     ip, just_fired, ev_last,
                     [&](real* gv) {
                         scatter(eu);
-                        b2_vcondition(gv, w, p, tprev);
+                        b2_vcondition(gv, w, pe, tprev);
                     },
                     vcond_at,
                     [&](real* gv) {
                         scatter(eun);
-                        b2_vcondition(gv, w, p, tnew);
+                        b2_vcondition(gv, w, pe, tnew);
                     },
                     th_end, ev_idx);
 #else
@@ -414,12 +419,12 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                     ip, just_fired,
                     [&]() -> real {
                         scatter(eu);
-                        return b2_condition(w, p, tprev);
+                        return b2_condition(w, pe, tprev);
                     },
                     cond_at,
                     [&]() -> real {
                         scatter(eun);
-                        return b2_condition(w, p, tnew);
+                        return b2_condition(w, pe, tnew);
                     },
                     th_end);
 #endif
@@ -477,10 +482,12 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
             real W[B2_N];
 #pragma unroll
             for (int i = 0; i < B2_N; i++) W[i] = fb[i * 32];
+            real pa[B2_NPA];
+            load_params(pa);
 #ifdef B2_NCOND
-            b2_vaffect(W, p, tnew, ev_idx);   // per lane: the index of the function that fired
+            b2_vaffect(W, pa, tnew, ev_idx);   // per lane: the index of the function that fired
 #else
-            b2_affect(W, p, tnew);
+            b2_affect(W, pa, tnew);
 #endif
             real wn[B2_NL], fnew[B2_NL];
             B2_OWNED(wn, W, g)
@@ -538,3 +545,6 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
         }
     }
 }
+#undef atol_
+#undef rtol_
+#undef B2_TOLIDX

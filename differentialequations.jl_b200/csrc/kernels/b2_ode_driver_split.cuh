@@ -40,7 +40,14 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     __shared__ __align__(16) real s_par[B2_NPA * 32];   // the trajectories' parameters, read by the out-of-line RHS
     __shared__ int s_flag[4];
     const unsigned lane = threadIdx.x & 31u;
-    const int g = threadIdx.x >> 5;
+    // Warp role = which quarter of the components this warp owns (role 0 also talks to the work queue and runs the event
+    // search).  Warp w of every CTA sits on scheduler w % 4, so with role = warp index one scheduler of the SM would run
+    // the heaviest role of EVERY resident CTA while the other three wait at the barriers; rotating the assignment with the
+    // CTA index spreads the roles over the schedulers (B2_ROLE_ROTATE=0: experiments).
+#ifndef B2_ROLE_ROTATE
+#define B2_ROLE_ROTATE 1
+#endif
+    const int g = B2_ROLE_ROTATE ? (int)(((threadIdx.x >> 5) + blockIdx.x) & 3u) : (int)(threadIdx.x >> 5);
     const int c0 = g * B2_NL;
     real* const gout = reinterpret_cast<real*>(a.out_u);
     const real* const gu0 = reinterpret_cast<const real*>(a.u0);

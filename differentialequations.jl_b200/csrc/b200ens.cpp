@@ -891,7 +891,6 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
     // chunk size: keep both pipeline slots under ~1/4 of the device memory and at least a few waves
     long long total = 0;
     for (const auto& r : ranges) total += r.second - r.first;
-    const long long lo = ranges.empty() ? 0 : ranges[0].first;
     const size_t per_traj = (size_t)n * es + (size_t)np * es + out_per_traj + noise_per_traj + 4 + sizeof(b200ens_stats);
     size_t free_b = 0, total_b = 0;
     mark("saveat");
@@ -911,16 +910,19 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
     long long chunk = std::min<long long>(total, 1 << 20);
     const long long mem_cap = (long long)((free_b / 8) / std::max<size_t>(1, per_traj));
     chunk = std::max<long long>(1, std::min(chunk, mem_cap));
+    // A chunk = one kernel launch over `cn` trajectories that sit contiguously in the DEVICE buffers; on the host it is
+    // one or more pieces (the blocks dealt to this device, multi-device solves): every piece is H2D-copied to its offset
+    // in the chunk and D2H-copied straight back to its own place in the caller's arrays.  So a device launches the same
+    // few large kernels whether its share of the ensemble is one range or many interleaved blocks.
+    struct Piece {
+        long long g0, cn, off;   // first global trajectory, count, offset inside the chunk
+    };
+    struct Chunk {
+        long long cn = 0;
+        std::vector<Piece> pieces;
+    };
     std::vector<long long> sched;
-    std::vector<std::pair<long long, long long>> work;   // (first trajectory, count) of every chunk, in launch order
-    if (ranges.size() > 1) {
-        // several blocks (multi-device dealing): one chunk per block, split further only when a block exceeds the cap
-        if (const char* e = getenv("B200ENS_CHUNK")) chunk = std::max<long long>(1, atoll(e));
-        for (const auto& r : ranges)
-            for (long long a0 = r.first; a0 < r.second; a0 += chunk) work.emplace_back(a0, std::min(chunk, r.second - a0));
-        chunk = 0;
-        for (const auto& w : work) chunk = std::max(chunk, w.second);
-    } else if (const char* e = getenv("B200ENS_CHUNK")) {   // fixed size (tests, experiments)
+    if (const char* e = getenv("B200ENS_CHUNK")) {   // fixed size (tests, experiments)
         chunk = std::max<long long>(1, atoll(e));
         for (long long r = total; r > 0; r -= chunk) sched.push_back(std::min(chunk, r));
     } else {
@@ -943,12 +945,24 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
         }
         chunk = *std::max_element(sched.begin(), sched.end());
     }
-    if (work.empty()) {
-        long long a0 = lo;
-        for (size_t i = 0; a0 < lo + total; i++) {
-            const long long cn = std::min<long long>(sched[std::min(i, sched.size() - 1)], lo + total - a0);
-            work.emplace_back(a0, cn);
-            a0 += cn;
+    std::vector<Chunk> work;   // in launch order; the chunk sizes follow `sched` over the concatenation of the ranges
+    {
+        size_t ri = 0;
+        long long rpos = ranges.empty() ? 0 : ranges[0].first;
+        long long left = total;
+        for (size_t i = 0; left > 0; i++) {
+            Chunk c;
+            long long want = std::min<long long>(sched[std::min(i, sched.size() - 1)], left);
+            while (want > 0) {
+                const long long take = std::min(want, ranges[ri].second - rpos);
+                c.pieces.push_back({rpos, take, c.cn});
+                c.cn += take;
+                want -= take;
+                rpos += take;
+                if (rpos == ranges[ri].second && ++ri < ranges.size()) rpos = ranges[ri].first;
+            }
+            left -= c.cn;
+            work.push_back(std::move(c));
         }
     }
 
@@ -974,7 +988,7 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
     const bool stage_out = !(is_pinned(mom ? nullptr : out_u) && is_pinned(retcode) && is_pinned(stats));
     struct Pending {
         bool used = false;
-        long long g0 = 0, cn = 0;
+        const Chunk* ck = nullptr;
     } pend[kMaxSlots];
     int nslots = kMaxSlots;
     if (const char* e = getenv("B200ENS_SLOTS")) nslots = std::max(1, std::min(kMaxSlots, atoi(e)));
@@ -983,12 +997,15 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
     auto collect = [&](Slot& s, const Pending& pd) -> int {
         CU(cudaEventSynchronize(s.ev[3]));
         if (stage_out) {
-            const char* h = s.h_out;
-            if (out_b) par_memcpy(out_u + (size_t)pd.g0 * out_per_traj, h, (size_t)pd.cn * out_b);
-            h += (size_t)pd.cn * out_b;
-            memcpy(retcode + pd.g0, h, (size_t)pd.cn * sizeof(int));
-            h += (size_t)pd.cn * sizeof(int);
-            if (stats) par_memcpy(stats + pd.g0, h, (size_t)pd.cn * sizeof(b200ens_stats));
+            const long long ccn = pd.ck->cn;
+            const char* h_o = s.h_out;
+            const char* h_rc = h_o + (size_t)ccn * out_b;
+            const char* h_st = h_rc + (size_t)ccn * sizeof(int);
+            for (const Piece& pc : pd.ck->pieces) {
+                if (out_b) par_memcpy(out_u + (size_t)pc.g0 * out_per_traj, h_o + (size_t)pc.off * out_b, (size_t)pc.cn * out_b);
+                memcpy(retcode + pc.g0, h_rc + (size_t)pc.off * sizeof(int), (size_t)pc.cn * sizeof(int));
+                if (stats) par_memcpy(stats + pc.g0, h_st + (size_t)pc.off * sizeof(b200ens_stats), (size_t)pc.cn * sizeof(b200ens_stats));
+            }
         }
         float a_ = 0, b_ = 0, c_ = 0;
         CU(cudaEventElapsedTime(&a_, s.ev[0], s.ev[1]));
@@ -999,9 +1016,10 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
         res->d2h += c_;
         return 0;
     };
-    for (const auto& wk : work) {
-        const long long cn = wk.second;
-        const long long g0 = wk.first;  // global index of the chunk's first trajectory
+    for (const Chunk& wk : work) {
+        const long long cn = wk.cn;
+        const long long g0 = wk.pieces[0].g0;  // global index of the chunk's first trajectory (Philox streams: SDE solves are
+                                               // dealt as ONE contiguous range per device, so the chunk is contiguous too)
         Slot& s = d->slot[it % nslots];
         if (pend[it % nslots].used) {
             rc = collect(s, pend[it % nslots]);
@@ -1021,24 +1039,30 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
             CU(cudaMalloc(&s.stats, (size_t)cn * sizeof(b200ens_stats)));
             s.cap_n = (size_t)cn;
         }
-        const char *src_u0 = u0 + (size_t)g0 * n * es, *src_p = np ? p + (size_t)g0 * np * es : nullptr;
-        const char* src_dW = dW ? dW + (size_t)g0 * noise_per_traj : nullptr;
         if (stage_in) {
             const size_t bu = (size_t)cn * n * es, bp = (size_t)cn * np * es, bw = dW ? (size_t)cn * noise_per_traj : 0;
             if ((rc = grow_host(&s.h_in, &s.cap_hin, bu + bp + bw))) return rc;
-            par_memcpy(s.h_in, src_u0, bu);
-            if (bp) par_memcpy(s.h_in + bu, src_p, bp);
-            if (bw) par_memcpy(s.h_in + bu + bp, src_dW, bw);
-            src_u0 = s.h_in;
-            src_p = s.h_in + bu;
-            src_dW = dW ? s.h_in + bu + bp : nullptr;
+            for (const Piece& pc : wk.pieces) {
+                par_memcpy(s.h_in + (size_t)pc.off * n * es, u0 + (size_t)pc.g0 * n * es, (size_t)pc.cn * n * es);
+                if (bp) par_memcpy(s.h_in + bu + (size_t)pc.off * np * es, p + (size_t)pc.g0 * np * es, (size_t)pc.cn * np * es);
+                if (bw) par_memcpy(s.h_in + bu + bp + (size_t)pc.off * noise_per_traj, dW + (size_t)pc.g0 * noise_per_traj, (size_t)pc.cn * noise_per_traj);
+            }
         }
         if (stage_out && (rc = grow_host(&s.h_out, &s.cap_hout, (size_t)cn * (out_b + sizeof(int) + (stats ? sizeof(b200ens_stats) : 0)))))
             return rc;
         CU(cudaEventRecord(s.ev[0], s.stream));
-        CU(cudaMemcpyAsync(s.u0, src_u0, (size_t)cn * n * es, cudaMemcpyHostToDevice, s.stream));
-        if (np) CU(cudaMemcpyAsync(s.p, src_p, (size_t)cn * np * es, cudaMemcpyHostToDevice, s.stream));
-        if (dW) CU(cudaMemcpyAsync(s.dW, src_dW, (size_t)cn * noise_per_traj, cudaMemcpyHostToDevice, s.stream));
+        if (stage_in) {
+            const size_t bu = (size_t)cn * n * es, bp = (size_t)cn * np * es;
+            CU(cudaMemcpyAsync(s.u0, s.h_in, bu, cudaMemcpyHostToDevice, s.stream));
+            if (np) CU(cudaMemcpyAsync(s.p, s.h_in + bu, bp, cudaMemcpyHostToDevice, s.stream));
+            if (dW) CU(cudaMemcpyAsync(s.dW, s.h_in + bu + bp, (size_t)cn * noise_per_traj, cudaMemcpyHostToDevice, s.stream));
+        } else {
+            for (const Piece& pc : wk.pieces) {
+                CU(cudaMemcpyAsync((char*)s.u0 + (size_t)pc.off * n * es, u0 + (size_t)pc.g0 * n * es, (size_t)pc.cn * n * es, cudaMemcpyHostToDevice, s.stream));
+                if (np) CU(cudaMemcpyAsync((char*)s.p + (size_t)pc.off * np * es, p + (size_t)pc.g0 * np * es, (size_t)pc.cn * np * es, cudaMemcpyHostToDevice, s.stream));
+                if (dW) CU(cudaMemcpyAsync((char*)s.dW + (size_t)pc.off * noise_per_traj, dW + (size_t)pc.g0 * noise_per_traj, (size_t)pc.cn * noise_per_traj, cudaMemcpyHostToDevice, s.stream));
+            }
+        }
         B2Args a = base;
         a.u0 = s.u0;
         a.p = s.p;
@@ -1082,21 +1106,26 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
             CU(cudaLaunchKernel((const void*)mom_kernel, dim3(gx, gy), dim3(128), margs, 0, s.stream));
             res->launches++;
         }
-        {
-            char* dst_out = stage_out ? s.h_out : (out_u ? out_u + (size_t)g0 * out_per_traj : nullptr);
-            char* dst_rc = stage_out ? s.h_out + (size_t)cn * out_b : (char*)(retcode + g0);
-            char* dst_st = stage_out ? dst_rc + (size_t)cn * sizeof(int) : (char*)(stats ? stats + g0 : nullptr);
-            if (out_b) CU(cudaMemcpyAsync(dst_out, s.out, (size_t)cn * out_per_traj, cudaMemcpyDeviceToHost, s.stream));
+        if (stage_out) {
+            char* dst_rc = s.h_out + (size_t)cn * out_b;
+            char* dst_st = dst_rc + (size_t)cn * sizeof(int);
+            if (out_b) CU(cudaMemcpyAsync(s.h_out, s.out, (size_t)cn * out_per_traj, cudaMemcpyDeviceToHost, s.stream));
             CU(cudaMemcpyAsync(dst_rc, s.rc, (size_t)cn * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
             if (stats) CU(cudaMemcpyAsync(dst_st, s.stats, (size_t)cn * sizeof(b200ens_stats), cudaMemcpyDeviceToHost, s.stream));
-            if (every)   // step times straight into the caller's [N][capacity] array
-                CU(cudaMemcpyAsync(out_t_every + (size_t)g0 * n_save * es, s.every_t, (size_t)cn * n_save * es, cudaMemcpyDeviceToHost, s.stream));
+        } else {
+            for (const Piece& pc : wk.pieces) {
+                if (out_b) CU(cudaMemcpyAsync(out_u + (size_t)pc.g0 * out_per_traj, (char*)s.out + (size_t)pc.off * out_per_traj, (size_t)pc.cn * out_per_traj, cudaMemcpyDeviceToHost, s.stream));
+                CU(cudaMemcpyAsync(retcode + pc.g0, s.rc + pc.off, (size_t)pc.cn * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+                if (stats) CU(cudaMemcpyAsync(stats + pc.g0, s.stats + pc.off, (size_t)pc.cn * sizeof(b200ens_stats), cudaMemcpyDeviceToHost, s.stream));
+            }
         }
+        if (every)   // step times straight into the caller's [N][capacity] array
+            for (const Piece& pc : wk.pieces)
+                CU(cudaMemcpyAsync(out_t_every + (size_t)pc.g0 * n_save * es, (char*)s.every_t + (size_t)pc.off * n_save * es, (size_t)pc.cn * n_save * es, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaEventRecord(s.ev[3], s.stream));
         mark("enq", cn);
         pend[it % nslots].used = true;
-        pend[it % nslots].g0 = g0;
-        pend[it % nslots].cn = cn;
+        pend[it % nslots].ck = &wk;
         res->launches++;
         it++;
     }
@@ -1226,8 +1255,7 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     const char* force_s = getenv("B200ENS_SPLIT");
     const bool split_off = (d->flags & B200ENS_MODEL_NOSPLIT) || (force_s && atoi(force_s) == 0);
     const bool split_on = (d->flags & B200ENS_MODEL_SPLIT) || (force_s && atoi(force_s) == 1);
-    const bool vector_cb = d->condition_src && strstr(d->condition_src, "B2_NCOND") != nullptr;   // one-thread kernels only
-    const bool split_eligible = nvec && !d->dcondition_src && !vector_cb && d->n_state >= 4 && !flag_k &&
+    const bool split_eligible = nvec && !d->dcondition_src && d->n_state >= 4 && !flag_k &&   // (Continuous and VectorContinuous callbacks: both kernels)
                                 !(force_k && atoi(force_k) == 1);
     const bool surely_spills = d->alg == B200ENS_VERN7 && nvec * d->n_state * (d->dtype == B200ENS_F64 ? 2 : 1) > 200;   // + ~55 registers for everything else > 255
     if (try_regs && split_eligible && !split_off && (split_on || surely_spills) && try_split(0, false, split_on)) {
@@ -1382,8 +1410,8 @@ static int solve_host(b200ens_model* m, const b200ens_opts* o, int64_t N, const 
     // D2H-copied straight into its place in the caller's arrays -- the gather is still implicit, there is no collective
     // -- and every trajectory is computed exactly as before (Philox streams are keyed by the global index).
     int k_blocks = o->shard_blocks > 0 ? o->shard_blocks : 8;
-    if (G == 1) k_blocks = 1;
-    while (k_blocks > 1 && N / ((long long)G * k_blocks) < 4096) k_blocks /= 2;   // blocks stay large enough for 50+ GB/s copies
+    if (G == 1 || is_sde(m->alg)) k_blocks = 1;   // SDE steppers: uniform work, and Philox streams are keyed by consecutive indices
+    while (k_blocks > 1 && N / ((long long)G * k_blocks) < 8192) k_blocks /= 2;   // pieces stay large enough for efficient copies
     std::vector<Ranges> deal(G);
     {
         const long long nb = (long long)G * k_blocks;

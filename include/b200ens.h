@@ -56,7 +56,7 @@ enum b200ens_error {
    steppers now pack component PAIRS of one trajectory into FFMA2/FMUL2, which is faster and bit-identical) */
 #define B200ENS_MODEL_KSMEM 4u     /* force ERK stage vectors into shared memory (default: automatic when the register variant spills > 4 KB) */
 #define B200ENS_MODEL_SPLIT 8u     /* force the split kernel (one trajectory per lane of a 4-warp CTA, components split over the
-                                      warps; Tsit5 / Vern7 with at most a scalar ContinuousCallback; default: automatic when
+                                      warps; Tsit5 / Vern7, ContinuousCallback or VectorContinuousCallback but no DiscreteCallback; default: automatic when
                                       the one-thread variant spills > 1 KB (Vern7) / 4 KB (Tsit5)) */
 #define B200ENS_MODEL_NOSPLIT 16u  /* never use the split kernel */
 #define B200ENS_MODEL_SDE_ADAPTIVE 32u /* SRIW1 / SOSRA only: compile the ADAPTIVE stepper (embedded error estimate, PI controller

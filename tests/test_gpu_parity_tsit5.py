@@ -173,7 +173,7 @@ def test_block_dealing_matches_single_device(B, gpu_lib, monkeypatch, shards, bl
 
 def test_block_dealing_balances_an_ordered_sweep(B, gpu_lib):
     """On >= 2 real GPUs: the ordered rho-sweep (work per trajectory grows ~10x along it) with the boustrophedon deal keeps
-    the per-device kernel times within 5 % of each other; contiguous ranges (shard_blocks=1) do not."""
+    the per-device kernel times within 10 % of each other; contiguous ranges (shard_blocks=1) do not."""
     from b200ens import workloads as W
 
     ndev = gpu_lib.lib().b200ens_device_count()
@@ -189,7 +189,7 @@ def test_block_dealing_balances_an_ordered_sweep(B, gpu_lib):
     bal1 = contiguous.timing["kernel_ms_min"] / contiguous.timing["kernel_ms"]
     print(f"per-device kernel time min/max on {ndev} GPUs: dealt {bal:.3f} ({dealt.timing['kernel_ms']:.2f} ms), "
           f"contiguous {bal1:.3f} ({contiguous.timing['kernel_ms']:.2f} ms)")
-    assert bal > 0.95 and bal1 < 0.9
+    assert bal > 0.9 and bal1 < 0.7
     assert np.array_equal(dealt.u_array, contiguous.u_array) and np.array_equal(dealt.stats, contiguous.stats)
 
 

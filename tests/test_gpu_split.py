@@ -76,3 +76,50 @@ def test_split_state_count_not_divisible_by_four(B, gpu_lib):
     cb = B.ContinuousCallback(lambda u, t, integrator: u[5] - 0.4, lambda integrator: integrator.u.__setitem__(5, integrator.u[5] + 0.3))
     for alg in (B.Tsit5(), B.Vern7()):
         _same(*_pair(B, prob, alg, u0, p, saveat=np.linspace(0.0, 5.0, 26), dt=0.01, abstol=1e-9, reltol=1e-9, callback=cb))
+
+
+def test_split_vector_continuous_callback_bit_identical(B, gpu_lib):
+    """VectorContinuousCallback (qa.jl:124) in the split kernel: the event search is the one shared with the one-thread
+    kernel (kernels/b2_control.cuh), so event counts, per-index affect!, per-index terminate! and every saved value must be
+    bit-identical between the two kernels -- on the 16-species network (two thresholds on different species) and on a
+    system whose size is not divisible by four."""
+    from b200ens import workloads as W
+
+    N = 500
+    u0, p = W.net16_params(N)
+
+    def vcond(out, u, t, integrator):
+        out[0] = u[0] - integrator.p[4]
+        out[1] = u[5] - 0.02
+
+    def vaffect(integrator, idx):
+        if idx == 1:
+            integrator.u[0] = integrator.u[0] + integrator.p[5]
+        else:
+            integrator.u[5] = integrator.u[5] * 0.5
+
+    cb = B.VectorContinuousCallback(vcond, vaffect, 2)
+    a, b = _pair(B, W.net16_problem(), B.Vern7(), u0, p, saveat=np.linspace(0.0, 10.0, 21), dt=0.01, abstol=1e-8, reltol=1e-8,
+                 callback=cb)
+    assert np.all(a.retcodes == 1) and a.stats[:, 3].max() >= 2
+    _same(a, b)
+
+    def vaffect_term(integrator, idx):
+        if idx == 1:
+            integrator.u[0] = integrator.u[0] + integrator.p[5]
+        else:
+            B.terminate_b(integrator)
+
+    cbt = B.VectorContinuousCallback(vcond, vaffect_term, 2)
+    x, y = _pair(B, W.net16_problem(), B.Tsit5(), u0, p, saveat=np.linspace(0.0, 10.0, 21), dt=0.01, abstol=1e-8, reltol=1e-8,
+                 callback=cbt)
+    assert np.any(x.retcodes == 2)
+    _same(x, y)
+    # a CallbackSet of two ContinuousCallbacks is lowered to one vector callback by the host mirror
+    rng = np.random.default_rng(12)
+    u6 = rng.random((257, 6))
+    p6 = np.stack([1.0 + rng.random(257), 0.5 + rng.random(257), 0.1 * rng.random(257)], axis=1)
+    prob6 = B.ODEProblem(_ring6, np.ones(6), (0.0, 5.0), np.array([1.0, 1.0, 0.1]))
+    cs = B.CallbackSet(B.ContinuousCallback(lambda u, t, integrator: u[5] - 0.4, lambda integrator: integrator.u.__setitem__(5, integrator.u[5] + 0.3)),
+                       B.ContinuousCallback(lambda u, t, integrator: u[1] - 0.6, lambda integrator: integrator.u.__setitem__(1, integrator.u[1] - 0.2)))
+    _same(*_pair(B, prob6, B.Vern7(), u6, p6, saveat=np.linspace(0.0, 5.0, 26), dt=0.01, abstol=1e-9, reltol=1e-9, callback=cs))

@@ -9,6 +9,10 @@ for pth in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tools")):
         sys.path.insert(0, pth)
 
 
+# the test suite JIT-compiles ~60 models: keep their cubins out of the in-tree cache that ships with the library
+os.environ.setdefault("B200ENS_CACHE_DIR", os.path.join(os.environ.get("TMPDIR", "/tmp"), "b200ens_test_cubin_cache"))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -38,9 +38,10 @@ __device__ __forceinline__ void b2_normals(unsigned long long seed, unsigned lon
     const double u1 = ((double)(a >> 11) + 0.5) * 1.1102230246251565404e-16;
     const double u2 = ((double)(b >> 11) + 0.5) * 1.1102230246251565404e-16;
     const double rad = sqrt(-2.0 * log(u1));
-    const double ang = B2_TWO_PI * u2;
-    z[0] = rad * cos(ang);
-    z[1] = rad * sin(ang);
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);   // angle 2 pi u2: exact argument (2 u2), one shared range reduction
+    z[0] = rad * cs;
+    z[1] = rad * sn;
 }
 #else
 #define B2_NORMALS_PER_CALL 4
@@ -55,9 +56,11 @@ __device__ __forceinline__ void b2_normals(unsigned long long seed, unsigned lon
         const float u1 = ((float)(w[2 * h] >> 8) + 0.5f) * 5.9604644775390625e-8f;
         const float u2 = ((float)(w[2 * h + 1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
         const float rad = sqrtf(-2.0f * logf(u1));
-        const float ang = (float)B2_TWO_PI * u2;
-        z[2 * h] = rad * cosf(ang);
-        z[2 * h + 1] = rad * sinf(ang);
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);   // angle 2 pi u2 with an exact argument and ONE range reduction: ~30 issue slots
+                                          // fewer per pair than sinf + cosf of a rounded 2 pi u2, and closer to the true value
+        z[2 * h] = rad * cs;
+        z[2 * h + 1] = rad * sn;
     }
 }
 #endif

@@ -137,9 +137,11 @@ void orc_normals_f32(uint64_t seed, uint64_t traj, uint64_t block, float z[4]) {
         const float u1 = ((float)(r[2 * h] >> 8) + 0.5f) * 5.9604644775390625e-8f;
         const float u2 = ((float)(r[2 * h + 1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
         const float rad = sqrtf(-2.0f * logf(u1));
-        const float ang = (float)TWO_PI * u2;
-        z[2 * h] = rad * cosf(ang);
-        z[2 * h + 1] = rad * sinf(ang);
+        /* cos / sin of the angle 2 pi u2 correctly rounded to Float32 (evaluated in double): the kernels use
+         * sincospif(2 u2), which is accurate to ~1 ulp of the same true value */
+        const double ang = TWO_PI * (double)u2;
+        z[2 * h] = rad * (float)cos(ang);
+        z[2 * h + 1] = rad * (float)sin(ang);
     }
 }
 void orc_normals_f64(uint64_t seed, uint64_t traj, uint64_t block, double z[2]) {

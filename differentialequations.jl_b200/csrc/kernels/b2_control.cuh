@@ -89,14 +89,12 @@ __device__ __forceinline__ real b2_itp_left(real lo, real hi, real glo, real ghi
 __device__ __forceinline__ bool b2_sign_change(real gprev, real g) { return (gprev < 0 && g >= 0) || (gprev > 0 && g <= 0); }
 
 // ---- scalar ContinuousCallback (A.8): sign change over interp_points samples of the dense output, then the ITP
-// root-find.  cond_start(): the event function at (u, tprev); cond_at(theta): on the interpolant; the sample at mm == ip is
-// the event function at (u_new, tnew).  After an event at the end of the previous step the reference sign is taken at theta = 0.01
+// root-find.  cond_start(): the event function at (u, tprev); cond_at(theta): on the interpolant; cond_end(): at
+// (u_new, tnew).  After an event at the end of the previous step the reference sign is taken at theta = 0.01
 // (repeat_nudge).  Returns true and the event's theta when the event fires inside this step.
-// cond_sample(mm, theta): the event function at sample mm of interp_points (theta = mm/ip; mm == ip: the step end) -- the
-// one-thread driver evaluates it on the spot, the split driver looks up the value another warp of the CTA computed.
-template <class CondStart, class CondAt, class CondSample>
+template <class CondStart, class CondAt, class CondEnd>
 __device__ __forceinline__ bool b2_event_search(const int ip, const bool just_fired, CondStart&& cond_start, CondAt&& cond_at,
-                                                CondSample&& cond_sample, real& th_end) {
+                                                CondEnd&& cond_end, real& th_end) {
     real gprev, lo = 0, hi = 0, glo, ghi = 0;
     bool fired = false;
     if (just_fired) {
@@ -108,7 +106,7 @@ __device__ __forceinline__ bool b2_event_search(const int ip, const bool just_fi
     glo = gprev;
     for (int mm = 1; mm <= ip && !fired; mm++) {
         const real th = (mm == ip) ? (real)1 : (real)mm / (real)ip;
-        const real g = cond_sample(mm, th);
+        const real g = (mm == ip) ? cond_end() : cond_at(th);
         if (b2_sign_change(gprev, g)) {
             fired = true;
             hi = th;

@@ -296,12 +296,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                                 fill_w(th);
                                 return b2_condition(w, p, b2_fma(th, dts, tprev));
                             },
-                            [&](int mm, real th) -> real {
-                                if (mm == ip) return b2_condition(un, p, tnew);
-                                fill_w(th);
-                                return b2_condition(w, p, b2_fma(th, dts, tprev));
-                            },
-                            th_end);
+                            [&]() -> real { return b2_condition(un, p, tnew); }, th_end);
 #endif   // B2_NCOND
                         if (fired) tnew = b2_fma(th_end, dts, tprev);
 #endif

@@ -102,10 +102,6 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     __shared__ __align__(16) real s_ev[B2_EV_M * (Alg::DEG + 2) * 32];
     __shared__ real s_evres[32];
     __shared__ int s_evidx[32];
-#ifndef B2_NCOND
-#define B2_EV_MAXIP 16
-    __shared__ real s_evs[B2_EV_MAXIP * 32];   // the interp_points samples of the scalar event function, [sample][lane]
-#endif
     bool just_fired = false;
     int ev_last = 0;   // VectorContinuousCallback: index of the function that fired the last event
     const int ip = a.interp_points;
@@ -398,26 +394,6 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
             // The search is sequential per lane and only ~1 lane in 10 fires on a given step: it would cost every warp the
             // full ~20 root-find iterations at 3/32 lane efficiency (ncu: 27 % of all issued instructions when
             // replicated).  Warp 0 searches alone and publishes theta of the event (or -1) for the other three.
-#ifndef B2_NCOND
-            // The interp_points samples of the scalar event function are independent of each other: the four warps
-            // evaluate them CONCURRENTLY (warp role g takes samples g+1, g+5, g+9, ...; every warp holds the same
-            // coefficient data) and leave the values in shared memory; the search in the role-0 warp then only looks them
-            // up.  Same values as evaluating them one after the other, ~7 evaluations off the CTA's critical path.
-            const bool coop = ip <= B2_EV_MAXIP;
-            if (coop) {
-                for (int mm = g + 1; mm <= ip; mm += B2_SPLIT_G) {
-                    real gv;
-                    if (mm == ip) {
-                        scatter(eun);
-                        gv = b2_condition(w, pe, tnew);
-                    } else {
-                        gv = cond_at((real)mm / (real)ip);
-                    }
-                    s_evs[(mm - 1) * 32 + lane] = gv;
-                }
-                __syncthreads();
-            }
-#endif
             if (g == 0 && accepted) {
 #ifdef B2_NCOND
                 // VectorContinuousCallback (qa.jl:124): the search of b2_control.cuh, shared with the one-thread driver
@@ -453,13 +429,9 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                         return b2_condition(w, pe, tprev);
                     },
                     cond_at,
-                    [&](int mm, real th) -> real {
-                        if (coop) return s_evs[(mm - 1) * 32 + lane];
-                        if (mm == ip) {
-                            scatter(eun);
-                            return b2_condition(w, pe, tnew);
-                        }
-                        return cond_at(th);
+                    [&]() -> real {
+                        scatter(eun);
+                        return b2_condition(w, pe, tnew);
                     },
                     th_end);
 #endif

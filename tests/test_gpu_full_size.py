@@ -57,3 +57,62 @@ def test_10M_trajectories_properties_and_sampled_bit_parity(B, gpu_lib, oracle):
     sl = slice(0, N, 16)
     ref, rrc, rst = oracle.solve("lorenz", "Tsit5", u0[sl], p[sl], (0.0, 10.0), SAVEAT, 0.1, dtype=np.float32)
     assert np.array_equal(out[sl], ref) and np.array_equal(st[sl, :3], rst[:, :3])
+
+
+def test_config3_robertson_rodas5p_1M_bit_identical(B, gpu_lib, oracle):
+    """BASELINE config 3 at its full size: 1M Robertson trajectories, Rodas5P with the analytic Jacobian, abstol 1e-8,
+    reltol 1e-6, t in [0, 1e5], saveat 10^(-5..5) -- every saved value, retcode and step count against the oracle."""
+    from b200ens import workloads as W
+
+    N = 1_000_000
+    u0, p = W.robertson_params(N)
+    eprob = B.EnsembleProblem(W.robertson_problem(), u0s=u0, ps=p)
+    sol = B.solve(eprob, B.Rodas5P(), B.EnsembleB200(), trajectories=N, saveat=W.ROBERTSON_SAVEAT, dt=1e-6, abstol=1e-8, reltol=1e-6)
+    ref, rc, st = oracle.solve("robertson", "Rodas5P", u0, p, (0.0, 1e5), W.ROBERTSON_SAVEAT, 1e-6, abstol=1e-8, reltol=1e-6)
+    assert np.array_equal(sol.retcodes, rc) and np.all(rc == 1)
+    assert np.array_equal(sol.stats[:, :3], st[:, :3])
+    assert np.array_equal(sol.u_array, ref)
+    assert np.abs(sol.u_array.sum(axis=2) - 1.0).max() < 1e-6      # the Robertson invariant y1 + y2 + y3 = 1 on all 11M saved states
+
+
+def test_config4_gbm_em_10M_device_philox(B, gpu_lib, oracle):
+    """BASELINE config 4 at its full size: 10M GBM paths, Euler-Maruyama, dt = 1/256, Philox4x32-10 on the device.  Three
+    200k-path windows (same global trajectory indices = same Philox streams) against the oracle to the ulp-level tolerance of
+    the Box-Muller functions, and the law of the whole ensemble."""
+    from b200ens import workloads as W
+
+    N = 10_000_000
+    u0, p = W.gbm_params(N, dtype=np.float32)
+    eprob = B.EnsembleProblem(W.gbm_problem(np.float32), u0s=u0, ps=p)
+    sol = B.solve(eprob, B.EM(), B.EnsembleB200(), trajectories=N, saveat=[1.0], dt=1 / 256, seed=7)
+    assert np.all(sol.retcodes == 1) and np.all(np.isfinite(sol.u_array))
+    mu = p[:, 0].astype(np.float64)
+    assert abs(np.mean(sol.u_array[:, 0, 0] / np.exp(mu)) - 1.0) < 2e-3           # E[u(1)] = exp(mu): 10M paths -> ~5e-4
+    # three windows of 200k paths (start, middle, end of the ensemble; the oracle gets the window's global index base, so it
+    # draws the same Philox streams)
+    worst = 0.0
+    for lo in (0, 4_900_000, N - 200_000):
+        hi = lo + 200_000
+        ref, rc, _ = oracle.solve("gbm", "EM", u0[lo:hi], p[lo:hi], (0.0, 1.0), [1.0], 1 / 256, dtype=np.float32, seed=7, adaptive=False,
+                                  traj_offset=lo)
+        a, b = sol.u_array[lo:hi, 0, 0].astype(np.float64), ref[:, 0, 0].astype(np.float64)
+        worst = max(worst, float((np.abs(a - b) / np.abs(b)).max()))
+    assert worst < 5e-4, worst
+
+
+def test_config5_net16_vern7_event_1M_bit_identical(B, gpu_lib, oracle):
+    """BASELINE config 5 at its full trajectory count: 1M trajectories of the 16-species network, Vern7, abstol = reltol =
+    1e-8, the bolus ContinuousCallback (~17 events per trajectory), split kernel -- saved values (11 save points to keep the
+    comparison arrays at 1.4 GB), retcodes, step / RHS / event counts bit for bit against the oracle."""
+    from b200ens import workloads as W
+
+    N = 1_000_000
+    u0, p = W.net16_params(N)
+    sv = np.linspace(0.0, 10.0, 11)
+    eprob = B.EnsembleProblem(W.net16_problem(), u0s=u0, ps=p)
+    sol = B.solve(eprob, B.Vern7(), B.EnsembleB200(), trajectories=N, saveat=sv, dt=0.01, abstol=1e-8, reltol=1e-8, callback=W.net16_callback())
+    ref, rc, st = oracle.solve("net16", "Vern7", u0, p, (0.0, 10.0), sv, 0.01, abstol=1e-8, reltol=1e-8, event=True)
+    assert np.array_equal(sol.retcodes, rc) and np.all(rc == 1)
+    assert np.array_equal(sol.stats, st)                    # naccept, nreject, nf, nevents
+    assert np.array_equal(sol.u_array, ref)
+    assert st[:, 3].mean() > 10

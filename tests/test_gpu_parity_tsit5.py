@@ -172,24 +172,37 @@ def test_block_dealing_matches_single_device(B, gpu_lib, monkeypatch, shards, bl
 
 
 def test_block_dealing_balances_an_ordered_sweep(B, gpu_lib):
-    """On >= 2 real GPUs: the ordered rho-sweep (work per trajectory grows ~10x along it) with the boustrophedon deal keeps
-    the per-device kernel times within 10 % of each other; contiguous ranges (shard_blocks=1) do not."""
+    """On >= 2 real GPUs, COMPUTE-bound shape (one save point, so the device-to-host copy does not hide the kernels): the
+    ordered rho-sweep (work per trajectory grows ~10x along it) with contiguous ranges (shard_blocks=1) leaves the first GPU
+    idle while the last integrates the chaotic end; the boustrophedon deal gives every device the same mix.  Measured on
+    the wall clock of the whole call (the per-chunk kernel events overlap on a device and are only indicative)."""
+    import time
+
     from b200ens import workloads as W
 
     ndev = gpu_lib.lib().b200ens_device_count()
     if ndev < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    N = 1_000_000
+    N = 4_000_000
     u0, p = W.lorenz_params(N, "ordered", dtype=np.float32)
     devs = list(range(ndev))
-    _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1, devices=devs)   # warm-up: JIT, buffers
-    dealt = _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1, devices=devs)
-    contiguous = _solve_gpu(B, np.float32, u0, p, SAVEAT, 0.1, devices=devs, shard_blocks=1)
-    bal = dealt.timing["kernel_ms_min"] / dealt.timing["kernel_ms"]
-    bal1 = contiguous.timing["kernel_ms_min"] / contiguous.timing["kernel_ms"]
-    print(f"per-device kernel time min/max on {ndev} GPUs: dealt {bal:.3f} ({dealt.timing['kernel_ms']:.2f} ms), "
-          f"contiguous {bal1:.3f} ({contiguous.timing['kernel_ms']:.2f} ms)")
-    assert bal > 0.9 and bal1 < 0.7
+    sv = [10.0]
+
+    def run(blocks):
+        best, sol = 1e9, None
+        for _ in range(3):
+            t = time.perf_counter()
+            sol = _solve_gpu(B, np.float32, u0, p, sv, 0.1, devices=devs, shard_blocks=blocks)
+            best = min(best, time.perf_counter() - t)
+        return best, sol
+
+    run(0)   # warm-up: JIT, buffers, pinning of the bounce buffers
+    t_dealt, dealt = run(0)
+    t_contig, contiguous = run(1)
+    print(f"{ndev} GPUs, 4M ordered Lorenz trajectories, one save point: dealt {t_dealt * 1e3:.2f} ms, contiguous {t_contig * 1e3:.2f} ms; "
+          f"kernel min/max dealt {dealt.timing['kernel_ms_min'] / dealt.timing['kernel_ms']:.2f}, "
+          f"contiguous {contiguous.timing['kernel_ms_min'] / contiguous.timing['kernel_ms']:.2f}")
+    assert t_dealt < 0.9 * t_contig
     assert np.array_equal(dealt.u_array, contiguous.u_array) and np.array_equal(dealt.stats, contiguous.stats)
 
 

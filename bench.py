@@ -471,6 +471,31 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_val = world * N * a.steps / e2e_s
+    # ---- the same ensemble when the caller wants per-save-point statistics instead of the trajectories
+    # (b200ens_solve_moments: EnsembleSummary / timestep_meanvar reduced on the device): 4 B of retcode per trajectory and
+    # 2 x 33 doubles come back instead of 132 B per trajectory, so this path is NOT bound by the host link
+    e2e_summary = None
+    try:
+        for _ in range(2):
+            model.solve_moments(o, u0_pin, p_pin, SAVEAT, rc=rc_pin)
+        if world > 1:
+            dist.barrier()
+        ts0 = time.perf_counter()
+        for _ in range(a.steps):
+            s_sum, s_sq, s_cnt, _, _ = model.solve_moments(o, u0_pin, p_pin, SAVEAT, rc=rc_pin)
+        es_s = time.perf_counter() - ts0
+        if world > 1:
+            tt = torch.tensor([es_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            es_s = float(tt.item())
+        mean_dev = s_sum / max(s_cnt, 1)
+        mean_host = out_pin.astype(np.float64).mean(axis=0)
+        e2e_summary = {"value": world * N * a.steps / es_s, "unit": "trajectories/s", "ms_per_step": es_s / a.steps * 1e3,
+                       "h2d_bytes_per_step": int(u0_h.nbytes + p_h.nbytes), "d2h_bytes_per_step": int(4 * N + 2 * n_save * 3 * 8 + 8),
+                       "count": int(s_cnt), "max_abs_mean_diff_vs_full_output": float(np.abs(mean_dev - mean_host).max())}
+    except Exception as e:  # noqa: BLE001
+        e2e_summary = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
     # ---- the host-link ceiling of THIS box at this GPU count: the same bytes, copies only (no kernel), all ranks at once.
     # e2e cannot beat it; `frac_of_host_ceiling` says how close the pipelined solve gets.
     host_ceiling = None
@@ -534,6 +559,7 @@ def main():
             "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "trajectories/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / a.steps * 1e3, "matches_device_leg": same, "host_ceiling": host_ceiling,
+                    "summary_path": e2e_summary,
                     "outside_the_timed_region": {"prob_func_vectorised_ms": prob_func_ms, "model_build_ms": jit_ms,
                                                  "note": "prob_func as a parameter matrix (numpy, once per ensemble) and the one-time trace + NVRTC JIT (cubins are cached on disk)"},
                     "frac_of_host_ceiling": (e2e_val / host_ceiling["traj_per_s_at_ceiling"]) if host_ceiling and "traj_per_s_at_ceiling" in host_ceiling else None},

@@ -216,7 +216,7 @@ class Model:
         return out, times, rc, stats, tm
 
     # ---- ensemble moments without shipping trajectories to the host (b200ens_solve_moments)
-    def solve_moments(self, opts, u0, p, saveat, dW=None):
+    def solve_moments(self, opts, u0, p, saveat, dW=None, rc=None):
         N = u0.shape[0]
         dt = self.dtype
         u0 = np.ascontiguousarray(u0, dtype=dt)
@@ -226,7 +226,8 @@ class Model:
         s = np.zeros((n_save, self.n_state))
         q = np.zeros((n_save, self.n_state))
         cnt = C.c_int64(0)
-        rc = np.zeros(N, dtype=np.int32)
+        if rc is None:
+            rc = np.zeros(N, dtype=np.int32)
         if dW is not None:
             dW = np.ascontiguousarray(dW, dtype=dt)
         tm = Timing()

@@ -449,7 +449,7 @@ int nvrtc_compile(b200ens_model* m) {
     if (r != NVRTC_SUCCESS) return fail(B200ENS_E_COMPILE, "nvrtcCreateProgram: %s", nv->GetErrorString(r));
     std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--ptxas-options=-v",
                                      fast ? "--fmad=true" : "--fmad=false", "--prec-div=true", "--prec-sqrt=true",
-                                     "--ftz=false"};
+                                     "--ftz=false", "-default-device"};   // -default-device: generic lambdas inside device code (b2_sde.cuh)
     r = nv->CompileProgram(prog, (int)opts.size(), opts.data());
     size_t logn = 0;
     nv->GetProgramLogSize(prog, &logn);
@@ -749,8 +749,36 @@ int launch(b200ens_model* m, const LaunchPlan& lp, const B2Args& a, cudaStream_t
 
 // ---------------------------------------------------------------- expected-work ordering (kernels/b2_work.cuh)
 constexpr int kWorkBuckets = 1024, kWorkTile = 4;
-constexpr size_t kWorkHead = 16 + 2 * (size_t)kWorkBuckets * sizeof(unsigned);   // counter | histogram | cursors
-size_t work_scratch_bytes(long long N) { return kWorkHead + (size_t)N * (sizeof(unsigned) + sizeof(unsigned short)) + 16; }
+// The order is established inside windows of consecutive trajectories (kernels/b2_work.cuh: keeps the output rows that
+// are being written at any moment within L2's reach, so fewer sectors are evicted half-written).  Measured, 1M Lorenz
+// trajectories (profiles/README.md): every window boundary costs lane coherence (64k windows: +9 % time), the DRAM
+// traffic falls from 2.1x to 1.3-1.45x the algorithmic bytes; a window whose output footprint is ~70 MB is as fast as
+// the global sort or slightly faster (f32 512k: 0.795 vs 0.804 ms, f64 256k: 1.426 vs 1.446 ms).  Rows that are whole
+// 32-byte sectors (n_state * sizeof(T) a multiple of 32, e.g. the 16-species network) are never half-written: one
+// global sort (windows cost config 5 10 %).  B200ENS_WORK_WINDOW overrides (0 = one global sort).
+long long work_window(long long N, size_t out_bytes_per_traj, size_t row_bytes, int requested) {
+    const long long tile = (long long)kWorkBuckets * kWorkTile;
+    long long w = 1 << 18;
+    static const char* e = getenv("B200ENS_WORK_WINDOW");
+    if (requested > 1) {   // opts.work_order > 1: the caller's window
+        w = requested;
+    } else if (e) {
+        w = atoll(e);
+        if (w <= 0) w = N;
+    } else if (row_bytes % 32 == 0 || out_bytes_per_traj == 0) {
+        w = N;
+    } else {
+        while (w < (1ll << 24) && (size_t)(2 * w) * out_bytes_per_traj <= (72u << 20)) w *= 2;
+    }
+    w = std::max(tile, (w + tile - 1) / tile * tile);
+    return w;
+}
+long long work_windows(long long N, long long window) { return std::max<long long>(1, (N + window - 1) / window); }
+size_t work_head_bytes(long long nwin) { return 16 + 2 * (size_t)nwin * kWorkBuckets * sizeof(unsigned); }   // counter | histograms | cursors
+size_t work_scratch_bytes(long long N) {   // sized for the smallest window (most histograms)
+    const long long tile = (long long)kWorkBuckets * kWorkTile;
+    return work_head_bytes(work_windows(N, tile)) + (size_t)N * (sizeof(unsigned) + sizeof(unsigned short)) + 16;
+}
 bool want_work_order(const b200ens_model* m, const b200ens_opts* o, const B2Args& a, long long N) {
     if (!m->k_work_keys || !a.adaptive || N >= (1ll << 32)) return false;
     if (const char* e = getenv("B200ENS_WORK_ORDER")) return atoi(e) != 0;   // experiments
@@ -758,17 +786,21 @@ bool want_work_order(const b200ens_model* m, const b200ens_opts* o, const B2Args
 }
 // Enqueues memset + b2_work_keys + b2_work_scatter on `stream`; points a->perm / a->work_counter into `scratch`.
 // a->u0, a->p, a->N and the tolerances must be final.
-int enqueue_work_order(b200ens_model* m, DeviceCtx* d, B2Args* a, void* scratch, cudaStream_t stream) {
+int enqueue_work_order(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, B2Args* a, void* scratch, cudaStream_t stream) {
+    const long long window = work_window(a->N, (size_t)a->n_save * m->n_state * m->elem(), (size_t)m->n_state * m->elem(), o->work_order);
+    const long long nwin = work_windows(a->N, window);
+    const size_t head = work_head_bytes(nwin);
     char* base = (char*)scratch;
     unsigned* hist = (unsigned*)(base + 16);
-    unsigned* cursor = hist + kWorkBuckets;
-    unsigned* perm = cursor + kWorkBuckets;
+    unsigned* cursor = hist + nwin * kWorkBuckets;
+    unsigned* perm = cursor + nwin * kWorkBuckets;
     unsigned short* keys = (unsigned short*)(perm + a->N);
-    CU(cudaMemsetAsync(base, 0, kWorkHead, stream));
+    CU(cudaMemsetAsync(base, 0, head, stream));
     a->work_counter = (unsigned long long*)base;
     a->perm = nullptr;
     {
-        void* params[] = {(void*)a, (void*)&keys, (void*)&hist};
+        long long win = window;
+        void* params[] = {(void*)a, (void*)&keys, (void*)&hist, (void*)&win};
         // every block ends with one global atomic per non-empty bucket: fewer, longer-running blocks mean fewer atomics on
         // the ~100 hot histogram addresses (B200ENS_KEYS_GRID_MULT: blocks per SM, experiments)
         static const int mult = getenv("B200ENS_KEYS_GRID_MULT") ? std::max(1, atoi(getenv("B200ENS_KEYS_GRID_MULT"))) : 4;   // measured 1M Lorenz f32: 0.954 (8), 0.949 (4), 0.952 (2) ms per step
@@ -776,10 +808,10 @@ int enqueue_work_order(b200ens_model* m, DeviceCtx* d, B2Args* a, void* scratch,
         CU(cudaLaunchKernel((const void*)m->k_work_keys, dim3(grid), dim3(256), params, 0, stream));
     }
     {
-        long long N = a->N;
+        long long N = a->N, win = window;
         const unsigned short* ck = keys;
         const unsigned* ch = hist;
-        void* params[] = {(void*)&N, (void*)&ck, (void*)&ch, (void*)&cursor, (void*)&perm};
+        void* params[] = {(void*)&N, (void*)&ck, (void*)&ch, (void*)&cursor, (void*)&perm, (void*)&win};
         const long long tile = (long long)kWorkBuckets * kWorkTile;
         CU(cudaLaunchKernel((const void*)m->k_work_scatter, dim3((unsigned)((N + tile - 1) / tile)), dim3(kWorkBuckets), params, 0,
                             stream));
@@ -1085,7 +1117,7 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
         CU(cudaEventRecord(s.ev[1], s.stream));
         if (want_work_order(m, o, a, cn)) {
             if ((rc = grow(&s.work, &s.cap_work, work_scratch_bytes(cn)))) return rc;
-            if ((rc = enqueue_work_order(m, d, &a, s.work, s.stream))) return rc;
+            if ((rc = enqueue_work_order(m, o, d, &a, s.work, s.stream))) return rc;
             res->launches += 2;
         } else {
             CU(cudaMemsetAsync(s.counter, 0, sizeof(unsigned long long), s.stream));
@@ -1533,7 +1565,7 @@ int b200ens_solve_device(b200ens_model* m, const b200ens_opts* o, int32_t device
     if (want_work_order(m, o, a, N)) {
         // stream-ordered scratch: after warm-up the pool hands the same block back without touching the driver
         CU(cudaMallocAsync(&work, work_scratch_bytes(N), st));
-        if ((rc = enqueue_work_order(m, d, &a, work, st))) return rc;
+        if ((rc = enqueue_work_order(m, o, d, &a, work, st))) return rc;
         launches += 2;
     } else {
         CU(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));

@@ -174,6 +174,12 @@ __device__ __forceinline__ void b2_sde_step(real* __restrict__ u, const real* __
     }
 }
 
+template <bool B>
+struct B2Bool {
+    static constexpr bool v = B;
+};
+__host__ __device__ constexpr int b2_gcd_c(int a, int b) { return b == 0 ? a : b2_gcd_c(b, a % b); }
+
 template <int ALG>
 __device__ __forceinline__ void b2_sde_driver(const B2Args& a) {
     extern __shared__ __align__(16) unsigned char b2_smem[];
@@ -215,83 +221,104 @@ __device__ __forceinline__ void b2_sde_driver(const B2Args& a) {
             }
             const unsigned long long traj = a.traj_offset + (unsigned long long)idx;
             real zbuf[B2_NORMALS_PER_CALL];
-            int zavail = 0;
             unsigned long long zblock = 0;
             // The time grid is driven by the INTEGER step index: t_k = fma(k, dt, t0), k < nsteps = ceil((t1 - t0)/dt)
             // (computed once in double by the host), the last step ends exactly at t1.  Accumulating t += dt in the
             // state type drifts (Float32, dt = 0.0057, t1 = 100: 17546 steps against an injected-increment buffer of
             // 17544), which read past the trajectory's block of dW.
             const int nsteps = (int)a.nsteps_noise;
-            for (; step < nsteps; step++) {
-                if (step >= a.maxiters) {
-                    rc = B2_RC_MAXITERS;
-                    break;
-                }
-                const bool last = step == nsteps - 1;
-                const real t = b2_fma((real)step, dt_user, t0);
-                const real dt = last ? t1 - t : dt_user;
-                real up[B2_N], dW[B2_N], dZ[B2_N];
+            // Per-step control kept out of the loop body: the 64-bit maxiters bound as an int, sqrt(dt) of the regular
+            // step hoisted (the IEEE square root is ~12 issue slots; only the clipped last step has another dt), the next
+            // save time cached in a register (was a global load + compare per step).  The steps run in GROUPS of
+            // U = K / gcd(K, NEED): a group consumes a whole number of K-normal Philox blocks, so inside the unrolled
+            // group every normal's position in its block is a compile-time constant (no availability counter, no
+            // select chain / indexed branch per normal).  Same stream layout -- normal q of a path is element q % K of
+            // its block q / K -- and the same bits as the step-at-a-time loop.
+            constexpr int NEED = NVEC * B2_N, KN = B2_NORMALS_PER_CALL;
+            constexpr int GC = b2_gcd_c(KN, NEED), U = KN / GC;
+            const int maxit = a.maxiters > 0x7fffffffLL ? 0x7fffffff : (int)a.maxiters;
+            const real sq_user = b2_sqrt(dt_user);
+            real tau_next = si < n_save ? __ldg(gsave + si) : (real)__int_as_float(0x7f800000);
+            bool stop = false;
+            // one group of U steps starting at step0.  TAIL = false: the caller guarantees that the group contains
+            // neither the last step nor a step past maxiters, so those tests (and the clipped step's own dt and
+            // square root) are compiled out of the main loop
+            auto run_group = [&](const int step0, auto tail_tag) {
+                constexpr bool TAIL = decltype(tail_tag)::v;
 #pragma unroll
-                for (int i = 0; i < B2_N; i++) up[i] = u[i];
-                if (a.noise_injected) {
-                    const real* src = gdW + ((size_t)idx * a.nsteps_noise + (size_t)step) * (NVEC * B2_N);
-#pragma unroll
-                    for (int i = 0; i < B2_N; i++) {
-                        dW[i] = src[i];
-                        dZ[i] = NVEC > 1 ? src[B2_N + i] : (real)0;
-                    }
-                } else {
-                    // take the next NEED normals of this trajectory's stream; the K-normal Philox block is cached in
-                    // zbuf and indexed with selects (all lanes of a warp are in lockstep, so the refill branch is uniform)
-                    constexpr int NEED = NVEC * B2_N;
-                    real z[NEED];
-                    const real sq = b2_sqrt(dt);
-#pragma unroll
-                    for (int j = 0; j < NEED; j++) {
-                        if (zavail == 0) {
-                            b2_normals(a.seed, traj, zblock, zbuf);
-                            zblock++;
-                            zavail = B2_NORMALS_PER_CALL;
+                for (int s = 0; s < U; s++) {
+                    step = step0 + s;
+                    if (TAIL) {
+                        if (step >= nsteps) break;
+                        if (step >= maxit) {
+                            rc = B2_RC_MAXITERS;
+                            stop = true;
+                            break;
                         }
-                        const int pos = B2_NORMALS_PER_CALL - zavail;
-#if B2_F64
-                        z[j] = pos == 0 ? zbuf[0] : zbuf[1];
-#else
-                        z[j] = pos == 0 ? zbuf[0] : pos == 1 ? zbuf[1] : pos == 2 ? zbuf[2] : zbuf[3];
-#endif
-                        zavail--;
                     }
+                    const bool last = TAIL && step == nsteps - 1;
+                    const real t = b2_fma((real)step, dt_user, t0);
+                    const real dt = last ? t1 - t : dt_user;
+                    real up[B2_N], dW[B2_N], dZ[B2_N];
 #pragma unroll
-                    for (int i = 0; i < B2_N; i++) {
-                        dW[i] = sq * z[i];
-                        dZ[i] = NVEC > 1 ? sq * z[(NVEC > 1 ? B2_N : 0) + i] : (real)0;
-                    }
-                }
-                b2_sde_step<ALG, false>(u, up, dW, dZ, p, t, dt, nullptr, nullptr);
-                bool bad = false;
+                    for (int i = 0; i < B2_N; i++) up[i] = u[i];
+                    if (a.noise_injected) {
+                        const real* src = gdW + ((size_t)idx * a.nsteps_noise + (size_t)step) * (NVEC * B2_N);
 #pragma unroll
-                for (int i = 0; i < B2_N; i++) bad |= b2_isnan(u[i]);
-                if (bad) {
-                    rc = B2_RC_UNSTABLE;
-                    break;
-                }
-                const real tprev = t;
-                const real tnew = last ? t1 : b2_fma((real)(step + 1), dt_user, t0);
-                while (si < n_save) {  // linear interpolation between grid points
-                    const real tau = __ldg(gsave + si);
-                    if (!(tau <= tnew)) break;
-                    if (tau == tnew) {
-                        sink.put(si, u);
+                        for (int i = 0; i < B2_N; i++) {
+                            dW[i] = src[i];
+                            dZ[i] = NVEC > 1 ? src[B2_N + i] : (real)0;
+                        }
                     } else {
-                        const real th = (tau - tprev) / dt;
-                        real w[B2_N];
+                        real z[NEED];
+                        const real sq = last ? b2_sqrt(dt) : sq_user;
 #pragma unroll
-                        for (int i = 0; i < B2_N; i++) w[i] = b2_fma(th, u[i] - up[i], up[i]);
-                        sink.put(si, w);
+                        for (int j = 0; j < NEED; j++) {
+                            const int q = s * NEED + j;   // position in the group's stream: a constant after unrolling
+                            if (q % KN == 0) {
+                                b2_normals(a.seed, traj, zblock, zbuf);
+                                zblock++;
+                            }
+                            z[j] = zbuf[q % KN];
+                        }
+#pragma unroll
+                        for (int i = 0; i < B2_N; i++) {
+                            dW[i] = sq * z[i];
+                            dZ[i] = NVEC > 1 ? sq * z[(NVEC > 1 ? B2_N : 0) + i] : (real)0;
+                        }
                     }
-                    si++;
+                    b2_sde_step<ALG, false>(u, up, dW, dZ, p, t, dt, nullptr, nullptr);
+                    bool bad = false;
+#pragma unroll
+                    for (int i = 0; i < B2_N; i++) bad |= b2_isnan(u[i]);
+                    if (bad) {
+                        rc = B2_RC_UNSTABLE;
+                        stop = true;
+                        break;
+                    }
+                    const real tprev = t;
+                    const real tnew = last ? t1 : b2_fma((real)(step + 1), dt_user, t0);
+                    while (tau_next <= tnew) {  // linear interpolation between grid points
+                        const real tau = tau_next;
+                        if (tau == tnew) {
+                            sink.put(si, u);
+                        } else {
+                            const real th = (tau - tprev) / dt;
+                            real w[B2_N];
+#pragma unroll
+                            for (int i = 0; i < B2_N; i++) w[i] = b2_fma(th, u[i] - up[i], up[i]);
+                            sink.put(si, w);
+                        }
+                        si++;
+                        tau_next = si < n_save ? __ldg(gsave + si) : (real)__int_as_float(0x7f800000);
+                    }
+                    step = step0 + s + 1;   // completed steps (the stats' naccept)
                 }
-            }
+            };
+            const int nmain = (nsteps - 1 < maxit ? nsteps - 1 : maxit) / U * U;   // whole groups before the last step / maxiters
+            int step0 = 0;
+            for (; step0 < nmain && !stop; step0 += U) run_group(step0, B2Bool<false>());
+            for (; step0 < nsteps && !stop; step0 += U) run_group(step0, B2Bool<true>());
             if (rc == 0) rc = B2_RC_SUCCESS;
             else sink.fill(si, n_save, (real)__int_as_float(0x7fc00000));
             a.retcode[idx] = rc;

@@ -19,6 +19,15 @@
 //   b2_work_keys    : proxy -> key[i], global histogram
 //   b2_work_scatter : every block scans the histogram itself, ranks its tile in shared memory and reserves
 //                     one range per non-empty bucket with a single global atomicAdd -> perm[position] = i
+//
+// WINDOWS.  The order is established inside windows of `window` consecutive trajectories (a multiple of the scatter
+// tile; window >= N = one global sort), window after window.  A global permutation scatters the trajectories that are
+// in flight at any moment over the WHOLE output array: every 32-byte sector of out_u then sits half-written in L2
+// for the whole kernel, the array (132 MB for 1M Float32 Lorenz trajectories) does not fit, and sectors are evicted
+// partially written and fetched back (ncu round 1/2: DRAM traffic 2.1x the algorithmic bytes).  With windows the
+// rows being written at any time span one or two windows (tens of MB), sectors complete in L2 and travel to DRAM
+// once.  Scheduling keeps what it needs: neighbours in the queue still take similar step counts, and the last
+// trajectories to start are the shortest of the last window.
 #pragma once
 #include "b2_common.cuh"
 
@@ -33,15 +42,33 @@ __device__ __forceinline__ unsigned b2_work_bucket(float proxy) {
     return (unsigned)(B2_WB - 1 - k);
 }
 
+// hist: [n_windows][B2_WB].  A block's 256 trajectories of one grid-stride iteration are consecutive, hence in ONE
+// window (window is a multiple of 256): the block keeps the histogram of its current window in shared memory and
+// flushes it when the window changes (block-uniform) and at the end.
 extern "C" __global__ void __launch_bounds__(256) b2_work_keys(const __grid_constant__ B2Args a, unsigned short* __restrict__ keys,
-                                                                  unsigned* __restrict__ hist) {
+                                                                  unsigned* __restrict__ hist, const long long window) {
     __shared__ unsigned sh[B2_WB];
     for (int i = threadIdx.x; i < B2_WB; i += blockDim.x) sh[i] = 0u;
     __syncthreads();
     const sreal* const gu0 = reinterpret_cast<const sreal*>(a.u0);
     const sreal* const gp = reinterpret_cast<const sreal*>(a.p);
     const sreal t0 = B2_ARG(a, t0);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += (long long)gridDim.x * blockDim.x) {
+    long long cur_w = -1;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < a.N; base += (long long)gridDim.x * blockDim.x) {
+        const long long w = base / window;
+        if (w != cur_w) {   // block-uniform
+            if (cur_w >= 0) {
+                __syncthreads();
+                for (int i = threadIdx.x; i < B2_WB; i += blockDim.x) {
+                    if (sh[i]) atomicAdd(&hist[cur_w * B2_WB + i], sh[i]);
+                    sh[i] = 0u;
+                }
+                __syncthreads();
+            }
+            cur_w = w;
+        }
+        const long long i = base + threadIdx.x;
+        if (i >= a.N) continue;
         sreal u[B2_N], p[B2_NPA], f0[B2_N], f1[B2_N], u1[B2_N];
 #pragma unroll
         for (int j = 0; j < B2_N; j++) u[j] = gu0[i * B2_N + j];
@@ -73,13 +100,20 @@ extern "C" __global__ void __launch_bounds__(256) b2_work_keys(const __grid_cons
         atomicAdd(&sh[k], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < B2_WB; i += blockDim.x)
-        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+    if (cur_w >= 0)
+        for (int i = threadIdx.x; i < B2_WB; i += blockDim.x)
+            if (sh[i]) atomicAdd(&hist[cur_w * B2_WB + i], sh[i]);
 }
 
+// hist / cursor: [n_windows][B2_WB]; a tile (B2_WB * B2_WTILE consecutive trajectories) lies in one window (window is a
+// multiple of the tile) and is ranked into that window's range of perm.
 extern "C" __global__ void __launch_bounds__(B2_WB) b2_work_scatter(long long N, const unsigned short* __restrict__ keys,
-                                                                      const unsigned* __restrict__ hist, unsigned* __restrict__ cursor,
-                                                                      unsigned* __restrict__ perm) {
+                                                                      const unsigned* __restrict__ hist_all, unsigned* __restrict__ cursor_all,
+                                                                      unsigned* __restrict__ perm, const long long window) {
+    const long long win = ((long long)blockIdx.x * (B2_WB * B2_WTILE)) / window;
+    const unsigned* const hist = hist_all + win * B2_WB;
+    unsigned* const cursor = cursor_all + win * B2_WB;
+    const unsigned wbase = (unsigned)(win * window);
     __shared__ unsigned offs[B2_WB];    // exclusive scan of the global histogram, then + this block's reserved base
     __shared__ unsigned cnt[B2_WB];     // this tile's histogram
     __shared__ unsigned wsum[32];
@@ -121,7 +155,7 @@ extern "C" __global__ void __launch_bounds__(B2_WB) b2_work_scatter(long long N,
     __syncthreads();
     // one global atomic per non-empty bucket reserves this tile's range inside the bucket
     const unsigned c = cnt[tid];
-    offs[tid] = excl + (c ? atomicAdd(&cursor[tid], c) : 0u);
+    offs[tid] = wbase + excl + (c ? atomicAdd(&cursor[tid], c) : 0u);
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < B2_WTILE; j++) {

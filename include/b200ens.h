@@ -123,7 +123,10 @@ typedef struct b200ens_opts {
     int32_t stage_outputs;  /* -1 auto, 0 direct global stores, 1 stage saveat outputs in shared memory */
     int32_t work_order;     /* -1 auto (on for adaptive ODE solves of >= 32768 trajectories per device chunk), 0 caller's
                                order, 1 integrate trajectories in descending expected-work order (device-side counting
-                               sort on the initial-step proxy; scheduling only, results are bit-identical) */
+                               sort on the initial-step proxy; scheduling only, results are bit-identical).  The order is
+                               established inside windows of consecutive trajectories (sized so that the output rows in
+                               flight stay within L2's reach; one window when the rows are whole 32-byte sectors);
+                               a value > 1 is an explicit window size in trajectories (rounded up to 4096) */
     int32_t save_everystep; /* 1: save every accepted step instead of the saveat grid (upstream default without saveat):
                                n_save is then the CAPACITY per trajectory, saveat is ignored (may be NULL), out_u is
                                [N][n_save][n_state] and out_t (required) is [N][n_save] of the state type: slot 0 = (t0, u0),

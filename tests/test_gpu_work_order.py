@@ -71,3 +71,17 @@ def test_nan_and_failing_trajectories_keep_their_slots(B, gpu_lib):
     assert np.array_equal(outs[0].retcodes, outs[1].retcodes)
     assert outs[1].retcodes[7] != 1 and outs[1].retcodes[100] != 1
     assert np.array_equal(outs[0].u_array, outs[1].u_array, equal_nan=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_windowed_ordering_is_bit_identical(B, gpu_lib, dtype):
+    """The order is established inside windows of consecutive trajectories (b2_work.cuh; keeps the output rows in flight
+    within L2's reach).  work_order > 1 = explicit window: several windows, a ragged last one, and one tile per window
+    must give the bits of the caller's order."""
+    N = 70001
+    _, _, ref = _lorenz(B, dtype, N, 0)
+    for window in (4096, 8192, 65536):
+        _, _, w = _lorenz(B, dtype, N, window)
+        assert np.array_equal(ref.retcodes, w.retcodes) and np.all(w.retcodes == 1), window
+        assert np.array_equal(ref.stats, w.stats), window
+        assert np.array_equal(ref.u_array, w.u_array), window

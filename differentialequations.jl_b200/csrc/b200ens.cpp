@@ -84,6 +84,9 @@ struct B2Args {
     float f_tol_a[32], f_tol_r[32];
     void* every_t;
     int save_every, pad1_;
+    double* mom_sum;
+    double* mom_sq;
+    unsigned long long* mom_fail;
 };
 
 bool is_sde(int alg) { return alg == B200ENS_EM || alg == B200ENS_SOSRA || alg == B200ENS_SRIW1; }
@@ -511,6 +514,11 @@ struct Slot {  // one pipeline slot = one stream + device buffers for one chunk
     // pinned bounce buffers for callers whose arrays are pageable (e.g. plain Julia Arrays)
     char *h_in = nullptr, *h_out = nullptr;
     size_t cap_hin = 0, cap_hout = 0;
+    // fused ensemble moments: this chunk's [sum | sumsq | failures] on the device and its pinned host copy
+    void* macc = nullptr;
+    size_t cap_macc = 0;
+    char* h_macc = nullptr;
+    size_t cap_hmacc = 0;
 };
 constexpr int kMaxSlots = 4;
 struct DeviceCtx {
@@ -740,7 +748,7 @@ int launch(b200ens_model* m, const LaunchPlan& lp, const B2Args& a, cudaStream_t
     // the specialised entry keeps 32-bit output offsets in its Float32 save queue: fall back to the generic entry beyond 2^32 elements
     const bool off32_ok = m->dtype == B200ENS_F64 || (unsigned long long)a.N * (unsigned long long)a.n_save * m->n_state < (1ull << 32);
     const bool tstops_ok = !a.save_tstops || is_rosenbrock(m->alg);   // the Rosenbrock entry keeps save_tstops a run-time flag
-    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && tstops_ok && a.dt > 0 && a.stage_stride == 0 && off32_ok && !a.save_every) ? m->kernel_adaptive : m->kernel;
+    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && tstops_ok && a.dt > 0 && a.stage_stride == 0 && off32_ok && !a.save_every && !a.mom_sum) ? m->kernel_adaptive : m->kernel;   // fused moments: generic entry
     if (k != m->kernel && lp.smem > 48 * 1024)
         CU(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, lp.smem));
     CU(cudaLaunchKernel((const void*)k, dim3(lp.grid), dim3(lp.block), params, lp.smem, stream));
@@ -877,6 +885,7 @@ struct ShardResult {
     std::string err;
     double h2d = 0, kern = 0, d2h = 0, total = 0;
     int launches = 0;
+    int fused = 0, fused_fallbacks = 0;   // ensemble moments accumulated inside the solve kernel; chunks recomputed through out_u
     LaunchPlan lp;
 };
 
@@ -1006,12 +1015,26 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
     const int row_len = n_save * n;
     cudaKernel_t mom_kernel = nullptr;
     double* d_acc = nullptr;
+    // FUSED mode: the ODE kernels add every saved value to the accumulators themselves (global double reductions) and
+    // out_u is never allocated, written or read back.  Measured on B200 (profiles/README.md, round 2): it removes the
+    // out_u traffic entirely (config 5 with 1001 save points: 2 x 12.8 GB per 100k trajectories -> 0.5 MB) but the L2
+    // sustains ~1e11 Float64 reductions per second when they are spread over thousands of addresses and 3e10 on a few
+    // thousand, so the fused solve is 18 % SLOWER than solve + second pass (b2_moments.cuh) on config 5 and 5x slower
+    // on 1M Lorenz trajectories x 401 save points: HBM absorbs the rows faster than L2 adds them.  Hence the second
+    // pass is the default; the fused mode is taken when a trajectory's rows are so large (>= 4 MB) that out_u would
+    // force tiny chunks, or on request (B200ENS_FUSE_MOMENTS=1; =0 forbids it).  Only successful trajectories may
+    // count: a chunk in which any trajectory failed is recomputed through out_u (rare; mom_fail tells).
+    bool fuse = mom && !is_sde(m->alg) && !every && out_per_traj >= ((size_t)4 << 20);
+    if (const char* e = getenv("B200ENS_FUSE_MOMENTS")) fuse = mom && !is_sde(m->alg) && !every && row_len > 0 && atoi(e) != 0;
+    const size_t acc_bytes = (2 * (size_t)row_len + 1) * sizeof(double);
     if (mom) {
         if ((rc = moments_kernel(m->dtype == B200ENS_F64, &mom_kernel))) return rc;
-        if ((rc = grow(&d->acc, &d->cap_acc, (2 * (size_t)row_len + 1) * sizeof(double)))) return rc;
+        if ((rc = grow(&d->acc, &d->cap_acc, acc_bytes))) return rc;
         d_acc = static_cast<double*>(d->acc);
-        CU(cudaMemsetAsync(d_acc, 0, (2 * (size_t)row_len + 1) * sizeof(double), d->slot[0].stream));
+        CU(cudaMemsetAsync(d_acc, 0, acc_bytes, d->slot[0].stream));
         CU(cudaStreamSynchronize(d->slot[0].stream));  // both pipeline streams accumulate into it
+        for (int i = 0; i < row_len; i++) mom->sum[i] = mom->sumsq[i] = 0.0;
+        mom->count = 0;
     }
 
     // Callers with pageable arrays (plain Julia Arrays, numpy): stage through pinned bounce buffers with a parallel
@@ -1021,13 +1044,60 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
     struct Pending {
         bool used = false;
         const Chunk* ck = nullptr;
+        B2Args args{};     // fused moments: what the chunk was launched with (the fallback relaunches it through out_u)
+        LaunchPlan lp;
     } pend[kMaxSlots];
     int nslots = kMaxSlots;
     if (const char* e = getenv("B200ENS_SLOTS")) nslots = std::max(1, std::min(kMaxSlots, atoi(e)));
     int it = 0;
     const size_t out_b = (mom || !n_save) ? 0 : out_per_traj;   // bytes per trajectory in the staged output block
+    auto launch_second_pass = [&](Slot& s, long long cn, double* acc) -> int {   // b2_moments.cuh over s.out / s.rc
+        long long nn = cn;
+        int rl = row_len;
+        const void* po = s.out;
+        const int* prc = s.rc;
+        double* ps = acc;
+        double* pq = acc + row_len;
+        unsigned long long* pc = reinterpret_cast<unsigned long long*>(acc + 2 * (size_t)row_len);
+        void* margs[] = {&po, &prc, &nn, &rl, &ps, &pq, &pc};
+        const int gx = (row_len + 127) / 128;
+        const int gy = (int)std::max<long long>(1, std::min<long long>(cn, (long long)d->sms * 16 / gx));
+        CU(cudaLaunchKernel((const void*)mom_kernel, dim3(gx, gy), dim3(128), margs, 0, s.stream));
+        res->launches++;
+        return 0;
+    };
     auto collect = [&](Slot& s, const Pending& pd) -> int {
         CU(cudaEventSynchronize(s.ev[3]));
+        if (fuse) {
+            const double* h = reinterpret_cast<const double*>(s.h_macc);
+            unsigned long long fails;
+            memcpy(&fails, h + 2 * (size_t)row_len, sizeof fails);
+            unsigned long long cnt = (unsigned long long)pd.ck->cn;
+            if (fails) {
+                // some trajectory of this chunk failed after contributing: recompute the chunk through out_u and the
+                // second pass (inputs, permutation and retcode buffers of the slot are still in place)
+                int r2;
+                if ((r2 = grow(&s.out, &s.cap_out, std::max<size_t>(es, (size_t)pd.ck->cn * out_per_traj)))) return r2;
+                B2Args a2 = pd.args;
+                a2.out_u = s.out;
+                a2.mom_sum = a2.mom_sq = nullptr;
+                a2.mom_fail = nullptr;
+                CU(cudaMemsetAsync(a2.work_counter, 0, sizeof(unsigned long long), s.stream));
+                if ((r2 = launch(m, pd.lp, a2, s.stream))) return r2;
+                res->launches++;
+                CU(cudaMemsetAsync(s.macc, 0, acc_bytes, s.stream));
+                if ((r2 = launch_second_pass(s, pd.ck->cn, static_cast<double*>(s.macc)))) return r2;
+                CU(cudaMemcpyAsync(s.h_macc, s.macc, acc_bytes, cudaMemcpyDeviceToHost, s.stream));
+                CU(cudaStreamSynchronize(s.stream));
+                memcpy(&cnt, h + 2 * (size_t)row_len, sizeof cnt);
+                res->fused_fallbacks++;
+            }
+            for (int i = 0; i < row_len; i++) {
+                mom->sum[i] += h[i];
+                mom->sumsq[i] += h[row_len + i];
+            }
+            mom->count += (long long)cnt;
+        }
         if (stage_out) {
             const long long ccn = pd.ck->cn;
             const char* h_o = s.h_out;
@@ -1059,7 +1129,11 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
         }
         if ((rc = grow(&s.u0, &s.cap_u0, (size_t)cn * n * es))) return rc;
         if ((rc = grow(&s.p, &s.cap_p, std::max<size_t>(es, (size_t)cn * np * es)))) return rc;
-        if ((rc = grow(&s.out, &s.cap_out, std::max<size_t>(es, (size_t)cn * out_per_traj)))) return rc;
+        if (!fuse && (rc = grow(&s.out, &s.cap_out, std::max<size_t>(es, (size_t)cn * out_per_traj)))) return rc;
+        if (fuse) {
+            if ((rc = grow(&s.macc, &s.cap_macc, acc_bytes))) return rc;
+            if ((rc = grow_host(&s.h_macc, &s.cap_hmacc, acc_bytes))) return rc;
+        }
         if (dW && (rc = grow(&s.dW, &s.cap_dW, (size_t)cn * noise_per_traj))) return rc;
         if (every && (rc = grow(&s.every_t, &s.cap_every, (size_t)cn * n_save * es))) return rc;
         if ((size_t)cn > s.cap_n) {
@@ -1111,6 +1185,13 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
         a.n_save = n_save;
         a.refill_threshold = lp.refill;
         a.stage_stride = lp.stride;
+        if (fuse) {
+            a.out_u = nullptr;
+            a.mom_sum = static_cast<double*>(s.macc);
+            a.mom_sq = a.mom_sum + row_len;
+            a.mom_fail = reinterpret_cast<unsigned long long*>(a.mom_sum + 2 * (size_t)row_len);
+            CU(cudaMemsetAsync(s.macc, 0, acc_bytes, s.stream));
+        }
         LaunchPlan l2 = lp;
         const long long pb = m->split ? 32 : (long long)lp.block;
         l2.grid = (int)std::max<long long>(1, std::min<long long>(lp.grid, (cn + pb - 1) / pb));
@@ -1124,19 +1205,10 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
         }
         if ((rc = launch(m, l2, a, s.stream))) return rc;
         CU(cudaEventRecord(s.ev[2], s.stream));
-        if (mom) {
-            long long nn = cn;
-            int rl = row_len;
-            const void* po = s.out;
-            const int* prc = s.rc;
-            double* ps = d_acc;
-            double* pq = d_acc + row_len;
-            unsigned long long* pc = reinterpret_cast<unsigned long long*>(d_acc + 2 * (size_t)row_len);
-            void* margs[] = {&po, &prc, &nn, &rl, &ps, &pq, &pc};
-            const int gx = (row_len + 127) / 128;
-            const int gy = (int)std::max<long long>(1, std::min<long long>(cn, (long long)d->sms * 16 / gx));
-            CU(cudaLaunchKernel((const void*)mom_kernel, dim3(gx, gy), dim3(128), margs, 0, s.stream));
-            res->launches++;
+        if (fuse) {
+            CU(cudaMemcpyAsync(s.h_macc, s.macc, acc_bytes, cudaMemcpyDeviceToHost, s.stream));
+        } else if (mom) {
+            if ((rc = launch_second_pass(s, cn, d_acc))) return rc;
         }
         if (stage_out) {
             char* dst_rc = s.h_out + (size_t)cn * out_b;
@@ -1158,6 +1230,8 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
         mark("enq", cn);
         pend[it % nslots].used = true;
         pend[it % nslots].ck = &wk;
+        pend[it % nslots].args = a;
+        pend[it % nslots].lp = l2;
         res->launches++;
         it++;
     }
@@ -1166,7 +1240,7 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
         mark("collect", k);
     }
     if (trace) fprintf(stderr, "[b200ens trace dev %d]%s\n", dev, trace_txt.c_str());
-    if (mom) {
+    if (mom && !fuse) {
         std::vector<double> h(2 * (size_t)row_len + 1);
         CU(cudaMemcpy(h.data(), d_acc, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
         for (int i = 0; i < row_len; i++) {
@@ -1177,6 +1251,7 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
         memcpy(&c, &h[2 * (size_t)row_len], sizeof c);
         mom->count = (long long)c;
     }
+    res->fused = fuse ? 1 : 0;
     CU(cudaGetLastError());
     res->total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     return 0;

@@ -78,6 +78,13 @@ struct B2Args {
     // (t0, u0), slot k the state after the k-th accepted step; slots past the capacity are dropped (stats.naccept tells)
     void* every_t;
     int save_every, pad1_;
+    // fused ensemble moments (b200ens_solve_moments, rows of >= 1024 values): when mom_sum is set the ODE kernels ADD
+    // every saved value and its square to mom_sum / mom_sq [n_save][n_state] (double, global reductions) instead of
+    // storing it to out_u, which is then never allocated; a trajectory that ends in a failure bumps mom_fail (the host
+    // recomputes such a chunk through out_u, so only successful trajectories ever count).
+    double* mom_sum;
+    double* mom_sq;
+    unsigned long long* mom_fail;
 };
 
 #if B2_F64
@@ -208,8 +215,21 @@ struct B2Sink {
     sreal* stage;       // this lane's staging row (null in direct mode)
     sreal* gout;       // out_u as real*
     long long base;    // idx * n_save * B2_N
+    const B2Args* margs;   // fused-moments mode: the kernel's argument block (generic entries; nullptr in the specialised
+                           // ones folds everything away).  The accumulator pointers are read from the constant bank
+                           // where they are used instead of living in registers for the whole loop.
+    __device__ __forceinline__ bool moments() const { return margs != nullptr && margs->mom_sum != nullptr; }
     __device__ __forceinline__ void put(int si, const sreal (&v)[B2_N]) const {
-        if (stage) {
+        if (moments()) {
+            double* const ms = margs->mom_sum + si * B2_N;
+            double* const mq = margs->mom_sq + si * B2_N;
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) {
+                const double x = (double)v[i];
+                atomicAdd(ms + i, x);
+                atomicAdd(mq + i, x * x);
+            }
+        } else if (stage) {
 #pragma unroll
             for (int i = 0; i < B2_N; i++) stage[si * B2_N + i] = v[i];
         } else {
@@ -218,6 +238,7 @@ struct B2Sink {
         }
     }
     __device__ __forceinline__ void fill(int si, int n_save, sreal v) const {
+        if (moments()) return;   // failures are counted, not accumulated (B2Args.mom_fail)
         for (; si < n_save; si++) {
 #pragma unroll
             for (int i = 0; i < B2_N; i++) {

@@ -66,6 +66,8 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     sink.stage = stride ? warp_stage + (size_t)lane * stride : nullptr;
     sink.gout = gout;
     sink.base = 0;
+    // fused ensemble moments: only the generic entry (ADAPT < 0) reads the pointers, the specialised entries fold them away
+    sink.margs = ADAPT < 0 ? &a : nullptr;
 
     for (;;) {
         // ---------------- phase 0: retire / refill (warp-uniform control flow)
@@ -391,6 +393,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                 sink.fill(si, n_save, (real)__int_as_float(0x7fc00000));
             }
             a.retcode[idx] = rc;
+            if (sink.moments() && rc != B2_RC_SUCCESS && rc != B2_RC_TERMINATED) atomicAdd(a.mom_fail, 1ull);
             if (a.stats) {
                 B2Stats s;
                 s.naccept = naccept;

@@ -55,6 +55,19 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     const real* const gsave = reinterpret_cast<const real*>(a.saveat);
     const int n_save = a.n_save;
     const long long out_per_traj = (long long)n_save * B2_N;
+    // fused ensemble moments (B2Args.mom_sum): generic entry only; a saved value is ADDED to the per-(save point,
+    // component) sums instead of being stored
+    // (the pointers are read from the kernel-argument constant bank where they are used, not held in registers)
+#define msum (ADAPT < 0 ? a.mom_sum : (double*)nullptr)
+    auto put_owned = [&](long long obase_, int si_, int j, real v) {
+        if (msum) {
+            const double x = (double)v;
+            atomicAdd(a.mom_sum + (long long)si_ * B2_N + c0 + j, x);
+            atomicAdd(a.mom_sq + (long long)si_ * B2_N + c0 + j, x * x);
+        } else {
+            gout[obase_ + (long long)si_ * B2_N + c0 + j] = v;
+        }
+    };
 
     const real t0 = B2_ARG(a, t0), t1 = B2_ARG(a, t1), dt_user = B2_ARG(a, dt);
     const B2Ctl ctl = b2_ctl_init(a);   // the PI controller works in Float32 (b2_control.cuh)
@@ -146,7 +159,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                         while (si < n_save && __ldg(gsave + si) <= t0) {
 #pragma unroll
                             for (int j = 0; j < B2_NL; j++)
-                                if (c0 + j < B2_N) gout[obase + (long long)si * B2_N + c0 + j] = u[j];
+                                if (c0 + j < B2_N) put_owned(obase, si, j, u[j]);
                             si++;
                         }
                         tau_next = si < n_save ? __ldg(gsave + si) : INF;
@@ -472,7 +485,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
             if (need) {
 #pragma unroll
                 for (int j = 0; j < B2_NL; j++)
-                    if (c0 + j < B2_N) gout[obase + (long long)si * B2_N + c0 + j] = at_end ? un[j] : w[j];
+                    if (c0 + j < B2_N) put_owned(obase, si, j, at_end ? un[j] : w[j]);
                 si++;
                 tau_next = si < n_save ? __ldg(gsave + si) : INF;
             }
@@ -529,16 +542,16 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
 
         // ---------------- phase 4: retire finished / failed lanes
         if (rc != 0) {
-            if (rc != B2_RC_SUCCESS) {
+            if (rc != B2_RC_SUCCESS && !(msum && rc != B2_RC_TERMINATED)) {
                 for (; si < n_save; si++) {
 #pragma unroll
                     for (int j = 0; j < B2_NL; j++)
-                        if (c0 + j < B2_N)
-                            gout[obase + (long long)si * B2_N + c0 + j] = rc == B2_RC_TERMINATED ? u[j] : (real)__int_as_float(0x7fc00000);
+                        if (c0 + j < B2_N) put_owned(obase, si, j, rc == B2_RC_TERMINATED ? u[j] : (real)__int_as_float(0x7fc00000));
                 }
             }
             if (g == 0) {
                 a.retcode[idx] = rc;
+                if (msum && rc != B2_RC_SUCCESS && rc != B2_RC_TERMINATED) atomicAdd(a.mom_fail, 1ull);
                 if (a.stats) {
                     B2Stats s;
                     s.naccept = naccept;
@@ -552,6 +565,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
         }
     }
 }
+#undef msum
 #undef atol_
 #undef rtol_
 #undef B2_TOLIDX

@@ -200,6 +200,7 @@ __device__ __forceinline__ void b2_sde_driver(const B2Args& a) {
     B2Sink sink;
     sink.stage = stride ? warp_stage + (size_t)lane * stride : nullptr;
     sink.gout = gout;
+    sink.margs = nullptr;   // fused moments: ODE kernels only
     bool exhausted = false;
     while (!exhausted) {
         // uniform work per path: hand out whole warps of consecutive paths

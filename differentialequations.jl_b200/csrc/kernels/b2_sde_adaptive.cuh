@@ -38,6 +38,7 @@ __device__ __forceinline__ void b2_sde_adaptive_driver(const B2Args& a) {
     B2Sink sink;
     sink.stage = nullptr;
     sink.gout = gout;
+    sink.margs = nullptr;   // fused moments: ODE kernels only
     sink.base = 0;
     // ---- per-lane path state
     real u[B2_N], p[B2_NPA];

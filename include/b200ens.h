@@ -207,7 +207,11 @@ int b200ens_solve_device(b200ens_model* m, const b200ens_opts* o, int32_t device
  * out_u the call returns, for every (save point, component), the sum and the sum of squares over the trajectories
  * that finished with B200ENS_RC_SUCCESS or B200ENS_RC_TERMINATED (SciMLBase.successful_retcode), and their number:
  *   sum [n_save][n_state], sumsq [n_save][n_state] (double), count (int64).  mean = sum/count,
- *   var = (sumsq - sum^2/count)/(count-1).  Partial results of several GPUs / ranks add up. */
+ *   var = (sumsq - sum^2/count)/(count-1).  Partial results of several GPUs / ranks add up.
+ * Two device paths, same results: the solve writes out_u into HBM chunk buffers and a streaming second pass reduces
+ * them (default: HBM absorbs the rows faster than L2 adds them), or -- FUSED, for rows of >= 4 MB per trajectory or with
+ * B200ENS_FUSE_MOMENTS=1 in the environment -- the ODE kernels add every saved value to the accumulators themselves and
+ * out_u is never allocated (a chunk in which a trajectory fails is recomputed through out_u, so failures never count). */
 int b200ens_solve_moments(b200ens_model* m, const b200ens_opts* o, int64_t N, const void* u0, const void* p,
                           const void* saveat, int32_t n_save, const void* dW, double* sum, double* sumsq,
                           int64_t* count, int32_t* retcode, b200ens_timing* timing);

@@ -48,7 +48,8 @@ class Opts(C.Structure):
         ("block_threads", C.c_int32), ("stage_outputs", C.c_int32),
         ("work_order", C.c_int32), ("save_everystep", C.c_int32),
         ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double)),
-        ("noise_stream_len", C.c_int64), ("shard_blocks", C.c_int32), ("reserved0", C.c_int32),
+        ("noise_stream_len", C.c_int64), ("shard_blocks", C.c_int32), ("n_tstops", C.c_int32),
+        ("tstops", C.POINTER(C.c_double)),
     ]
 
 
@@ -116,7 +117,7 @@ def lib():
     L.b200ens_host_alloc.restype = C.c_void_p
     L.b200ens_host_free.argtypes = [C.c_void_p]
     L.b200ens_host_free.restype = None
-    if L.b200ens_abi_version() != 5:
+    if L.b200ens_abi_version() != 6:
         raise ImportError("libb200ens ABI version mismatch")
     _lib = L
     return L

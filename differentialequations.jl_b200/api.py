@@ -501,21 +501,32 @@ def build_model(prob, alg, callback=None, fast_math=False, ksmem=False, split=No
     return model
 
 
-def _saveat_array(saveat, tspan, dtype):
+def _saveat_array(saveat, tspan, dtype, save_start=None, save_end=None):
+    """The save grid of solve(...; saveat, save_start, save_end): a number is a spacing and includes both
+    ends of tspan (test/core.jl:93-95); a vector is taken as given; save_start / save_end = True / False force the
+    end point of tspan in or out (None: upstream's default, i.e. whatever the grid says)."""
     t0, t1 = tspan
     if saveat is None:
-        return np.array([t0, t1], dtype=dtype)
-    if np.ndim(saveat) == 0:
+        ts = np.array([t0, t1], dtype=np.float64)
+    elif np.ndim(saveat) == 0:
         step = float(saveat)
         k = int(np.floor((t1 - t0) / step * (1 + 1e-12) + 1e-9))
         ts = t0 + step * np.arange(k + 1)
         ts[np.abs(ts - t1) < 1e-12 * max(1.0, abs(t1))] = t1
         if ts[-1] < t1:
             ts = np.append(ts, t1)
-        return ts.astype(dtype)
-    ts = np.asarray(saveat, dtype=np.float64)
-    if ts.size and (np.any(np.diff(ts) <= 0) or ts[0] < t0 or ts[-1] > t1):
-        raise ValueError("saveat must be strictly increasing and inside tspan")
+    else:
+        ts = np.asarray(saveat, dtype=np.float64)
+        if ts.size and (np.any(np.diff(ts) <= 0) or ts[0] < t0 or ts[-1] > t1):
+            raise ValueError("saveat must be strictly increasing and inside tspan")
+    for flag, tend, front in ((save_start, t0, True), (save_end, t1, False)):
+        if flag is None:
+            continue
+        has = ts.size > 0 and (ts[0] if front else ts[-1]) == tend
+        if flag and not has:
+            ts = np.concatenate(([tend], ts)) if front else np.concatenate((ts, [tend]))
+        elif not flag and has:
+            ts = ts[1:] if front else ts[:-1]
     return ts.astype(dtype)
 
 
@@ -606,7 +617,8 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, batch_size=None, **kw)
 
 def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, abstol=None, reltol=None,
                 adaptive=None, callback=None, maxiters=None, save_everystep=None, dense=False, seed=0, dW=None,
-                save_tstops=None, summary=False, _lo=0, _repeat=1, **kwargs):
+                save_tstops=None, summary=False, tstops=None, save_start=None, save_end=None, dtmin=None, dtmax=None,
+                qmin=None, qmax=None, gamma=None, beta1=None, beta2=None, qoldinit=None, _lo=0, _repeat=1, **kwargs):
     """One device solve of trajectories _lo+1 .. _lo+trajectories of the ensemble."""
     if kwargs:
         raise TypeError(f"solve: unsupported keyword arguments {sorted(kwargs)}")
@@ -655,7 +667,7 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
     model = build_model(base, alg, callback, ensemblealg.fast_math,
                         ensemblealg.stage_vectors_in_smem, False if save_everystep else ensemblealg.split,
                         sde_adaptive=sde_adaptive)
-    ts = _saveat_array(saveat, base.tspan, dtype)
+    ts = _saveat_array(saveat, base.tspan, dtype, save_start, save_end)
     t_pack = time.perf_counter()
     u0, p = _pack(eprob, N, dtype, _lo, _repeat, int(seed or 0))
     t_pack = time.perf_counter() - t_pack
@@ -679,6 +691,22 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
     o._tol_keep = tol_keep   # the arrays must outlive every solve that uses these options (dense re-solves too)
     if maxiters is not None:
         o.maxiters = int(maxiters)
+    # step-size control keywords of solve: None = upstream's default, chosen by the library
+    for name, val in (("dtmin", dtmin), ("dtmax", dtmax), ("qmin", qmin), ("qmax", qmax), ("gamma", gamma), ("beta1", beta1),
+                      ("beta2", beta2), ("qoldinit", qoldinit)):
+        if val is not None:
+            if not float(val) >= 0:
+                raise ValueError(f"{name} must be >= 0")
+            setattr(o, name, float(val))
+    if tstops is not None and len(tstops):
+        # solve(...; tstops = [...]): times the integrator must hit exactly (handle_tstop!); with a DiscreteCallback whose
+        # condition is t == tstop this is upstream's dosing idiom
+        if alg.is_sde:
+            raise NotImplementedError("tstops with an SDE stepper")
+        tsv = np.ascontiguousarray(np.sort(np.unique(np.asarray(tstops, dtype=np.float64))))
+        tol_keep.append(tsv)
+        o.tstops = tsv.ctypes.data_as(_lib.C.POINTER(_lib.C.c_double))
+        o.n_tstops = int(tsv.shape[0])
     # an output_func rerun (repeat > 1) redraws the noise like upstream does: the Philox key depends on (seed, repeat)
     o.seed = (int(seed) + (int(_repeat) - 1) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
     o.traj_offset = int(_lo)    # global trajectory index of this batch's first trajectory (Philox counter base)

@@ -298,12 +298,48 @@ def emit_vector_callback(cb, n_state, n_param):
     return cond_src, aff_src, False   # termination is per event index (B2_VTERM_MASK), not the global flag
 
 
+class _TimeProxy:
+    """The `t` a DiscreteCallback condition is traced with.  Julia's `t == 4.0` on a symbolic time is a symbolic
+    equation (upstream's dosing idiom: condition(u, t, integrator) = t == 4.0 together with tstops = [4.0]); Python's
+    `==` on a sympy Symbol is structural and answers False.  This proxy forwards arithmetic to the symbol and turns
+    the comparisons into sympy relationals."""
+
+    def __init__(self, sym):
+        self._s = sym
+
+    def _sympy_(self):
+        return self._s
+
+    def __eq__(self, other):
+        return sp.Eq(self._s, sp.sympify(other))
+
+    def __ne__(self, other):
+        return sp.Ne(self._s, sp.sympify(other))
+
+    __hash__ = None
+
+    def __lt__(self, o): return self._s < sp.sympify(o)
+    def __le__(self, o): return self._s <= sp.sympify(o)
+    def __gt__(self, o): return self._s > sp.sympify(o)
+    def __ge__(self, o): return self._s >= sp.sympify(o)
+    def __add__(self, o): return self._s + sp.sympify(o)
+    def __radd__(self, o): return sp.sympify(o) + self._s
+    def __sub__(self, o): return self._s - sp.sympify(o)
+    def __rsub__(self, o): return sp.sympify(o) - self._s
+    def __mul__(self, o): return self._s * sp.sympify(o)
+    def __rmul__(self, o): return sp.sympify(o) * self._s
+    def __truediv__(self, o): return self._s / sp.sympify(o)
+    def __rtruediv__(self, o): return sp.sympify(o) / self._s
+    def __pow__(self, o): return self._s ** sp.sympify(o)
+    def __neg__(self): return -self._s
+
+
 def emit_discrete_callback(cb, n_state, n_param):
     """DiscreteCallback(condition, affect!) -> (dcondition_src, daffect_src, terminate).  condition(u,t,integrator)
     must trace to a sympy relational / boolean (e.g. `t >= 0.5`, `(u[0] > 1) & (t < 3)`)."""
     integ = _TraceIntegrator(n_state, n_param)
     try:
-        g = cb.condition(integ.u, integ.t, integ)
+        g = cb.condition(integ.u, _TimeProxy(integ.t), integ)
         g = sp.sympify(g)
         if not (g.is_Relational or g.is_Boolean or g in (sp.true, sp.false)):
             raise TypeError("condition must be a boolean expression")

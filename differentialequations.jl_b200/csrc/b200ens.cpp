@@ -87,6 +87,8 @@ struct B2Args {
     double* mom_sum;
     double* mom_sq;
     unsigned long long* mom_fail;
+    const void* tstops;
+    int n_tstops, pad2_;
 };
 
 bool is_sde(int alg) { return alg == B200ENS_EM || alg == B200ENS_SOSRA || alg == B200ENS_SRIW1; }
@@ -529,6 +531,8 @@ struct DeviceCtx {
     Slot slot[kMaxSlots];
     void* saveat = nullptr;
     size_t cap_save = 0;
+    void* tstops = nullptr;   // solve(...; tstops) in the state type
+    size_t cap_tstops = 0;
     void* acc = nullptr;      // ensemble-moments accumulators
     size_t cap_acc = 0;
     unsigned long long* counters = nullptr;  // ring for solve_device
@@ -735,6 +739,14 @@ int check_opts(const b200ens_model* m, const b200ens_opts* o, int n_save, const 
         if (n_save < 2) return fail(B200ENS_E_INVALID, "save_everystep: n_save is the capacity per trajectory and must be >= 2");
         if (o->stage_outputs > 0) return fail(B200ENS_E_UNSUPPORTED, "save_everystep with stage_outputs=1");
     }
+    if (o->n_tstops < 0 || (o->n_tstops > 0 && !o->tstops)) return fail(B200ENS_E_INVALID, "n_tstops = %d with tstops = %p", o->n_tstops, (const void*)o->tstops);
+    if (o->n_tstops > 0) {
+        if (is_sde(m->alg)) return fail(B200ENS_E_UNSUPPORTED, "tstops with an SDE stepper (fixed-step solves hit their dt grid; adaptive SDE: not implemented)");
+        for (int i = 0; i < o->n_tstops; i++) {
+            if (o->tstops[i] != o->tstops[i]) return fail(B200ENS_E_INVALID, "tstops[%d] is NaN", i);
+            if (i && !(o->tstops[i] > o->tstops[i - 1])) return fail(B200ENS_E_INVALID, "tstops must be strictly ascending (entry %d)", i);
+        }
+    }
     if (o->noise_injected && !dW) return fail(B200ENS_E_INVALID, "noise_injected=1 but dW is NULL");
     if ((m->flags & B200ENS_MODEL_SDE_ADAPTIVE) && o->stage_outputs > 0)
         return fail(B200ENS_E_UNSUPPORTED, "adaptive SDE kernels store their outputs directly (stage_outputs=1 is not available)");
@@ -743,12 +755,32 @@ int check_opts(const b200ens_model* m, const b200ens_opts* o, int n_save, const 
     return 0;
 }
 
+// solve(...; tstops): the entries inside (t0, t1), converted to the state type (what the kernels compare t against)
+std::vector<char> tstops_bytes(const b200ens_model* m, const b200ens_opts* o, int* n_out) {
+    std::vector<char> b;
+    int k = 0;
+    for (int i = 0; i < o->n_tstops; i++) {
+        const double v = o->tstops[i];
+        if (!(v > o->t0 && v < o->t1)) continue;
+        if (m->dtype == B200ENS_F64) {
+            b.insert(b.end(), (const char*)&v, (const char*)&v + 8);
+        } else {
+            const float f = (float)v;
+            if (k && memcmp(&f, b.data() + (size_t)(k - 1) * 4, 4) == 0) continue;   // two doubles that round to one float
+            b.insert(b.end(), (const char*)&f, (const char*)&f + 4);
+        }
+        k++;
+    }
+    *n_out = k;
+    return b;
+}
+
 int launch(b200ens_model* m, const LaunchPlan& lp, const B2Args& a, cudaStream_t stream) {
     void* params[] = {(void*)&a};
     // the specialised entry keeps 32-bit output offsets in its Float32 save queue: fall back to the generic entry beyond 2^32 elements
     const bool off32_ok = m->dtype == B200ENS_F64 || (unsigned long long)a.N * (unsigned long long)a.n_save * m->n_state < (1ull << 32);
     const bool tstops_ok = !a.save_tstops || is_rosenbrock(m->alg);   // the Rosenbrock entry keeps save_tstops a run-time flag
-    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && tstops_ok && a.dt > 0 && a.stage_stride == 0 && off32_ok && !a.save_every && !a.mom_sum) ? m->kernel_adaptive : m->kernel;   // fused moments: generic entry
+    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && tstops_ok && a.dt > 0 && a.stage_stride == 0 && off32_ok && !a.save_every && !a.mom_sum && a.n_tstops == 0) ? m->kernel_adaptive : m->kernel;   // fused moments, tstops: generic entry
     if (k != m->kernel && lp.smem > 48 * 1024)
         CU(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, lp.smem));
     CU(cudaLaunchKernel((const void*)k, dim3(lp.grid), dim3(lp.block), params, lp.smem, stream));
@@ -927,6 +959,14 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
     };
     const bool every = o->save_everystep != 0;   // n_save = capacity, no saveat grid
     if (n_save && !every) CU(cudaMemcpyAsync(d->saveat, saveat, (size_t)n_save * es, cudaMemcpyHostToDevice, d->slot[0].stream));
+    int n_ts = 0;
+    const std::vector<char> ts_host = tstops_bytes(m, o, &n_ts);
+    if (n_ts) {
+        if ((rc = grow(&d->tstops, &d->cap_tstops, ts_host.size()))) return rc;
+        CU(cudaMemcpyAsync(d->tstops, ts_host.data(), ts_host.size(), cudaMemcpyHostToDevice, d->slot[0].stream));
+    }
+    base.tstops = n_ts ? d->tstops : nullptr;
+    base.n_tstops = n_ts;
     CU(cudaStreamSynchronize(d->slot[0].stream));
 
     // chunk size: keep both pipeline slots under ~1/4 of the device memory and at least a few waves
@@ -1635,6 +1675,18 @@ int b200ens_solve_device(b200ens_model* m, const b200ens_opts* o, int32_t device
         CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, st));
     }
+    void* d_ts = nullptr;
+    {
+        int n_ts = 0;
+        const std::vector<char> ts_host = tstops_bytes(m, o, &n_ts);
+        if (n_ts) {   // pageable source: the copy is staged before cudaMemcpyAsync returns
+            CU(cudaMallocAsync(&d_ts, ts_host.size(), st));
+            CU(cudaMemcpyAsync(d_ts, ts_host.data(), ts_host.size(), cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        a.tstops = d_ts;
+        a.n_tstops = n_ts;
+    }
     void* work = nullptr;
     int launches = 1;
     if (want_work_order(m, o, a, N)) {
@@ -1647,6 +1699,7 @@ int b200ens_solve_device(b200ens_model* m, const b200ens_opts* o, int32_t device
     }
     if ((rc = launch(m, lp, a, st))) return rc;
     if (work) CU(cudaFreeAsync(work, st));
+    if (d_ts) CU(cudaFreeAsync(d_ts, st));
     if (timing) {
         CU(cudaEventRecord(e1, st));
         CU(cudaEventSynchronize(e1));

@@ -85,6 +85,10 @@ struct B2Args {
     double* mom_sum;
     double* mom_sq;
     unsigned long long* mom_fail;
+    // solve(...; tstops = [...]): times the integrator must hit exactly (handle_tstop!), ascending, of the
+    // state type; read by the generic entries only
+    const void* tstops;
+    int n_tstops, pad2_;
 };
 
 #if B2_F64

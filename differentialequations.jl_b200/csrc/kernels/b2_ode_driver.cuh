@@ -41,6 +41,9 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     constexpr bool EVERY = ADAPT < 0;   // save_everystep exists in the generic entry only (specialised entries: saveat)
     const bool adaptive = ADAPT < 0 ? (a.adaptive != 0) : (ADAPT != 0);
     const bool save_tstops = TSTOPS < 0 ? (a.save_tstops != 0) : (TSTOPS != 0);
+    // solve(...; tstops): generic entry only (the specialised entries are not launched with tstops and fold this away)
+    const int n_ts = ADAPT < 0 ? a.n_tstops : 0;
+    const real* const gts = reinterpret_cast<const real*>(a.tstops);
 
     Alg alg;
 #if B2_KSMEM
@@ -54,6 +57,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     float lq = lqinit;
     long long idx = -1, iter = 0;
     int si = 0, naccept = 0, nreject = 0, nf = 0, nevents = 0;
+    int ti = 0;   // next user tstop of this lane
     // next save time of this lane (cached: the saveat check runs twice per iteration); +inf when none is left
     real tau_next = (real)__int_as_float(0x7f800000);
     bool active = false, dirty = false, exhausted = false;
@@ -95,6 +99,8 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                         iter = 0;
                         si = 0;
                         naccept = nreject = nevents = 0;
+                        ti = 0;
+                        while (ti < n_ts && __ldg(gts + ti) <= t0) ti++;
                         // the first saved value is u0 itself (test/core.jl:34)
                         if (EVERY && a.save_every) {
                             // save_everystep: slot 0 = (t0, u0); `si` counts the slots written, no saveat grid
@@ -171,6 +177,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
             iter++;
             if (!adaptive) dt = dt_user;
             if (save_tstops && tau_next < t1) tstop = tau_next;
+            if (ti < n_ts) tstop = b2_min(tstop, __ldg(gts + ti));
             const bool clipped = dt > tstop - t;
             if (clipped) dt = tstop - t;
             const bool toosmall = dt <= b2_max(dtmin, (real)B2_EPS * b2_abs(t));
@@ -332,6 +339,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
         // ---------------- phase 3: commit the accepted step (loopfooter!: FSAL hand-over, next dt)
         if (accepted) {
             t = tnew;
+            while (ti < n_ts && __ldg(gts + ti) <= t) ti++;
 #if B2_HAS_EVENT
             if (fired) {
                 real w[B2_N];

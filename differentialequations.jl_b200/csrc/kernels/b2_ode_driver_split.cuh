@@ -76,6 +76,8 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     const real dtmax = B2_ARG(a, dtmax), dtmin = B2_ARG(a, dtmin);
     const bool adaptive = ADAPT < 0 ? (a.adaptive != 0) : (ADAPT != 0);
     const bool save_tstops = TSTOPS < 0 ? (a.save_tstops != 0) : (TSTOPS != 0);
+    const int n_ts = ADAPT < 0 ? a.n_tstops : 0;   // solve(...; tstops): generic entry only
+    const real* const gts = reinterpret_cast<const real*>(a.tstops);
     const real INF = (real)__int_as_float(0x7f800000);
     // tolerances of the owned components: read from the kernel-argument constant bank with a warp-uniform index where
     // they are used (not held in 4 * NL registers); padded components take the last real one
@@ -110,6 +112,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     float lq = lqinit;
     long long idx = -1, iter = 0, obase = 0;
     int si = 0, naccept = 0, nreject = 0, nf = 0, nevents = 0;
+    int ti = 0;   // next user tstop of this lane (replicated in the four warps)
     bool active = false, exhausted = false;
 #if B2_HAS_EVENT
     __shared__ __align__(16) real s_ev[B2_EV_M * (Alg::DEG + 2) * 32];
@@ -155,6 +158,8 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                         iter = 0;
                         si = 0;
                         naccept = nreject = nevents = 0;
+                        ti = 0;
+                        while (ti < n_ts && __ldg(gts + ti) <= t0) ti++;
                         // the first saved value is u0 itself (test/core.jl:34)
                         while (si < n_save && __ldg(gsave + si) <= t0) {
 #pragma unroll
@@ -242,6 +247,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
             iter++;
             if (!adaptive) dt = dt_user;
             if (save_tstops && tau_next < t1) tstop = tau_next;
+            if (ti < n_ts) tstop = b2_min(tstop, __ldg(gts + ti));
             const bool clipped = dt > tstop - t;
             if (clipped) dt = tstop - t;
             const bool toosmall = dt <= b2_max(dtmin, (real)B2_EPS * b2_abs(t));
@@ -528,6 +534,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
 #endif
         if (accepted) {
             t = tnew;
+            while (ti < n_ts && __ldg(gts + ti) <= t) ti++;
             if (!fired) {
 #pragma unroll
                 for (int j = 0; j < B2_NL; j++) u[j] = un[j];

@@ -18,7 +18,7 @@ using SciMLBase, Symbolics
 import SciMLBase: __solve, AbstractEnsembleProblem, EnsembleAlgorithm, EnsembleSolution, ReturnCode
 
 const LIB = get(ENV, "B200ENS_LIB", "libb200ens.so")
-const ABI_VERSION = 5
+const ABI_VERSION = 6
 
 struct EnsembleB200 <: EnsembleAlgorithm
     devices::Vector{Int}          # empty = all visible GPUs
@@ -43,7 +43,8 @@ mutable struct Opts
     work_order::Int32; save_everystep::Int32
     abstol_vec::Ptr{Float64}; reltol_vec::Ptr{Float64}
     noise_stream_len::Int64
-    shard_blocks::Int32; reserved0::Int32
+    shard_blocks::Int32; n_tstops::Int32
+    tstops::Ptr{Float64}
     Opts() = new()
 end
 struct Stats; naccept::Int32; nreject::Int32; nf::Int32; nevents::Int32; end
@@ -205,7 +206,7 @@ cptr(s) = s === nothing ? Cstring(C_NULL) : Base.unsafe_convert(Cstring, s)
 
 """One device solve of trajectories lo+1 .. lo+N (1-based, like upstream's batches)."""
 function solve_batch_b200(eprob, alg, ens::EnsembleB200, model::Ptr{Cvoid}, lo::Int, N::Int, repeat::Int, ts, term::Int, ip::Int;
-                          dt, abstol, reltol, adaptive, maxiters, seed)
+                          dt, abstol, reltol, adaptive, maxiters, seed, tstops, dtmin, dtmax)
     prob = eprob.prob
     T = eltype(prob.u0); n = length(prob.u0); m = length(prob.p)
     U0 = pinned(T, n, N); P = pinned(T, max(m, 1), N)
@@ -228,11 +229,14 @@ function solve_batch_b200(eprob, alg, ens::EnsembleB200, model::Ptr{Cvoid}, lo::
     o.abstol = isempty(atolv) ? abstol : atolv[1]; o.reltol = isempty(rtolv) ? reltol : rtolv[1]
     o.abstol_vec = isempty(atolv) ? C_NULL : pointer(atolv); o.reltol_vec = isempty(rtolv) ? C_NULL : pointer(rtolv)
     o.maxiters = maxiters; o.seed = seed; o.traj_offset = lo; o.refill_threshold = ens.refill_threshold
+    dtmin === nothing || (o.dtmin = dtmin); dtmax === nothing || (o.dtmax = dtmax)
+    tsv = sort(unique(collect(Float64, tstops)))             # solve(...; tstops): times the integrator must hit exactly
+    o.tstops = isempty(tsv) ? C_NULL : pointer(tsv); o.n_tstops = length(tsv)
     o.event_terminate = term; o.interp_points = ip
     o.device_mask = isempty(ens.devices) ? 0 : reduce(|, UInt32(1) .<< ens.devices)
     out = pinned(T, n, length(ts), N)                   # column-major == [N][n_save][n_state] of the ABI
     rc = Vector{Int32}(undef, N); st = Vector{Stats}(undef, N); tm = Timing()
-    GC.@preserve atolv rtolv check(ccall((:b200ens_solve, LIB), Cint,
+    GC.@preserve atolv rtolv tsv check(ccall((:b200ens_solve, LIB), Cint,
         (Ptr{Cvoid}, Ref{Opts}, Int64, Ptr{T}, Ptr{T}, Ptr{T}, Int32, Ptr{T}, Ptr{T}, Ptr{T}, Ptr{Int32}, Ptr{Stats}, Ref{Timing}),
         model, o, N, U0, P, ts, length(ts), C_NULL, out, C_NULL, rc, st, tm))
     map(1:N) do i
@@ -243,7 +247,7 @@ end
 
 function __solve(eprob::AbstractEnsembleProblem, alg, ens::EnsembleB200; trajectories, batch_size = trajectories, saveat = nothing,
                  dt = 0.0, abstol = 1e-6, reltol = 1e-3, adaptive = true, maxiters = 100_000, seed = UInt64(0),
-                 callback = nothing, kwargs...)
+                 callback = nothing, tstops = Float64[], dtmin = nothing, dtmax = nothing, kwargs...)
     isempty(kwargs) || error("EnsembleB200: unsupported solve keyword arguments $(collect(keys(kwargs)))")
     haskey(ALG_IDS, nameof(typeof(alg))) || error("EnsembleB200: algorithm $(nameof(typeof(alg))) is not implemented on the device")
     prob = eprob.prob
@@ -259,7 +263,7 @@ function __solve(eprob::AbstractEnsembleProblem, alg, ens::EnsembleB200; traject
                       cptr(rhs), cptr(jac), cptr(tgrad), cptr(noise), cptr(csrc), cptr(asrc), Cstring(C_NULL), cptr(dcsrc), cptr(dasrc))
         check(ccall((:b200ens_compile, LIB), Cint, (Ref{ModelDesc}, Ref{Ptr{Cvoid}}, Ptr{UInt8}, Csize_t), d, model, log, length(log)))
     end
-    kw = (; dt = Float64(dt), abstol, reltol, adaptive, maxiters, seed)
+    kw = (; dt = Float64(dt), abstol, reltol, adaptive, maxiters, seed, tstops, dtmin, dtmax)
     elapsed = @elapsed begin
         # the batch / output_func / reduction loop of SciMLBase.__solve for ensembles (qa.jl:56,192; SURVEY 3.3), after the gather
         u = eprob.u_init === nothing ? [] : eprob.u_init          # UNVERIFIED: upstream's default u_init

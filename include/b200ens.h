@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200ENS_ABI_VERSION 5
+#define B200ENS_ABI_VERSION 6
 
 /* scalar type of u, p, t (Julia eltype(u0)) */
 enum b200ens_dtype { B200ENS_F32 = 0, B200ENS_F64 = 1 };
@@ -144,7 +144,11 @@ typedef struct b200ens_opts {
                                  0,1,..,G-1,G-1,..,1,0,0,1,.. -- every device gets the same mix of an ORDERED parameter sweep
                                  (work varies ~10x along the Lorenz rho-sweep; a linear trend cancels exactly), results are
                                  bit-identical to k = 1 (contiguous ranges [g N/G, (g+1) N/G)) */
-    int32_t reserved0;        /* must be 0 */
+    int32_t n_tstops;         /* number of entries of tstops (0: none) */
+    const double* tstops;     /* solve(...; tstops = [...]) (SURVEY A.1 handle_tstop!): ascending times the integrator must hit
+                                 exactly -- a step that would pass the next one is clipped to end on it, e.g. so that a
+                                 DiscreteCallback with condition t == 4.0 sees that time (the classic dosing example).  Entries
+                                 outside (t0, t1) are ignored.  ODE steppers only (a fixed-step SDE solve has its dt grid) */
 } b200ens_opts;
 
 typedef struct b200ens_stats {

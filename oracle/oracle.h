@@ -71,7 +71,9 @@ typedef struct {
                                  contract (Float32 norm with a Newton reciprocal, log-domain controller with polynomial
                                  log2 / exp2).  ODE steppers only.  Exists to MEASURE what the contract changes
                                  (tests/test_spec_arith.py); the kernels are compared bit for bit against spec_arith = 0 */
-    int32_t pad2_;
+    int32_t n_tstops;         /* solve(...; tstops): number of entries of tstops */
+    const double* tstops;     /* ascending times the integrator must hit exactly (handle_tstop!); compared in the
+                                 state type; entries outside (t0, t1) are ignored.  ODE steppers only */
 } orc_opts;
 
 /* u0 [N][n], p [N][m], saveat [n_save], out_u [N][n_save][n], retcode [N], stats [N] or NULL.

@@ -36,7 +36,8 @@ class Opts(C.Structure):
         ("vcond", C.c_void_p), ("vaffect", C.c_void_p), ("ncond", C.c_int32), ("vterm_mask", C.c_uint32),
         ("mass", C.POINTER(C.c_double)),
         ("every_t", C.c_void_p), ("save_everystep", C.c_int32), ("sde_adaptive", C.c_int32),
-        ("noise_stream_len", C.c_int64), ("spec_arith", C.c_int32), ("pad2_", C.c_int32),
+        ("noise_stream_len", C.c_int64), ("spec_arith", C.c_int32), ("n_tstops", C.c_int32),
+        ("tstops", C.POINTER(C.c_double)),
     ]
 
 
@@ -116,7 +117,7 @@ def fns_from_host_model(dll, f64):
 
 def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adaptive=True, dtype=np.float64,
           maxiters=100000, dW=None, seed=0, event=False, terminate=False, interp_points=10, nthreads=0,
-          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, ncond=0, vterm_mask=0, mass_matrix=None, save_everystep=0, sde_adaptive=False, spec_arith=False, **ctl):
+          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, ncond=0, vterm_mask=0, mass_matrix=None, save_everystep=0, sde_adaptive=False, spec_arith=False, tstops=None, **ctl):
     """Run the oracle.  model: built-in name, or fns = dict(rhs=ptr, jac=ptr, ...)."""
     L = lib()
     f64 = np.dtype(dtype) == np.float64
@@ -151,6 +152,9 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
         save_tstops = alg in ("Rodas4", "Rodas5", "Rodas5P")
     o.save_tstops = int(save_tstops)
     o.sde_adaptive = int(bool(sde_adaptive))
+    if tstops is not None and len(tstops):
+        tv = np.ascontiguousarray(tstops, dtype=np.float64)
+        keep.append(tv); o.tstops = tv.ctypes.data_as(C.POINTER(C.c_double)); o.n_tstops = int(tv.shape[0])
     o.spec_arith = int(bool(spec_arith))   # step control to the letter of SURVEY A.4 / A.5 (the yardstick, not the contract)
     if sde_adaptive and dW is not None:    # injected STANDARD NORMALS [N][len], consumed in order by RSwM
         o.noise_stream_len = int(np.asarray(dW).reshape(N, -1).shape[1])

@@ -32,6 +32,7 @@ class ModelDesc(C.Structure):
         ("rhs_src", C.c_char_p), ("jac_src", C.c_char_p), ("tgrad_src", C.c_char_p), ("noise_src", C.c_char_p),
         ("condition_src", C.c_char_p), ("affect_src", C.c_char_p), ("name", C.c_char_p),
         ("dcondition_src", C.c_char_p), ("daffect_src", C.c_char_p),
+        ("save_idxs", C.POINTER(C.c_int32)), ("n_save_idxs", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -139,7 +140,7 @@ class Model:
 
     def __init__(self, n_state, n_param, dtype, alg, rhs_src, jac_src=None, tgrad_src=None, noise_src=None,
                  condition_src=None, affect_src=None, name="model", fast_math=False,
-                 dcondition_src=None, daffect_src=None, ksmem=False, split=None, sde_adaptive=False):
+                 dcondition_src=None, daffect_src=None, ksmem=False, split=None, sde_adaptive=False, save_idxs=None):
         L = lib()
         d = ModelDesc()
         d.struct_size = C.sizeof(ModelDesc)
@@ -154,12 +155,17 @@ class Model:
         d.noise_src, d.condition_src, d.affect_src = enc(noise_src), enc(condition_src), enc(affect_src)
         d.name = enc(name)
         d.dcondition_src, d.daffect_src = enc(dcondition_src), enc(daffect_src)
+        idx_arr = None
+        if save_idxs is not None:   # solve(...; save_idxs): the output rows hold these components only
+            idx_arr = (C.c_int32 * len(save_idxs))(*[int(i) for i in save_idxs])
+            d.save_idxs, d.n_save_idxs = idx_arr, len(save_idxs)
         self.handle = C.c_void_p()
         logbuf = C.create_string_buffer(1 << 16)
         code = L.b200ens_compile(C.byref(d), C.byref(self.handle), logbuf, len(logbuf))
         self.log = logbuf.value.decode(errors="replace")
         check(code)
         self.n_state, self.n_param, self.dtype, self.alg = n_state, n_param, np.dtype(dtype), alg
+        self.n_out = len(save_idxs) if save_idxs is not None else n_state   # entries of an output row
         self.has_event = condition_src is not None or dcondition_src is not None
 
     def info(self):
@@ -185,7 +191,7 @@ class Model:
         n_save = saveat.shape[0]
         assert u0.shape == (N, self.n_state)
         if out is None:
-            out = np.empty((N, n_save, self.n_state), dtype=dt)
+            out = np.empty((N, n_save, self.n_out), dtype=dt)
         if rc is None:
             rc = np.zeros(N, dtype=np.int32)
         if stats is None and want_stats:
@@ -204,7 +210,7 @@ class Model:
         dt = self.dtype
         u0 = np.ascontiguousarray(u0, dtype=dt)
         p = np.ascontiguousarray(p, dtype=dt).reshape(N, self.n_param)
-        out = np.empty((N, capacity, self.n_state), dtype=dt)
+        out = np.empty((N, capacity, self.n_out), dtype=dt)
         times = np.empty((N, capacity), dtype=dt)
         rc = np.zeros(N, dtype=np.int32)
         stats = np.zeros((N, 4), dtype=np.int32)
@@ -224,8 +230,8 @@ class Model:
         p = np.ascontiguousarray(p, dtype=dt).reshape(N, self.n_param)
         saveat = np.ascontiguousarray(saveat, dtype=dt)
         n_save = saveat.shape[0]
-        s = np.zeros((n_save, self.n_state))
-        q = np.zeros((n_save, self.n_state))
+        s = np.zeros((n_save, self.n_out))
+        q = np.zeros((n_save, self.n_out))
         cnt = C.c_int64(0)
         if rc is None:
             rc = np.zeros(N, dtype=np.int32)

@@ -451,13 +451,17 @@ class _LazySeq:
 _model_cache = {}
 
 
-def build_model(prob, alg, callback=None, fast_math=False, ksmem=False, split=None, sde_adaptive=False):
+def build_model(prob, alg, callback=None, fast_math=False, ksmem=False, split=None, sde_adaptive=False, save_idxs=None):
     """Trace prob.f (and g / callback), emit CUDA C, JIT it for sm_100a.  Cached per function objects."""
     n, m = prob.u0.shape[0], prob.p.shape[0]
     dtype = prob.u0.dtype
     mm = getattr(prob, "mass_matrix", None)
+    if save_idxs is not None:
+        save_idxs = tuple(int(i) for i in (save_idxs if np.ndim(save_idxs) else [save_idxs]))
+        if not save_idxs or len(set(save_idxs)) != len(save_idxs) or min(save_idxs) < 0 or max(save_idxs) >= n:
+            raise ValueError(f"save_idxs must be distinct 0-based components of the state (length {n})")
     key = (id(prob.f), id(prob.g), n, m, dtype.str, alg.name, id(callback), fast_math, ksmem, split,
-           None if mm is None else mm.tobytes(), sde_adaptive, os.environ.get("B200ENS_DEFINES", ""))
+           None if mm is None else mm.tobytes(), sde_adaptive, os.environ.get("B200ENS_DEFINES", ""), save_idxs)
     hit = _model_cache.get(key)
     # the entry keeps STRONG references to f, g and the callback, so none of their ids can be recycled for another object
     # while it is cached; a hit still has to be the very same objects
@@ -494,7 +498,7 @@ def build_model(prob, alg, callback=None, fast_math=False, ksmem=False, split=No
         srcs["dcondition_src"], srcs["daffect_src"], term = codegen.emit_discrete_callback(dcb, n, m)
         terminate |= 2 if term else 0
     model = _lib.Model(n, m, dtype, alg.name, name=getattr(prob.f, "__name__", "model"), fast_math=fast_math,
-                       ksmem=ksmem, split=split, sde_adaptive=sde_adaptive, **srcs)
+                       ksmem=ksmem, split=split, sde_adaptive=sde_adaptive, save_idxs=save_idxs, **srcs)
     model.sources = srcs
     model.event_terminate = terminate
     _model_cache[key] = (model, prob.f, prob.g, callback)
@@ -618,7 +622,8 @@ def solve(prob, alg, ensemblealg=None, trajectories=None, batch_size=None, **kw)
 def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=None, abstol=None, reltol=None,
                 adaptive=None, callback=None, maxiters=None, save_everystep=None, dense=False, seed=0, dW=None,
                 save_tstops=None, summary=False, tstops=None, save_start=None, save_end=None, dtmin=None, dtmax=None,
-                qmin=None, qmax=None, gamma=None, beta1=None, beta2=None, qoldinit=None, _lo=0, _repeat=1, **kwargs):
+                qmin=None, qmax=None, gamma=None, beta1=None, beta2=None, qoldinit=None, save_idxs=None, _lo=0, _repeat=1,
+                **kwargs):
     """One device solve of trajectories _lo+1 .. _lo+trajectories of the ensemble."""
     if kwargs:
         raise TypeError(f"solve: unsupported keyword arguments {sorted(kwargs)}")
@@ -666,7 +671,7 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
         dt = 0.0   # automatic per-trajectory initial step on the device
     model = build_model(base, alg, callback, ensemblealg.fast_math,
                         ensemblealg.stage_vectors_in_smem, False if save_everystep else ensemblealg.split,
-                        sde_adaptive=sde_adaptive)
+                        sde_adaptive=sde_adaptive, save_idxs=save_idxs)
     ts = _saveat_array(saveat, base.tspan, dtype, save_start, save_end)
     t_pack = time.perf_counter()
     u0, p = _pack(eprob, N, dtype, _lo, _repeat, int(seed or 0))

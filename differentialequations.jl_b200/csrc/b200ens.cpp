@@ -114,6 +114,7 @@ constexpr int kBlock = 128;
 
 struct b200ens_model {
     int n_state = 0, n_param = 0, dtype = 0, alg = 0;
+    int n_out = 0;          // entries of an output row: n_state, or the number of save_idxs
     unsigned flags = 0;
     bool has_event = false, has_noise = false;
     std::string name, source, log;
@@ -315,6 +316,12 @@ std::string build_source(const b200ens_model_desc* d, int min_blocks, int block,
             if (!item.empty()) s += "#define " + (eq == std::string::npos ? item : item.substr(0, eq) + " " + item.substr(eq + 1)) + "\n";
             pos = end + 1;
         }
+    }
+    // (before the prelude: b2_common.cuh reads B2_NOUT)
+    if (d->n_save_idxs > 0) {   // solve(...; save_idxs): B2_NOUT + the component of every output column (b2_common.cuh)
+        s += "#define B2_NOUT " + std::to_string(d->n_save_idxs) + "\nstatic constexpr int B2_SAVE_IDXS_[B2_NOUT] = {";
+        for (int i = 0; i < d->n_save_idxs; i++) s += (i ? ", " : "") + std::to_string(d->save_idxs[i]);
+        s += "};\n";
     }
     s += head;
     for (const char* part : {d->rhs_src, d->jac_src, d->tgrad_src, d->noise_src, d->condition_src, d->affect_src,
@@ -632,7 +639,7 @@ int plan_launch(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, long long
     const int block = m->block;
     const size_t es = m->elem();
     const size_t ksm = m->ksmem ? (size_t)m->kvec_bytes * block : 0;
-    int stride = n_save * m->n_state;
+    int stride = n_save * m->n_out;
     if (stride % 2 == 0) stride += 1;  // odd row stride: conflict-free staging rows
     size_t smem = (size_t)block * stride * es;
     int nb_direct = 0, nb_staged = 0;
@@ -778,9 +785,10 @@ std::vector<char> tstops_bytes(const b200ens_model* m, const b200ens_opts* o, in
 int launch(b200ens_model* m, const LaunchPlan& lp, const B2Args& a, cudaStream_t stream) {
     void* params[] = {(void*)&a};
     // the specialised entry keeps 32-bit output offsets in its Float32 save queue: fall back to the generic entry beyond 2^32 elements
-    const bool off32_ok = m->dtype == B200ENS_F64 || (unsigned long long)a.N * (unsigned long long)a.n_save * m->n_state < (1ull << 32);
+    const bool off32_ok = m->dtype == B200ENS_F64 || (unsigned long long)a.N * (unsigned long long)a.n_save * m->n_out < (1ull << 32);
     const bool tstops_ok = !a.save_tstops || is_rosenbrock(m->alg);   // the Rosenbrock entry keeps save_tstops a run-time flag
-    cudaKernel_t k = (m->kernel_adaptive && a.adaptive && tstops_ok && a.dt > 0 && a.stage_stride == 0 && off32_ok && !a.save_every && !a.mom_sum && a.n_tstops == 0) ? m->kernel_adaptive : m->kernel;   // fused moments, tstops: generic entry
+    static const bool force_generic = getenv("B200ENS_GENERIC_ENTRY") && atoi(getenv("B200ENS_GENERIC_ENTRY")) != 0;   // tests: the generic entry must give the specialised one's bits
+    cudaKernel_t k = (!force_generic && m->kernel_adaptive && a.adaptive && tstops_ok && a.dt > 0 && a.stage_stride == 0 && off32_ok && !a.save_every && !a.mom_sum && a.n_tstops == 0) ? m->kernel_adaptive : m->kernel;   // fused moments, tstops: generic entry
     if (k != m->kernel && lp.smem > 48 * 1024)
         CU(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, lp.smem));
     CU(cudaLaunchKernel((const void*)k, dim3(lp.grid), dim3(lp.block), params, lp.smem, stream));
@@ -827,7 +835,7 @@ bool want_work_order(const b200ens_model* m, const b200ens_opts* o, const B2Args
 // Enqueues memset + b2_work_keys + b2_work_scatter on `stream`; points a->perm / a->work_counter into `scratch`.
 // a->u0, a->p, a->N and the tolerances must be final.
 int enqueue_work_order(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, B2Args* a, void* scratch, cudaStream_t stream) {
-    const long long window = work_window(a->N, (size_t)a->n_save * m->n_state * m->elem(), (size_t)m->n_state * m->elem(), o->work_order);
+    const long long window = work_window(a->N, (size_t)a->n_save * m->n_out * m->elem(), (size_t)m->n_out * m->elem(), o->work_order);
     const long long nwin = work_windows(a->N, window);
     const size_t head = work_head_bytes(nwin);
     char* base = (char*)scratch;
@@ -941,7 +949,7 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
     const bool sde_adapt = (m->flags & B200ENS_MODEL_SDE_ADAPTIVE) != 0;   // dW = [N][noise_stream_len] standard normals
     const size_t noise_per_traj = !dW ? 0 : sde_adapt ? (size_t)base.nsteps_noise * es
                                   : (size_t)base.nsteps_noise * ((m->alg == B200ENS_SOSRA || m->alg == B200ENS_SRIW1) ? 2 : 1) * n * es;
-    const size_t out_per_traj = (size_t)n_save * n * es;
+    const size_t out_per_traj = (size_t)n_save * m->n_out * es;
 
     rc = grow(&d->saveat, &d->cap_save, std::max<size_t>(es, (size_t)n_save * es));
     if (rc) return rc;
@@ -1052,7 +1060,7 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
     if (rc) return rc;
     res->lp = lp;
     // moments mode: device accumulators [sum | sumsq | count] instead of the D2H copy of out_u
-    const int row_len = n_save * n;
+    const int row_len = n_save * m->n_out;
     cudaKernel_t mom_kernel = nullptr;
     double* d_acc = nullptr;
     // FUSED mode: the ODE kernels add every saved value to the accumulators themselves (global double reductions) and
@@ -1357,8 +1365,16 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
         return fail(B200ENS_E_INVALID, "dcondition_src and daffect_src must be given together");
     if (is_sde(d->alg) && (d->condition_src || d->dcondition_src))
         return fail(B200ENS_E_UNSUPPORTED, "callbacks on SDE algorithms are not supported");
+    if (d->n_save_idxs < 0 || d->n_save_idxs > d->n_state || (d->n_save_idxs > 0 && !d->save_idxs))
+        return fail(B200ENS_E_INVALID, "n_save_idxs = %d (n_state %d)", d->n_save_idxs, d->n_state);
+    for (int i = 0; i < d->n_save_idxs; i++) {
+        if (d->save_idxs[i] < 0 || d->save_idxs[i] >= d->n_state) return fail(B200ENS_E_INVALID, "save_idxs[%d] = %d is not a component of the state", i, d->save_idxs[i]);
+        for (int j = 0; j < i; j++)
+            if (d->save_idxs[j] == d->save_idxs[i]) return fail(B200ENS_E_INVALID, "save_idxs holds component %d twice", d->save_idxs[i]);
+    }
     auto m = std::make_unique<b200ens_model>();
     m->n_state = d->n_state;
+    m->n_out = d->n_save_idxs > 0 ? d->n_save_idxs : d->n_state;
     m->n_param = d->n_param;
     m->dtype = d->dtype;
     m->alg = d->alg;
@@ -1541,7 +1557,7 @@ static int solve_host(b200ens_model* m, const b200ens_opts* o, int64_t N, const 
     if ((long long)devs.size() > N) devs.resize((size_t)N);
     const int G = (int)devs.size();
     std::vector<ShardResult> res(G);
-    const size_t row_len = (size_t)n_save * m->n_state;
+    const size_t row_len = (size_t)n_save * m->n_out;
     std::vector<Moments> moms(G);
     std::vector<std::vector<double>> mbuf(G);
     if (moments)
@@ -1628,7 +1644,7 @@ int b200ens_solve_moments(b200ens_model* m, const b200ens_opts* o, int64_t N, co
     if (!sum || !sumsq || !count) return fail(B200ENS_E_INVALID, "null moments buffer");
     if (N == 0) {
         *count = 0;
-        for (int i = 0; m && i < n_save * m->n_state; i++) sum[i] = sumsq[i] = 0.0;
+        for (int i = 0; m && i < n_save * m->n_out; i++) sum[i] = sumsq[i] = 0.0;
     }
     return solve_host(m, o, N, u0, p, saveat, n_save, dW, nullptr, nullptr, retcode, nullptr, timing, sum, sumsq, count);
 }

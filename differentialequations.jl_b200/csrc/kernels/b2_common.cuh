@@ -33,6 +33,16 @@ typedef sreal real;
 #define B2_KSMEM 0   // 1: ERK stage vectors live in shared memory (large n_state), see b2_erk.cuh
 #endif
 #define B2_N B2_NSTATE
+// solve(...; save_idxs = [...]): only these components of the state are saved, in this order.  The generated prelude
+// then defines B2_NOUT and `static constexpr int B2_SAVE_IDXS_[B2_NOUT]`; out_u rows have B2_NOUT entries.
+#ifdef B2_NOUT
+#define B2_SIDX(k) (B2_SAVE_IDXS_[k])
+#define B2_HAS_SAVE_IDXS 1
+#else
+#define B2_NOUT B2_NSTATE
+#define B2_SIDX(k) (k)
+#define B2_HAS_SAVE_IDXS 0
+#endif
 #define B2_NPA (B2_NPARAM > 0 ? B2_NPARAM : 1)
 #define B2_FULL 0xffffffffu
 
@@ -218,36 +228,36 @@ __device__ __forceinline__ double b2_itp_pw(double wd) {
 struct B2Sink {
     sreal* stage;       // this lane's staging row (null in direct mode)
     sreal* gout;       // out_u as real*
-    long long base;    // idx * n_save * B2_N
+    long long base;    // idx * n_save * B2_NOUT
     const B2Args* margs;   // fused-moments mode: the kernel's argument block (generic entries; nullptr in the specialised
                            // ones folds everything away).  The accumulator pointers are read from the constant bank
                            // where they are used instead of living in registers for the whole loop.
     __device__ __forceinline__ bool moments() const { return margs != nullptr && margs->mom_sum != nullptr; }
     __device__ __forceinline__ void put(int si, const sreal (&v)[B2_N]) const {
         if (moments()) {
-            double* const ms = margs->mom_sum + si * B2_N;
-            double* const mq = margs->mom_sq + si * B2_N;
+            double* const ms = margs->mom_sum + si * B2_NOUT;
+            double* const mq = margs->mom_sq + si * B2_NOUT;
 #pragma unroll
-            for (int i = 0; i < B2_N; i++) {
-                const double x = (double)v[i];
-                atomicAdd(ms + i, x);
-                atomicAdd(mq + i, x * x);
+            for (int k = 0; k < B2_NOUT; k++) {
+                const double x = (double)v[B2_SIDX(k)];
+                atomicAdd(ms + k, x);
+                atomicAdd(mq + k, x * x);
             }
         } else if (stage) {
 #pragma unroll
-            for (int i = 0; i < B2_N; i++) stage[si * B2_N + i] = v[i];
+            for (int k = 0; k < B2_NOUT; k++) stage[si * B2_NOUT + k] = v[B2_SIDX(k)];
         } else {
 #pragma unroll
-            for (int i = 0; i < B2_N; i++) gout[base + (long long)si * B2_N + i] = v[i];
+            for (int k = 0; k < B2_NOUT; k++) gout[base + (long long)si * B2_NOUT + k] = v[B2_SIDX(k)];
         }
     }
     __device__ __forceinline__ void fill(int si, int n_save, sreal v) const {
         if (moments()) return;   // failures are counted, not accumulated (B2Args.mom_fail)
         for (; si < n_save; si++) {
 #pragma unroll
-            for (int i = 0; i < B2_N; i++) {
-                if (stage) stage[si * B2_N + i] = v;
-                else gout[base + (long long)si * B2_N + i] = v;
+            for (int k = 0; k < B2_NOUT; k++) {
+                if (stage) stage[si * B2_NOUT + k] = v;
+                else gout[base + (long long)si * B2_NOUT + k] = v;
             }
         }
     }

@@ -54,19 +54,29 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     const real* const gp = reinterpret_cast<const real*>(a.p);
     const real* const gsave = reinterpret_cast<const real*>(a.saveat);
     const int n_save = a.n_save;
-    const long long out_per_traj = (long long)n_save * B2_N;
+    const long long out_per_traj = (long long)n_save * B2_NOUT;
     // fused ensemble moments (B2Args.mom_sum): generic entry only; a saved value is ADDED to the per-(save point,
     // component) sums instead of being stored
     // (the pointers are read from the kernel-argument constant bank where they are used, not held in registers)
 #define msum (ADAPT < 0 ? a.mom_sum : (double*)nullptr)
-    auto put_owned = [&](long long obase_, int si_, int j, real v) {
+    auto put_at = [&](long long obase_, int si_, int pos, real v) {   // pos: position inside the output row
         if (msum) {
             const double x = (double)v;
-            atomicAdd(a.mom_sum + (long long)si_ * B2_N + c0 + j, x);
-            atomicAdd(a.mom_sq + (long long)si_ * B2_N + c0 + j, x * x);
+            atomicAdd(a.mom_sum + (long long)si_ * B2_NOUT + pos, x);
+            atomicAdd(a.mom_sq + (long long)si_ * B2_NOUT + pos, x * x);
         } else {
-            gout[obase_ + (long long)si_ * B2_N + c0 + j] = v;
+            gout[obase_ + (long long)si_ * B2_NOUT + pos] = v;
         }
+    };
+    // component c0 + j of this warp's block (j is a compile-time index at every call site)
+    auto put_owned = [&](long long obase_, int si_, int j, real v) {
+#if B2_HAS_SAVE_IDXS
+#pragma unroll
+        for (int k = 0; k < B2_NOUT; k++)
+            if (B2_SIDX(k) == c0 + j) put_at(obase_, si_, k, v);   // save_idxs: where (and whether) the component is saved
+#else
+        put_at(obase_, si_, c0 + j, v);
+#endif
     };
 
     const real t0 = B2_ARG(a, t0), t1 = B2_ARG(a, t1), dt_user = B2_ARG(a, dt);

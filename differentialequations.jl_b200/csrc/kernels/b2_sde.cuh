@@ -193,7 +193,7 @@ __device__ __forceinline__ void b2_sde_driver(const B2Args& a) {
     const real* const gsave = reinterpret_cast<const real*>(a.saveat);
     const real* const gdW = reinterpret_cast<const real*>(a.dW);
     const int n_save = a.n_save;
-    const int out_per_traj = n_save * B2_N;
+    const int out_per_traj = n_save * B2_NOUT;
     constexpr int NVEC = (ALG == 7 || ALG == 9) ? 2 : 1;
     const real t0 = B2_ARG(a, t0), t1 = B2_ARG(a, t1), dt_user = B2_ARG(a, dt);
 

@@ -28,7 +28,7 @@ __device__ __forceinline__ void b2_sde_adaptive_driver(const B2Args& a) {
     const real* const gp = reinterpret_cast<const real*>(a.p);
     const real* const gsave = reinterpret_cast<const real*>(a.saveat);
     const int n_save = a.n_save;
-    const int out_per_traj = n_save * B2_N;
+    const int out_per_traj = n_save * B2_NOUT;
     const real t0 = B2_ARG(a, t0), t1 = B2_ARG(a, t1), dt_user = B2_ARG(a, dt);
     const real dtmax = B2_ARG(a, dtmax), dtmin = B2_ARG(a, dtmin);
     const real delta = ALG == 9 ? (real)(1.0 / 6.0) : (real)1;

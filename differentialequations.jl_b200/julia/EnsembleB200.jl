@@ -32,6 +32,7 @@ struct ModelDesc
     rhs_src::Cstring; jac_src::Cstring; tgrad_src::Cstring; noise_src::Cstring
     condition_src::Cstring; affect_src::Cstring; name::Cstring
     dcondition_src::Cstring; daffect_src::Cstring
+    save_idxs::Ptr{Int32}; n_save_idxs::Int32; reserved0::Int32
 end
 mutable struct Opts
     struct_size::UInt32; adaptive::Int32
@@ -205,7 +206,7 @@ end
 cptr(s) = s === nothing ? Cstring(C_NULL) : Base.unsafe_convert(Cstring, s)
 
 """One device solve of trajectories lo+1 .. lo+N (1-based, like upstream's batches)."""
-function solve_batch_b200(eprob, alg, ens::EnsembleB200, model::Ptr{Cvoid}, lo::Int, N::Int, repeat::Int, ts, term::Int, ip::Int;
+function solve_batch_b200(eprob, alg, ens::EnsembleB200, model::Ptr{Cvoid}, lo::Int, N::Int, repeat::Int, ts, term::Int, ip::Int, nout::Int;
                           dt, abstol, reltol, adaptive, maxiters, seed, tstops, dtmin, dtmax)
     prob = eprob.prob
     T = eltype(prob.u0); n = length(prob.u0); m = length(prob.p)
@@ -234,7 +235,7 @@ function solve_batch_b200(eprob, alg, ens::EnsembleB200, model::Ptr{Cvoid}, lo::
     o.tstops = isempty(tsv) ? C_NULL : pointer(tsv); o.n_tstops = length(tsv)
     o.event_terminate = term; o.interp_points = ip
     o.device_mask = isempty(ens.devices) ? 0 : reduce(|, UInt32(1) .<< ens.devices)
-    out = pinned(T, n, length(ts), N)                   # column-major == [N][n_save][n_state] of the ABI
+    out = pinned(T, nout, length(ts), N)                # column-major == [N][n_save][n_out] of the ABI (n_out = n_state, or length(save_idxs))
     rc = Vector{Int32}(undef, N); st = Vector{Stats}(undef, N); tm = Timing()
     GC.@preserve atolv rtolv tsv check(ccall((:b200ens_solve, LIB), Cint,
         (Ptr{Cvoid}, Ref{Opts}, Int64, Ptr{T}, Ptr{T}, Ptr{T}, Int32, Ptr{T}, Ptr{T}, Ptr{T}, Ptr{Int32}, Ptr{Stats}, Ref{Timing}),
@@ -247,7 +248,7 @@ end
 
 function __solve(eprob::AbstractEnsembleProblem, alg, ens::EnsembleB200; trajectories, batch_size = trajectories, saveat = nothing,
                  dt = 0.0, abstol = 1e-6, reltol = 1e-3, adaptive = true, maxiters = 100_000, seed = UInt64(0),
-                 callback = nothing, tstops = Float64[], dtmin = nothing, dtmax = nothing, kwargs...)
+                 callback = nothing, tstops = Float64[], dtmin = nothing, dtmax = nothing, save_idxs = nothing, kwargs...)
     isempty(kwargs) || error("EnsembleB200: unsupported solve keyword arguments $(collect(keys(kwargs)))")
     haskey(ALG_IDS, nameof(typeof(alg))) || error("EnsembleB200: algorithm $(nameof(typeof(alg))) is not implemented on the device")
     prob = eprob.prob
@@ -258,9 +259,12 @@ function __solve(eprob::AbstractEnsembleProblem, alg, ens::EnsembleB200; traject
     rhs, jac, tgrad, noise, us, ps, t = model_sources(prob, alg)
     csrc, asrc, dcsrc, dasrc, term, ip = callback_sources(callback, us, ps, t)     # lowers every callback or errors
     model = Ref{Ptr{Cvoid}}(C_NULL); log = Vector{UInt8}(undef, 1 << 16)
-    GC.@preserve rhs jac tgrad noise csrc asrc dcsrc dasrc begin
+    sidx = save_idxs === nothing ? Int32[] : Int32.(collect(save_idxs) .- 1)      # solve(...; save_idxs): 0-based for the ABI
+    nout = isempty(sidx) ? n : length(sidx)
+    GC.@preserve rhs jac tgrad noise csrc asrc dcsrc dasrc sidx begin
         d = ModelDesc(sizeof(ModelDesc), n, m, T == Float64 ? 1 : 0, ALG_IDS[nameof(typeof(alg))], 0,
-                      cptr(rhs), cptr(jac), cptr(tgrad), cptr(noise), cptr(csrc), cptr(asrc), Cstring(C_NULL), cptr(dcsrc), cptr(dasrc))
+                      cptr(rhs), cptr(jac), cptr(tgrad), cptr(noise), cptr(csrc), cptr(asrc), Cstring(C_NULL), cptr(dcsrc), cptr(dasrc),
+                      isempty(sidx) ? Ptr{Int32}(C_NULL) : pointer(sidx), length(sidx), 0)
         check(ccall((:b200ens_compile, LIB), Cint, (Ref{ModelDesc}, Ref{Ptr{Cvoid}}, Ptr{UInt8}, Csize_t), d, model, log, length(log)))
     end
     kw = (; dt = Float64(dt), abstol, reltol, adaptive, maxiters, seed, tstops, dtmin, dtmax)
@@ -271,14 +275,14 @@ function __solve(eprob::AbstractEnsembleProblem, alg, ens::EnsembleB200; traject
         N = trajectories
         for lo in 0:batch_size:(N - 1)
             nb = min(batch_size, N - lo)
-            sols = solve_batch_b200(eprob, alg, ens, model[], lo, nb, 1, ts, term, ip; kw...)
+            sols = solve_batch_b200(eprob, alg, ens, model[], lo, nb, 1, ts, term, ip, nout; kw...)
             data = map(1:nb) do j
                 out, rerun = eprob.output_func(sols[j], lo + j)
                 rep = 1
                 while rerun
                     rep += 1
                     rep > 100 && error("EnsembleB200: output_func keeps asking for a rerun (100 repeats)")
-                    one = solve_batch_b200(eprob, alg, ens, model[], lo + j - 1, 1, rep, ts, term, ip; kw..., seed = seed + UInt64(rep - 1) * 0x9E3779B97F4A7C15)
+                    one = solve_batch_b200(eprob, alg, ens, model[], lo + j - 1, 1, rep, ts, term, ip, nout; kw..., seed = seed + UInt64(rep - 1) * 0x9E3779B97F4A7C15)
                     out, rerun = eprob.output_func(one[1], lo + j)
                 end
                 out

@@ -98,6 +98,12 @@ typedef struct b200ens_model_desc {
     const char* name;       /* label for logs / cache, may be NULL */
     const char* dcondition_src;
     const char* daffect_src;
+    const int32_t* save_idxs; /* solve(...; save_idxs = [...]): NULL, or the 0-based state components that are saved, in this
+                                 order (distinct, each < n_state).  out_u rows, the moments and save_everystep rows then
+                                 have n_save_idxs entries instead of n_state: the kernels store (and the host link carries)
+                                 only what the caller asked for */
+    int32_t n_save_idxs;      /* number of entries of save_idxs; 0 = every component */
+    int32_t reserved0;        /* must be 0 */
 } b200ens_model_desc;
 
 /* solve keyword arguments (test/core.jl:14,54,72,93: reltol, abstol, dense/saveat, callback).

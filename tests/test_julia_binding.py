@@ -10,7 +10,7 @@ HDR = os.path.join(ROOT, "include", "b200ens.h")
 JL = os.path.join(ROOT, "differentialequations.jl_b200", "julia", "EnsembleB200.jl")
 
 C2JL = {"uint32_t": "UInt32", "int32_t": "Int32", "int64_t": "Int64", "uint64_t": "UInt64", "double": "Float64",
-        "const char*": "Cstring", "const double*": "Ptr{Float64}"}
+        "const char*": "Cstring", "const double*": "Ptr{Float64}", "const int32_t*": "Ptr{Int32}"}
 
 
 def c_struct_fields(name):

@@ -787,7 +787,8 @@ int launch(b200ens_model* m, const LaunchPlan& lp, const B2Args& a, cudaStream_t
     // the specialised entry keeps 32-bit output offsets in its Float32 save queue: fall back to the generic entry beyond 2^32 elements
     const bool off32_ok = m->dtype == B200ENS_F64 || (unsigned long long)a.N * (unsigned long long)a.n_save * m->n_out < (1ull << 32);
     const bool tstops_ok = !a.save_tstops || is_rosenbrock(m->alg);   // the Rosenbrock entry keeps save_tstops a run-time flag
-    static const bool force_generic = getenv("B200ENS_GENERIC_ENTRY") && atoi(getenv("B200ENS_GENERIC_ENTRY")) != 0;   // tests: the generic entry must give the specialised one's bits
+    const char* fg = getenv("B200ENS_GENERIC_ENTRY");   // tests: the generic entry must give the specialised one's bits
+    const bool force_generic = fg && atoi(fg) != 0;
     cudaKernel_t k = (!force_generic && m->kernel_adaptive && a.adaptive && tstops_ok && a.dt > 0 && a.stage_stride == 0 && off32_ok && !a.save_every && !a.mom_sum && a.n_tstops == 0) ? m->kernel_adaptive : m->kernel;   // fused moments, tstops: generic entry
     if (k != m->kernel && lp.smem > 48 * 1024)
         CU(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, lp.smem));

@@ -55,7 +55,9 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
     real u[B2_N], p[B2_NPA];
     real t = t0, dt = dt_user;
     float lq = lqinit;
-    long long idx = -1, iter = 0;
+    long long idx = -1;
+    int iter = 0;   // step attempts of this lane's trajectory (maxiters is clamped to 2^31 - 1: 32-bit compare per iteration)
+    const int maxit = a.maxiters > 0x7fffffffLL ? 0x7fffffff : (int)a.maxiters;
     int si = 0, naccept = 0, nreject = 0, nf = 0, nevents = 0;
     int ti = 0;   // next user tstop of this lane
     // next save time of this lane (cached: the saveat check runs twice per iteration); +inf when none is left
@@ -181,7 +183,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
             const bool clipped = dt > tstop - t;
             if (clipped) dt = tstop - t;
             const bool toosmall = dt <= b2_max(dtmin, (real)B2_EPS * b2_abs(t));
-            if (iter > a.maxiters) rc = B2_RC_MAXITERS;
+            if (iter > maxit) rc = B2_RC_MAXITERS;
             else if (b2_isnan(dt)) rc = B2_RC_DTNAN;
             else if (adaptive & !clipped & toosmall) rc = B2_RC_DTLESSTHANMIN;
             do_step = rc == 0;

@@ -120,7 +120,9 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
     }
     real t = t0, dt = dt_user, tau_next = INF;
     float lq = lqinit;
-    long long idx = -1, iter = 0, obase = 0;
+    long long idx = -1, obase = 0;
+    int iter = 0;
+    const int maxit = a.maxiters > 0x7fffffffLL ? 0x7fffffff : (int)a.maxiters;
     int si = 0, naccept = 0, nreject = 0, nf = 0, nevents = 0;
     int ti = 0;   // next user tstop of this lane (replicated in the four warps)
     bool active = false, exhausted = false;
@@ -261,7 +263,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
             const bool clipped = dt > tstop - t;
             if (clipped) dt = tstop - t;
             const bool toosmall = dt <= b2_max(dtmin, (real)B2_EPS * b2_abs(t));
-            if (iter > a.maxiters) rc = B2_RC_MAXITERS;
+            if (iter > maxit) rc = B2_RC_MAXITERS;
             else if (b2_isnan(dt)) rc = B2_RC_DTNAN;
             else if (adaptive & !clipped & toosmall) rc = B2_RC_DTLESSTHANMIN;
             do_step = rc == 0;

@@ -85,3 +85,28 @@ def test_windowed_ordering_is_bit_identical(B, gpu_lib, dtype):
         assert np.array_equal(ref.retcodes, w.retcodes) and np.all(w.retcodes == 1), window
         assert np.array_equal(ref.stats, w.stats), window
         assert np.array_equal(ref.u_array, w.u_array), window
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_generic_entry_gives_the_specialised_entrys_bits(B, gpu_lib, dtype):
+    """Solves with tstops, fused moments, save_everystep or an automatic dt run through the generic kernel entry; the
+    headline shape runs through the compile-time specialised one.  Same template, same bits (B200ENS_GENERIC_ENTRY=1
+    forces the generic entry)."""
+    import os
+
+    from b200ens import workloads as W
+
+    N = 40000
+    _, _, spec = _lorenz(B, dtype, N, -1)
+    u0r, pr = W.robertson_params(2000)
+    kr = dict(trajectories=2000, saveat=W.ROBERTSON_SAVEAT, dt=1e-6, abstol=1e-8, reltol=1e-6)
+    spec_r = B.solve(B.EnsembleProblem(W.robertson_problem(), u0s=u0r, ps=pr), B.Rodas5P(), B.EnsembleB200(), **kr) if dtype == np.float64 else None
+    os.environ["B200ENS_GENERIC_ENTRY"] = "1"
+    try:
+        _, _, gen = _lorenz(B, dtype, N, -1)
+        gen_r = B.solve(B.EnsembleProblem(W.robertson_problem(), u0s=u0r, ps=pr), B.Rodas5P(), B.EnsembleB200(), **kr) if dtype == np.float64 else None
+    finally:
+        del os.environ["B200ENS_GENERIC_ENTRY"]
+    assert np.array_equal(spec.u_array, gen.u_array) and np.array_equal(spec.stats, gen.stats)
+    if spec_r is not None:
+        assert np.array_equal(spec_r.u_array, gen_r.u_array) and np.array_equal(spec_r.stats, gen_r.stats)

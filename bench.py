@@ -496,6 +496,25 @@ def main():
     except Exception as e:  # noqa: BLE001
         e2e_summary = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
+    # ---- informational: the same ensemble with solve(...; save_idxs = [3]) -- only z(t) is saved: 44 + 4 B per trajectory
+    # come back instead of 132 + 4, the host link stops being the bound.  Not the headline (another output contract).
+    e2e_save_idxs = None
+    try:
+        if world == 1:
+            model_z = b200ens.build_model(W.lorenz_problem(npdt, TSPAN), b200ens.Tsit5(), save_idxs=[2])
+            out_z = _lib.pinned_empty((N, n_save, 1), npdt)
+            for _ in range(2):
+                model_z.solve(o, u0_pin, p_pin, SAVEAT, out=out_z, rc=rc_pin, want_stats=False)
+            tz0 = time.perf_counter()
+            for _ in range(a.steps):
+                model_z.solve(o, u0_pin, p_pin, SAVEAT, out=out_z, rc=rc_pin, want_stats=False)
+            ez_s = time.perf_counter() - tz0
+            e2e_save_idxs = {"value": N * a.steps / ez_s, "unit": "trajectories/s", "ms_per_step": ez_s / a.steps * 1e3,
+                             "save_idxs": [3], "d2h_bytes_per_step": int(out_z.nbytes + rc_pin.nbytes),
+                             "identical_to_column_of_full_output": bool(np.array_equal(out_z[:, :, 0], out_pin[:, :, 2]))}
+    except Exception as e:  # noqa: BLE001
+        e2e_save_idxs = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
     # ---- the host-link ceiling of THIS box at this GPU count: the same bytes, copies only (no kernel), all ranks at once.
     # e2e cannot beat it; `frac_of_host_ceiling` says how close the pipelined solve gets.
     host_ceiling = None
@@ -559,7 +578,7 @@ def main():
             "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "trajectories/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / a.steps * 1e3, "matches_device_leg": same, "host_ceiling": host_ceiling,
-                    "summary_path": e2e_summary,
+                    "summary_path": e2e_summary, "save_idxs_path": e2e_save_idxs,
                     "outside_the_timed_region": {"prob_func_vectorised_ms": prob_func_ms, "model_build_ms": jit_ms,
                                                  "note": "prob_func as a parameter matrix (numpy, once per ensemble) and the one-time trace + NVRTC JIT (cubins are cached on disk)"},
                     "frac_of_host_ceiling": (e2e_val / host_ceiling["traj_per_s_at_ceiling"]) if host_ceiling and "traj_per_s_at_ceiling" in host_ceiling else None},

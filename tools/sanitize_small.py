@@ -36,3 +36,37 @@ print("dae + vector tolerances", s.retcode.name, len(s.t))
 u0g, pg = W.gbm_params(2000)
 s = B.solve(B.EnsembleProblem(W.gbm_problem(), u0s=u0g, ps=pg), B.SRIW1(), B.EnsembleB200(), trajectories=2000, saveat=[1.0], dt=1 / 64, seed=5)
 print("sriw1", (s.retcodes == 1).all())
+# round-2 additions: tstops + DiscreteCallback, save_idxs (one-thread + split), windowed work order, fused moments
+# (+ the fallback through out_u), grouped SDE loops (EM / SOSRA), adaptive SDE
+import os
+prob = B.ODEProblem(lambda u, p, t: [-p[0] * u[0]], np.array([10.0]), (0.0, 12.0), np.array([0.5, 10.0]))
+dcb = B.DiscreteCallback(lambda u, t, integ: (t == 4.0) | (t == 8.0), lambda integ: integ.u.__setitem__(0, integ.u[0] + integ.p[1]))
+pp = np.stack([0.2 + np.random.default_rng(0).random(700), np.full(700, 10.0)], axis=1)
+s = B.solve(B.EnsembleProblem(prob, u0s=np.full((700, 1), 10.0), ps=pp), B.Tsit5(), B.EnsembleB200(), trajectories=700, saveat=1.0, dt=0.1,
+            callback=dcb, tstops=[4.0, 8.0])
+print("tstops dosing", (s.retcodes == 1).all(), s.stats[:, 3].mean())
+u0n, pn = W.net16_params(200)
+s = B.solve(B.EnsembleProblem(W.net16_problem(), u0s=u0n, ps=pn), B.Vern7(), B.EnsembleB200(split=True), trajectories=200,
+            saveat=np.linspace(0, 10, 11), dt=0.01, abstol=1e-6, reltol=1e-6, callback=W.net16_callback(), save_idxs=[15, 0, 5], tstops=[3.3])
+print("split save_idxs tstops", (s.retcodes == 1).all(), s.u_array.shape)
+u0l, pl = W.lorenz_params(9000, "random", 0, np.float32)
+s = B.solve(B.EnsembleProblem(W.lorenz_problem(np.float32), u0s=u0l, ps=pl), B.Tsit5(), B.EnsembleB200(work_order=4096), trajectories=9000,
+            saveat=np.arange(0, 10.5, 1.0), dt=0.1, save_idxs=[2])
+print("windowed order + save_idxs", (s.retcodes == 1).all(), s.u_array.shape)
+os.environ["B200ENS_FUSE_MOMENTS"] = "1"
+pl64 = pl.astype(np.float64); pl64[7] = np.nan
+s = B.solve(B.EnsembleProblem(W.lorenz_problem(), u0s=u0l.astype(np.float64), ps=pl64), B.Tsit5(), B.EnsembleB200(), trajectories=9000,
+            saveat=np.arange(0, 10.5, 1.0), dt=0.1, summary=True)
+print("fused moments with a failing trajectory", s.num_monte)
+s = B.solve(B.EnsembleProblem(W.net16_problem(), u0s=u0n, ps=pn), B.Vern7(), B.EnsembleB200(split=True), trajectories=200,
+            saveat=np.linspace(0, 10, 11), dt=0.01, abstol=1e-6, reltol=1e-6, callback=W.net16_callback(), summary=True)
+print("fused moments split", s.num_monte)
+del os.environ["B200ENS_FUSE_MOMENTS"]
+u0a, pa = W.lorenz_additive_params(1500)
+for alg in (B.EM(), B.SOSRA()):
+    s = B.solve(B.EnsembleProblem(W.lorenz_additive_problem(), u0s=u0a, ps=pa), alg, B.EnsembleB200(), trajectories=1500, saveat=[0.3, 1.0],
+                dt=1 / 256, seed=3)
+    print("sde grouped loop", alg.name, (s.retcodes == 1).all())
+pr1 = B.SDEProblem(W.lorenz_add_f, W.lorenz_add_g, np.array([1.0, 0.0, 0.0]), (0.0, 1.0), np.array([10.0, 28.0, 8.0 / 3.0, 3.0]))
+s = B.solve(B.EnsembleProblem(pr1, u0s=u0a, ps=pa), B.SOSRA(), B.EnsembleB200(), trajectories=1500, saveat=[1.0], dt=0.01, adaptive=True, seed=3)
+print("sde adaptive", (s.retcodes == 1).all())

@@ -1236,6 +1236,7 @@ int solve_shard(b200ens_model* m, const b200ens_opts* o, int dev, const Ranges& 
         a.stage_stride = lp.stride;
         if (fuse) {
             a.out_u = nullptr;
+            a.stage_stride = 0;   // nothing to stage or flush: the sink adds instead of storing
             a.mom_sum = static_cast<double*>(s.macc);
             a.mom_sq = a.mom_sum + row_len;
             a.mom_fail = reinterpret_cast<unsigned long long*>(a.mom_sum + 2 * (size_t)row_len);

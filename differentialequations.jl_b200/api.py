@@ -175,16 +175,36 @@ def remake(prob, **kw):
     return prob._replace(**kw)
 
 
-class ContinuousCallback:
-    """ContinuousCallback(condition, affect!) with condition(u,t,integrator) and affect!(integrator)
-    (test/core.jl:69-72).  Both must be symbolically traceable (they are emitted as CUDA C)."""
+class _SameAffect:
+    """Default of affect_neg!: the downcrossing affect is the upcrossing affect (upstream: affect_neg! = affect!)."""
 
-    def __init__(self, condition, affect, interp_points=10, save_positions=(False, False)):
+    def __repr__(self):
+        return "affect_neg! = affect!"
+
+
+SAME_AFFECT = _SameAffect()
+
+
+class ContinuousCallback:
+    """ContinuousCallback(condition, affect!, affect_neg! = affect!; interp_points) with condition(u,t,integrator) and
+    affect!(integrator) (test/core.jl:69-72): an upcrossing of the condition (negative -> positive) runs
+    affect!, a downcrossing affect_neg!; `None` for either one ignores that direction (upstream's `nothing`).  All
+    functions must be symbolically traceable (they are emitted as CUDA C)."""
+
+    def __init__(self, condition, affect, affect_neg=SAME_AFFECT, interp_points=10, save_positions=(False, False)):
         self.condition = condition
         self.affect = affect
+        self.affect_neg = affect if affect_neg is SAME_AFFECT else affect_neg
+        if self.affect is None and self.affect_neg is None:
+            raise ValueError("ContinuousCallback: affect! and affect_neg! cannot both be nothing")
         self.interp_points = interp_points
         if tuple(save_positions) != (False, False):
             raise NotImplementedError("EnsembleB200 needs save_positions=(false,false) (saveat output is fixed-size)")
+
+    @property
+    def direction(self):
+        """0: both directions, +1: upcrossings only, -1: downcrossings only."""
+        return 1 if self.affect_neg is None else (-1 if self.affect is None else 0)
 
 
 class VectorContinuousCallback:
@@ -192,15 +212,26 @@ class VectorContinuousCallback:
     event functions, the earliest root among those that change sign fires and affect!(integrator, idx) receives its
     1-based index.  Both must be symbolically traceable."""
 
-    def __init__(self, condition, affect, len, interp_points=10, save_positions=(False, False)):
+    def __init__(self, condition, affect, len, affect_neg=SAME_AFFECT, interp_points=10, save_positions=(False, False)):
         self.condition = condition
         self.affect = affect
+        # affect_neg!: the same function (default) or None = upcrossings only; affect = None with affect_neg = downcrossings only
+        self.affect_neg = affect if affect_neg is SAME_AFFECT else affect_neg
+        if self.affect is None and self.affect_neg is None:
+            raise ValueError("VectorContinuousCallback: affect! and affect_neg! cannot both be nothing")
+        if self.affect is not None and self.affect_neg is not None and self.affect_neg is not self.affect:
+            raise NotImplementedError("VectorContinuousCallback with an affect_neg! different from affect! (use nothing for "
+                                      "one of them, or ContinuousCallbacks)")
         self.len = int(len)
         self.interp_points = interp_points
         if not 1 <= self.len <= 16:
             raise ValueError("VectorContinuousCallback: len must be in 1..16")
         if tuple(save_positions) != (False, False):
             raise NotImplementedError("EnsembleB200 needs save_positions=(false,false) (saveat output is fixed-size)")
+
+    @property
+    def direction(self):
+        return 1 if self.affect_neg is None else (-1 if self.affect is None else 0)
 
 
 class DiscreteCallback:
@@ -228,15 +259,20 @@ class CallbackSet:
             if any(isinstance(c, VectorContinuousCallback) for c in cont):
                 raise NotImplementedError("a VectorContinuousCallback cannot be combined with further continuous callbacks")
             scalars = list(cont)
+            if any(c.direction != scalars[0].direction or (c.direction == 0 and c.affect_neg is not c.affect) for c in scalars):
+                raise NotImplementedError("a CallbackSet of several ContinuousCallbacks needs one common direction "
+                                          "(all two-sided with affect_neg! = affect!, all upcrossing-only or all downcrossing-only)")
+            sdir = scalars[0].direction
 
             def condition(out, u, t, integrator, _cbs=scalars):
                 for k, c in enumerate(_cbs):
                     out[k] = c.condition(u, t, integrator)
 
-            def affect(integrator, idx, _cbs=scalars):
-                _cbs[idx - 1].affect(integrator)
+            def affect(integrator, idx, _cbs=scalars, _d=sdir):
+                (_cbs[idx - 1].affect_neg if _d < 0 else _cbs[idx - 1].affect)(integrator)
 
-            cont = [VectorContinuousCallback(condition, affect, len(scalars),
+            cont = [VectorContinuousCallback(condition, affect if sdir >= 0 else None, len(scalars),
+                                             affect_neg=(SAME_AFFECT if sdir == 0 else (None if sdir > 0 else affect)),
                                              interp_points=max(c.interp_points for c in scalars))]
         self.continuous = cont
 
@@ -493,7 +529,7 @@ def build_model(prob, alg, callback=None, fast_math=False, ksmem=False, split=No
     if ccb is not None:
         emit = codegen.emit_vector_callback if isinstance(ccb, VectorContinuousCallback) else codegen.emit_callback
         srcs["condition_src"], srcs["affect_src"], term = emit(ccb, n, m)
-        terminate |= 1 if term else 0
+        terminate |= int(term) & 5   # bit 0: affect! terminates, bit 2: affect_neg! does (opts.event_terminate)
     if dcb is not None:
         srcs["dcondition_src"], srcs["daffect_src"], term = codegen.emit_discrete_callback(dcb, n, m)
         terminate |= 2 if term else 0

@@ -234,23 +234,39 @@ def emit_callback(cb, n_state, n_param):
     cond_src = (f"#undef B2_COND_MASK\n#define B2_COND_MASK 0x{mask:x}u\n"
                 "__device__ __forceinline__ real b2_condition(const real* __restrict__ u, const real* __restrict__ p, "
                 "const real t) {\n    (void)u; (void)p; (void)t;\n    return " + _c(g) + ";\n}\n")
-    integ2 = _TraceIntegrator(n_state, n_param)
-    try:
-        cb.affect(integ2)
-    except NotImplementedError:
-        raise   # a precise rejection (e.g. affect! writing integrator.p) is the message the user needs
-    except Exception as e:
-        raise NotImplementedError("ContinuousCallback affect! is not symbolically traceable") from e
-    lines = []
-    changed = [(i, v) for i, (s, v) in enumerate(zip(integ2.u.syms, integ2.u.vals)) if v != s]
-    # evaluate all right-hand sides before assigning (affect! sees the pre-event state)
-    for i, v in changed:
-        lines.append(f"    const real n{i} = {_c(v)};")
-    for i, _ in changed:
-        lines.append(f"    u[{i}] = n{i};")
-    aff_src = ("__device__ __forceinline__ void b2_affect(real* __restrict__ u, const real* __restrict__ p, "
+    direction = getattr(cb, "direction", 0)
+    if direction:
+        cond_src = f"#undef B2_EVENT_DIR\n#define B2_EVENT_DIR {direction}\n" + cond_src
+
+    def trace_affect(fn, name):
+        it = _TraceIntegrator(n_state, n_param)
+        try:
+            fn(it)
+        except NotImplementedError:
+            raise   # a precise rejection (e.g. affect! writing integrator.p) is the message the user needs
+        except Exception as e:
+            raise NotImplementedError("ContinuousCallback affect! is not symbolically traceable") from e
+        lines = []
+        changed = [(i, v) for i, (s, v) in enumerate(zip(it.u.syms, it.u.vals)) if v != s]
+        # evaluate all right-hand sides before assigning (affect! sees the pre-event state)
+        for i, v in changed:
+            lines.append(f"    const real n{i} = {_c(v)};")
+        for i, _ in changed:
+            lines.append(f"    u[{i}] = n{i};")
+        src = (f"__device__ __forceinline__ void {name}(real* __restrict__ u, const real* __restrict__ p, "
                "const real t) {\n    (void)u; (void)p; (void)t;\n" + "\n".join(lines) + "\n}\n")
-    return cond_src, aff_src, bool(integ2.terminated)
+        return src, bool(it.terminated)
+
+    affect_neg = getattr(cb, "affect_neg", cb.affect)
+    if direction < 0:     # downcrossings only: the one affect that can run is affect_neg!
+        aff_src, term = trace_affect(affect_neg, "b2_affect")
+        return cond_src, aff_src, int(term)
+    aff_src, term = trace_affect(cb.affect, "b2_affect")
+    if direction == 0 and affect_neg is not cb.affect:
+        neg_src, term_neg = trace_affect(affect_neg, "b2_affect_neg")
+        aff_src += "#undef B2_HAS_AFFECT_NEG\n#define B2_HAS_AFFECT_NEG 1\n" + neg_src
+        return cond_src, aff_src, int(term) | (4 if term_neg else 0)
+    return cond_src, aff_src, int(term)
 
 
 def emit_vector_callback(cb, n_state, n_param):
@@ -274,14 +290,17 @@ def emit_vector_callback(cb, n_state, n_param):
         if any(g.has(sym) for g in gs):
             mask |= 1 << i
     body = _emit_body([f"g[{k}]" for k in range(nc)], gs)
-    cond_src = (f"#undef B2_COND_MASK\n#define B2_COND_MASK 0x{mask:x}u\n#define B2_NCOND {nc}\n"
+    direction = getattr(cb, "direction", 0)
+    vaffect = cb.affect_neg if direction < 0 else cb.affect
+    cond_src = ((f"#undef B2_EVENT_DIR\n#define B2_EVENT_DIR {direction}\n" if direction else "") +
+                f"#undef B2_COND_MASK\n#define B2_COND_MASK 0x{mask:x}u\n#define B2_NCOND {nc}\n"
                 "__device__ __forceinline__ void b2_vcondition(real* __restrict__ g, const real* __restrict__ u, "
                 "const real* __restrict__ p, const real t) {\n    (void)u; (void)p; (void)t;\n" + body + "\n}\n")
     cases, terminated = [], []
     for k in range(nc):
         it = _TraceIntegrator(n_state, n_param)
         try:
-            cb.affect(it, k + 1)
+            vaffect(it, k + 1)
         except NotImplementedError:
             raise   # a precise rejection (e.g. affect! writing integrator.p) is the message the user needs
         except Exception as e:
@@ -373,7 +392,7 @@ using std::sqrt; using std::pow; using std::sin; using std::cos; using std::exp;
 """
 
 
-def host_wrapper_source(sources, names=("b2_rhs", "b2_jac", "b2_tgrad", "b2_noise", "b2_condition", "b2_affect",
+def host_wrapper_source(sources, names=("b2_rhs", "b2_jac", "b2_tgrad", "b2_noise", "b2_condition", "b2_affect", "b2_affect_neg",
                                         "b2_dcondition", "b2_daffect", "b2_vcondition", "b2_vaffect")):
     """C++ translation unit exposing the emitted functions for float and double with C linkage
     (oracle side of the parity tests)."""
@@ -392,7 +411,7 @@ def host_wrapper_source(sources, names=("b2_rhs", "b2_jac", "b2_tgrad", "b2_nois
                 parts.append(f"int {nm}_{suf}(const {ty}* u, const {ty}* p, {ty} t) {{ return ns_{suf}::{nm}(u, p, t) ? 1 : 0; }}\n")
             elif nm == "b2_vaffect":
                 parts.append(f"void {nm}_{suf}({ty}* u, const {ty}* p, {ty} t, int idx) {{ ns_{suf}::{nm}(u, p, t, idx); }}\n")
-            elif nm in ("b2_affect", "b2_daffect"):
+            elif nm in ("b2_affect", "b2_affect_neg", "b2_daffect"):
                 parts.append(f"void {nm}_{suf}({ty}* u, const {ty}* p, {ty} t) {{ ns_{suf}::{nm}(u, p, t); }}\n")
             else:
                 parts.append(f"void {nm}_{suf}({ty}* o, const {ty}* u, const {ty}* p, {ty} t) {{ ns_{suf}::{nm}(o, u, p, t); }}\n")

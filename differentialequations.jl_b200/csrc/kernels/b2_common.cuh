@@ -26,6 +26,12 @@ typedef sreal real;
 #ifndef B2_HAS_DEVENT
 #define B2_HAS_DEVENT 0
 #endif
+// ContinuousCallback direction (an upcrossing triggers affect!, a downcrossing affect_neg!).  The condition
+// source redefines B2_EVENT_DIR: 0 both directions, +1 upcrossings only (affect_neg! = nothing), -1 downcrossings only
+// (affect! = nothing); the affect source sets B2_HAS_AFFECT_NEG 1 when it also defines b2_affect_neg (a downcrossing of
+// a scalar callback then runs it instead of b2_affect).  The direction is the sign of the condition at the step start.
+#define B2_EVENT_DIR 0
+#define B2_HAS_AFFECT_NEG 0
 #ifndef B2_HAS_MASS
 #define B2_HAS_MASS 0   // 1: the model source defines the constant mass matrix B2_MASS_[n*n] (Rodas family: M u' = f)
 #endif

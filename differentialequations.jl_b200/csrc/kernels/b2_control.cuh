@@ -86,15 +86,19 @@ __device__ __forceinline__ real b2_itp_left(real lo, real hi, real glo, real ghi
     }
     return lo;
 }
-__device__ __forceinline__ bool b2_sign_change(real gprev, real g) { return (gprev < 0 && g >= 0) || (gprev > 0 && g <= 0); }
+// a sign change relative to the sign at the step start, in an enabled direction (B2_EVENT_DIR, b2_common.cuh)
+__device__ __forceinline__ bool b2_sign_change(real gprev, real g) {
+    return (B2_EVENT_DIR >= 0 && gprev < 0 && g >= 0) || (B2_EVENT_DIR <= 0 && gprev > 0 && g <= 0);
+}
 
 // ---- scalar ContinuousCallback (A.8): sign change over interp_points samples of the dense output, then the ITP
 // root-find.  cond_start(): the event function at (u, tprev); cond_at(theta): on the interpolant; cond_end(): at
 // (u_new, tnew).  After an event at the end of the previous step the reference sign is taken at theta = 0.01
 // (repeat_nudge).  Returns true and the event's theta when the event fires inside this step.
+// `down` receives 1 when the event is a downcrossing (condition positive at the step start), else 0.
 template <class CondStart, class CondAt, class CondEnd>
 __device__ __forceinline__ bool b2_event_search(const int ip, const bool just_fired, CondStart&& cond_start, CondAt&& cond_at,
-                                                CondEnd&& cond_end, real& th_end) {
+                                                CondEnd&& cond_end, real& th_end, int& down) {
     real gprev, lo = 0, hi = 0, glo, ghi = 0;
     bool fired = false;
     if (just_fired) {
@@ -140,7 +144,10 @@ __device__ __forceinline__ bool b2_event_search(const int ip, const bool just_fi
             }
         }
     }
-    if (fired) th_end = b2_itp_left(lo, hi, glo, ghi, gprev, cond_at);
+    if (fired) {
+        th_end = b2_itp_left(lo, hi, glo, ghi, gprev, cond_at);
+        down = gprev < 0 ? 0 : 1;
+    }
     return fired;
 }
 

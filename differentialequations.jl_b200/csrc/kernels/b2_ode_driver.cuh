@@ -307,7 +307,7 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                                 fill_w(th);
                                 return b2_condition(w, p, b2_fma(th, dts, tprev));
                             },
-                            [&]() -> real { return b2_condition(un, p, tnew); }, th_end);
+                            [&]() -> real { return b2_condition(un, p, tnew); }, th_end, ev_idx);   // ev_idx: 1 = downcrossing
 #endif   // B2_NCOND
                         if (fired) tnew = b2_fma(th_end, dts, tprev);
 #endif
@@ -348,10 +348,20 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                 alg.interp(u, un, th_end, dts, w);
 #ifdef B2_NCOND
                 b2_vaffect(w, p, t, ev_idx);
-                if ((B2_VTERM_MASK >> ev_idx) & 1u) rc = B2_RC_TERMINATED;   // this index's affect! called terminate!
+                if (((B2_VTERM_MASK >> ev_idx) & 1u) || (a.event_terminate & 1)) rc = B2_RC_TERMINATED;   // this index's affect! called terminate!
 #else
-                (void)ev_idx;
+#if B2_HAS_AFFECT_NEG   // a downcrossing runs affect_neg! (event_terminate bit 2: it calls terminate!)
+                if (ev_idx == 1) {
+                    b2_affect_neg(w, p, t);
+                    if (a.event_terminate & 4) rc = B2_RC_TERMINATED;
+                } else {
+                    b2_affect(w, p, t);
+                    if (a.event_terminate & 1) rc = B2_RC_TERMINATED;
+                }
+#else
                 b2_affect(w, p, t);
+                if (a.event_terminate & 1) rc = B2_RC_TERMINATED;
+#endif
 #endif
 #pragma unroll
                 for (int i = 0; i < B2_N; i++) u[i] = w[i];
@@ -359,7 +369,6 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                 alg.start(u, p, t);
                 nf++;
                 just_fired = true;
-                if (a.event_terminate & 1) rc = B2_RC_TERMINATED;
             } else
 #endif
             {

@@ -464,7 +464,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                         scatter(eun);
                         return b2_condition(w, pe, tnew);
                     },
-                    th_end);
+                    th_end, ev_idx);   // ev_idx: 1 = downcrossing
 #endif
             }
             if (g == 0) s_evidx[lane] = ev_idx;
@@ -524,6 +524,9 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
             load_params(pa);
 #ifdef B2_NCOND
             b2_vaffect(W, pa, tnew, ev_idx);   // per lane: the index of the function that fired
+#elif B2_HAS_AFFECT_NEG
+            if (ev_idx == 1) b2_affect_neg(W, pa, tnew);   // per lane: a downcrossing runs affect_neg!
+            else b2_affect(W, pa, tnew);
 #else
             b2_affect(W, pa, tnew);
 #endif
@@ -537,7 +540,7 @@ __device__ __forceinline__ void b2_ode_driver_split(const B2Args& a) {
                 nevents++;
                 nf++;
                 just_fired = true;
-                if (a.event_terminate & 1) rc = B2_RC_TERMINATED;
+                if (a.event_terminate & ((B2_HAS_AFFECT_NEG && ev_idx == 1) ? 4 : 1)) rc = B2_RC_TERMINATED;
 #ifdef B2_NCOND
                 if ((B2_VTERM_MASK >> ev_idx) & 1u) rc = B2_RC_TERMINATED;   // this index's affect! called terminate!
 #endif

@@ -131,38 +131,53 @@ function callback_sources(callback, us, ps, t)
     term = 0; ip = 10
     integ0 = TraceIntegrator(copy(us), Tuple(ps), t, false)
     if !isempty(cont)
+        # direction of every continuous callback (SURVEY A.8): 0 both, +1 upcrossings only (affect_neg! === nothing),
+        # -1 downcrossings only (affect! === nothing)
+        cbdir(c) = c.affect_neg! === nothing ? 1 : (c.affect! === nothing ? -1 : 0)
         for c in cont
-            c.affect_neg! === c.affect! || error("EnsembleB200: affect_neg! different from affect! is not supported")
+            (c.affect! === nothing && c.affect_neg! === nothing) && error("EnsembleB200: affect! and affect_neg! are both nothing")
             c.save_positions == (false, false) || c.save_positions == (true, true) ||   # with saveat upstream's GPU path requires (false,false); (true,true) is the CPU default and has no effect with saveat
                 error("EnsembleB200: save_positions = $(c.save_positions) is not supported")
         end
         ip = cont[1].interp_points
         all(c -> c.interp_points == ip, cont) || error("EnsembleB200: all continuous callbacks must share interp_points")
         if length(cont) == 1 && cont[1] isa SciMLBase.ContinuousCallback
-            g = cont[1].condition(us, t, integ0)
-            newu, terminated = trace_affect(cont[1].affect!, us, ps, t)
-            csrc = "#undef B2_COND_MASK\n#define B2_COND_MASK 0x$(string(cond_mask([g], us), base = 16))u\n" * scalar_fn("b2_condition", "real", g)
+            c1 = cont[1]; d1 = cbdir(c1)
+            g = c1.condition(us, t, integ0)
+            csrc = (d1 == 0 ? "" : "#undef B2_EVENT_DIR\n#define B2_EVENT_DIR $d1\n") *
+                   "#undef B2_COND_MASK\n#define B2_COND_MASK 0x$(string(cond_mask([g], us), base = 16))u\n" * scalar_fn("b2_condition", "real", g)
+            # the one affect that can run is b2_affect; a two-sided callback with its own affect_neg! adds b2_affect_neg
+            newu, terminated = trace_affect(d1 < 0 ? c1.affect_neg! : c1.affect!, us, ps, t)
             asrc = affect_fn("b2_affect", newu)
             term |= terminated ? 1 : 0
+            if d1 == 0 && c1.affect_neg! !== c1.affect!
+                newn, termn = trace_affect(c1.affect_neg!, us, ps, t)
+                asrc *= "#undef B2_HAS_AFFECT_NEG\n#define B2_HAS_AFFECT_NEG 1\n" * affect_fn("b2_affect_neg", newn)
+                term |= termn ? 4 : 0
+            end
         else
             # several ContinuousCallbacks and/or VectorContinuousCallbacks: one vector callback on the device
             gs = Num[]; branches = String[]; tmask = UInt32(0)
+            dset = cbdir(cont[1])
+            all(c -> cbdir(c) == dset && (dset != 0 || c.affect_neg! === c.affect!), cont) ||
+                error("EnsembleB200: several continuous callbacks need one common direction (all two-sided with affect_neg! === affect!, all upcrossing-only or all downcrossing-only)")
             for c in cont
                 if c isa SciMLBase.VectorContinuousCallback
                     out = Vector{Num}(undef, c.len); c.condition(out, us, t, integ0)
                     for k in 1:c.len
-                        newu, terminated = trace_affect(c.affect!, us, ps, t, k)
+                        newu, terminated = trace_affect(dset < 0 ? c.affect_neg! : c.affect!, us, ps, t, k)
                         push!(gs, out[k]); push!(branches, join(["u[$(i - 1)] = " * string(cexpr(e)) * ";" for (i, e) in enumerate(newu)], " "))
                         terminated && (tmask |= UInt32(1) << (length(gs) - 1))
                     end
                 else
-                    newu, terminated = trace_affect(c.affect!, us, ps, t)
+                    newu, terminated = trace_affect(dset < 0 ? c.affect_neg! : c.affect!, us, ps, t)
                     push!(gs, c.condition(us, t, integ0)); push!(branches, join(["u[$(i - 1)] = " * string(cexpr(e)) * ";" for (i, e) in enumerate(newu)], " "))
                     terminated && (tmask |= UInt32(1) << (length(gs) - 1))
                 end
             end
             length(gs) <= 16 || error("EnsembleB200: at most 16 event functions")
-            csrc = "#undef B2_COND_MASK\n#define B2_COND_MASK 0x$(string(cond_mask(gs, us), base = 16))u\n#define B2_NCOND $(length(gs))\n" *
+            csrc = (dset == 0 ? "" : "#undef B2_EVENT_DIR\n#define B2_EVENT_DIR $dset\n") *
+                   "#undef B2_COND_MASK\n#define B2_COND_MASK 0x$(string(cond_mask(gs, us), base = 16))u\n#define B2_NCOND $(length(gs))\n" *
                    vector_fn("b2_vcondition", "g", gs)
             # the right-hand sides read the PRE-event state: copy it first
             asrc = "#define B2_VTERM_MASK 0x$(string(tmask, base = 16))u\n" *

@@ -73,6 +73,11 @@ enum b200ens_error {
  *   __device__ void b2_noise    (real* g,  const real* u, const real* p, real t);   diagonal noise
  *   __device__ real b2_condition(const real* u, const real* p, real t);             ContinuousCallback
  *   __device__ void b2_affect   (real* u,  const real* p, real t);
+ *   direction (upstream: an upcrossing runs affect!, a downcrossing affect_neg!; `nothing` ignores that direction):
+ *   condition_src may carry `#undef B2_EVENT_DIR` + `#define B2_EVENT_DIR +1` (upcrossings only) or `-1`
+ *   (downcrossings only; b2_affect is then the downcrossing affect); a two-sided callback whose affect_neg! differs
+ *   from affect! adds `#undef B2_HAS_AFFECT_NEG` + `#define B2_HAS_AFFECT_NEG 1` and
+ *   __device__ void b2_affect_neg(real* u, const real* p, real t);                to affect_src
  *   VectorContinuousCallback (qa.jl:124): condition_src carries `#define B2_NCOND <len>` and defines
  *   __device__ void b2_vcondition(real* g, const real* u, const real* p, real t);   affect_src defines
  *   __device__ void b2_vaffect  (real* u,  const real* p, real t, int idx);         idx = 0-based event index
@@ -120,7 +125,8 @@ typedef struct b200ens_opts {
     uint64_t seed;          /* Philox key */
     uint64_t traj_offset;   /* global index of trajectory 0 of this call (Philox counter base) */
     int32_t noise_injected; /* 1: dW holds the Brownian increments; 0: Philox4x32-10 on device */
-    int32_t event_terminate;/* bit 0: the ContinuousCallback terminates the trajectory (terminate!); bit 1: the DiscreteCallback does */
+    int32_t event_terminate;/* bit 0: the ContinuousCallback's affect! terminates the trajectory (terminate!); bit 1: the DiscreteCallback
+                               does; bit 2: the ContinuousCallback's affect_neg! does (read only when affect_src defines b2_affect_neg) */
     int32_t interp_points;  /* ContinuousCallback interp_points, <=0: 10 */
     int32_t save_tstops;    /* -1 auto (on for Rodas*), 0 interpolate, 1 saveat points are tstops */
     uint32_t device_mask;   /* bit g set: use CUDA device g; 0: all visible devices */

@@ -72,6 +72,11 @@ typedef struct {
                                  log2 / exp2).  ODE steppers only.  Exists to MEASURE what the contract changes
                                  (tests/test_spec_arith.py); the kernels are compared bit for bit against spec_arith = 0 */
     int32_t n_tstops;         /* solve(...; tstops): number of entries of tstops */
+    int32_t event_dir;        /* ContinuousCallback / VectorContinuousCallback direction (an upcrossing triggers affect!, a
+                                 downcrossing affect_neg!): 0 both, +1 upcrossings only (affect_neg! = nothing), -1 downcrossings only
+                                 (affect! = nothing).  The direction is the sign of the condition at the step start */
+    int32_t pad2_;
+    void* affect_neg;         /* NULL: downcrossings run `affect` (upstream's default affect_neg! = affect!) */
     const double* tstops;     /* ascending times the integrator must hit exactly (handle_tstop!); compared in the
                                  state type; entries outside (t0, t1) are ignored.  ODE steppers only */
 } orc_opts;

@@ -37,6 +37,7 @@ class Opts(C.Structure):
         ("mass", C.POINTER(C.c_double)),
         ("every_t", C.c_void_p), ("save_everystep", C.c_int32), ("sde_adaptive", C.c_int32),
         ("noise_stream_len", C.c_int64), ("spec_arith", C.c_int32), ("n_tstops", C.c_int32),
+        ("event_dir", C.c_int32), ("pad2_", C.c_int32), ("affect_neg", C.c_void_p),
         ("tstops", C.POINTER(C.c_double)),
     ]
 
@@ -107,7 +108,7 @@ def fns_from_host_model(dll, f64):
     out = {}
     for key, nm in (("rhs", "b2_rhs"), ("jac", "b2_jac"), ("tgrad", "b2_tgrad"), ("noise", "b2_noise"),
                     ("cond", "b2_condition"), ("affect", "b2_affect"), ("dcond", "b2_dcondition"),
-                    ("daffect", "b2_daffect"), ("vcond", "b2_vcondition"), ("vaffect", "b2_vaffect")):
+                    ("daffect", "b2_daffect"), ("vcond", "b2_vcondition"), ("vaffect", "b2_vaffect"), ("affect_neg", "b2_affect_neg")):
         try:
             out[key] = C.cast(getattr(dll, f"{nm}_{suf}"), C.c_void_p).value
         except AttributeError:
@@ -117,7 +118,7 @@ def fns_from_host_model(dll, f64):
 
 def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adaptive=True, dtype=np.float64,
           maxiters=100000, dW=None, seed=0, event=False, terminate=False, interp_points=10, nthreads=0,
-          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, ncond=0, vterm_mask=0, mass_matrix=None, save_everystep=0, sde_adaptive=False, spec_arith=False, tstops=None, **ctl):
+          fns=None, want_stats=True, save_tstops=None, traj_offset=0, devent=False, dterminate=False, ncond=0, vterm_mask=0, mass_matrix=None, save_everystep=0, sde_adaptive=False, spec_arith=False, tstops=None, event_dir=0, terminate_neg=False, **ctl):
     """Run the oracle.  model: built-in name, or fns = dict(rhs=ptr, jac=ptr, ...)."""
     L = lib()
     f64 = np.dtype(dtype) == np.float64
@@ -147,7 +148,8 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
     o.noise_injected = 0 if dW is None else 1
     o.seed = seed
     o.traj_offset = traj_offset
-    o.has_event, o.event_terminate, o.interp_points = int(event), int(terminate), interp_points
+    o.has_event, o.event_terminate, o.interp_points = int(event), int(bool(terminate)) | (4 if terminate_neg else 0), interp_points
+    o.event_dir = int(event_dir)   # 0 both directions, +1 upcrossings only, -1 downcrossings only
     if save_tstops is None:
         save_tstops = alg in ("Rodas4", "Rodas5", "Rodas5P")
     o.save_tstops = int(save_tstops)
@@ -162,6 +164,7 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
     o.rhs, o.jac, o.noise = get("rhs"), get("jac"), get("noise")
     o.tgrad = get("tgrad") if fns else None
     o.cond, o.affect = (get("cond"), get("affect")) if event and not ncond else (None, None)
+    o.affect_neg = (fns or {}).get("affect_neg") if (event and not ncond and fns) else None
     if ncond:   # VectorContinuousCallback
         o.vcond, o.vaffect, o.ncond, o.vterm_mask = get("vcond"), get("vaffect"), int(ncond), int(vterm_mask)
     o.dcond, o.daffect = (get("dcond"), get("daffect")) if devent else (None, None)

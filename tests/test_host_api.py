@@ -73,9 +73,9 @@ def test_callback_tracing_and_rejection(B):
 
     cb = B.ContinuousCallback(lambda u, t, integ: u[0] - integ.p[1], lambda integ: integ.u.__setitem__(0, integ.u[0] + 1))
     cond, aff, term = codegen.emit_callback(cb, 2, 2)
-    assert "return -p[1] + u[0];" in cond and "u[0] = n0;" in aff and term is False
+    assert "return -p[1] + u[0];" in cond and "u[0] = n0;" in aff and term == 0
     cbt = B.ContinuousCallback(lambda u, t, integ: t - 0.5, lambda integ: B.terminate_b(integ))
-    assert codegen.emit_callback(cbt, 1, 1)[2] is True
+    assert codegen.emit_callback(cbt, 1, 1)[2] == 1   # bit 0: affect! terminates (bit 2: affect_neg!)
 
     def opaque(u, t, integ):
         return 1.0 if float(u[0]) > 0 else -1.0             # not symbolically traceable

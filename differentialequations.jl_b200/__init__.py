@@ -19,13 +19,13 @@ packs the per-trajectory u0/p matrices and wraps the outputs.  No CPU fallback e
 from . import _lib, codegen
 from . import analysis as EnsembleAnalysis
 from ._lib import B200EnsError, Model, pinned_empty
-from .api import (EM, SOSRA, SRIW1, CallbackSet, ContinuousCallback, DiscreteCallback, EnsembleB200, EnsembleContext, EnsembleProblem, get_rng, has_rng, EnsembleSolution,
+from .api import (EM, FBDF, SOSRA, SRIW1, CallbackSet, ContinuousCallback, DiscreteCallback, EnsembleB200, EnsembleContext, EnsembleProblem, get_rng, has_rng, EnsembleSolution,
                   EnsembleSummary, ODEFunction, ODEProblem, SDEFunction, successful_retcode,
                   ODESolution, ReturnCode, Rodas4, Rodas5, Rodas5P, Rosenbrock23, SDEProblem, Tsit5, VectorContinuousCallback, Vern7,
                   ReducedEnsembleSolution, build_model, remake, solve, terminate_b)
 
 __all__ = [
     "ODEProblem", "SDEProblem", "ODEFunction", "SDEFunction", "successful_retcode", "EnsembleProblem", "EnsembleB200", "EnsembleContext", "get_rng", "has_rng", "EnsembleSolution", "EnsembleSummary", "ODESolution", "ReturnCode",
-    "ContinuousCallback", "VectorContinuousCallback", "DiscreteCallback", "CallbackSet", "remake", "solve", "terminate_b", "Tsit5", "Vern7", "Rosenbrock23", "Rodas4", "Rodas5",
+    "ContinuousCallback", "VectorContinuousCallback", "DiscreteCallback", "CallbackSet", "remake", "solve", "terminate_b", "Tsit5", "Vern7", "Rosenbrock23", "FBDF", "Rodas4", "Rodas5",
     "Rodas5P", "EM", "SOSRA", "SRIW1", "build_model", "Model", "B200EnsError", "pinned_empty", "EnsembleAnalysis", "ReducedEnsembleSolution",
 ]

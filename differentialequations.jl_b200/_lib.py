@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libb200ens.so")
 
 F32, F64 = 0, 1
-ALG_IDS = {"Tsit5": 1, "Vern7": 2, "Rosenbrock23": 3, "Rodas5": 4, "Rodas5P": 5, "EM": 6, "SOSRA": 7, "Rodas4": 8, "SRIW1": 9}
+ALG_IDS = {"Tsit5": 1, "Vern7": 2, "Rosenbrock23": 3, "Rodas5": 4, "Rodas5P": 5, "EM": 6, "SOSRA": 7, "Rodas4": 8, "SRIW1": 9, "FBDF": 10}
 MODEL_FAST_MATH = 1
 MODEL_KSMEM = 4
 MODEL_SPLIT = 8

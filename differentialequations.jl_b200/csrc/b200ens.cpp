@@ -95,6 +95,7 @@ bool is_sde(int alg) { return alg == B200ENS_EM || alg == B200ENS_SOSRA || alg =
 bool is_rosenbrock(int alg) {
     return alg == B200ENS_ROSENBROCK23 || alg == B200ENS_RODAS4 || alg == B200ENS_RODAS5 || alg == B200ENS_RODAS5P;
 }
+bool needs_jac(int alg) { return is_rosenbrock(alg) || alg == B200ENS_FBDF; }   // W = I/(gamma dt) - J or I - beta dt J
 int alg_order(int alg) {
     switch (alg) {
     case B200ENS_TSIT5: return 5;
@@ -498,7 +499,7 @@ int ensure_loaded(b200ens_model* m) {
     // optional entry points are looked up only in modules that define them (kernels/b2_entry.cuh): no failing API
     // calls on the normal path (they show up as errors under compute-sanitizer)
     const bool erk = m->alg == B200ENS_TSIT5 || m->alg == B200ENS_VERN7;
-    if (erk || is_rosenbrock(m->alg))
+    if (erk || needs_jac(m->alg))
         CU(cudaLibraryGetKernel(&m->kernel_adaptive, m->lib, "b2_ensemble_kernel_adaptive"));
     if (!is_sde(m->alg)) {
         CU(cudaLibraryGetKernel(&m->k_work_keys, m->lib, "b2_work_keys"));
@@ -1354,10 +1355,12 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     if (d->n_state < 1 || d->n_state > 32) return fail(B200ENS_E_INVALID, "n_state must be in 1..32");
     if (d->n_param < 0 || d->n_param > 64) return fail(B200ENS_E_INVALID, "n_param must be in 0..64");
     if (d->dtype != B200ENS_F32 && d->dtype != B200ENS_F64) return fail(B200ENS_E_INVALID, "bad dtype");
-    if (d->alg < B200ENS_TSIT5 || d->alg > B200ENS_SRIW1) return fail(B200ENS_E_INVALID, "bad alg id %d", d->alg);
+    if (d->alg < B200ENS_TSIT5 || d->alg > B200ENS_FBDF) return fail(B200ENS_E_INVALID, "bad alg id %d", d->alg);
     if (!d->rhs_src) return fail(B200ENS_E_INVALID, "rhs_src is required");
-    if (is_rosenbrock(d->alg) && !d->jac_src)
-        return fail(B200ENS_E_UNSUPPORTED, "Rosenbrock methods need the analytic Jacobian (jac_src); there is no AD/finite-difference fallback");
+    if (needs_jac(d->alg) && !d->jac_src)
+        return fail(B200ENS_E_UNSUPPORTED, "Rosenbrock methods and FBDF need the analytic Jacobian (jac_src); there is no AD/finite-difference fallback");
+    if (d->alg == B200ENS_FBDF && (d->condition_src || d->dcondition_src))
+        return fail(B200ENS_E_UNSUPPORTED, "callbacks with FBDF are not supported (an event restarts the multistep history; use a Rosenbrock method)");
     if (is_sde(d->alg) && !d->noise_src) return fail(B200ENS_E_INVALID, "SDE algorithms need noise_src");
     if ((d->flags & B200ENS_MODEL_SDE_ADAPTIVE) && d->alg != B200ENS_SOSRA && d->alg != B200ENS_SRIW1)
         return fail(B200ENS_E_UNSUPPORTED, "B200ENS_MODEL_SDE_ADAPTIVE needs a stepper with an embedded error estimate: SRIW1 or SOSRA");

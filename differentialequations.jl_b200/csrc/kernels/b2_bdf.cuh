@@ -1,0 +1,325 @@
+// b2_bdf.cuh -- FBDF: variable-order (1..5), variable-step BDF in fixed-leading-coefficient form with a per-thread
+// register LU and the analytic Jacobian b2_jac.  Reference name: FBDF /root/reference/test/qa/qa.jl:57 (re-exported from
+// OrdinaryDiffEq).  Restated from the published algorithm [UPSTREAM-RECALLED structure: the last
+// k+1 solution values kept at their own times, re-sampled on the equidistant grid of the current dt by Lagrange
+// interpolation, constant-step BDF-k coefficients, divided-difference error and order estimates]; the written contract
+// is oracle/oracle_impl.inc (fbdf_step / fbdf_accept / fbdf_reject / fbdf_push), mirrored here operation for operation.
+//
+//   history   (x_j, h_j), j = 0..k, x_0 = t, newest first                       -- per-thread local arrays (k is run-time)
+//   predictor Lagrange interpolant of the history at t + dt                     (first step: u0 = uprev)
+//   corrector z + tmp = beta_k dt f(z, t + dt), tmp = sum_j cw_j h_j; simplified Newton, W = I - beta dt J(uprev, t)
+//             factored once per step, convergence-rate test (kappa = 1/100, <= 10 iterations)
+//   estimates terk_m = m! dt^m [t+dt, x_0..x_{m-1}]u, lte = -(1/(k+1) + sum_j (a_j/beta) r_j) terk_{k+1}
+//   control   the driver's OWN_CONTROL path (b2_ode_driver.cuh): accept iff ||lte|| <= 1, order +-1 from the scaled
+//             norms T_m, dt_new = dt / q with q = (2 T_k/(k+1))^(1/(k+1)) and a steady band, Newton failure: dt/2
+// Saveat uses the cubic Hermite interpolant on (uprev, f(uprev)), (u, f(u)) -- upstream's default for multistep methods.
+#pragma once
+#include "b2_common.cuh"
+#include "b2_rosenbrock.cuh"   // B2LU
+
+// [k][0] = beta_k, [k][j] = a_j: u_{n+1} + sum_j a_j u_{n+1-j} = beta dt f(u_{n+1})
+__constant__ double B2_BDFC[6][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {1.0, -1.0, 0, 0, 0, 0},
+    {2.0 / 3.0, -4.0 / 3.0, 1.0 / 3.0, 0, 0, 0},
+    {6.0 / 11.0, -18.0 / 11.0, 9.0 / 11.0, -2.0 / 11.0, 0, 0},
+    {12.0 / 25.0, -48.0 / 25.0, 36.0 / 25.0, -16.0 / 25.0, 3.0 / 25.0, 0},
+    {60.0 / 137.0, -300.0 / 137.0, 300.0 / 137.0, -200.0 / 137.0, 75.0 / 137.0, -12.0 / 137.0}};
+// 1/(m+1) and log2(m+1) as Float32 constants, m = 0..6
+__constant__ float B2_INVP1[7] = {1.0f, 0.5f, 0.333333343f, 0.25f, 0.2f, 0.166666672f, 0.142857149f};
+__constant__ float B2_LG2P1[7] = {0.0f, 1.0f, 1.5849625f, 2.0f, 2.32192802f, 2.5849625f, 2.80735493f};
+
+struct B2Fbdf {
+    static constexpr int ORDER = 1;          // initial-dt exponent and controller defaults (the order itself is run-time)
+    static constexpr int DEG = 0;
+    static constexpr bool OWN_CONTROL = true;
+    __device__ __forceinline__ void bind(real*) {}
+    __device__ __forceinline__ void poly_coeffs(int, real (&)[1]) const {}
+
+    real f0[B2_N], fnew[B2_N];
+    int k, ncons, consfail, iters, nlfails;
+    float eta_old;
+    real ts[7];
+    real hist[7][B2_N];
+    float T2[8];
+
+    __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {
+        b2_rhs(f0, u, p, t);
+        k = 1;
+        ncons = consfail = iters = nlfails = 0;
+        eta_old = 1.0f;
+    }
+    __device__ __forceinline__ real fsal0(int i) const { return f0[i]; }
+
+    // Lagrange basis values L_j(x) of the points ts[0..k]
+    __device__ __forceinline__ void lagrange_w(real x, real (&L)[7]) const {
+        for (int j = 0; j <= k; j++) {
+            real num = 1, den = 1;
+            for (int m = 0; m <= k; m++) {
+                if (m == j) continue;
+                num = num * (x - ts[m]);
+                den = den * (ts[j] - ts[m]);
+            }
+            L[j] = num / den;
+        }
+    }
+
+    // one step attempt; returns true when the Newton iteration failed (un / ut are then meaningless)
+    __device__ __forceinline__ bool step(const real (&up)[B2_N], const real (&p)[B2_NPA], real t, real dt, real (&un)[B2_N],
+                                         real (&ut)[B2_N], const B2Args& a, int& nf) {
+        const real tdt = t + dt;
+        const real beta = (real)B2_BDFC[k][0];
+        real L[7], cw[7], z[B2_N], tmp[B2_N];
+        if (iters == 0) {
+            ts[0] = t;
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) hist[0][i] = up[i];
+        }
+        // predictor
+        if (iters >= 1) {
+            lagrange_w(tdt, L);
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) {
+                real s = L[0] * hist[0][i];
+                for (int j = 1; j <= k; j++) s = b2_fma(L[j], hist[j][i], s);
+                z[i] = s;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) z[i] = up[i];
+        }
+        // tmp = sum_j cw_j h_j: the BDF-k combination of the history re-sampled at t - i dt
+        for (int j = 0; j <= k; j++) cw[j] = 0;
+        cw[0] = (real)B2_BDFC[k][1];
+        for (int i = 1; i <= k - 1; i++) {
+            lagrange_w(t - (real)i * dt, L);
+            const real ai = (real)B2_BDFC[k][i + 1];
+            for (int j = 0; j <= k; j++) cw[j] = b2_fma(ai, L[j], cw[j]);
+        }
+        const int kk = k > 1 ? k : 0;
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) {
+            real s = cw[0] * hist[0][i];
+            for (int j = 1; j <= kk; j++) s = b2_fma(cw[j], hist[j][i], s);
+            tmp[i] = s;
+        }
+        // W = I - beta dt J(uprev, t)
+        const real bdt = beta * dt;
+        B2LU lu;
+        {
+            real J[B2_N * B2_N];
+            b2_jac(J, up, p, t);
+#pragma unroll
+            for (int i = 0; i < B2_N; i++)
+#pragma unroll
+                for (int j = 0; j < B2_N; j++) lu.A[i][j] = b2_fma(-bdt, J[i * B2_N + j], (i == j) ? (real)1 : (real)0);
+        }
+        lu.factor();
+        const float inv_n = __fdiv_rn(1.0f, (float)B2_N), kappa = 0.01f;
+        float eta = b2_fastexp2(__fmul_rn(0.8f, b2_fastlog2(fmaxf(eta_old, 1.1920929e-7f))));
+        float ndz_prev = 0.0f;
+        bool conv = false;
+        for (int it = 1; it <= 10; it++) {
+            real fz[B2_N], dz[B2_N];
+            b2_rhs(fz, z, p, tdt);
+            nf++;
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) dz[i] = b2_fma(bdt, fz[i], -(z[i] + tmp[i]));
+            lu.solve(dz);
+            float acc = 0.0f;
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) {
+                const real sk = b2_fma(b2_max(b2_abs(up[i]), b2_abs(z[i])), B2_RTOL(a, i), B2_ATOL(a, i));
+                const float r = __fmul_rn((float)dz[i], b2_rcp_nr((float)sk));
+                acc = __fmaf_rn(r, r, acc);
+            }
+            const float ndz = __fsqrt_rn(__fmul_rn(acc, inv_n));
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) z[i] = z[i] + dz[i];
+            if (!(ndz == ndz)) break;                 // NaN: failure
+            if (it == 1) {
+                if (ndz < 1e-5f) {
+                    conv = true;
+                    break;
+                }
+            } else {
+                const float theta = __fdiv_rn(ndz, ndz_prev);
+                if (theta > 2.0f) break;              // diverging
+                if (theta < 1.0f) {
+                    float pw = 1.0f;
+                    for (int m = 0; m < 10 - it; m++) pw = __fmul_rn(pw, theta);
+                    const float om = __fsub_rn(1.0f, theta);
+                    if (__fdiv_rn(__fmul_rn(ndz, pw), om) > kappa) break;   // will not get there in the remaining iterations
+                    eta = __fdiv_rn(theta, om);
+                } else {
+                    eta = 1e30f;
+                }
+            }
+            if (__fmul_rn(eta, ndz) < kappa) {
+                conv = true;
+                break;
+            }
+            ndz_prev = ndz;
+        }
+        if (!conv) {
+            nlfails++;
+            return true;
+        }
+        nlfails = 0;
+        eta_old = eta;
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) un[i] = z[i];
+        // divided differences through the new point: y_0 = t + dt, y_j = x_{j-1}
+        float rsk[B2_N];
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) {
+            const real sk = b2_fma(b2_max(b2_abs(up[i]), b2_abs(un[i])), B2_RTOL(a, i), B2_ATOL(a, i));
+            rsk[i] = b2_rcp_nr((float)sk);
+        }
+        const int Lv = (k + 1 < iters + 1) ? k + 1 : iters + 1;   // levels the history supports (k+1 unless first step)
+        real y[8], d[8][B2_N], fac = 1;
+        y[0] = tdt;
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) d[0][i] = un[i];
+        for (int j = 1; j <= Lv; j++) {
+            y[j] = ts[j - 1];
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) d[j][i] = hist[j - 1][i];
+        }
+        for (int m = 0; m < 8; m++) T2[m] = 0.0f;
+        {
+            float acc = 0.0f;
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) {
+                const float r = __fmul_rn((float)d[0][i], rsk[i]);
+                acc = __fmaf_rn(r, r, acc);
+            }
+            T2[0] = __fmul_rn(acc, inv_n);
+        }
+        real terkp1[B2_N];
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) terkp1[i] = 0;
+        for (int l = 1; l <= Lv; l++) {
+            for (int j = 0; j + l <= Lv; j++) {
+                const real inv = (real)1 / (y[j] - y[j + l]);
+#pragma unroll
+                for (int i = 0; i < B2_N; i++) d[j][i] = (d[j][i] - d[j + 1][i]) * inv;
+            }
+            fac = fac * ((real)l * dt);
+            float acc = 0.0f;
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) {
+                const real v = fac * d[0][i];
+                if (l == k + 1) terkp1[i] = v;
+                const float r = __fmul_rn((float)v, rsk[i]);
+                acc = __fmaf_rn(r, r, acc);
+            }
+            T2[l] = __fmul_rn(acc, inv_n);
+        }
+        if (Lv < k + 1) {
+            // first step (one history point): the error estimate is the change of the solution itself
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) ut[i] = un[i] - up[i];
+        } else {
+            real cl = (real)1 / (real)(k + 1);
+            for (int j = 2; j <= k; j++) {
+                const real xj = t - (real)(j - 1) * dt;
+                real num = 1;
+                for (int m = 0; m <= k; m++) num = num * (xj - ts[m]);
+                cl = b2_fma((real)(B2_BDFC[k][j] / B2_BDFC[k][0]), num / fac, cl);
+            }
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) ut[i] = cl * terkp1[i];
+        }
+        if (!(ncons > k + 1 && k < 5)) T2[k + 1] = 0.0f;   // the order-(k+1) estimate is only trusted after k+2 steps at order k
+        return false;
+    }
+
+    // accepted step: order selection and the next dt (as a multiplier of dt)
+    __device__ __forceinline__ float accept(float qmin, float qmax) {
+        const float* T = T2;
+        int kn = k;
+        if (kn < 5 && ncons >= kn + 2 &&
+            ((kn == 1 && T[1] > T[2]) || (kn == 2 && T[1] > T[2] && T[2] > T[3]) ||
+             (kn > 2 && T[kn - 2] > T[kn - 1] && T[kn - 1] > T[kn] && T[kn] > T[kn + 1]))) {
+            kn++;
+        } else {
+            while (kn > 2 && !(T[kn - 2] > T[kn - 1] && T[kn - 1] > T[kn] && T[kn] > T[kn + 1])) kn--;
+        }
+        const float terk2 = T[kn];
+        if (kn != k) ncons = 0;
+        k = kn;
+        float qi;
+        if (terk2 == 0.0f) {
+            qi = qmax;
+        } else {
+            // log2 q = (1 + log2(T_k) - log2(k+1)) / (k+1)
+            const float lq = __fmul_rn(__fsub_rn(__fadd_rn(1.0f, __fmul_rn(0.5f, b2_fastlog2(terk2))), B2_LG2P1[kn]), B2_INVP1[kn]);
+            qi = (lq >= 0.0f && lq <= 1.0f) ? 1.0f : b2_fastexp2(-lq);   // steady band: 1 <= q <= 2 keeps dt
+            qi = fminf(qmax, fmaxf(qmin, qi));
+        }
+        consfail = 0;
+        ncons++;
+        iters++;
+        return qi;
+    }
+    // rejected step (||lte|| > 1): new dt multiplier, possibly one order down
+    __device__ __forceinline__ float reject(float EE2) {
+        const int k0 = k;
+        consfail++;
+        ncons = 0;
+        const float half = consfail > 1 ? 0.5f : 1.0f;
+        const float lz = 0.26303440f;   // log2(1.2)
+        float l = -__fadd_rn(lz, __fmul_rn(__fmul_rn(0.5f, b2_fastlog2(EE2)), B2_INVP1[k0]));
+        if (k0 > 1) {
+            const float lm = T2[k0 - 1] > 0.0f ? -__fadd_rn(lz, __fmul_rn(__fmul_rn(0.5f, b2_fastlog2(T2[k0 - 1])), B2_INVP1[k0 - 1])) : 0.0f;
+            if (lm > l) {
+                l = lm;
+                k = k0 - 1;
+            }
+        }
+        return __fmul_rn(half, b2_fastexp2(fminf(l, 0.0f)));
+    }
+    // Newton failure: the driver halves dt; one order down after three failures in a row
+    __device__ __forceinline__ void newton_fail() {
+        if (k > 1 && nlfails >= 3) k--;
+        consfail++;
+        ncons = 0;
+    }
+    __device__ __forceinline__ void fixed_accept() { iters++; }   // fixed step: the order stays 1 (backward Euler)
+
+    // f(u_new) (Hermite end slope) and the history push: the order is already the next step's
+    __device__ __forceinline__ void accepted(const real (&u)[B2_N], const real (&p)[B2_NPA], real tnew, int& nf) {
+        b2_rhs(fnew, u, p, tnew);
+        nf += 1;
+        const int top = k + 1 < 6 ? k + 1 : 6;
+        for (int j = top; j >= 1; j--) {
+            ts[j] = ts[j - 1];
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) hist[j][i] = hist[j - 1][i];
+        }
+        ts[0] = tnew;
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) hist[0][i] = u[i];
+    }
+    __device__ __forceinline__ void prepare_dense(const real (&)[B2_N], const real (&)[B2_NPA], real, real, int&) {}
+    // cubic Hermite on (up, f0), (un, fnew): the default dense output of multistep methods
+    __device__ __forceinline__ void interp(const real (&up)[B2_N], const real (&un)[B2_N], real th, real dt,
+                                           real (&out)[B2_N]) const {
+        const real om = (real)1 - th;
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) {
+            const real du = un[i] - up[i];
+            real inner = ((real)1 - (real)2 * th) * du;
+            inner = b2_fma((th - (real)1) * dt, f0[i], inner);
+            inner = b2_fma(th * dt, fnew[i], inner);
+            real v = om * up[i];
+            v = b2_fma(th, un[i], v);
+            out[i] = b2_fma(th * (th - (real)1), inner, v);
+        }
+    }
+    __device__ __forceinline__ void advance() {
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) f0[i] = fnew[i];
+    }
+};

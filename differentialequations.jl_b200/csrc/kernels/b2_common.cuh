@@ -59,6 +59,7 @@ typedef sreal real;
 #define B2_RC_DTLESSTHANMIN 4
 #define B2_RC_UNSTABLE 5
 #define B2_RC_DTNAN 6
+#define B2_RC_FAILURE 7
 
 struct B2Stats {
     int naccept, nreject, nf, nevents;

@@ -19,6 +19,9 @@
 #elif B2_ALG == 3 || B2_ALG == 4 || B2_ALG == 5 || B2_ALG == 8
 #include "b2_rosenbrock.cuh"
 #include "b2_ode_driver.cuh"
+#elif B2_ALG == 10
+#include "b2_bdf.cuh"
+#include "b2_ode_driver.cuh"
 #elif B2_ALG == 6 || B2_ALG == 7 || B2_ALG == 9
 #include "b2_sde.cuh"
 #ifdef B2_SDE_ADAPT
@@ -66,6 +69,13 @@ extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble
 }
 #endif
 
+#if B2_ALG == 10
+// FBDF: adaptive, caller-supplied dt, direct stores, saveat through the Hermite interpolant
+extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble_kernel_adaptive(const __grid_constant__ B2Args a) {
+    b2_ode_driver<B2Fbdf, 1, 0, 0, 0>(a);
+}
+#endif
+
 extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble_kernel(const __grid_constant__ B2Args a) {
 #if B2_ALG == 1 && B2_SPLIT
     b2_ode_driver_split<B2Tsit5>(a);
@@ -79,6 +89,8 @@ extern "C" __global__ void __launch_bounds__(B2_BLOCK, B2_MINBLOCKS) b2_ensemble
     b2_ode_driver<B2Ros23>(a);
 #elif B2_ALG == 4 || B2_ALG == 5 || B2_ALG == 8
     b2_ode_driver<B2Rodas>(a);
+#elif B2_ALG == 10
+    b2_ode_driver<B2Fbdf>(a);
 #elif defined(B2_SDE_ADAPT)
     b2_sde_adaptive_driver<B2_ALG>(a);
 #else

@@ -15,6 +15,17 @@
 #include "b2_common.cuh"
 #include "b2_control.cuh"
 
+// Steppers with their own step-size / order control (FBDF, b2_bdf.cuh) declare `static constexpr bool OWN_CONTROL = true`:
+// their step() reports a failed Newton iteration and the accept / reject decisions call back into the stepper.
+template <class A, class = void>
+struct b2_own_control {
+    static constexpr bool value = false;
+};
+template <class A>
+struct b2_own_control<A, decltype((void)A::OWN_CONTROL)> {
+    static constexpr bool value = A::OWN_CONTROL;
+};
+
 // ADAPT / TSTOPS: 0 or 1 = compile-time specialisation of the two solve options that sit in the per-iteration
 // control path, -1 = read them from the argument block.  AUTODT = 0 compiles the automatic-initial-step block out
 // (the specialised entry is only launched with a caller-supplied dt; keeps its register pressure down).
@@ -196,14 +207,16 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
         {
             {
                 if (do_step) {
-                    alg.step(u, p, t, dt, un, ut, adaptive, nf);
+                    bool nfail = false;   // OWN_CONTROL steppers: the corrector's Newton iteration did not converge
+                    if constexpr (b2_own_control<Alg>::value) nfail = alg.step(u, p, t, dt, un, ut, a, nf);
+                    else alg.step(u, p, t, dt, un, ut, adaptive, nf);
                     accepted = true;
                     dts = dt;
                     dtnew = dt;
-                    if (adaptive) {
-                        // error norm (A.4): scale in the working precision, ratio / square / sum in Float32 (EEst only
-                        // steers the step size; keeps Float64 kernels free of IEEE double divisions).  Accept iff
-                        // EEst^2 <= 1.  The division is the Newton reciprocal b2_rcp_nr (6.6e-6 accurate).
+                    // error norm (A.4): scale in the working precision, ratio / square / sum in Float32 (EEst only
+                    // steers the step size; keeps Float64 kernels free of IEEE double divisions).  Accept iff
+                    // EEst^2 <= 1.  The division is the Newton reciprocal b2_rcp_nr (6.6e-6 accurate).
+                    auto err_norm2 = [&]() -> float {
                         float acc = 0.0f;
 #pragma unroll
                         for (int i = 0; i < B2_N; i++) {
@@ -230,7 +243,45 @@ __device__ __forceinline__ void b2_ode_driver(const B2Args& a) {
                             }
                         }
 #endif
-                        const float EE2 = __fmul_rn(acc, inv_n);
+                        return __fmul_rn(acc, inv_n);
+                    };
+                    if (b2_own_control<Alg>::value) {
+                        if constexpr (b2_own_control<Alg>::value) {
+                            if (nfail) {
+                                // retry with dt/2 (a fixed-step run cannot: Failure)
+                                accepted = false;
+                                if (adaptive) {
+                                    nreject++;
+                                    alg.newton_fail();
+                                    dt = dt * (real)0.5;
+                                } else {
+                                    rc = B2_RC_FAILURE;
+                                }
+                            } else if (adaptive) {
+                                const float EE2 = err_norm2();
+                                if (EE2 != EE2) {
+                                    rc = B2_RC_DTNAN;
+                                    accepted = false;
+                                } else if (!(EE2 <= 1.0f)) {
+                                    accepted = false;
+                                    nreject++;
+                                    dt = dt * (real)alg.reject(EE2);
+                                } else {
+                                    dtnew = dt * (real)alg.accept(ctl.qmin, ctl.qmax);
+                                }
+                            } else {
+                                alg.fixed_accept();
+                                bool bad = false;
+#pragma unroll
+                                for (int i = 0; i < B2_N; i++) bad |= b2_isnan(un[i]);
+                                if (bad) {
+                                    rc = B2_RC_UNSTABLE;
+                                    accepted = false;
+                                }
+                            }
+                        }
+                    } else if (adaptive) {
+                        const float EE2 = err_norm2();
                         // PI controller (A.5), log domain, branch-free accept/reject (b2_control.cuh)
                         const B2Decision d = b2_pi_controller(EE2, lq, ctl);
                         const real dtq = dt * (real)d.qi;

@@ -56,7 +56,7 @@ mutable struct Timing
     Timing() = new()
 end
 
-const ALG_IDS = Dict(:Tsit5 => 1, :Vern7 => 2, :Rosenbrock23 => 3, :Rodas5 => 4, :Rodas5P => 5, :EM => 6, :SOSRA => 7, :Rodas4 => 8, :SRIW1 => 9)
+const ALG_IDS = Dict(:Tsit5 => 1, :Vern7 => 2, :Rosenbrock23 => 3, :Rodas5 => 4, :Rodas5P => 5, :EM => 6, :SOSRA => 7, :Rodas4 => 8, :SRIW1 => 9, :FBDF => 10)
 # b200ens_retcode 0..7 -> SciMLBase.ReturnCode, by NAME (the integer values of upstream's enum are not part of the ABI)
 const RETCODES = (ReturnCode.Default, ReturnCode.Success, ReturnCode.Terminated, ReturnCode.MaxIters,
                   ReturnCode.DtLessThanMin, ReturnCode.Unstable, ReturnCode.DtNaN, ReturnCode.Failure)
@@ -210,7 +210,7 @@ function model_sources(prob, alg)
         rhs = "#undef B2_HAS_MASS\n#define B2_HAS_MASS 1\nstatic constexpr double B2_MASS_[$(n * n)] = {" *
               join(string.(Float64.(vec(permutedims(Matrix(M))))), ", ") * "};\n" * rhs
     end
-    stiff = nameof(typeof(alg)) in (:Rosenbrock23, :Rodas4, :Rodas5, :Rodas5P)
+    stiff = nameof(typeof(alg)) in (:Rosenbrock23, :Rodas4, :Rodas5, :Rodas5P, :FBDF)   # analytic Jacobian for W
     jac = stiff ? vector_fn("b2_jac", "J", vec(permutedims(Symbolics.jacobian(du, us)))) : nothing   # row-major
     tgrad = stiff ? vector_fn("b2_tgrad", "dT", Symbolics.derivative.(du, t)) : nothing
     noise = prob isa SciMLBase.SDEProblem ?

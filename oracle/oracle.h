@@ -25,7 +25,7 @@ extern "C" {
 #define ORC_PMAX 64
 
 enum { ORC_TSIT5 = 1, ORC_VERN7 = 2, ORC_ROSENBROCK23 = 3, ORC_RODAS5 = 4, ORC_RODAS5P = 5,
-       ORC_EM = 6, ORC_SOSRA = 7, ORC_RODAS4 = 8, ORC_SRIW1 = 9 };
+       ORC_EM = 6, ORC_SOSRA = 7, ORC_RODAS4 = 8, ORC_SRIW1 = 9, ORC_FBDF = 10 };
 enum { ORC_RC_DEFAULT = 0, ORC_RC_SUCCESS = 1, ORC_RC_TERMINATED = 2, ORC_RC_MAXITERS = 3,
        ORC_RC_DTLESSTHANMIN = 4, ORC_RC_UNSTABLE = 5, ORC_RC_DTNAN = 6, ORC_RC_FAILURE = 7 };
 

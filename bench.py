@@ -95,9 +95,11 @@ def oracle_throughput(dtype, sweep, n_target, seconds, seed=0):
 #   Vern7: 118 n + 10 F + 14                     16-species network n = 16, F = 190        -> 3802
 #   Rosenbrock23 (n = 3, Robertson F = 13, J = 8):  W 9 + LU 18 + 3 solves x 18 + 3 F + ~60 of vector sums / norm -> 190
 #   Rodas5 / Rodas5P (s = 8):  J 8 + W 9 + LU 18 + 8 solves x 18 + 8 F + a-sums 96 + C-sums 147 + 42 + norm/controller 29 -> 600
+#   FBDF (n = 3, typical order k = 4, 2 Newton iterations): J 8 + W 9 + LU 18 + 2 x (F 13 + residual 9 + solve 18 + norm 12)
+#       + Lagrange weights and re-sampling ~220 + divided differences and their norms ~160 + f(u_new) 13 + control ~20 -> 550 (rough)
 #   EM: 2n + 2n + F + G + n (dW = sqrt(dt) z)     GBM n = 1: 7;  stochastic Lorenz n = 3, F = 8, G = 0: 23
 #   SOSRA (3 drift stages, additive noise):  3 F + stage sums 2 x (4n + 2n) + update 12 n + chi2 3n + 6n (dW, dZ) -> 111 (n = 3)
-CFG_FLOPS = {"Tsit5": 266.0, "Vern7_net16": 3802.0, "Rosenbrock23": 190.0, "Rodas5": 600.0, "Rodas5P": 600.0,
+CFG_FLOPS = {"Tsit5": 266.0, "Vern7_net16": 3802.0, "Rosenbrock23": 190.0, "Rodas5": 600.0, "Rodas5P": 600.0, "FBDF": 550.0,
              "EM_gbm": 7.0, "EM_lorenz": 23.0, "SOSRA_lorenz": 111.0}
 
 
@@ -185,7 +187,7 @@ def run_configs(dev, stream, peaks_tf, hbm_peak, cpu_seconds, cores):
     run("cfg2_lorenz_tsit5_f64_1M", W.lorenz_problem(np.float64, TSPAN), B.Tsit5(), u0, p, SAVE11, DT0, CFG_FLOPS["Tsit5"], "lorenz", cpu_n=1000000)
     # config 3: Robertson, Rosenbrock23 / Rodas5 / Rodas5P with the analytic Jacobian, 1M trajectories
     u0, p = W.robertson_params(1_000_000)
-    for alg in (B.Rosenbrock23(), B.Rodas5(), B.Rodas5P()):
+    for alg in (B.Rosenbrock23(), B.Rodas5(), B.Rodas5P(), B.FBDF()):
         run(f"cfg3_robertson_{alg.name}_f64_1M", W.robertson_problem(), alg, u0, p, W.ROBERTSON_SAVEAT, 1e-6, CFG_FLOPS[alg.name], "robertson",
             abstol=1e-8, reltol=1e-6, cpu_n=200000)
     # config 4: GBM (EM) and stochastic Lorenz (EM, SOSRA), 10M paths, Philox on the device

@@ -5,11 +5,11 @@
 // interpolation, constant-step BDF-k coefficients, divided-difference error and order estimates]; the written contract
 // is oracle/oracle_impl.inc (fbdf_step / fbdf_accept / fbdf_reject / fbdf_push), mirrored here operation for operation.
 //
-//   history   (x_j, h_j), j = 0..k, x_0 = t, newest first                       -- per-thread local arrays (k is run-time)
-//   predictor Lagrange interpolant of the history at t + dt                     (first step: u0 = uprev)
-//   corrector z + tmp = beta_k dt f(z, t + dt), tmp = sum_j cw_j h_j; simplified Newton, W = I - beta dt J(uprev, t)
+//   history   times x_j (x_0 = t, newest first) and the Newton divided differences dd[l] = [x_0..x_l]u -- in registers
+//   predictor the interpolation polynomial of (x_0..x_k) at t + dt, Horner on the Newton form (first step: u0 = uprev)
+//   corrector z + tmp = beta_k dt f(z, t + dt), tmp = a_1 uprev + sum_s a_{s+1} P(t - s dt); simplified Newton, W = I - beta dt J(uprev, t)
 //             factored once per step, convergence-rate test (kappa = 1/100, <= 10 iterations)
-//   estimates terk_m = m! dt^m [t+dt, x_0..x_{m-1}]u, lte = -(1/(k+1) + sum_j (a_j/beta) r_j) terk_{k+1}
+//   estimates terk_m = m! dt^m [t+dt, x_0..x_{m-1}]u (one new diagonal of the Newton table per step: k+1 divisions), lte = -(1/(k+1) + sum_j (a_j/beta) r_j) terk_{k+1}
 //   control   the driver's OWN_CONTROL path (b2_ode_driver.cuh): accept iff ||lte|| <= 1, order +-1 from the scaled
 //             norms T_m, dt_new = dt / q with q = (2 T_k/(k+1))^(1/(k+1)) and a steady band, Newton failure: dt/2
 // Saveat uses the cubic Hermite interpolant on (uprev, f(uprev)), (u, f(u)) -- upstream's default for multistep methods.
@@ -17,18 +17,30 @@
 #include "b2_common.cuh"
 #include "b2_rosenbrock.cuh"   // B2LU
 
-// [k][0] = beta_k, [k][j] = a_j: u_{n+1} + sum_j a_j u_{n+1-j} = beta dt f(u_{n+1})
-__constant__ double B2_BDFC[6][6] = {
+// [k][0] = beta_k, [k][j] = a_j: u_{n+1} + sum_j a_j u_{n+1-j} = beta dt f(u_{n+1}).  Read with a per-lane order k:
+// plain global constants (a __constant__ bank would serialise the lanes of a warp that sit at different orders).
+static __device__ const double B2_BDFC[6][6] = {
     {0, 0, 0, 0, 0, 0},
     {1.0, -1.0, 0, 0, 0, 0},
     {2.0 / 3.0, -4.0 / 3.0, 1.0 / 3.0, 0, 0, 0},
     {6.0 / 11.0, -18.0 / 11.0, 9.0 / 11.0, -2.0 / 11.0, 0, 0},
     {12.0 / 25.0, -48.0 / 25.0, 36.0 / 25.0, -16.0 / 25.0, 3.0 / 25.0, 0},
     {60.0 / 137.0, -300.0 / 137.0, 300.0 / 137.0, -200.0 / 137.0, 75.0 / 137.0, -12.0 / 137.0}};
+// a_j / beta (the oracle divides the table entries at run time: the same IEEE quotient, folded here at compile time)
+static __device__ const double B2_BDFR[6][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {0, (-1.0) / (1.0), 0, 0, 0, 0},
+    {0, (-4.0 / 3.0) / (2.0 / 3.0), (1.0 / 3.0) / (2.0 / 3.0), 0, 0, 0},
+    {0, (-18.0 / 11.0) / (6.0 / 11.0), (9.0 / 11.0) / (6.0 / 11.0), (-2.0 / 11.0) / (6.0 / 11.0), 0, 0},
+    {0, (-48.0 / 25.0) / (12.0 / 25.0), (36.0 / 25.0) / (12.0 / 25.0), (-16.0 / 25.0) / (12.0 / 25.0), (3.0 / 25.0) / (12.0 / 25.0), 0},
+    {0, (-300.0 / 137.0) / (60.0 / 137.0), (300.0 / 137.0) / (60.0 / 137.0), (-200.0 / 137.0) / (60.0 / 137.0), (75.0 / 137.0) / (60.0 / 137.0),
+     (-12.0 / 137.0) / (60.0 / 137.0)}};
 // 1/(m+1) and log2(m+1) as Float32 constants, m = 0..6
-__constant__ float B2_INVP1[7] = {1.0f, 0.5f, 0.333333343f, 0.25f, 0.2f, 0.166666672f, 0.142857149f};
-__constant__ float B2_LG2P1[7] = {0.0f, 1.0f, 1.5849625f, 2.0f, 2.32192802f, 2.5849625f, 2.80735493f};
+static __device__ const float B2_INVP1[7] = {1.0f, 0.5f, 0.333333343f, 0.25f, 0.2f, 0.166666672f, 0.142857149f};
+static __device__ const float B2_LG2P1[7] = {0.0f, 1.0f, 1.5849625f, 2.0f, 2.32192802f, 2.5849625f, 2.80735493f};
 
+// The order k is a run-time value per lane, but every array below is indexed with compile-time constants only (loops
+// over the maximal range with the inactive levels masked), so the divided-difference table stays in registers.
 struct B2Fbdf {
     static constexpr int ORDER = 1;          // initial-dt exponent and controller defaults (the order itself is run-time)
     static constexpr int DEG = 0;
@@ -37,30 +49,46 @@ struct B2Fbdf {
     __device__ __forceinline__ void poly_coeffs(int, real (&)[1]) const {}
 
     real f0[B2_N], fnew[B2_N];
-    int k, ncons, consfail, iters, nlfails;
+    int k, ncons, consfail, iters, nlfails, Lv;
     float eta_old;
-    real ts[7];
-    real hist[7][B2_N];
-    float T2[8];
+    real x[7];            // times of the history, newest first (x[0] = t)
+    real dd[7][B2_N];     // Newton divided differences of the history: dd[l] = [x_0 .. x_l]u
+    real inv[7];          // 1 / (t + dt - x_{l-1}) of the last step attempt: accepted() re-forms the new diagonal from them
+    float T2[8];          // squared scaled norms of terk_m
 
     __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {
         b2_rhs(f0, u, p, t);
         k = 1;
-        ncons = consfail = iters = nlfails = 0;
+        ncons = consfail = iters = nlfails = Lv = 0;
         eta_old = 1.0f;
+#pragma unroll
+        for (int l = 0; l < 7; l++) {
+            x[l] = 0;
+            inv[l] = 0;
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) dd[l][i] = 0;
+        }
     }
     __device__ __forceinline__ real fsal0(int i) const { return f0[i]; }
+    __device__ __forceinline__ float Tat(int m) const {   // T2[m] for a run-time m without indexing memory
+        float v = T2[0];
+#pragma unroll
+        for (int j = 1; j < 8; j++) v = (m == j) ? T2[j] : v;
+        return v;
+    }
 
-    // Lagrange basis values L_j(x) of the points ts[0..k]
-    __device__ __forceinline__ void lagrange_w(real x, real (&L)[7]) const {
-        for (int j = 0; j <= k; j++) {
-            real num = 1, den = 1;
-            for (int m = 0; m <= k; m++) {
-                if (m == j) continue;
-                num = num * (x - ts[m]);
-                den = den * (ts[j] - ts[m]);
-            }
-            L[j] = num / den;
+    // the interpolation polynomial of the history (x_0..x_k) at xe, Newton form / Horner: P = dd[k];
+    // P = fma(P, xe - x_l, dd[l]) for l = k-1..0.  Levels above k are masked to zero: fma(0, dx, 0) = 0 and
+    // fma(0, dx, dd[k]) = dd[k] exactly, so the fixed-length loop gives the variable-length loop's bits.
+    __device__ __forceinline__ void poly(real xe, real (&out)[B2_N]) const {
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) out[i] = 0;
+#pragma unroll
+        for (int l = 5; l >= 0; l--) {
+            const real dx = xe - x[l];
+            const bool on = l <= k;
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) out[i] = b2_fma(out[i], dx, on ? dd[l][i] : (real)0);
         }
     }
 
@@ -69,39 +97,34 @@ struct B2Fbdf {
                                          real (&ut)[B2_N], const B2Args& a, int& nf) {
         const real tdt = t + dt;
         const real beta = (real)B2_BDFC[k][0];
-        real L[7], cw[7], z[B2_N], tmp[B2_N];
+        real z[B2_N], tmp[B2_N];
         if (iters == 0) {
-            ts[0] = t;
+            x[0] = t;
 #pragma unroll
-            for (int i = 0; i < B2_N; i++) hist[0][i] = up[i];
+            for (int i = 0; i < B2_N; i++) dd[0][i] = up[i];
         }
         // predictor
         if (iters >= 1) {
-            lagrange_w(tdt, L);
-#pragma unroll
-            for (int i = 0; i < B2_N; i++) {
-                real s = L[0] * hist[0][i];
-                for (int j = 1; j <= k; j++) s = b2_fma(L[j], hist[j][i], s);
-                z[i] = s;
-            }
+            poly(tdt, z);
         } else {
 #pragma unroll
             for (int i = 0; i < B2_N; i++) z[i] = up[i];
         }
-        // tmp = sum_j cw_j h_j: the BDF-k combination of the history re-sampled at t - i dt
-        for (int j = 0; j <= k; j++) cw[j] = 0;
-        cw[0] = (real)B2_BDFC[k][1];
-        for (int i = 1; i <= k - 1; i++) {
-            lagrange_w(t - (real)i * dt, L);
-            const real ai = (real)B2_BDFC[k][i + 1];
-            for (int j = 0; j <= k; j++) cw[j] = b2_fma(ai, L[j], cw[j]);
-        }
-        const int kk = k > 1 ? k : 0;
+        // tmp = a_1 uprev + sum_s a_{s+1} P(t - s dt): the BDF-k combination of the history re-sampled on the grid of dt
+        {
+            const real a1 = (real)B2_BDFC[k][1];
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) {
-            real s = cw[0] * hist[0][i];
-            for (int j = 1; j <= kk; j++) s = b2_fma(cw[j], hist[j][i], s);
-            tmp[i] = s;
+            for (int i = 0; i < B2_N; i++) tmp[i] = a1 * dd[0][i];
+        }
+#pragma unroll
+        for (int s = 1; s <= 4; s++) {
+            if (s <= k - 1) {
+                real P[B2_N];
+                poly(t - (real)s * dt, P);
+                const real as = (real)B2_BDFC[k][s + 1];
+#pragma unroll
+                for (int i = 0; i < B2_N; i++) tmp[i] = b2_fma(as, P[i], tmp[i]);
+            }
         }
         // W = I - beta dt J(uprev, t)
         const real bdt = beta * dt;
@@ -169,52 +192,47 @@ struct B2Fbdf {
         eta_old = eta;
 #pragma unroll
         for (int i = 0; i < B2_N; i++) un[i] = z[i];
-        // divided differences through the new point: y_0 = t + dt, y_j = x_{j-1}
+        // divided differences through the new point, one new diagonal of the Newton table:
+        //   nd[0] = u, nd[l] = (nd[l-1] - dd[l-1]) / (t + dt - x_{l-1});  terk_l = l! dt^l nd[l]
+        // Only the running level is kept; accepted() re-forms the diagonal from the stored reciprocals (same operations).
         float rsk[B2_N];
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
             const real sk = b2_fma(b2_max(b2_abs(up[i]), b2_abs(un[i])), B2_RTOL(a, i), B2_ATOL(a, i));
             rsk[i] = b2_rcp_nr((float)sk);
         }
-        const int Lv = (k + 1 < iters + 1) ? k + 1 : iters + 1;   // levels the history supports (k+1 unless first step)
-        real y[8], d[8][B2_N], fac = 1;
-        y[0] = tdt;
+        Lv = (k + 1 < iters + 1) ? k + 1 : iters + 1;   // levels the history supports (k+1 unless first step)
+        real fac = 1, terkp1[B2_N], cur[B2_N];
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) d[0][i] = un[i];
-        for (int j = 1; j <= Lv; j++) {
-            y[j] = ts[j - 1];
-#pragma unroll
-            for (int i = 0; i < B2_N; i++) d[j][i] = hist[j - 1][i];
-        }
         for (int m = 0; m < 8; m++) T2[m] = 0.0f;
         {
             float acc = 0.0f;
 #pragma unroll
             for (int i = 0; i < B2_N; i++) {
-                const float r = __fmul_rn((float)d[0][i], rsk[i]);
+                cur[i] = un[i];
+                terkp1[i] = 0;
+                const float r = __fmul_rn((float)un[i], rsk[i]);
                 acc = __fmaf_rn(r, r, acc);
             }
             T2[0] = __fmul_rn(acc, inv_n);
         }
-        real terkp1[B2_N];
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) terkp1[i] = 0;
-        for (int l = 1; l <= Lv; l++) {
-            for (int j = 0; j + l <= Lv; j++) {
-                const real inv = (real)1 / (y[j] - y[j + l]);
+        for (int l = 1; l <= 6; l++) {
+            if (l <= Lv) {
+                const real iv = (real)1 / (tdt - x[l - 1]);
+                inv[l] = iv;
+                fac = fac * ((real)l * dt);
+                float acc = 0.0f;
 #pragma unroll
-                for (int i = 0; i < B2_N; i++) d[j][i] = (d[j][i] - d[j + 1][i]) * inv;
+                for (int i = 0; i < B2_N; i++) {
+                    cur[i] = (cur[i] - dd[l - 1][i]) * iv;
+                    const real v = fac * cur[i];
+                    if (l == k + 1) terkp1[i] = v;
+                    const float r = __fmul_rn((float)v, rsk[i]);
+                    acc = __fmaf_rn(r, r, acc);
+                }
+                T2[l] = __fmul_rn(acc, inv_n);
             }
-            fac = fac * ((real)l * dt);
-            float acc = 0.0f;
-#pragma unroll
-            for (int i = 0; i < B2_N; i++) {
-                const real v = fac * d[0][i];
-                if (l == k + 1) terkp1[i] = v;
-                const float r = __fmul_rn((float)v, rsk[i]);
-                acc = __fmaf_rn(r, r, acc);
-            }
-            T2[l] = __fmul_rn(acc, inv_n);
         }
         if (Lv < k + 1) {
             // first step (one history point): the error estimate is the change of the solution itself
@@ -222,31 +240,41 @@ struct B2Fbdf {
             for (int i = 0; i < B2_N; i++) ut[i] = un[i] - up[i];
         } else {
             real cl = (real)1 / (real)(k + 1);
-            for (int j = 2; j <= k; j++) {
-                const real xj = t - (real)(j - 1) * dt;
-                real num = 1;
-                for (int m = 0; m <= k; m++) num = num * (xj - ts[m]);
-                cl = b2_fma((real)(B2_BDFC[k][j] / B2_BDFC[k][0]), num / fac, cl);
+            const real inv_fac = (real)1 / fac;
+#pragma unroll
+            for (int j = 2; j <= 5; j++) {
+                if (j <= k) {
+                    const real xj = t - (real)(j - 1) * dt;
+                    real num = 1;
+#pragma unroll
+                    for (int m = 0; m <= 5; m++)
+                        if (m <= k) num = num * (xj - x[m]);
+                    cl = b2_fma((real)B2_BDFR[k][j], num * inv_fac, cl);
+                }
             }
 #pragma unroll
             for (int i = 0; i < B2_N; i++) ut[i] = cl * terkp1[i];
         }
-        if (!(ncons > k + 1 && k < 5)) T2[k + 1] = 0.0f;   // the order-(k+1) estimate is only trusted after k+2 steps at order k
+        {   // the order-(k+1) estimate is only trusted after k+2 steps at order k (value selects, not conditional stores:
+            // the compiler turns those into a run-time index and the whole table moves to local memory)
+            const bool drop = !(ncons > k + 1 && k < 5);
+#pragma unroll
+            for (int m = 2; m <= 6; m++) T2[m] = (drop && m == k + 1) ? 0.0f : T2[m];
+        }
         return false;
     }
 
     // accepted step: order selection and the next dt (as a multiplier of dt)
     __device__ __forceinline__ float accept(float qmin, float qmax) {
-        const float* T = T2;
         int kn = k;
         if (kn < 5 && ncons >= kn + 2 &&
-            ((kn == 1 && T[1] > T[2]) || (kn == 2 && T[1] > T[2] && T[2] > T[3]) ||
-             (kn > 2 && T[kn - 2] > T[kn - 1] && T[kn - 1] > T[kn] && T[kn] > T[kn + 1]))) {
+            ((kn == 1 && T2[1] > T2[2]) || (kn == 2 && T2[1] > T2[2] && T2[2] > T2[3]) ||
+             (kn > 2 && Tat(kn - 2) > Tat(kn - 1) && Tat(kn - 1) > Tat(kn) && Tat(kn) > Tat(kn + 1)))) {
             kn++;
         } else {
-            while (kn > 2 && !(T[kn - 2] > T[kn - 1] && T[kn - 1] > T[kn] && T[kn] > T[kn + 1])) kn--;
+            while (kn > 2 && !(Tat(kn - 2) > Tat(kn - 1) && Tat(kn - 1) > Tat(kn) && Tat(kn) > Tat(kn + 1))) kn--;
         }
-        const float terk2 = T[kn];
+        const float terk2 = Tat(kn);
         if (kn != k) ncons = 0;
         k = kn;
         float qi;
@@ -272,7 +300,8 @@ struct B2Fbdf {
         const float lz = 0.26303440f;   // log2(1.2)
         float l = -__fadd_rn(lz, __fmul_rn(__fmul_rn(0.5f, b2_fastlog2(EE2)), B2_INVP1[k0]));
         if (k0 > 1) {
-            const float lm = T2[k0 - 1] > 0.0f ? -__fadd_rn(lz, __fmul_rn(__fmul_rn(0.5f, b2_fastlog2(T2[k0 - 1])), B2_INVP1[k0 - 1])) : 0.0f;
+            const float Tm = Tat(k0 - 1);
+            const float lm = Tm > 0.0f ? -__fadd_rn(lz, __fmul_rn(__fmul_rn(0.5f, b2_fastlog2(Tm)), B2_INVP1[k0 - 1])) : 0.0f;
             if (lm > l) {
                 l = lm;
                 k = k0 - 1;
@@ -288,19 +317,32 @@ struct B2Fbdf {
     }
     __device__ __forceinline__ void fixed_accept() { iters++; }   // fixed step: the order stays 1 (backward Euler)
 
-    // f(u_new) (Hermite end slope) and the history push: the order is already the next step's
+    // f(u_new) (Hermite end slope) and the history push: the new diagonal of the divided-difference table, re-formed in
+    // place from the step's reciprocals, becomes the table
     __device__ __forceinline__ void accepted(const real (&u)[B2_N], const real (&p)[B2_NPA], real tnew, int& nf) {
         b2_rhs(fnew, u, p, tnew);
         nf += 1;
-        const int top = k + 1 < 6 ? k + 1 : 6;
-        for (int j = top; j >= 1; j--) {
-            ts[j] = ts[j - 1];
 #pragma unroll
-            for (int i = 0; i < B2_N; i++) hist[j][i] = hist[j - 1][i];
+        for (int j = 6; j >= 1; j--) x[j] = x[j - 1];
+        x[0] = tnew;
+        real prev[B2_N];
+#pragma unroll
+        for (int i = 0; i < B2_N; i++) prev[i] = u[i];
+#pragma unroll
+        for (int l = 1; l <= 6; l++) {
+            const bool on = l <= Lv;
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) {
+                const real c = (prev[i] - dd[l - 1][i]) * inv[l];
+                dd[l - 1][i] = on ? prev[i] : dd[l - 1][i];
+                prev[i] = on ? c : prev[i];
+            }
         }
-        ts[0] = tnew;
 #pragma unroll
-        for (int i = 0; i < B2_N; i++) hist[0][i] = u[i];
+        for (int l = 1; l <= 6; l++) {
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) dd[l][i] = (l == Lv) ? prev[i] : dd[l][i];
+        }
     }
     __device__ __forceinline__ void prepare_dense(const real (&)[B2_N], const real (&)[B2_NPA], real, real, int&) {}
     // cubic Hermite on (up, f0), (un, fnew): the default dense output of multistep methods

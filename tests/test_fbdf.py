@@ -122,8 +122,7 @@ def test_gpu_fbdf_robertson_bit_identical(B, gpu_lib, oracle, save_tstops):
     assert np.abs(sol.u_array.sum(axis=2) - 1.0).max() < 1e-7     # conserved up to the Newton tolerance (kappa x reltol)
     # and it is a stiff solver: the hand-written model agrees at the solver tolerance
     ref2, rc2, _ = oracle.solve("robertson", "Rodas5P", u0, p, (0.0, 1e5), W.ROBERTSON_SAVEAT, 1e-6, abstol=1e-10, reltol=1e-10)
-    big = np.abs(ref2) > 1e-6
-    assert np.max(np.abs(sol.u_array - ref2)[big] / np.abs(ref2)[big]) < (1e-4 if save_tstops else 2e-3)
+    assert np.max(np.abs(sol.u_array - ref2) / (1e-8 + 1e-6 * np.abs(ref2))) < 20.0     # measured on one set: 2.7-4.9 (CPU test)
 
 
 @pytest.mark.gpu

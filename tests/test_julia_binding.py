@@ -71,7 +71,7 @@ def test_ccalls_name_exported_symbols_with_the_right_arity():
 def test_enum_tables_match_the_header():
     hdr = open(HDR).read()
     jl = open(JL).read()
-    algs = dict(re.findall(r"B200ENS_(TSIT5|VERN7|ROSENBROCK23|RODAS5P|RODAS5|RODAS4|EM|SOSRA|SRIW1) = (\d+)", hdr))
+    algs = dict(re.findall(r"B200ENS_(TSIT5|VERN7|ROSENBROCK23|RODAS5P|RODAS5|RODAS4|EM|SOSRA|SRIW1|FBDF) = (\d+)", hdr))
     jl_algs = {k.upper(): v for k, v in re.findall(r":(\w+) => (\d+)", re.search(r"const ALG_IDS = Dict\((.*?)\)", jl).group(1))}
     assert jl_algs == algs
     rcs = [n for n, _ in sorted(re.findall(r"B200ENS_RC_(\w+) = (\d+)", hdr), key=lambda x: int(x[1]))]

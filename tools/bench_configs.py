@@ -47,7 +47,7 @@ scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 if which in ("all", "3"):
     N = int(1_000_000 * scale)
     u0, p = W.robertson_params(N)
-    for alg in (B.Rosenbrock23(), B.Rodas5(), B.Rodas5P()):
+    for alg in (B.Rosenbrock23(), B.Rodas5(), B.Rodas5P(), B.FBDF()):
         run(f"cfg3 robertson {alg.name}", W.robertson_problem(), alg, u0, p, W.ROBERTSON_SAVEAT, 1e-6, abstol=1e-8, reltol=1e-6)
 if which in ("all", "4"):
     N = int(10_000_000 * scale)

@@ -78,23 +78,34 @@ struct B2Fbdf {
     }
 
     // the interpolation polynomial of the history (x_0..x_k) at xe, Newton form / Horner: P = dd[k];
-    // P = fma(P, xe - x_l, dd[l]) for l = k-1..0.  Levels above k are masked to zero: fma(0, dx, 0) = 0 and
-    // fma(0, dx, dd[k]) = dd[k] exactly, so the fixed-length loop gives the variable-length loop's bits.
+    // P = fma(P, xe - x_l, dd[l]) for l = k-1..0.  INVARIANT: dd[l] = 0 for l > k (kept by accepted() / drop_levels(); the
+    // levels above the order are never read by the algorithm), so the fixed-length loop needs no masks:
+    // fma(0, dx, 0) = 0 and fma(0, dx, dd[k]) = dd[k] exactly -- the variable-length loop's bits.
     __device__ __forceinline__ void poly(real xe, real (&out)[B2_N]) const {
 #pragma unroll
         for (int i = 0; i < B2_N; i++) out[i] = 0;
 #pragma unroll
         for (int l = 5; l >= 0; l--) {
             const real dx = xe - x[l];
-            const bool on = l <= k;
 #pragma unroll
-            for (int i = 0; i < B2_N; i++) out[i] = b2_fma(out[i], dx, on ? dd[l][i] : (real)0);
+            for (int i = 0; i < B2_N; i++) out[i] = b2_fma(out[i], dx, dd[l][i]);
+        }
+    }
+    __device__ __forceinline__ void drop_levels() {   // after the order went down
+#pragma unroll
+        for (int l = 1; l <= 6; l++) {
+#pragma unroll
+            for (int i = 0; i < B2_N; i++) dd[l][i] = (l > k) ? (real)0 : dd[l][i];
         }
     }
 
     // one step attempt; returns true when the Newton iteration failed (un / ut are then meaningless)
     __device__ __forceinline__ bool step(const real (&up)[B2_N], const real (&p)[B2_NPA], real t, real dt, real (&un)[B2_N],
                                          real (&ut)[B2_N], const B2Args& a, int& nf) {
+        // the lanes that step enter together (the driver's __syncwarp() + `if (do_step)`); they leave the Newton loop after
+        // different iteration counts and are brought back together behind it (ncu: without this the ~1500 instructions
+        // behind the loop ran 1.7x per warp-iteration at 16/32 lanes)
+        const unsigned am = __activemask();
         const real tdt = t + dt;
         const real beta = (real)B2_BDFC[k][0];
         real z[B2_N], tmp[B2_N];
@@ -184,6 +195,7 @@ struct B2Fbdf {
             }
             ndz_prev = ndz;
         }
+        __syncwarp(am);
         if (!conv) {
             nlfails++;
             return true;
@@ -266,13 +278,16 @@ struct B2Fbdf {
 
     // accepted step: order selection and the next dt (as a multiplier of dt)
     __device__ __forceinline__ float accept(float qmin, float qmax) {
+        // bit m of dec: T_{m-1} > T_m.  Order kn keeps / raises when T_{kn-2} > T_{kn-1} > T_kn > T_{kn+1}: bits kn-1, kn, kn+1
+        unsigned dec = 0;
+#pragma unroll
+        for (int m = 1; m <= 7; m++) dec |= (T2[m - 1] > T2[m]) ? (1u << m) : 0u;
         int kn = k;
         if (kn < 5 && ncons >= kn + 2 &&
-            ((kn == 1 && T2[1] > T2[2]) || (kn == 2 && T2[1] > T2[2] && T2[2] > T2[3]) ||
-             (kn > 2 && Tat(kn - 2) > Tat(kn - 1) && Tat(kn - 1) > Tat(kn) && Tat(kn) > Tat(kn + 1)))) {
+            ((kn == 1 && (dec & 4u)) || (kn == 2 && (dec & 12u) == 12u) || (kn > 2 && ((dec >> (kn - 1)) & 7u) == 7u))) {
             kn++;
         } else {
-            while (kn > 2 && !(Tat(kn - 2) > Tat(kn - 1) && Tat(kn - 1) > Tat(kn) && Tat(kn) > Tat(kn + 1))) kn--;
+            while (kn > 2 && ((dec >> (kn - 1)) & 7u) != 7u) kn--;
         }
         const float terk2 = Tat(kn);
         if (kn != k) ncons = 0;
@@ -305,13 +320,17 @@ struct B2Fbdf {
             if (lm > l) {
                 l = lm;
                 k = k0 - 1;
+                drop_levels();
             }
         }
         return __fmul_rn(half, b2_fastexp2(fminf(l, 0.0f)));
     }
     // Newton failure: the driver halves dt; one order down after three failures in a row
     __device__ __forceinline__ void newton_fail() {
-        if (k > 1 && nlfails >= 3) k--;
+        if (k > 1 && nlfails >= 3) {
+            k--;
+            drop_levels();
+        }
         consfail++;
         ncons = 0;
     }
@@ -339,9 +358,9 @@ struct B2Fbdf {
             }
         }
 #pragma unroll
-        for (int l = 1; l <= 6; l++) {
+        for (int l = 1; l <= 6; l++) {   // k is already the next step's order: levels above it are zero (poly's invariant)
 #pragma unroll
-            for (int i = 0; i < B2_N; i++) dd[l][i] = (l == Lv) ? prev[i] : dd[l][i];
+            for (int i = 0; i < B2_N; i++) dd[l][i] = (l > k) ? (real)0 : ((l == Lv) ? prev[i] : dd[l][i]);
         }
     }
     __device__ __forceinline__ void prepare_dense(const real (&)[B2_N], const real (&)[B2_NPA], real, real, int&) {}

@@ -517,8 +517,6 @@ def build_model(prob, alg, callback=None, fast_math=False, ksmem=False, split=No
             raise NotImplementedError("callbacks on mass-matrix problems (their interpolant needs u', which M u' = f does "
                                       "not give for algebraic components)")
         srcs["rhs_src"] = codegen.emit_mass(mm) + srcs["rhs_src"]
-    if alg.name == "FBDF" and callback is not None:
-        raise NotImplementedError("callbacks with FBDF (an event restarts the multistep history; use a Rosenbrock method)")
     if alg.name in ("Rosenbrock23", "Rodas4", "Rodas5", "Rodas5P", "FBDF"):
         if getattr(prob, "jac", None) is not None:
             codegen.check_user_jacobian(prob.jac, exprs, usyms, n, m)

@@ -1359,8 +1359,6 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     if (!d->rhs_src) return fail(B200ENS_E_INVALID, "rhs_src is required");
     if (needs_jac(d->alg) && !d->jac_src)
         return fail(B200ENS_E_UNSUPPORTED, "Rosenbrock methods and FBDF need the analytic Jacobian (jac_src); there is no AD/finite-difference fallback");
-    if (d->alg == B200ENS_FBDF && (d->condition_src || d->dcondition_src))
-        return fail(B200ENS_E_UNSUPPORTED, "callbacks with FBDF are not supported (an event restarts the multistep history; use a Rosenbrock method)");
     if (is_sde(d->alg) && !d->noise_src) return fail(B200ENS_E_INVALID, "SDE algorithms need noise_src");
     if ((d->flags & B200ENS_MODEL_SDE_ADAPTIVE) && d->alg != B200ENS_SOSRA && d->alg != B200ENS_SRIW1)
         return fail(B200ENS_E_UNSUPPORTED, "B200ENS_MODEL_SDE_ADAPTIVE needs a stepper with an embedded error estimate: SRIW1 or SOSRA");

@@ -56,6 +56,7 @@ struct B2Fbdf {
     real inv[7];          // 1 / (t + dt - x_{l-1}) of the last step attempt: accepted() re-forms the new diagonal from them
     float T2[8];          // squared scaled norms of terk_m
 
+    // first step, and after every callback that modified u (upstream: u_modified -> reinitFBDF!): order 1, empty history
     __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {
         b2_rhs(f0, u, p, t);
         k = 1;

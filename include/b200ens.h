@@ -37,7 +37,7 @@ enum b200ens_alg {
     B200ENS_RODAS5P = 5, B200ENS_EM = 6, B200ENS_SOSRA = 7, B200ENS_RODAS4 = 8,
     B200ENS_SRIW1 = 9,  /* Roessler SRI W1: strong order 1.5 for diagonal noise (fixed dt; dW and dZ per step) */
     B200ENS_FBDF = 10   /* FBDF (qa.jl:57): variable-order (1..5) fixed-leading-coefficient BDF, Newton corrector with the analytic
-                           Jacobian (jac_src required), Hermite dense output; no callbacks, no mass matrix */
+                           Jacobian (jac_src required), Hermite dense output; a callback that fires restarts the history at order 1; no mass matrix */
 };
 
 /* per-trajectory return codes <- SciMLBase.ReturnCode (qa.jl:213); the Julia glue maps by name */

@@ -91,15 +91,37 @@ def test_fbdf_linear_closed_form_and_fixed_step(oracle):
     assert abs(out[0, 0, 0] - g["u0"][0] / (1 - g["p"][0] * dt) ** 64) < 1e-13
 
 
-def test_fbdf_kernel_compiles_and_rejects_callbacks(B):
-    from b200ens import workloads as W
-
+def test_fbdf_kernel_compiles(B):
     for dtype in (np.float64, np.float32):
         prob = B.ODEProblem(vdp, np.array([2.0, 0.0], dtype=dtype), (0.0, 1.0), np.array([5.0], dtype=dtype))
         info = B.build_model(prob, B.FBDF()).info()
-        assert info["regs"] > 0 and info["cubin_bytes"] > 0
-    with pytest.raises(NotImplementedError):
-        B.build_model(W.robertson_problem(), B.FBDF(), B.ContinuousCallback(lambda u, t, i: u[0] - 0.5, lambda i: None))
+        assert info["regs"] > 0 and info["cubin_bytes"] > 0 and info["lmem"] == 0   # the divided-difference table stays in registers
+
+
+def _sawtooth_callback(B):
+    # u1 decays like exp(-p1 t); every time it falls through 0.5 it is kicked back up by 0.4
+    return B.ContinuousCallback(lambda u, t, integrator: u[1] - 0.5, None, lambda integrator: integrator.u.__setitem__(1, integrator.u[1] + 0.4))
+
+
+def test_fbdf_with_a_callback_restarts_its_history(oracle, B):
+    """A ContinuousCallback on FBDF: the event is located on the Hermite dense output, affect! modifies u and the multistep
+    history restarts at order 1 (upstream: u_modified -> reinitFBDF!).  Closed form of the sawtooth: u1 falls from 1 to 0.5
+    in ln(2)/p1, then from 0.9 to 0.5 in ln(1.8)/p1 per tooth."""
+    N, T = 16, 5.0
+    p = np.stack([np.full(N, 200.0), np.linspace(0.3, 2.0, N)], axis=1)
+    u0 = np.tile([0.0, 1.0], (N, 1))
+    cb = _sawtooth_callback(B)
+    prob = B.ODEProblem(decay, u0[0], (0.0, T), p[0])
+    model = B.build_model(prob, B.FBDF(), cb)
+    out, rc, st = oracle.solve(None, "FBDF", u0, p, (0.0, T), [T], 1e-3, abstol=1e-9, reltol=1e-9, event=True, event_dir=-1,
+                               save_tstops=False, fns=oracle_fns(oracle, B, model))
+    assert np.all(rc == 1)
+    t_first = np.log(2.0) / p[:, 1]
+    teeth = np.where(T > t_first, 1 + np.floor((T - t_first) / (np.log(1.8) / p[:, 1])), 0).astype(int)
+    assert np.array_equal(st[:, 3], teeth)
+    t_last = t_first + (teeth - 1) * np.log(1.8) / p[:, 1]
+    exact = np.where(teeth > 0, 0.9 * np.exp(-p[:, 1] * (T - t_last)), np.exp(-p[:, 1] * T))
+    assert np.max(np.abs(out[:, 0, 1] - exact)) < 2e-6
 
 
 # ---------------------------------------------------------------- GPU: kernel against the oracle
@@ -162,3 +184,32 @@ def test_gpu_fbdf_fixed_step_is_backward_euler(B, gpu_lib, oracle):
     assert np.array_equal(sol.retcodes, rc) and np.all(rc == 1) and np.all(st[:, 0] == 128)
     assert np.array_equal(sol.stats, st) and np.array_equal(sol.u_array, ref)
     assert np.max(np.abs(sol.u_array[:, 1, 1] - (1 + p[:, 1] / 128) ** -128.0)) < 1e-12
+
+
+@pytest.mark.gpu
+def test_gpu_fbdf_with_callbacks_matches_oracle(B, gpu_lib, oracle):
+    """ContinuousCallback (downcrossings only) and a DiscreteCallback on FBDF: events on the Hermite dense output, history
+    restart after every affect! -- bit for bit against the oracle."""
+    N, T = 1024, 5.0
+    rng = np.random.default_rng(12)
+    p = np.stack([10.0 ** rng.uniform(1, 3, N), rng.uniform(0.3, 2.0, N)], axis=1)
+    u0 = np.tile([0.0, 1.0], (N, 1))
+    saveat = np.linspace(0.0, T, 11)
+    prob = B.ODEProblem(decay, u0[0], (0.0, T), p[0])
+    cb = _sawtooth_callback(B)
+    sol = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), B.FBDF(), B.EnsembleB200(), trajectories=N, saveat=saveat, dt=1e-3,
+                  abstol=1e-8, reltol=1e-8, callback=cb)
+    model = B.build_model(prob, B.FBDF(), cb)
+    ref, rc, st = oracle.solve(None, "FBDF", u0, p, (0.0, T), saveat, 1e-3, abstol=1e-8, reltol=1e-8, event=True, event_dir=-1,
+                               save_tstops=False, fns=oracle_fns(oracle, B, model))
+    assert np.array_equal(sol.retcodes, rc) and np.all(rc == 1)
+    assert np.array_equal(sol.stats, st) and np.array_equal(sol.u_array, ref)
+    assert st[:, 3].min() >= 1
+    dcb = B.DiscreteCallback(lambda u, t, integrator: u[1] < 0.3, lambda integrator: integrator.u.__setitem__(1, integrator.u[1] + 0.5))
+    sol = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), B.FBDF(), B.EnsembleB200(), trajectories=N, saveat=saveat, dt=1e-3,
+                  abstol=1e-8, reltol=1e-8, callback=dcb)
+    model = B.build_model(prob, B.FBDF(), dcb)
+    ref, rc, st = oracle.solve(None, "FBDF", u0, p, (0.0, T), saveat, 1e-3, abstol=1e-8, reltol=1e-8, devent=True,
+                               save_tstops=False, fns=oracle_fns(oracle, B, model))
+    assert np.array_equal(sol.retcodes, rc) and np.array_equal(sol.stats, st) and np.array_equal(sol.u_array, ref)
+    assert st[:, 3].max() >= 1

@@ -70,3 +70,25 @@ for alg in (B.EM(), B.SOSRA()):
 pr1 = B.SDEProblem(W.lorenz_add_f, W.lorenz_add_g, np.array([1.0, 0.0, 0.0]), (0.0, 1.0), np.array([10.0, 28.0, 8.0 / 3.0, 3.0]))
 s = B.solve(B.EnsembleProblem(pr1, u0s=u0a, ps=pa), B.SOSRA(), B.EnsembleB200(), trajectories=1500, saveat=[1.0], dt=0.01, adaptive=True, seed=3)
 print("sde adaptive", (s.retcodes == 1).all())
+# session-3 additions: FBDF (plain, with a downcrossing-only ContinuousCallback, fixed step), affect_neg! in the one-thread
+# and the split kernel
+u0r, pr = W.robertson_params(600)
+s = B.solve(B.EnsembleProblem(W.robertson_problem(), u0s=u0r, ps=pr), B.FBDF(), B.EnsembleB200(), trajectories=600, saveat=W.ROBERTSON_SAVEAT,
+            dt=1e-6, abstol=1e-8, reltol=1e-6)
+print("fbdf robertson", (s.retcodes == 1).all(), s.stats[:, 0].mean())
+def _decay(du, u, p, t):
+    du[0] = -p[0] * (u[0] - u[1]); du[1] = -p[1] * u[1]
+pd = np.stack([np.full(400, 200.0), np.linspace(0.3, 2.0, 400)], axis=1)
+cbn = B.ContinuousCallback(lambda u, t, integ: u[1] - 0.5, None, lambda integ: integ.u.__setitem__(1, integ.u[1] + 0.4))
+s = B.solve(B.EnsembleProblem(B.ODEProblem(_decay, np.array([0.0, 1.0]), (0.0, 5.0), pd[0]), u0s=np.tile([0.0, 1.0], (400, 1)), ps=pd), B.FBDF(),
+            B.EnsembleB200(), trajectories=400, saveat=1.0, dt=1e-3, abstol=1e-8, reltol=1e-8, callback=cbn)
+print("fbdf downcrossing callback", (s.retcodes == 1).all(), s.stats[:, 3].mean())
+s = B.solve(B.EnsembleProblem(B.ODEProblem(_decay, np.array([0.0, 1.0]), (0.0, 1.0), pd[0]), u0s=np.tile([0.0, 1.0], (400, 1)), ps=pd), B.FBDF(),
+            B.EnsembleB200(), trajectories=400, saveat=[1.0], dt=1 / 64, adaptive=False)
+print("fbdf fixed step", (s.retcodes == 1).all())
+cb2 = B.ContinuousCallback(lambda u, t, integ: u[1] - 0.12, lambda integ: integ.u.__setitem__(0, integ.u[0] + 0.2),
+                           lambda integ: integ.u.__setitem__(2, integ.u[2] + 0.05))
+for split in (True, False):
+    s = B.solve(B.EnsembleProblem(W.net16_problem(), u0s=u0n, ps=pn), B.Vern7(), B.EnsembleB200(split=split), trajectories=200,
+                saveat=np.linspace(0, 10, 11), dt=0.01, abstol=1e-6, reltol=1e-6, callback=cb2)
+    print("affect_neg split" if split else "affect_neg one-thread", (s.retcodes == 1).all(), s.stats[:, 3].mean())

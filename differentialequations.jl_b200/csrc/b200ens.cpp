@@ -660,6 +660,11 @@ int plan_launch(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, long long
     if (o->stage_outputs > 0 && !staged && !m->split)
         return fail(B200ENS_E_UNSUPPORTED, "stage_outputs=1 but %zu bytes of shared memory per block do not fit", smem);
     int nb = staged ? nb_staged : nb_direct;
+    // stiff steppers beyond 8 states run their LU with rolled loops on a local-memory matrix (b2_rosenbrock.cuh,
+    // B2_LU_ROLLED): ~3.5 KB of local memory per thread.  Two resident CTAs per SM are 129 MB of it on 148 SMs -- more than
+    // the L2 holds; one CTA per SM is as fast (Rodas5P, n = 16: 305 vs 325 ms per 100k trajectories) or faster (FBDF: 299 vs
+    // 388 ms) (profiles/README.md)
+    if (needs_jac(m->alg) && m->n_state > 8 && m->lmem >= 2048) nb = std::min(nb, 1);
     if (const char* e = getenv("B200ENS_BLOCKS_PER_SM")) nb = std::max(1, std::min(nb, atoi(e)));  // experiments
     if (nb < 1) return fail(B200ENS_E_CUDA, "kernel cannot be resident (occupancy 0)");
     lp->block = block;

@@ -7,18 +7,32 @@
 #include "b2_common.cuh"
 #include "tableaus_gen.cuh"
 
+// Small systems (n <= 8): fully unrolled, A / dinv / piv are registers.  Larger systems: the O(n^3) unrolled code is megabytes of
+// SASS (n = 16: a 4 MB cubin, minutes of JIT, instruction-cache bound) -- the loops stay rolled, the matrix lives in the
+// thread's local memory (L1 / L2 resident) and factor / solve are out-of-line functions.  Same operations in the same order:
+// bit-identical either way (B2_LU_ROLLED can be forced with B200ENS_DEFINES for the A/B test).
+#ifndef B2_LU_ROLLED
+#define B2_LU_ROLLED (B2_N > 8)
+#endif
+#if B2_LU_ROLLED
+#define B2_LU_UNROLL _Pragma("unroll 1")
+#define B2_LU_INLINE __noinline__
+#else
+#define B2_LU_UNROLL _Pragma("unroll")
+#define B2_LU_INLINE __forceinline__
+#endif
 // W (n x n) factored once per step and reused for every stage right-hand side.
 struct B2LU {
     real A[B2_N][B2_N];
     real dinv[B2_N];
     int piv[B2_N];
 
-    __device__ __forceinline__ void factor() {
-#pragma unroll
+    __device__ B2_LU_INLINE void factor() {
+B2_LU_UNROLL
         for (int k = 0; k < B2_N; k++) {
             int pr = k;
             real best = b2_abs(A[k][k]);
-#pragma unroll
+B2_LU_UNROLL
             for (int i = k + 1; i < B2_N; i++) {
                 const real v = b2_abs(A[i][k]);
                 if (v > best) {
@@ -27,10 +41,10 @@ struct B2LU {
                 }
             }
             piv[k] = pr;
-#pragma unroll
+B2_LU_UNROLL
             for (int i = k + 1; i < B2_N; i++) {
                 const bool sw = pr == i;
-#pragma unroll
+B2_LU_UNROLL
                 for (int j = 0; j < B2_N; j++) {
                     const real x = A[k][j], y = A[i][j];
                     A[k][j] = sw ? y : x;
@@ -38,19 +52,19 @@ struct B2LU {
                 }
             }
             dinv[k] = (real)1 / A[k][k];
-#pragma unroll
+B2_LU_UNROLL
             for (int i = k + 1; i < B2_N; i++) {
                 const real l = A[i][k] * dinv[k];
                 A[i][k] = l;
-#pragma unroll
+B2_LU_UNROLL
                 for (int j = k + 1; j < B2_N; j++) A[i][j] = b2_fma(-l, A[k][j], A[i][j]);
             }
         }
     }
-    __device__ __forceinline__ void solve(real (&b)[B2_N]) const {
-#pragma unroll
+    __device__ B2_LU_INLINE void solve(real (&b)[B2_N]) const {
+B2_LU_UNROLL
         for (int k = 0; k < B2_N; k++) {
-#pragma unroll
+B2_LU_UNROLL
             for (int i = k + 1; i < B2_N; i++) {
                 const bool sw = piv[k] == i;
                 const real x = b[k], y = b[i];
@@ -58,17 +72,17 @@ struct B2LU {
                 b[i] = sw ? x : y;
             }
         }
-#pragma unroll
+B2_LU_UNROLL
         for (int i = 1; i < B2_N; i++) {
             real s = b[i];
-#pragma unroll
+B2_LU_UNROLL
             for (int j = 0; j < i; j++) s = b2_fma(-A[i][j], b[j], s);
             b[i] = s;
         }
-#pragma unroll
+B2_LU_UNROLL
         for (int i = B2_N - 1; i >= 0; i--) {
             real s = b[i];
-#pragma unroll
+B2_LU_UNROLL
             for (int j = i + 1; j < B2_N; j++) s = b2_fma(-A[i][j], b[j], s);
             b[i] = s * dinv[i];
         }

@@ -213,3 +213,29 @@ def test_gpu_fbdf_with_callbacks_matches_oracle(B, gpu_lib, oracle):
                                save_tstops=False, fns=oracle_fns(oracle, B, model))
     assert np.array_equal(sol.retcodes, rc) and np.array_equal(sol.stats, st) and np.array_equal(sol.u_array, ref)
     assert st[:, 3].max() >= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg", ["Rodas5P", "FBDF"])
+def test_gpu_stiff_steppers_on_the_16_species_network(B, gpu_lib, oracle, alg):
+    """n = 16: beyond 8 states the LU of the stiff steppers runs with rolled loops on a local-memory matrix (b2_rosenbrock.cuh,
+    B2_LU_ROLLED) instead of fully unrolled register code -- the same operations in the same order, so still bit-identical
+    to the oracle."""
+    from b200ens import workloads as W
+
+    N = 256
+    u0, p = W.net16_params(N)
+    prob = W.net16_problem()
+    saveat = np.linspace(0.0, 10.0, 11)
+    A = getattr(B, alg)()
+    sol = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), A, B.EnsembleB200(), trajectories=N, saveat=saveat, dt=0.01, abstol=1e-8,
+                  reltol=1e-8)
+    model = B.build_model(prob, A)
+    assert model.info()["cubin_bytes"] < 2_500_000           # rolled LU: ~1 MB instead of 4 MB of unrolled SASS
+    ref, rc, st = oracle.solve(None, alg, u0, p, (0.0, 10.0), saveat, 0.01, abstol=1e-8, reltol=1e-8, fns=oracle_fns(oracle, B, model))
+    assert np.array_equal(sol.retcodes, rc) and np.all(rc == 1)
+    assert np.array_equal(sol.stats, st) and np.array_equal(sol.u_array, ref)
+    # against the explicit high-order solve of the same (non-stiff at these rates) network
+    v7 = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), B.Vern7(), B.EnsembleB200(), trajectories=N, saveat=saveat, dt=0.01, abstol=1e-11,
+                 reltol=1e-11)
+    assert np.max(np.abs(sol.u_array - v7.u_array)) < (2e-6 if alg == "FBDF" else 2e-7)

@@ -47,6 +47,16 @@ def test_stiff_ode_solve(B, gpu_lib):                     # core.jl:39-49 (the p
     assert abs(sol.u[-1][0] - 0.0178) < 5e-4              # y1(1e5) of the classic problem (1.786e-2)
 
 
+def test_stiff_ode_solve_fbdf(B, gpu_lib):               # qa.jl:57 exports FBDF next to Rodas5P; same problem, same call shape
+    from b200ens import workloads as W
+
+    prob = B.ODEProblem(W.robertson, [1.0, 0.0, 0.0], (0.0, 1.0e5), (0.04, 3.0e7, 1.0e4))
+    sol = B.solve(prob, B.FBDF())                        # default tolerances, automatic initial dt, every step saved
+    assert sol.retcode == B.ReturnCode.Success
+    assert abs(sum(sol.u[-1]) - 1.0) < 1e-6 and sol.t[-1] == 1.0e5
+    assert 0.015 < sol.u[-1][0] < 0.02                    # y1(1e5) = 0.017866 (scipy Radau, tests/golden/robertson.json)
+
+
 def test_solution_interpolation(B, gpu_lib):              # core.jl:51-58
     prob = B.ODEProblem(lambda u, p, t: [1.01 * u[0]], 0.5, (0.0, 1.0))
     sol = B.solve(prob, B.Tsit5(), dense=True)

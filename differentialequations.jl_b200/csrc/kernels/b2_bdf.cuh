@@ -348,18 +348,22 @@ struct B2Fbdf {
         real prev[B2_N];
 #pragma unroll
         for (int i = 0; i < B2_N; i++) prev[i] = u[i];
+        // (monotone conditions `l <= Lv` compile to predicated register moves; a chain of `l == Lv` stores would be merged
+        // into one run-time-indexed store and move the table to local memory)
 #pragma unroll
         for (int l = 1; l <= 6; l++) {
-            const bool on = l <= Lv;
+            if (l <= Lv) {
 #pragma unroll
-            for (int i = 0; i < B2_N; i++) {
-                const real c = (prev[i] - dd[l - 1][i]) * inv[l];
-                dd[l - 1][i] = on ? prev[i] : dd[l - 1][i];
-                prev[i] = on ? c : prev[i];
+                for (int i = 0; i < B2_N; i++) {
+                    const real c = (prev[i] - dd[l - 1][i]) * inv[l];
+                    dd[l - 1][i] = prev[i];
+                    prev[i] = c;
+                }
             }
         }
+        // level Lv receives the last value; k is already the next step's order: levels above it are zero (poly's invariant)
 #pragma unroll
-        for (int l = 1; l <= 6; l++) {   // k is already the next step's order: levels above it are zero (poly's invariant)
+        for (int l = 1; l <= 6; l++) {
 #pragma unroll
             for (int i = 0; i < B2_N; i++) dd[l][i] = (l > k) ? (real)0 : ((l == Lv) ? prev[i] : dd[l][i]);
         }

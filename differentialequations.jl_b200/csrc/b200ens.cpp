@@ -661,11 +661,11 @@ int plan_launch(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, long long
         return fail(B200ENS_E_UNSUPPORTED, "stage_outputs=1 but %zu bytes of shared memory per block do not fit", smem);
     int nb = staged ? nb_staged : nb_direct;
     // stiff steppers beyond 8 states run their LU with rolled loops on a local-memory matrix (b2_rosenbrock.cuh,
-    // B2_LU_ROLLED): ~3.5 KB of local memory per thread.  Two resident CTAs per SM are 129 MB of it on 148 SMs -- more than
-    // the L2 holds; one CTA per SM is as fast (Rodas5P, n = 16: 305 vs 325 ms per 100k trajectories) or faster (FBDF: 299 vs
-    // 388 ms) (profiles/README.md)
+    // B2_LU_ROLLED): ~3.5 KB of local memory per thread.  One CTA (of 64 threads, b200ens_compile) per SM keeps it inside the
+    // L1; more resident threads spill it to the L2 and are slower (profiles/README.md)
+    const int nb_occ = nb;
     if (needs_jac(m->alg) && m->n_state > 8 && m->lmem >= 2048) nb = std::min(nb, 1);
-    if (const char* e = getenv("B200ENS_BLOCKS_PER_SM")) nb = std::max(1, std::min(nb, atoi(e)));  // experiments
+    if (const char* e = getenv("B200ENS_BLOCKS_PER_SM")) nb = std::max(1, std::min(nb_occ, atoi(e)));  // experiments
     if (nb < 1) return fail(B200ENS_E_CUDA, "kernel cannot be resident (occupancy 0)");
     lp->block = block;
     lp->stride = staged ? stride : 0;
@@ -1433,9 +1433,16 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
         try_regs = false;   // settled
         rc = 0;
     }
+    // B200ENS_BLOCK: threads per CTA of the one-thread kernels (experiments; default 128)
+    int blk = kBlock;
+    // stiff steppers beyond 8 states keep W and the stage vectors in ~3.5 KB of local memory per thread: 64 threads per SM
+    // (one CTA of 64) keep that inside the L1 (Rodas5P, n = 16: 111 ms per 100k trajectories against 144 ms with 128 threads)
+    if (needs_jac(d->alg) && d->n_state > 8) blk = 64;
+    if (const char* e = getenv("B200ENS_BLOCK")) blk = std::max(32, std::min(256, atoi(e) / 32 * 32));
     if (try_regs) {
+        m->block = blk;
         for (;; mb--) {
-            m->source = build_source(d, mb, kBlock, 0);
+            m->source = build_source(d, mb, blk, 0);
             rc = nvrtc_compile(m.get());
             if (rc) break;
             parse_ptxas_log(m.get());

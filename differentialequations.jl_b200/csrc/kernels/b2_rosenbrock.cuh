@@ -27,6 +27,7 @@ struct B2LU {
     real dinv[B2_N];
     int piv[B2_N];
 
+#if !B2_LU_ROLLED
     __device__ B2_LU_INLINE void factor() {
 B2_LU_UNROLL
         for (int k = 0; k < B2_N; k++) {
@@ -87,6 +88,88 @@ B2_LU_UNROLL
             b[i] = s * dinv[i];
         }
     }
+#else
+    // Rolled variant: the matrix is local memory, every access is a load / store with L1 / L2 latency.  The same
+    // operations on the same values (bit-identical), organised for memory: rows are swapped only when the pivot moved
+    // (the select form above touches 2 n^2 entries per column), and the inner loops fetch four entries of both rows
+    // before the dependent multiply-adds so that the loads overlap.
+    __device__ B2_LU_INLINE void factor() {
+        for (int k = 0; k < B2_N; k++) {
+            int pr = k;
+            real best = b2_abs(A[k][k]);
+            for (int i = k + 1; i < B2_N; i++) {
+                const real v = b2_abs(A[i][k]);
+                if (v > best) {
+                    best = v;
+                    pr = i;
+                }
+            }
+            piv[k] = pr;
+            if (pr != k) {
+                for (int j = 0; j < B2_N; j++) {
+                    const real x = A[k][j], y = A[pr][j];
+                    A[k][j] = y;
+                    A[pr][j] = x;
+                }
+            }
+            const real di = (real)1 / A[k][k];
+            dinv[k] = di;
+            for (int i = k + 1; i < B2_N; i++) {
+                const real l = A[i][k] * di;
+                A[i][k] = l;
+                const real nl = -l;
+                int j = k + 1;
+                for (; j + 3 < B2_N; j += 4) {
+                    const real p0 = A[k][j], p1 = A[k][j + 1], p2 = A[k][j + 2], p3 = A[k][j + 3];
+                    const real a0 = A[i][j], a1 = A[i][j + 1], a2 = A[i][j + 2], a3 = A[i][j + 3];
+                    A[i][j] = b2_fma(nl, p0, a0);
+                    A[i][j + 1] = b2_fma(nl, p1, a1);
+                    A[i][j + 2] = b2_fma(nl, p2, a2);
+                    A[i][j + 3] = b2_fma(nl, p3, a3);
+                }
+                for (; j < B2_N; j++) A[i][j] = b2_fma(nl, A[k][j], A[i][j]);
+            }
+        }
+    }
+    __device__ B2_LU_INLINE void solve(real (&b)[B2_N]) const {
+        for (int k = 0; k < B2_N; k++) {
+            const int pr = piv[k];
+            if (pr != k) {
+                const real x = b[k];
+                b[k] = b[pr];
+                b[pr] = x;
+            }
+        }
+        for (int i = 1; i < B2_N; i++) {
+            real s = b[i];
+            int j = 0;
+            for (; j + 3 < i; j += 4) {
+                const real a0 = A[i][j], a1 = A[i][j + 1], a2 = A[i][j + 2], a3 = A[i][j + 3];
+                const real y0 = b[j], y1 = b[j + 1], y2 = b[j + 2], y3 = b[j + 3];
+                s = b2_fma(-a0, y0, s);
+                s = b2_fma(-a1, y1, s);
+                s = b2_fma(-a2, y2, s);
+                s = b2_fma(-a3, y3, s);
+            }
+            for (; j < i; j++) s = b2_fma(-A[i][j], b[j], s);
+            b[i] = s;
+        }
+        for (int i = B2_N - 1; i >= 0; i--) {
+            real s = b[i];
+            int j = i + 1;
+            for (; j + 3 < B2_N; j += 4) {
+                const real a0 = A[i][j], a1 = A[i][j + 1], a2 = A[i][j + 2], a3 = A[i][j + 3];
+                const real y0 = b[j], y1 = b[j + 1], y2 = b[j + 2], y3 = b[j + 3];
+                s = b2_fma(-a0, y0, s);
+                s = b2_fma(-a1, y1, s);
+                s = b2_fma(-a2, y2, s);
+                s = b2_fma(-a3, y3, s);
+            }
+            for (; j < B2_N; j++) s = b2_fma(-A[i][j], b[j], s);
+            b[i] = s * dinv[i];
+        }
+    }
+#endif
 };
 
 #define B2_ROS23_D 0.29289321881345247560   /* 1/(2+sqrt 2) */

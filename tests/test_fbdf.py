@@ -239,3 +239,29 @@ def test_gpu_stiff_steppers_on_the_16_species_network(B, gpu_lib, oracle, alg):
     v7 = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), B.Vern7(), B.EnsembleB200(), trajectories=N, saveat=saveat, dt=0.01, abstol=1e-11,
                  reltol=1e-11)
     assert np.max(np.abs(sol.u_array - v7.u_array)) < (2e-6 if alg == "FBDF" else 2e-7)
+
+
+@pytest.mark.gpu
+def test_gpu_fbdf_with_solve_options(B, gpu_lib, oracle):
+    """FBDF through the generic kernel entry: user tstops (bit-identical to the oracle), save_idxs (the selected columns of
+    the full run) and the on-device ensemble summary (mean of the full output)."""
+    from b200ens import workloads as W
+
+    N = 1500
+    u0, p = W.robertson_params(N)
+    prob = W.robertson_problem((0.0, 1e3))
+    sv = np.array([1e-3, 1.0, 40.0, 1e3])
+    kw = dict(trajectories=N, saveat=sv, dt=1e-6, abstol=1e-8, reltol=1e-6)
+    eprob = B.EnsembleProblem(prob, u0s=u0, ps=p)
+    full = B.solve(eprob, B.FBDF(), B.EnsembleB200(), **kw)
+    ts = B.solve(eprob, B.FBDF(), B.EnsembleB200(), tstops=[0.5, 40.0, 333.0], **kw)
+    model = B.build_model(prob, B.FBDF())
+    ref, rc, st = oracle.solve(None, "FBDF", u0, p, (0.0, 1e3), sv, 1e-6, abstol=1e-8, reltol=1e-6, save_tstops=False,
+                               tstops=[0.5, 40.0, 333.0], fns=oracle_fns(oracle, B, model))
+    assert np.array_equal(ts.retcodes, rc) and np.all(rc == 1) and np.array_equal(ts.stats, st) and np.array_equal(ts.u_array, ref)
+    assert not np.array_equal(ts.stats, full.stats)                       # the stops change the step sequence
+    cols = B.solve(eprob, B.FBDF(), B.EnsembleB200(), save_idxs=[2, 0], **kw)
+    assert np.array_equal(cols.u_array, full.u_array[:, :, [2, 0]])
+    summ = B.solve(eprob, B.FBDF(), B.EnsembleB200(), summary=True, **kw)
+    assert summ.num_monte == N
+    assert np.max(np.abs(np.asarray(summ.u) - full.u_array.mean(axis=0))) < 1e-12

@@ -54,6 +54,13 @@ def parse():
     return ap.parse_args()
 
 
+def bench_config(a):
+    """The `config` object of the JSON line: names the workload and nothing arm-specific, so that the GPU arm and the
+    `--impl reference` arm print the SAME object (the driver compares them); launch details live under `launch`."""
+    return {"workload": workload_name(a), "trajectories_per_gpu": a.trajectories,
+            "l2": "GPU arm: flushed between timed steps (256 MiB memset); CPU arm: not applicable"}
+
+
 def workload_name(a):
     return (f"lorenz_tsit5_adaptive_{a.dtype}_{a.trajectories}traj_per_gpu_{a.sweep}_sweep_saveat0:1:10"
             f"_abstol1e-6_reltol1e-3")
@@ -227,7 +234,7 @@ def run_reference(a, rank, world):
         "impl": "reference", "metric": "trajectories/sec (Lorenz Tsit5, 1M traj)", "value": v, "unit": "trajectories/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-        "config": {"workload": workload_name(a), "note": "restated CPU baseline (oracle port of the EnsembleThreads path), not Julia"},
+        "config": bench_config(a), "note": "restated CPU baseline (oracle port of the EnsembleThreads path), not Julia",
         "cpu_baseline": {"value": v, "unit": "trajectories/s", "cores": base["cores"], "kind": "port", "sample": base["sample"]},
         "e2e": {"value": v, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -572,8 +579,8 @@ def main():
             "metric": "trajectories/sec (Lorenz Tsit5, 1M traj)", "value": value, "unit": "trajectories/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(a), "trajectories_per_gpu": N, "l2": "flushed between timed steps (256 MiB memset)",
-                       "parallelism": f"trajectory ranges sharded over {world} GPU(s), no collective",
+            "config": bench_config(a),
+            "launch": {"parallelism": f"trajectory ranges sharded over {world} GPU(s), no collective",
                        "refill_threshold": a.refill, "stage_outputs": a.stage, "work_order": a.work_order,
                        "kernels_per_step": launches_per_step, "all_success": ok, "same_kernel_at_10M_trajectories": big, "numa": numa,
                        "regs": model.info()["regs"]},

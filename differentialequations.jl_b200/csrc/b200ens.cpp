@@ -125,6 +125,7 @@ struct b200ens_model {
     int ksmem = 0;          // 1: ERK stage vectors in shared memory
     int split = 0;          // 1: one trajectory per lane of a 4-warp CTA, components split over the warps (b2_split.cuh)
     int kvec_bytes = 0;     // shared-memory bytes per thread for them
+    int has_mass = 0;       // the RHS source carries a constant mass matrix (B2_HAS_MASS)
     std::mutex mu;
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
@@ -705,7 +706,8 @@ int fill_args(const b200ens_model* m, const b200ens_opts* o, B2Args* a) {
     a->event_terminate = o->event_terminate;
     a->interp_points = o->interp_points > 0 ? o->interp_points : 10;
     int st = o->save_tstops;
-    if (st < 0) st = (m->alg == B200ENS_RODAS4 || m->alg == B200ENS_RODAS5 || m->alg == B200ENS_RODAS5P) ? 1 : 0;
+    // auto: interpolate (every stepper has a dense output); mass-matrix problems (index-1 DAEs, Rodas family) save at tstops
+    if (st < 0) st = m->has_mass ? 1 : 0;
     a->save_tstops = st;
     if (!(o->t1 > o->t0)) return fail(B200ENS_E_INVALID, "tspan must satisfy t1 > t0 (forward integration only)");
     if (!(o->dt > 0) && !(a->adaptive && o->dt == 0))
@@ -1386,6 +1388,7 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     m->n_param = d->n_param;
     m->dtype = d->dtype;
     m->alg = d->alg;
+    m->has_mass = strstr(d->rhs_src, "#define B2_HAS_MASS 1") != nullptr;
     m->flags = d->flags;
     m->has_event = d->condition_src != nullptr;
     m->has_noise = d->noise_src != nullptr;

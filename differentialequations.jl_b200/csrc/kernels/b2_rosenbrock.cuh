@@ -288,6 +288,12 @@ __constant__ real B2_RODAS_C[8][8] = {{0}, {RT(C21)}, {RT(C31), RT(C32)}, {RT(C4
                                       {RT(C81), RT(C82), RT(C83), RT(C84), RT(C85), RT(C86), RT(C87)}};
 __constant__ real B2_RODAS_c[8] = {0, RT(c2), RT(c3), RT(c4), RT(c5), 1, 1, 1};
 __constant__ real B2_RODAS_d[8] = {RT(d1), RT(d2), RT(d3), RT(d4), RT(d5), 0, 0, 0};
+// dense-output weights in the transformed stage variables (order 4, derived: tools/derive_rodas_dense.py)
+#define B2_RODAS_HDEG 4
+__constant__ real B2_RODAS_H[8][4] = {{RT(H11), RT(H12), RT(H13), RT(H14)}, {RT(H21), RT(H22), RT(H23), RT(H24)},
+                                      {RT(H31), RT(H32), RT(H33), RT(H34)}, {RT(H41), RT(H42), RT(H43), RT(H44)},
+                                      {RT(H51), RT(H52), RT(H53), RT(H54)}, {RT(H61), RT(H62), RT(H63), RT(H64)},
+                                      {RT(H71), RT(H72), RT(H73), RT(H74)}, {RT(H81), RT(H82), RT(H83), RT(H84)}};
 #else
 __constant__ real B2_RODAS_A[6][6] = {{0}, {RT(a21)}, {RT(a31), RT(a32)}, {RT(a41), RT(a42), RT(a43)},
                                       {RT(a51), RT(a52), RT(a53), RT(a54)}, {0}};
@@ -296,6 +302,9 @@ __constant__ real B2_RODAS_C[6][6] = {{0}, {RT(C21)}, {RT(C31), RT(C32)}, {RT(C4
                                       {RT(C61), RT(C62), RT(C63), RT(C64), RT(C65)}};
 __constant__ real B2_RODAS_c[6] = {0, RT(c2), RT(c3), RT(c4), 1, 1};
 __constant__ real B2_RODAS_d[6] = {RT(d1), RT(d2), RT(d3), RT(d4), 0, 0};
+#define B2_RODAS_HDEG 3   // Rodas4: order-3 dense output
+__constant__ real B2_RODAS_H[6][4] = {{RT(H11), RT(H12), RT(H13), 0}, {RT(H21), RT(H22), RT(H23), 0}, {RT(H31), RT(H32), RT(H33), 0},
+                                      {RT(H41), RT(H42), RT(H43), 0}, {RT(H51), RT(H52), RT(H53), 0}, {RT(H61), RT(H62), RT(H63), 0}};
 #endif
 
 struct B2Rodas {
@@ -304,6 +313,7 @@ struct B2Rodas {
     static constexpr int DEG = 0;  // no coefficient form: the event search uses interp() directly
     __device__ __forceinline__ void poly_coeffs(int, real (&)[1]) const {}
     real f0[B2_N], fnew[B2_N];
+    real k[B2_RODAS_S][B2_N];   // stage increments of the last step: the dense output is a weighted sum of them
 
     __device__ __forceinline__ void start(const real (&u)[B2_N], const real (&p)[B2_NPA], real t) {
         b2_rhs(f0, u, p, t);
@@ -313,7 +323,6 @@ struct B2Rodas {
                                          real (&u)[B2_N], real (&ut)[B2_N], bool, int& nf) {
         B2LU lu;
         real J[B2_N * B2_N], U[B2_N], rhs[B2_N], fU[B2_N];
-        real k[B2_RODAS_S][B2_N];
         const real dtgi = (real)1 / (dt * RT(gamma));
         const real dtinv = (real)1 / dt;
         b2_jac(J, up, p, t);
@@ -409,20 +418,26 @@ struct B2Rodas {
         nf += 1;
     }
     __device__ __forceinline__ void prepare_dense(const real (&)[B2_N], const real (&)[B2_NPA], real, real, int&) {}
-    // cubic Hermite on (up, f0), (un, fnew) -- documented deviation: upstream's own Rodas
-    // interpolant was not recoverable; by default saveat points are tstops instead.
-    __device__ __forceinline__ void interp(const real (&up)[B2_N], const real (&un)[B2_N], real th, real dt,
+    // Dense output in the transformed stage variables: out = up + sum_i w_i k_i, w_i = theta * Horner(theta; h_i1..h_iD).
+    // Order 4 (Rodas5 / Rodas5P) / 3 (Rodas4), derived from the Rosenbrock order conditions (tools/derive_rodas_dense.py);
+    // documented deviation: upstream's own coefficients were not recoverable.  On Robertson it is as accurate
+    // as saving at tstops and an order of magnitude better than the cubic Hermite it replaced (profiles/README.md).
+    __device__ __forceinline__ void interp(const real (&up)[B2_N], const real (&)[B2_N], real th, real,
                                            real (&out)[B2_N]) const {
-        const real om = (real)1 - th;
+        real w[B2_RODAS_S];
+#pragma unroll
+        for (int st = 0; st < B2_RODAS_S; st++) {
+            real pv = B2_RODAS_H[st][B2_RODAS_HDEG - 1];
+#pragma unroll
+            for (int q = B2_RODAS_HDEG - 2; q >= 0; q--) pv = b2_fma(th, pv, B2_RODAS_H[st][q]);
+            w[st] = th * pv;
+        }
 #pragma unroll
         for (int i = 0; i < B2_N; i++) {
-            const real du = un[i] - up[i];
-            real inner = ((real)1 - (real)2 * th) * du;
-            inner = b2_fma((th - (real)1) * dt, f0[i], inner);
-            inner = b2_fma(th * dt, fnew[i], inner);
-            real v = om * up[i];
-            v = b2_fma(th, un[i], v);
-            out[i] = b2_fma(th * (th - (real)1), inner, v);
+            real v = up[i];
+#pragma unroll
+            for (int st = 0; st < B2_RODAS_S; st++) v = b2_fma(w[st], k[st][i], v);
+            out[i] = v;
         }
     }
     __device__ __forceinline__ void advance() {

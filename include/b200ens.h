@@ -130,7 +130,8 @@ typedef struct b200ens_opts {
     int32_t event_terminate;/* bit 0: the ContinuousCallback's affect! terminates the trajectory (terminate!); bit 1: the DiscreteCallback
                                does; bit 2: the ContinuousCallback's affect_neg! does (read only when affect_src defines b2_affect_neg) */
     int32_t interp_points;  /* ContinuousCallback interp_points, <=0: 10 */
-    int32_t save_tstops;    /* -1 auto (on for Rodas*), 0 interpolate, 1 saveat points are tstops */
+    int32_t save_tstops;    /* -1 auto (interpolate; on for mass-matrix problems), 0 interpolate through the stepper's dense output,
+                               1 saveat points are tstops (steps are clipped to them) */
     uint32_t device_mask;   /* bit g set: use CUDA device g; 0: all visible devices */
     int32_t refill_threshold; /* lanes of a warp that must be idle before it fetches new trajectories; <=0 auto */
     int32_t block_threads;  /* <=0 auto */

@@ -105,3 +105,33 @@ def test_generated_headers_match_json():
         for name, tab in T.items():
             for k, v in tab.items():
                 assert f"#define B2T_{name.upper()}_{k} " in txt
+
+
+def test_rodas_dense_weights_are_reproducible_and_consistent():
+    """tools/rodas_dense.json (the dense-output weights of Rodas4 / Rodas5 / Rodas5P in the kernels' stage variables) is what
+    tools/derive_rodas_dense.py derives from tools/tableaus.json, the generated headers carry the same numbers, and
+    m_i(1) reproduces the step itself: y(t + h) = U_s + k_s, i.e. weights (a_s1, .., a_s,s-1, 1)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    stored = json.load(open(os.path.join(root, "tools", "rodas_dense.json")))
+    tabs = json.load(open(os.path.join(root, "tools", "tableaus.json")))
+    hdr = open(os.path.join(root, "oracle", "tableaus_gen.h")).read()
+    for name in ("rodas4", "rodas5", "rodas5p"):
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "derive_rodas_dense.py"), name], capture_output=True, text=True)
+        fresh = json.loads(out.stdout)
+        assert "max residual" in out.stderr and float(out.stderr.split("max residual")[1].split()[0]) < 1e-12
+        m = [[float(v) for v in row] for row in stored[name]["m"]]
+        for i, row in enumerate(m):
+            for p_, v in enumerate(row):
+                assert abs(v - fresh["m"][i][p_]) < 1e-11 * max(1.0, abs(v))
+                assert f"#define B2T_{name.upper()}_H{i + 1}{p_ + 1} " in hdr
+        s = stored[name]["stages"]
+        last = [float(tabs[name][f"a{s - (2 if s == 8 else 1)}{j + 1}"]) for j in range(s - (3 if s == 8 else 2))]
+        # chained rows: a_s = (a_{nexp}, 1, .., 1)
+        want = last + [1.0] * (s - len(last))
+        got = [sum(row) for row in m]
+        assert max(abs(a - b) for a, b in zip(got, want)) < 1e-12, (got, want)

@@ -378,7 +378,7 @@ class ODESolution:
     def __call__(self, t):
         """sol(t): the continuous (dense-output) solution, as solve(...; dense=true) gives upstream
         (test/core.jl:51-58).  Evaluated by the SAME interpolant the saveat path uses (Tsit5: free 4th-order, Vern7:
-        order 6, Rosenbrock23: its own, Rodas: cubic Hermite): saveat points do not influence the step sequence, so
+        order 6, Rosenbrock23: its own, Rodas: derived order 3-4 dense output, FBDF: cubic Hermite): saveat points do not influence the step sequence, so
         re-running this one trajectory on the device with saveat = t returns exactly the value the dense output of the
         original run has at t -- no per-step storage of stage vectors."""
         if self._dense is None:

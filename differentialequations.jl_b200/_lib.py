@@ -118,7 +118,7 @@ def lib():
     L.b200ens_host_alloc.restype = C.c_void_p
     L.b200ens_host_free.argtypes = [C.c_void_p]
     L.b200ens_host_free.restype = None
-    if L.b200ens_abi_version() != 6:
+    if L.b200ens_abi_version() != 7:
         raise ImportError("libb200ens ABI version mismatch")
     _lib = L
     return L

@@ -18,7 +18,7 @@ using SciMLBase, Symbolics
 import SciMLBase: __solve, AbstractEnsembleProblem, EnsembleAlgorithm, EnsembleSolution, ReturnCode
 
 const LIB = get(ENV, "B200ENS_LIB", "libb200ens.so")
-const ABI_VERSION = 6
+const ABI_VERSION = 7
 
 struct EnsembleB200 <: EnsembleAlgorithm
     devices::Vector{Int}          # empty = all visible GPUs

@@ -24,7 +24,9 @@
 extern "C" {
 #endif
 
-#define B200ENS_ABI_VERSION 6
+/* 7: alg B200ENS_FBDF; ContinuousCallback directions through B2_EVENT_DIR / b2_affect_neg and event_terminate bit 2;
+ *    save_tstops = -1 (auto) now interpolates for the Rodas family too (derived dense output), tstops only with a mass matrix */
+#define B200ENS_ABI_VERSION 7
 
 /* scalar type of u, p, t (Julia eltype(u0)) */
 enum b200ens_dtype { B200ENS_F32 = 0, B200ENS_F64 = 1 };

@@ -19,7 +19,7 @@ def test_exports_every_declared_symbol(B):
     nm = subprocess.check_output(["nm", "-D", "--defined-only", B._lib.LIB_PATH], text=True)
     for sym in declared:
         assert hasattr(L, sym) and re.search(rf"\bT {sym}\b", nm), sym
-    assert L.b200ens_abi_version() == 6
+    assert L.b200ens_abi_version() == 7
 
 
 def test_struct_layouts_match_header(B, tmp_path):

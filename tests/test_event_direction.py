@@ -169,3 +169,18 @@ def test_gpu_split_kernel_event_direction(B, gpu_lib, oracle, case):
     assert np.array_equal(sol.retcodes, rc) and np.array_equal(sol.stats, st) and np.array_equal(sol.u_array, ref)
     assert np.array_equal(one.u_array, sol.u_array) and np.array_equal(one.stats, sol.stats)
     assert st[:, 3].max() >= 1
+
+
+def test_callbackset_of_one_sided_callbacks_lowers_to_one_vector_callback(B):
+    """Two upcrossing-only ContinuousCallbacks in a CallbackSet: one vector callback with the common direction."""
+    from b200ens import codegen
+
+    cs = B.CallbackSet(B.ContinuousCallback(_cond, _up, None),
+                       B.ContinuousCallback(lambda u, t, integrator: u[1] - 0.25, _down, None))
+    vcb = cs.continuous[0]
+    assert isinstance(vcb, B.VectorContinuousCallback) and vcb.len == 2 and vcb.direction == 1
+    c, a, _ = codegen.emit_vector_callback(vcb, 3, 2)
+    assert "#define B2_EVENT_DIR 1" in c and "#define B2_NCOND 2" in c and "case 1:" in a and "10" in a
+    dn = B.CallbackSet(B.ContinuousCallback(_cond, None, _up), B.ContinuousCallback(lambda u, t, integrator: u[1], None, _down))
+    c, a, _ = codegen.emit_vector_callback(dn.continuous[0], 3, 2)
+    assert "#define B2_EVENT_DIR -1" in c and "case 0:" in a

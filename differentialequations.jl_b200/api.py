@@ -511,8 +511,8 @@ def build_model(prob, alg, callback=None, fast_math=False, ksmem=False, split=No
     exprs, usyms, _, tsym = codegen.trace_vector_fn(prob.f, n, m)
     srcs = {"rhs_src": codegen.emit_rhs(exprs)}
     if mm is not None:
-        if alg.name not in ("Rodas4", "Rodas5", "Rodas5P"):
-            raise NotImplementedError(f"mass_matrix is supported by Rodas4 / Rodas5 / Rodas5P, not by {alg.name}")
+        if alg.name not in ("Rodas4", "Rodas5", "Rodas5P", "FBDF"):
+            raise NotImplementedError(f"mass_matrix is supported by Rodas4 / Rodas5 / Rodas5P / FBDF, not by {alg.name}")
         if callback is not None:
             raise NotImplementedError("callbacks on mass-matrix problems (their interpolant needs u', which M u' = f does "
                                       "not give for algebraic components)")

@@ -147,7 +147,12 @@ struct B2Fbdf {
 #pragma unroll
             for (int i = 0; i < B2_N; i++)
 #pragma unroll
+#if B2_HAS_MASS
+                // constant mass matrix (M u' = f, possibly singular: index-1 DAE): M (z + tmp) = beta dt f(z), W = M - beta dt J
+                for (int j = 0; j < B2_N; j++) lu.A[i][j] = b2_fma(-bdt, J[i * B2_N + j], (real)B2_MASS_[i * B2_N + j]);
+#else
                 for (int j = 0; j < B2_N; j++) lu.A[i][j] = b2_fma(-bdt, J[i * B2_N + j], (i == j) ? (real)1 : (real)0);
+#endif
         }
         lu.factor();
         const float inv_n = __fdiv_rn(1.0f, (float)B2_N), kappa = 0.01f;
@@ -158,8 +163,29 @@ struct B2Fbdf {
             real fz[B2_N], dz[B2_N];
             b2_rhs(fz, z, p, tdt);
             nf++;
+#if B2_HAS_MASS
+            {
+                real v[B2_N];
+#pragma unroll
+                for (int i = 0; i < B2_N; i++) v[i] = z[i] + tmp[i];
+#pragma unroll
+                for (int i = 0; i < B2_N; i++) {   // (M v)_i over the non-zero entries of row i in index order
+                    real acc = 0;
+                    bool first = true;
+#pragma unroll
+                    for (int j = 0; j < B2_N; j++) {
+                        if (B2_MASS_[i * B2_N + j] != 0.0) {
+                            acc = first ? (real)B2_MASS_[i * B2_N + j] * v[j] : b2_fma((real)B2_MASS_[i * B2_N + j], v[j], acc);
+                            first = false;
+                        }
+                    }
+                    dz[i] = b2_fma(bdt, fz[i], -acc);
+                }
+            }
+#else
 #pragma unroll
             for (int i = 0; i < B2_N; i++) dz[i] = b2_fma(bdt, fz[i], -(z[i] + tmp[i]));
+#endif
             lu.solve(dz);
             float acc = 0.0f;
 #pragma unroll

@@ -206,7 +206,7 @@ function model_sources(prob, alg)
     rhs = vector_fn("b2_rhs", "du", du)
     M = prob.f.mass_matrix                              # ODEFunction(f; mass_matrix = M): constant table in the RHS source
     if !(M isa SciMLBase.LinearAlgebra.UniformScaling)
-        nameof(typeof(alg)) in (:Rodas4, :Rodas5, :Rodas5P) || error("EnsembleB200: mass_matrix needs Rodas4 / Rodas5 / Rodas5P")
+        nameof(typeof(alg)) in (:Rodas4, :Rodas5, :Rodas5P, :FBDF) || error("EnsembleB200: mass_matrix needs Rodas4 / Rodas5 / Rodas5P / FBDF")
         rhs = "#undef B2_HAS_MASS\n#define B2_HAS_MASS 1\nstatic constexpr double B2_MASS_[$(n * n)] = {" *
               join(string.(Float64.(vec(permutedims(Matrix(M))))), ", ") * "};\n" * rhs
     end

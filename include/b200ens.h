@@ -39,7 +39,7 @@ enum b200ens_alg {
     B200ENS_RODAS5P = 5, B200ENS_EM = 6, B200ENS_SOSRA = 7, B200ENS_RODAS4 = 8,
     B200ENS_SRIW1 = 9,  /* Roessler SRI W1: strong order 1.5 for diagonal noise (fixed dt; dW and dZ per step) */
     B200ENS_FBDF = 10   /* FBDF (qa.jl:57): variable-order (1..5) fixed-leading-coefficient BDF, Newton corrector with the analytic
-                           Jacobian (jac_src required), Hermite dense output; a callback that fires restarts the history at order 1; no mass matrix */
+                           Jacobian (jac_src required), Hermite dense output; a callback that fires restarts the history at order 1; constant mass matrix as for the Rodas family */
 };
 
 /* per-trajectory return codes <- SciMLBase.ReturnCode (qa.jl:213); the Julia glue maps by name */
@@ -85,7 +85,7 @@ enum b200ens_error {
  *   VectorContinuousCallback (qa.jl:124): condition_src carries `#define B2_NCOND <len>` and defines
  *   __device__ void b2_vcondition(real* g, const real* u, const real* p, real t);   affect_src defines
  *   __device__ void b2_vaffect  (real* u,  const real* p, real t, int idx);         idx = 0-based event index
- *   constant mass matrix (M u' = f, Rodas4/5/5P): rhs_src carries `#define B2_HAS_MASS 1` and
+ *   constant mass matrix (M u' = f, Rodas4/5/5P and FBDF): rhs_src carries `#define B2_HAS_MASS 1` and
  *   `static constexpr double B2_MASS_[n*n]` (row-major)
  *   __device__ bool b2_dcondition(const real* u, const real* p, real t);            DiscreteCallback (qa.jl:36,
  *   __device__ void b2_daffect  (real* u,  const real* p, real t);                   test/core.jl:76-77)

@@ -265,3 +265,44 @@ def test_gpu_fbdf_with_solve_options(B, gpu_lib, oracle):
     summ = B.solve(eprob, B.FBDF(), B.EnsembleB200(), summary=True, **kw)
     assert summ.num_monte == N
     assert np.max(np.abs(np.asarray(summ.u) - full.u_array.mean(axis=0))) < 1e-12
+
+
+def rober_dae(du, u, p, t):
+    # Robertson as an index-1 DAE: M = diag(1, 1, 0), third equation = the conservation law
+    du[0] = -p[0] * u[0] + p[2] * u[1] * u[2]
+    du[1] = p[0] * u[0] - p[1] * u[1] ** 2 - p[2] * u[1] * u[2]
+    du[2] = u[0] + u[1] + u[2] - 1.0
+
+
+def test_fbdf_mass_matrix_dae_against_radau(oracle, B):
+    """FBDF on M u' = f with a singular constant mass matrix: M (z + tmp) = beta dt f(z), W = M - beta dt J.  The DAE form of
+    Robertson gives the accuracy of the ODE form and keeps the algebraic equation to rounding."""
+    g = _load("robertson.json")
+    prob = B.ODEProblem(rober_dae, np.array(g["u0"]), (0.0, 1e5), np.array(g["p"]), mass_matrix=np.diag([1.0, 1.0, 0.0]))
+    model = B.build_model(prob, B.FBDF())
+    fns = oracle_fns(oracle, B, model)
+    ref = np.array(g["u"])
+    for tol in (1e-4, 1e-6, 1e-8):
+        out, rc, st = oracle.solve(None, "FBDF", [g["u0"]], [g["p"]], (0.0, 1e5), g["t"], 1e-6, abstol=tol * 1e-2, reltol=tol, fns=fns,
+                                   mass_matrix=np.diag([1.0, 1.0, 0.0]))
+        assert rc[0] == 1
+        assert np.max(np.abs(out[0] - ref) / (tol * 1e-2 + tol * np.abs(ref))) < 10.0
+        assert np.abs(out[0].sum(axis=1) - 1.0).max() < 1e-14
+
+
+@pytest.mark.gpu
+def test_gpu_fbdf_mass_matrix_dae_bit_identical(B, gpu_lib, oracle):
+    from b200ens import workloads as W
+
+    N = 1024
+    u0, p = W.robertson_params(N)
+    M = np.diag([1.0, 1.0, 0.0])
+    prob = B.ODEProblem(rober_dae, u0[0], (0.0, 1e5), p[0], mass_matrix=M)
+    sol = B.solve(B.EnsembleProblem(prob, u0s=u0, ps=p), B.FBDF(), B.EnsembleB200(), trajectories=N, saveat=W.ROBERTSON_SAVEAT, dt=1e-6,
+                  abstol=1e-8, reltol=1e-6)
+    model = B.build_model(prob, B.FBDF())
+    ref, rc, st = oracle.solve(None, "FBDF", u0, p, (0.0, 1e5), W.ROBERTSON_SAVEAT, 1e-6, abstol=1e-8, reltol=1e-6, mass_matrix=M,
+                               fns=oracle_fns(oracle, B, model))
+    assert np.array_equal(sol.retcodes, rc) and np.all(rc == 1)
+    assert np.array_equal(sol.stats, st) and np.array_equal(sol.u_array, ref)
+    assert np.abs(sol.u_array.sum(axis=2) - 1.0).max() < 1e-13

@@ -677,8 +677,10 @@ def _solve_once(prob, alg, ensemblealg=None, trajectories=None, saveat=None, dt=
         raise NotImplementedError("save_everystep with SDE steppers / summary: pass the time grid as saveat instead")
     if dense and save_tstops:
         raise ValueError("dense=True needs interpolated saves (save_tstops=False): tstops would change the step sequence")
-    if getattr(prob.prob if isinstance(prob, EnsembleProblem) else prob, "mass_matrix", None) is not None and (dense or save_tstops is False or save_tstops == 0 and save_tstops is not None):
-        raise NotImplementedError("mass-matrix problems save at tstops only (no dense output / interpolated saveat)")
+    if (alg.name == "FBDF" and getattr(prob.prob if isinstance(prob, EnsembleProblem) else prob, "mass_matrix", None) is not None
+            and (dense or save_tstops is False or save_tstops == 0 and save_tstops is not None)):
+        raise NotImplementedError("FBDF on a mass-matrix problem saves at tstops only (its Hermite dense output takes f for u'); "
+                                  "the Rodas family interpolates DAEs through its own dense output")
     if dense and dW is not None:
         raise NotImplementedError("dense=True with injected noise increments")
     single = not isinstance(prob, EnsembleProblem)

@@ -706,8 +706,10 @@ int fill_args(const b200ens_model* m, const b200ens_opts* o, B2Args* a) {
     a->event_terminate = o->event_terminate;
     a->interp_points = o->interp_points > 0 ? o->interp_points : 10;
     int st = o->save_tstops;
-    // auto: interpolate (every stepper has a dense output); mass-matrix problems (index-1 DAEs, Rodas family) save at tstops
-    if (st < 0) st = m->has_mass ? 1 : 0;
+    // auto: interpolate (every stepper has a dense output).  FBDF on a mass-matrix problem saves at tstops: its Hermite dense
+    // output takes f for u', which M u' = f does not give for algebraic components (the Rodas dense output works on the stage
+    // increments and is used for DAEs too)
+    if (st < 0) st = (m->has_mass && m->alg == B200ENS_FBDF) ? 1 : 0;
     a->save_tstops = st;
     if (!(o->t1 > o->t0)) return fail(B200ENS_E_INVALID, "tspan must satisfy t1 > t0 (forward integration only)");
     if (!(o->dt > 0) && !(a->adaptive && o->dt == 0))

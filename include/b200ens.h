@@ -25,7 +25,7 @@ extern "C" {
 #endif
 
 /* 7: alg B200ENS_FBDF; ContinuousCallback directions through B2_EVENT_DIR / b2_affect_neg and event_terminate bit 2;
- *    save_tstops = -1 (auto) now interpolates for the Rodas family too (derived dense output), tstops only with a mass matrix */
+ *    save_tstops = -1 (auto) now interpolates for the Rodas family too (derived dense output, DAEs included) */
 #define B200ENS_ABI_VERSION 7
 
 /* scalar type of u, p, t (Julia eltype(u0)) */
@@ -132,7 +132,7 @@ typedef struct b200ens_opts {
     int32_t event_terminate;/* bit 0: the ContinuousCallback's affect! terminates the trajectory (terminate!); bit 1: the DiscreteCallback
                                does; bit 2: the ContinuousCallback's affect_neg! does (read only when affect_src defines b2_affect_neg) */
     int32_t interp_points;  /* ContinuousCallback interp_points, <=0: 10 */
-    int32_t save_tstops;    /* -1 auto (interpolate; on for mass-matrix problems), 0 interpolate through the stepper's dense output,
+    int32_t save_tstops;    /* -1 auto (interpolate; tstops for FBDF on a mass-matrix problem), 0 interpolate through the stepper's dense output,
                                1 saveat points are tstops (steps are clipped to them) */
     uint32_t device_mask;   /* bit g set: use CUDA device g; 0: all visible devices */
     int32_t refill_threshold; /* lanes of a warp that must be idle before it fetches new trajectories; <=0 auto */

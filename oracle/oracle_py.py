@@ -150,8 +150,8 @@ def solve(model, alg, u0, p, tspan, saveat, dt, abstol=1e-6, reltol=1e-3, adapti
     o.traj_offset = traj_offset
     o.has_event, o.event_terminate, o.interp_points = int(event), int(bool(terminate)) | (4 if terminate_neg else 0), interp_points
     o.event_dir = int(event_dir)   # 0 both directions, +1 upcrossings only, -1 downcrossings only
-    if save_tstops is None:   # mass-matrix problems (index-1 DAEs) save at tstops; everything else interpolates
-        save_tstops = mass_matrix is not None and alg in ("Rodas4", "Rodas5", "Rodas5P", "FBDF")
+    if save_tstops is None:   # everything interpolates, except FBDF on a mass-matrix problem (its Hermite output needs u')
+        save_tstops = mass_matrix is not None and alg == "FBDF"
     o.save_tstops = int(save_tstops)
     o.sde_adaptive = int(bool(sde_adaptive))
     if tstops is not None and len(tstops):

@@ -234,15 +234,23 @@ def test_mass_matrix_dae_rodas(B, gpu_lib, oracle):
         dae = B.solve(eprob, A, B.EnsembleB200(), trajectories=N, saveat=W.ROBERTSON_SAVEAT, dt=1e-6, abstol=1e-10, reltol=1e-8)
         assert np.all(dae.retcodes == 1)
         assert np.max(np.abs(dae.u_array.sum(axis=2) - 1.0)) < 1e-13          # the algebraic constraint holds exactly
-        assert np.max(np.abs(dae.u_array - ode.u_array) / (1e-9 + np.abs(ode.u_array))) < 1e-4
+        # DAE and ODE form take different steps and interpolate: they agree at the solver tolerance
+        assert np.max(np.abs(dae.u_array - ode.u_array) / (1e-10 + 1e-8 * np.abs(ode.u_array))) < 10.0
         ref, rc, st = oracle.solve(None, alg, u0, p, (0.0, 1e5), W.ROBERTSON_SAVEAT, 1e-6, abstol=1e-10, reltol=1e-8,
                                    fns=oracle_fns(oracle, B, B.build_model(prob, A)), mass_matrix=M)
         assert np.array_equal(dae.retcodes, rc) and np.array_equal(dae.stats[:, :3], st[:, :3])
         assert np.allclose(dae.u_array, ref, rtol=1e-12, atol=1e-300)
     with pytest.raises(NotImplementedError):
         B.solve(prob, B.Tsit5())
+    # dense output on a DAE: the Rodas dense output works on the stage increments (no u' needed); sol(t) keeps the
+    # linear algebraic equation and agrees with saving at t in the first place
+    dsol = B.solve(prob, B.Rodas5P(), reltol=1e-8, abstol=1e-8, dense=True)
+    v = dsol(np.array([0.5, 40.0, 7e3]))
+    assert np.max(np.abs(np.sum(v, axis=-1) - 1.0)) < 1e-13
+    direct = B.solve(prob, B.Rodas5P(), reltol=1e-8, abstol=1e-8, saveat=[0.5, 40.0, 7e3])
+    assert np.array_equal(np.asarray(v), np.asarray(direct.u))
     with pytest.raises(NotImplementedError):
-        B.solve(prob, B.Rodas5P(), dense=True)
+        B.solve(prob, B.FBDF(), dense=True)                # FBDF's Hermite output takes f for u'
 
 
 def test_save_everystep_default_for_single_solves(B, gpu_lib, oracle):

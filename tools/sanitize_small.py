@@ -92,3 +92,15 @@ for split in (True, False):
     s = B.solve(B.EnsembleProblem(W.net16_problem(), u0s=u0n, ps=pn), B.Vern7(), B.EnsembleB200(split=split), trajectories=200,
                 saveat=np.linspace(0, 10, 11), dt=0.01, abstol=1e-6, reltol=1e-6, callback=cb2)
     print("affect_neg split" if split else "affect_neg one-thread", (s.retcodes == 1).all(), s.stats[:, 3].mean())
+# end of session 3: Rodas dense output (interpolated saves, DAE), FBDF with a mass matrix, rolled LU (n = 16)
+def _rd2(du, u, p, t):
+    du[0] = -p[0] * u[0] + p[2] * u[1] * u[2]; du[1] = p[0] * u[0] - p[1] * u[1] ** 2 - p[2] * u[1] * u[2]; du[2] = u[0] + u[1] + u[2] - 1.0
+pdae = B.ODEProblem(_rd2, [1.0, 0.0, 0.0], (0.0, 1e3), (0.04, 3e7, 1e4), mass_matrix=np.diag([1.0, 1.0, 0.0]))
+for alg in (B.Rodas5P(), B.Rodas4(), B.FBDF()):
+    s = B.solve(B.EnsembleProblem(pdae, u0s=u0r[:300], ps=pr[:300]), alg, B.EnsembleB200(), trajectories=300, saveat=[1e-3, 1.0, 40.0, 1e3],
+                dt=1e-6, abstol=1e-8, reltol=1e-6)
+    print("dae", alg.name, (s.retcodes == 1).all(), float(np.abs(s.u_array.sum(axis=2) - 1).max()))
+for alg in (B.Rodas5P(), B.FBDF()):
+    s = B.solve(B.EnsembleProblem(W.net16_problem(), u0s=u0n[:64], ps=pn[:64]), alg, B.EnsembleB200(), trajectories=64,
+                saveat=np.linspace(0, 10, 5), dt=0.01, abstol=1e-6, reltol=1e-6)
+    print("rolled LU n=16", alg.name, (s.retcodes == 1).all())

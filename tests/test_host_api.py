@@ -351,7 +351,7 @@ def test_on_disk_cubin_cache(B, tmp_path):
     t1, r1 = first.stdout.split()[:2]
     t2, r2 = second.stdout.split()[:2]
     assert r1 == r2 and sorted(os.listdir(tmp_path / "cc")) == files       # nothing new was compiled
-    assert float(t2) < 0.5, (t1, t2)                                      # loaded, not compiled
+    assert float(t2) < max(1.0, 0.5 * float(t1)), (t1, t2)                # loaded, not compiled (a Vern7 JIT is 2-3 s)
     off = subprocess.run([sys.executable, "-c", code], env=dict(env, B200ENS_CACHE="0", B200ENS_CACHE_DIR=str(tmp_path / "none")),
                          capture_output=True, text=True)
     assert off.returncode == 0 and not os.path.exists(tmp_path / "none")

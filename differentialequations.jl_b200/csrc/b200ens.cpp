@@ -661,7 +661,7 @@ int plan_launch(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, long long
     if (o->stage_outputs > 0 && !staged && !m->split)
         return fail(B200ENS_E_UNSUPPORTED, "stage_outputs=1 but %zu bytes of shared memory per block do not fit", smem);
     int nb = staged ? nb_staged : nb_direct;
-    // stiff steppers beyond 8 states run their LU with rolled loops on a local-memory matrix (b2_rosenbrock.cuh,
+    // stiff steppers beyond 8 states keep W in local memory (beyond 10: rolled LU loops) on a local-memory matrix (b2_rosenbrock.cuh,
     // B2_LU_ROLLED): ~3.5 KB of local memory per thread.  One CTA (of 64 threads, b200ens_compile) per SM keeps it inside the
     // L1; more resident threads spill it to the L2 and are slower (profiles/README.md)
     const int nb_occ = nb;

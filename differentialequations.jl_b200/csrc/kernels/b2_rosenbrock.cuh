@@ -7,12 +7,12 @@
 #include "b2_common.cuh"
 #include "tableaus_gen.cuh"
 
-// Small systems (n <= 8): fully unrolled, A / dinv / piv are registers.  Larger systems: the O(n^3) unrolled code is megabytes of
+// Small systems (n <= 10): fully unrolled, A / dinv / piv are registers (spilling to constant-offset local memory beyond n ~ 6).  Larger systems: the O(n^3) unrolled code is megabytes of
 // SASS (n = 16: a 4 MB cubin, minutes of JIT, instruction-cache bound) -- the loops stay rolled, the matrix lives in the
 // thread's local memory (L1 / L2 resident) and factor / solve are out-of-line functions.  Same operations in the same order:
 // bit-identical either way (B2_LU_ROLLED can be forced with B200ENS_DEFINES for the A/B test).
 #ifndef B2_LU_ROLLED
-#define B2_LU_ROLLED (B2_N > 8)
+#define B2_LU_ROLLED (B2_N > 10)   // measured crossover (tools/exp_stiff_mid.py): n = 10 unrolled 22.7 vs rolled 28.1 ms, n = 12: 59.5 vs 51.2 ms
 #endif
 #if B2_LU_ROLLED
 #define B2_LU_UNROLL _Pragma("unroll 1")

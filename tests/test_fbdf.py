@@ -218,7 +218,7 @@ def test_gpu_fbdf_with_callbacks_matches_oracle(B, gpu_lib, oracle):
 @pytest.mark.gpu
 @pytest.mark.parametrize("alg", ["Rodas5P", "FBDF"])
 def test_gpu_stiff_steppers_on_the_16_species_network(B, gpu_lib, oracle, alg):
-    """n = 16: beyond 8 states the LU of the stiff steppers runs with rolled loops on a local-memory matrix (b2_rosenbrock.cuh,
+    """n = 16: beyond 10 states the LU of the stiff steppers runs with rolled loops on a local-memory matrix (b2_rosenbrock.cuh,
     B2_LU_ROLLED) instead of fully unrolled register code -- the same operations in the same order, so still bit-identical
     to the oracle."""
     from b200ens import workloads as W

@@ -661,11 +661,14 @@ int plan_launch(b200ens_model* m, const b200ens_opts* o, DeviceCtx* d, long long
     if (o->stage_outputs > 0 && !staged && !m->split)
         return fail(B200ENS_E_UNSUPPORTED, "stage_outputs=1 but %zu bytes of shared memory per block do not fit", smem);
     int nb = staged ? nb_staged : nb_direct;
-    // stiff steppers beyond 8 states keep W in local memory (beyond 10: rolled LU loops) on a local-memory matrix (b2_rosenbrock.cuh,
+    // stiff steppers beyond 10 states run their LU with rolled loops on a local-memory matrix on a local-memory matrix (b2_rosenbrock.cuh,
     // B2_LU_ROLLED): ~3.5 KB of local memory per thread.  One CTA (of 64 threads, b200ens_compile) per SM keeps it inside the
     // L1; more resident threads spill it to the L2 and are slower (profiles/README.md)
     const int nb_occ = nb;
-    if (needs_jac(m->alg) && m->n_state > 8 && m->lmem >= 2048) nb = std::min(nb, 1);
+    // resident threads per SM so that their local memory (~224 KB) stays inside the L1: measured best at n = 12 (2 KB per
+    // thread): 128 threads (38 ms per 100k trajectories; 64: 64 ms, 256: 51 ms), at n = 16 (3.4 KB): 64 threads
+    if (needs_jac(m->alg) && m->n_state > 10 && m->lmem >= 1024)
+        nb = std::min(nb, std::max(1, (int)(229376.0 / ((double)m->lmem * block) + 0.5)));
     if (const char* e = getenv("B200ENS_BLOCKS_PER_SM")) nb = std::max(1, std::min(nb_occ, atoi(e)));  // experiments
     if (nb < 1) return fail(B200ENS_E_CUDA, "kernel cannot be resident (occupancy 0)");
     lp->block = block;
@@ -1440,9 +1443,10 @@ int b200ens_compile(const b200ens_model_desc* d, b200ens_model** out, char* log,
     }
     // B200ENS_BLOCK: threads per CTA of the one-thread kernels (experiments; default 128)
     int blk = kBlock;
-    // stiff steppers beyond 8 states keep W and the stage vectors in ~3.5 KB of local memory per thread: 64 threads per SM
+    // stiff steppers beyond 10 states keep W and the stage vectors in 2-3.5 KB of local memory per thread: 64 threads per SM
     // (one CTA of 64) keep that inside the L1 (Rodas5P, n = 16: 111 ms per 100k trajectories against 144 ms with 128 threads)
-    if (needs_jac(d->alg) && d->n_state > 8) blk = 64;
+    // (the rolled-LU sizes only, n > 10: at n = 10 the unrolled kernel runs 2x faster with the usual 128 threads x 2 CTAs)
+    if (needs_jac(d->alg) && d->n_state > 10) blk = 64;
     if (const char* e = getenv("B200ENS_BLOCK")) blk = std::max(32, std::min(256, atoi(e) / 32 * 32));
     if (try_regs) {
         m->block = blk;
